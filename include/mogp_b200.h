@@ -1,0 +1,185 @@
+/*
+ * mogp_b200.h — C ABI of the B200 (sm_100a) likelihood engine for MoGP.
+ *
+ * The reference (fraenkel-lab/mogp) has no FFI: its hot path is a Python duck-typed
+ * interface, `GPobs` (mogp/obsmodel.py:6-94), called by the collapsed Gibbs sampler
+ * (mogp/mogp_constrained.py:231-284) and by `predict` (:312-347), with all arithmetic
+ * inside GPy.  Each entry point below names the reference call it replaces.  A
+ * maintainer binds these with ctypes; `mogp_b200/_capi.py` is
+ * that binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative MOGP_E* code; the message is
+ *     available from mogp_last_error(); nothing throws across the ABI;
+ *   - all `const double*` / `const int64_t*` arguments are HOST pointers unless the
+ *     name ends in `_dev`; copies to / from the device happen inside the call on the
+ *     engine's stream (so timing a call with host buffers is an end-to-end timing);
+ *   - an engine owns one CUDA stream; calls on one engine are not thread-safe, calls
+ *     on different engines are (one host thread + one engine per Gibbs chain);
+ *   - theta is the natural-parameter vector in GPy's order
+ *         rbf    : [A, rbf.variance, rbf.lengthscale, Gaussian_noise.variance]
+ *         linear : [A, linear.variances, bias.variance, Gaussian_noise.variance]
+ *     (A is present but ignored when mean_func = 0);
+ *   - all arithmetic is FP64.
+ */
+#ifndef MOGP_B200_H
+#define MOGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOGP_OK 0
+#define MOGP_EINVAL (-1)  /* bad argument */
+#define MOGP_ECUDA (-2)   /* CUDA runtime error (no device, launch failure, ...) */
+#define MOGP_ENOMEM (-3)  /* device allocation failed */
+#define MOGP_ENOTPD (-4)  /* covariance not positive definite (GPy raises LinAlgError) */
+#define MOGP_EPROB (-5)   /* probabilities contain NaN (np.random.choice raises ValueError) */
+#define MOGP_ESTATE (-6)  /* call sequence error (e.g. cluster has no data) */
+
+#define MOGP_KERNEL_RBF 0
+#define MOGP_KERNEL_LINEAR 1
+
+typedef struct mogp_engine mogp_engine;
+
+/* Per-cluster model structure = the keyword arguments of GPobs.__init__ (obsmodel.py:7-8). */
+typedef struct mogp_model_spec {
+  int32_t kernel;              /* MOGP_KERNEL_RBF | MOGP_KERNEL_LINEAR   (obsmodel.py:25,35) */
+  int32_t mean_func;           /* NegLinear mean m(x) = -A x on/off      (obsmodel.py:44-49, neg_linear.py:22) */
+  int32_t signal_variance_fix; /* kernel variance excluded from the refit (obsmodel.py:29,38) */
+  int32_t noise_variance_fix;  /* noise variance excluded from the refit  (obsmodel.py:51) */
+} mogp_model_spec;
+
+/* ---- engine lifetime -------------------------------------------------------------- */
+int mogp_engine_create(int32_t device, mogp_engine** out);
+void mogp_engine_destroy(mogp_engine* h);
+const char* mogp_last_error(const mogp_engine* h); /* h may be NULL: error of the failed create */
+int mogp_version(void);
+/* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
+int64_t mogp_launch_count(const mogp_engine* h);
+/* Block until the engine's stream is idle. */
+int mogp_sync(mogp_engine* h);
+/* Device-side time, in ms, spent between the two most recent mogp_timer_start/stop marks
+   (CUDA events recorded on the engine's stream). */
+int mogp_timer_start(mogp_engine* h);
+int mogp_timer_stop(mogp_engine* h, double* ms_out);
+
+/* ---- patients: the NaN-compacted rows of X, Y (mogp_constrained.py:246-247) --------- */
+/* CSR: visits of patient n are x[off[n]..off[n+1]).  y_thr[n] is the RAW cell
+   Y[n, index_to_eval] used by the monotonicity threshold (mogp_constrained.py:256-262);
+   it may be NaN (then the test is false, as in NumPy).  y_thr may be NULL. */
+int mogp_set_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x,
+                      const double* y, const double* y_thr);
+
+/* ---- one cluster's GP = one GPobs object ------------------------------------------------- */
+/* GPobs.__init__ (obsmodel.py:7-61) minus data: allocates a cluster slot. */
+int mogp_cluster_create(mogp_engine* h, const mogp_model_spec* spec, const double theta[4], int32_t* slot_out);
+int mogp_cluster_free(mogp_engine* h, int32_t slot);
+int mogp_cluster_set_theta(mogp_engine* h, int32_t slot, const double theta[4]); /* re-runs inference if data is set */
+int mogp_cluster_get_theta(mogp_engine* h, int32_t slot, double theta[4]);
+/* GPy set_XY (obsmodel.py:73,92) / GPRegression construction (:46): replace the data and run
+   exact inference (fused K build + blocked Cholesky + inverse factor + alpha + log marginal). */
+int mogp_cluster_set_data(mogp_engine* h, int32_t slot, int64_t m, const double* x, const double* y);
+/* Same, data gathered on the device from the patient table (members in the given order). */
+int mogp_cluster_set_members(mogp_engine* h, int32_t slot, int64_t n_members, const int64_t* patient_ids);
+/* Append points at fixed theta (obsmodel.py:89-92 before optimize): rank-n update of the factors. */
+int mogp_cluster_append(mogp_engine* h, int32_t slot, int64_t n, const double* x, const double* y);
+/* Delete rows [p, p+n) of the cluster's data at fixed theta (the inverse of append; replaces the set_XY of
+   update_data, obsmodel.py:68-73): closed-form re-triangularisation of the factor, chunks of <= 16 rows. */
+int mogp_cluster_remove_rows(mogp_engine* h, int32_t slot, int64_t p, int64_t n);
+/* Score of the cluster's own rows [p, p+n) (n <= 16) under the cluster WITHOUT them — what
+   update_data + calc_score / get_pred_at_loc (mogp_constrained.py:239-266) compute — by the leave-block-out
+   identity, leaving the cluster untouched.  *mu_thr = predictive mean at row p + thr_index (NaN if < 0). */
+int mogp_cluster_leave_out_score(mogp_engine* h, int32_t slot, int64_t p, int64_t n, int32_t thr_index,
+                                 double* score, double* mu_thr);
+int64_t mogp_cluster_size(mogp_engine* h, int32_t slot);
+int mogp_cluster_get_data(mogp_engine* h, int32_t slot, double* x, double* y);
+/* model.log_likelihood() (obsmodel.py:56,65): log marginal likelihood, no prior term. */
+int mogp_cluster_loglik(mogp_engine* h, int32_t slot, double* lml);
+/* paramz Model._objective_grads (reached from obsmodel.py:94): f = -(LML + log prior + log Jacobian)
+   and df/dt at optimiser coordinates t (Logexp space, free parameters only, GPy order).
+   Leaves the cluster at theta(t), like paramz does.  *n_free_out = number of free parameters. */
+int mogp_cluster_objective(mogp_engine* h, int32_t slot, const double* t, int32_t n_t, double* f, double* g);
+int mogp_cluster_n_free(mogp_engine* h, int32_t slot);
+/* Current optimiser coordinates t = Logexp^-1(theta) of the free parameters. */
+int mogp_cluster_get_optimizer_array(mogp_engine* h, int32_t slot, double* t, int32_t* n_t);
+/* Gradient of the log marginal w.r.t. natural theta (4 entries, GPy order), for tests. */
+int mogp_cluster_lml_grad(mogp_engine* h, int32_t slot, double grad_theta[4]);
+/* GP._raw_predict + likelihood noise (obsmodel.py:85 -> model.predict without normalizer):
+   mean[i], var[i] (= v* + noise) at xs[i]. */
+int mogp_cluster_predict(mogp_engine* h, int32_t slot, int64_t n, const double* xs, double* mean, double* var);
+/* model.log_predictive_density (obsmodel.py:80): per-visit log densities at (xs, ys). */
+int mogp_cluster_log_predictive_density(mogp_engine* h, int32_t slot, int64_t n, const double* xs,
+                                        const double* ys, double* lpd);
+
+/* ---- batched pair scoring: GPobs.calc_score for patients x clusters (a1 + a2) ------------- */
+/* Query patients given on the host as CSR.  score[p * n_slots + c] = sum over visits of the
+   predictive log density of patient p under cluster slots[c] (obsmodel.py:75-81).
+   mu_thr (optional) receives the predictive mean at visit `thr_index` of each patient
+   (get_pred_at_loc, obsmodel.py:83-85), mu_thr[p * n_slots + c]. */
+int mogp_score_pairs(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x, const double* y,
+                     int32_t n_slots, const int32_t* slots, int32_t thr_index, double* score, double* mu_thr);
+/* Same with every array already resident on the device (bench `value` path). */
+int mogp_score_pairs_dev(mogp_engine* h, int64_t n_patients, int64_t n_visits, const int64_t* off_dev,
+                         const double* x_dev, const double* y_dev, int32_t n_slots, const int32_t* slots,
+                         int32_t thr_index, double* score_dev, double* mu_thr_dev);
+/* New-cluster marginal (GPobs.__init__ on one patient, obsmodel.py:56; mogp_constrained.py:246-250,
+   :330-339): ll[p] = log N(y_p | -A_p x_p, K_theta + (noise + 1e-8) I) with A_p = |a_draw[p]|. */
+int mogp_new_cluster_ll(mogp_engine* h, const mogp_model_spec* spec, const double theta[4], int64_t n_patients,
+                        const int64_t* off, const double* x, const double* y, const double* a_draw, double* ll);
+
+/* ---- collapsed Gibbs sweep (mogp_constrained.py:231-284 + allocmodel.py:22-34) ------------- */
+typedef struct mogp_chain_config {
+  mogp_model_spec spec;
+  double alpha;           /* DP concentration (allocmodel.py:8) */
+  double signal_variance; /* initial theta of a new cluster (obsmodel.py:7-8, 27, 37) */
+  double noise_variance;
+  double lengthscale;     /* 4.0 in the reference */
+  int32_t use_threshold;  /* threshold is not None (mogp_constrained.py:254) */
+  int32_t thr_index;      /* 1 with onset anchor else 0 (mogp_constrained.py:256) */
+  double threshold;
+  /* 0: reference-exact data order — a leaving patient's cluster is re-extracted in patient-index order and
+        refactorised (mogp_constrained.py:239-242), a joining patient's rows go last (obsmodel.py:77-78);
+     1: rank-n up/down-dates at fixed theta + leave-block-out score for the patient's own cluster
+        (same mathematics, rows kept in arrival order; agrees with mode 0 to rounding). */
+  int32_t fast_updates;
+  int32_t reserved;
+} mogp_chain_config;
+
+/* initialize_sampler + calc_suffstats (mogp_constrained.py:187-214,220): z[N] = initial cluster id per patient
+   (ids 0..n_ids-1), theta_of_id[4*k..] = hyper-parameters of cluster k (A = |randn| drawn by the caller in id
+   order).  Builds one cluster slot per non-empty id from the patient table (members in index order). */
+int mogp_chain_init(mogp_engine* h, const mogp_chain_config* cfg, int64_t n_patients, const int32_t* z,
+                    int32_t n_ids, const double* theta_of_id);
+/* One patient step in three phases, so that a caller can teacher-force or refit between them:
+   begin  : take patient n out of its cluster (mogp_constrained.py:232-242, allocmodel.py:24);
+   score  : score[i] = log prior weight + log likelihood of active id ids[i] (last = new cluster), with the
+            monotonicity rule applied (:244-271); a_draw = the randn consumed by the newcomer's NegLinear map;
+   commit : assign to chosen_id (allocmodel.py:29-34; :279-284 WITHOUT the hyper-parameter refit — the caller
+            runs it through mogp_cluster_objective when the schedule asks for one). */
+int mogp_chain_step_begin(mogp_engine* h, int64_t n);
+int mogp_chain_step_score(mogp_engine* h, double a_draw, int32_t* n_active, int32_t* ids_out, double* score_out,
+                          int32_t cap_out);
+int mogp_chain_step_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_new);
+/* begin + score + draw + commit with pre-drawn randomness (u = the uniform consumed by np.random.choice, :277).
+   Outputs (optional): chosen id, p_out[0..*n_active) = probabilities over ids_out. */
+int mogp_chain_step(mogp_engine* h, int64_t n, double a_draw, double u, int32_t* chosen_id, int32_t* is_new,
+                    int32_t* n_active, int32_t* ids_out, double* p_out, int32_t cap_out);
+/* n_steps consecutive steps (one sweep when n_steps = N) without refits: order[], a_draw[], u[] per step.
+   min_margin (optional) = the smallest |u - cdf edge| seen (assignment-parity diagnostic). */
+int mogp_chain_sweep(mogp_engine* h, int64_t n_steps, const int64_t* order, const double* a_draw, const double* u,
+                     int32_t* chosen_ids, double* min_margin);
+int mogp_chain_get_state(mogp_engine* h, int32_t* z /*N*/, int64_t* Nk, int32_t* slot_of_id, int32_t cap_ids,
+                         int32_t* n_ids);
+/* Last step's minimum |u - cdf edge|. */
+double mogp_chain_last_margin(const mogp_engine* h);
+/* The draw alone (host arithmetic, no device): p = exp(score - logsumexp(score)) and NumPy's
+   choice(): cdf = cumsum(p); cdf /= cdf[-1]; index = searchsorted(cdf, u, 'right')  (mogp_constrained.py:272-277). */
+int mogp_host_choice(const double* score, int32_t n, double u, double* p_out, int32_t* index_out, double* margin_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOGP_B200_H */

@@ -1,0 +1,352 @@
+"""ctypes binding of include/mogp_b200.h — the only way the package reaches the device.
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible,
+the calls raise.  (`oracle/` is test infrastructure and is never imported from here.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._build import LIB
+
+MOGP_OK, MOGP_EINVAL, MOGP_ECUDA, MOGP_ENOMEM, MOGP_ENOTPD, MOGP_EPROB, MOGP_ESTATE = 0, -1, -2, -3, -4, -5, -6
+KERNEL_RBF, KERNEL_LINEAR = 0, 1
+KERNEL_CODE = {"rbf": KERNEL_RBF, "linear": KERNEL_LINEAR}
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("mogp_b200 engine error {}: {}".format(code, msg))
+        self.code = code
+
+
+class ModelSpec(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("mean_func", C.c_int32), ("signal_variance_fix", C.c_int32),
+                ("noise_variance_fix", C.c_int32)]
+
+
+class ChainConfig(C.Structure):
+    _fields_ = [("spec", ModelSpec), ("alpha", C.c_double), ("signal_variance", C.c_double),
+                ("noise_variance", C.c_double), ("lengthscale", C.c_double), ("use_threshold", C.c_int32),
+                ("thr_index", C.c_int32), ("threshold", C.c_double), ("fast_updates", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+_H = C.c_void_p
+
+# name -> (restype, argtypes): every symbol include/mogp_b200.h declares
+SIGNATURES = {
+    "mogp_engine_create": (C.c_int, [C.c_int32, C.POINTER(_H)]),
+    "mogp_engine_destroy": (None, [_H]),
+    "mogp_last_error": (C.c_char_p, [_H]),
+    "mogp_version": (C.c_int, []),
+    "mogp_launch_count": (C.c_int64, [_H]),
+    "mogp_sync": (C.c_int, [_H]),
+    "mogp_timer_start": (C.c_int, [_H]),
+    "mogp_timer_stop": (C.c_int, [_H, _dp]),
+    "mogp_set_patients": (C.c_int, [_H, C.c_int64, _lp, _dp, _dp, _dp]),
+    "mogp_cluster_create": (C.c_int, [_H, C.POINTER(ModelSpec), _dp, _ip]),
+    "mogp_cluster_free": (C.c_int, [_H, C.c_int32]),
+    "mogp_cluster_set_theta": (C.c_int, [_H, C.c_int32, _dp]),
+    "mogp_cluster_get_theta": (C.c_int, [_H, C.c_int32, _dp]),
+    "mogp_cluster_set_data": (C.c_int, [_H, C.c_int32, C.c_int64, _dp, _dp]),
+    "mogp_cluster_set_members": (C.c_int, [_H, C.c_int32, C.c_int64, _lp]),
+    "mogp_cluster_append": (C.c_int, [_H, C.c_int32, C.c_int64, _dp, _dp]),
+    "mogp_cluster_remove_rows": (C.c_int, [_H, C.c_int32, C.c_int64, C.c_int64]),
+    "mogp_cluster_size": (C.c_int64, [_H, C.c_int32]),
+    "mogp_cluster_get_data": (C.c_int, [_H, C.c_int32, _dp, _dp]),
+    "mogp_cluster_loglik": (C.c_int, [_H, C.c_int32, _dp]),
+    "mogp_cluster_objective": (C.c_int, [_H, C.c_int32, _dp, C.c_int32, _dp, _dp]),
+    "mogp_cluster_n_free": (C.c_int, [_H, C.c_int32]),
+    "mogp_cluster_get_optimizer_array": (C.c_int, [_H, C.c_int32, _dp, _ip]),
+    "mogp_cluster_lml_grad": (C.c_int, [_H, C.c_int32, _dp]),
+    "mogp_cluster_predict": (C.c_int, [_H, C.c_int32, C.c_int64, _dp, _dp, _dp]),
+    "mogp_cluster_log_predictive_density": (C.c_int, [_H, C.c_int32, C.c_int64, _dp, _dp, _dp]),
+    "mogp_cluster_leave_out_score": (C.c_int, [_H, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _dp, _dp]),
+    "mogp_score_pairs": (C.c_int, [_H, C.c_int64, _lp, _dp, _dp, C.c_int32, _ip, C.c_int32, _dp, _dp]),
+    "mogp_score_pairs_dev": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, _ip,
+                                       C.c_int32, C.c_void_p, C.c_void_p]),
+    "mogp_new_cluster_ll": (C.c_int, [_H, C.POINTER(ModelSpec), _dp, C.c_int64, _lp, _dp, _dp, _dp, _dp]),
+    "mogp_chain_init": (C.c_int, [_H, C.POINTER(ChainConfig), C.c_int64, _ip, C.c_int32, _dp]),
+    "mogp_chain_step_begin": (C.c_int, [_H, C.c_int64]),
+    "mogp_chain_step_score": (C.c_int, [_H, C.c_double, _ip, _ip, _dp, C.c_int32]),
+    "mogp_chain_step_commit": (C.c_int, [_H, C.c_int32, C.c_double, _ip]),
+    "mogp_chain_step": (C.c_int, [_H, C.c_int64, C.c_double, C.c_double, _ip, _ip, _ip, _ip, _dp, C.c_int32]),
+    "mogp_chain_sweep": (C.c_int, [_H, C.c_int64, _lp, _dp, _dp, _ip, _dp]),
+    "mogp_chain_get_state": (C.c_int, [_H, _ip, _lp, _ip, C.c_int32, _ip]),
+    "mogp_chain_last_margin": (C.c_double, [_H]),
+    "mogp_host_choice": (C.c_int, [_dp, C.c_int32, C.c_double, _dp, _ip, _dp]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree library (built by `__graft_entry__.build()` / `python -m mogp_b200._build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        raise ImportError("mogp_b200: {} is missing — build it with `python -m mogp_b200._build` "
+                          "(there is no CPU fallback)".format(LIB))
+    lib = C.CDLL(LIB)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def dptr(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def iptr(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+def lptr(a):
+    return a.ctypes.data_as(_lp) if a is not None else None
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    """One engine handle = one CUDA stream + cluster slots (see include/mogp_b200.h)."""
+
+    def __init__(self, device=None):
+        self.lib = load_library()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = _H()
+        rc = self.lib.mogp_engine_create(int(device), C.byref(h))
+        if rc != MOGP_OK:
+            raise EngineError(rc, self.lib.mogp_last_error(None).decode())
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mogp_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != MOGP_OK:
+            code = rc
+            msg = self.lib.mogp_last_error(self.h).decode()
+            if code == MOGP_ENOTPD:
+                raise np.linalg.LinAlgError(msg)        # what GPy's jitchol raises
+            if code == MOGP_EPROB:
+                raise ValueError("probabilities contain NaN")   # what np.random.choice raises
+            raise EngineError(code, msg)
+
+    # -- convenience wrappers ---------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.mogp_launch_count(self.h))
+
+    def sync(self):
+        self.check(self.lib.mogp_sync(self.h))
+
+    def set_patients(self, off, x, y, y_thr=None):
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        x, y = f64(x), f64(y)
+        y_thr = None if y_thr is None else f64(y_thr)
+        self.check(self.lib.mogp_set_patients(self.h, len(off) - 1, lptr(off), dptr(x), dptr(y), dptr(y_thr)))
+
+    def cluster_create(self, spec, theta):
+        slot = C.c_int32(-1)
+        theta = f64(theta)
+        self.check(self.lib.mogp_cluster_create(self.h, C.byref(spec), dptr(theta), C.byref(slot)))
+        return slot.value
+
+    def cluster_free(self, slot):
+        self.check(self.lib.mogp_cluster_free(self.h, slot))
+
+    def cluster_set_data(self, slot, x, y):
+        x, y = f64(x).ravel(), f64(y).ravel()
+        self.check(self.lib.mogp_cluster_set_data(self.h, slot, x.size, dptr(x), dptr(y)))
+
+    def cluster_set_members(self, slot, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        self.check(self.lib.mogp_cluster_set_members(self.h, slot, ids.size, lptr(ids)))
+
+    def cluster_append(self, slot, x, y):
+        x, y = f64(x).ravel(), f64(y).ravel()
+        self.check(self.lib.mogp_cluster_append(self.h, slot, x.size, dptr(x), dptr(y)))
+
+    def cluster_remove_rows(self, slot, p, n):
+        self.check(self.lib.mogp_cluster_remove_rows(self.h, slot, int(p), int(n)))
+
+    def cluster_size(self, slot):
+        return int(self.lib.mogp_cluster_size(self.h, slot))
+
+    def cluster_get_data(self, slot):
+        m = self.cluster_size(slot)
+        x, y = np.empty(m), np.empty(m)
+        self.check(self.lib.mogp_cluster_get_data(self.h, slot, dptr(x), dptr(y)))
+        return x, y
+
+    def cluster_get_theta(self, slot):
+        th = np.empty(4)
+        self.check(self.lib.mogp_cluster_get_theta(self.h, slot, dptr(th)))
+        return th
+
+    def cluster_set_theta(self, slot, theta):
+        theta = f64(theta)
+        self.check(self.lib.mogp_cluster_set_theta(self.h, slot, dptr(theta)))
+
+    def cluster_loglik(self, slot):
+        v = C.c_double()
+        self.check(self.lib.mogp_cluster_loglik(self.h, slot, C.byref(v)))
+        return v.value
+
+    def cluster_lml_grad(self, slot):
+        g = np.empty(4)
+        self.check(self.lib.mogp_cluster_lml_grad(self.h, slot, dptr(g)))
+        return g
+
+    def cluster_n_free(self, slot):
+        return int(self.lib.mogp_cluster_n_free(self.h, slot))
+
+    def cluster_optimizer_array(self, slot):
+        t = np.empty(4)
+        n = C.c_int32()
+        self.check(self.lib.mogp_cluster_get_optimizer_array(self.h, slot, dptr(t), C.byref(n)))
+        return t[:n.value].copy()
+
+    def cluster_objective(self, slot, t=None, want_grad=True):
+        f = C.c_double()
+        nfree = self.cluster_n_free(slot)
+        g = np.empty(max(nfree, 1))
+        if t is not None:
+            t = f64(t)
+        rc = self.lib.mogp_cluster_objective(self.h, slot, dptr(t), 0 if t is None else t.size, C.byref(f),
+                                             dptr(g) if want_grad else None)
+        self.check(rc)
+        return f.value, g[:nfree].copy()
+
+    def cluster_predict(self, slot, xs):
+        xs = f64(xs).ravel()
+        mean, var = np.empty(xs.size), np.empty(xs.size)
+        self.check(self.lib.mogp_cluster_predict(self.h, slot, xs.size, dptr(xs), dptr(mean), dptr(var)))
+        return mean, var
+
+    def cluster_lpd(self, slot, xs, ys):
+        xs, ys = f64(xs).ravel(), f64(ys).ravel()
+        out = np.empty(xs.size)
+        self.check(self.lib.mogp_cluster_log_predictive_density(self.h, slot, xs.size, dptr(xs), dptr(ys), dptr(out)))
+        return out
+
+    def cluster_leave_out_score(self, slot, p, n, thr_index=-1):
+        s, mu = C.c_double(), C.c_double()
+        self.check(self.lib.mogp_cluster_leave_out_score(self.h, slot, int(p), int(n), int(thr_index),
+                                                         C.byref(s), C.byref(mu)))
+        return s.value, mu.value
+
+    def score_pairs(self, off, x, y, slots, thr_index=-1, want_mu=False):
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        x, y = f64(x), f64(y)
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        P = len(off) - 1
+        score = np.empty((P, slots.size))
+        mu = np.empty((P, slots.size)) if want_mu else None
+        self.check(self.lib.mogp_score_pairs(self.h, P, lptr(off), dptr(x), dptr(y), slots.size, iptr(slots),
+                                             int(thr_index), dptr(score), dptr(mu)))
+        return (score, mu) if want_mu else score
+
+    def new_cluster_ll(self, spec, theta, off, x, y, a_draw):
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        x, y, theta = f64(x), f64(y), f64(theta)
+        a_draw = None if a_draw is None else f64(a_draw)
+        out = np.empty(len(off) - 1)
+        self.check(self.lib.mogp_new_cluster_ll(self.h, C.byref(spec), dptr(theta), len(off) - 1, lptr(off), dptr(x),
+                                                dptr(y), dptr(a_draw), dptr(out)))
+        return out
+
+    # -- chain ----------------------------------------------------------------------------------
+    def chain_init(self, cfg, z, theta_of_id):
+        z = np.ascontiguousarray(z, dtype=np.int32)
+        theta_of_id = f64(theta_of_id).reshape(-1, 4)
+        self.check(self.lib.mogp_chain_init(self.h, C.byref(cfg), z.size, iptr(z), theta_of_id.shape[0],
+                                            dptr(theta_of_id)))
+
+    def chain_step_begin(self, n):
+        self.check(self.lib.mogp_chain_step_begin(self.h, int(n)))
+
+    def chain_step_score(self, a_draw, cap=4096):
+        ids = np.empty(cap, dtype=np.int32)
+        sc = np.empty(cap)
+        n = C.c_int32()
+        self.check(self.lib.mogp_chain_step_score(self.h, float(a_draw), C.byref(n), iptr(ids), dptr(sc), cap))
+        return ids[:n.value].copy(), sc[:n.value].copy()
+
+    def chain_step_commit(self, chosen, a_draw):
+        is_new = C.c_int32()
+        self.check(self.lib.mogp_chain_step_commit(self.h, int(chosen), float(a_draw), C.byref(is_new)))
+        return bool(is_new.value)
+
+    def chain_step(self, n, a_draw, u, cap=4096):
+        ids = np.empty(cap, dtype=np.int32)
+        p = np.empty(cap)
+        na, chosen, is_new = C.c_int32(), C.c_int32(), C.c_int32()
+        self.check(self.lib.mogp_chain_step(self.h, int(n), float(a_draw), float(u), C.byref(chosen), C.byref(is_new),
+                                            C.byref(na), iptr(ids), dptr(p), cap))
+        return chosen.value, bool(is_new.value), ids[:na.value].copy(), p[:na.value].copy()
+
+    def chain_sweep(self, order, a_draw, u):
+        order = np.ascontiguousarray(order, dtype=np.int64)
+        a_draw = None if a_draw is None else f64(a_draw)
+        u = f64(u)
+        chosen = np.empty(order.size, dtype=np.int32)
+        mm = C.c_double()
+        self.check(self.lib.mogp_chain_sweep(self.h, order.size, lptr(order), dptr(a_draw), dptr(u), iptr(chosen),
+                                             C.byref(mm)))
+        return chosen, mm.value
+
+    def chain_state(self, N):
+        n_ids = C.c_int32()
+        self.check(self.lib.mogp_chain_get_state(self.h, None, None, None, 0, C.byref(n_ids)))
+        k = n_ids.value
+        z = np.empty(N, dtype=np.int32)
+        Nk = np.empty(k, dtype=np.int64)
+        slots = np.empty(k, dtype=np.int32)
+        self.check(self.lib.mogp_chain_get_state(self.h, iptr(z), lptr(Nk), iptr(slots), k, C.byref(n_ids)))
+        return z, Nk, slots
+
+
+def host_choice(score, u):
+    """The engine's host-side draw (no device needed)."""
+    lib = load_library()
+    score = f64(score)
+    p = np.empty(score.size)
+    idx, margin = C.c_int32(), C.c_double()
+    rc = lib.mogp_host_choice(dptr(score), score.size, float(u), dptr(p), C.byref(idx), C.byref(margin))
+    if rc == MOGP_EPROB:
+        raise ValueError("probabilities contain NaN")
+    if rc != MOGP_OK:
+        raise EngineError(rc, "mogp_host_choice")
+    return idx.value, p, margin.value
+
+
+_default_engine = None
+
+
+def default_engine():
+    """Process-wide engine used by GPobs objects created without an explicit one."""
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine

@@ -1,0 +1,563 @@
+// chain.inl — host orchestration of the structural updates and of the collapsed Gibbs step
+// (mogp/mogp_constrained.py:231-284 + mogp/allocmodel.py:22-34).  Included by engine.cu.
+namespace {
+
+// ---- buffer pool: clusters own one buffer of cap*cap + 4*cap + 16 doubles; row deletions ping-pong ----
+int pool_get(mogp_engine* h, int64_t cap, double** out) {
+  for (size_t i = 0; i < h->pool.size(); ++i)
+    if (h->pool[i].first == cap) {
+      *out = h->pool[i].second;
+      h->pool.erase(h->pool.begin() + i);
+      return MOGP_OK;
+    }
+  CK(h, cudaMalloc((void**)out, sizeof(double) * (size_t)(cap * cap + 4 * cap + 16)));
+  return MOGP_OK;
+}
+void pool_put(mogp_engine* h, int64_t cap, double* buf) {
+  if (buf) h->pool.emplace_back(cap, buf);
+}
+
+// z (optional), alpha and the log marginal from the current M; results stay on the device until asked for.
+int refresh_vectors(mogp_engine* h, Cluster& c, bool recompute_z) {
+  const int64_t mpad = round_up(c.m, TB);
+  Theta th = make_theta(c);
+  if (recompute_z) {
+    k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.x(), c.y(), (int)c.m, th, c.z());
+    LAUNCHED(h);
+  }
+  k_alpha<<<(unsigned)(mpad / 32), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.z(), (int)c.m, c.alpha());
+  LAUNCHED(h);
+  k_lml<<<1, 1024, 0, h->stream>>>(c.M, c.cap, c.z(), c.x(), c.alpha(), (int)c.m, c.stat());
+  LAUNCHED(h);
+  c.stat_on_device = true;
+  c.grad_valid = false;
+  return MOGP_OK;
+}
+
+int fetch_stat(mogp_engine* h, Cluster& c) {
+  if (!c.stat_on_device) return MOGP_OK;
+  TRY(ensure_pin(h, 256));
+  CK(h, cudaMemcpyAsync(h->pin, c.stat(), sizeof(double) * 9, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  const double* hs = reinterpret_cast<const double*>(h->pin);
+  int hinfo;
+  memcpy(&hinfo, hs + 8, sizeof(int));
+  c.stat_on_device = false;
+  if (hinfo != 0 || !isfinite(hs[0])) {
+    c.valid = false;
+    FAIL(h, MOGP_ENOTPD, "rank update lost positive definiteness (m=%lld)", (long long)c.m);
+  }
+  c.lml = hs[0];
+  c.quad = hs[1];
+  c.logdet = hs[2];
+  return MOGP_OK;
+}
+
+// Append n <= NP points whose T = M Kx (n columns x mpad) and predictive means are already on the device.
+int append_core(mogp_engine* h, Cluster& c, int n, const double* xB_dev, const double* yB_dev, const double* T_dev,
+                const double* mu_dev) {
+  const int64_t m = c.m, mpad_old = round_up(m, TB), mnew = m + n, mpad_new = round_up(mnew, TB);
+  if (mnew > c.cap) TRY(cluster_reserve(h, c, mnew, true));
+  const int nb = (int)(mpad_old / TB);
+  TRY(ensure(h, &h->d_apw, &h->apw_elems, NP * NP + NP + NP * mpad_old + APPEND_KS * NP * mpad_old));
+  ApWork w;
+  w.Li = h->d_apw;
+  w.znew = w.Li + NP * NP;
+  w.Ct = w.znew + NP;
+  w.part = w.Ct + NP * mpad_old;
+  Theta th = make_theta(c);
+  int* info = reinterpret_cast<int*>(c.stat() + 8);
+  k_append_small<<<1, 256, 0, h->stream>>>(T_dev, mu_dev, (int)mpad_old, xB_dev, yB_dev, n, th, w, info);
+  LAUNCHED(h);
+  k_append_rows<<<dim3(nb, APPEND_KS), NTHREADS, AP_ROWS_SMEM, h->stream>>>(c.M, c.cap, nb, (int)mpad_old, w);
+  LAUNCHED(h);
+  if (mpad_new > mpad_old) {
+    k_pad_identity<<<64, 256, 0, h->stream>>>(c.M, c.cap, (int)mpad_old, (int)mpad_new);
+    LAUNCHED(h);
+  }
+  k_append_finalize<<<(unsigned)((mpad_new + 255) / 256), 256, 0, h->stream>>>(c.M, c.cap, (int)m, n, (int)mpad_old,
+                                                                               (int)mpad_new, w, xB_dev, yB_dev, c.x(), c.y(),
+                                                                               c.z());
+  LAUNCHED(h);
+  c.m = mnew;
+  CK(h, cudaGetLastError());
+  return refresh_vectors(h, c, false);
+}
+
+// mogp_cluster_append: host points, any n (chunks of NP).
+int append_points(mogp_engine* h, Cluster& c, int64_t n, const double* x, const double* y) {
+  int32_t slot = (int32_t)(&c - h->cl.data());
+  for (int64_t q0 = 0; q0 < n; q0 += NP) {
+    const int nn = (int)std::min<int64_t>(NP, n - q0);
+    int64_t off[2] = {0, nn};
+    TRY(stage_query(h, 1, off, x + q0, y + q0, nullptr));
+    ScorePlan pl;
+    TRY(score_device(h, 1, nn, h->d_qoff, h->d_q, h->d_q + nn, 1, &slot, -1, nullptr, nullptr, nullptr, nullptr, nullptr, true, &pl));
+    Cluster& cc = h->cl[slot];
+    TRY(append_core(h, cc, nn, h->d_q, h->d_q + nn, pl.T, pl.mu));
+    cc.hx.insert(cc.hx.end(), x + q0, x + q0 + nn);
+    cc.hy.insert(cc.hy.end(), y + q0, y + q0 + nn);
+  }
+  return fetch_stat(h, h->cl[slot]);
+}
+
+RmGeom make_geom(const Cluster& c, int64_t p, int n) {
+  RmGeom g;
+  g.m = (int)c.m;
+  g.n = n;
+  g.p = (int)p;
+  g.mnew = (int)(c.m - n);
+  g.nbn = (int)std::max<int64_t>(1, round_up(g.mnew, TB) / TB);
+  g.I0 = std::min((int)(p / TB), g.nbn - 1);
+  g.ld = c.cap;
+  return g;
+}
+
+int rm_work(mogp_engine* h, const RmGeom& g, RmWork* w) {
+  const int64_t nT = g.nbn - g.I0, rows = nT * TB;
+  TRY(ensure(h, &h->d_upd, &h->upd_elems, rows * NP * 2 + rows + nT * NG + NG + 8));
+  w->Bt = h->d_upd;
+  w->Gt = w->Bt + rows * NP;
+  w->u = w->Gt + rows * NP;
+  w->Pgram = w->u + rows;
+  w->Gc = w->Pgram + nT * NG;
+  w->own = w->Gc + NG;
+  return MOGP_OK;
+}
+
+// Block Gram partials of the rows [p, p+n) of cluster c (input of both the own score and the deletion).
+int rm_gram(mogp_engine* h, Cluster& c, int64_t p, int n) {
+  RmGeom g = make_geom(c, p, n);
+  RmWork w;
+  TRY(rm_work(h, g, &w));
+  k_rm_gram<<<g.nbn - g.I0, 256, 0, h->stream>>>(c.M, g, w);
+  LAUNCHED(h);
+  return MOGP_OK;
+}
+
+// Leave-block-out score into w.own[0..2] (device).
+int own_score(mogp_engine* h, Cluster& c, int64_t p, int n, const double* yB_dev, int thr_index) {
+  RmGeom g = make_geom(c, p, n);
+  RmWork w;
+  TRY(rm_work(h, g, &w));
+  k_own_final<<<1, 256, 0, h->stream>>>(c.alpha(), yB_dev, g, w, g.nbn - g.I0, make_theta(c), thr_index, w.own);
+  LAUNCHED(h);
+  return MOGP_OK;
+}
+
+// Delete rows/cols [p, p+n) (n <= NP) at fixed theta; rm_gram(c, p, n) must have been run on the current M.
+int remove_core(mogp_engine* h, Cluster& c, int64_t p, int n) {
+  RmGeom g = make_geom(c, p, n);
+  RmWork w;
+  TRY(rm_work(h, g, &w));
+  const int nT = g.nbn - g.I0;
+  k_rm_prep<<<nT, 256, RM_PREP_SMEM, h->stream>>>(g, w);
+  LAUNCHED(h);
+  double* nbuf = nullptr;
+  TRY(pool_get(h, c.cap, &nbuf));
+  double* nM = nbuf;
+  double* nvec = nbuf + c.cap * c.cap;
+  k_rm_apply<<<g.nbn, NTHREADS, RM_APPLY_SMEM, h->stream>>>(c.M, nM, g, w);
+  LAUNCHED(h);
+  k_rm_vec<<<(unsigned)((g.mnew + 255) / 256), 256, 0, h->stream>>>(c.x(), c.y(), nvec, nvec + c.cap, g);
+  LAUNCHED(h);
+  // stat block travels with the buffer
+  CK(h, cudaMemcpyAsync(nvec + 4 * c.cap, c.stat(), sizeof(double) * 16, cudaMemcpyDeviceToDevice, h->stream));
+  pool_put(h, c.cap, c.M);
+  c.M = nM;
+  c.vec = nvec;
+  c.m = g.mnew;
+  c.hx.erase(c.hx.begin() + p, c.hx.begin() + p + n);
+  c.hy.erase(c.hy.begin() + p, c.hy.begin() + p + n);
+  CK(h, cudaGetLastError());
+  return refresh_vectors(h, c, true);
+}
+
+// ---- the draw: np.exp(s - logsumexp(s)) then np.random.choice(active, p=p) (mogp_constrained.py:272-277) ----
+// choice(): cdf = cumsum(p); cdf /= cdf[-1]; index = searchsorted(cdf, u, side='right').
+int host_choice(const double* score, int n, double u, double* p_out, int* index_out, double* margin_out) {
+  double amax = -INFINITY;
+  for (int i = 0; i < n; ++i) {
+    if (isnan(score[i])) return MOGP_EPROB;
+    if (score[i] > amax) amax = score[i];
+  }
+  if (!isfinite(amax)) return MOGP_EPROB;
+  double ssum = 0.0;
+  for (int i = 0; i < n; ++i) ssum += exp(score[i] - amax);
+  const double lse = log(ssum) + amax;
+  std::vector<double> cdf(n);
+  double run = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double p = exp(score[i] - lse);
+    if (p_out) p_out[i] = p;
+    run += p;
+    cdf[i] = run;
+  }
+  if (!(fabs(run - 1.0) <= 1.4901161193847656e-08)) return MOGP_EPROB;  // choice(): probabilities do not sum to 1
+  int idx = n;
+  double margin = INFINITY;
+  for (int i = 0; i < n; ++i) {
+    cdf[i] /= cdf[n - 1];
+    if (idx == n && cdf[i] > u) idx = i;
+    margin = std::min(margin, fabs(cdf[i] - u));
+  }
+  if (idx >= n) idx = n - 1;
+  if (index_out) *index_out = idx;
+  if (margin_out) *margin_out = margin;
+  return MOGP_OK;
+}
+
+Theta newcomer_theta(const mogp_chain_config& cfg) {
+  Theta th;
+  th.A = 0.0;
+  th.k0 = cfg.signal_variance;
+  th.k1 = cfg.spec.kernel == MOGP_KERNEL_RBF ? cfg.lengthscale : 1.0;  // Bias(1) in the linear model (obsmodel.py:37)
+  th.noise = cfg.noise_variance;
+  th.kernel = cfg.spec.kernel;
+  th.mean_func = cfg.spec.mean_func;
+  return th;
+}
+
+int chain_check(mogp_engine* h, int64_t n) {
+  if (!h) return MOGP_EINVAL;
+  if (!h->chain.active) FAIL(h, MOGP_ESTATE, "no chain attached");
+  if (n < 0 || n >= h->chain.N) FAIL(h, MOGP_EINVAL, "patient %lld out of range", (long long)n);
+  return MOGP_OK;
+}
+
+// position (row offset) of patient n inside cluster c; -1 if absent
+int64_t member_offset(mogp_engine* h, const Cluster& c, int64_t n, size_t* index) {
+  int64_t off = 0;
+  for (size_t i = 0; i < c.members.size(); ++i) {
+    if (c.members[i] == n) {
+      if (index) *index = i;
+      return off;
+    }
+    off += h->h_off[c.members[i] + 1] - h->h_off[c.members[i]];
+  }
+  return -1;
+}
+
+int rebuild_from_members(mogp_engine* h, Cluster& c) {
+  std::vector<double> xs, ys;
+  for (int64_t id : c.members) {
+    xs.insert(xs.end(), h->h_x.begin() + h->h_off[id], h->h_x.begin() + h->h_off[id + 1]);
+    ys.insert(ys.end(), h->h_y.begin() + h->h_off[id], h->h_y.begin() + h->h_off[id + 1]);
+  }
+  if (xs.empty()) FAIL(h, MOGP_ESTATE, "cluster members have no visits");
+  return upload_data(h, c, (int64_t)xs.size(), xs.data(), ys.data());
+}
+
+// Step phase 1: take patient n out (mogp_constrained.py:232-244).
+int chain_begin(mogp_engine* h, int64_t n) {
+  Chain& ch = h->chain;
+  if (ch.pending >= 0) FAIL(h, MOGP_ESTATE, "previous step not committed");
+  const int32_t prev = ch.z[n];
+  if (prev < 0 || prev >= (int32_t)ch.Nk.size() || ch.slot_of_id[prev] < 0) FAIL(h, MOGP_ESTATE, "patient %lld has no cluster", (long long)n);
+  ch.z[n] = -1;
+  ch.Nk[prev] -= 1;  // allocmodel.calc_score, allocmodel.py:24
+  ch.pending = n;
+  ch.pending_prev = prev;
+  ch.pending_lazy = 0;
+  ch.pending_p = -1;
+  ch.gram_ready = false;
+  Cluster& c = h->cl[ch.slot_of_id[prev]];
+  const int64_t ni = h->h_off[n + 1] - h->h_off[n];
+  if (ch.Nk[prev] == 0) {  // obsmodel[curr_k] = None (:235-237)
+    TRY(mogp_cluster_free(h, ch.slot_of_id[prev]));
+    ch.slot_of_id[prev] = -1;
+    return MOGP_OK;
+  }
+  if (ch.cfg.fast_updates && ni > 0 && ni <= NP && c.valid) {
+    ch.pending_lazy = 1;  // rows stay in place; the own score is the leave-block-out form
+    return MOGP_OK;
+  }
+  // reference-exact: re-extract the members in patient-index order and refactorise (:239-242)
+  size_t idx = 0;
+  if (member_offset(h, c, n, &idx) < 0) FAIL(h, MOGP_ESTATE, "patient %lld not in its cluster's member list", (long long)n);
+  c.members.erase(c.members.begin() + idx);
+  std::sort(c.members.begin(), c.members.end());
+  return rebuild_from_members(h, c);
+}
+
+// Step phase 2: score[active] = log prior weight + log likelihood (:244-271).  Needs a_draw for the newcomer.
+int chain_score(mogp_engine* h, double a_draw) {
+  Chain& ch = h->chain;
+  const int64_t n = ch.pending;
+  if (n < 0) FAIL(h, MOGP_ESTATE, "chain_score without chain_begin");
+  const int64_t c0 = h->h_off[n], ni = h->h_off[n + 1] - c0;
+  ch.act_ids.clear();
+  ch.act_score.clear();
+  ch.score_slots.clear();
+  const int32_t n_ids = (int32_t)ch.Nk.size();
+  for (int32_t k = 0; k < n_ids; ++k)
+    if (ch.Nk[k] > 0) ch.act_ids.push_back(k);
+  ch.act_ids.push_back(n_ids);  // the new-cluster slot (weight alpha)
+  const int nact = (int)ch.act_ids.size();
+  ch.act_score.assign(nact, 0.0);
+  const int32_t own = ch.pending_lazy ? ch.pending_prev : -1;
+  for (int i = 0; i + 1 < nact; ++i)
+    if (ch.act_ids[i] != own) ch.score_slots.push_back(ch.slot_of_id[ch.act_ids[i]]);
+  const int ns = (int)ch.score_slots.size();
+  const int thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
+  // outputs on the device: score[ns] | mu_thr[ns] | new_ll[1] | own[3]
+  TRY(ensure(h, &h->d_out, &h->out_elems, 2 * (int64_t)ns + 8));
+  double* d_score = h->d_out;
+  double* d_muthr = h->d_out + ns;
+  double* d_newll = h->d_out + 2 * ns;
+  double* d_own = d_newll + 1;
+  ch.plan = ScorePlan();
+  if (ni > 0) {
+    if (own >= 0) {
+      Cluster& c = h->cl[ch.slot_of_id[own]];
+      ch.pending_p = member_offset(h, c, n, nullptr);
+      if (ch.pending_p < 0) FAIL(h, MOGP_ESTATE, "patient %lld not in its cluster's member list", (long long)n);
+      TRY(rm_gram(h, c, ch.pending_p, (int)ni));
+      ch.gram_ready = true;
+      TRY(own_score(h, c, ch.pending_p, (int)ni, h->d_py + c0, thr_index));
+      RmGeom g = make_geom(c, ch.pending_p, (int)ni);
+      RmWork w;
+      TRY(rm_work(h, g, &w));
+      CK(h, cudaMemcpyAsync(d_own, w.own, sizeof(double) * 3, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (ns > 0)
+      TRY(score_device(h, 1, ni, h->d_off + n, h->d_px + c0, h->d_py + c0, ns, ch.score_slots.data(), thr_index, d_score,
+                       d_muthr, nullptr, nullptr, nullptr, ch.cfg.fast_updates != 0, &ch.plan));
+    // the newcomer: GPobs(x_n, y_n) at A = |a_draw|, l = 4, noise_0 (:246-250)
+    ch.a_dev_val = a_draw;
+    TRY(ensure(h, &h->d_q, &h->q_elems, 8));
+    CK(h, cudaMemcpyAsync(h->d_q, &ch.a_dev_val, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_new_ll<<<1, 64, 0, h->stream>>>(h->d_off + n, h->d_px + c0, h->d_py + c0, h->d_q, newcomer_theta(ch.cfg), d_newll);
+    LAUNCHED(h);
+    CK(h, cudaGetLastError());
+  }
+  std::vector<double> host(2 * ns + 8, 0.0);
+  if (ni > 0) TRY(copy_back(h, host.data(), h->d_out, 2 * ns + 4));
+  const double ythr = (ch.cfg.use_threshold && !h->h_ythr.empty()) ? h->h_ythr[n] : NAN;
+  int si = 0;
+  for (int i = 0; i < nact; ++i) {
+    const int32_t id = ch.act_ids[i];
+    double prior, ll, muthr = NAN;
+    if (i == nact - 1) {
+      prior = log(ch.cfg.alpha + 1e-16);  // allocmodel.py:25-26
+      ll = host[2 * ns];
+      if (ni > 0 && !isfinite(ll)) FAIL(h, MOGP_ENOTPD, "new-cluster covariance not positive definite");
+    } else {
+      prior = log((double)ch.Nk[id] + 1e-16);
+      if (id == own) {
+        if (ni > 0 && host[2 * ns + 3] != 1.0) FAIL(h, MOGP_ENOTPD, "leave-out block not positive definite");
+        ll = host[2 * ns + 1];
+        muthr = host[2 * ns + 2];
+      } else {
+        ll = host[si];
+        muthr = host[ns + si];
+        ++si;
+      }
+      // monotonicity rule (:254-263): Y[n, idx] - y* > threshold  ->  -inf
+      if (ch.cfg.use_threshold && ni > 0 && (ythr - muthr > ch.cfg.threshold)) ll = -INFINITY;
+    }
+    ch.act_score[i] = prior + ll;
+  }
+  return MOGP_OK;
+}
+
+// Step phase 3: assign (mogp_constrained.py:277-284 minus the refit).
+int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_new_out) {
+  Chain& ch = h->chain;
+  const int64_t n = ch.pending;
+  if (n < 0) FAIL(h, MOGP_ESTATE, "chain_commit without chain_begin");
+  const int32_t n_ids = (int32_t)ch.Nk.size();
+  const bool is_new = chosen_id == n_ids;
+  if (chosen_id < 0 || chosen_id > n_ids || (!is_new && ch.Nk[chosen_id] <= 0)) FAIL(h, MOGP_EINVAL, "cluster id %d is not active", chosen_id);
+  const int64_t c0 = h->h_off[n], ni = h->h_off[n + 1] - c0;
+  const int32_t prev = ch.pending_prev;
+  if (ch.pending_lazy && chosen_id == prev) {
+    // stayed: the factor already contains the patient (the reference re-appends the same rows)
+  } else {
+    if (ch.pending_lazy) {  // really leaves: delete its rows from the previous cluster
+      Cluster& c = h->cl[ch.slot_of_id[prev]];
+      size_t idx = 0;
+      const int64_t p = member_offset(h, c, n, &idx);
+      if (!ch.gram_ready) TRY(rm_gram(h, c, p, (int)ni));
+      TRY(remove_core(h, c, p, (int)ni));
+      c.members.erase(c.members.begin() + idx);
+    }
+    if (is_new) {
+      int32_t slot;
+      double th[4] = {fabs(a_draw), ch.cfg.signal_variance,
+                      ch.cfg.spec.kernel == MOGP_KERNEL_RBF ? ch.cfg.lengthscale : 1.0, ch.cfg.noise_variance};
+      TRY(mogp_cluster_create(h, &ch.cfg.spec, th, &slot));
+      Cluster& c = h->cl[slot];
+      c.members.assign(1, n);
+      TRY(rebuild_from_members(h, c));
+      if (ch.cfg.fast_updates) TRY(infer(h, c));
+      ch.Nk.push_back(0);
+      ch.slot_of_id.push_back(slot);
+    } else {
+      Cluster& c = h->cl[ch.slot_of_id[chosen_id]];
+      bool done = false;
+      if (ch.cfg.fast_updates && c.valid && ni > 0 && ni <= NP && ch.plan.T) {
+        int si = -1;
+        for (size_t q = 0; q < ch.score_slots.size(); ++q)
+          if (ch.score_slots[q] == ch.slot_of_id[chosen_id]) si = (int)q;
+        if (si >= 0) {
+          // T and the predictive means of this cluster are still in the scoring scratch
+          SlotView sv;
+          const int64_t mpad = round_up(c.m, TB);
+          int64_t kx_off = 0;
+          for (int q = 0; q < si; ++q) kx_off += ch.plan.Rpad * round_up(h->cl[ch.score_slots[q]].m, TB);
+          (void)sv;
+          (void)mpad;
+          TRY(append_core(h, c, (int)ni, h->d_px + c0, h->d_py + c0, ch.plan.T + kx_off, ch.plan.mu + (int64_t)si * ch.plan.Rpad));
+          c.hx.insert(c.hx.end(), h->h_x.begin() + c0, h->h_x.begin() + c0 + ni);
+          c.hy.insert(c.hy.end(), h->h_y.begin() + c0, h->h_y.begin() + c0 + ni);
+          c.members.push_back(n);
+          done = true;
+        }
+      }
+      if (!done) {  // reference order: existing rows, then the patient's (obsmodel.py:77-78, 89-92)
+        c.members.push_back(n);
+        TRY(rebuild_from_members(h, c));
+      }
+    }
+  }
+  ch.z[n] = chosen_id;
+  ch.Nk[chosen_id] += 1;  // allocmodel.update_suffstats, allocmodel.py:29-34
+  ch.pending = -1;
+  ch.plan = ScorePlan();
+  if (is_new_out) *is_new_out = is_new ? 1 : 0;
+  return MOGP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mogp_host_choice(const double* score, int32_t n, double u, double* p_out, int32_t* index_out, double* margin_out) {
+  if (!score || n <= 0) return MOGP_EINVAL;
+  int idx = 0;
+  int rc = host_choice(score, n, u, p_out, &idx, margin_out);
+  if (index_out) *index_out = idx;
+  return rc;
+}
+
+int mogp_chain_init(mogp_engine* h, const mogp_chain_config* cfg, int64_t n_patients, const int32_t* z, int32_t n_ids,
+                    const double* theta_of_id) {
+  if (!h) return MOGP_EINVAL;
+  if (!cfg || !z || n_ids <= 0 || !theta_of_id) FAIL(h, MOGP_EINVAL, "null argument");
+  if (h->P <= 0 || n_patients != h->P) FAIL(h, MOGP_EINVAL, "chain needs the patient table (%lld patients set)", (long long)h->P);
+  if (cfg->use_threshold && h->h_ythr.empty()) FAIL(h, MOGP_EINVAL, "threshold rule needs y_thr in mogp_set_patients");
+  Chain& ch = h->chain;
+  // release the clusters of a previous chain
+  if (ch.active)
+    for (int32_t s : ch.slot_of_id)
+      if (s >= 0 && s < (int32_t)h->cl.size() && h->cl[s].used) mogp_cluster_free(h, s);
+  ch = Chain();
+  ch.cfg = *cfg;
+  ch.N = n_patients;
+  ch.z.assign(z, z + n_patients);
+  ch.Nk.assign(n_ids, 0);
+  ch.slot_of_id.assign(n_ids, -1);
+  std::vector<std::vector<int64_t>> mem(n_ids);
+  for (int64_t i = 0; i < n_patients; ++i) {
+    if (z[i] < 0 || z[i] >= n_ids) FAIL(h, MOGP_EINVAL, "z[%lld] = %d out of range", (long long)i, z[i]);
+    ch.Nk[z[i]] += 1;  // allocmodel.calc_suffstats: bincount (allocmodel.py:18-20)
+    mem[z[i]].push_back(i);
+  }
+  for (int32_t k = 0; k < n_ids; ++k) {
+    if (ch.Nk[k] == 0) continue;
+    int32_t slot;
+    TRY(mogp_cluster_create(h, &cfg->spec, theta_of_id + 4 * k, &slot));
+    ch.slot_of_id[k] = slot;
+    TRY(mogp_cluster_set_members(h, slot, (int64_t)mem[k].size(), mem[k].data()));
+  }
+  ch.active = true;
+  return MOGP_OK;
+}
+
+int mogp_chain_step_begin(mogp_engine* h, int64_t n) {
+  TRY(chain_check(h, n));
+  return chain_begin(h, n);
+}
+
+int mogp_chain_step_score(mogp_engine* h, double a_draw, int32_t* n_active, int32_t* ids_out, double* score_out, int32_t cap_out) {
+  if (!h) return MOGP_EINVAL;
+  if (!h->chain.active) FAIL(h, MOGP_ESTATE, "no chain attached");
+  TRY(chain_score(h, a_draw));
+  Chain& ch = h->chain;
+  const int nact = (int)ch.act_ids.size();
+  if (n_active) *n_active = nact;
+  if (cap_out < nact && (ids_out || score_out)) FAIL(h, MOGP_EINVAL, "output capacity %d < %d active ids", cap_out, nact);
+  for (int i = 0; i < nact; ++i) {
+    if (ids_out) ids_out[i] = ch.act_ids[i];
+    if (score_out) score_out[i] = ch.act_score[i];
+  }
+  return MOGP_OK;
+}
+
+int mogp_chain_step_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_new) {
+  if (!h) return MOGP_EINVAL;
+  if (!h->chain.active) FAIL(h, MOGP_ESTATE, "no chain attached");
+  return chain_commit(h, chosen_id, a_draw, is_new);
+}
+
+int mogp_chain_step(mogp_engine* h, int64_t n, double a_draw, double u, int32_t* chosen_id, int32_t* is_new, int32_t* n_active,
+                    int32_t* ids_out, double* p_out, int32_t cap_out) {
+  TRY(chain_check(h, n));
+  TRY(chain_begin(h, n));
+  TRY(chain_score(h, a_draw));
+  Chain& ch = h->chain;
+  const int nact = (int)ch.act_ids.size();
+  std::vector<double> p(nact);
+  int idx = 0;
+  int rc = host_choice(ch.act_score.data(), nact, u, p.data(), &idx, &ch.last_margin);
+  if (rc != MOGP_OK) FAIL(h, rc, "probabilities contain NaN (patient %lld)", (long long)n);
+  if (n_active) *n_active = nact;
+  if (ids_out || p_out) {
+    if (cap_out < nact) FAIL(h, MOGP_EINVAL, "output capacity %d < %d active ids", cap_out, nact);
+    for (int i = 0; i < nact; ++i) {
+      if (ids_out) ids_out[i] = ch.act_ids[i];
+      if (p_out) p_out[i] = p[i];
+    }
+  }
+  const int32_t chosen = ch.act_ids[idx];
+  if (chosen_id) *chosen_id = chosen;
+  return chain_commit(h, chosen, a_draw, is_new);
+}
+
+int mogp_chain_sweep(mogp_engine* h, int64_t n_steps, const int64_t* order, const double* a_draw, const double* u,
+                     int32_t* chosen_ids, double* min_margin) {
+  if (!h) return MOGP_EINVAL;
+  if (!order || !u || n_steps < 0) FAIL(h, MOGP_EINVAL, "null argument");
+  if (h->chain.active && h->chain.cfg.spec.mean_func && !a_draw) FAIL(h, MOGP_EINVAL, "mean_func needs a_draw");
+  double mm = INFINITY;
+  for (int64_t s = 0; s < n_steps; ++s) {
+    int32_t chosen = -1;
+    TRY(mogp_chain_step(h, order[s], a_draw ? a_draw[s] : 0.0, u[s], &chosen, nullptr, nullptr, nullptr, nullptr, 0));
+    if (chosen_ids) chosen_ids[s] = chosen;
+    mm = std::min(mm, h->chain.last_margin);
+  }
+  if (min_margin) *min_margin = mm;
+  return MOGP_OK;
+}
+
+int mogp_chain_get_state(mogp_engine* h, int32_t* z, int64_t* Nk, int32_t* slot_of_id, int32_t cap_ids, int32_t* n_ids) {
+  if (!h) return MOGP_EINVAL;
+  if (!h->chain.active) FAIL(h, MOGP_ESTATE, "no chain attached");
+  Chain& ch = h->chain;
+  const int32_t k = (int32_t)ch.Nk.size();
+  if (n_ids) *n_ids = k;
+  if (z) memcpy(z, ch.z.data(), sizeof(int32_t) * ch.N);
+  if (Nk || slot_of_id) {
+    if (cap_ids < k) FAIL(h, MOGP_EINVAL, "capacity %d < %d cluster ids", cap_ids, k);
+    for (int32_t i = 0; i < k; ++i) {
+      if (Nk) Nk[i] = ch.Nk[i];
+      if (slot_of_id) slot_of_id[i] = ch.slot_of_id[i];
+    }
+  }
+  return MOGP_OK;
+}
+
+double mogp_chain_last_margin(const mogp_engine* h) { return h ? h->chain.last_margin : NAN; }
+
+}  // extern "C"

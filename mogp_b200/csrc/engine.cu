@@ -1,0 +1,910 @@
+// engine.cu — host side of the C ABI declared in include/mogp_b200.h.
+//
+// One engine = one CUDA stream + a table of cluster slots.  A slot is the device image of one
+// reference `GPobs` object (mogp/obsmodel.py:6-94): its data (x, y), its hyper-parameters theta and the
+// result of exact GP inference at theta — the INVERSE Cholesky factor M = chol(K + (noise+1e-8) I)^-1,
+// alpha = Ky^-1 (y - m(x)) and the log marginal likelihood.  Scoring consumes M as a product
+// (T = M Kx, DMMA) instead of GPy's triangular solve (dtrtrs), which has no parallel slack.
+//
+// Nothing here falls back to the CPU: every numerical entry point launches kernels of this library
+// and fails with MOGP_ECUDA when there is no device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/mogp_b200.h"
+#include "score.cuh"
+#include "update.cuh"
+
+using namespace mogp;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
+
+struct Cluster {
+  bool used = false;
+  mogp_model_spec spec{};
+  double theta[4] = {0, 0, 0, 0};
+  int64_t m = 0;     // data points
+  int64_t cap = 0;   // allocated edge of M (multiple of 64) = leading dimension
+  double* M = nullptr;    // one pooled buffer: M[cap*cap] followed by vec
+  double* vec = nullptr;  // x | y | alpha | z (cap each) | stat[16]   (= M + cap*cap)
+  std::vector<double> hx, hy;     // host mirror of the data (pickling, jitter mean, get_data)
+  std::vector<int64_t> members;   // chain-managed clusters: patient ids in data order
+  bool valid = false;             // factor / alpha / lml correspond to (data, theta)
+  double lml = 0.0, quad = 0.0, logdet = 0.0;
+  double grad[4] = {0, 0, 0, 0};
+  bool grad_valid = false;
+  bool stat_on_device = false;    // lml / quad / logdet of the last rank update not fetched yet
+  double* x() const { return vec; }
+  double* y() const { return vec + cap; }
+  double* alpha() const { return vec + 2 * cap; }
+  double* z() const { return vec + 3 * cap; }
+  double* stat() const { return vec + 4 * cap; }
+};
+
+struct ScorePlan {
+  int64_t R = 0, Rpad = 0;
+  int BN = 8;
+  int n_slots = 0;
+  int max_nb = 0;
+  int64_t kx_total = 0, part_total = 0;
+  double *kxT = nullptr, *part = nullptr, *mu = nullptr, *T = nullptr;
+};
+
+struct Chain {
+  bool active = false;
+  mogp_chain_config cfg{};
+  int64_t N = 0;
+  std::vector<int32_t> z;
+  std::vector<int64_t> Nk;
+  std::vector<int32_t> slot_of_id;
+  int64_t pending = -1;      // patient currently removed (between begin and commit)
+  int32_t pending_prev = -1; // its previous cluster id
+  int32_t pending_lazy = 0;  // fast mode: the patient's rows are still inside its previous cluster
+  int64_t pending_p = -1;    // ... at this row offset
+  bool gram_ready = false;   // k_rm_gram has run for (previous cluster, pending_p)
+  std::vector<int32_t> score_slots;  // slots scored by the batched pass of this step, in order
+  ScorePlan plan;                    // where their T / mu live in the scratch
+  double a_dev_val = 0.0;
+  double last_margin = 0.0;
+  std::vector<int32_t> act_ids;
+  std::vector<double> act_score;
+};
+
+}  // namespace
+
+struct mogp_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  std::vector<Cluster> cl;
+  // patient table
+  int64_t P = 0, V = 0;
+  std::vector<int64_t> h_off;
+  std::vector<double> h_x, h_y, h_ythr;
+  int64_t* d_off = nullptr;
+  double *d_px = nullptr, *d_py = nullptr;
+  // factorisation workspace
+  double* d_L = nullptr;
+  int64_t L_elems = 0;
+  double* d_partial = nullptr;
+  int64_t partial_elems = 0;
+  // scoring scratch
+  SlotView* d_slots = nullptr;
+  int64_t slots_cap = 0;
+  double* d_scr = nullptr;
+  int64_t scr_elems = 0;
+  double* d_q = nullptr;  // query staging: x | y | a_draw
+  int64_t q_elems = 0;
+  int64_t* d_qoff = nullptr;
+  int64_t qoff_elems = 0;
+  double* d_out = nullptr;  // outputs staged on the device before the copy back
+  int64_t out_elems = 0;
+  // pinned host staging
+  char* pin = nullptr;
+  size_t pin_bytes = 0;
+  Chain chain;
+  // update workspace (update.cuh)
+  double* d_upd = nullptr;
+  int64_t upd_elems = 0;
+  double* d_apw = nullptr;   // append workspace
+  int64_t apw_elems = 0;
+  std::vector<std::pair<int64_t, double*>> pool;  // free cluster buffers by capacity
+};
+
+namespace {
+
+#define FAIL(h, code, ...)                                  \
+  do {                                                      \
+    char _b[512];                                           \
+    snprintf(_b, sizeof _b, __VA_ARGS__);                   \
+    (h)->err = _b;                                          \
+    return (code);                                          \
+  } while (0)
+
+#define CK(h, call)                                                                               \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess) FAIL(h, _e == cudaErrorMemoryAllocation ? MOGP_ENOMEM : MOGP_ECUDA,    \
+                                "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define TRY(expr)            \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc != MOGP_OK) return _rc; \
+  } while (0)
+
+#define LAUNCHED(h) ((h)->launches++)
+
+template <typename T>
+int ensure(mogp_engine* h, T** p, int64_t* have, int64_t need) {
+  if (need <= *have) return MOGP_OK;
+  if (*p) CK(h, cudaFree(*p));
+  *p = nullptr;
+  *have = 0;
+  int64_t want = need + need / 4;
+  CK(h, cudaMalloc((void**)p, sizeof(T) * (size_t)want));
+  *have = want;
+  return MOGP_OK;
+}
+
+int ensure_pin(mogp_engine* h, size_t need) {
+  if (need <= h->pin_bytes) return MOGP_OK;
+  if (h->pin) CK(h, cudaFreeHost(h->pin));
+  h->pin = nullptr;
+  h->pin_bytes = 0;
+  size_t want = need + need / 2 + 4096;
+  CK(h, cudaMallocHost((void**)&h->pin, want));
+  h->pin_bytes = want;
+  return MOGP_OK;
+}
+
+Theta make_theta(const Cluster& c) {
+  Theta th;
+  th.A = c.theta[0];
+  th.k0 = c.theta[1];
+  th.k1 = c.theta[2];
+  th.noise = c.theta[3];
+  th.kernel = c.spec.kernel;
+  th.mean_func = c.spec.mean_func;
+  return th;
+}
+
+int check_slot(mogp_engine* h, int32_t slot) {
+  if (!h) return MOGP_EINVAL;
+  if (slot < 0 || slot >= (int32_t)h->cl.size() || !h->cl[slot].used) FAIL(h, MOGP_EINVAL, "bad cluster slot %d", slot);
+  return MOGP_OK;
+}
+
+// Capacity classes (x1.25 steps, multiples of 64) so that buffers can be pooled and ping-ponged.
+int64_t cap_class(int64_t need) {
+  int64_t c = TB;
+  while (c < need) c = round_up(c + c / 4, TB);
+  return c;
+}
+
+int pool_get(mogp_engine* h, int64_t cap, double** out);
+void pool_put(mogp_engine* h, int64_t cap, double* buf);
+
+int cluster_reserve(mogp_engine* h, Cluster& c, int64_t m_new, bool keep) {
+  int64_t need = round_up(std::max<int64_t>(m_new, 1), TB);
+  if (need <= c.cap) return MOGP_OK;
+  const int64_t cap = cap_class(need + (keep ? need / 8 : 0));
+  double* buf = nullptr;
+  TRY(pool_get(h, cap, &buf));
+  double* M = buf;
+  double* vec = buf + cap * cap;
+  CK(h, cudaMemsetAsync(vec, 0, sizeof(double) * (size_t)(4 * cap + 16), h->stream));
+  if (keep && c.cap > 0) {
+    const int64_t mp = round_up(c.m, TB);
+    CK(h, cudaMemcpy2DAsync(M, cap * sizeof(double), c.M, c.cap * sizeof(double), mp * sizeof(double), mp,
+                            cudaMemcpyDeviceToDevice, h->stream));
+    for (int q = 0; q < 4; ++q)
+      CK(h, cudaMemcpyAsync(vec + q * cap, c.vec + q * c.cap, sizeof(double) * c.m, cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(vec + 4 * cap, c.vec + 4 * c.cap, sizeof(double) * 16, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (c.M) pool_put(h, c.cap, c.M);  // stream-ordered reuse: every consumer runs on h->stream
+  c.M = M;
+  c.vec = vec;
+  c.cap = cap;
+  return MOGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact inference at (data, theta): ExactGaussianInference.inference as reached by GPy's
+// GPRegression.__init__ / set_XY / every optimiser evaluation (obsmodel.py:46,73,92,94).
+// jitchol's retry ladder (GPy.util.linalg.jitchol: diag.mean()*1e-6, x10 per try, 5 tries).
+int infer(mogp_engine* h, Cluster& c) {
+  c.valid = false;
+  c.grad_valid = false;
+  if (c.m <= 0) FAIL(h, MOGP_ESTATE, "cluster has no data");
+  const int64_t mpad = round_up(c.m, TB);
+  const int nb = (int)(mpad / TB);
+  const int64_t ld = c.cap;
+  TRY(ensure(h, &h->d_L, &h->L_elems, ld * mpad));
+  Theta th = make_theta(c);
+  double* st = c.stat();
+  int* info = reinterpret_cast<int*>(st + 8);
+  TRY(ensure_pin(h, 256));
+  double jitter = 0.0;
+  for (int attempt = 0;; ++attempt) {
+    CK(h, cudaMemsetAsync(info, 0, sizeof(int), h->stream));
+    k_build<<<dim3(nb, nb), NTHREADS, 0, h->stream>>>(h->d_L, c.M, ld, c.x(), (int)c.m, th, jitter);
+    LAUNCHED(h);
+    for (int p = 0; p < nb; ++p) {
+      k_panel<<<nb, NTHREADS, PANEL_SMEM, h->stream>>>(h->d_L, c.M, ld, p, info);
+      LAUNCHED(h);
+      if (p + 1 < nb) {
+        k_trail<<<dim3(nb, nb - p - 1), NTHREADS, TRAIL_SMEM, h->stream>>>(h->d_L, c.M, ld, p);
+        LAUNCHED(h);
+      }
+    }
+    k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, ld, c.x(), c.y(), (int)c.m, th, c.z());
+    LAUNCHED(h);
+    k_alpha<<<(unsigned)(mpad / 32), NTHREADS, 0, h->stream>>>(c.M, ld, c.z(), (int)c.m, c.alpha());
+    LAUNCHED(h);
+    k_lml<<<1, 1024, 0, h->stream>>>(c.M, ld, c.z(), c.x(), c.alpha(), (int)c.m, st);
+    LAUNCHED(h);
+    CK(h, cudaMemcpyAsync(h->pin, st, sizeof(double) * 9, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    const double* hs = reinterpret_cast<const double*>(h->pin);
+    int hinfo;
+    memcpy(&hinfo, hs + 8, sizeof(int));
+    if (hinfo == 0 && isfinite(hs[0])) {
+      c.lml = hs[0];
+      c.quad = hs[1];
+      c.logdet = hs[2];
+      c.valid = true;
+      c.stat_on_device = false;
+      return MOGP_OK;
+    }
+    // jitchol: fail at once on a non-positive diagonal, else retry with growing jitter
+    double dsum = 0.0;
+    bool nonpos = false;
+    for (int64_t i = 0; i < c.m; ++i) {
+      double d = (c.spec.kernel == MOGP_KERNEL_RBF ? c.theta[1] : c.theta[1] * c.hx[i] * c.hx[i] + c.theta[2]) +
+                 c.theta[3] + GPY_JITTER;
+      if (!(d > 0.0)) nonpos = true;
+      dsum += d;
+    }
+    if (nonpos || attempt >= 5 || !isfinite(dsum)) FAIL(h, MOGP_ENOTPD, "covariance not positive definite (m=%lld)", (long long)c.m);
+    jitter = (attempt == 0) ? dsum / (double)c.m * 1e-6 : jitter * 10.0;
+  }
+}
+
+// Gradient of the log marginal likelihood w.r.t. natural theta at the current factor.
+int infer_grad(mogp_engine* h, Cluster& c) {
+  if (!c.valid) TRY(infer(h, c));
+  const int64_t mpad = round_up(c.m, TB);
+  const int nb = (int)(mpad / TB);
+  const int nz = (nb + GRAD_KC - 1) / GRAD_KC;
+  const int64_t n_partial = (int64_t)nb * nb * nz;
+  TRY(ensure(h, &h->d_partial, &h->partial_elems, n_partial * 3));
+  Theta th = make_theta(c);
+  double* st = c.stat();
+  k_grad<<<dim3(nb, nb, nz), NTHREADS, GRAD_SMEM, h->stream>>>(c.M, c.cap, nb, c.x(), c.alpha(), (int)c.m, th,
+                                                                h->d_partial);
+  LAUNCHED(h);
+  k_grad_final<<<1, 256, 0, h->stream>>>(h->d_partial, (int)n_partial, th, st, st + 10);
+  LAUNCHED(h);
+  CK(h, cudaMemcpyAsync(h->pin, st + 10, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, cudaGetLastError());
+  memcpy(c.grad, h->pin, sizeof(double) * 4);
+  c.grad_valid = true;
+  return MOGP_OK;
+}
+
+int upload_data(mogp_engine* h, Cluster& c, int64_t m, const double* x, const double* y) {
+  TRY(cluster_reserve(h, c, m, false));
+  c.hx.assign(x, x + m);
+  c.hy.assign(y, y + m);
+  c.m = m;
+  TRY(ensure_pin(h, sizeof(double) * 2 * m + 256));
+  // pin[0..256) is reserved for small read-backs
+  double* stage = reinterpret_cast<double*>(h->pin + 256);
+  memcpy(stage, x, sizeof(double) * m);
+  memcpy(stage + m, y, sizeof(double) * m);
+  CK(h, cudaMemcpyAsync(c.x(), stage, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(c.y(), stage + m, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+  c.valid = false;
+  c.grad_valid = false;
+  return MOGP_OK;
+}
+
+// ---- paramz pieces of the optimiser objective (host scalars) -----------------------
+constexpr double LIM_VAL = 36.0;
+
+double logexp_f(double t) {  // paramz Logexp.f
+  if (t > LIM_VAL) return t;
+  double tc = t < -709.782712893384 ? -709.782712893384 : t;
+  return log1p(exp(tc));
+}
+double logexp_finv(double th) { return th > LIM_VAL ? th : log(expm1(th)); }  // Logexp.finv
+double logexp_gradfactor(double th) { return th > LIM_VAL ? 1.0 : -expm1(-th); }
+
+struct Gamma {
+  double a, b;
+  bool on;
+};
+// Gamma.from_EV(E, V): a = E^2/V, b = E/V   (obsmodel.py:28,32,41,47,54)
+Gamma from_EV(double E, double V) { return Gamma{E * E / V, E / V, true}; }
+
+void priors_of(const mogp_model_spec& s, Gamma pr[4], bool fixed[4]) {
+  const Gamma none{0, 0, false};
+  pr[0] = s.mean_func ? from_EV(2.0 / 3.0, 0.2) : none;
+  fixed[0] = !s.mean_func;  // absent parameter
+  pr[1] = s.signal_variance_fix ? none : from_EV(1.0, 0.5);
+  fixed[1] = s.signal_variance_fix != 0;
+  pr[2] = s.kernel == MOGP_KERNEL_RBF ? from_EV(4.0, 9.0) : none;  // Bias variance: positive, no prior
+  fixed[2] = false;
+  pr[3] = s.noise_variance_fix ? none : from_EV(0.75, 0.25 * 0.25);
+  fixed[3] = s.noise_variance_fix != 0;
+}
+
+// ---- scoring --------------------------------------------------------------------------------------------
+template <int BN>
+void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout) {
+  const int smem = (TB * LD_C + BN * LD_C) * (int)sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_score_gemm<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_done = true;
+  }
+  dim3 grid((unsigned)(pl.Rpad / BN), (unsigned)pl.max_nb, (unsigned)pl.n_slots);
+  k_score_gemm<BN><<<grid, NTHREADS, smem, h->stream>>>(h->d_slots, pl.kxT, (int)pl.Rpad, pl.part, Tout);
+  LAUNCHED(h);
+}
+
+// Device-resident query (off_dev[n_pat+1] with off_dev[0] = first column, xs/ys indexed from 0 = that
+// column).  Runs k_kx -> k_score_gemm -> k_score_epi; outputs stay on the device.
+int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_dev, const double* xs_dev,
+                 const double* ys_dev, int32_t n_slots, const int32_t* slots, int32_t thr_index, double* score_dev,
+                 double* mu_thr_dev, double* col_mean, double* col_var, double* col_lpd, bool keep_T, ScorePlan* plan_out) {
+  if (n_slots <= 0 || n_pat <= 0 || R <= 0) return MOGP_OK;
+  ScorePlan pl;
+  pl.R = R;
+  pl.BN = R <= 8 ? 8 : (R <= 16 ? 16 : (R <= 32 ? 32 : 64));
+  pl.Rpad = round_up(R, pl.BN);
+  pl.n_slots = n_slots;
+  TRY(ensure_pin(h, 256 + sizeof(SlotView) * (size_t)n_slots));
+  SlotView* hv = reinterpret_cast<SlotView*>(h->pin + 256);
+  for (int s = 0; s < n_slots; ++s) {
+    TRY(check_slot(h, slots[s]));
+    Cluster& c = h->cl[slots[s]];
+    if (!c.valid) TRY(infer(h, c));
+    SlotView v;
+    v.M = c.M;
+    v.x = c.x();
+    v.alpha = c.alpha();
+    v.ld = c.cap;
+    v.m = (int)c.m;
+    v.mpad = (int)round_up(c.m, TB);
+    v.th = make_theta(c);
+    v.kx_off = pl.kx_total;
+    v.part_off = pl.part_total;
+    pl.kx_total += pl.Rpad * (int64_t)v.mpad;
+    pl.part_total += (int64_t)(v.mpad / TB) * pl.Rpad;
+    pl.max_nb = std::max(pl.max_nb, v.mpad / TB);
+    hv[s] = v;
+  }
+  TRY(ensure(h, &h->d_slots, &h->slots_cap, n_slots));
+  const int64_t mu_total = (int64_t)n_slots * pl.Rpad;
+  const int64_t need = pl.kx_total * (keep_T ? 2 : 1) + pl.part_total + mu_total;
+  TRY(ensure(h, &h->d_scr, &h->scr_elems, need));
+  pl.kxT = h->d_scr;
+  pl.part = pl.kxT + pl.kx_total;
+  pl.mu = pl.part + pl.part_total;
+  pl.T = keep_T ? pl.mu + mu_total : nullptr;
+  CK(h, cudaMemcpyAsync(h->d_slots, hv, sizeof(SlotView) * (size_t)n_slots, cudaMemcpyHostToDevice, h->stream));
+  k_kx<<<dim3((unsigned)((pl.Rpad + 7) / 8), (unsigned)n_slots), NTHREADS, 0, h->stream>>>(h->d_slots, xs_dev, (int)R,
+                                                                                            (int)pl.Rpad, pl.kxT, pl.mu);
+  LAUNCHED(h);
+  switch (pl.BN) {
+    case 8: launch_score_gemm<8>(h, pl, pl.T); break;
+    case 16: launch_score_gemm<16>(h, pl, pl.T); break;
+    case 32: launch_score_gemm<32>(h, pl, pl.T); break;
+    default: launch_score_gemm<64>(h, pl, pl.T); break;
+  }
+  const int64_t pairs = n_pat * n_slots;
+  k_score_epi<<<(unsigned)((pairs + 255) / 256), 256, 0, h->stream>>>(h->d_slots, n_slots, off_dev, n_pat, xs_dev, ys_dev,
+                                                                     (int)pl.Rpad, pl.part, pl.mu, thr_index, score_dev,
+                                                                     mu_thr_dev, col_mean, col_var, col_lpd);
+  LAUNCHED(h);
+  CK(h, cudaGetLastError());
+  if (plan_out) *plan_out = pl;
+  return MOGP_OK;
+}
+
+// Upload a host CSR query into the staging buffers (d_qoff, d_q = x | y | a_draw).
+int stage_query(mogp_engine* h, int64_t n_pat, const int64_t* off, const double* x, const double* y, const double* a_draw) {
+  if (n_pat <= 0 || !off || !x) FAIL(h, MOGP_EINVAL, "empty query");
+  const int64_t base = off[0], R = off[n_pat] - off[0];
+  if (R <= 0) FAIL(h, MOGP_EINVAL, "query has no visits");
+  for (int64_t p = 0; p < n_pat; ++p)
+    if (off[p + 1] < off[p]) FAIL(h, MOGP_EINVAL, "offsets must be non-decreasing");
+  const size_t bytes = sizeof(int64_t) * (n_pat + 1) + sizeof(double) * (2 * R + n_pat);
+  TRY(ensure_pin(h, 256 + bytes));
+  TRY(ensure(h, &h->d_qoff, &h->qoff_elems, n_pat + 1));
+  TRY(ensure(h, &h->d_q, &h->q_elems, 2 * R + n_pat));
+  int64_t* so = reinterpret_cast<int64_t*>(h->pin + 256);
+  double* sd = reinterpret_cast<double*>(so + n_pat + 1);
+  memcpy(so, off, sizeof(int64_t) * (n_pat + 1));
+  memcpy(sd, x + base, sizeof(double) * R);
+  if (y) memcpy(sd + R, y + base, sizeof(double) * R);
+  else memset(sd + R, 0, sizeof(double) * R);
+  if (a_draw) memcpy(sd + 2 * R, a_draw, sizeof(double) * n_pat);
+  else memset(sd + 2 * R, 0, sizeof(double) * n_pat);
+  CK(h, cudaMemcpyAsync(h->d_qoff, so, sizeof(int64_t) * (n_pat + 1), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_q, sd, sizeof(double) * (2 * R + n_pat), cudaMemcpyHostToDevice, h->stream));
+  // the pinned buffer is reused by later stagings: finish the copies first
+  CK(h, cudaStreamSynchronize(h->stream));
+  return MOGP_OK;
+}
+
+int copy_back(mogp_engine* h, double* dst, const double* src_dev, int64_t n) {
+  TRY(ensure_pin(h, 256 + sizeof(double) * (size_t)n));
+  CK(h, cudaMemcpyAsync(h->pin + 256, src_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  memcpy(dst, h->pin + 256, sizeof(double) * n);
+  return MOGP_OK;
+}
+
+}  // namespace
+
+#include "chain.inl"
+
+// =================================================================================================
+extern "C" {
+
+int mogp_version(void) { return 100; }
+
+int mogp_engine_create(int32_t device, mogp_engine** out) {
+  if (!out) return MOGP_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return MOGP_ECUDA;
+  }
+  if (device < 0 || device >= n) {
+    g_create_error = "device index out of range";
+    return MOGP_EINVAL;
+  }
+  mogp_engine* h = new mogp_engine();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+    g_create_error = std::string("engine init failed: ") + cudaGetErrorString(cudaGetLastError());
+    delete h;
+    return MOGP_ECUDA;
+  }
+  cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
+  cudaFuncSetAttribute(k_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAIL_SMEM);
+  cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM);
+  update_set_attributes();
+  *out = h;
+  return MOGP_OK;
+}
+
+void mogp_engine_destroy(mogp_engine* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto& c : h->cl)
+    if (c.M) cudaFree(c.M);
+  cudaFree(h->d_off);
+  cudaFree(h->d_px);
+  cudaFree(h->d_py);
+  cudaFree(h->d_L);
+  cudaFree(h->d_partial);
+  cudaFree(h->d_slots);
+  cudaFree(h->d_scr);
+  cudaFree(h->d_q);
+  cudaFree(h->d_qoff);
+  cudaFree(h->d_out);
+  cudaFree(h->d_upd);
+  cudaFree(h->d_apw);
+  for (auto& pb : h->pool) cudaFree(pb.second);
+  if (h->pin) cudaFreeHost(h->pin);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* mogp_last_error(const mogp_engine* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int64_t mogp_launch_count(const mogp_engine* h) { return h ? h->launches : 0; }
+
+int mogp_sync(mogp_engine* h) {
+  if (!h) return MOGP_EINVAL;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return MOGP_OK;
+}
+int mogp_timer_start(mogp_engine* h) {
+  if (!h) return MOGP_EINVAL;
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  return MOGP_OK;
+}
+int mogp_timer_stop(mogp_engine* h, double* ms_out) {
+  if (!h || !ms_out) return MOGP_EINVAL;
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  CK(h, cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  *ms_out = ms;
+  return MOGP_OK;
+}
+
+// ---- patients ---------------------------------------------------------------------------------------------
+int mogp_set_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x, const double* y,
+                      const double* y_thr) {
+  if (!h) return MOGP_EINVAL;
+  if (n_patients <= 0 || !off || !x || !y || off[0] != 0) FAIL(h, MOGP_EINVAL, "bad patient table");
+  for (int64_t p = 0; p < n_patients; ++p)
+    if (off[p + 1] < off[p]) FAIL(h, MOGP_EINVAL, "offsets must be non-decreasing");
+  const int64_t V = off[n_patients];
+  h->P = n_patients;
+  h->V = V;
+  h->h_off.assign(off, off + n_patients + 1);
+  h->h_x.assign(x, x + V);
+  h->h_y.assign(y, y + V);
+  if (y_thr) h->h_ythr.assign(y_thr, y_thr + n_patients);
+  else h->h_ythr.clear();
+  cudaFree(h->d_off);
+  cudaFree(h->d_px);
+  cudaFree(h->d_py);
+  h->d_off = nullptr;
+  h->d_px = h->d_py = nullptr;
+  CK(h, cudaMalloc((void**)&h->d_off, sizeof(int64_t) * (n_patients + 1)));
+  CK(h, cudaMalloc((void**)&h->d_px, sizeof(double) * std::max<int64_t>(V, 1)));
+  CK(h, cudaMalloc((void**)&h->d_py, sizeof(double) * std::max<int64_t>(V, 1)));
+  TRY(ensure_pin(h, 256 + sizeof(int64_t) * (n_patients + 1) + sizeof(double) * 2 * V));
+  int64_t* so = reinterpret_cast<int64_t*>(h->pin + 256);
+  double* sd = reinterpret_cast<double*>(so + n_patients + 1);
+  memcpy(so, off, sizeof(int64_t) * (n_patients + 1));
+  memcpy(sd, x, sizeof(double) * V);
+  memcpy(sd + V, y, sizeof(double) * V);
+  CK(h, cudaMemcpyAsync(h->d_off, so, sizeof(int64_t) * (n_patients + 1), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_px, sd, sizeof(double) * V, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_py, sd + V, sizeof(double) * V, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->chain.active = false;
+  return MOGP_OK;
+}
+
+// ---- clusters -----------------------------------------------------------------------------------------------
+int mogp_cluster_create(mogp_engine* h, const mogp_model_spec* spec, const double theta[4], int32_t* slot_out) {
+  if (!h) return MOGP_EINVAL;
+  if (!spec || !theta || !slot_out) FAIL(h, MOGP_EINVAL, "null argument");
+  if (spec->kernel != MOGP_KERNEL_RBF && spec->kernel != MOGP_KERNEL_LINEAR) FAIL(h, MOGP_EINVAL, "unknown kernel %d", spec->kernel);
+  int32_t slot = -1;
+  for (size_t i = 0; i < h->cl.size(); ++i)
+    if (!h->cl[i].used) {
+      slot = (int32_t)i;
+      break;
+    }
+  if (slot < 0) {
+    h->cl.emplace_back();
+    slot = (int32_t)h->cl.size() - 1;
+  }
+  Cluster& c = h->cl[slot];
+  c.used = true;
+  c.spec = *spec;
+  memcpy(c.theta, theta, sizeof(double) * 4);
+  c.m = 0;
+  c.valid = c.grad_valid = false;
+  c.hx.clear();
+  c.hy.clear();
+  c.members.clear();
+  *slot_out = slot;
+  return MOGP_OK;
+}
+
+int mogp_cluster_free(mogp_engine* h, int32_t slot) {
+  TRY(check_slot(h, slot));
+  Cluster& c = h->cl[slot];
+  if (c.M) pool_put(h, c.cap, c.M);  // stream-ordered reuse by the next cluster of that capacity class
+  c.M = c.vec = nullptr;
+  c.cap = 0;
+  c.used = false;
+  c.m = 0;
+  c.valid = c.grad_valid = false;
+  c.hx.clear();
+  c.hy.clear();
+  c.members.clear();
+  return MOGP_OK;
+}
+
+int mogp_cluster_set_theta(mogp_engine* h, int32_t slot, const double theta[4]) {
+  TRY(check_slot(h, slot));
+  Cluster& c = h->cl[slot];
+  for (int i = 1; i < 4; ++i)
+    if (!(theta[i] > 0.0) && !(i == 2 && c.spec.kernel == MOGP_KERNEL_LINEAR && theta[i] >= 0.0))
+      FAIL(h, MOGP_EINVAL, "theta[%d] = %g must be positive", i, theta[i]);
+  memcpy(c.theta, theta, sizeof(double) * 4);
+  c.valid = c.grad_valid = false;
+  if (c.m > 0) return infer(h, c);
+  return MOGP_OK;
+}
+
+int mogp_cluster_get_theta(mogp_engine* h, int32_t slot, double theta[4]) {
+  TRY(check_slot(h, slot));
+  memcpy(theta, h->cl[slot].theta, sizeof(double) * 4);
+  return MOGP_OK;
+}
+
+int mogp_cluster_set_data(mogp_engine* h, int32_t slot, int64_t m, const double* x, const double* y) {
+  TRY(check_slot(h, slot));
+  if (m <= 0 || !x || !y) FAIL(h, MOGP_EINVAL, "cluster data must be non-empty");
+  Cluster& c = h->cl[slot];
+  c.members.clear();
+  TRY(upload_data(h, c, m, x, y));
+  return infer(h, c);
+}
+
+int mogp_cluster_set_members(mogp_engine* h, int32_t slot, int64_t n_members, const int64_t* ids) {
+  TRY(check_slot(h, slot));
+  if (n_members <= 0 || !ids) FAIL(h, MOGP_EINVAL, "member list must be non-empty");
+  if (h->P <= 0) FAIL(h, MOGP_ESTATE, "no patient table");
+  std::vector<double> xs, ys;
+  for (int64_t i = 0; i < n_members; ++i) {
+    if (ids[i] < 0 || ids[i] >= h->P) FAIL(h, MOGP_EINVAL, "patient id %lld out of range", (long long)ids[i]);
+    xs.insert(xs.end(), h->h_x.begin() + h->h_off[ids[i]], h->h_x.begin() + h->h_off[ids[i] + 1]);
+    ys.insert(ys.end(), h->h_y.begin() + h->h_off[ids[i]], h->h_y.begin() + h->h_off[ids[i] + 1]);
+  }
+  if (xs.empty()) FAIL(h, MOGP_EINVAL, "members have no visits");
+  Cluster& c = h->cl[slot];
+  TRY(upload_data(h, c, (int64_t)xs.size(), xs.data(), ys.data()));
+  c.members.assign(ids, ids + n_members);
+  return infer(h, c);
+}
+
+int mogp_cluster_append(mogp_engine* h, int32_t slot, int64_t n, const double* x, const double* y) {
+  TRY(check_slot(h, slot));
+  if (n <= 0 || !x || !y) FAIL(h, MOGP_EINVAL, "nothing to append");
+  Cluster& c = h->cl[slot];
+  if (c.m == 0) return mogp_cluster_set_data(h, slot, n, x, y);
+  if (!c.valid) TRY(infer(h, c));
+  return append_points(h, c, n, x, y);
+}
+
+int mogp_cluster_remove_rows(mogp_engine* h, int32_t slot, int64_t p, int64_t n) {
+  TRY(check_slot(h, slot));
+  Cluster& c = h->cl[slot];
+  if (p < 0 || n <= 0 || p + n > c.m) FAIL(h, MOGP_EINVAL, "rows [%lld, %lld) outside the cluster (m=%lld)", (long long)p, (long long)(p + n), (long long)c.m);
+  if (n == c.m) FAIL(h, MOGP_EINVAL, "cannot remove every row; free the cluster instead");
+  if (!c.valid) TRY(infer(h, c));
+  c.members.clear();
+  int64_t left = n;
+  while (left > 0) {  // last chunk first so that p stays valid
+    const int nn = (int)std::min<int64_t>(NP, left);
+    const int64_t q = p + left - nn;
+    TRY(rm_gram(h, c, q, nn));
+    TRY(remove_core(h, c, q, nn));
+    left -= nn;
+  }
+  return fetch_stat(h, c);
+}
+
+int mogp_cluster_leave_out_score(mogp_engine* h, int32_t slot, int64_t p, int64_t n, int32_t thr_index, double* score,
+                                 double* mu_thr) {
+  TRY(check_slot(h, slot));
+  Cluster& c = h->cl[slot];
+  if (p < 0 || n <= 0 || n > NP || p + n > c.m || n == c.m) FAIL(h, MOGP_EINVAL, "bad leave-out block");
+  if (!c.valid) TRY(infer(h, c));
+  TRY(rm_gram(h, c, p, (int)n));
+  TRY(own_score(h, c, p, (int)n, c.y() + p, thr_index));
+  RmGeom g = make_geom(c, p, (int)n);
+  RmWork w;
+  TRY(rm_work(h, g, &w));
+  double out[3];
+  TRY(copy_back(h, out, w.own, 3));
+  if (out[2] != 1.0) FAIL(h, MOGP_ENOTPD, "leave-out block not positive definite");
+  if (score) *score = out[0];
+  if (mu_thr) *mu_thr = out[1];
+  return MOGP_OK;
+}
+
+int64_t mogp_cluster_size(mogp_engine* h, int32_t slot) {
+  if (check_slot(h, slot) != MOGP_OK) return -1;
+  return h->cl[slot].m;
+}
+
+int mogp_cluster_get_data(mogp_engine* h, int32_t slot, double* x, double* y) {
+  TRY(check_slot(h, slot));
+  Cluster& c = h->cl[slot];
+  if (x) memcpy(x, c.hx.data(), sizeof(double) * c.m);
+  if (y) memcpy(y, c.hy.data(), sizeof(double) * c.m);
+  return MOGP_OK;
+}
+
+int mogp_cluster_loglik(mogp_engine* h, int32_t slot, double* lml) {
+  TRY(check_slot(h, slot));
+  Cluster& c = h->cl[slot];
+  if (!c.valid) TRY(infer(h, c));
+  TRY(fetch_stat(h, c));
+  *lml = c.lml;
+  return MOGP_OK;
+}
+
+int mogp_cluster_lml_grad(mogp_engine* h, int32_t slot, double grad_theta[4]) {
+  TRY(check_slot(h, slot));
+  Cluster& c = h->cl[slot];
+  if (!c.grad_valid) TRY(infer_grad(h, c));
+  memcpy(grad_theta, c.grad, sizeof(double) * 4);
+  return MOGP_OK;
+}
+
+int mogp_cluster_n_free(mogp_engine* h, int32_t slot) {
+  if (check_slot(h, slot) != MOGP_OK) return MOGP_EINVAL;
+  Gamma pr[4];
+  bool fixed[4];
+  priors_of(h->cl[slot].spec, pr, fixed);
+  int n = 0;
+  for (int i = 0; i < 4; ++i) n += !fixed[i];
+  return n;
+}
+
+int mogp_cluster_get_optimizer_array(mogp_engine* h, int32_t slot, double* t, int32_t* n_t) {
+  TRY(check_slot(h, slot));
+  Cluster& c = h->cl[slot];
+  Gamma pr[4];
+  bool fixed[4];
+  priors_of(c.spec, pr, fixed);
+  int n = 0;
+  for (int i = 0; i < 4; ++i)
+    if (!fixed[i]) t[n++] = logexp_finv(c.theta[i]);
+  if (n_t) *n_t = n;
+  return MOGP_OK;
+}
+
+int mogp_cluster_objective(mogp_engine* h, int32_t slot, const double* t, int32_t n_t, double* f, double* g) {
+  TRY(check_slot(h, slot));
+  Cluster& c = h->cl[slot];
+  Gamma pr[4];
+  bool fixed[4];
+  priors_of(c.spec, pr, fixed);
+  int nfree = 0;
+  for (int i = 0; i < 4; ++i) nfree += !fixed[i];
+  if (t) {
+    if (n_t != nfree) FAIL(h, MOGP_EINVAL, "expected %d optimiser coordinates, got %d", nfree, n_t);
+    int q = 0;
+    for (int i = 0; i < 4; ++i)
+      if (!fixed[i]) c.theta[i] = logexp_f(t[q++]);
+    c.valid = c.grad_valid = false;
+  }
+  if (!c.valid) TRY(infer(h, c));
+  if (g && !c.grad_valid) TRY(infer_grad(h, c));
+  // log prior + log Jacobian of the Logexp transform for every parameter that has a prior
+  double lp = 0.0, dlp[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) {
+    if (!pr[i].on) continue;
+    const double th = c.theta[i];
+    lp += -lgamma(pr[i].a) + pr[i].a * log(pr[i].b) + (pr[i].a - 1.0) * log(th) - pr[i].b * th;
+    lp += logexp_finv(th) - th;
+    dlp[i] = (pr[i].a - 1.0) / th - pr[i].b + 1.0 / expm1(th);
+  }
+  TRY(fetch_stat(h, c));
+  if (f) *f = -c.lml - lp;
+  if (g) {
+    int q = 0;
+    for (int i = 0; i < 4; ++i)
+      if (!fixed[i]) g[q++] = -(c.grad[i] + dlp[i]) * logexp_gradfactor(c.theta[i]);
+  }
+  return MOGP_OK;
+}
+
+int mogp_cluster_log_predictive_density(mogp_engine* h, int32_t slot, int64_t n, const double* xs, const double* ys,
+                                        double* lpd) {
+  TRY(check_slot(h, slot));
+  if (n <= 0 || !xs || !ys || !lpd) FAIL(h, MOGP_EINVAL, "bad query");
+  int64_t off[2] = {0, n};
+  TRY(stage_query(h, 1, off, xs, ys, nullptr));
+  ScorePlan pl;
+  TRY(ensure(h, &h->d_out, &h->out_elems, 3 * round_up(n, 64) + 8));
+  const int64_t Rp = round_up(n, 64);
+  TRY(score_device(h, 1, n, h->d_qoff, h->d_q, h->d_q + n, 1, &slot, -1, nullptr, nullptr, nullptr, nullptr, h->d_out, false, &pl));
+  (void)Rp;
+  return copy_back(h, lpd, h->d_out, n);
+}
+
+int mogp_cluster_predict(mogp_engine* h, int32_t slot, int64_t n, const double* xs, double* mean, double* var) {
+  TRY(check_slot(h, slot));
+  if (n <= 0 || !xs) FAIL(h, MOGP_EINVAL, "bad query");
+  int64_t off[2] = {0, n};
+  TRY(stage_query(h, 1, off, xs, nullptr, nullptr));
+  ScorePlan pl;
+  const int64_t Rp = round_up(n, 64);
+  TRY(ensure(h, &h->d_out, &h->out_elems, 2 * Rp + 8));
+  TRY(score_device(h, 1, n, h->d_qoff, h->d_q, nullptr, 1, &slot, -1, nullptr, nullptr, h->d_out, h->d_out + Rp, nullptr, false, &pl));
+  if (mean) TRY(copy_back(h, mean, h->d_out, n));
+  if (var) TRY(copy_back(h, var, h->d_out + Rp, n));
+  return MOGP_OK;
+}
+
+// ---- batched pair scoring ------------------------------------------------------------------------------------------
+int mogp_score_pairs_dev(mogp_engine* h, int64_t n_patients, int64_t n_visits, const int64_t* off_dev, const double* x_dev,
+                         const double* y_dev, int32_t n_slots, const int32_t* slots, int32_t thr_index, double* score_dev,
+                         double* mu_thr_dev) {
+  if (!h) return MOGP_EINVAL;
+  if (n_patients <= 0 || n_visits <= 0 || !off_dev || !x_dev || !y_dev || n_slots <= 0 || !slots || !score_dev)
+    FAIL(h, MOGP_EINVAL, "bad arguments");
+  return score_device(h, n_patients, n_visits, off_dev, x_dev, y_dev, n_slots, slots, thr_index, score_dev, mu_thr_dev,
+                      nullptr, nullptr, nullptr, false, nullptr);
+}
+
+int mogp_score_pairs(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x, const double* y, int32_t n_slots,
+                     const int32_t* slots, int32_t thr_index, double* score, double* mu_thr) {
+  if (!h) return MOGP_EINVAL;
+  if (n_patients <= 0 || !off || !x || !y || n_slots <= 0 || !slots || !score) FAIL(h, MOGP_EINVAL, "bad arguments");
+  // Chunk the patients so the cross-covariance scratch stays bounded (~2 GiB).
+  int64_t msum = 0;
+  for (int s = 0; s < n_slots; ++s) {
+    TRY(check_slot(h, slots[s]));
+    msum += round_up(h->cl[slots[s]].m, TB);
+  }
+  const int64_t max_cols = std::max<int64_t>(64, ((int64_t)1 << 28) / std::max<int64_t>(msum, 1));
+  int64_t p0 = 0;
+  while (p0 < n_patients) {
+    int64_t p1 = p0 + 1;
+    while (p1 < n_patients && off[p1 + 1] - off[p0] <= max_cols) ++p1;
+    const int64_t np = p1 - p0, R = off[p1] - off[p0];
+    if (R <= 0) {  // patients without visits score 0 (empty sum)
+      for (int64_t q = p0 * n_slots; q < p1 * n_slots; ++q) {
+        score[q] = 0.0;
+        if (mu_thr) mu_thr[q] = NAN;
+      }
+      p0 = p1;
+      continue;
+    }
+    TRY(stage_query(h, np, off + p0, x, y, nullptr));
+    const int64_t pairs = np * n_slots;
+    TRY(ensure(h, &h->d_out, &h->out_elems, 2 * pairs));
+    TRY(score_device(h, np, R, h->d_qoff, h->d_q, h->d_q + R, n_slots, slots, thr_index, h->d_out,
+                     mu_thr ? h->d_out + pairs : nullptr, nullptr, nullptr, nullptr, false, nullptr));
+    TRY(copy_back(h, score + p0 * n_slots, h->d_out, pairs));
+    if (mu_thr) TRY(copy_back(h, mu_thr + p0 * n_slots, h->d_out + pairs, pairs));
+    p0 = p1;
+  }
+  return MOGP_OK;
+}
+
+int mogp_new_cluster_ll(mogp_engine* h, const mogp_model_spec* spec, const double theta[4], int64_t n_patients, const int64_t* off,
+                        const double* x, const double* y, const double* a_draw, double* ll) {
+  if (!h) return MOGP_EINVAL;
+  if (!spec || !theta || n_patients <= 0 || !off || !x || !y || !ll) FAIL(h, MOGP_EINVAL, "bad arguments");
+  if (spec->mean_func && !a_draw) FAIL(h, MOGP_EINVAL, "mean_func needs the randn draws of the NegLinear mapping");
+  for (int64_t p = 0; p < n_patients; ++p)
+    if (off[p + 1] - off[p] > 64 || off[p + 1] - off[p] <= 0) FAIL(h, MOGP_EINVAL, "new-cluster model needs 1..64 visits per patient");
+  TRY(stage_query(h, n_patients, off, x, y, a_draw));
+  const int64_t R = off[n_patients] - off[0];
+  Theta th;
+  th.A = 0.0;
+  th.k0 = theta[1];
+  th.k1 = theta[2];
+  th.noise = theta[3];
+  th.kernel = spec->kernel;
+  th.mean_func = spec->mean_func;
+  TRY(ensure(h, &h->d_out, &h->out_elems, n_patients));
+  k_new_ll<<<(unsigned)n_patients, 64, 0, h->stream>>>(h->d_qoff, h->d_q, h->d_q + R, h->d_q + 2 * R, th, h->d_out);
+  LAUNCHED(h);
+  CK(h, cudaGetLastError());
+  return copy_back(h, ll, h->d_out, n_patients);
+}
+
+}  // extern "C"

@@ -1,0 +1,318 @@
+// factor.cuh — exact GP inference for one cluster on the device:
+//   Ky = K(x,x) + (noise + 1e-8) I           (k_build; GPy ExactGaussianInference + kern.K)
+//   L  = chol(Ky)      (blocked right-looking, DMMA trailing updates)      [GPy: dpotrf]
+//   M  = L^-1          (blocked, same launches; replaces GPy's dtrtri/dpotri + dtrtrs)
+//   z  = M r, alpha = M^T z, LML = -(m ln 2pi + 2 sum ln L_ii + z.z)/2       [GPy: dpotrs]
+//   gradient of LML w.r.t. theta, contracted tile by tile from W = M^T M    [GPy: dL_dK]
+// Reference call sites: mogp/obsmodel.py:46,56,65,73,92,94.  Formula-level fidelity
+// (SURVEY.md §2.3): r^2 by the expansion x^2 + x'^2 - 2xx' with clip, sqrt then square,
+// the 1e-8 jitter.
+#pragma once
+#include "tile.cuh"
+
+namespace mogp {
+
+constexpr double GPY_JITTER = 1e-8;
+constexpr double LOG_2_PI = 1.8378770664093454835606594728112;
+
+struct Theta {
+  double A, k0, k1, noise;
+  int kernel;     // 0 rbf, 1 linear+bias
+  int mean_func;  // NegLinear on/off
+};
+
+// r^2 exactly as GPy's Stationary._unscaled_dist evaluates it (no FMA contraction).
+__device__ __forceinline__ double r2_expansion(double xi, double xj) {
+  double r2 = __dadd_rn(__dmul_rn(-2.0, __dmul_rn(xi, xj)), __dadd_rn(__dmul_rn(xi, xi), __dmul_rn(xj, xj)));
+  return r2 > 0.0 ? r2 : 0.0;
+}
+
+// k(xi, xj); `same` marks a diagonal element of the symmetric matrix (GPy forces r = 0 there).
+// scaled_r2 (optional) returns (dist / lengthscale)^2 for the lengthscale gradient.
+__device__ __forceinline__ double kern_eval(const Theta& th, double xi, double xj, bool same, double* scaled_r2) {
+  if (th.kernel == 0) {
+    double r = same ? 0.0 : sqrt(r2_expansion(xi, xj)) / th.k1;
+    double rr = __dmul_rn(r, r);
+    if (scaled_r2) *scaled_r2 = rr;
+    return th.k0 * exp(-0.5 * rr);
+  }
+  double xx = __dmul_rn(xi, xj);
+  if (scaled_r2) *scaled_r2 = xx;
+  return __dadd_rn(__dmul_rn(th.k0, xx), th.k1);
+}
+
+__device__ __forceinline__ double kern_diag(const Theta& th, double x) {
+  return th.kernel == 0 ? th.k0 : __dadd_rn(__dmul_rn(th.k0, __dmul_rn(x, x)), th.k1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ky (lower) into L, zero accumulator into M.  Rows >= m are identity padding.
+// grid (nb, nb): x = block column, y = block row; CTAs above the diagonal exit.
+__global__ void __launch_bounds__(NTHREADS) k_build(double* __restrict__ L, double* __restrict__ M, int64_t ld,
+                                                    const double* __restrict__ x, int m, Theta th, double jitter) {
+  const int bj = blockIdx.x, bi = blockIdx.y;
+  if (bj > bi) return;
+  __shared__ double sxi[TB], sxj[TB];
+  if (threadIdx.x < TB) {
+    int i = bi * TB + threadIdx.x, j = bj * TB + threadIdx.x;
+    sxi[threadIdx.x] = i < m ? x[i] : 0.0;
+    sxj[threadIdx.x] = j < m ? x[j] : 0.0;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < TB * TB; idx += NTHREADS) {
+    int a = idx >> 6, b = idx & 63;
+    int i = bi * TB + a, j = bj * TB + b;
+    double v = 0.0;
+    if (j <= i) {
+      if (i < m) {
+        v = kern_eval(th, sxi[a], sxj[b], i == j, nullptr);
+        if (i == j) v = __dadd_rn(v, __dadd_rn(th.noise, GPY_JITTER)) + jitter;
+      } else {
+        v = (i == j) ? 1.0 : 0.0;
+      }
+    }
+    L[(int64_t)i * ld + j] = v;
+    M[(int64_t)i * ld + j] = 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Panel step p, one CTA per block b of block-row/column p:
+//   b == p : L_pp = chol(A_pp), M_pp = L_pp^-1
+//   b >  p : L_bp = A_bp M_pp^T                       (TRSM by the inverse of the diagonal tile)
+//   b <  p : M_pb = -M_pp Acc_pb                      (finalise block-row p of the inverse factor)
+// Every CTA factors the diagonal tile redundantly (no extra launch / grid barrier).
+constexpr int PANEL_SMEM = (TB * LD_C + TB * LD_C + TB * LD_R + TB) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(NTHREADS) k_panel(double* __restrict__ L, double* __restrict__ M, int64_t ld, int p,
+                                                    int* __restrict__ info) {
+  extern __shared__ __align__(16) double smem[];
+  double* sD = smem;                 // [64][LD_C]  A_pp -> L_pp
+  double* sM = sD + TB * LD_C;       // [64][LD_C]  M_pp
+  double* sT = sM + TB * LD_C;       // [64][LD_R]  the CTA's own tile
+  double* col = sT + TB * LD_R;      // [64]
+  const int b = blockIdx.x;
+  const int64_t dpp = (int64_t)p * TB * ld + (int64_t)p * TB;
+  load_tile<LD_C>(sD, L + dpp, ld);
+  if (b > p) load_tile<LD_C>(sT, L + (int64_t)b * TB * ld + (int64_t)p * TB, ld);
+  if (b < p) load_tile<LD_R>(sT, M + (int64_t)p * TB * ld + (int64_t)b * TB, ld);
+  int fail = potrf_tile<LD_C>(sD, col);
+  if (fail && b == p && threadIdx.x == 0) atomicCAS(info, 0, p * TB + fail);
+  trtri_tile<LD_C>(sD, sM);
+  if (b == p) {
+    for (int idx = threadIdx.x; idx < TB * TB; idx += NTHREADS) {
+      int i = idx >> 6, j = idx & 63;
+      L[dpp + (int64_t)i * ld + j] = sD[i * LD_C + j];
+      M[dpp + (int64_t)i * ld + j] = sM[i * LD_C + j];
+    }
+    return;
+  }
+  Acc64 acc;
+  acc.zero();
+  if (b > p) {
+    warp_mma<2, 4, true, true>(acc, sT, sM, warp_rb64(), warp_cb64());  // A_bp * M_pp^T
+    double* out = L + (int64_t)b * TB * ld + (int64_t)p * TB;
+    for_each_acc64(acc, [&](int r, int c, double& v) { out[(int64_t)r * ld + c] = v; });
+  } else {
+    warp_mma<2, 4, true, false>(acc, sM, sT, warp_rb64(), warp_cb64());  // M_pp * Acc_pb
+    double* out = M + (int64_t)p * TB * ld + (int64_t)b * TB;
+    for_each_acc64(acc, [&](int r, int c, double& v) { out[(int64_t)r * ld + c] = -v; });
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// After panel p: grid (nb, nb), x = block column j, y = block row i (> p):
+//   j > p, j <= i : A_ij -= L_ip L_jp^T                (Cholesky trailing update)
+//   j <= p        : Acc_ij += L_ip M_pj                (right-looking update of the inverse factor)
+constexpr int TRAIL_SMEM = (TB * LD_C + TB * LD_R) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(NTHREADS) k_trail(double* __restrict__ L, double* __restrict__ M, int64_t ld, int p) {
+  const int bj = blockIdx.x, bi = blockIdx.y + p + 1;
+  if (bj > bi) return;
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;             // L_ip   [64][LD_C]
+  double* sB = sA + TB * LD_C;   // L_jp [64][LD_C]  or  M_pj [64][LD_R]
+  load_tile<LD_C>(sA, L + (int64_t)bi * TB * ld + (int64_t)p * TB, ld);
+  Acc64 acc;
+  acc.zero();
+  if (bj > p) {
+    load_tile<LD_C>(sB, L + (int64_t)bj * TB * ld + (int64_t)p * TB, ld);
+    __syncthreads();
+    warp_mma<2, 4, true, true>(acc, sA, sB, warp_rb64(), warp_cb64());
+    double* out = L + (int64_t)bi * TB * ld + (int64_t)bj * TB;
+    const bool diag = (bi == bj);
+    for_each_acc64(acc, [&](int r, int c, double& v) {
+      if (!diag || c <= r) out[(int64_t)r * ld + c] -= v;
+    });
+  } else {
+    load_tile<LD_R>(sB, M + (int64_t)p * TB * ld + (int64_t)bj * TB, ld);
+    __syncthreads();
+    warp_mma<2, 4, true, false>(acc, sA, sB, warp_rb64(), warp_cb64());
+    double* out = M + (int64_t)bi * TB * ld + (int64_t)bj * TB;
+    for_each_acc64(acc, [&](int r, int c, double& v) { out[(int64_t)r * ld + c] += v; });
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// z = M r with r = y + A x (residual of the NegLinear mean, neg_linear.py:22-23). Warp per row.
+__global__ void __launch_bounds__(NTHREADS) k_z(const double* __restrict__ M, int64_t ld, const double* __restrict__ x,
+                                                const double* __restrict__ y, int m, Theta th,
+                                                double* __restrict__ z) {
+  const int i = blockIdx.x * (NTHREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= m) return;
+  const double A = th.mean_func ? th.A : 0.0;
+  double acc = 0.0;
+  for (int j = lane; j <= i; j += 32) acc += M[(int64_t)i * ld + j] * (y[j] + A * x[j]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) z[i] = acc;
+}
+
+// alpha = M^T z.  CTA per strip of 32 columns, warps split the rows, fixed-order reduction.
+__global__ void __launch_bounds__(NTHREADS) k_alpha(const double* __restrict__ M, int64_t ld,
+                                                    const double* __restrict__ z, int m, double* __restrict__ alpha) {
+  __shared__ double red[NTHREADS / 32][33];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+  double acc = 0.0;
+  for (int i = blockIdx.x * 32 + w; i < m; i += NTHREADS / 32) acc += M[(int64_t)i * ld + j] * z[i];
+  red[w][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (w == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < NTHREADS / 32; ++q) s += red[q][threadIdx.x];
+    if (j < m) alpha[j] = s;
+  }
+}
+
+// One CTA: quad = z.z, logdet = 2 sum ln L_ii = -2 sum ln M_ii, sxa = sum x_i alpha_i, LML.  out[0..3].
+__global__ void __launch_bounds__(1024) k_lml(const double* __restrict__ M, int64_t ld, const double* __restrict__ z,
+                                              const double* __restrict__ x, const double* __restrict__ alpha, int m,
+                                              double* __restrict__ out) {
+  __shared__ double red[3][1024];
+  double q = 0.0, ld2 = 0.0, sxa = 0.0;
+  for (int i = threadIdx.x; i < m; i += 1024) {
+    q += z[i] * z[i];
+    ld2 -= log(M[(int64_t)i * ld + i]);
+    sxa += x[i] * alpha[i];
+  }
+  red[0][threadIdx.x] = q;
+  red[1][threadIdx.x] = ld2;
+  red[2][threadIdx.x] = sxa;
+  __syncthreads();
+  for (int s = 512; s; s >>= 1) {
+    if (threadIdx.x < s) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + s];
+      red[1][threadIdx.x] += red[1][threadIdx.x + s];
+      red[2][threadIdx.x] += red[2][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double logdet = 2.0 * red[1][0];
+    out[0] = 0.5 * (-(double)m * LOG_2_PI - logdet - red[0][0]);  // log marginal likelihood
+    out[1] = red[0][0];                                           // r^T Ky^-1 r
+    out[2] = logdet;
+    out[3] = red[2][0];                                           // x . alpha  (dLML/dA = -x.alpha)
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gradient contraction.  W = M^T M is never materialised: CTA (bj, bi, kc) forms the partial tile
+//   W_ij^(kc) = sum_{k in chunk kc, k >= bi} M_k,bi^T M_k,bj
+// and contracts it (plus the alpha alpha^T term, on chunk 0 only) with dK/dtheta built on the fly:
+//   S0 = sum dL_dK_ij * K_ij        (-> d/d variance [rbf], d/d bias [linear: K_ij := 1])
+//   S1 = sum dL_dK_ij * K_ij * r2   (-> d/d lengthscale [rbf], d/d variances [linear: x_i x_j])
+//   S2 = trace(dL_dK)               (-> d/d noise)
+// with dL_dK = (alpha alpha^T - W)/2 (GPy ExactGaussianInference).  Partials are written per CTA
+// and summed in a fixed order by k_grad_final, so the result is run-to-run deterministic.
+constexpr int GRAD_KC = 4;
+constexpr int GRAD_SMEM = (2 * TB * LD_R) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(NTHREADS) k_grad(const double* __restrict__ M, int64_t ld, int nb,
+                                                   const double* __restrict__ x, const double* __restrict__ alpha,
+                                                   int m, Theta th, double* __restrict__ partial) {
+  const int bj = blockIdx.x, bi = blockIdx.y, kc = blockIdx.z;
+  const int cta = (kc * gridDim.y + bi) * gridDim.x + bj;
+  const int k0 = bi + kc * GRAD_KC;
+  __shared__ double red[3][NTHREADS / 32];
+  if (bj > bi || k0 >= nb) {
+    if (threadIdx.x < 3) partial[(int64_t)cta * 3 + threadIdx.x] = 0.0;
+    return;
+  }
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;
+  double* sB = sA + TB * LD_R;
+  Acc64 acc;
+  acc.zero();
+  const int k1 = min(nb, k0 + GRAD_KC);
+  for (int k = k0; k < k1; ++k) {
+    __syncthreads();
+    load_tile<LD_R>(sA, M + (int64_t)k * TB * ld + (int64_t)bi * TB, ld);
+    load_tile<LD_R>(sB, M + (int64_t)k * TB * ld + (int64_t)bj * TB, ld);
+    __syncthreads();
+    warp_mma<2, 4, false, false>(acc, sA, sB, warp_rb64(), warp_cb64());
+  }
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for_each_acc64(acc, [&](int r, int c, double& w) {
+    int i = bi * TB + r, j = bj * TB + c;
+    if (i < m && j <= i) {
+      double aa = (kc == 0) ? alpha[i] * alpha[j] : 0.0;
+      double dl = 0.5 * (aa - w);
+      double f = (i == j) ? 1.0 : 2.0;
+      double r2;
+      double kij = kern_eval(th, x[i], x[j], i == j, &r2);
+      if (th.kernel == 1) kij = 1.0;
+      s0 += f * dl * kij;
+      s1 += f * dl * kij * r2;
+      if (i == j) s2 += dl;
+    }
+  });
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s0;
+    red[1][threadIdx.x >> 5] = s1;
+    red[2][threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < NTHREADS / 32; ++q) s += red[threadIdx.x][q];
+    partial[(int64_t)cta * 3 + threadIdx.x] = s;
+  }
+}
+
+// grad_theta[4] = dLML/d[A, k0, k1, noise] from the partial sums (one CTA, fixed order).
+__global__ void __launch_bounds__(256) k_grad_final(const double* __restrict__ partial, int n_partial, Theta th,
+                                                    const double* __restrict__ lml_out, double* __restrict__ grad) {
+  __shared__ double red[3][256];
+  double s[3] = {0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < n_partial; i += 256)
+    for (int q = 0; q < 3; ++q) s[q] += partial[(int64_t)i * 3 + q];
+  for (int q = 0; q < 3; ++q) red[q][threadIdx.x] = s[q];
+  __syncthreads();
+  for (int st = 128; st; st >>= 1) {
+    if (threadIdx.x < st)
+      for (int q = 0; q < 3; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    grad[0] = th.mean_func ? -lml_out[3] : 0.0;  // neg_linear.py:25-26 with dL_dm = alpha
+    if (th.kernel == 0) {
+      grad[1] = red[0][0] / th.k0;  // Stationary.update_gradients_full: sum(K * dL_dK) / variance
+      grad[2] = red[1][0] / th.k1;  // -sum(dL_dr * r) / lengthscale, dK_dr = -r K
+    } else {
+      grad[1] = red[1][0];  // Linear: sum(dL_dK * x x^T)
+      grad[2] = red[0][0];  // Bias:   sum(dL_dK)
+    }
+    grad[3] = red[2][0];  // Gaussian.exact_inference_gradients: trace(dL_dK)
+  }
+}
+
+}  // namespace mogp

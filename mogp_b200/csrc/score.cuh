@@ -1,0 +1,237 @@
+// score.cuh — per-(patient, cluster) predictive log-likelihood (GPobs.calc_score,
+// mogp/obsmodel.py:75-81 -> GPy GP.log_predictive_density -> Posterior._raw_predict), the
+// threshold mean (get_pred_at_loc, obsmodel.py:83-85) and the new-cluster marginal
+// (GPobs.__init__ on one patient, obsmodel.py:56).
+//
+// For cluster c with inverse factor M_c (m x m) and query visits x*_1..x*_R (all patients' visits
+// packed as columns):
+//   KxT[c][col][j] = k(x_c[j], x*_col)                       k_kx   (cross covariance, built once)
+//   mu[c][col]     = sum_j KxT alpha_c[j]  - A_c x*_col      k_kx
+//   T = M_c Kx  (DMMA), part[c][rb][col] = sum_{i in row block rb} T[i][col]^2      k_score_gemm
+//   v* = kdiag - sum_rb part, clipped at 1e-15;  lpd = -ln(2pi)/2 - ln(v*+s2)/2 - (y-mu)^2/(2(v*+s2))
+//   score[p][c] = sum over the patient's visits                                    k_score_epi
+// Only the diagonal predictive variance is used, visits are scored independently.
+#pragma once
+#include "factor.cuh"
+
+namespace mogp {
+
+// Per-slot view used by the batched scoring kernels (array of these lives in device memory).
+struct SlotView {
+  const double* M;      // inverse factor, row-major lower, ld
+  const double* x;      // cluster inputs
+  const double* alpha;  // Ky^-1 r
+  int64_t ld;
+  int m, mpad;
+  Theta th;
+  int64_t kx_off;    // offset (doubles) of this slot's KxT block in the scratch: [col][mpad]
+  int64_t part_off;  // offset (doubles) of this slot's partial block: [rb][Rpad]
+};
+
+// grid (ceil(R/8), n_slots); warp per query column.
+__global__ void __launch_bounds__(NTHREADS) k_kx(const SlotView* __restrict__ slots, const double* __restrict__ xs,
+                                                 int R, int Rpad, double* __restrict__ kxT, double* __restrict__ mu) {
+  const SlotView sv = slots[blockIdx.y];
+  const int col = blockIdx.x * (NTHREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (col >= Rpad) return;
+  double* out = kxT + sv.kx_off + (int64_t)col * sv.mpad;
+  if (col >= R) {  // zero padding columns so the GEMM needs no mask
+    for (int j = lane; j < sv.mpad; j += 32) out[j] = 0.0;
+    return;
+  }
+  const double xq = xs[col];
+  double acc = 0.0;
+  for (int j = lane; j < sv.mpad; j += 32) {
+    double v = 0.0;
+    if (j < sv.m) {
+      v = kern_eval(sv.th, sv.x[j], xq, false, nullptr);
+      acc += v * sv.alpha[j];
+    }
+    out[j] = v;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) mu[(int64_t)blockIdx.y * Rpad + col] = sv.th.mean_func ? acc + xq * (-sv.th.A) : acc;
+}
+
+// T = M Kx for a 64-row block and a BN-column tile; emits column sums of squares per row block.
+// grid (n_col_tiles, max_nb, n_slots).  BN in {8,16,32,64}.
+template <int BN>
+struct ScoreShape;
+template <>
+struct ScoreShape<8> { static constexpr int MS = 1, NS = 1, WM = 8, WN = 1; };
+template <>
+struct ScoreShape<16> { static constexpr int MS = 1, NS = 2, WM = 8, WN = 1; };
+template <>
+struct ScoreShape<32> { static constexpr int MS = 2, NS = 2, WM = 4, WN = 2; };
+template <>
+struct ScoreShape<64> { static constexpr int MS = 2, NS = 4, WM = 4, WN = 2; };
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS) k_score_gemm(const SlotView* __restrict__ slots,
+                                                         const double* __restrict__ kxT, int Rpad,
+                                                         double* __restrict__ part, double* __restrict__ Tout) {
+  using S = ScoreShape<BN>;
+  const SlotView sv = slots[blockIdx.z];
+  const int nb = sv.mpad / TB;
+  // heavy row blocks first: block row rb needs rb+1 tile products
+  const int rb = nb - 1 - (int)blockIdx.y;
+  if (rb < 0) return;
+  const int c0 = blockIdx.x * BN;
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;            // M tile   [64][LD_C]
+  double* sB = sA + TB * LD_C;  // KxT tile [BN][LD_C]  (stored [col][k])
+  __shared__ double red[S::WM][BN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp / S::WN, wn = warp % S::WN;
+  const int rbase = wm * 8 * S::MS, cbase = wn * 8 * S::NS;
+  Acc<S::MS, S::NS> acc;
+  acc.zero();
+  const double* kx = kxT + sv.kx_off + (int64_t)c0 * sv.mpad;
+  for (int kb = 0; kb <= rb; ++kb) {
+    __syncthreads();
+    load_tile<LD_C>(sA, sv.M + (int64_t)rb * TB * sv.ld + (int64_t)kb * TB, sv.ld);
+    load_tile<LD_C, BN>(sB, kx + (int64_t)kb * TB, sv.mpad);
+    __syncthreads();
+    warp_mma<S::MS, S::NS, true, true>(acc, sA, sB, rbase, cbase);
+  }
+  if (Tout) {  // optional: keep T (= L^-1 Kx) for the rank-n append of the chosen cluster
+    double* o = Tout + sv.kx_off;
+#pragma unroll
+    for (int i = 0; i < S::MS; ++i)
+#pragma unroll
+      for (int j = 0; j < S::NS; ++j) {
+        int r = rb * TB + rbase + 8 * i + g, c = c0 + cbase + 8 * j + 2 * t;
+        o[(int64_t)c * sv.mpad + r] = acc.v[i][j][0];
+        o[(int64_t)(c + 1) * sv.mpad + r] = acc.v[i][j][1];
+      }
+  }
+  // column sums of squares over this warp's rows, then over the WM warps (fixed order)
+#pragma unroll
+  for (int j = 0; j < S::NS; ++j) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < S::MS; ++i) {
+      s0 += acc.v[i][j][0] * acc.v[i][j][0];
+      s1 += acc.v[i][j][1] * acc.v[i][j][1];
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (g == 0) {
+      red[wm][cbase + 8 * j + 2 * t] = s0;
+      red[wm][cbase + 8 * j + 2 * t + 1] = s1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < BN) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < S::WM; ++q) s += red[q][threadIdx.x];
+    part[sv.part_off + (int64_t)rb * Rpad + c0 + threadIdx.x] = s;
+  }
+}
+
+// Per (patient, slot): finish the predictive moments and sum the per-visit log densities.
+// Optional per-column outputs (mean, var incl. noise, lpd) serve predict / log_predictive_density.
+__global__ void __launch_bounds__(256) k_score_epi(const SlotView* __restrict__ slots, int n_slots,
+                                                   const int64_t* __restrict__ off, int64_t n_pat,
+                                                   const double* __restrict__ xs, const double* __restrict__ ys,
+                                                   int Rpad, const double* __restrict__ part,
+                                                   const double* __restrict__ mu, int thr_index,
+                                                   double* __restrict__ score, double* __restrict__ mu_thr,
+                                                   double* __restrict__ col_mean, double* __restrict__ col_var,
+                                                   double* __restrict__ col_lpd) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_pat * n_slots) return;
+  const int64_t p = gid / n_slots;
+  const int c = (int)(gid % n_slots);
+  const SlotView sv = slots[c];
+  const int nb = sv.mpad / TB;
+  const int64_t c0 = off[p] - off[0], c1 = off[p + 1] - off[0];
+  double total = 0.0;
+  for (int64_t col = c0; col < c1; ++col) {
+    double ss = 0.0;
+    for (int rb = 0; rb < nb; ++rb) ss += part[sv.part_off + (int64_t)rb * Rpad + col];
+    double v = kern_diag(sv.th, xs[col]) - ss;
+    v = v > 1e-15 ? v : 1e-15;  // Posterior._raw_predict clips the variance
+    const double vn = v + sv.th.noise;
+    const double m = mu[(int64_t)c * Rpad + col];
+    const double d = ys ? ys[col] - m : 0.0;
+    const double lpd = -0.5 * LOG_2_PI - 0.5 * log(vn) - 0.5 * (d * d) / vn;
+    total += lpd;
+    if (col_mean) col_mean[(int64_t)c * Rpad + col] = m;
+    if (col_var) col_var[(int64_t)c * Rpad + col] = vn;
+    if (col_lpd) col_lpd[(int64_t)c * Rpad + col] = lpd;
+  }
+  if (score) score[gid] = total;
+  if (mu_thr) {
+    const int64_t ct = c0 + thr_index;
+    mu_thr[gid] = (thr_index >= 0 && ct < c1) ? mu[(int64_t)c * Rpad + ct] : nan("");
+  }
+}
+
+// New-cluster marginal: one CTA (64 threads) per patient, n <= 64 visits, all in shared memory.
+//   ll = log N(y | -A x, K + (noise + 1e-8) I),  A = |a_draw|   (GPobs.__init__, obsmodel.py:44-56)
+__global__ void __launch_bounds__(64) k_new_ll(const int64_t* __restrict__ off, const double* __restrict__ xs,
+                                               const double* __restrict__ ys, const double* __restrict__ a_draw,
+                                               Theta th, double* __restrict__ ll) {
+  __shared__ double S[64][65];
+  __shared__ double r[64], xv[64];
+  const int64_t p = blockIdx.x;
+  const int64_t c0 = off[p] - off[0];
+  const int n = (int)(off[p + 1] - off[p]);
+  const int tid = threadIdx.x;
+  const double A = th.mean_func ? fabs(a_draw[p]) : 0.0;
+  if (n > 64 || n <= 0) {
+    if (tid == 0) ll[p] = nan("");
+    return;
+  }
+  if (tid < n) {
+    xv[tid] = xs[c0 + tid];
+    r[tid] = ys[c0 + tid] + A * xv[tid];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * n; idx += 64) {
+    int i = idx / n, j = idx % n;
+    if (j <= i) {
+      double v = kern_eval(th, xv[i], xv[j], i == j, nullptr);
+      if (i == j) v = __dadd_rn(v, __dadd_rn(th.noise, GPY_JITTER));
+      S[i][j] = v;
+    }
+  }
+  __syncthreads();
+  // right-looking Cholesky, thread per row
+  bool bad = false;
+  for (int k = 0; k < n; ++k) {
+    double dkk = S[k][k];
+    if (!(dkk > 0.0)) { bad = true; dkk = 1.0; }
+    double d = sqrt(dkk);
+    __syncthreads();
+    if (tid == k) S[k][k] = d;
+    if (tid > k && tid < n) S[tid][k] /= d;
+    __syncthreads();
+    if (tid > k && tid < n) {
+      double lik = S[tid][k];
+      for (int j = k + 1; j <= tid; ++j) S[tid][j] -= lik * S[j][k];
+    }
+    __syncthreads();
+  }
+  // forward solve z = L^-1 r (thread 0; n <= 64), quad = z.z, logdet
+  if (tid == 0) {
+    double quad = 0.0, lsum = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double s = r[i];
+      for (int j = 0; j < i; ++j) s -= S[i][j] * r[j];
+      s /= S[i][i];
+      r[i] = s;
+      quad += s * s;
+      lsum += log(S[i][i]);
+    }
+    ll[p] = bad ? nan("") : 0.5 * (-(double)n * LOG_2_PI - 2.0 * lsum - quad);
+  }
+}
+
+}  // namespace mogp

@@ -1,0 +1,440 @@
+// update.cuh — rank-n up/down-dates of a cluster's inverse Cholesky factor M at fixed theta, and the
+// leave-block-out ("own cluster") score that avoids most down-dates altogether.
+//
+// The reference refactorises the whole cluster (O(m^3), GPy set_XY) every time a patient leaves
+// (mogp/obsmodel.py:68-73, mogp_constrained.py:239-242) or joins (obsmodel.py:87-92).  With
+// Ky = L L^T, M = L^-1, W = Ky^-1 = M^T M and a patient's n rows at offset p (block B):
+//
+//  * own-cluster score without removing the patient:  y_B | y_rest ~ N(y_B - C alpha_B, C), C = W_BB^-1,
+//    W_BB = sum_k b_k b_k^T with b_k = M[k, p..p+n)  (k_rm_gram + k_own_final);
+//  * row deletion: M' (rows/cols of B removed) = u_i (M[i,j] - g_i . h_{i-1}[:,j]) for i > B, where
+//    G_i = sum_{k<=i} b_k b_k^T, g_i = G_{i-1}^-1 b_i, u_i = (1 + b_i.g_i)^-1/2, h_i[:,j] = sum_{k<=i} b_k M[k,j]
+//    (the closed form of the Givens sweep that re-triangularises M after a column block is dropped);
+//    k_rm_gram -> k_rm_prep -> k_rm_apply, tile by tile with DMMA for the in-tile prefix;
+//  * append: M' = [[M, 0], [-Ls^-1 T^T M, Ls^-1]], T = M Kx (kept by the scoring pass),
+//    Ls = chol(Kss + (noise+1e-8) I - T^T T);  k_append_small -> k_append_rows -> k_append_finalize.
+#pragma once
+#include "score.cuh"
+
+namespace mogp {
+
+constexpr int NP = 16;                  // max rows appended / removed / left out per operation
+constexpr int NG = NP * (NP + 1) / 2;   // packed lower-triangular n x n
+constexpr int LD_W = 84;                // smem ld of the [64][64+NP] operand (84 = 4 mod 16)
+
+__device__ __forceinline__ void tri_unpack(int t, int& a, int& b) {  // t -> (a >= b)
+  a = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((a + 1) * (a + 2) / 2 <= t) ++a;
+  while (a * (a + 1) / 2 > t) --a;
+  b = t - a * (a + 1) / 2;
+}
+__device__ __forceinline__ int tri_idx(int a, int b) { return a * (a + 1) / 2 + b; }
+
+// In-place Cholesky of the packed SPD matrix G (n x n, element (a,b) at G[tri_idx(a,b)*stride]).
+// Returns false on a non-positive pivot.
+__device__ __forceinline__ bool chol_packed(double* G, int n, int stride) {
+  for (int k = 0; k < n; ++k) {
+    double d = G[tri_idx(k, k) * stride];
+    for (int q = 0; q < k; ++q) {
+      double l = G[tri_idx(k, q) * stride];
+      d -= l * l;
+    }
+    if (!(d > 0.0)) return false;
+    d = sqrt(d);
+    G[tri_idx(k, k) * stride] = d;
+    for (int i = k + 1; i < n; ++i) {
+      double s = G[tri_idx(i, k) * stride];
+      for (int q = 0; q < k; ++q) s -= G[tri_idx(i, q) * stride] * G[tri_idx(k, q) * stride];
+      G[tri_idx(i, k) * stride] = s / d;
+    }
+  }
+  return true;
+}
+// Solve (L L^T) g = b with the packed factor; b overwritten by g.
+__device__ __forceinline__ void chol_solve_packed(const double* L, int n, int stride, double* b) {
+  for (int i = 0; i < n; ++i) {
+    double s = b[i];
+    for (int q = 0; q < i; ++q) s -= L[tri_idx(i, q) * stride] * b[q];
+    b[i] = s / L[tri_idx(i, i) * stride];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int q = i + 1; q < n; ++q) s -= L[tri_idx(q, i) * stride] * b[q];
+    b[i] = s / L[tri_idx(i, i) * stride];
+  }
+}
+
+// Geometry of a block deletion: rows/cols [p, p+n) leave an m x m factor.  "New" indices i' address the
+// (m-n) x (m-n) result: old row = i' (< p) or i' + n.
+struct RmGeom {
+  int m, n, p;
+  int mnew;   // m - n
+  int I0;     // first 64-row tile (new space) that holds updated rows: p / 64
+  int nbn;    // tiles of the result: ceil(mnew / 64), at least 1
+  int64_t ld;
+};
+
+// Workspace (doubles): Bt[nrows][NP] | Gt[nrows][NP] | u[nrows] | Pgram[nT][NG] | Gc[NG] | own[4]
+struct RmWork {
+  double *Bt, *Gt, *u, *Pgram, *Gc, *own;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Per 64-row tile (new space, tiles I0..nbn-1): stage b rows, partial Gram of the tile, carriers' Gram.
+__global__ void __launch_bounds__(256) k_rm_gram(const double* __restrict__ M, RmGeom g, RmWork w) {
+  __shared__ double sb[TB][NP + 1];
+  const int I = g.I0 + blockIdx.x;
+  for (int idx = threadIdx.x; idx < TB * NP; idx += 256) {
+    int r = idx / NP, a = idx % NP;
+    int ip = I * TB + r;
+    double v = 0.0;
+    if (a < g.n && ip >= g.p && ip < g.mnew) v = M[(int64_t)(ip + g.n) * g.ld + g.p + a];
+    sb[r][a] = v;
+    w.Bt[((int64_t)blockIdx.x * TB + r) * NP + a] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NG) {
+    int a, b;
+    tri_unpack(threadIdx.x, a, b);
+    double s = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < TB; ++r) s += sb[r][a] * sb[r][b];
+    w.Pgram[(int64_t)blockIdx.x * NG + threadIdx.x] = s;
+    if (blockIdx.x == 0) {  // carriers: rows p..p+n-1 of the block columns (lower triangular M_BB)
+      double c = 0.0;
+      if (a < g.n)
+        for (int q = a; q < g.n; ++q) c += M[(int64_t)(g.p + q) * g.ld + g.p + a] * M[(int64_t)(g.p + q) * g.ld + g.p + b];
+      w.Gc[threadIdx.x] = (a < g.n) ? c : (a == b ? 1.0 : 0.0);  // unused rows: identity keeps chol happy
+    }
+  }
+}
+
+// Leave-block-out score of the block's own patient under the cluster that still contains it.
+//   out[0] = sum_i log N(y_i | mu_i, v_i), out[1] = predictive mean at visit thr_index, out[2] = ok flag
+__global__ void __launch_bounds__(256) k_own_final(const double* __restrict__ alpha, const double* __restrict__ yB, RmGeom g,
+                                                   RmWork w, int nT, Theta th, int thr_index, double* __restrict__ out) {
+  __shared__ double G[NG], C[NP][NP], v[NP];
+  __shared__ int ok;
+  if (threadIdx.x < NG) {
+    double s = w.Gc[threadIdx.x];
+    for (int I = 0; I < nT; ++I) s += w.Pgram[(int64_t)I * NG + threadIdx.x];
+    G[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ok = chol_packed(G, g.n, 1) ? 1 : 0;
+  __syncthreads();
+  if (threadIdx.x < g.n) {  // column threadIdx.x of C = W_BB^-1
+    double e[NP];
+    for (int i = 0; i < g.n; ++i) e[i] = (i == (int)threadIdx.x) ? 1.0 : 0.0;
+    chol_solve_packed(G, g.n, 1, e);
+    for (int i = 0; i < g.n; ++i) C[i][threadIdx.x] = e[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < g.n) {
+    double s = 0.0;
+    for (int q = 0; q < g.n; ++q) s += C[threadIdx.x][q] * alpha[g.p + q];
+    v[threadIdx.x] = s;  // y_i - mu_i
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.0;
+    for (int i = 0; i < g.n; ++i) {
+      // C_ii = k** + noise + 1e-8 - q_i; GPy clips v* = k** - q_i at 1e-15 and then adds the noise
+      double vstar = C[i][i] - th.noise - GPY_JITTER;
+      double vn = vstar > 1e-15 ? C[i][i] - GPY_JITTER : 1e-15 + th.noise;
+      total += -0.5 * LOG_2_PI - 0.5 * log(vn) - 0.5 * (v[i] * v[i]) / vn;
+    }
+    out[0] = total;
+    out[1] = (thr_index >= 0 && thr_index < g.n) ? yB[thr_index] - v[thr_index] : nan("");
+    out[2] = ok ? 1.0 : 0.0;
+  }
+}
+
+// Per tile: G_{i-1} for each of its rows (running Gram, snapshots in shared memory), then one thread per
+// row solves g_i = G_{i-1}^-1 b_i and u_i = (1 + b_i.g_i)^-1/2.
+constexpr int RM_PREP_SMEM = (NG * (TB + 1) + TB * (NP + 1)) * (int)sizeof(double);
+__global__ void __launch_bounds__(256) k_rm_prep(RmGeom g, RmWork w) {
+  extern __shared__ __align__(16) double smem[];
+  double* snap = smem;                  // [NG][TB+1]
+  double* sb = snap + NG * (TB + 1);    // [TB][NP+1]
+  const int I = g.I0 + blockIdx.x;
+  for (int idx = threadIdx.x; idx < TB * NP; idx += 256) {
+    int r = idx / NP, a = idx % NP;
+    sb[r * (NP + 1) + a] = w.Bt[((int64_t)blockIdx.x * TB + r) * NP + a];
+  }
+  __syncthreads();
+  if (threadIdx.x < NG) {
+    int a, b;
+    tri_unpack(threadIdx.x, a, b);
+    double run = w.Gc[threadIdx.x];
+    for (int J = 0; J < (int)blockIdx.x; ++J) run += w.Pgram[(int64_t)J * NG + threadIdx.x];
+    for (int k = 0; k < TB; ++k) {
+      snap[threadIdx.x * (TB + 1) + k] = run;
+      run += sb[k * (NP + 1) + a] * sb[k * (NP + 1) + b];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < TB) {
+    const int r = threadIdx.x, ip = I * TB + r;
+    double gv[NP];
+    double u = 1.0;
+#pragma unroll
+    for (int a = 0; a < NP; ++a) gv[a] = 0.0;
+    if (ip >= g.p && ip < g.mnew) {
+      double* Gr = snap + r;  // element t at Gr[t*(TB+1)]
+      bool ok = chol_packed(Gr, g.n, TB + 1);
+      for (int a = 0; a < g.n; ++a) gv[a] = sb[r * (NP + 1) + a];
+      if (ok) {
+        chol_solve_packed(Gr, g.n, TB + 1, gv);
+        double s = 0.0;
+        for (int a = 0; a < g.n; ++a) s += gv[a] * sb[r * (NP + 1) + a];
+        u = 1.0 / sqrt(1.0 + s);
+      } else {
+        u = nan("");
+      }
+    }
+    for (int a = 0; a < NP; ++a) w.Gt[((int64_t)blockIdx.x * TB + r) * NP + a] = (a < g.n) ? gv[a] : 0.0;
+    w.u[(int64_t)blockIdx.x * TB + r] = u;
+  }
+}
+
+// One CTA per 64-column block J' of the result; walks down the row tiles carrying h (n x 64).
+constexpr int RM_APPLY_SMEM = (TB * LD_W + (TB + NP) * LD_R + TB * (NP + 1) + TB) * (int)sizeof(double);
+__global__ void __launch_bounds__(NTHREADS) k_rm_apply(const double* __restrict__ Mo, double* __restrict__ Mn, RmGeom g,
+                                                       RmWork w) {
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;                       // [64][LD_W]: S (cols 0..63) | Gt (cols 64..64+NP)
+  double* sB = sA + TB * LD_W;             // [64+NP][LD_R]: old tile (rows 0..63) ; h (rows 64..64+NP)
+  double* sb = sB + (TB + NP) * LD_R;      // [64][NP+1]
+  double* su = sb + TB * (NP + 1);         // [64]
+  const int J = blockIdx.x, tid = threadIdx.x;
+  const int64_t ld = g.ld;
+  auto src = [&](int ip, int jp) -> double {
+    if (ip >= g.mnew || jp >= g.mnew) return (ip == jp) ? 1.0 : 0.0;
+    int i = ip < g.p ? ip : ip + g.n, j = jp < g.p ? jp : jp + g.n;
+    return Mo[(int64_t)i * ld + j];
+  };
+  // plain copies above the first updated tile
+  for (int I = J; I < g.I0 && I < g.nbn; ++I)
+    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+      int r = idx >> 6, c = idx & 63;
+      Mn[(int64_t)(I * TB + r) * ld + J * TB + c] = src(I * TB + r, J * TB + c);
+    }
+  const int Ifirst = max(J, g.I0);
+  // h = sum over the carrier rows p..p+n-1 of b_k M[k, j]
+  for (int idx = tid; idx < NP * TB; idx += NTHREADS) {
+    int q = idx >> 6, c = idx & 63;
+    double s = 0.0;
+    int jp = J * TB + c;
+    if (q < g.n && jp < g.mnew) {
+      int j = jp < g.p ? jp : jp + g.n;
+      for (int a = q; a < g.n; ++a) s += Mo[(int64_t)(g.p + a) * ld + g.p + q] * Mo[(int64_t)(g.p + a) * ld + j];
+    }
+    sB[(TB + q) * LD_R + c] = s;
+  }
+  for (int I = Ifirst; I < g.nbn; ++I) {
+    const int64_t wrow = (int64_t)(I - g.I0) * TB;
+    __syncthreads();
+    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+      int r = idx >> 6, c = idx & 63;
+      sB[r * LD_R + c] = src(I * TB + r, J * TB + c);
+    }
+    for (int idx = tid; idx < TB * NP; idx += NTHREADS) {
+      int r = idx / NP, a = idx % NP;
+      sb[r * (NP + 1) + a] = w.Bt[(wrow + r) * NP + a];
+      sA[r * LD_W + TB + a] = w.Gt[(wrow + r) * NP + a];
+    }
+    if (tid < TB) su[tid] = w.u[wrow + tid];
+    __syncthreads();
+    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+      int r = idx >> 6, k = idx & 63;
+      double s = 0.0;
+      if (k < r) {
+#pragma unroll
+        for (int a = 0; a < NP; ++a) s += sA[r * LD_W + TB + a] * sb[k * (NP + 1) + a];
+      }
+      sA[r * LD_W + k] = s;
+    }
+    __syncthreads();
+    Acc64 acc;
+    acc.zero();
+    warp_mma<2, 4, true, false, TB + NP, LD_W, LD_R>(acc, sA, sB, warp_rb64(), warp_cb64());
+    for_each_acc64(acc, [&](int r, int c, double& v) {
+      Mn[(int64_t)(I * TB + r) * ld + J * TB + c] = su[r] * (sB[r * LD_R + c] - v);
+    });
+    __syncthreads();
+    // h += B_tile^T * old tile
+    for (int idx = tid; idx < NP * TB; idx += NTHREADS) {
+      int q = idx >> 6, c = idx & 63;
+      if (q < g.n) {
+        double s = sB[(TB + q) * LD_R + c];
+#pragma unroll 8
+        for (int k = 0; k < TB; ++k) s += sb[k * (NP + 1) + q] * sB[k * LD_R + c];
+        sB[(TB + q) * LD_R + c] = s;
+      }
+    }
+  }
+}
+
+// x, y of the result (new order = old order with the block dropped).
+__global__ void k_rm_vec(const double* __restrict__ xo, const double* __restrict__ yo, double* __restrict__ xn,
+                         double* __restrict__ yn, RmGeom g) {
+  int ip = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= g.mnew) return;
+  int i = ip < g.p ? ip : ip + g.n;
+  xn[ip] = xo[i];
+  yn[ip] = yo[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Identity padding for block rows/cols [from, to) of M (to, from multiples of 64).
+__global__ void k_pad_identity(double* __restrict__ M, int64_t ld, int from, int to) {
+  const int64_t total = (int64_t)to * to - (int64_t)from * from;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int i, j;
+    const int64_t top = (int64_t)from * (to - from);  // rows < from, cols [from, to)
+    if (idx < top) {
+      i = (int)(idx / (to - from));
+      j = from + (int)(idx % (to - from));
+    } else {
+      int64_t q = idx - top;
+      i = from + (int)(q / to);
+      j = (int)(q % to);
+    }
+    M[(int64_t)i * ld + j] = (i == j) ? 1.0 : 0.0;
+  }
+}
+
+// Workspace of an append: S/Li [NP*NP] | znew [NP] | Ct [NP][mpad] | part [KS][NP][mpad]
+constexpr int APPEND_KS = 4;
+struct ApWork {
+  double *Li, *znew, *Ct, *part;
+};
+
+// One CTA: S = Kss + (noise + 1e-8) I - T^T T, Ls = chol(S), Li = Ls^-1, znew = Li (y_B - mu_B), Ct = Li T^T.
+//   T[c*mpad + r] (column c = new point), mu[c] = predictive mean at x_B[c] (mean function included).
+__global__ void __launch_bounds__(256) k_append_small(const double* __restrict__ T, const double* __restrict__ mu, int mpad,
+                                                      const double* __restrict__ xB, const double* __restrict__ yB, int n,
+                                                      Theta th, ApWork w, int* __restrict__ info) {
+  __shared__ double S[NP][NP + 1], Li[NP][NP + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int npairs = n * (n + 1) / 2;
+  for (int t = warp; t < npairs; t += 8) {
+    int a, b;
+    tri_unpack(t, a, b);
+    double s = 0.0;
+    for (int r = lane; r < mpad; r += 32) s += T[(int64_t)a * mpad + r] * T[(int64_t)b * mpad + r];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      double k = kern_eval(th, xB[a], xB[b], a == b, nullptr);
+      if (a == b) k = __dadd_rn(k, __dadd_rn(th.noise, GPY_JITTER));
+      S[a][b] = k - s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bool ok = true;
+    for (int k = 0; k < n && ok; ++k) {
+      double d = S[k][k];
+      for (int q = 0; q < k; ++q) d -= S[k][q] * S[k][q];
+      if (!(d > 0.0)) { ok = false; break; }
+      d = sqrt(d);
+      S[k][k] = d;
+      for (int i = k + 1; i < n; ++i) {
+        double s = S[i][k];
+        for (int q = 0; q < k; ++q) s -= S[i][q] * S[k][q];
+        S[i][k] = s / d;
+      }
+    }
+    if (!ok) atomicCAS(info, 0, 1);
+    // Li = Ls^-1 (lower), column by column
+    for (int c = 0; c < n; ++c)
+      for (int i = 0; i < n; ++i) {
+        double s = (i == c) ? 1.0 : 0.0;
+        if (i < c) { Li[i][c] = 0.0; continue; }
+        for (int q = c; q < i; ++q) s -= S[i][q] * Li[q][c];
+        Li[i][c] = ok ? s / S[i][i] : nan("");
+      }
+  }
+  __syncthreads();
+  if (threadIdx.x < NP * NP) {
+    int i = threadIdx.x / NP, c = threadIdx.x % NP;
+    w.Li[threadIdx.x] = (i < n && c < n) ? Li[i][c] : 0.0;
+  }
+  if (threadIdx.x < NP) {
+    double s = 0.0;
+    if ((int)threadIdx.x < n)
+      for (int q = 0; q <= (int)threadIdx.x; ++q) s += Li[threadIdx.x][q] * (yB[q] - mu[q]);
+    w.znew[threadIdx.x] = s;
+  }
+  for (int idx = threadIdx.x; idx < NP * mpad; idx += 256) {
+    int i = idx / mpad, k = idx % mpad;
+    double s = 0.0;
+    if (i < n)
+      for (int q = 0; q <= i; ++q) s += Li[i][q] * T[(int64_t)q * mpad + k];
+    w.Ct[(int64_t)i * mpad + k] = s;
+  }
+}
+
+// part[s][i][j] = sum over row blocks kb = J + s, J + s + KS, ... of Ct[i][kb-block] * M[kb-block][J-block].
+constexpr int AP_ROWS_SMEM = (TB * LD_R + NP * LD_C) * (int)sizeof(double);
+__global__ void __launch_bounds__(NTHREADS) k_append_rows(const double* __restrict__ M, int64_t ld, int nb, int mpad, ApWork w) {
+  extern __shared__ __align__(16) double smem[];
+  double* sT = smem;               // M tile [k][c], LD_R
+  double* sC = sT + TB * LD_R;     // Ct tile [i][k], LD_C
+  const int J = blockIdx.x, s = blockIdx.y;
+  Acc<2, 1> acc;
+  acc.zero();
+  const int warp = threadIdx.x >> 5;
+  for (int kb = J + s; kb < nb; kb += APPEND_KS) {
+    __syncthreads();
+    load_tile<LD_R>(sT, M + (int64_t)kb * TB * ld + (int64_t)J * TB, ld);
+    load_tile<LD_C, NP>(sC, w.Ct + (int64_t)kb * TB, mpad);
+    __syncthreads();
+    warp_mma<2, 1, true, false>(acc, sC, sT, 0, warp * 8);
+  }
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int r = 8 * i + g, c = J * TB + warp * 8 + 2 * t;
+    double* o = w.part + ((int64_t)s * NP + r) * mpad + c;
+    o[0] = acc.v[i][0][0];
+    o[1] = acc.v[i][0][1];
+  }
+}
+
+// Write the n new rows of M, extend x, y, z.  grid: ceil(mpad_new / 256).
+__global__ void k_append_finalize(double* __restrict__ M, int64_t ld, int m, int n, int mpad_old, int mpad_new, ApWork w,
+                                  const double* __restrict__ xB, const double* __restrict__ yB, double* __restrict__ x,
+                                  double* __restrict__ y, double* __restrict__ z) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= mpad_new) return;
+  for (int i = 0; i < n; ++i) {
+    double v;
+    if (j < m) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < APPEND_KS; ++q) s += w.part[((int64_t)q * NP + i) * mpad_old + j];
+      v = -s;
+    } else if (j < m + n) {
+      v = w.Li[i * NP + (j - m)];
+    } else {
+      v = 0.0;
+    }
+    M[(int64_t)(m + i) * ld + j] = v;
+  }
+  if (j < n) {
+    x[m + j] = xB[j];
+    y[m + j] = yB[j];
+    z[m + j] = w.znew[j];
+  }
+}
+
+inline void update_set_attributes() {
+  cudaFuncSetAttribute(k_rm_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_PREP_SMEM);
+  cudaFuncSetAttribute(k_rm_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_APPLY_SMEM);
+  cudaFuncSetAttribute(k_append_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_ROWS_SMEM);
+}
+
+}  // namespace mogp

@@ -1,0 +1,226 @@
+"""`GPobs` — one cluster's GP, the drop-in boundary of the reference (mogp/obsmodel.py:6-94).
+
+Same constructor, attributes (`model, ll, X, Y, tempX, tempY, templl`) and methods
+(`calc_ll, update_data, calc_score, get_pred_at_loc, update_suffstats`); `.model` stands in for
+the `GPy.models.GPRegression` object as far as the reference's callers use it
+(`log_likelihood, set_XY, log_predictive_density, predict, optimize, normalizer, model[i]`).
+Every number comes from a cluster slot of the CUDA engine (include/mogp_b200.h).
+"""
+import numpy as np
+from scipy import optimize as _sciopt
+
+from . import _capi
+
+
+class Standardize:
+    """GPy.util.normalizer.Standardize as used at mogp_constrained.py:155-158."""
+
+    def __init__(self, mean=None, std=None):
+        self.mean = mean
+        self.std = std
+
+    def inverse_mean(self, X):
+        return X * self.std + self.mean
+
+    def inverse_variance(self, var):
+        return var * (self.std ** 2)
+
+
+def _col(a):
+    return np.asarray(a, dtype=np.float64).reshape(-1, 1)
+
+
+class GPModel:
+    """Device-backed stand-in for the GPRegression object held by `GPobs.model`.
+
+    Parameter order = GPy's (mean function, kernel, likelihood), SURVEY.md §2.3:
+        rbf    : [neg_linmap.A, rbf.variance, rbf.lengthscale, Gaussian_noise.variance]
+        linear : [neg_linmap.A, sum.linear.variances, sum.bias.variance, Gaussian_noise.variance]
+    without the leading A when mean_func=False (obsmodel.py:48-49).
+    """
+
+    def __init__(self, engine, spec, theta, slot=None, X=None, Y=None):
+        self._engine = engine
+        self._spec = spec
+        self.normalizer = None
+        self.n_evals = 0
+        self._fail_count = 0
+        self._last_grad = None
+        self._slot = engine.cluster_create(spec, theta) if slot is None else slot
+        self._owns_slot = slot is None
+        if X is not None:
+            self.set_XY(X, Y)
+
+    # ---- structure -------------------------------------------------------------------------
+    @property
+    def slot(self):
+        return self._slot
+
+    @property
+    def mean_func(self):
+        return bool(self._spec.mean_func)
+
+    @property
+    def kernel_name(self):
+        return 'rbf' if self._spec.kernel == _capi.KERNEL_RBF else 'linear'
+
+    @property
+    def param_names(self):
+        k = ['rbf.variance', 'rbf.lengthscale'] if self.kernel_name == 'rbf' else \
+            ['sum.linear.variances', 'sum.bias.variance']
+        return (['neg_linmap.A'] if self.mean_func else []) + k + ['Gaussian_noise.variance']
+
+    @property
+    def param_array(self):
+        th = self._engine.cluster_get_theta(self._slot)
+        return th if self.mean_func else th[1:]
+
+    def __getitem__(self, i):
+        return self.param_array[i]
+
+    @property
+    def X(self):
+        return self._engine.cluster_get_data(self._slot)[0].reshape(-1, 1)
+
+    @property
+    def Y(self):
+        return self._engine.cluster_get_data(self._slot)[1].reshape(-1, 1)
+
+    # ---- the five GPy calls of obsmodel.py ---------------------------------------------------
+    def set_XY(self, X, Y):                                       # obsmodel.py:73,92
+        self._engine.cluster_set_data(self._slot, X, Y)
+
+    def log_likelihood(self):                                     # obsmodel.py:56,65
+        return self._engine.cluster_loglik(self._slot)
+
+    def log_predictive_density(self, x_test, y_test, Y_metadata=None):   # obsmodel.py:80
+        return self._engine.cluster_lpd(self._slot, x_test, y_test).reshape(-1, 1)
+
+    def predict(self, Xnew):                                      # obsmodel.py:85
+        mu, var = self._engine.cluster_predict(self._slot, Xnew)
+        mu, var = mu.reshape(-1, 1), var.reshape(-1, 1)
+        if self.normalizer is not None:
+            mu = self.normalizer.inverse_mean(mu)
+            var = self.normalizer.inverse_variance(var)
+        return mu, var
+
+    def objective_function(self):
+        return self._engine.cluster_objective(self._slot, None, want_grad=False)[0]
+
+    def objective_grads(self, t):
+        """paramz Model._objective_grads: (f, df/dt) in Logexp space; a non-PD covariance returns a huge
+        objective up to 10 times in a row, as paramz does."""
+        self.n_evals += 1
+        try:
+            f, g = self._engine.cluster_objective(self._slot, t)
+            self._fail_count = 0
+            self._last_grad = g
+        except np.linalg.LinAlgError:
+            if self._fail_count >= 10:
+                raise
+            self._fail_count += 1
+            f = np.finfo(np.float64).max
+            g = np.clip(self._last_grad if self._last_grad is not None else np.zeros(len(t)), -1e10, 1e10)
+        return f, g
+
+    def optimize(self):                                           # obsmodel.py:94, mogp_constrained.py:333
+        """paramz Model.optimize() default = scipy L-BFGS-B (maxfun = maxiter = 1000, m=10, factr=1e7,
+        pgtol=1e-5), warm-started at the current hyper-parameters; then f(x_opt) and a final set."""
+        if self._engine.cluster_n_free(self._slot) == 0:
+            return
+        t0 = self._engine.cluster_optimizer_array(self._slot)
+        x_opt, _f, _d = _sciopt.fmin_l_bfgs_b(self.objective_grads, t0, maxfun=1000, maxiter=1000)
+        self.objective_grads(x_opt)
+        self._engine.cluster_objective(self._slot, x_opt, want_grad=False)
+
+    def plot_mean(self, *a, **k):
+        raise NotImplementedError("GPy/matplotlib plotting is outside the likelihood engine")
+
+    plot_confidence = plot_mean
+
+    def release(self):
+        if self._owns_slot and self._slot is not None:
+            try:
+                self._engine.cluster_free(self._slot)
+            except Exception:
+                pass
+            self._slot = None
+
+    def __del__(self):
+        self.release()
+
+    # ---- pickling (joblib.dump of the whole sampler, mogp_constrained.py:174-179) ----------------
+    def __getstate__(self):
+        x, y = self._engine.cluster_get_data(self._slot)
+        s = self._spec
+        return dict(theta=self._engine.cluster_get_theta(self._slot), x=x, y=y, normalizer=self.normalizer,
+                    spec=(s.kernel, s.mean_func, s.signal_variance_fix, s.noise_variance_fix))
+
+    def __setstate__(self, st):
+        self._engine = _capi.default_engine()
+        self._spec = _capi.ModelSpec(*st['spec'])
+        self.normalizer = st['normalizer']
+        self.n_evals, self._fail_count, self._last_grad = 0, 0, None
+        self._slot = self._engine.cluster_create(self._spec, st['theta'])
+        self._owns_slot = True
+        self.set_XY(st['x'], st['y'])
+
+
+def make_spec(kernel, mean_func, signal_variance_fix, noise_variance_fix):
+    if kernel not in _capi.KERNEL_CODE:
+        raise ValueError("Implemented kernels limited to 'rbf' or 'linear'. Was " + str(kernel))
+    return _capi.ModelSpec(_capi.KERNEL_CODE[kernel], int(bool(mean_func)), int(bool(signal_variance_fix)),
+                           int(bool(noise_variance_fix)))
+
+
+def initial_theta(kernel, signal_variance, noise_variance, lengthscale, a_draw):
+    """Starting hyper-parameters of a fresh GPobs (obsmodel.py:25-54): A0 = |randn| (GPy.mappings.Linear draw
+    mapped to the positive side by the Logexp constraint), l0 = lengthscale (4), Bias variance 1."""
+    k1 = float(lengthscale) if kernel == 'rbf' else 1.0
+    return np.array([abs(float(a_draw)) if a_draw is not None else 0.0, float(signal_variance), k1,
+                     float(noise_variance)])
+
+
+class GPobs:
+    """Reference signature: obsmodel.py:7-8."""
+
+    def __init__(self, X, Y, kernel='rbf', signal_variance=1., signal_variance_fix=True, noise_variance=1.,
+                 noise_variance_fix=False, mean_func=True, lengthscale=4., engine=None, _slot=None):
+        engine = engine or _capi.default_engine()
+        spec = make_spec(kernel, mean_func, signal_variance_fix, noise_variance_fix)
+        if _slot is not None:               # view of a slot the chain engine already manages
+            self.model = GPModel(engine, spec, None, slot=_slot)
+            self.X, self.Y = None, None
+        else:
+            # GPy.mappings.Linear.__init__ draws A from the global generator (neg_linear.py:19-20)
+            a_draw = np.random.randn(1, 1)[0, 0] if mean_func else None
+            theta = initial_theta(kernel, signal_variance, noise_variance, lengthscale, a_draw)
+            self.model = GPModel(engine, spec, theta, X=_col(X), Y=_col(Y))
+            self.X, self.Y = X, Y
+        self.ll = self.model.log_likelihood()                      # obsmodel.py:56
+        self.tempX = None
+        self.tempY = None
+        self.templl = None
+
+    def calc_ll(self):                                             # obsmodel.py:63-66
+        self.ll = self.model.log_likelihood()
+        return self.ll
+
+    def update_data(self, X, Y):                                   # obsmodel.py:68-73
+        self.X, self.Y = X, Y
+        self.model.set_XY(_col(X), _col(Y))
+
+    def calc_score(self, Xnew, Ynew):                              # obsmodel.py:75-81
+        X, Y = (self.model.X, self.model.Y) if self.X is None else (_col(self.X), _col(self.Y))
+        self.tempX = np.vstack([X, _col(Xnew)])
+        self.tempY = np.vstack([Y, _col(Ynew)])
+        return np.sum(self.model.log_predictive_density(_col(Xnew), _col(Ynew), None))
+
+    def get_pred_at_loc(self, Xnew, index=0):                      # obsmodel.py:83-85
+        return self.model.predict(np.asarray(Xnew)[index].reshape(-1, 1))
+
+    def update_suffstats(self, optimize_params=True):              # obsmodel.py:87-94
+        self.X, self.Y = self.tempX, self.tempY
+        self.model.set_XY(self.X, self.Y)
+        if optimize_params:
+            self.model.optimize()

@@ -1,0 +1,49 @@
+"""Synthetic sparse ALSFRS-R-shaped trajectories for tests and bench.py.
+
+Per patient: n_visits ~ U{3..10}; first visit t0 ~ U(0.2, 3) years after onset, later visits spread so that
+all t are in (0, 8]; a trajectory family (linear decline / early sigmoid / late sigmoid) with a per-patient
+rate; y = clip(round(f(t) + N(0, 1.5^2)), 0, 48); onset anchor (x=0, y=48) prepended
+(analysis/process_data_for_mogp_experiments.py:33-36); NaN-padded to T = 11 columns.
+"""
+import numpy as np
+
+
+def alsfrs_like(n_patients, seed=0, max_visits=10, min_visits=3, anchor=True):
+    rs = np.random.RandomState(seed)
+    T = max_visits + (1 if anchor else 0)
+    X = np.full((n_patients, T), np.nan)
+    Y = np.full((n_patients, T), np.nan)
+    for i in range(n_patients):
+        nv = rs.randint(min_visits, max_visits + 1)
+        t0 = rs.uniform(0.2, 3.0)
+        gaps = rs.uniform(0.1, 1.0, nv - 1)
+        t = np.concatenate([[t0], t0 + np.cumsum(gaps)])
+        if t[-1] > 8.0:
+            t = t0 + (t - t0) * (8.0 - t0) / (t[-1] - t0)
+        fam = rs.randint(3)
+        rate = rs.uniform(0.5, 1.5)
+        if fam == 0:
+            f = 48.0 - 6.0 * rate * t
+        elif fam == 1:
+            f = 48.0 / (1.0 + np.exp(2.0 * rate * (t - 1.5)))
+        else:
+            f = 48.0 / (1.0 + np.exp(1.5 * rate * (t - 4.0)))
+        y = np.clip(np.round(f + rs.randn(nv) * 1.5), 0, 48)
+        o = 1 if anchor else 0
+        if anchor:
+            X[i, 0], Y[i, 0] = 0.0, 48.0
+        X[i, o:o + nv] = t
+        Y[i, o:o + nv] = y
+    return X, Y
+
+
+def block_init(n_patients, n_clusters, X=None):
+    """A deterministic initial partition with n_clusters roughly equal clusters: patients ranked by their
+    first real visit time (the quantity the reference's k-means init clusters on) and cut into quantile blocks."""
+    if X is None:
+        return (np.arange(n_patients) * n_clusters // n_patients).astype(np.int32)
+    col = 1 if X.shape[1] > 1 else 0
+    order = np.argsort(X[:, col], kind='stable')
+    z = np.empty(n_patients, dtype=np.int32)
+    z[order] = (np.arange(n_patients) * n_clusters // n_patients).astype(np.int32)
+    return z

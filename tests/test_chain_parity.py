@@ -1,0 +1,175 @@
+"""GPU parity of the Gibbs chain: teacher-forced steps (L2), the reference tutorial's golden trace
+free-running on the engine (L3), the rank-update fast path against the refactorising oracle, and the
+reference's own smoke tests (mogp/test_package.py)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import tutorial_data, TUTORIAL_Z0_BLOCK
+from test_oracle_kat import TRACE_1_9, Z_FINAL_10
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from mogp_b200 import _capi
+    e = _capi.Engine(0)
+    yield e
+    e.close()
+
+
+def _theta_of(model):
+    th = np.zeros(4)
+    th[(0 if model.mean_func else 1):] = model.param_array
+    return th
+
+
+def test_teacher_forced_steps_tutorial(eng, single_blas_thread):
+    """Engine fed the oracle's state: same p vector (<=1e-9), same active ids, same counts, every step."""
+    from mogp_b200 import MoGP_constrained
+    X, Y = tutorial_data()
+    z0 = np.tile(np.array(TUTORIAL_Z0_BLOCK), 3)
+    orc = oracle.MoGP_constrained(X=X, Y=Y, alpha=1., num_iter=3, rand_seed=0, normalize=True, init_z=z0)
+    orc.initialize_sampler(orc.num_init_clusters, True)
+    orc.allocmodel.calc_suffstats(orc.z)
+    orc.step_log = []
+    mix = MoGP_constrained(X=X, Y=Y, alpha=1., num_iter=3, rand_seed=0, normalize=True, init_z=z0, engine=eng)
+    mix.initialize_sampler(mix.num_init_clusters, True)       # consumes the same 5 randn draws
+    worst = 0.0
+    for sweep in range(2):
+        rs_state = np.random.get_state()
+        perm = np.random.permutation(np.arange(60))
+        for n in perm:
+            # draws the oracle is about to consume, replayed for the engine
+            st = np.random.get_state()
+            a = np.random.randn(1, 1)[0, 0]
+            u = np.random.random_sample()
+            np.random.set_state(st)
+            orc.gibbs_step(n)
+            rec = orc.step_log[-1]
+            eng.chain_step_begin(n)
+            ids, score = eng.chain_step_score(a)
+            from mogp_b200._capi import host_choice
+            idx, p, _margin = host_choice(score, u)
+            assert list(ids) == list(rec['active'])
+            worst = max(worst, np.max(np.abs(p - rec['p'])))
+            assert np.max(np.abs(p - rec['p'])) < 1e-9
+            assert ids[idx] == rec['z']
+            is_new = eng.chain_step_commit(rec['z'], a)
+            # teacher forcing: adopt the oracle's post-refit hyper-parameters
+            _z, Nk, slots = eng.chain_state(60)
+            assert list(Nk) == list(orc.allocmodel.Nk)
+            if not is_new:
+                eng.cluster_set_theta(int(slots[rec['z']]), _theta_of(orc.obsmodel[rec['z']].model))
+                assert abs(eng.cluster_loglik(int(slots[rec['z']])) - orc.obsmodel[rec['z']].model.log_likelihood()) \
+                    <= 1e-9 * abs(orc.obsmodel[rec['z']].model.log_likelihood())
+    print("worst |dp| over teacher-forced steps:", worst)
+
+
+def test_tutorial_chain_reproduces_the_notebook(eng):
+    """L3: the free-running engine chain prints the reference notebook's trace
+    (example/tutorial_train_mogp_model.ipynb:L117-127, L201-203, L272-289)."""
+    from mogp_b200 import MoGP_constrained
+    X, Y = tutorial_data()
+    z0 = np.tile(np.array(TUTORIAL_Z0_BLOCK), 3)
+    mix = MoGP_constrained(X=X, Y=Y, alpha=1., num_iter=10, rand_seed=0, normalize=True, init_z=z0, engine=eng)
+    mix.sample()
+    assert list(mix.init_occupancy) == [30, 6, 12, 6, 6]
+    assert [list(t) for t in mix.trace] == TRACE_1_9
+    assert list(mix.z) == Z_FINAL_10
+    assert list(np.where(mix.allocmodel.Nk > 0)[0]) == [0, 1, 3]
+    m = mix.obsmodel[0].model
+    assert m.param_names == ['neg_linmap.A', 'rbf.variance', 'rbf.lengthscale', 'Gaussian_noise.variance']
+    assert m[0] == pytest.approx(0.28341388, abs=5e-8)
+    assert m[1] == 1.0
+    assert m[2] == pytest.approx(1.5770597538950126, rel=1e-6)
+    assert m[3] == pytest.approx(0.013348237935366946, rel=1e-6)
+    assert m.objective_function() == pytest.approx(-37.289086611673795, rel=1e-9)
+    print("min draw margin:", mix.min_margin)
+
+
+@pytest.mark.parametrize("kernel,mean_func,threshold", [('rbf', True, 0.5), ('rbf', False, None), ('linear', True, None)])
+def test_fast_sweeps_match_oracle(eng, kernel, mean_func, threshold, single_blas_thread):
+    """refit='sweep': the engine's rank-n up/down-dates + leave-block-out score against the oracle, which
+    refactorises on every move as the reference does. Same assignments, same counts, LMLs to 1e-9."""
+    from mogp_b200 import MoGP_constrained
+    from mogp_b200.synth import alsfrs_like, block_init
+    N = 120
+    X, Y = alsfrs_like(N, seed=3)
+    z0 = block_init(N, 4, X)
+    kw = dict(alpha=0.9, num_iter=4, rand_seed=1, normalize=True, kernel=kernel, mean_func=mean_func,
+              threshold=threshold, noise_variance=0.5, refit='sweep', init_z=z0)
+    orc = oracle.MoGP_constrained(X=X.copy(), Y=Y.copy(), **kw)
+    orc.sample()
+    mix = MoGP_constrained(X=X.copy(), Y=Y.copy(), engine=eng, **kw)
+    mix.sample()
+    print("min draw margin:", mix.min_margin, "traces:", [list(t) for t in mix.trace])
+    assert [list(t) for t in mix.trace] == [list(t) for t in orc.trace]
+    assert list(mix.z) == list(orc.z)
+    assert list(mix.allocmodel.Nk) == list(orc.allocmodel.Nk)
+    assert np.allclose(mix.lobs, orc.lobs, rtol=1e-6)
+    assert np.allclose(mix.lalloc, orc.lalloc, rtol=1e-13)
+
+
+def test_reference_smoke_nan_rows(eng):
+    """mogp/test_package.py:30-46 — NaN in the middle / at the end of a row, one initial cluster."""
+    from mogp_b200 import MoGP_constrained
+    X = np.array([[0., 1., 2., 3.], [0., 1., np.nan, 3.], [0., 1., 2., np.nan]])
+    Y = np.array([[48., 40., 35., 30.], [48., 41., np.nan, 28.], [48., 39., 33., np.nan]])
+    mix = MoGP_constrained(X=X, Y=Y, alpha=1., num_iter=5, rand_seed=0, normalize=True, num_init_clusters=1,
+                           engine=eng)
+    mix.sample()
+    assert mix.allocmodel.Nk.sum() == 3
+    orc = oracle.MoGP_constrained(X=X, Y=Y, alpha=1., num_iter=5, rand_seed=0, normalize=True, num_init_clusters=1)
+    orc.sample()
+    assert list(mix.z) == list(orc.z)
+
+
+def test_predict_and_rank(eng):
+    """MoGP_constrained.predict / utils.rank_cluster_prediction (mogp_constrained.py:312-347, utils.py:9-29;
+    query of mogp/test_package.py:57-58) against the oracle on the same fitted state."""
+    from mogp_b200 import MoGP_constrained, utils
+    X, Y = tutorial_data()
+    z0 = np.tile(np.array(TUTORIAL_Z0_BLOCK), 3)
+    kw = dict(alpha=1., num_iter=4, rand_seed=0, normalize=True, init_z=z0)
+    orc = oracle.MoGP_constrained(X=X, Y=Y, **kw)
+    orc.sample()
+    mix = MoGP_constrained(X=X, Y=Y, engine=eng, **kw)
+    mix.sample()
+    assert list(mix.z) == list(orc.z)
+    # same hyper-parameters on both sides, then compare predict()
+    _z, _Nk, slots = eng.chain_state(60)
+    for k in np.where(orc.allocmodel.Nk > 0)[0]:
+        eng.cluster_set_theta(int(slots[k]), _theta_of(orc.obsmodel[k].model))
+    x_new, y_new = np.array([0.25, 0.5, 1, 2.4]), np.array([46., 44., 41., 19.])
+    np.random.seed(11)
+    po = orc.predict(x_new, y_new)
+    np.random.seed(11)
+    pe = mix.predict(x_new, y_new)
+    assert pe.shape == po.shape
+    assert np.max(np.abs(pe - po)) < 1e-9
+    np.random.seed(11)
+    ro = oracle.rank_cluster_prediction(orc, x_new, y_new)
+    np.random.seed(11)
+    re = utils.rank_cluster_prediction(mix, x_new, y_new)
+    assert list(ro[0]) == list(re[0])
+
+
+def test_pickle_roundtrip(eng, tmp_path):
+    """joblib checkpoints (mogp_constrained.py:174-179, 289-310): dump, load, predict from the loaded model."""
+    import joblib
+    from mogp_b200 import MoGP_constrained
+    X, Y = tutorial_data()
+    z0 = np.tile(np.array(TUTORIAL_Z0_BLOCK), 3)
+    mix = MoGP_constrained(X=X, Y=Y, alpha=1., num_iter=3, rand_seed=0, normalize=True, init_z=z0,
+                           savepath=tmp_path, savename='m', engine=eng)
+    mix.sample()
+    assert (tmp_path / 'm_iterinit.pkl').exists() and (tmp_path / 'm.pkl').exists()
+    loaded = joblib.load(tmp_path / 'm.pkl')
+    k = int(np.where(loaded.allocmodel.Nk > 0)[0][0])
+    xs = np.linspace(0, 6, 9).reshape(-1, 1)
+    m0, v0 = mix.obsmodel[k].model.predict(xs)
+    m1, v1 = loaded.obsmodel[k].model.predict(xs)
+    assert np.allclose(m0, m1, rtol=1e-12) and np.allclose(v0, v1, rtol=1e-12)
+    assert loaded.obsmodel[k].model.normalizer is not None
