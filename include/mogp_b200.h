@@ -95,6 +95,9 @@ int mogp_cluster_remove_rows(mogp_engine* h, int32_t slot, int64_t p, int64_t n)
 int mogp_cluster_leave_out_score(mogp_engine* h, int32_t slot, int64_t p, int64_t n, int32_t thr_index,
                                  double* score, double* mu_thr);
 int64_t mogp_cluster_size(mogp_engine* h, int32_t slot);
+/* Diagnostics: the m x m inverse Cholesky factor M = chol(K + (noise + 1e-8) I)^-1 (row-major, lower) and
+   alpha = Ky^-1 (y - m(x)) as currently held on the device.  Either output may be NULL. */
+int mogp_cluster_get_factor(mogp_engine* h, int32_t slot, double* M_out, double* alpha_out);
 int mogp_cluster_get_data(mogp_engine* h, int32_t slot, double* x, double* y);
 /* model.log_likelihood() (obsmodel.py:56,65): log marginal likelihood, no prior term. */
 int mogp_cluster_loglik(mogp_engine* h, int32_t slot, double* lml);

@@ -58,6 +58,7 @@ SIGNATURES = {
     "mogp_cluster_append": (C.c_int, [_H, C.c_int32, C.c_int64, _dp, _dp]),
     "mogp_cluster_remove_rows": (C.c_int, [_H, C.c_int32, C.c_int64, C.c_int64]),
     "mogp_cluster_size": (C.c_int64, [_H, C.c_int32]),
+    "mogp_cluster_get_factor": (C.c_int, [_H, C.c_int32, _dp, _dp]),
     "mogp_cluster_get_data": (C.c_int, [_H, C.c_int32, _dp, _dp]),
     "mogp_cluster_loglik": (C.c_int, [_H, C.c_int32, _dp]),
     "mogp_cluster_objective": (C.c_int, [_H, C.c_int32, _dp, C.c_int32, _dp, _dp]),
@@ -198,6 +199,12 @@ class Engine:
         x, y = np.empty(m), np.empty(m)
         self.check(self.lib.mogp_cluster_get_data(self.h, slot, dptr(x), dptr(y)))
         return x, y
+
+    def cluster_get_factor(self, slot):
+        m = self.cluster_size(slot)
+        M, alpha = np.empty((m, m)), np.empty(m)
+        self.check(self.lib.mogp_cluster_get_factor(self.h, slot, dptr(M), dptr(alpha)))
+        return np.tril(M), alpha      # tiles above the diagonal are never written on the device
 
     def cluster_get_theta(self, slot):
         th = np.empty(4)

@@ -8,9 +8,11 @@ int pool_get(mogp_engine* h, int64_t cap, double** out) {
     if (h->pool[i].first == cap) {
       *out = h->pool[i].second;
       h->pool.erase(h->pool.begin() + i);
+      if (poison_enabled()) CK(h, cudaMemsetAsync(*out, 0xFF, sizeof(double) * (size_t)(cap * cap + 4 * cap + 16), h->stream));
       return MOGP_OK;
     }
   CK(h, cudaMalloc((void**)out, sizeof(double) * (size_t)(cap * cap + 4 * cap + 16)));
+  if (poison_enabled()) CK(h, cudaMemsetAsync(*out, 0xFF, sizeof(double) * (size_t)(cap * cap + 4 * cap + 16), h->stream));
   return MOGP_OK;
 }
 void pool_put(mogp_engine* h, int64_t cap, double* buf) {
@@ -38,7 +40,7 @@ int fetch_stat(mogp_engine* h, Cluster& c) {
   if (!c.stat_on_device) return MOGP_OK;
   TRY(ensure_pin(h, 256));
   CK(h, cudaMemcpyAsync(h->pin, c.stat(), sizeof(double) * 9, cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, sync_stream(h));
   const double* hs = reinterpret_cast<const double*>(h->pin);
   int hinfo;
   memcpy(&hinfo, hs + 8, sizeof(int));

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -111,9 +112,14 @@ struct mogp_engine {
   int64_t qoff_elems = 0;
   double* d_out = nullptr;  // outputs staged on the device before the copy back
   int64_t out_elems = 0;
-  // pinned host staging
+  // pinned host staging: pin = small read-backs (always synchronised at once); pin_dn = bulk read-backs
+  // (same); pin_up = uploads, bump-allocated so that no range is rewritten before the stream has consumed it
   char* pin = nullptr;
   size_t pin_bytes = 0;
+  char* pin_dn = nullptr;
+  size_t dn_bytes = 0;
+  char* pin_up = nullptr;
+  size_t up_bytes = 0, up_off = 0;
   Chain chain;
   // update workspace (update.cuh)
   double* d_upd = nullptr;
@@ -148,6 +154,17 @@ namespace {
 
 #define LAUNCHED(h) ((h)->launches++)
 
+// MOGP_DEBUG_POISON=1 fills every fresh device buffer with NaN bit patterns, so that a read of memory
+// no kernel has written shows up in the results (debugging aid; off by default).
+bool poison_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MOGP_DEBUG_POISON");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 template <typename T>
 int ensure(mogp_engine* h, T** p, int64_t* have, int64_t need) {
   if (need <= *have) return MOGP_OK;
@@ -156,6 +173,7 @@ int ensure(mogp_engine* h, T** p, int64_t* have, int64_t need) {
   *have = 0;
   int64_t want = need + need / 4;
   CK(h, cudaMalloc((void**)p, sizeof(T) * (size_t)want));
+  if (poison_enabled()) CK(h, cudaMemsetAsync(*p, 0xFF, sizeof(T) * (size_t)want, h->stream));
   *have = want;
   return MOGP_OK;
 }
@@ -168,6 +186,43 @@ int ensure_pin(mogp_engine* h, size_t need) {
   size_t want = need + need / 2 + 4096;
   CK(h, cudaMallocHost((void**)&h->pin, want));
   h->pin_bytes = want;
+  return MOGP_OK;
+}
+
+// Every wait on the stream goes through here: afterwards the upload staging can be reused from the start.
+cudaError_t sync_stream(mogp_engine* h) {
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  h->up_off = 0;
+  return e;
+}
+
+// A fresh range of the upload staging buffer; valid until the next sync_stream().
+int stage_alloc(mogp_engine* h, size_t bytes, char** out) {
+  bytes = (bytes + 255) / 256 * 256;
+  if (h->up_off + bytes > h->up_bytes) {
+    CK(h, sync_stream(h));
+    if (bytes > h->up_bytes) {
+      if (h->pin_up) CK(h, cudaFreeHost(h->pin_up));
+      h->pin_up = nullptr;
+      h->up_bytes = 0;
+      size_t want = std::max<size_t>(bytes * 2, (size_t)1 << 20);
+      CK(h, cudaMallocHost((void**)&h->pin_up, want));
+      h->up_bytes = want;
+    }
+  }
+  *out = h->pin_up + h->up_off;
+  h->up_off += bytes;
+  return MOGP_OK;
+}
+
+int ensure_dn(mogp_engine* h, size_t need) {
+  if (need <= h->dn_bytes) return MOGP_OK;
+  if (h->pin_dn) CK(h, cudaFreeHost(h->pin_dn));
+  h->pin_dn = nullptr;
+  h->dn_bytes = 0;
+  size_t want = need + need / 2 + 4096;
+  CK(h, cudaMallocHost((void**)&h->pin_dn, want));
+  h->dn_bytes = want;
   return MOGP_OK;
 }
 
@@ -258,7 +313,7 @@ int infer(mogp_engine* h, Cluster& c) {
     k_lml<<<1, 1024, 0, h->stream>>>(c.M, ld, c.z(), c.x(), c.alpha(), (int)c.m, st);
     LAUNCHED(h);
     CK(h, cudaMemcpyAsync(h->pin, st, sizeof(double) * 9, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, sync_stream(h));
     CK(h, cudaGetLastError());
     const double* hs = reinterpret_cast<const double*>(h->pin);
     int hinfo;
@@ -301,7 +356,7 @@ int infer_grad(mogp_engine* h, Cluster& c) {
   k_grad_final<<<1, 256, 0, h->stream>>>(h->d_partial, (int)n_partial, th, st, st + 10);
   LAUNCHED(h);
   CK(h, cudaMemcpyAsync(h->pin, st + 10, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, sync_stream(h));
   CK(h, cudaGetLastError());
   memcpy(c.grad, h->pin, sizeof(double) * 4);
   c.grad_valid = true;
@@ -313,9 +368,9 @@ int upload_data(mogp_engine* h, Cluster& c, int64_t m, const double* x, const do
   c.hx.assign(x, x + m);
   c.hy.assign(y, y + m);
   c.m = m;
-  TRY(ensure_pin(h, sizeof(double) * 2 * m + 256));
-  // pin[0..256) is reserved for small read-backs
-  double* stage = reinterpret_cast<double*>(h->pin + 256);
+  char* up = nullptr;
+  TRY(stage_alloc(h, sizeof(double) * 2 * m, &up));
+  double* stage = reinterpret_cast<double*>(up);
   memcpy(stage, x, sizeof(double) * m);
   memcpy(stage + m, y, sizeof(double) * m);
   CK(h, cudaMemcpyAsync(c.x(), stage, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
@@ -380,12 +435,15 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   pl.BN = R <= 8 ? 8 : (R <= 16 ? 16 : (R <= 32 ? 32 : 64));
   pl.Rpad = round_up(R, pl.BN);
   pl.n_slots = n_slots;
-  TRY(ensure_pin(h, 256 + sizeof(SlotView) * (size_t)n_slots));
-  SlotView* hv = reinterpret_cast<SlotView*>(h->pin + 256);
-  for (int s = 0; s < n_slots; ++s) {
+  for (int s = 0; s < n_slots; ++s) {  // (inference synchronises: do it before staging anything)
     TRY(check_slot(h, slots[s]));
+    if (!h->cl[slots[s]].valid) TRY(infer(h, h->cl[slots[s]]));
+  }
+  char* up = nullptr;
+  TRY(stage_alloc(h, sizeof(SlotView) * (size_t)n_slots, &up));
+  SlotView* hv = reinterpret_cast<SlotView*>(up);
+  for (int s = 0; s < n_slots; ++s) {
     Cluster& c = h->cl[slots[s]];
-    if (!c.valid) TRY(infer(h, c));
     SlotView v;
     v.M = c.M;
     v.x = c.x();
@@ -437,10 +495,11 @@ int stage_query(mogp_engine* h, int64_t n_pat, const int64_t* off, const double*
   for (int64_t p = 0; p < n_pat; ++p)
     if (off[p + 1] < off[p]) FAIL(h, MOGP_EINVAL, "offsets must be non-decreasing");
   const size_t bytes = sizeof(int64_t) * (n_pat + 1) + sizeof(double) * (2 * R + n_pat);
-  TRY(ensure_pin(h, 256 + bytes));
   TRY(ensure(h, &h->d_qoff, &h->qoff_elems, n_pat + 1));
   TRY(ensure(h, &h->d_q, &h->q_elems, 2 * R + n_pat));
-  int64_t* so = reinterpret_cast<int64_t*>(h->pin + 256);
+  char* up = nullptr;
+  TRY(stage_alloc(h, bytes, &up));
+  int64_t* so = reinterpret_cast<int64_t*>(up);
   double* sd = reinterpret_cast<double*>(so + n_pat + 1);
   memcpy(so, off, sizeof(int64_t) * (n_pat + 1));
   memcpy(sd, x + base, sizeof(double) * R);
@@ -450,16 +509,14 @@ int stage_query(mogp_engine* h, int64_t n_pat, const int64_t* off, const double*
   else memset(sd + 2 * R, 0, sizeof(double) * n_pat);
   CK(h, cudaMemcpyAsync(h->d_qoff, so, sizeof(int64_t) * (n_pat + 1), cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->d_q, sd, sizeof(double) * (2 * R + n_pat), cudaMemcpyHostToDevice, h->stream));
-  // the pinned buffer is reused by later stagings: finish the copies first
-  CK(h, cudaStreamSynchronize(h->stream));
   return MOGP_OK;
 }
 
 int copy_back(mogp_engine* h, double* dst, const double* src_dev, int64_t n) {
-  TRY(ensure_pin(h, 256 + sizeof(double) * (size_t)n));
-  CK(h, cudaMemcpyAsync(h->pin + 256, src_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));
-  memcpy(dst, h->pin + 256, sizeof(double) * n);
+  TRY(ensure_dn(h, sizeof(double) * (size_t)n));
+  CK(h, cudaMemcpyAsync(h->pin_dn, src_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, sync_stream(h));
+  memcpy(dst, h->pin_dn, sizeof(double) * n);
   return MOGP_OK;
 }
 
@@ -504,7 +561,7 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
 void mogp_engine_destroy(mogp_engine* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  sync_stream(h);
   for (auto& c : h->cl)
     if (c.M) cudaFree(c.M);
   cudaFree(h->d_off);
@@ -521,6 +578,8 @@ void mogp_engine_destroy(mogp_engine* h) {
   cudaFree(h->d_apw);
   for (auto& pb : h->pool) cudaFree(pb.second);
   if (h->pin) cudaFreeHost(h->pin);
+  if (h->pin_dn) cudaFreeHost(h->pin_dn);
+  if (h->pin_up) cudaFreeHost(h->pin_up);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
@@ -532,7 +591,7 @@ int64_t mogp_launch_count(const mogp_engine* h) { return h ? h->launches : 0; }
 
 int mogp_sync(mogp_engine* h) {
   if (!h) return MOGP_EINVAL;
-  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, sync_stream(h));
   return MOGP_OK;
 }
 int mogp_timer_start(mogp_engine* h) {
@@ -573,8 +632,9 @@ int mogp_set_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, co
   CK(h, cudaMalloc((void**)&h->d_off, sizeof(int64_t) * (n_patients + 1)));
   CK(h, cudaMalloc((void**)&h->d_px, sizeof(double) * std::max<int64_t>(V, 1)));
   CK(h, cudaMalloc((void**)&h->d_py, sizeof(double) * std::max<int64_t>(V, 1)));
-  TRY(ensure_pin(h, 256 + sizeof(int64_t) * (n_patients + 1) + sizeof(double) * 2 * V));
-  int64_t* so = reinterpret_cast<int64_t*>(h->pin + 256);
+  char* up = nullptr;
+  TRY(stage_alloc(h, sizeof(int64_t) * (n_patients + 1) + sizeof(double) * 2 * V, &up));
+  int64_t* so = reinterpret_cast<int64_t*>(up);
   double* sd = reinterpret_cast<double*>(so + n_patients + 1);
   memcpy(so, off, sizeof(int64_t) * (n_patients + 1));
   memcpy(sd, x, sizeof(double) * V);
@@ -582,7 +642,7 @@ int mogp_set_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, co
   CK(h, cudaMemcpyAsync(h->d_off, so, sizeof(int64_t) * (n_patients + 1), cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->d_px, sd, sizeof(double) * V, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->d_py, sd + V, sizeof(double) * V, cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));
+  CK(h, sync_stream(h));
   h->chain.active = false;
   return MOGP_OK;
 }
@@ -717,6 +777,22 @@ int mogp_cluster_leave_out_score(mogp_engine* h, int32_t slot, int64_t p, int64_
   if (out[2] != 1.0) FAIL(h, MOGP_ENOTPD, "leave-out block not positive definite");
   if (score) *score = out[0];
   if (mu_thr) *mu_thr = out[1];
+  return MOGP_OK;
+}
+
+int mogp_cluster_get_factor(mogp_engine* h, int32_t slot, double* M_out, double* alpha_out) {
+  TRY(check_slot(h, slot));
+  Cluster& c = h->cl[slot];
+  if (!c.valid) TRY(infer(h, c));
+  if (M_out) {
+    CK(h, cudaMemcpy2DAsync(M_out, c.m * sizeof(double), c.M, c.cap * sizeof(double), c.m * sizeof(double), c.m,
+                            cudaMemcpyDeviceToHost, h->stream));
+    CK(h, sync_stream(h));
+  }
+  if (alpha_out) {
+    CK(h, cudaMemcpyAsync(alpha_out, c.alpha(), c.m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, sync_stream(h));
+  }
   return MOGP_OK;
 }
 

@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(NTHREADS) k_rm_apply(const double* __restrict_
   auto src = [&](int ip, int jp) -> double {
     if (ip >= g.mnew || jp >= g.mnew) return (ip == jp) ? 1.0 : 0.0;
     int i = ip < g.p ? ip : ip + g.n, j = jp < g.p ? jp : jp + g.n;
+    if (j > i) return 0.0;  // strictly upper: tiles above the diagonal are never written, do not read them
     return Mo[(int64_t)i * ld + j];
   };
   // plain copies above the first updated tile
@@ -228,7 +229,8 @@ __global__ void __launch_bounds__(NTHREADS) k_rm_apply(const double* __restrict_
     int jp = J * TB + c;
     if (q < g.n && jp < g.mnew) {
       int j = jp < g.p ? jp : jp + g.n;
-      for (int a = q; a < g.n; ++a) s += Mo[(int64_t)(g.p + a) * ld + g.p + q] * Mo[(int64_t)(g.p + a) * ld + j];
+      for (int a = q; a < g.n; ++a)
+        if (j <= g.p + a) s += Mo[(int64_t)(g.p + a) * ld + g.p + q] * Mo[(int64_t)(g.p + a) * ld + j];
     }
     sB[(TB + q) * LD_R + c] = s;
   }
