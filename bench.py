@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — Gibbs sweeps/sec at 10k patients (BASELINE.json `metric`, configs[2]) on N B200s.
+
+One "step" = one collapsed Gibbs sweep of MoGP_constrained over all patients (mogp_constrained.py:231-284)
+followed by the hyper-parameter refit of every active cluster (refit='sweep', the schedule BASELINE.json names
+for the 10k-patient configuration).  N > 1 runs N independent chains (seed = rank), one per GPU — the
+alpha/seed-sweep sharding of SURVEY.md §8(e); a single chain is strictly sequential ("replicas only").
+
+  value     whole-job sweeps/s, patient table resident in HBM (C-ABI chain calls + host L-BFGS-B driver)
+  e2e       the same through the public API `MoGP_constrained.sweep()` with the patient table re-sent from
+            host memory every sweep and the results (z, Nk, log-likelihoods) read back
+  roofline  the scoring product T = M Kx (k_score_gemm), timed with CUDA events on the engine's stream
+  cpu_baseline / --impl reference   the CPU oracle (NumPy/SciPy restatement of the reference + GPy), on a
+            bounded sample of the same sweep, all host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--patients", type=int, default=10000)
+    ap.add_argument("--clusters", type=int, default=30)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=12, help="patient-steps of the bounded CPU sample")
+    return ap.parse_args()
+
+
+def workload(args, seed):
+    from mogp_b200.synth import alsfrs_like
+    # patients drawn from `clusters` latent progression classes; the chain starts from those classes (the
+    # reference starts from k-means; either way BASELINE's configuration is "~30 active clusters")
+    X, Y, z0 = alsfrs_like(args.patients, seed=seed, n_classes=args.clusters, return_labels=True)
+    z0 = np.unique(z0, return_inverse=True)[1].astype(np.int32)
+    kw = dict(alpha=args.clusters / np.log10(args.patients), num_iter=2, rand_seed=seed, normalize=True, kernel='rbf',
+              mean_func=True, threshold=0.5, signal_variance=1., signal_variance_fix=True, noise_variance=0.5,
+              noise_variance_fix=False, onset_anchor=True, refit='sweep', init_z=z0)
+    return X, Y, kw
+
+
+def config(args):
+    return {"workload": "MoGP_constrained Gibbs sweep, {} synthetic ALSFRS-R-like patients (3-10 visits + onset anchor), "
+                        "{} initial clusters, rbf + neg_linear mean, threshold 0.5, hyper-parameter refit of every active "
+                        "cluster each sweep (BASELINE configs[2])".format(args.patients, args.clusters),
+            "patients": args.patients, "init_clusters": args.clusters, "refit": "sweep",
+            "cache": "inputs larger than L2: the resident cluster factors total > 700 MB vs 126 MB of L2",
+            "parallelism": "independent chains, one per GPU (seed = rank)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        if not sm:
+            return None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+def oracle_sample(args, n_steps, refit_clusters=1, seed=0):
+    """Time the CPU oracle on a bounded sample of the sweep: n_steps consecutive patient-steps from the same
+    initial state + the L-BFGS-B refit of `refit_clusters` clusters; extrapolate to sweeps/s."""
+    import oracle
+    X, Y, kw = workload(args, seed)
+    t0 = time.perf_counter()
+    orc = oracle.MoGP_constrained(X=X, Y=Y, **kw)
+    orc.initialize_sampler(orc.num_init_clusters, True)
+    orc.allocmodel.calc_suffstats(orc.z)
+    t_init = time.perf_counter() - t0
+    return orc, t_init
+
+
+def oracle_step_times(orc, n_steps, refit_clusters):
+    perm = np.random.permutation(np.arange(orc.allocmodel.N))[:n_steps]
+    t0 = time.perf_counter()
+    for n in perm:
+        orc.gibbs_step(n)
+    t_step = (time.perf_counter() - t0) / max(n_steps, 1)
+    act = np.where(orc.allocmodel.Nk > 0)[0]
+    t0 = time.perf_counter()
+    evals = 0
+    for k in act[:refit_clusters]:
+        m = orc.obsmodel[k].model
+        e0 = m.n_evals
+        m.optimize()
+        evals += m.n_evals - e0
+    t_refit = (time.perf_counter() - t0) / max(refit_clusters, 1)
+    return t_step, t_refit, len(act), evals
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = os.cpu_count()
+    orc, t_init = oracle_sample(args, 0)
+    N = args.patients
+    per_step = max(2, args.cpu_steps // 3)
+    times = []
+    for it in range(args.warmup + args.steps):
+        ts, tr, nact, evals = oracle_step_times(orc, per_step, 1)
+        if it >= args.warmup:
+            times.append(N * ts + nact * tr)
+    sweep_s = float(np.mean(times))
+    value = 1.0 / sweep_s
+    sample = ("each step = {} consecutive patient-steps + the L-BFGS-B refit of 1 cluster, from the same initial state; "
+              "sweep time = N*mean(step) + active*refit".format(per_step))
+    line = {"impl": "reference", "metric": "Gibbs sweeps/sec @10k patients", "value": value, "unit": "sweeps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sweep_s * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config(args),
+            "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": ncores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mogp_b200 import _capi, MoGP_constrained
+    from mogp_b200.utils import pack_patients
+
+    eng = _capi.Engine(local)
+    X, Y, kw = workload(args, seed=rank)
+    mix = MoGP_constrained(X=X, Y=Y, engine=eng, **kw)
+    mix.initialize_sampler(args.clusters, True)
+    off, px, py = pack_patients(mix.X, mix.Y)
+    N = args.patients
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_sweep():
+        """value path: C-ABI chain sweep over the resident patient table + refit of every active cluster."""
+        perm, a, u = mix._draws_for_sweep(N)
+        eng.chain_sweep(perm, a, u)
+        mix._sync_state()
+        for k in mix._active():
+            mix.obsmodel[k].model.optimize()
+
+    def e2e_sweep():
+        """public API with host buffers: patient table host->device, sweep, results device->host."""
+        eng.refresh_patients(off, px, py)
+        mix.sweep()
+        lobs = sum(mix.obsmodel[k].calc_ll() for k in mix._active())
+        return float(lobs) + float(mix.allocmodel.calc_ll())
+
+    for _ in range(args.warmup):
+        device_sweep()
+    moved_probe = mix.z.copy()
+
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    eng.profile(True)
+    eng.profile_read(reset=True)
+    eng.timer_start()
+    for _ in range(args.steps):
+        device_sweep()
+    ms = eng.timer_stop()
+    prof = eng.profile_read(reset=True)
+    eng.profile(False)
+    launches = eng.launch_count() - l0
+    barrier()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    moved = int(np.sum(mix.z != moved_probe))
+
+    # e2e
+    barrier()
+    b0 = eng.transfer_bytes()
+    eng.timer_start()
+    for _ in range(args.steps):
+        ll = e2e_sweep()
+    ms_e2e = eng.timer_stop()
+    b1 = eng.transfer_bytes()
+    barrier()
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e_max = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # gather the chains' results (the only collective of this mode)
+    occupancy = [int(v) for v in mix.allocmodel.Nk[mix.allocmodel.Nk > 0]]
+    if world > 1:
+        zt = torch.from_numpy(mix.z.astype(np.int32)).cuda()
+        out = [torch.empty_like(zt) for _ in range(world)]
+        dist.all_gather(out, zt)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else \
+            (6650.0, "fallback (B200_PROFILING.md)")
+        achieved = prof["alg_bytes"] / (prof["ms"] * 1e-3) / 1e9 if prof["ms"] > 0 else None
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "score_gemm_traffic.json"))).get("traffic_bytes_per_launch")
+        except Exception:
+            pass
+        line = {"metric": "Gibbs sweeps/sec @10k patients", "value": world * args.steps / (ms_max * 1e-3), "unit": "sweeps/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config(args),
+                "e2e": {"value": world * args.steps / (ms_e2e_max * 1e-3), "unit": "sweeps/s",
+                        "h2d_bytes_per_step": (b1[0] - b0[0]) // args.steps, "d2h_bytes_per_step": (b1[1] - b0[1]) // args.steps},
+                "gpu_launches": int(launches),
+                "roofline": {"kernel": "k_score_gemm (T = M Kx, FP64 DMMA)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                             "peak_source": peak_src, "launches": prof["launches"],
+                             "avg_launch_us": prof["ms"] / max(prof["launches"], 1) * 1e3,
+                             "alg_bytes_per_launch": prof["alg_bytes"] / max(prof["launches"], 1),
+                             "fp64_tflops": prof["alg_flops"] / (prof["ms"] * 1e-3) / 1e12 if prof["ms"] > 0 else None,
+                             "share_of_step": prof["ms"] / ms},
+                "clocks": clocks,
+                "chain": {"active_clusters": len(occupancy), "patients_moved_in_timed_sweeps": moved,
+                          "pair_logliks_per_s": world * args.steps * N * len(occupancy) / (ms_max * 1e-3),
+                          "refit_evals": int(mix.n_refit_evals), "total_loglik": ll}}
+        if world == 1 and not args.no_cpu_baseline:
+            orc, _t_init = oracle_sample(args, 0)
+            ts, tr, nact, evals = oracle_step_times(orc, args.cpu_steps, 1)
+            sweep_s = N * ts + nact * tr
+            line["cpu_baseline"] = {"value": 1.0 / sweep_s, "unit": "sweeps/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "{} consecutive patient-steps ({:.3f} s each) + L-BFGS-B refit of 1 cluster ({:.2f} s, "
+                                              "{} evaluations) from the same initial state; sweep = N*step + active*refit"
+                                              .format(args.cpu_steps, ts, tr, evals)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,19 @@ int mogp_timer_stop(mogp_engine* h, double* ms_out);
 int mogp_set_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x,
                       const double* y, const double* y_thr);
 
+/* Re-send the same table (same offsets) from host memory without disturbing an attached chain. */
+int mogp_refresh_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x, const double* y);
+
+/* ---- accounting for bench.py ------------------------------------------------------------------ */
+/* Bytes this engine has copied host->device / device->host since creation. */
+int mogp_transfer_bytes(mogp_engine* h, int64_t* h2d, int64_t* d2h);
+/* Device time of the dominant kernel (the scoring product T = M Kx): CUDA events on the engine's stream
+   around every launch while enabled.  *ms = summed launch durations, *alg_bytes / *alg_flops = the
+   algorithmic traffic / work of those launches (per (patient, cluster) pair
+   8 (m^2/2 + 3m) + 16 n + 8 bytes and n m (m + 10) flops). */
+int mogp_profile(mogp_engine* h, int32_t enable);
+int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg_bytes, double* alg_flops, int32_t reset);
+
 /* ---- one cluster's GP = one GPobs object ------------------------------------------------- */
 /* GPobs.__init__ (obsmodel.py:7-61) minus data: allocates a cluster slot. */
 int mogp_cluster_create(mogp_engine* h, const mogp_model_spec* spec, const double theta[4], int32_t* slot_out);

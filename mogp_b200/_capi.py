@@ -49,6 +49,10 @@ SIGNATURES = {
     "mogp_timer_start": (C.c_int, [_H]),
     "mogp_timer_stop": (C.c_int, [_H, _dp]),
     "mogp_set_patients": (C.c_int, [_H, C.c_int64, _lp, _dp, _dp, _dp]),
+    "mogp_refresh_patients": (C.c_int, [_H, C.c_int64, _lp, _dp, _dp]),
+    "mogp_transfer_bytes": (C.c_int, [_H, _lp, _lp]),
+    "mogp_profile": (C.c_int, [_H, C.c_int32]),
+    "mogp_profile_read": (C.c_int, [_H, _lp, _dp, _dp, _dp, C.c_int32]),
     "mogp_cluster_create": (C.c_int, [_H, C.POINTER(ModelSpec), _dp, _ip]),
     "mogp_cluster_free": (C.c_int, [_H, C.c_int32]),
     "mogp_cluster_set_theta": (C.c_int, [_H, C.c_int32, _dp]),
@@ -166,6 +170,30 @@ class Engine:
         x, y = f64(x), f64(y)
         y_thr = None if y_thr is None else f64(y_thr)
         self.check(self.lib.mogp_set_patients(self.h, len(off) - 1, lptr(off), dptr(x), dptr(y), dptr(y_thr)))
+
+    def refresh_patients(self, off, x, y):
+        self.check(self.lib.mogp_refresh_patients(self.h, len(off) - 1, lptr(off), dptr(x), dptr(y)))
+
+    def transfer_bytes(self):
+        a, b = C.c_int64(), C.c_int64()
+        self.check(self.lib.mogp_transfer_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def profile(self, on):
+        self.check(self.lib.mogp_profile(self.h, int(bool(on))))
+
+    def profile_read(self, reset=True):
+        n, ms, by, fl = C.c_int64(), C.c_double(), C.c_double(), C.c_double()
+        self.check(self.lib.mogp_profile_read(self.h, C.byref(n), C.byref(ms), C.byref(by), C.byref(fl), int(reset)))
+        return dict(launches=n.value, ms=ms.value, alg_bytes=by.value, alg_flops=fl.value)
+
+    def timer_start(self):
+        self.check(self.lib.mogp_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self.check(self.lib.mogp_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def cluster_create(self, spec, theta):
         slot = C.c_int32(-1)

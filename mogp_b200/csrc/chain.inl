@@ -41,6 +41,7 @@ int fetch_stat(mogp_engine* h, Cluster& c) {
   TRY(ensure_pin(h, 256));
   CK(h, cudaMemcpyAsync(h->pin, c.stat(), sizeof(double) * 9, cudaMemcpyDeviceToHost, h->stream));
   CK(h, sync_stream(h));
+  h->bytes_d2h += 72;
   const double* hs = reinterpret_cast<const double*>(h->pin);
   int hinfo;
   memcpy(&hinfo, hs + 8, sizeof(int));
@@ -329,6 +330,7 @@ int chain_score(mogp_engine* h, double a_draw) {
     ch.a_dev_val = a_draw;
     TRY(ensure(h, &h->d_q, &h->q_elems, 8));
     CK(h, cudaMemcpyAsync(h->d_q, &ch.a_dev_val, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->bytes_h2d += 8;
     k_new_ll<<<1, 64, 0, h->stream>>>(h->d_off + n, h->d_px + c0, h->d_py + c0, h->d_q, newcomer_theta(ch.cfg), d_newll);
     LAUNCHED(h);
     CK(h, cudaGetLastError());

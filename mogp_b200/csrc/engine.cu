@@ -127,6 +127,13 @@ struct mogp_engine {
   double* d_apw = nullptr;   // append workspace
   int64_t apw_elems = 0;
   std::vector<std::pair<int64_t, double*>> pool;  // free cluster buffers by capacity
+  // accounting (bench.py): bytes moved by the C ABI calls, and device time of the scoring GEMM
+  int64_t bytes_h2d = 0, bytes_d2h = 0;
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop), recycled
+  size_t prof_used = 0;
+  double prof_ms = 0.0, prof_bytes = 0.0, prof_flops = 0.0;
+  int64_t prof_launches = 0;
 };
 
 namespace {
@@ -245,6 +252,12 @@ int check_slot(mogp_engine* h, int32_t slot) {
 
 // Capacity classes (x1.25 steps, multiples of 64) so that buffers can be pooled and ping-ponged.
 int64_t cap_class(int64_t need) {
+  static int64_t forced = -1;  // MOGP_DEBUG_CAP: force one capacity (debugging aid)
+  if (forced < 0) {
+    const char* e = getenv("MOGP_DEBUG_CAP");
+    forced = e ? atoll(e) : 0;
+  }
+  if (forced >= need) return round_up(forced, TB);
   int64_t c = TB;
   while (c < need) c = round_up(c + c / 4, TB);
   return c;
@@ -314,6 +327,7 @@ int infer(mogp_engine* h, Cluster& c) {
     LAUNCHED(h);
     CK(h, cudaMemcpyAsync(h->pin, st, sizeof(double) * 9, cudaMemcpyDeviceToHost, h->stream));
     CK(h, sync_stream(h));
+    h->bytes_d2h += 72;
     CK(h, cudaGetLastError());
     const double* hs = reinterpret_cast<const double*>(h->pin);
     int hinfo;
@@ -335,7 +349,9 @@ int infer(mogp_engine* h, Cluster& c) {
       if (!(d > 0.0)) nonpos = true;
       dsum += d;
     }
-    if (nonpos || attempt >= 5 || !isfinite(dsum)) FAIL(h, MOGP_ENOTPD, "covariance not positive definite (m=%lld)", (long long)c.m);
+    if (nonpos || attempt >= 5 || !isfinite(dsum))
+      FAIL(h, MOGP_ENOTPD, "covariance not positive definite (m=%lld, first bad pivot %d, lml %g, theta %g %g %g %g)",
+           (long long)c.m, hinfo, hs[0], c.theta[0], c.theta[1], c.theta[2], c.theta[3]);
     jitter = (attempt == 0) ? dsum / (double)c.m * 1e-6 : jitter * 10.0;
   }
 }
@@ -375,6 +391,7 @@ int upload_data(mogp_engine* h, Cluster& c, int64_t m, const double* x, const do
   memcpy(stage + m, y, sizeof(double) * m);
   CK(h, cudaMemcpyAsync(c.x(), stage, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(c.y(), stage + m, sizeof(double) * m, cudaMemcpyHostToDevice, h->stream));
+  h->bytes_h2d += (int64_t)sizeof(double) * 2 * m;
   c.valid = false;
   c.grad_valid = false;
   return MOGP_OK;
@@ -411,6 +428,27 @@ void priors_of(const mogp_model_spec& s, Gamma pr[4], bool fixed[4]) {
 }
 
 // ---- scoring --------------------------------------------------------------------------------------------
+// Profiling of the dominant kernel (k_score_gemm): CUDA events on the launching stream around every launch.
+void prof_drain(mogp_engine* h) {
+  if (h->prof_used == 0) return;
+  cudaEventSynchronize(h->prof_ev[h->prof_used - 1]);
+  for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) h->prof_ms += ms;
+  }
+  h->prof_used = 0;
+}
+void prof_mark(mogp_engine* h, bool stop) {
+  if (!h->prof_on) return;
+  if (!stop && h->prof_used + 2 > 8192) prof_drain(h);
+  if (h->prof_used >= h->prof_ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->prof_ev.push_back(e);
+  }
+  cudaEventRecord(h->prof_ev[h->prof_used++], h->stream);
+}
+
 template <int BN>
 void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout) {
   const int smem = (TB * LD_C + BN * LD_C) * (int)sizeof(double);
@@ -420,7 +458,9 @@ void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout) {
     attr_done = true;
   }
   dim3 grid((unsigned)(pl.Rpad / BN), (unsigned)pl.max_nb, (unsigned)pl.n_slots);
+  prof_mark(h, false);
   k_score_gemm<BN><<<grid, NTHREADS, smem, h->stream>>>(h->d_slots, pl.kxT, (int)pl.Rpad, pl.part, Tout);
+  prof_mark(h, true);
   LAUNCHED(h);
 }
 
@@ -458,7 +498,13 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
     pl.part_total += (int64_t)(v.mpad / TB) * pl.Rpad;
     pl.max_nb = std::max(pl.max_nb, v.mpad / TB);
     hv[s] = v;
+    if (h->prof_on) {  // B_pair = 8 (m^2/2 + 3m) + 16 n + 8 per (patient, cluster); F = n m (m + 10)
+      const double m = (double)c.m;
+      h->prof_bytes += (double)n_pat * (8.0 * (m * m / 2 + 3 * m) + 8.0) + 16.0 * (double)R;
+      h->prof_flops += (double)R * m * (m + 10.0);
+    }
   }
+  if (h->prof_on) h->prof_launches += 1;
   TRY(ensure(h, &h->d_slots, &h->slots_cap, n_slots));
   const int64_t mu_total = (int64_t)n_slots * pl.Rpad;
   const int64_t need = pl.kx_total * (keep_T ? 2 : 1) + pl.part_total + mu_total;
@@ -468,6 +514,7 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   pl.mu = pl.part + pl.part_total;
   pl.T = keep_T ? pl.mu + mu_total : nullptr;
   CK(h, cudaMemcpyAsync(h->d_slots, hv, sizeof(SlotView) * (size_t)n_slots, cudaMemcpyHostToDevice, h->stream));
+  h->bytes_h2d += (int64_t)sizeof(SlotView) * n_slots;
   k_kx<<<dim3((unsigned)((pl.Rpad + 7) / 8), (unsigned)n_slots), NTHREADS, 0, h->stream>>>(h->d_slots, xs_dev, (int)R,
                                                                                             (int)pl.Rpad, pl.kxT, pl.mu);
   LAUNCHED(h);
@@ -509,6 +556,7 @@ int stage_query(mogp_engine* h, int64_t n_pat, const int64_t* off, const double*
   else memset(sd + 2 * R, 0, sizeof(double) * n_pat);
   CK(h, cudaMemcpyAsync(h->d_qoff, so, sizeof(int64_t) * (n_pat + 1), cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->d_q, sd, sizeof(double) * (2 * R + n_pat), cudaMemcpyHostToDevice, h->stream));
+  h->bytes_h2d += (int64_t)bytes;
   return MOGP_OK;
 }
 
@@ -516,6 +564,7 @@ int copy_back(mogp_engine* h, double* dst, const double* src_dev, int64_t n) {
   TRY(ensure_dn(h, sizeof(double) * (size_t)n));
   CK(h, cudaMemcpyAsync(h->pin_dn, src_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(h, sync_stream(h));
+  h->bytes_d2h += (int64_t)sizeof(double) * n;
   memcpy(dst, h->pin_dn, sizeof(double) * n);
   return MOGP_OK;
 }
@@ -580,6 +629,7 @@ void mogp_engine_destroy(mogp_engine* h) {
   if (h->pin) cudaFreeHost(h->pin);
   if (h->pin_dn) cudaFreeHost(h->pin_dn);
   if (h->pin_up) cudaFreeHost(h->pin_up);
+  for (auto e : h->prof_ev) cudaEventDestroy(e);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
@@ -610,6 +660,22 @@ int mogp_timer_stop(mogp_engine* h, double* ms_out) {
 }
 
 // ---- patients ---------------------------------------------------------------------------------------------
+static int upload_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x, const double* y) {
+  const int64_t V = off[n_patients];
+  char* up = nullptr;
+  TRY(stage_alloc(h, sizeof(int64_t) * (n_patients + 1) + sizeof(double) * 2 * V, &up));
+  int64_t* so = reinterpret_cast<int64_t*>(up);
+  double* sd = reinterpret_cast<double*>(so + n_patients + 1);
+  memcpy(so, off, sizeof(int64_t) * (n_patients + 1));
+  memcpy(sd, x, sizeof(double) * V);
+  memcpy(sd + V, y, sizeof(double) * V);
+  CK(h, cudaMemcpyAsync(h->d_off, so, sizeof(int64_t) * (n_patients + 1), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_px, sd, sizeof(double) * V, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_py, sd + V, sizeof(double) * V, cudaMemcpyHostToDevice, h->stream));
+  h->bytes_h2d += (int64_t)(sizeof(int64_t) * (n_patients + 1) + sizeof(double) * 2 * V);
+  return MOGP_OK;
+}
+
 int mogp_set_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x, const double* y,
                       const double* y_thr) {
   if (!h) return MOGP_EINVAL;
@@ -632,18 +698,46 @@ int mogp_set_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, co
   CK(h, cudaMalloc((void**)&h->d_off, sizeof(int64_t) * (n_patients + 1)));
   CK(h, cudaMalloc((void**)&h->d_px, sizeof(double) * std::max<int64_t>(V, 1)));
   CK(h, cudaMalloc((void**)&h->d_py, sizeof(double) * std::max<int64_t>(V, 1)));
-  char* up = nullptr;
-  TRY(stage_alloc(h, sizeof(int64_t) * (n_patients + 1) + sizeof(double) * 2 * V, &up));
-  int64_t* so = reinterpret_cast<int64_t*>(up);
-  double* sd = reinterpret_cast<double*>(so + n_patients + 1);
-  memcpy(so, off, sizeof(int64_t) * (n_patients + 1));
-  memcpy(sd, x, sizeof(double) * V);
-  memcpy(sd + V, y, sizeof(double) * V);
-  CK(h, cudaMemcpyAsync(h->d_off, so, sizeof(int64_t) * (n_patients + 1), cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->d_px, sd, sizeof(double) * V, cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->d_py, sd + V, sizeof(double) * V, cudaMemcpyHostToDevice, h->stream));
+  TRY(upload_patients(h, n_patients, off, x, y));
   CK(h, sync_stream(h));
   h->chain.active = false;
+  return MOGP_OK;
+}
+
+/* Re-send the same patient table (same offsets) from the host without disturbing the chain: the per-sweep
+   host->device copy of an end-to-end run whose data live in host memory. */
+int mogp_refresh_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x, const double* y) {
+  if (!h) return MOGP_EINVAL;
+  if (n_patients != h->P || !off || !x || !y || off[n_patients] != h->V) FAIL(h, MOGP_EINVAL, "patient table shape changed");
+  if (memcmp(off, h->h_off.data(), sizeof(int64_t) * (n_patients + 1)) != 0) FAIL(h, MOGP_EINVAL, "patient offsets changed");
+  return upload_patients(h, n_patients, off, x, y);
+}
+
+int mogp_profile(mogp_engine* h, int32_t enable) {
+  if (!h) return MOGP_EINVAL;
+  prof_drain(h);
+  h->prof_on = enable != 0;
+  return MOGP_OK;
+}
+
+int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg_bytes, double* alg_flops, int32_t reset) {
+  if (!h) return MOGP_EINVAL;
+  prof_drain(h);
+  if (launches) *launches = h->prof_launches;
+  if (ms) *ms = h->prof_ms;
+  if (alg_bytes) *alg_bytes = h->prof_bytes;
+  if (alg_flops) *alg_flops = h->prof_flops;
+  if (reset) {
+    h->prof_launches = 0;
+    h->prof_ms = h->prof_bytes = h->prof_flops = 0.0;
+  }
+  return MOGP_OK;
+}
+
+int mogp_transfer_bytes(mogp_engine* h, int64_t* h2d, int64_t* d2h) {
+  if (!h) return MOGP_EINVAL;
+  if (h2d) *h2d = h->bytes_h2d;
+  if (d2h) *d2h = h->bytes_d2h;
   return MOGP_OK;
 }
 

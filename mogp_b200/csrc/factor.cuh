@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(NTHREADS) k_build(double* __restrict__ L, doub
 //   b == p : L_pp = chol(A_pp), M_pp = L_pp^-1
 //   b >  p : L_bp = A_bp M_pp^T                       (TRSM by the inverse of the diagonal tile)
 //   b <  p : M_pb = -M_pp Acc_pb                      (finalise block-row p of the inverse factor)
-// Every CTA factors the diagonal tile redundantly (no extra launch / grid barrier).
+// Every CTA factors the diagonal tile redundantly (no extra launch / grid barrier); the diagonal tile of L
+// keeps A_pp (L_pp itself is never needed again: log-determinants come from the diagonal of M).
 constexpr int PANEL_SMEM = (TB * LD_C + TB * LD_C + TB * LD_R + TB) * (int)sizeof(double);
 
 __global__ void __launch_bounds__(NTHREADS) k_panel(double* __restrict__ L, double* __restrict__ M, int64_t ld, int p,
@@ -100,9 +101,10 @@ __global__ void __launch_bounds__(NTHREADS) k_panel(double* __restrict__ L, doub
   if (fail && b == p && threadIdx.x == 0) atomicCAS(info, 0, p * TB + fail);
   trtri_tile<LD_C>(sD, sM);
   if (b == p) {
+    // Only M_pp is stored.  A_pp must stay untouched in L: the other CTAs of this launch read it, and a CTA
+    // scheduled late (more CTAs than fit on the device at once) would otherwise see the factored tile.
     for (int idx = threadIdx.x; idx < TB * TB; idx += NTHREADS) {
       int i = idx >> 6, j = idx & 63;
-      L[dpp + (int64_t)i * ld + j] = sD[i * LD_C + j];
       M[dpp + (int64_t)i * ld + j] = sM[i * LD_C + j];
     }
     return;

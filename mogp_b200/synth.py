@@ -8,8 +8,13 @@ rate; y = clip(round(f(t) + N(0, 1.5^2)), 0, 48); onset anchor (x=0, y=48) prepe
 import numpy as np
 
 
-def alsfrs_like(n_patients, seed=0, max_visits=10, min_visits=3, anchor=True):
+def alsfrs_like(n_patients, seed=0, max_visits=10, min_visits=3, anchor=True, n_classes=None, return_labels=False):
+    """n_classes=None: every patient draws its own (family, rate).  n_classes=C: patients belong to C latent
+    progression classes (family x rate x onset on a grid, small per-patient jitter) — the shape of a sampler
+    that has found its clusters, which is the state BASELINE.json's 10k-patient configuration names
+    (~30 active clusters)."""
     rs = np.random.RandomState(seed)
+    labels = np.zeros(n_patients, dtype=np.int32)
     T = max_visits + (1 if anchor else 0)
     X = np.full((n_patients, T), np.nan)
     Y = np.full((n_patients, T), np.nan)
@@ -20,20 +25,31 @@ def alsfrs_like(n_patients, seed=0, max_visits=10, min_visits=3, anchor=True):
         t = np.concatenate([[t0], t0 + np.cumsum(gaps)])
         if t[-1] > 8.0:
             t = t0 + (t - t0) * (8.0 - t0) / (t[-1] - t0)
-        fam = rs.randint(3)
-        rate = rs.uniform(0.5, 1.5)
+        if n_classes is None:
+            fam = rs.randint(3)
+            rate = rs.uniform(0.5, 1.5)
+            mid = 1.5 if fam == 1 else 4.0
+        else:
+            c = rs.randint(n_classes)
+            labels[i] = c
+            fam = c % 3
+            q = (c // 3) / max(1, (n_classes + 2) // 3 - 1) if n_classes > 3 else 0.5
+            rate = (0.3 + 1.5 * q) * rs.uniform(0.97, 1.03)
+            mid = (1.0 + 2.0 * q) if fam == 1 else (3.0 + 3.0 * q)
         if fam == 0:
             f = 48.0 - 6.0 * rate * t
         elif fam == 1:
-            f = 48.0 / (1.0 + np.exp(2.0 * rate * (t - 1.5)))
+            f = 48.0 / (1.0 + np.exp(2.0 * rate * (t - mid)))
         else:
-            f = 48.0 / (1.0 + np.exp(1.5 * rate * (t - 4.0)))
+            f = 48.0 / (1.0 + np.exp(1.5 * rate * (t - mid)))
         y = np.clip(np.round(f + rs.randn(nv) * 1.5), 0, 48)
         o = 1 if anchor else 0
         if anchor:
             X[i, 0], Y[i, 0] = 0.0, 48.0
         X[i, o:o + nv] = t
         Y[i, o:o + nv] = y
+    if return_labels:
+        return X, Y, labels
     return X, Y
 
 
