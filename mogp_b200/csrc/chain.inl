@@ -21,16 +21,12 @@ void pool_put(mogp_engine* h, int64_t cap, double* buf) {
 
 // z (optional), alpha and the log marginal from the current M; results stay on the device until asked for.
 int refresh_vectors(mogp_engine* h, Cluster& c, bool recompute_z) {
-  const int64_t mpad = round_up(c.m, TB);
   Theta th = make_theta(c);
   if (recompute_z) {
     k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.x(), c.y(), (int)c.m, th, c.z());
     LAUNCHED(h);
   }
-  k_alpha<<<(unsigned)(mpad / 32), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.z(), (int)c.m, c.alpha());
-  LAUNCHED(h);
-  k_lml<<<1, 1024, 0, h->stream>>>(c.M, c.cap, c.z(), c.x(), c.alpha(), (int)c.m, c.stat());
-  LAUNCHED(h);
+  TRY(launch_alpha_lml(h, c));
   c.stat_on_device = true;
   c.grad_valid = false;
   return MOGP_OK;
@@ -62,17 +58,20 @@ int append_core(mogp_engine* h, Cluster& c, int n, const double* xB_dev, const d
   const int64_t m = c.m, mpad_old = round_up(m, TB), mnew = m + n, mpad_new = round_up(mnew, TB);
   if (mnew > c.cap) TRY(cluster_reserve(h, c, mnew, true));
   const int nb = (int)(mpad_old / TB);
-  TRY(ensure(h, &h->d_apw, &h->apw_elems, NP * NP + NP + NP * mpad_old + APPEND_KS * NP * mpad_old));
+  const int nblk = (int)((mpad_old + AP_GRAM_ROWS - 1) / AP_GRAM_ROWS);
+  TRY(ensure(h, &h->d_apw, &h->apw_elems, NP * NP + NP + (int64_t)nblk * NG + APPEND_KS * NP * mpad_old));
   ApWork w;
   w.Li = h->d_apw;
   w.znew = w.Li + NP * NP;
-  w.Ct = w.znew + NP;
-  w.part = w.Ct + NP * mpad_old;
+  w.gpart = w.znew + NP;
+  w.part = w.gpart + (int64_t)nblk * NG;
   Theta th = make_theta(c);
   int* info = reinterpret_cast<int*>(c.stat() + 8);
-  k_append_small<<<1, 256, 0, h->stream>>>(T_dev, mu_dev, (int)mpad_old, xB_dev, yB_dev, n, th, w, info);
+  k_append_gram<<<nblk, 256, 0, h->stream>>>(T_dev, (int)mpad_old, n, w);
   LAUNCHED(h);
-  k_append_rows<<<dim3(nb, APPEND_KS), NTHREADS, AP_ROWS_SMEM, h->stream>>>(c.M, c.cap, nb, (int)mpad_old, w);
+  k_append_small<<<1, 256, 0, h->stream>>>(mu_dev, nblk, xB_dev, yB_dev, n, th, w, info);
+  LAUNCHED(h);
+  k_append_rows<<<dim3(nb, APPEND_KS), NTHREADS, AP_ROWS_SMEM, h->stream>>>(c.M, c.cap, nb, (int)mpad_old, T_dev, n, w);
   LAUNCHED(h);
   if (mpad_new > mpad_old) {
     k_pad_identity<<<64, 256, 0, h->stream>>>(c.M, c.cap, (int)mpad_old, (int)mpad_new);
@@ -118,7 +117,8 @@ RmGeom make_geom(const Cluster& c, int64_t p, int n) {
 
 int rm_work(mogp_engine* h, const RmGeom& g, RmWork* w) {
   const int64_t nT = g.nbn - g.I0, rows = nT * TB;
-  TRY(ensure(h, &h->d_upd, &h->upd_elems, rows * NP * 2 + rows + nT * NG + NG + 8));
+  const int64_t ph = nT * g.nbn * (int64_t)(NP * TB);  // P and H tiles of the deletion
+  TRY(ensure(h, &h->d_upd, &h->upd_elems, rows * NP * 2 + rows + nT * NG + NG + 8 + 2 * ph));
   w->Bt = h->d_upd;
   w->Gt = w->Bt + rows * NP;
   w->u = w->Gt + rows * NP;
@@ -160,7 +160,13 @@ int remove_core(mogp_engine* h, Cluster& c, int64_t p, int n) {
   TRY(pool_get(h, c.cap, &nbuf));
   double* nM = nbuf;
   double* nvec = nbuf + c.cap * c.cap;
-  k_rm_apply<<<g.nbn, NTHREADS, RM_APPLY_SMEM, h->stream>>>(c.M, nM, g, w);
+  double* P = w.own + 8;
+  double* H = P + (int64_t)nT * g.nbn * (NP * TB);
+  k_rm_hpart<<<dim3(g.nbn, nT), NTHREADS, 0, h->stream>>>(c.M, g, w, P);
+  LAUNCHED(h);
+  k_rm_hscan<<<g.nbn, NP * TB, 0, h->stream>>>(c.M, g, P, H);
+  LAUNCHED(h);
+  k_rm_apply<<<dim3(g.nbn, g.nbn), NTHREADS, RM_APPLY_SMEM, h->stream>>>(c.M, nM, g, w, H);
   LAUNCHED(h);
   k_rm_vec<<<(unsigned)((g.mnew + 255) / 256), 256, 0, h->stream>>>(c.x(), c.y(), nvec, nvec + c.cap, g);
   LAUNCHED(h);

@@ -58,7 +58,8 @@ struct ScorePlan {
   int n_slots = 0;
   int max_nb = 0;
   int64_t kx_total = 0, part_total = 0;
-  double *kxT = nullptr, *part = nullptr, *mu = nullptr, *T = nullptr;
+  int max_rblk = 0;  // row blocks (of KX_ROWS) of the largest slot
+  double *kxT = nullptr, *part = nullptr, *mupart = nullptr, *mu = nullptr, *T = nullptr;
 };
 
 struct Chain {
@@ -101,6 +102,8 @@ struct mogp_engine {
   int64_t L_elems = 0;
   double* d_partial = nullptr;
   int64_t partial_elems = 0;
+  double* d_apart = nullptr;  // row-chunk partials of alpha = M^T z
+  int64_t apart_elems = 0;
   // scoring scratch
   SlotView* d_slots = nullptr;
   int64_t slots_cap = 0;
@@ -290,6 +293,19 @@ int cluster_reserve(mogp_engine* h, Cluster& c, int64_t m_new, bool keep) {
   return MOGP_OK;
 }
 
+// alpha = M^T z (two stages) and the log marginal likelihood from the current M and z.
+int launch_alpha_lml(mogp_engine* h, Cluster& c) {
+  const int64_t mpad = round_up(c.m, TB);
+  const int nchunk = (int)((c.m + ALPHA_ROWS - 1) / ALPHA_ROWS);
+  TRY(ensure(h, &h->d_apart, &h->apart_elems, (int64_t)nchunk * mpad));
+  k_alpha_part<<<dim3((unsigned)(mpad / TB), (unsigned)nchunk), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.z(), (int)c.m,
+                                                                                           (int)mpad, h->d_apart);
+  LAUNCHED(h);
+  k_lml<<<1, 1024, 0, h->stream>>>(c.M, c.cap, c.z(), c.x(), h->d_apart, nchunk, (int)mpad, c.alpha(), (int)c.m, c.stat());
+  LAUNCHED(h);
+  return MOGP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Exact inference at (data, theta): ExactGaussianInference.inference as reached by GPy's
 // GPRegression.__init__ / set_XY / every optimiser evaluation (obsmodel.py:46,73,92,94).
@@ -321,10 +337,7 @@ int infer(mogp_engine* h, Cluster& c) {
     }
     k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, ld, c.x(), c.y(), (int)c.m, th, c.z());
     LAUNCHED(h);
-    k_alpha<<<(unsigned)(mpad / 32), NTHREADS, 0, h->stream>>>(c.M, ld, c.z(), (int)c.m, c.alpha());
-    LAUNCHED(h);
-    k_lml<<<1, 1024, 0, h->stream>>>(c.M, ld, c.z(), c.x(), c.alpha(), (int)c.m, st);
-    LAUNCHED(h);
+    TRY(launch_alpha_lml(h, c));
     CK(h, cudaMemcpyAsync(h->pin, st, sizeof(double) * 9, cudaMemcpyDeviceToHost, h->stream));
     CK(h, sync_stream(h));
     h->bytes_d2h += 72;
@@ -451,7 +464,7 @@ void prof_mark(mogp_engine* h, bool stop) {
 
 template <int BN>
 void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout) {
-  const int smem = (TB * LD_C + BN * LD_C) * (int)sizeof(double);
+  const int smem = ScoreSmem<BN>::BYTES;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_score_gemm<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -497,6 +510,7 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
     pl.kx_total += pl.Rpad * (int64_t)v.mpad;
     pl.part_total += (int64_t)(v.mpad / TB) * pl.Rpad;
     pl.max_nb = std::max(pl.max_nb, v.mpad / TB);
+    pl.max_rblk = std::max(pl.max_rblk, (v.mpad + KX_ROWS - 1) / KX_ROWS);
     hv[s] = v;
     if (h->prof_on) {  // B_pair = 8 (m^2/2 + 3m) + 16 n + 8 per (patient, cluster); F = n m (m + 10)
       const double m = (double)c.m;
@@ -506,17 +520,18 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   }
   if (h->prof_on) h->prof_launches += 1;
   TRY(ensure(h, &h->d_slots, &h->slots_cap, n_slots));
-  const int64_t mu_total = (int64_t)n_slots * pl.Rpad;
-  const int64_t need = pl.kx_total * (keep_T ? 2 : 1) + pl.part_total + mu_total;
+  const int64_t mu_total = (int64_t)n_slots * pl.Rpad, mupart_total = mu_total * pl.max_rblk;
+  const int64_t need = pl.kx_total * (keep_T ? 2 : 1) + pl.part_total + mu_total + mupart_total;
   TRY(ensure(h, &h->d_scr, &h->scr_elems, need));
   pl.kxT = h->d_scr;
   pl.part = pl.kxT + pl.kx_total;
   pl.mu = pl.part + pl.part_total;
-  pl.T = keep_T ? pl.mu + mu_total : nullptr;
+  pl.mupart = pl.mu + mu_total;
+  pl.T = keep_T ? pl.mupart + mupart_total : nullptr;
   CK(h, cudaMemcpyAsync(h->d_slots, hv, sizeof(SlotView) * (size_t)n_slots, cudaMemcpyHostToDevice, h->stream));
   h->bytes_h2d += (int64_t)sizeof(SlotView) * n_slots;
-  k_kx<<<dim3((unsigned)((pl.Rpad + 7) / 8), (unsigned)n_slots), NTHREADS, 0, h->stream>>>(h->d_slots, xs_dev, (int)R,
-                                                                                            (int)pl.Rpad, pl.kxT, pl.mu);
+  k_kx<<<dim3((unsigned)pl.max_rblk, (unsigned)((pl.Rpad + KX_COLS - 1) / KX_COLS), (unsigned)n_slots), KX_ROWS, 0,
+         h->stream>>>(h->d_slots, xs_dev, (int)R, (int)pl.Rpad, pl.max_rblk, pl.kxT, pl.mupart);
   LAUNCHED(h);
   switch (pl.BN) {
     case 8: launch_score_gemm<8>(h, pl, pl.T); break;
@@ -526,7 +541,8 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   }
   const int64_t pairs = n_pat * n_slots;
   k_score_epi<<<(unsigned)((pairs + 255) / 256), 256, 0, h->stream>>>(h->d_slots, n_slots, off_dev, n_pat, xs_dev, ys_dev,
-                                                                     (int)pl.Rpad, pl.part, pl.mu, thr_index, score_dev,
+                                                                     (int)pl.Rpad, pl.part, pl.mupart, pl.max_rblk, pl.mu,
+                                                                     thr_index, score_dev,
                                                                      mu_thr_dev, col_mean, col_var, col_lpd);
   LAUNCHED(h);
   CK(h, cudaGetLastError());
@@ -618,6 +634,7 @@ void mogp_engine_destroy(mogp_engine* h) {
   cudaFree(h->d_py);
   cudaFree(h->d_L);
   cudaFree(h->d_partial);
+  cudaFree(h->d_apart);
   cudaFree(h->d_slots);
   cudaFree(h->d_scr);
   cudaFree(h->d_q);

@@ -170,33 +170,50 @@ __global__ void __launch_bounds__(NTHREADS) k_z(const double* __restrict__ M, in
   if (lane == 0) z[i] = acc;
 }
 
-// alpha = M^T z.  CTA per strip of 32 columns, warps split the rows, fixed-order reduction.
-__global__ void __launch_bounds__(NTHREADS) k_alpha(const double* __restrict__ M, int64_t ld,
-                                                    const double* __restrict__ z, int m, double* __restrict__ alpha) {
-  __shared__ double red[NTHREADS / 32][33];
-  const int j = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
-  double acc = 0.0;
-  for (int i = blockIdx.x * 32 + w; i < m; i += NTHREADS / 32) acc += M[(int64_t)i * ld + j] * z[i];
-  red[w][threadIdx.x & 31] = acc;
+// alpha = M^T z in two deterministic stages.  Stage 1: CTA (J, C) sums rows [256 C, 256 C + 256) of the 64-column
+// strip J (each warp reads whole 512-byte row segments) into apart[C][col]; stage 2 (inside k_lml) adds the
+// row chunks in order.
+constexpr int ALPHA_ROWS = 256;
+__global__ void __launch_bounds__(NTHREADS) k_alpha_part(const double* __restrict__ M, int64_t ld,
+                                                         const double* __restrict__ z, int m, int mpad,
+                                                         double* __restrict__ apart) {
+  __shared__ double2 red[NTHREADS / 32][32];
+  const int J = blockIdx.x, C = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = max(C * ALPHA_ROWS, J * TB), r1 = min((C + 1) * ALPHA_ROWS, m);
+  double2 acc = make_double2(0.0, 0.0);
+  for (int i = r0 + w; i < r1; i += NTHREADS / 32) {
+    const double2 v = *reinterpret_cast<const double2*>(M + (int64_t)i * ld + J * TB + 2 * lane);
+    const double zi = z[i];
+    acc.x += v.x * zi;
+    acc.y += v.y * zi;
+  }
+  red[w][lane] = acc;
   __syncthreads();
   if (w == 0) {
-    double s = 0.0;
+    double2 s = make_double2(0.0, 0.0);
 #pragma unroll
-    for (int q = 0; q < NTHREADS / 32; ++q) s += red[q][threadIdx.x];
-    if (j < m) alpha[j] = s;
+    for (int q = 0; q < NTHREADS / 32; ++q) {
+      s.x += red[q][lane].x;
+      s.y += red[q][lane].y;
+    }
+    *reinterpret_cast<double2*>(apart + (int64_t)C * mpad + J * TB + 2 * lane) = s;
   }
 }
 
-// One CTA: quad = z.z, logdet = 2 sum ln L_ii = -2 sum ln M_ii, sxa = sum x_i alpha_i, LML.  out[0..3].
+// One CTA: alpha = sum of the row-chunk partials; quad = z.z, logdet = 2 sum ln L_ii = -2 sum ln M_ii,
+// sxa = sum x_i alpha_i, LML.  out[0..3].
 __global__ void __launch_bounds__(1024) k_lml(const double* __restrict__ M, int64_t ld, const double* __restrict__ z,
-                                              const double* __restrict__ x, const double* __restrict__ alpha, int m,
-                                              double* __restrict__ out) {
+                                              const double* __restrict__ x, const double* __restrict__ apart, int nchunk,
+                                              int mpad, double* __restrict__ alpha, int m, double* __restrict__ out) {
   __shared__ double red[3][1024];
   double q = 0.0, ld2 = 0.0, sxa = 0.0;
   for (int i = threadIdx.x; i < m; i += 1024) {
+    double a = 0.0;
+    for (int c = i / ALPHA_ROWS; c < nchunk; ++c) a += apart[(int64_t)c * mpad + i];  // chunks above row i hold zeros
+    alpha[i] = a;
     q += z[i] * z[i];
     ld2 -= log(M[(int64_t)i * ld + i]);
-    sxa += x[i] * alpha[i];
+    sxa += x[i] * a;
   }
   red[0][threadIdx.x] = q;
   red[1][threadIdx.x] = ld2;

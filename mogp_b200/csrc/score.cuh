@@ -28,30 +28,40 @@ struct SlotView {
   int64_t part_off;  // offset (doubles) of this slot's partial block: [rb][Rpad]
 };
 
-// grid (ceil(R/8), n_slots); warp per query column.
-__global__ void __launch_bounds__(NTHREADS) k_kx(const SlotView* __restrict__ slots, const double* __restrict__ xs,
-                                                 int R, int Rpad, double* __restrict__ kxT, double* __restrict__ mu) {
-  const SlotView sv = slots[blockIdx.y];
-  const int col = blockIdx.x * (NTHREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (col >= Rpad) return;
-  double* out = kxT + sv.kx_off + (int64_t)col * sv.mpad;
-  if (col >= R) {  // zero padding columns so the GEMM needs no mask
-    for (int j = lane; j < sv.mpad; j += 32) out[j] = 0.0;
-    return;
-  }
-  const double xq = xs[col];
-  double acc = 0.0;
-  for (int j = lane; j < sv.mpad; j += 32) {
+// Cross covariance, built once per scoring pass: KxT[slot][col][j] = k(x_slot[j], x*_col) (zero in the padding),
+// and the row-block partials of Kx^T alpha.  grid (ceil(mpad_max/256), ceil(Rpad/16), n_slots): one thread per
+// cluster point j, 16 query columns per CTA, coalesced stores along j.
+constexpr int KX_ROWS = 256, KX_COLS = 16;
+__global__ void __launch_bounds__(KX_ROWS) k_kx(const SlotView* __restrict__ slots, const double* __restrict__ xs, int R,
+                                                int Rpad, int max_rblk, double* __restrict__ kxT,
+                                                double* __restrict__ mupart) {
+  const SlotView sv = slots[blockIdx.z];
+  const int j = blockIdx.x * KX_ROWS + threadIdx.x;
+  if (blockIdx.x * KX_ROWS >= sv.mpad) return;
+  __shared__ double wred[KX_ROWS / 32][KX_COLS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.y * KX_COLS;
+  const bool live = j < sv.m;
+  const double xj = live ? sv.x[j] : 0.0, aj = live ? sv.alpha[j] : 0.0;
+#pragma unroll 4
+  for (int q = 0; q < KX_COLS; ++q) {
+    const int col = c0 + q;
+    if (col >= Rpad) break;
     double v = 0.0;
-    if (j < sv.m) {
-      v = kern_eval(sv.th, sv.x[j], xq, false, nullptr);
-      acc += v * sv.alpha[j];
-    }
-    out[j] = v;
-  }
+    if (live && col < R) v = kern_eval(sv.th, xj, xs[col], false, nullptr);
+    if (j < sv.mpad) kxT[sv.kx_off + (int64_t)col * sv.mpad + j] = v;
+    double p = v * aj;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) mu[(int64_t)blockIdx.y * Rpad + col] = sv.th.mean_func ? acc + xq * (-sv.th.A) : acc;
+    for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    if (lane == 0) wred[warp][q] = p;
+  }
+  __syncthreads();
+  if (threadIdx.x < KX_COLS && c0 + threadIdx.x < Rpad) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < KX_ROWS / 32; ++w) s += wred[w][threadIdx.x];
+    mupart[((int64_t)blockIdx.z * max_rblk + blockIdx.x) * Rpad + c0 + threadIdx.x] = s;
+  }
 }
 
 // T = M Kx for a 64-row block and a BN-column tile; emits column sums of squares per row block.
@@ -67,11 +77,29 @@ struct ScoreShape<32> { static constexpr int MS = 2, NS = 2, WM = 4, WN = 2; };
 template <>
 struct ScoreShape<64> { static constexpr int MS = 2, NS = 4, WM = 4, WN = 2; };
 
+// Stages of the tile pipeline by column-tile width (one CTA per SM; a stage = one 64x64 tile of M + BN x 64 of KxT).
 template <int BN>
-__global__ void __launch_bounds__(NTHREADS) k_score_gemm(const SlotView* __restrict__ slots,
-                                                         const double* __restrict__ kxT, int Rpad,
-                                                         double* __restrict__ part, double* __restrict__ Tout) {
+struct ScoreStages { static constexpr int S = BN <= 16 ? 5 : (BN == 32 ? 4 : 3); };
+template <int BN>
+struct ScoreSmem {
+  static constexpr int STAGE = (TB + BN) * LD_C;  // doubles per stage
+  static constexpr int BYTES = ScoreStages<BN>::S * STAGE * (int)sizeof(double);
+};
+
+// The product is HBM-bound for the few columns of one patient (2 n flops per 8 bytes of M): the tiles of M are
+// streamed through an S-stage ring of cp.async (LDGSTS, L1-bypassing) copies into padded rows, so the DMMA
+// fragment loads stay conflict free; S-1 tiles (~40 KB each) are in flight per SM while the 8 warps run the
+// DMMAs of the current one; one block barrier per tile.
+// (Measured on B200: the same ring fed by 512-byte cp.async.bulk row copies + mbarriers ran 1.45x SLOWER than
+// even the unpipelined loop - per-copy overhead of the TMA unit; a single bulk copy per tile needs tile-major
+// storage of M, see DESIGN.md "next".)
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1) k_score_gemm(const SlotView* __restrict__ slots,
+                                                            const double* __restrict__ kxT, int Rpad,
+                                                            double* __restrict__ part, double* __restrict__ Tout) {
   using S = ScoreShape<BN>;
+  constexpr int NS = ScoreStages<BN>::S;
+  constexpr int STAGE = ScoreSmem<BN>::STAGE;
   const SlotView sv = slots[blockIdx.z];
   const int nb = sv.mpad / TB;
   // heavy row blocks first: block row rb needs rb+1 tile products
@@ -79,22 +107,33 @@ __global__ void __launch_bounds__(NTHREADS) k_score_gemm(const SlotView* __restr
   if (rb < 0) return;
   const int c0 = blockIdx.x * BN;
   extern __shared__ __align__(16) double smem[];
-  double* sA = smem;            // M tile   [64][LD_C]
-  double* sB = sA + TB * LD_C;  // KxT tile [BN][LD_C]  (stored [col][k])
   __shared__ double red[S::WM][BN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int wm = warp / S::WN, wn = warp % S::WN;
   const int rbase = wm * 8 * S::MS, cbase = wn * 8 * S::NS;
+  const double* Mrow = sv.M + (int64_t)rb * TB * sv.ld;
+  const double* kx = kxT + sv.kx_off + (int64_t)c0 * sv.mpad;
+  const int ntiles = rb + 1;
+  auto issue = [&](int tile) {
+    if (tile < ntiles) {
+      double* sA = smem + (tile % NS) * STAGE;
+      load_tile_async<LD_C>(sA, Mrow + (int64_t)tile * TB, sv.ld);
+      load_tile_async<LD_C, BN>(sA + TB * LD_C, kx + (int64_t)tile * TB, sv.mpad);
+    }
+    cp_async_commit();  // (possibly empty: keeps the group count uniform)
+  };
+#pragma unroll
+  for (int tile = 0; tile < NS - 1; ++tile) issue(tile);
   Acc<S::MS, S::NS> acc;
   acc.zero();
-  const double* kx = kxT + sv.kx_off + (int64_t)c0 * sv.mpad;
-  for (int kb = 0; kb <= rb; ++kb) {
-    __syncthreads();
-    load_tile<LD_C>(sA, sv.M + (int64_t)rb * TB * sv.ld + (int64_t)kb * TB, sv.ld);
-    load_tile<LD_C, BN>(sB, kx + (int64_t)kb * TB, sv.mpad);
-    __syncthreads();
-    warp_mma<S::MS, S::NS, true, true>(acc, sA, sB, rbase, cbase);
+  for (int tile = 0; tile < ntiles; ++tile) {
+    cp_async_wait<NS - 2>();  // this thread's copies of `tile` have landed
+    __syncthreads();          // ... everybody's have, and everybody is done with tile-1: refill its stage
+    issue(tile + NS - 1);
+    const double* sA = smem + (tile % NS) * STAGE;
+    warp_mma<S::MS, S::NS, true, true>(acc, sA, sA + TB * LD_C, rbase, cbase);
   }
+  cp_async_wait<0>();
   if (Tout) {  // optional: keep T (= L^-1 Kx) for the rank-n append of the chosen cluster
     double* o = Tout + sv.kx_off;
 #pragma unroll
@@ -140,7 +179,8 @@ __global__ void __launch_bounds__(256) k_score_epi(const SlotView* __restrict__ 
                                                    const int64_t* __restrict__ off, int64_t n_pat,
                                                    const double* __restrict__ xs, const double* __restrict__ ys,
                                                    int Rpad, const double* __restrict__ part,
-                                                   const double* __restrict__ mu, int thr_index,
+                                                   const double* __restrict__ mupart, int max_rblk,
+                                                   double* __restrict__ mu, int thr_index,
                                                    double* __restrict__ score, double* __restrict__ mu_thr,
                                                    double* __restrict__ col_mean, double* __restrict__ col_var,
                                                    double* __restrict__ col_lpd) {
@@ -158,7 +198,11 @@ __global__ void __launch_bounds__(256) k_score_epi(const SlotView* __restrict__ 
     double v = kern_diag(sv.th, xs[col]) - ss;
     v = v > 1e-15 ? v : 1e-15;  // Posterior._raw_predict clips the variance
     const double vn = v + sv.th.noise;
-    const double m = mu[(int64_t)c * Rpad + col];
+    double m = 0.0;
+    const int nrb = (sv.mpad + KX_ROWS - 1) / KX_ROWS;
+    for (int rb = 0; rb < nrb; ++rb) m += mupart[((int64_t)c * max_rblk + rb) * Rpad + col];
+    if (sv.th.mean_func) m += xs[col] * (-sv.th.A);  // + m(x*) = -A x*  (neg_linear.py:22-23)
+    mu[(int64_t)c * Rpad + col] = m;
     const double d = ys ? ys[col] - m : 0.0;
     const double lpd = -0.5 * LOG_2_PI - 0.5 * log(vn) - 0.5 * (d * d) / vn;
     total += lpd;
@@ -167,7 +211,7 @@ __global__ void __launch_bounds__(256) k_score_epi(const SlotView* __restrict__ 
     if (col_lpd) col_lpd[(int64_t)c * Rpad + col] = lpd;
   }
   if (score) score[gid] = total;
-  if (mu_thr) {
+  if (mu_thr) {  // (written by this thread in the loop above)
     const int64_t ct = c0 + thr_index;
     mu_thr[gid] = (thr_index >= 0 && ct < c1) ? mu[(int64_t)c * Rpad + ct] : nan("");
   }

@@ -27,6 +27,59 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
+// ---- TMA bulk copies + mbarrier (sm_90+/sm_100a): cp.async.bulk moves whole 512-byte tile rows from global
+// to (padded) shared-memory rows and signals an mbarrier with the byte count; SASS: UBLKCP + SYNCS. ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// ---- cp.async (LDGSTS) 16-byte copies: global -> padded shared rows, no register staging ----
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// Asynchronous version of load_tile: ROWS x 64 tile into s[ROWS][LD].
+template <int LD, int ROWS = TB>
+__device__ __forceinline__ void load_tile_async(double* __restrict__ s, const double* __restrict__ g, int64_t ld) {
+#pragma unroll
+  for (int q = 0; q < (ROWS * TB / 2 + NTHREADS - 1) / NTHREADS; ++q) {
+    int idx = threadIdx.x + q * NTHREADS;
+    if ((ROWS * TB / 2) % NTHREADS == 0 || idx < ROWS * TB / 2) {
+      int r = idx >> 5, c = (idx & 31) << 1;
+      cp_async16(s + r * LD + c, g + (int64_t)r * ld + c);
+    }
+  }
+}
+
 // Copy a ROWS x 64 tile (row-major, leading dimension ld) from global to shared memory [ROWS][LD].
 template <int LD, int ROWS = TB>
 __device__ __forceinline__ void load_tile(double* __restrict__ s, const double* __restrict__ g, int64_t ld) {
@@ -97,46 +150,91 @@ __device__ __forceinline__ void for_each_acc64(Acc64& acc, F f) {
 // In-place lower Cholesky of the 64x64 tile s[64][LD] (lower part valid on entry).
 // Returns 0 or (1 + first non-positive pivot column); result uniform across the CTA.
 // The strict upper triangle is zeroed.
+//
+// Blocked by 8 columns: warp 0 factors the 8-column panel in registers (lane l owns rows l and l+32, pivots
+// and multipliers travel by shuffle - no block barrier inside a panel), then all 256 threads apply the rank-8
+// update to the trailing part.  16 block barriers per tile instead of 128.
 template <int LD>
 __device__ int potrf_tile(double* __restrict__ s, double* __restrict__ col) {
-  const int tid = threadIdx.x;
-  int fail = 0;
-  for (int k = 0; k < TB; ++k) {
-    __syncthreads();
-    double dkk = s[k * LD + k];
-    if (!(dkk > 0.0)) {
-      if (fail == 0) fail = k + 1;
-      dkk = 1.0;  // keep going with a harmless pivot; the caller discards the result
-    }
-    double d = sqrt(dkk);
-    if (tid < TB && tid >= k) {
-      double c = (tid == k) ? d : s[tid * LD + k] / d;
-      col[tid] = c;
-    }
-    __syncthreads();
-    if (tid < TB && tid >= k) s[tid * LD + k] = col[tid];
-    // trailing update: thread owns the 4x4 patch (i = 4*ti + a, j = 4*tj + b)
-    const int ti = tid >> 4, tj = tid & 15;
-    if (4 * ti + 3 > k && tj <= ti) {
+  (void)col;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ int s_fail;
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 < TB; k0 += 8) {
+    if (warp == 0) {
+      double a[2][8];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        int i = 4 * ti + a;
-        double ci = col[i];
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          int j = 4 * tj + b;
-          if (j > k && j <= i) s[i * LD + j] -= ci * col[j];
+        for (int j = 0; j < 8; ++j) a[h][j] = s[(lane + 32 * h) * LD + k0 + j];
+      int fail = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int pr = k0 + j;  // pivot row
+        double dkk = __shfl_sync(0xffffffffu, pr < 32 ? a[0][j] : a[1][j], pr & 31);
+        if (!(dkk > 0.0)) {
+          if (fail == 0) fail = pr + 1;
+          dkk = 1.0;  // keep going with a harmless pivot; the caller discards the result
+        }
+        const double d = sqrt(dkk);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = lane + 32 * h;
+          a[h][j] = (r == pr) ? d : (r > pr ? a[h][j] / d : a[h][j]);
+        }
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c) {
+          const int cr = k0 + c;  // row whose multiplier l_{cr, pr} scales column c
+          const double lc = __shfl_sync(0xffffffffu, cr < 32 ? a[0][j] : a[1][j], cr & 31);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (lane + 32 * h >= cr) a[h][c] -= a[h][j] * lc;
         }
       }
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = lane + 32 * h;
+          if (r >= k0 + j) s[r * LD + k0 + j] = a[h][j];
+        }
+      if (fail && lane == 0 && s_fail == 0) s_fail = fail;
     }
+    __syncthreads();
+    // trailing update: A[i][j] -= sum_q L[i][k0+q] L[j][k0+q] for i >= j >= k0 + 8; thread owns a 4x4 patch
+    const int ti = tid >> 4, tj = tid & 15;
+    if (4 * ti + 3 >= k0 + 8 && tj <= ti) {
+      double li[4][8], lj[4][8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          li[e][q] = s[(4 * ti + e) * LD + k0 + q];
+          lj[e][q] = s[(4 * tj + e) * LD + k0 + q];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          const int i = 4 * ti + e, j = 4 * tj + f;
+          if (j >= k0 + 8 && j <= i) {
+            double acc = s[i * LD + j];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc -= li[e][q] * lj[f][q];
+            s[i * LD + j] = acc;
+          }
+        }
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
     int i = idx >> 6, j = idx & 63;
     if (j > i) s[i * LD + j] = 0.0;
   }
   __syncthreads();
-  return fail;
+  return s_fail;
 }
 
 // sM = inverse of the lower-triangular tile sL (both [64][LD]); upper triangle of sM zeroed.

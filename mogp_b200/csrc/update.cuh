@@ -198,84 +198,117 @@ __global__ void __launch_bounds__(256) k_rm_prep(RmGeom g, RmWork w) {
   }
 }
 
-// One CTA per 64-column block J' of the result; walks down the row tiles carrying h (n x 64).
-constexpr int RM_APPLY_SMEM = (TB * LD_W + (TB + NP) * LD_R + TB * (NP + 1) + TB) * (int)sizeof(double);
-__global__ void __launch_bounds__(NTHREADS) k_rm_apply(const double* __restrict__ Mo, double* __restrict__ Mn, RmGeom g,
-                                                       RmWork w) {
-  extern __shared__ __align__(16) double smem[];
-  double* sA = smem;                       // [64][LD_W]: S (cols 0..63) | Gt (cols 64..64+NP)
-  double* sB = sA + TB * LD_W;             // [64+NP][LD_R]: old tile (rows 0..63) ; h (rows 64..64+NP)
-  double* sb = sB + (TB + NP) * LD_R;      // [64][NP+1]
-  double* su = sb + TB * (NP + 1);         // [64]
-  const int J = blockIdx.x, tid = threadIdx.x;
-  const int64_t ld = g.ld;
-  auto src = [&](int ip, int jp) -> double {
-    if (ip >= g.mnew || jp >= g.mnew) return (ip == jp) ? 1.0 : 0.0;
-    int i = ip < g.p ? ip : ip + g.n, j = jp < g.p ? jp : jp + g.n;
-    if (j > i) return 0.0;  // strictly upper: tiles above the diagonal are never written, do not read them
-    return Mo[(int64_t)i * ld + j];
-  };
-  // plain copies above the first updated tile
-  for (int I = J; I < g.I0 && I < g.nbn; ++I)
-    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
-      int r = idx >> 6, c = idx & 63;
-      Mn[(int64_t)(I * TB + r) * ld + J * TB + c] = src(I * TB + r, J * TB + c);
-    }
-  const int Ifirst = max(J, g.I0);
-  // h = sum over the carrier rows p..p+n-1 of b_k M[k, j]
+// Element (ip, jp) of the result's source: the old factor with rows/cols [p, p+n) skipped, identity padding
+// beyond mnew, zero strictly above the diagonal (tiles above the diagonal are never written: do not read them).
+__device__ __forceinline__ double rm_src(const double* __restrict__ Mo, const RmGeom& g, int ip, int jp) {
+  if (ip >= g.mnew || jp >= g.mnew) return (ip == jp) ? 1.0 : 0.0;
+  const int i = ip < g.p ? ip : ip + g.n, j = jp < g.p ? jp : jp + g.n;
+  if (j > i) return 0.0;
+  return Mo[(int64_t)i * g.ld + j];
+}
+
+// h_{i-1}[:, j] is a prefix sum over rows; it is formed in three fully parallel steps over the lower tiles
+// (I >= J, I >= I0) of the result:
+//   k_rm_hpart : P[I][J] = B_I^T * old tile (I, J)                                (n x 64 per tile)
+//   k_rm_hscan : H[I][J] = carriers' term + sum_{I' < I} P[I'][J]                  (exclusive scan down each J)
+//   k_rm_apply : new tile = diag(u) (old - S_I old - G_I H[I][J]),  S_I = strict_lower(G_I B_I^T)   (DMMA)
+// P and H are stored as [I - I0][J][NP][64].
+__global__ void __launch_bounds__(NTHREADS) k_rm_hpart(const double* __restrict__ Mo, RmGeom g, RmWork w,
+                                                       double* __restrict__ P) {
+  const int J = blockIdx.x, I = g.I0 + blockIdx.y;
+  if (J > I) return;
+  __shared__ double sT[TB][TB + 1];
+  __shared__ double sb[TB][NP + 1];
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+    int r = idx >> 6, c = idx & 63;
+    sT[r][c] = rm_src(Mo, g, I * TB + r, J * TB + c);
+  }
+  for (int idx = tid; idx < TB * NP; idx += NTHREADS) {
+    int r = idx / NP, a = idx % NP;
+    sb[r][a] = w.Bt[((int64_t)blockIdx.y * TB + r) * NP + a];
+  }
+  __syncthreads();
+  double* out = P + ((int64_t)blockIdx.y * g.nbn + J) * (NP * TB);
   for (int idx = tid; idx < NP * TB; idx += NTHREADS) {
     int q = idx >> 6, c = idx & 63;
     double s = 0.0;
-    int jp = J * TB + c;
-    if (q < g.n && jp < g.mnew) {
-      int j = jp < g.p ? jp : jp + g.n;
-      for (int a = q; a < g.n; ++a)
-        if (j <= g.p + a) s += Mo[(int64_t)(g.p + a) * ld + g.p + q] * Mo[(int64_t)(g.p + a) * ld + j];
+    if (q < g.n) {
+#pragma unroll 8
+      for (int k = 0; k < TB; ++k) s += sb[k][q] * sT[k][c];
     }
-    sB[(TB + q) * LD_R + c] = s;
+    out[idx] = s;
+  }
+}
+
+// grid nbn (one CTA per column block), NP*64 threads: thread (q, c) walks down the row tiles.
+__global__ void __launch_bounds__(NP * TB) k_rm_hscan(const double* __restrict__ Mo, RmGeom g, const double* __restrict__ P,
+                                                      double* __restrict__ H) {
+  const int J = blockIdx.x, q = threadIdx.x >> 6, c = threadIdx.x & 63;
+  const int Ifirst = max(J, g.I0);
+  // carriers: rows p..p+n-1 contribute b_k[q] M[k, j]
+  double run = 0.0;
+  const int jp = J * TB + c;
+  if (q < g.n && jp < g.mnew) {
+    const int j = jp < g.p ? jp : jp + g.n;
+    for (int a = q; a < g.n; ++a)
+      if (j <= g.p + a) run += Mo[(int64_t)(g.p + a) * g.ld + g.p + q] * Mo[(int64_t)(g.p + a) * g.ld + j];
   }
   for (int I = Ifirst; I < g.nbn; ++I) {
-    const int64_t wrow = (int64_t)(I - g.I0) * TB;
-    __syncthreads();
+    const int64_t off = ((int64_t)(I - g.I0) * g.nbn + J) * (NP * TB) + threadIdx.x;
+    H[off] = run;
+    run += P[off];
+  }
+}
+
+constexpr int RM_APPLY_SMEM = (TB * LD_W + (TB + NP) * LD_R + TB * (NP + 1) + TB) * (int)sizeof(double);
+__global__ void __launch_bounds__(NTHREADS) k_rm_apply(const double* __restrict__ Mo, double* __restrict__ Mn, RmGeom g,
+                                                       RmWork w, const double* __restrict__ H) {
+  const int J = blockIdx.x, I = blockIdx.y, tid = threadIdx.x;
+  if (J > I) return;
+  const int64_t ld = g.ld;
+  if (I < g.I0) {  // rows above the deleted block: plain copy
     for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
       int r = idx >> 6, c = idx & 63;
-      sB[r * LD_R + c] = src(I * TB + r, J * TB + c);
+      Mn[(int64_t)(I * TB + r) * ld + J * TB + c] = rm_src(Mo, g, I * TB + r, J * TB + c);
     }
-    for (int idx = tid; idx < TB * NP; idx += NTHREADS) {
-      int r = idx / NP, a = idx % NP;
-      sb[r * (NP + 1) + a] = w.Bt[(wrow + r) * NP + a];
-      sA[r * LD_W + TB + a] = w.Gt[(wrow + r) * NP + a];
-    }
-    if (tid < TB) su[tid] = w.u[wrow + tid];
-    __syncthreads();
-    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
-      int r = idx >> 6, k = idx & 63;
-      double s = 0.0;
-      if (k < r) {
-#pragma unroll
-        for (int a = 0; a < NP; ++a) s += sA[r * LD_W + TB + a] * sb[k * (NP + 1) + a];
-      }
-      sA[r * LD_W + k] = s;
-    }
-    __syncthreads();
-    Acc64 acc;
-    acc.zero();
-    warp_mma<2, 4, true, false, TB + NP, LD_W, LD_R>(acc, sA, sB, warp_rb64(), warp_cb64());
-    for_each_acc64(acc, [&](int r, int c, double& v) {
-      Mn[(int64_t)(I * TB + r) * ld + J * TB + c] = su[r] * (sB[r * LD_R + c] - v);
-    });
-    __syncthreads();
-    // h += B_tile^T * old tile
-    for (int idx = tid; idx < NP * TB; idx += NTHREADS) {
-      int q = idx >> 6, c = idx & 63;
-      if (q < g.n) {
-        double s = sB[(TB + q) * LD_R + c];
-#pragma unroll 8
-        for (int k = 0; k < TB; ++k) s += sb[k * (NP + 1) + q] * sB[k * LD_R + c];
-        sB[(TB + q) * LD_R + c] = s;
-      }
-    }
+    return;
   }
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;                       // [64][LD_W]: S (cols 0..63) | G (cols 64..64+NP)
+  double* sB = sA + TB * LD_W;             // [64+NP][LD_R]: old tile (rows 0..63) ; H (rows 64..64+NP)
+  double* sb = sB + (TB + NP) * LD_R;      // [64][NP+1]
+  double* su = sb + TB * (NP + 1);         // [64]
+  const int64_t wrow = (int64_t)(I - g.I0) * TB;
+  const double* Hs = H + ((int64_t)(I - g.I0) * g.nbn + J) * (NP * TB);
+  for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+    int r = idx >> 6, c = idx & 63;
+    sB[r * LD_R + c] = rm_src(Mo, g, I * TB + r, J * TB + c);
+  }
+  for (int idx = tid; idx < NP * TB; idx += NTHREADS) sB[(TB + (idx >> 6)) * LD_R + (idx & 63)] = Hs[idx];
+  for (int idx = tid; idx < TB * NP; idx += NTHREADS) {
+    int r = idx / NP, a = idx % NP;
+    sb[r * (NP + 1) + a] = w.Bt[(wrow + r) * NP + a];
+    sA[r * LD_W + TB + a] = w.Gt[(wrow + r) * NP + a];
+  }
+  if (tid < TB) su[tid] = w.u[wrow + tid];
+  __syncthreads();
+  for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+    int r = idx >> 6, k = idx & 63;
+    double s = 0.0;
+    if (k < r) {
+#pragma unroll
+      for (int a = 0; a < NP; ++a) s += sA[r * LD_W + TB + a] * sb[k * (NP + 1) + a];
+    }
+    sA[r * LD_W + k] = s;
+  }
+  __syncthreads();
+  Acc64 acc;
+  acc.zero();
+  warp_mma<2, 4, true, false, TB + NP, LD_W, LD_R>(acc, sA, sB, warp_rb64(), warp_cb64());
+  for_each_acc64(acc, [&](int r, int c, double& v) {
+    Mn[(int64_t)(I * TB + r) * ld + J * TB + c] = su[r] * (sB[r * LD_R + c] - v);
+  });
 }
 
 // x, y of the result (new order = old order with the block dropped).
@@ -307,28 +340,46 @@ __global__ void k_pad_identity(double* __restrict__ M, int64_t ld, int from, int
   }
 }
 
-// Workspace of an append: S/Li [NP*NP] | znew [NP] | Ct [NP][mpad] | part [KS][NP][mpad]
+// Workspace of an append: Li [NP*NP] | znew [NP] | gpart [nblk][NG] | part [KS][NP][mpad]
 constexpr int APPEND_KS = 4;
+constexpr int AP_GRAM_ROWS = 256;
 struct ApWork {
-  double *Li, *znew, *Ct, *part;
+  double *Li, *znew, *gpart, *part;
 };
 
-// One CTA: S = Kss + (noise + 1e-8) I - T^T T, Ls = chol(S), Li = Ls^-1, znew = Li (y_B - mu_B), Ct = Li T^T.
-//   T[c*mpad + r] (column c = new point), mu[c] = predictive mean at x_B[c] (mean function included).
-__global__ void __launch_bounds__(256) k_append_small(const double* __restrict__ T, const double* __restrict__ mu, int mpad,
-                                                      const double* __restrict__ xB, const double* __restrict__ yB, int n,
-                                                      Theta th, ApWork w, int* __restrict__ info) {
-  __shared__ double S[NP][NP + 1], Li[NP][NP + 1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int npairs = n * (n + 1) / 2;
-  for (int t = warp; t < npairs; t += 8) {
+// Partial Gram matrices of T (n columns x mpad rows, T[c*mpad + r]): gpart[blk][(a,b)] over 256 rows.
+__global__ void __launch_bounds__(256) k_append_gram(const double* __restrict__ T, int mpad, int n, ApWork w) {
+  __shared__ double sT[NP][AP_GRAM_ROWS + 1];
+  const int r0 = blockIdx.x * AP_GRAM_ROWS;
+  for (int idx = threadIdx.x; idx < NP * AP_GRAM_ROWS; idx += 256) {
+    int a = idx / AP_GRAM_ROWS, r = idx % AP_GRAM_ROWS;
+    sT[a][r] = (a < n && r0 + r < mpad) ? T[(int64_t)a * mpad + r0 + r] : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < NG) {
     int a, b;
-    tri_unpack(t, a, b);
+    tri_unpack(threadIdx.x, a, b);
     double s = 0.0;
-    for (int r = lane; r < mpad; r += 32) s += T[(int64_t)a * mpad + r] * T[(int64_t)b * mpad + r];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
+    if (a < n) {
+#pragma unroll 8
+      for (int r = 0; r < AP_GRAM_ROWS; ++r) s += sT[a][r] * sT[b][r];
+    }
+    w.gpart[(int64_t)blockIdx.x * NG + threadIdx.x] = s;
+  }
+}
+
+// One CTA: S = Kss + (noise + 1e-8) I - T^T T, Ls = chol(S), Li = Ls^-1, znew = Li (y_B - mu_B).
+//   mu[c] = predictive mean at x_B[c] (mean function included).
+__global__ void __launch_bounds__(256) k_append_small(const double* __restrict__ mu, int nblk, const double* __restrict__ xB,
+                                                      const double* __restrict__ yB, int n, Theta th, ApWork w,
+                                                      int* __restrict__ info) {
+  __shared__ double S[NP][NP + 1], Li[NP][NP + 1];
+  if (threadIdx.x < NG) {
+    int a, b;
+    tri_unpack(threadIdx.x, a, b);
+    if (a < n) {
+      double s = 0.0;
+      for (int q = 0; q < nblk; ++q) s += w.gpart[(int64_t)q * NG + threadIdx.x];
       double k = kern_eval(th, xB[a], xB[b], a == b, nullptr);
       if (a == b) k = __dadd_rn(k, __dadd_rn(th.noise, GPY_JITTER));
       S[a][b] = k - s;
@@ -370,29 +421,36 @@ __global__ void __launch_bounds__(256) k_append_small(const double* __restrict__
       for (int q = 0; q <= (int)threadIdx.x; ++q) s += Li[threadIdx.x][q] * (yB[q] - mu[q]);
     w.znew[threadIdx.x] = s;
   }
-  for (int idx = threadIdx.x; idx < NP * mpad; idx += 256) {
-    int i = idx / mpad, k = idx % mpad;
-    double s = 0.0;
-    if (i < n)
-      for (int q = 0; q <= i; ++q) s += Li[i][q] * T[(int64_t)q * mpad + k];
-    w.Ct[(int64_t)i * mpad + k] = s;
-  }
 }
 
-// part[s][i][j] = sum over row blocks kb = J + s, J + s + KS, ... of Ct[i][kb-block] * M[kb-block][J-block].
-constexpr int AP_ROWS_SMEM = (TB * LD_R + NP * LD_C) * (int)sizeof(double);
-__global__ void __launch_bounds__(NTHREADS) k_append_rows(const double* __restrict__ M, int64_t ld, int nb, int mpad, ApWork w) {
+// part[s][i][j] = sum over row blocks kb = J + s, J + s + KS, ... of (Li T^T)[i][kb-block] * M[kb-block][J-block].
+constexpr int AP_ROWS_SMEM = (TB * LD_R + NP * LD_C + NP * LD_C) * (int)sizeof(double);
+__global__ void __launch_bounds__(NTHREADS) k_append_rows(const double* __restrict__ M, int64_t ld, int nb, int mpad,
+                                                          const double* __restrict__ T, int n, ApWork w) {
   extern __shared__ __align__(16) double smem[];
   double* sT = smem;               // M tile [k][c], LD_R
-  double* sC = sT + TB * LD_R;     // Ct tile [i][k], LD_C
+  double* sC = sT + TB * LD_R;     // (Li T^T) tile [i][k], LD_C
+  double* sR = sC + NP * LD_C;     // raw T tile [q][k], LD_C
+  __shared__ double sLi[NP][NP + 1];
   const int J = blockIdx.x, s = blockIdx.y;
+  if (threadIdx.x < NP * NP) sLi[threadIdx.x / NP][threadIdx.x % NP] = w.Li[threadIdx.x];
   Acc<2, 1> acc;
   acc.zero();
   const int warp = threadIdx.x >> 5;
   for (int kb = J + s; kb < nb; kb += APPEND_KS) {
     __syncthreads();
     load_tile<LD_R>(sT, M + (int64_t)kb * TB * ld + (int64_t)J * TB, ld);
-    load_tile<LD_C, NP>(sC, w.Ct + (int64_t)kb * TB, mpad);
+    for (int idx = threadIdx.x; idx < NP * TB; idx += NTHREADS) {
+      int q = idx >> 6, k = idx & 63;
+      sR[q * LD_C + k] = q < n ? T[(int64_t)q * mpad + kb * TB + k] : 0.0;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NP * TB; idx += NTHREADS) {
+      int i = idx >> 6, k = idx & 63;
+      double v = 0.0;
+      for (int q = 0; q <= i && q < n; ++q) v += sLi[i][q] * sR[q * LD_C + k];
+      sC[i * LD_C + k] = v;
+    }
     __syncthreads();
     warp_mma<2, 1, true, false>(acc, sC, sT, 0, warp * 8);
   }
