@@ -26,14 +26,19 @@ int refresh_vectors(mogp_engine* h, Cluster& c, bool recompute_z) {
     k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.x(), c.y(), (int)c.m, th, c.z());
     LAUNCHED(h);
   }
-  TRY(launch_alpha_lml(h, c));
+  TRY(launch_alpha(h, c));
   c.stat_on_device = true;
+  c.lml_dirty = true;
   c.grad_valid = false;
   return MOGP_OK;
 }
 
 int fetch_stat(mogp_engine* h, Cluster& c) {
   if (!c.stat_on_device) return MOGP_OK;
+  if (c.lml_dirty) {
+    TRY(launch_alpha_lml(h, c));
+    c.lml_dirty = false;
+  }
   TRY(ensure_pin(h, 256));
   CK(h, cudaMemcpyAsync(h->pin, c.stat(), sizeof(double) * 9, cudaMemcpyDeviceToHost, h->stream));
   CK(h, sync_stream(h));

@@ -45,6 +45,7 @@ struct Cluster {
   double grad[4] = {0, 0, 0, 0};
   bool grad_valid = false;
   bool stat_on_device = false;    // lml / quad / logdet of the last rank update not fetched yet
+  bool lml_dirty = false;         // ... and not even reduced yet (k_lml runs when somebody asks)
   double* x() const { return vec; }
   double* y() const { return vec + cap; }
   double* alpha() const { return vec + 2 * cap; }
@@ -293,6 +294,19 @@ int cluster_reserve(mogp_engine* h, Cluster& c, int64_t m_new, bool keep) {
   return MOGP_OK;
 }
 
+// alpha = M^T z only (after a rank update): the log marginal is reduced lazily, see fetch_stat.
+int launch_alpha(mogp_engine* h, Cluster& c) {
+  const int64_t mpad = round_up(c.m, TB);
+  const int nchunk = (int)((c.m + ALPHA_ROWS - 1) / ALPHA_ROWS);
+  TRY(ensure(h, &h->d_apart, &h->apart_elems, (int64_t)nchunk * mpad));
+  k_alpha_part<<<dim3((unsigned)(mpad / TB), (unsigned)nchunk), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.z(), (int)c.m,
+                                                                                           (int)mpad, h->d_apart);
+  LAUNCHED(h);
+  k_alpha_reduce<<<(unsigned)((c.m + 255) / 256), 256, 0, h->stream>>>(h->d_apart, nchunk, (int)mpad, c.alpha(), (int)c.m);
+  LAUNCHED(h);
+  return MOGP_OK;
+}
+
 // alpha = M^T z (two stages) and the log marginal likelihood from the current M and z.
 int launch_alpha_lml(mogp_engine* h, Cluster& c) {
   const int64_t mpad = round_up(c.m, TB);
@@ -351,6 +365,7 @@ int infer(mogp_engine* h, Cluster& c) {
       c.logdet = hs[2];
       c.valid = true;
       c.stat_on_device = false;
+      c.lml_dirty = false;
       return MOGP_OK;
     }
     // jitchol: fail at once on a non-positive diagonal, else retry with growing jitter
@@ -370,8 +385,11 @@ int infer(mogp_engine* h, Cluster& c) {
 }
 
 // Gradient of the log marginal likelihood w.r.t. natural theta at the current factor.
+int fetch_stat(mogp_engine* h, Cluster& c);
+
 int infer_grad(mogp_engine* h, Cluster& c) {
   if (!c.valid) TRY(infer(h, c));
+  TRY(fetch_stat(h, c));  // x.alpha of a rank-updated cluster is reduced lazily
   const int64_t mpad = round_up(c.m, TB);
   const int nb = (int)(mpad / TB);
   const int nz = (nb + GRAD_KC - 1) / GRAD_KC;
@@ -540,7 +558,7 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
     default: launch_score_gemm<64>(h, pl, pl.T); break;
   }
   const int64_t pairs = n_pat * n_slots;
-  k_score_epi<<<(unsigned)((pairs + 255) / 256), 256, 0, h->stream>>>(h->d_slots, n_slots, off_dev, n_pat, xs_dev, ys_dev,
+  k_score_epi<<<(unsigned)((pairs + 7) / 8), 256, 0, h->stream>>>(h->d_slots, n_slots, off_dev, n_pat, xs_dev, ys_dev,
                                                                      (int)pl.Rpad, pl.part, pl.mupart, pl.max_rblk, pl.mu,
                                                                      thr_index, score_dev,
                                                                      mu_thr_dev, col_mean, col_var, col_lpd);

@@ -200,6 +200,16 @@ __global__ void __launch_bounds__(NTHREADS) k_alpha_part(const double* __restric
   }
 }
 
+// alpha[i] = sum of the row-chunk partials (fixed order).
+__global__ void __launch_bounds__(256) k_alpha_reduce(const double* __restrict__ apart, int nchunk, int mpad,
+                                                      double* __restrict__ alpha, int m) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  double a = 0.0;
+  for (int c = i / ALPHA_ROWS; c < nchunk; ++c) a += apart[(int64_t)c * mpad + i];
+  alpha[i] = a;
+}
+
 // One CTA: alpha = sum of the row-chunk partials; quad = z.z, logdet = 2 sum ln L_ii = -2 sum ln M_ii,
 // sxa = sum x_i alpha_i, LML.  out[0..3].
 __global__ void __launch_bounds__(1024) k_lml(const double* __restrict__ M, int64_t ld, const double* __restrict__ z,

@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_score_gemm(const SlotView* __re
   }
 }
 
-// Per (patient, slot): finish the predictive moments and sum the per-visit log densities.
+// Per (patient, slot): finish the predictive moments and sum the per-visit log densities.  One warp per pair:
+// lanes take the patient's visits (columns), each sums its column's row-block partials in a fixed order, the
+// visit log densities are added across the warp by a shuffle tree (deterministic).
 // Optional per-column outputs (mean, var incl. noise, lpd) serve predict / log_predictive_density.
 __global__ void __launch_bounds__(256) k_score_epi(const SlotView* __restrict__ slots, int n_slots,
                                                    const int64_t* __restrict__ off, int64_t n_pat,
@@ -184,22 +186,23 @@ __global__ void __launch_bounds__(256) k_score_epi(const SlotView* __restrict__ 
                                                    double* __restrict__ score, double* __restrict__ mu_thr,
                                                    double* __restrict__ col_mean, double* __restrict__ col_var,
                                                    double* __restrict__ col_lpd) {
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (gid >= n_pat * n_slots) return;
   const int64_t p = gid / n_slots;
   const int c = (int)(gid % n_slots);
   const SlotView sv = slots[c];
   const int nb = sv.mpad / TB;
+  const int nrb = (sv.mpad + KX_ROWS - 1) / KX_ROWS;
   const int64_t c0 = off[p] - off[0], c1 = off[p + 1] - off[0];
   double total = 0.0;
-  for (int64_t col = c0; col < c1; ++col) {
+  for (int64_t col = c0 + lane; col < c1; col += 32) {
     double ss = 0.0;
     for (int rb = 0; rb < nb; ++rb) ss += part[sv.part_off + (int64_t)rb * Rpad + col];
     double v = kern_diag(sv.th, xs[col]) - ss;
     v = v > 1e-15 ? v : 1e-15;  // Posterior._raw_predict clips the variance
     const double vn = v + sv.th.noise;
     double m = 0.0;
-    const int nrb = (sv.mpad + KX_ROWS - 1) / KX_ROWS;
     for (int rb = 0; rb < nrb; ++rb) m += mupart[((int64_t)c * max_rblk + rb) * Rpad + col];
     if (sv.th.mean_func) m += xs[col] * (-sv.th.A);  // + m(x*) = -A x*  (neg_linear.py:22-23)
     mu[(int64_t)c * Rpad + col] = m;
@@ -209,11 +212,13 @@ __global__ void __launch_bounds__(256) k_score_epi(const SlotView* __restrict__ 
     if (col_mean) col_mean[(int64_t)c * Rpad + col] = m;
     if (col_var) col_var[(int64_t)c * Rpad + col] = vn;
     if (col_lpd) col_lpd[(int64_t)c * Rpad + col] = lpd;
+    if (mu_thr && col == c0 + thr_index) mu_thr[gid] = m;
   }
-  if (score) score[gid] = total;
-  if (mu_thr) {  // (written by this thread in the loop above)
-    const int64_t ct = c0 + thr_index;
-    mu_thr[gid] = (thr_index >= 0 && ct < c1) ? mu[(int64_t)c * Rpad + ct] : nan("");
+#pragma unroll
+  for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  if (lane == 0) {
+    if (score) score[gid] = total;
+    if (mu_thr && !(thr_index >= 0 && c0 + thr_index < c1)) mu_thr[gid] = nan("");
   }
 }
 

@@ -5,7 +5,7 @@ from mogp_b200 import _capi
 from mogp_b200.obsmodel import make_spec
 eng=_capi.Engine(0)
 spec=make_spec('rbf',True,True,False)
-for m in [19000, 24000]:
+for m in [2600]:
     rs=np.random.RandomState(m)
     x=np.sort(rs.uniform(0,8,m)); x[:m//8]=0.0
     y=(48-6*x+rs.randn(m)*3-30)/20
