@@ -37,6 +37,12 @@ def parse():
     ap.add_argument("--clusters", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=12, help="patient-steps of the bounded CPU sample")
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "predict", "chains"],
+                    help="sweep: the headline (BASELINE configs[2]); predict: batch prediction, patients sharded "
+                         "(configs[4]); chains: independent 2k-patient chains dealt to the GPUs (configs[3])")
+    ap.add_argument("--query-patients", type=int, default=1000000)
+    ap.add_argument("--chains", type=int, default=64)
+    ap.add_argument("--chain-patients", type=int, default=2000)
     return ap.parse_args()
 
 
@@ -289,10 +295,163 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------
+def run_predict(args):
+    """configs[4]: P synthetic patients scored against a random-init 40-cluster model, patients sharded across the
+    ranks (no collective on the data path), one all_gather of the probability matrix at the end."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mogp_b200 import _capi, MoGP_constrained, parallel
+    from mogp_b200.synth import alsfrs_like, alsfrs_like_fast
+    from mogp_b200.utils import pack_patients
+    K = 40
+    eng = _capi.Engine(local)
+    Xt, Yt, z0 = alsfrs_like(3000, seed=0, n_classes=K, return_labels=True)
+    z0 = np.unique(z0, return_inverse=True)[1].astype(np.int32)
+    mix = MoGP_constrained(X=Xt, Y=Yt, alpha=K / np.log10(3000), rand_seed=0, normalize=True, noise_variance=0.5,
+                           init_z=z0, engine=eng)
+    mix.initialize_sampler(K, True)
+    rs = np.random.RandomState(1)
+    _z, Nk, slots = eng.chain_state(3000)
+    for k in np.where(Nk > 0)[0]:          # theta_k around the priors' means (SURVEY.md §8d cfg5)
+        eng.cluster_set_theta(int(slots[k]), np.array([rs.gamma(2.22, 1 / 3.33), 1.0, rs.gamma(1.78, 1 / 0.444) + 0.3,
+                                                       rs.gamma(9., 1 / 12.)]))
+    P = args.query_patients
+    Xq, Yq = alsfrs_like_fast(P, seed=2, n_classes=K)
+    a = np.random.RandomState(3).randn(P)
+    lo, hi = parallel.shard_bounds(P, world, rank)
+
+    def barrier():
+        eng.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nq = hi - lo
+    for _ in range(max(1, args.warmup)):
+        mix.predict_batch(Xq[lo:lo + min(nq, 20000)], Yq[lo:lo + min(nq, 20000)], a[lo:lo + min(nq, 20000)])
+    barrier()
+    l0 = eng.launch_count(); b0 = eng.transfer_bytes()
+    eng.profile(True); eng.profile_read(reset=True)
+    eng.timer_start()
+    for _ in range(args.steps):
+        probs = mix.predict_batch(Xq[lo:hi], Yq[lo:hi], a[lo:hi])
+    ms = eng.timer_stop()
+    prof = eng.profile_read(reset=True); eng.profile(False)
+    b1 = eng.transfer_bytes()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    full = parallel.all_gather_rows(probs, P) if world > 1 else probs
+    barrier()
+    if rank == 0:
+        n_act = int((Nk > 0).sum())
+        pairs = float(P) * n_act * args.steps
+        peak = 37.0
+        line = {"metric": "patient x cluster logliks/sec (batch prediction)", "value": pairs / (float(t.item()) * 1e-3),
+                "unit": "logliks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": float(t.item()) / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "batch prediction: {} synthetic patients x {} clusters (m_k ~ {}), patients sharded"
+                                       .format(P, n_act, int(np.mean([eng.cluster_size(int(s)) for s in slots if s >= 0])))},
+                "e2e": {"value": pairs / (float(t.item()) * 1e-3), "unit": "logliks/s",
+                        "h2d_bytes_per_step": (b1[0] - b0[0]) // args.steps, "d2h_bytes_per_step": (b1[1] - b0[1]) // args.steps},
+                "gpu_launches": int(eng.launch_count() - l0),
+                "roofline": {"kernel": "k_score_gemm<64>", "bound": "fp64", "achieved": prof["alg_flops"] / (prof["ms"] * 1e-3) / 1e12,
+                             "peak": peak, "unit": "TFLOP/s", "frac": prof["alg_flops"] / (prof["ms"] * 1e-3) / 1e12 / peak,
+                             "traffic": None, "peak_source": "nominal B200 FP64 (no measured FP64 peak in MEASURED_PEAKS.json)",
+                             "share_of_step": prof["ms"] / ms},
+                "check": {"rows_sum_to_one": bool(np.allclose(full.sum(1), 1.0, atol=1e-9)), "shape": list(full.shape)}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_chains(args):
+    """configs[3]: independent chains (seed = chain id) of `chain-patients` patients dealt round-robin to the
+    ranks; within a rank the chains run concurrently, one engine (stream) and one host thread each."""
+    import torch
+    import torch.distributed as dist
+    from concurrent.futures import ThreadPoolExecutor
+    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mogp_b200 import _capi, MoGP, parallel
+    from mogp_b200.synth import alsfrs_like
+    mine = parallel.chains_for_rank(args.chains, world, rank)
+    N = args.chain_patients
+    K0 = max(1, round(N / 50))
+
+    def make(cid):
+        eng = _capi.Engine(local)
+        X, Y, z0 = alsfrs_like(N, seed=100 + cid, n_classes=K0, return_labels=True)
+        z0 = np.unique(z0, return_inverse=True)[1].astype(np.int32)
+        mix = MoGP(X=X, Y=Y, alpha=K0 / np.log10(N), rand_seed=cid, normalize=True, noise_variance=0.5, refit='sweep',
+                   init_z=z0, engine=eng)
+        np.random.seed(cid)
+        mix.initialize_sampler(K0, True)
+        rs = np.random.RandomState(cid)
+        return eng, mix, rs
+
+    chains = [make(c) for c in mine]
+
+    def sweep(item):
+        eng, mix, rs = item
+        perm = rs.permutation(N)
+        u = rs.random_sample(N)
+        mix.sweep(perm, np.zeros(N), u)
+        return eng.launch_count()
+
+    pool = ThreadPoolExecutor(max_workers=max(1, len(chains)))
+    for _ in range(args.warmup):
+        list(pool.map(sweep, chains))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = sum(c[0].launch_count() for c in chains)
+    t0 = time.perf_counter()
+    start = torch.cuda.Event(enable_timing=True); stop = torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        list(pool.map(sweep, chains))
+    for c in chains:
+        c[0].sync()
+    stop.record(); torch.cuda.synchronize()
+    ms = max(start.elapsed_time(stop), (time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = parallel.gather_chain_results({c: dict(z=chains[i][1].z, Nk=chains[i][1].allocmodel.Nk) for i, c in enumerate(mine)},
+                                        args.chains)
+    if rank == 0:
+        line = {"metric": "Gibbs sweeps/sec over independent chains", "value": args.chains * args.steps / (float(t.item()) * 1e-3),
+                "unit": "chain-sweeps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": float(t.item()) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "{} independent MoGP (unconstrained) chains x {} patients, refit every sweep, "
+                                       "dealt round-robin to the GPUs".format(args.chains, N)},
+                "gpu_launches": int(sum(c[0].launch_count() for c in chains) - l0),
+                "check": {"chains_gathered": len(res), "active_clusters_chain0": int((res[0]['Nk'] > 0).sum())}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "predict":
+        run_predict(args)
+    elif args.workload == "chains":
+        run_chains(args)
     else:
         run_b200(args)
 

@@ -234,6 +234,7 @@ Theta newcomer_theta(const mogp_chain_config& cfg) {
 
 int chain_check(mogp_engine* h, int64_t n) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (!h->chain.active) FAIL(h, MOGP_ESTATE, "no chain attached");
   if (n < 0 || n >= h->chain.N) FAIL(h, MOGP_EINVAL, "patient %lld out of range", (long long)n);
   return MOGP_OK;
@@ -459,6 +460,7 @@ int mogp_host_choice(const double* score, int32_t n, double u, double* p_out, in
 int mogp_chain_init(mogp_engine* h, const mogp_chain_config* cfg, int64_t n_patients, const int32_t* z, int32_t n_ids,
                     const double* theta_of_id) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (!cfg || !z || n_ids <= 0 || !theta_of_id) FAIL(h, MOGP_EINVAL, "null argument");
   if (h->P <= 0 || n_patients != h->P) FAIL(h, MOGP_EINVAL, "chain needs the patient table (%lld patients set)", (long long)h->P);
   if (cfg->use_threshold && h->h_ythr.empty()) FAIL(h, MOGP_EINVAL, "threshold rule needs y_thr in mogp_set_patients");
@@ -497,6 +499,7 @@ int mogp_chain_step_begin(mogp_engine* h, int64_t n) {
 
 int mogp_chain_step_score(mogp_engine* h, double a_draw, int32_t* n_active, int32_t* ids_out, double* score_out, int32_t cap_out) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (!h->chain.active) FAIL(h, MOGP_ESTATE, "no chain attached");
   TRY(chain_score(h, a_draw));
   Chain& ch = h->chain;
@@ -512,6 +515,7 @@ int mogp_chain_step_score(mogp_engine* h, double a_draw, int32_t* n_active, int3
 
 int mogp_chain_step_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_new) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (!h->chain.active) FAIL(h, MOGP_ESTATE, "no chain attached");
   return chain_commit(h, chosen_id, a_draw, is_new);
 }
@@ -543,6 +547,7 @@ int mogp_chain_step(mogp_engine* h, int64_t n, double a_draw, double u, int32_t*
 int mogp_chain_sweep(mogp_engine* h, int64_t n_steps, const int64_t* order, const double* a_draw, const double* u,
                      int32_t* chosen_ids, double* min_margin) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (!order || !u || n_steps < 0) FAIL(h, MOGP_EINVAL, "null argument");
   if (h->chain.active && h->chain.cfg.spec.mean_func && !a_draw) FAIL(h, MOGP_EINVAL, "mean_func needs a_draw");
   double mm = INFINITY;
@@ -558,6 +563,7 @@ int mogp_chain_sweep(mogp_engine* h, int64_t n_steps, const int64_t* order, cons
 
 int mogp_chain_get_state(mogp_engine* h, int32_t* z, int64_t* Nk, int32_t* slot_of_id, int32_t cap_ids, int32_t* n_ids) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (!h->chain.active) FAIL(h, MOGP_ESTATE, "no chain attached");
   Chain& ch = h->chain;
   const int32_t k = (int32_t)ch.Nk.size();

@@ -250,6 +250,7 @@ Theta make_theta(const Cluster& c) {
 
 int check_slot(mogp_engine* h, int32_t slot) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // every cluster entry point comes through here; callers may be on any host thread
   if (slot < 0 || slot >= (int32_t)h->cl.size() || !h->cl[slot].used) FAIL(h, MOGP_EINVAL, "bad cluster slot %d", slot);
   return MOGP_OK;
 }
@@ -676,11 +677,13 @@ int64_t mogp_launch_count(const mogp_engine* h) { return h ? h->launches : 0; }
 
 int mogp_sync(mogp_engine* h) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   CK(h, sync_stream(h));
   return MOGP_OK;
 }
 int mogp_timer_start(mogp_engine* h) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   CK(h, cudaEventRecord(h->ev0, h->stream));
   return MOGP_OK;
 }
@@ -714,6 +717,7 @@ static int upload_patients(mogp_engine* h, int64_t n_patients, const int64_t* of
 int mogp_set_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x, const double* y,
                       const double* y_thr) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (n_patients <= 0 || !off || !x || !y || off[0] != 0) FAIL(h, MOGP_EINVAL, "bad patient table");
   for (int64_t p = 0; p < n_patients; ++p)
     if (off[p + 1] < off[p]) FAIL(h, MOGP_EINVAL, "offsets must be non-decreasing");
@@ -743,6 +747,7 @@ int mogp_set_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, co
    host->device copy of an end-to-end run whose data live in host memory. */
 int mogp_refresh_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x, const double* y) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (n_patients != h->P || !off || !x || !y || off[n_patients] != h->V) FAIL(h, MOGP_EINVAL, "patient table shape changed");
   if (memcmp(off, h->h_off.data(), sizeof(int64_t) * (n_patients + 1)) != 0) FAIL(h, MOGP_EINVAL, "patient offsets changed");
   return upload_patients(h, n_patients, off, x, y);
@@ -750,6 +755,7 @@ int mogp_refresh_patients(mogp_engine* h, int64_t n_patients, const int64_t* off
 
 int mogp_profile(mogp_engine* h, int32_t enable) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   prof_drain(h);
   h->prof_on = enable != 0;
   return MOGP_OK;
@@ -757,6 +763,7 @@ int mogp_profile(mogp_engine* h, int32_t enable) {
 
 int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg_bytes, double* alg_flops, int32_t reset) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   prof_drain(h);
   if (launches) *launches = h->prof_launches;
   if (ms) *ms = h->prof_ms;
@@ -771,6 +778,7 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
 
 int mogp_transfer_bytes(mogp_engine* h, int64_t* h2d, int64_t* d2h) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (h2d) *h2d = h->bytes_h2d;
   if (d2h) *d2h = h->bytes_d2h;
   return MOGP_OK;
@@ -779,6 +787,7 @@ int mogp_transfer_bytes(mogp_engine* h, int64_t* h2d, int64_t* d2h) {
 // ---- clusters -----------------------------------------------------------------------------------------------
 int mogp_cluster_create(mogp_engine* h, const mogp_model_spec* spec, const double theta[4], int32_t* slot_out) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (!spec || !theta || !slot_out) FAIL(h, MOGP_EINVAL, "null argument");
   if (spec->kernel != MOGP_KERNEL_RBF && spec->kernel != MOGP_KERNEL_LINEAR) FAIL(h, MOGP_EINVAL, "unknown kernel %d", spec->kernel);
   int32_t slot = -1;
@@ -1047,6 +1056,7 @@ int mogp_score_pairs_dev(mogp_engine* h, int64_t n_patients, int64_t n_visits, c
                          const double* y_dev, int32_t n_slots, const int32_t* slots, int32_t thr_index, double* score_dev,
                          double* mu_thr_dev) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (n_patients <= 0 || n_visits <= 0 || !off_dev || !x_dev || !y_dev || n_slots <= 0 || !slots || !score_dev)
     FAIL(h, MOGP_EINVAL, "bad arguments");
   return score_device(h, n_patients, n_visits, off_dev, x_dev, y_dev, n_slots, slots, thr_index, score_dev, mu_thr_dev,
@@ -1056,6 +1066,7 @@ int mogp_score_pairs_dev(mogp_engine* h, int64_t n_patients, int64_t n_visits, c
 int mogp_score_pairs(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x, const double* y, int32_t n_slots,
                      const int32_t* slots, int32_t thr_index, double* score, double* mu_thr) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (n_patients <= 0 || !off || !x || !y || n_slots <= 0 || !slots || !score) FAIL(h, MOGP_EINVAL, "bad arguments");
   // Chunk the patients so the cross-covariance scratch stays bounded (~2 GiB).
   int64_t msum = 0;
@@ -1092,6 +1103,7 @@ int mogp_score_pairs(mogp_engine* h, int64_t n_patients, const int64_t* off, con
 int mogp_new_cluster_ll(mogp_engine* h, const mogp_model_spec* spec, const double theta[4], int64_t n_patients, const int64_t* off,
                         const double* x, const double* y, const double* a_draw, double* ll) {
   if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (!spec || !theta || n_patients <= 0 || !off || !x || !y || !ll) FAIL(h, MOGP_EINVAL, "bad arguments");
   if (spec->mean_func && !a_draw) FAIL(h, MOGP_EINVAL, "mean_func needs the randn draws of the NegLinear mapping");
   for (int64_t p = 0; p < n_patients; ++p)

@@ -63,3 +63,35 @@ def block_init(n_patients, n_clusters, X=None):
     z = np.empty(n_patients, dtype=np.int32)
     z[order] = (np.arange(n_patients) * n_clusters // n_patients).astype(np.int32)
     return z
+
+
+def alsfrs_like_fast(n_patients, seed=0, max_visits=10, min_visits=3, n_classes=30):
+    """Vectorised variant of `alsfrs_like` for very large query sets (batch prediction, 1M patients):
+    same shape (onset anchor + 3..10 visits in (0, 8], NaN-padded to 11 columns), class-structured."""
+    rs = np.random.RandomState(seed)
+    T = max_visits + 1
+    nv = rs.randint(min_visits, max_visits + 1, n_patients)
+    t0 = rs.uniform(0.2, 3.0, n_patients)
+    gaps = rs.uniform(0.1, 1.0, (n_patients, max_visits))
+    gaps[:, 0] = 0.0
+    t = t0[:, None] + np.cumsum(gaps, axis=1)
+    last = t[np.arange(n_patients), nv - 1]
+    scale = np.where(last > 8.0, (8.0 - t0) / np.maximum(last - t0, 1e-12), 1.0)
+    t = t0[:, None] + (t - t0[:, None]) * scale[:, None]
+    c = rs.randint(n_classes, size=n_patients)
+    fam = c % 3
+    q = (c // 3) / max(1, (n_classes + 2) // 3 - 1) if n_classes > 3 else np.full(n_patients, 0.5)
+    rate = (0.3 + 1.5 * q) * rs.uniform(0.97, 1.03, n_patients)
+    mid = np.where(fam == 1, 1.0 + 2.0 * q, 3.0 + 3.0 * q)
+    lin = 48.0 - 6.0 * rate[:, None] * t
+    sig1 = 48.0 / (1.0 + np.exp(2.0 * rate[:, None] * (t - mid[:, None])))
+    sig2 = 48.0 / (1.0 + np.exp(1.5 * rate[:, None] * (t - mid[:, None])))
+    f = np.where(fam[:, None] == 0, lin, np.where(fam[:, None] == 1, sig1, sig2))
+    y = np.clip(np.round(f + rs.randn(n_patients, max_visits) * 1.5), 0, 48)
+    mask = np.arange(max_visits)[None, :] < nv[:, None]
+    X = np.full((n_patients, T), np.nan)
+    Y = np.full((n_patients, T), np.nan)
+    X[:, 0], Y[:, 0] = 0.0, 48.0
+    X[:, 1:] = np.where(mask, t, np.nan)
+    Y[:, 1:] = np.where(mask, y, np.nan)
+    return X, Y
