@@ -188,13 +188,18 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    split = [0.0, 0.0]   # host wall time in the patient steps / in the refits
+
     def device_sweep():
         """value path: C-ABI chain sweep over the resident patient table + refit of every active cluster."""
         perm, a, u = mix._draws_for_sweep(N)
+        t0 = time.perf_counter()
         eng.chain_sweep(perm, a, u)
         mix._sync_state()
-        for k in mix._active():
-            mix.obsmodel[k].model.optimize()
+        t1 = time.perf_counter()
+        mix.refit_all()
+        split[0] += t1 - t0
+        split[1] += time.perf_counter() - t1
 
     def e2e_sweep():
         """public API with host buffers: patient table host->device, sweep, results device->host."""
@@ -211,7 +216,11 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = eng.launch_count()
+    def all_launches():   # the chain's engine + the worker engines of the concurrent refit
+        return eng.launch_count() + sum(w.launch_count() for w in (mix._workers or []))
+
+    l0 = all_launches()
+    split[0] = split[1] = 0.0
     eng.profile(True)
     eng.profile_read(reset=True)
     eng.timer_start()
@@ -220,7 +229,8 @@ def run_b200(args):
     ms = eng.timer_stop()
     prof = eng.profile_read(reset=True)
     eng.profile(False)
-    launches = eng.launch_count() - l0
+    launches = all_launches() - l0
+    split_timed = (split[0] / args.steps, split[1] / args.steps)
     barrier()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -281,7 +291,8 @@ def run_b200(args):
                 "clocks": clocks,
                 "chain": {"active_clusters": len(occupancy), "patients_moved_in_timed_sweeps": moved,
                           "pair_logliks_per_s": world * args.steps * N * len(occupancy) / (ms_max * 1e-3),
-                          "refit_evals": int(mix.n_refit_evals), "total_loglik": ll}}
+                          "refit_evals": int(mix.n_refit_evals), "total_loglik": ll,
+                          "steps_s_per_sweep": split_timed[0], "refit_s_per_sweep": split_timed[1]}}
         if world == 1 and not args.no_cpu_baseline:
             orc, _t_init = oracle_sample(args, 0)
             ts, tr, nact, evals = oracle_step_times(orc, args.cpu_steps, 1)

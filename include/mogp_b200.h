@@ -118,6 +118,12 @@ int mogp_cluster_loglik(mogp_engine* h, int32_t slot, double* lml);
    and df/dt at optimiser coordinates t (Logexp space, free parameters only, GPy order).
    Leaves the cluster at theta(t), like paramz does.  *n_free_out = number of free parameters. */
 int mogp_cluster_objective(mogp_engine* h, int32_t slot, const double* t, int32_t n_t, double* f, double* g);
+/* The same evaluation for a cluster of `owner`, run on `worker`'s stream and workspaces (same device).  The
+   refits of different clusters are independent (obsmodel.py:94 is per cluster): a caller may evaluate several
+   clusters concurrently, one host thread + one worker engine each, provided the owner's stream is idle
+   (mogp_sync) and no two threads touch the same slot. */
+int mogp_cluster_objective_on(mogp_engine* worker, mogp_engine* owner, int32_t slot, const double* t, int32_t n_t,
+                              double* f, double* g);
 int mogp_cluster_n_free(mogp_engine* h, int32_t slot);
 /* Current optimiser coordinates t = Logexp^-1(theta) of the free parameters. */
 int mogp_cluster_get_optimizer_array(mogp_engine* h, int32_t slot, double* t, int32_t* n_t);

@@ -66,6 +66,7 @@ SIGNATURES = {
     "mogp_cluster_get_data": (C.c_int, [_H, C.c_int32, _dp, _dp]),
     "mogp_cluster_loglik": (C.c_int, [_H, C.c_int32, _dp]),
     "mogp_cluster_objective": (C.c_int, [_H, C.c_int32, _dp, C.c_int32, _dp, _dp]),
+    "mogp_cluster_objective_on": (C.c_int, [_H, _H, C.c_int32, _dp, C.c_int32, _dp, _dp]),
     "mogp_cluster_n_free": (C.c_int, [_H, C.c_int32]),
     "mogp_cluster_get_optimizer_array": (C.c_int, [_H, C.c_int32, _dp, _ip]),
     "mogp_cluster_lml_grad": (C.c_int, [_H, C.c_int32, _dp]),
@@ -262,15 +263,22 @@ class Engine:
         self.check(self.lib.mogp_cluster_get_optimizer_array(self.h, slot, dptr(t), C.byref(n)))
         return t[:n.value].copy()
 
-    def cluster_objective(self, slot, t=None, want_grad=True):
+    def cluster_objective(self, slot, t=None, want_grad=True, worker=None):
+        """(f, df/dt) of cluster `slot`; with `worker` (another Engine on the same device) the evaluation runs
+        on the worker's stream and workspaces, so several clusters can be refitted concurrently."""
         f = C.c_double()
         nfree = self.cluster_n_free(slot)
         g = np.empty(max(nfree, 1))
         if t is not None:
             t = f64(t)
-        rc = self.lib.mogp_cluster_objective(self.h, slot, dptr(t), 0 if t is None else t.size, C.byref(f),
-                                             dptr(g) if want_grad else None)
-        self.check(rc)
+        if worker is None:
+            rc = self.lib.mogp_cluster_objective(self.h, slot, dptr(t), 0 if t is None else t.size, C.byref(f),
+                                                 dptr(g) if want_grad else None)
+            self.check(rc)
+        else:
+            rc = self.lib.mogp_cluster_objective_on(worker.h, self.h, slot, dptr(t), 0 if t is None else t.size,
+                                                    C.byref(f), dptr(g) if want_grad else None)
+            worker.check(rc)
         return f.value, g[:nfree].copy()
 
     def cluster_predict(self, slot, xs):

@@ -987,9 +987,9 @@ int mogp_cluster_get_optimizer_array(mogp_engine* h, int32_t slot, double* t, in
   return MOGP_OK;
 }
 
-int mogp_cluster_objective(mogp_engine* h, int32_t slot, const double* t, int32_t n_t, double* f, double* g) {
-  TRY(check_slot(h, slot));
-  Cluster& c = h->cl[slot];
+// hw supplies the stream and the workspaces, c is the cluster (of hw itself or of another engine on the device).
+static int objective_impl(mogp_engine* hw, Cluster& c, const double* t, int32_t n_t, double* f, double* g) {
+  mogp_engine* h = hw;
   Gamma pr[4];
   bool fixed[4];
   priors_of(c.spec, pr, fixed);
@@ -1021,6 +1021,20 @@ int mogp_cluster_objective(mogp_engine* h, int32_t slot, const double* t, int32_
       if (!fixed[i]) g[q++] = -(c.grad[i] + dlp[i]) * logexp_gradfactor(c.theta[i]);
   }
   return MOGP_OK;
+}
+
+int mogp_cluster_objective(mogp_engine* h, int32_t slot, const double* t, int32_t n_t, double* f, double* g) {
+  TRY(check_slot(h, slot));
+  return objective_impl(h, h->cl[slot], t, n_t, f, g);
+}
+
+int mogp_cluster_objective_on(mogp_engine* worker, mogp_engine* owner, int32_t slot, const double* t, int32_t n_t, double* f,
+                              double* g) {
+  if (!worker || !owner) return MOGP_EINVAL;
+  cudaSetDevice(worker->device);
+  if (worker->device != owner->device) FAIL(worker, MOGP_EINVAL, "worker and owner engines must be on the same device");
+  if (slot < 0 || slot >= (int32_t)owner->cl.size() || !owner->cl[slot].used) FAIL(worker, MOGP_EINVAL, "bad cluster slot %d", slot);
+  return objective_impl(worker, owner->cl[slot], t, n_t, f, g);
 }
 
 int mogp_cluster_log_predictive_density(mogp_engine* h, int32_t slot, int64_t n, const double* xs, const double* ys,

@@ -22,7 +22,7 @@ from scipy.special import logsumexp
 
 from . import _capi
 from .allocmodel import DPmix
-from .obsmodel import GPobs, Standardize, make_spec, initial_theta
+from .obsmodel import GPobs, Standardize, make_spec, initial_theta, optimize_many
 from .utils import pack_patients
 
 
@@ -62,6 +62,8 @@ class MoGP_constrained:
         self.ll = []
         self.burnin = 25
         self.trace = []
+        self.refit_concurrency = 12    # worker engines (streams) for the end-of-sweep refits
+        self._workers = None
         self.min_margin = np.inf       # smallest |u - cdf edge| seen (assignment-parity diagnostic)
         self.n_refit_evals = 0
 
@@ -140,6 +142,7 @@ class MoGP_constrained:
     def __getstate__(self):
         st = dict(self.__dict__)
         st['_engine'] = None
+        st['_workers'] = None
         return st
 
     # -- engine plumbing ---------------------------------------------------------------------------------
@@ -248,10 +251,25 @@ class MoGP_constrained:
             _chosen, mm = eng.chain_sweep(perm, a if self.mean_func else None, u)
             self.min_margin = min(self.min_margin, mm)
             self._sync_state()
-            for k in self._active():                               # end-of-sweep refit, id order
-                self.obsmodel[k].model.optimize()
-                self.n_refit_evals += self.obsmodel[k].model.n_evals
-                self.obsmodel[k].model.n_evals = 0
+            self.refit_all()
+
+    def refit_all(self):
+        """refit='sweep': one L-BFGS-B refit per active cluster (independent; run concurrently on worker engines)."""
+        models = [self.obsmodel[k].model for k in self._active()]
+        optimize_many(models, self._refit_workers(len(models)))
+        for m in models:
+            self.n_refit_evals += m.n_evals
+            m.n_evals = 0
+
+    def _refit_workers(self, n_models):
+        want = min(self.refit_concurrency, n_models)
+        if want <= 1:
+            return []
+        if not hasattr(self, '_workers') or self._workers is None:
+            self._workers = []
+        while len(self._workers) < want:
+            self._workers.append(_capi.Engine(self.engine.device))
+        return self._workers[:want]
 
     def _refit_id(self, k):
         _z, _Nk, slots = self.engine.chain_state(self.allocmodel.N)

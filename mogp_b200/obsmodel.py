@@ -107,12 +107,12 @@ class GPModel:
     def objective_function(self):
         return self._engine.cluster_objective(self._slot, None, want_grad=False)[0]
 
-    def objective_grads(self, t):
+    def objective_grads(self, t, worker=None):
         """paramz Model._objective_grads: (f, df/dt) in Logexp space; a non-PD covariance returns a huge
         objective up to 10 times in a row, as paramz does."""
         self.n_evals += 1
         try:
-            f, g = self._engine.cluster_objective(self._slot, t)
+            f, g = self._engine.cluster_objective(self._slot, t, worker=worker)
             self._fail_count = 0
             self._last_grad = g
         except np.linalg.LinAlgError:
@@ -123,15 +123,16 @@ class GPModel:
             g = np.clip(self._last_grad if self._last_grad is not None else np.zeros(len(t)), -1e10, 1e10)
         return f, g
 
-    def optimize(self):                                           # obsmodel.py:94, mogp_constrained.py:333
+    def optimize(self, worker=None):                              # obsmodel.py:94, mogp_constrained.py:333
         """paramz Model.optimize() default = scipy L-BFGS-B (maxfun = maxiter = 1000, m=10, factr=1e7,
-        pgtol=1e-5), warm-started at the current hyper-parameters; then f(x_opt) and a final set."""
+        pgtol=1e-5), warm-started at the current hyper-parameters; then f(x_opt) and a final set.
+        `worker`: run the evaluations on another engine's stream (see `optimize_many`)."""
         if self._engine.cluster_n_free(self._slot) == 0:
             return
         t0 = self._engine.cluster_optimizer_array(self._slot)
-        x_opt, _f, _d = _sciopt.fmin_l_bfgs_b(self.objective_grads, t0, maxfun=1000, maxiter=1000)
-        self.objective_grads(x_opt)
-        self._engine.cluster_objective(self._slot, x_opt, want_grad=False)
+        x_opt, _f, _d = _sciopt.fmin_l_bfgs_b(lambda t: self.objective_grads(t, worker), t0, maxfun=1000, maxiter=1000)
+        self.objective_grads(x_opt, worker)
+        self._engine.cluster_objective(self._slot, x_opt, want_grad=False, worker=worker)
 
     def plot_mean(self, *a, **k):
         raise NotImplementedError("GPy/matplotlib plotting is outside the likelihood engine")
@@ -164,6 +165,36 @@ class GPModel:
         self._slot = self._engine.cluster_create(self._spec, st['theta'])
         self._owns_slot = True
         self.set_XY(st['x'], st['y'])
+
+
+def optimize_many(models, workers):
+    """Refit several clusters of one engine concurrently: the L-BFGS-B runs are independent (the reference
+    refits one cluster at a time, obsmodel.py:94; the result per cluster is the same), each runs in its own host
+    thread on a worker engine's stream so that the small factorisation kernels of different clusters overlap on
+    the GPU.  Deterministic: every cluster sees exactly the evaluations of its own sequential `optimize()`."""
+    models = list(models)
+    if not models:
+        return
+    if not workers or len(models) == 1:
+        for m in models:
+            m.optimize()
+        return
+    import queue
+    from concurrent.futures import ThreadPoolExecutor
+    models[0]._engine.sync()                       # the owner's stream must be idle before workers read its clusters
+    free = queue.Queue()
+    for w in workers:
+        free.put(w)
+
+    def run(m):
+        w = free.get()
+        try:
+            m.optimize(worker=w)
+        finally:
+            free.put(w)
+
+    with ThreadPoolExecutor(max_workers=len(workers)) as pool:
+        list(pool.map(run, models))
 
 
 def make_spec(kernel, mean_func, signal_variance_fix, noise_variance_fix):
