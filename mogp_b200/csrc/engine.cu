@@ -343,8 +343,12 @@ int infer(mogp_engine* h, Cluster& c) {
     k_build<<<dim3(nb, nb), NTHREADS, 0, h->stream>>>(h->d_L, c.M, ld, c.x(), (int)c.m, th, jitter);
     LAUNCHED(h);
     for (int p = 0; p < nb; ++p) {
-      k_panel<<<nb, NTHREADS, PANEL_SMEM, h->stream>>>(h->d_L, c.M, ld, p, info);
+      k_diag<<<1, NTHREADS, DIAG_SMEM, h->stream>>>(h->d_L, c.M, ld, p, info);
       LAUNCHED(h);
+      if (nb > 1) {
+        k_panel<<<nb - 1, NTHREADS, PANEL_SMEM, h->stream>>>(h->d_L, c.M, ld, p);
+        LAUNCHED(h);
+      }
       if (p + 1 < nb) {
         k_trail<<<dim3(nb, nb - p - 1), NTHREADS, TRAIL_SMEM, h->stream>>>(h->d_L, c.M, ld, p);
         LAUNCHED(h);
@@ -634,6 +638,7 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
     delete h;
     return MOGP_ECUDA;
   }
+  cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM);
   cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
   cudaFuncSetAttribute(k_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAIL_SMEM);
   cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM);

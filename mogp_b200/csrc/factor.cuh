@@ -77,38 +77,44 @@ __global__ void __launch_bounds__(NTHREADS) k_build(double* __restrict__ L, doub
 }
 
 // ---------------------------------------------------------------------------------------------
-// Panel step p, one CTA per block b of block-row/column p:
-//   b == p : L_pp = chol(A_pp), M_pp = L_pp^-1
-//   b >  p : L_bp = A_bp M_pp^T                       (TRSM by the inverse of the diagonal tile)
-//   b <  p : M_pb = -M_pp Acc_pb                      (finalise block-row p of the inverse factor)
-// Every CTA factors the diagonal tile redundantly (no extra launch / grid barrier); the diagonal tile of L
-// keeps A_pp (L_pp itself is never needed again: log-determinants come from the diagonal of M).
-constexpr int PANEL_SMEM = (TB * LD_C + TB * LD_C + TB * LD_R + TB) * (int)sizeof(double);
+// Panel step p in two launches:
+//   k_diag  (1 CTA)     : L_pp = chol(A_pp) (kept in shared memory only), M_pp = L_pp^-1 -> M
+//   k_panel (nb-1 CTAs) : b > p : L_bp = A_bp M_pp^T          (TRSM by the inverse of the diagonal tile)
+//                         b < p : M_pb = -M_pp Acc_pb         (finalise block-row p of the inverse factor)
+// The serial 64x64 factorisation runs once per panel on one SM instead of once per CTA: with several clusters
+// refitted concurrently (one stream each) that SM-time is what bounds the throughput.
+// The diagonal tile of L keeps A_pp (L_pp is never needed again: log-determinants come from the diagonal of M).
+constexpr int DIAG_SMEM = (TB * LD_C + TB * LD_C + 2 * TB) * (int)sizeof(double);
+constexpr int PANEL_SMEM = (TB * LD_C + TB * LD_R) * (int)sizeof(double);
 
-__global__ void __launch_bounds__(NTHREADS) k_panel(double* __restrict__ L, double* __restrict__ M, int64_t ld, int p,
-                                                    int* __restrict__ info) {
+__global__ void __launch_bounds__(NTHREADS) k_diag(const double* __restrict__ L, double* __restrict__ M, int64_t ld, int p,
+                                                   int* __restrict__ info) {
   extern __shared__ __align__(16) double smem[];
   double* sD = smem;                 // [64][LD_C]  A_pp -> L_pp
   double* sM = sD + TB * LD_C;       // [64][LD_C]  M_pp
-  double* sT = sM + TB * LD_C;       // [64][LD_R]  the CTA's own tile
-  double* col = sT + TB * LD_R;      // [64]
-  const int b = blockIdx.x;
+  double* col = sM + TB * LD_C;      // [2][64]
   const int64_t dpp = (int64_t)p * TB * ld + (int64_t)p * TB;
   load_tile<LD_C>(sD, L + dpp, ld);
-  if (b > p) load_tile<LD_C>(sT, L + (int64_t)b * TB * ld + (int64_t)p * TB, ld);
-  if (b < p) load_tile<LD_R>(sT, M + (int64_t)p * TB * ld + (int64_t)b * TB, ld);
   int fail = potrf_tile<LD_C>(sD, col);
-  if (fail && b == p && threadIdx.x == 0) atomicCAS(info, 0, p * TB + fail);
+  if (fail && threadIdx.x == 0) atomicCAS(info, 0, p * TB + fail);
   trtri_tile<LD_C>(sD, sM);
-  if (b == p) {
-    // Only M_pp is stored.  A_pp must stay untouched in L: the other CTAs of this launch read it, and a CTA
-    // scheduled late (more CTAs than fit on the device at once) would otherwise see the factored tile.
-    for (int idx = threadIdx.x; idx < TB * TB; idx += NTHREADS) {
-      int i = idx >> 6, j = idx & 63;
-      M[dpp + (int64_t)i * ld + j] = sM[i * LD_C + j];
-    }
-    return;
+  for (int idx = threadIdx.x; idx < TB * TB; idx += NTHREADS) {
+    int i = idx >> 6, j = idx & 63;
+    M[dpp + (int64_t)i * ld + j] = sM[i * LD_C + j];
   }
+}
+
+// grid nb - 1: blockIdx.x skips b == p.
+__global__ void __launch_bounds__(NTHREADS) k_panel(double* __restrict__ L, double* __restrict__ M, int64_t ld, int p) {
+  extern __shared__ __align__(16) double smem[];
+  double* sM = smem;                 // [64][LD_C]  M_pp
+  double* sT = sM + TB * LD_C;       // [64][LD_R]  the CTA's own tile
+  const int b = (int)blockIdx.x < p ? (int)blockIdx.x : (int)blockIdx.x + 1;
+  const int64_t dpp = (int64_t)p * TB * ld + (int64_t)p * TB;
+  load_tile<LD_C>(sM, M + dpp, ld);
+  if (b > p) load_tile<LD_C>(sT, L + (int64_t)b * TB * ld + (int64_t)p * TB, ld);
+  else load_tile<LD_R>(sT, M + (int64_t)p * TB * ld + (int64_t)b * TB, ld);
+  __syncthreads();
   Acc64 acc;
   acc.zero();
   if (b > p) {

@@ -147,117 +147,78 @@ __device__ __forceinline__ void for_each_acc64(Acc64& acc, F f) {
     }
 }
 
+// Barrier among the first 64 threads of the CTA only (warps 0 and 1), id 1.
+__device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
 // In-place lower Cholesky of the 64x64 tile s[64][LD] (lower part valid on entry).
 // Returns 0 or (1 + first non-positive pivot column); result uniform across the CTA.
 // The strict upper triangle is zeroed.
 //
-// Blocked by 8 columns: warp 0 factors the 8-column panel in registers (lane l owns rows l and l+32, pivots
-// and multipliers travel by shuffle - no block barrier inside a panel), then all 256 threads apply the rank-8
-// update to the trailing part.  16 block barriers per tile instead of 128.
+// Row-per-thread in registers: thread r < 64 keeps row r (64 doubles, statically indexed).  Step k: every
+// thread publishes its a[k] (one shared column, double-buffered), one 64-thread barrier, then
+// a[j] -= a[k] * col[j] / col[k] for k < j <= r.  One barrier and one reciprocal per column; the other six warps
+// wait at the closing block barrier.  (The 128-barrier shared-memory version of this routine was 70 % of the
+// refit time: ncu, profiles/r1_v0_launches_refit_region.csv.)
 template <int LD>
-__device__ int potrf_tile(double* __restrict__ s, double* __restrict__ col) {
-  (void)col;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+__device__ int potrf_tile(double* __restrict__ s, double* __restrict__ col /* >= 128 doubles */) {
+  const int r = threadIdx.x;
   __shared__ int s_fail;
-  if (tid == 0) s_fail = 0;
+  if (r == 0) s_fail = 0;
   __syncthreads();
-  for (int k0 = 0; k0 < TB; k0 += 8) {
-    if (warp == 0) {
-      double a[2][8];
+  if (r < TB) {
+    double a[TB];
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+    for (int j = 0; j < TB; ++j) a[j] = (j <= r) ? s[r * LD + j] : 0.0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[h][j] = s[(lane + 32 * h) * LD + k0 + j];
-      int fail = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int pr = k0 + j;  // pivot row
-        double dkk = __shfl_sync(0xffffffffu, pr < 32 ? a[0][j] : a[1][j], pr & 31);
-        if (!(dkk > 0.0)) {
-          if (fail == 0) fail = pr + 1;
-          dkk = 1.0;  // keep going with a harmless pivot; the caller discards the result
-        }
-        const double d = sqrt(dkk);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int r = lane + 32 * h;
-          a[h][j] = (r == pr) ? d : (r > pr ? a[h][j] / d : a[h][j]);
-        }
-#pragma unroll
-        for (int c = j + 1; c < 8; ++c) {
-          const int cr = k0 + c;  // row whose multiplier l_{cr, pr} scales column c
-          const double lc = __shfl_sync(0xffffffffu, cr < 32 ? a[0][j] : a[1][j], cr & 31);
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            if (lane + 32 * h >= cr) a[h][c] -= a[h][j] * lc;
-        }
+    for (int k = 0; k < TB; ++k) {
+      double* cb = col + (k & 1) * TB;
+      cb[r] = a[k];
+      bar64();
+      double dk = cb[k];
+      if (!(dk > 0.0)) {
+        if (r == k && s_fail == 0) s_fail = k + 1;
+        dk = 1.0;  // keep going with a harmless pivot; the caller discards the result
       }
+      const double inv = 1.0 / dk;
+      const double t = a[k] * inv;
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = lane + 32 * h;
-          if (r >= k0 + j) s[r * LD + k0 + j] = a[h][j];
-        }
-      if (fail && lane == 0 && s_fail == 0) s_fail = fail;
+      for (int j = k + 1; j < TB; ++j)
+        if (j <= r) a[j] -= t * cb[j];
+      a[k] = (r == k) ? sqrt(dk) : a[k] * rsqrt(dk);
     }
-    __syncthreads();
-    // trailing update: A[i][j] -= sum_q L[i][k0+q] L[j][k0+q] for i >= j >= k0 + 8; thread owns a 4x4 patch
-    const int ti = tid >> 4, tj = tid & 15;
-    if (4 * ti + 3 >= k0 + 8 && tj <= ti) {
-      double li[4][8], lj[4][8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          li[e][q] = s[(4 * ti + e) * LD + k0 + q];
-          lj[e][q] = s[(4 * tj + e) * LD + k0 + q];
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          const int i = 4 * ti + e, j = 4 * tj + f;
-          if (j >= k0 + 8 && j <= i) {
-            double acc = s[i * LD + j];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc -= li[e][q] * lj[f][q];
-            s[i * LD + j] = acc;
-          }
-        }
-    }
-    __syncthreads();
-  }
-  for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
-    int i = idx >> 6, j = idx & 63;
-    if (j > i) s[i * LD + j] = 0.0;
+    for (int j = 0; j < TB; ++j) s[r * LD + j] = (j <= r) ? a[j] : 0.0;
   }
   __syncthreads();
   return s_fail;
 }
 
 // sM = inverse of the lower-triangular tile sL (both [64][LD]); upper triangle of sM zeroed.
-// Column c is solved by the four lanes 4c..4c+3 (forward substitution, split dot products).
+// Column-per-thread in registers: thread c < 64 solves L x = e_c by forward substitution with x[0..63] statically
+// indexed (x_i = 0 for i < c falls out of the recurrence, so all threads run the same straight-line code);
+// the entries of L are shared-memory broadcasts; four partial sums per row shorten the dependent chain.
 template <int LD>
 __device__ void trtri_tile(const double* __restrict__ sL, double* __restrict__ sM) {
-  const int tid = threadIdx.x, c = tid >> 2, q = tid & 3;
-  for (int i = 0; i < TB; ++i) {
-    // warp-uniform trip count is not required: lanes of a quad stay together (same c)
-    double part = 0.0;
-    if (i > c) {
-      for (int j = c + q; j < i; j += 4) part += sL[i * LD + j] * sM[j * LD + c];
+  const int c = threadIdx.x;
+  if (c < TB) {
+    double x[TB];
+#pragma unroll
+    for (int i = 0; i < TB; ++i) {
+      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+      for (int j = 0; j + 3 < i; j += 4) {
+        p0 += sL[i * LD + j] * x[j];
+        p1 += sL[i * LD + j + 1] * x[j + 1];
+        p2 += sL[i * LD + j + 2] * x[j + 2];
+        p3 += sL[i * LD + j + 3] * x[j + 3];
+      }
+#pragma unroll
+      for (int j = (i / 4) * 4; j < i; ++j) p0 += sL[i * LD + j] * x[j];
+      const double rhs = (i == c) ? 1.0 : 0.0;
+      x[i] = (rhs - ((p0 + p1) + (p2 + p3))) / sL[i * LD + i];
     }
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    if (q == 0) {
-      double v;
-      if (i < c) v = 0.0;
-      else if (i == c) v = 1.0 / sL[i * LD + i];
-      else v = -part / sL[i * LD + i];
-      sM[i * LD + c] = v;
-    }
-    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < TB; ++i) sM[i * LD + c] = x[i];
   }
   __syncthreads();
 }

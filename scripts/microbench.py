@@ -34,3 +34,31 @@ for chunk in range(3):
     _z, Nk, slots = eng.chain_state(N)
 t0 = time.time(); mix._sync_state(); mix.obsmodel[0].model.optimize(); dt = time.time() - t0
 print("one refit: %.2fs, %d evals" % (dt, mix.obsmodel[0].model.n_evals))
+# concurrent refit scaling
+from mogp_b200.obsmodel import optimize_many
+import threading
+models = [mix.obsmodel[k].model for k in mix._active()]
+thetas = [eng.cluster_get_theta(m.slot) for m in models]
+for nw in (0, 2, 4, 8, 16):
+    for m, th in zip(models, thetas):
+        eng.cluster_set_theta(m.slot, th)
+        m.n_evals = 0
+    workers = [_capi.Engine(0) for _ in range(nw)]
+    eng.sync()
+    t0 = time.time(); optimize_many(models, workers); dt = time.time() - t0
+    ne = sum(m.n_evals for m in models)
+    print("refit all %d clusters, %2d workers: %.2f s, %d evals, %.2f ms/eval" % (len(models), nw, dt, ne, dt / ne * 1e3))
+# raw concurrency of the objective without scipy: each thread evaluates its cluster 10 times
+def raw(nw):
+    workers = [_capi.Engine(0) for _ in range(nw)]
+    ts = [eng.cluster_optimizer_array(m.slot) for m in models]
+    def run(i):
+        for rep in range(10):
+            eng.cluster_objective(models[i].slot, ts[i], worker=workers[i % nw])
+    eng.sync(); t0 = time.time()
+    th = [threading.Thread(target=lambda lst=list(range(w, len(models), nw)): [run(i) for i in lst]) for w in range(nw)]
+    [t.start() for t in th]; [t.join() for t in th]
+    dt = time.time() - t0
+    print("raw objective x10 on %d clusters, %2d threads: %.2f s -> %.2f ms/eval" % (len(models), nw, dt, dt / (10 * len(models)) * 1e3))
+for nw in (1, 4, 16):
+    raw(nw)
