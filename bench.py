@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--query-patients", type=int, default=1000000)
     ap.add_argument("--chains", type=int, default=64)
     ap.add_argument("--chain-patients", type=int, default=2000)
+    ap.add_argument("--chain-refit", default="sweep", choices=["sweep", "move"],
+                    help="chains workload: 'move' = the reference's schedule (L-BFGS-B after every move)")
     return ap.parse_args()
 
 
@@ -404,8 +406,9 @@ def run_chains(args):
         eng = _capi.Engine(local)
         X, Y, z0 = alsfrs_like(N, seed=100 + cid, n_classes=K0, return_labels=True)
         z0 = np.unique(z0, return_inverse=True)[1].astype(np.int32)
-        mix = MoGP(X=X, Y=Y, alpha=K0 / np.log10(N), rand_seed=cid, normalize=True, noise_variance=0.5, refit='sweep',
-                   init_z=z0, engine=eng)
+        mix = MoGP(X=X, Y=Y, alpha=K0 / np.log10(N), rand_seed=cid, normalize=True, noise_variance=0.5,
+                   refit=args.chain_refit, init_z=z0, engine=eng)
+        mix.refit_concurrency = 1          # the chains themselves already run concurrently
         np.random.seed(cid)
         mix.initialize_sampler(K0, True)
         rs = np.random.RandomState(cid)
@@ -446,8 +449,8 @@ def run_chains(args):
                 "unit": "chain-sweeps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": float(t.item()) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "{} independent MoGP (unconstrained) chains x {} patients, refit every sweep, "
-                                       "dealt round-robin to the GPUs".format(args.chains, N)},
+                "config": {"workload": "{} independent MoGP (unconstrained) chains x {} patients, refit='{}', "
+                                       "dealt round-robin to the GPUs".format(args.chains, N, args.chain_refit)},
                 "gpu_launches": int(sum(c[0].launch_count() for c in chains) - l0),
                 "check": {"chains_gathered": len(res), "active_clusters_chain0": int((res[0]['Nk'] > 0).sum())}}
         print(json.dumps(line), flush=True)

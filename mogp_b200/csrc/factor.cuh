@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(NTHREADS) k_diag(const double* __restrict__ L,
   load_tile<LD_C>(sD, L + dpp, ld);
   int fail = potrf_tile<LD_C>(sD, col);
   if (fail && threadIdx.x == 0) atomicCAS(info, 0, p * TB + fail);
-  trtri_tile<LD_C>(sD, sM);
+  trtri_tile<LD_C>(sD, sM, col);
   for (int idx = threadIdx.x; idx < TB * TB; idx += NTHREADS) {
     int i = idx >> 6, j = idx & 63;
     M[dpp + (int64_t)i * ld + j] = sM[i * LD_C + j];

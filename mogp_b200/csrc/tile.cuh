@@ -147,79 +147,120 @@ __device__ __forceinline__ void for_each_acc64(Acc64& acc, F f) {
     }
 }
 
-// Barrier among the first 64 threads of the CTA only (warps 0 and 1), id 1.
-__device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
-
-// In-place lower Cholesky of the 64x64 tile s[64][LD] (lower part valid on entry).
-// Returns 0 or (1 + first non-positive pivot column); result uniform across the CTA.
-// The strict upper triangle is zeroed.
+// ---- 64x64 diagonal tile: Cholesky and triangular inverse, patch-distributed in registers -------------------
+// All 256 threads take part: thread (ti, tj) = (tid >> 4, tid & 15) keeps the 4x4 patch rows 4ti.., cols 4tj.. in
+// registers (statically indexed).  Each of the 64 column steps publishes one column (or row) through a
+// double-buffered 64-entry shared array, costs ONE block barrier, and updates every patch with 16 FMAs.
+// The loop over the 16 patch columns is a real loop (compact code: the fully unrolled row-per-thread variant was
+// instruction-fetch bound), the 4 columns inside a patch are unrolled so register indices stay static.
 //
-// Row-per-thread in registers: thread r < 64 keeps row r (64 doubles, statically indexed).  Step k: every
-// thread publishes its a[k] (one shared column, double-buffered), one 64-thread barrier, then
-// a[j] -= a[k] * col[j] / col[k] for k < j <= r.  One barrier and one reciprocal per column; the other six warps
-// wait at the closing block barrier.  (The 128-barrier shared-memory version of this routine was 70 % of the
-// refit time: ncu, profiles/r1_v0_launches_refit_region.csv.)
+// In-place lower Cholesky of s[64][LD] (lower part valid on entry); strict upper triangle zeroed.
+// Returns 0 or (1 + first non-positive pivot column), uniform across the CTA.
 template <int LD>
-__device__ int potrf_tile(double* __restrict__ s, double* __restrict__ col /* >= 128 doubles */) {
-  const int r = threadIdx.x;
+__device__ int potrf_tile(double* __restrict__ s, double* __restrict__ buf /* >= 128 doubles */) {
+  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
   __shared__ int s_fail;
-  if (r == 0) s_fail = 0;
-  __syncthreads();
-  if (r < TB) {
-    double a[TB];
+  if (tid == 0) s_fail = 0;
+  __syncthreads();  // the tile was just staged by other threads
+  double a[4][4];
 #pragma unroll
-    for (int j = 0; j < TB; ++j) a[j] = (j <= r) ? s[r * LD + j] : 0.0;
+  for (int e = 0; e < 4; ++e)
 #pragma unroll
-    for (int k = 0; k < TB; ++k) {
-      double* cb = col + (k & 1) * TB;
-      cb[r] = a[k];
-      bar64();
+    for (int f = 0; f < 4; ++f) a[e][f] = (4 * tj + f <= 4 * ti + e) ? s[(4 * ti + e) * LD + 4 * tj + f] : 0.0;
+  for (int kb = 0; kb < 16; ++kb) {
+#pragma unroll
+    for (int kf = 0; kf < 4; ++kf) {
+      const int k = 4 * kb + kf;
+      double* cb = buf + (k & 1) * TB;
+      if (tj == kb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cb[4 * ti + e] = a[e][kf];
+      }
+      __syncthreads();
       double dk = cb[k];
       if (!(dk > 0.0)) {
-        if (r == k && s_fail == 0) s_fail = k + 1;
+        if (tid == 0 && s_fail == 0) s_fail = k + 1;
         dk = 1.0;  // keep going with a harmless pivot; the caller discards the result
       }
-      const double inv = 1.0 / dk;
-      const double t = a[k] * inv;
+      if (ti >= kb && tj <= ti) {
+        const double inv = 1.0 / dk;
+        double ci[4], cj[4];
 #pragma unroll
-      for (int j = k + 1; j < TB; ++j)
-        if (j <= r) a[j] -= t * cb[j];
-      a[k] = (r == k) ? sqrt(dk) : a[k] * rsqrt(dk);
+        for (int e = 0; e < 4; ++e) {
+          ci[e] = cb[4 * ti + e] * inv;
+          cj[e] = cb[4 * tj + e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const int i = 4 * ti + e, j = 4 * tj + f;
+            if (j > k && j <= i) a[e][f] -= ci[e] * cj[f];
+          }
+        if (tj == kb) {
+          const double rs = rsqrt(dk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = 4 * ti + e;
+            a[e][kf] = (i == k) ? sqrt(dk) : (i > k ? a[e][kf] * rs : a[e][kf]);
+          }
+        }
+      }
     }
-#pragma unroll
-    for (int j = 0; j < TB; ++j) s[r * LD + j] = (j <= r) ? a[j] : 0.0;
   }
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int f = 0; f < 4; ++f) s[(4 * ti + e) * LD + 4 * tj + f] = (4 * tj + f <= 4 * ti + e) ? a[e][f] : 0.0;
   __syncthreads();
   return s_fail;
 }
 
 // sM = inverse of the lower-triangular tile sL (both [64][LD]); upper triangle of sM zeroed.
-// Column-per-thread in registers: thread c < 64 solves L x = e_c by forward substitution with x[0..63] statically
-// indexed (x_i = 0 for i < c falls out of the recurrence, so all threads run the same straight-line code);
-// the entries of L are shared-memory broadcasts; four partial sums per row shorten the dependent chain.
+// Right-looking on X (= I at the start): step j scales row j by 1/L_jj, publishes it, and every row i > j
+// subtracts L_ij * row j.
 template <int LD>
-__device__ void trtri_tile(const double* __restrict__ sL, double* __restrict__ sM) {
-  const int c = threadIdx.x;
-  if (c < TB) {
-    double x[TB];
+__device__ void trtri_tile(const double* __restrict__ sL, double* __restrict__ sM, double* __restrict__ buf /* >= 128 */) {
+  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+  double x[4][4];
 #pragma unroll
-    for (int i = 0; i < TB; ++i) {
-      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+  for (int e = 0; e < 4; ++e)
 #pragma unroll
-      for (int j = 0; j + 3 < i; j += 4) {
-        p0 += sL[i * LD + j] * x[j];
-        p1 += sL[i * LD + j + 1] * x[j + 1];
-        p2 += sL[i * LD + j + 2] * x[j + 2];
-        p3 += sL[i * LD + j + 3] * x[j + 3];
+    for (int f = 0; f < 4; ++f) x[e][f] = (4 * ti + e == 4 * tj + f) ? 1.0 : 0.0;
+  for (int jb = 0; jb < 16; ++jb) {
+#pragma unroll
+    for (int jf = 0; jf < 4; ++jf) {
+      const int j = 4 * jb + jf;
+      double* rb = buf + (j & 1) * TB;
+      if (ti == jb) {
+        const double inv = 1.0 / sL[j * LD + j];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          x[jf][f] *= inv;
+          rb[4 * tj + f] = x[jf][f];
+        }
       }
+      __syncthreads();
+      if (ti >= jb && tj <= jb) {  // rows below j; row j has entries only in columns <= j
+        double r[4];
 #pragma unroll
-      for (int j = (i / 4) * 4; j < i; ++j) p0 += sL[i * LD + j] * x[j];
-      const double rhs = (i == c) ? 1.0 : 0.0;
-      x[i] = (rhs - ((p0 + p1) + (p2 + p3))) / sL[i * LD + i];
+        for (int f = 0; f < 4; ++f) r[f] = rb[4 * tj + f];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 4 * ti + e;
+          if (i > j) {
+            const double l = sL[i * LD + j];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) x[e][f] -= l * r[f];
+          }
+        }
+      }
     }
-#pragma unroll
-    for (int i = 0; i < TB; ++i) sM[i * LD + c] = x[i];
   }
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int f = 0; f < 4; ++f) sM[(4 * ti + e) * LD + 4 * tj + f] = (4 * tj + f <= 4 * ti + e) ? x[e][f] : 0.0;
   __syncthreads();
 }
 

@@ -112,6 +112,31 @@ def test_fast_sweeps_match_oracle(eng, kernel, mean_func, threshold, single_blas
     assert np.allclose(mix.lalloc, orc.lalloc, rtol=1e-13)
 
 
+@pytest.mark.slow
+def test_cfg1_reference_schedule_200_patients(eng):
+    """BASELINE configs[0] shape (MoGP_constrained, 200 sparse ALSFRS-R-like patients, rbf, threshold 0.5, refit after
+    every move = the reference's schedule), free-running for 3 iterations: same occupancy trace, assignments and
+    counts as the CPU oracle; hyper-parameters and log-likelihoods agree to the optimiser's tolerance."""
+    from mogp_b200 import MoGP_constrained
+    from mogp_b200.synth import alsfrs_like, block_init
+    N = 200
+    X, Y = alsfrs_like(N, seed=0)
+    z0 = block_init(N, round(N / 50), X)
+    kw = dict(alpha=round(N / 50) / np.log10(N), num_iter=3, rand_seed=0, normalize=True, threshold=0.5,
+              noise_variance=0.5, init_z=z0)
+    orc = oracle.MoGP_constrained(X=X.copy(), Y=Y.copy(), **kw)
+    orc.sample()
+    mix = MoGP_constrained(X=X.copy(), Y=Y.copy(), engine=eng, **kw)
+    mix.sample()
+    print("cfg1: min draw margin", mix.min_margin, "trace", [list(t) for t in mix.trace])
+    assert [list(t) for t in mix.trace] == [list(t) for t in orc.trace]
+    assert list(mix.z) == list(orc.z)
+    assert list(mix.allocmodel.Nk) == list(orc.allocmodel.Nk)
+    assert np.allclose(mix.lobs, orc.lobs, rtol=1e-6)
+    for k in np.where(orc.allocmodel.Nk > 0)[0]:
+        assert np.allclose(mix.obsmodel[k].model.param_array, orc.obsmodel[k].model.param_array, rtol=1e-4)
+
+
 def test_reference_smoke_nan_rows(eng):
     """mogp/test_package.py:30-46 — NaN in the middle / at the end of a row, one initial cluster."""
     from mogp_b200 import MoGP_constrained
