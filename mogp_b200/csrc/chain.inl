@@ -177,7 +177,8 @@ int remove_core(mogp_engine* h, Cluster& c, int64_t p, int n) {
   LAUNCHED(h);
   // stat block travels with the buffer
   CK(h, cudaMemcpyAsync(nvec + 4 * c.cap, c.stat(), sizeof(double) * 16, cudaMemcpyDeviceToDevice, h->stream));
-  pool_put(h, c.cap, c.M);
+  if (h->stream == h->side) h->pending_release.emplace_back(c.cap, c.M);  // reusable once the main stream has joined
+  else pool_put(h, c.cap, c.M);
   c.M = nM;
   c.vec = nvec;
   c.m = g.mnew;
@@ -323,28 +324,33 @@ int chain_score(mogp_engine* h, double a_draw) {
   double* d_own = d_newll + 1;
   ch.plan = ScorePlan();
   if (ni > 0) {
-    if (own >= 0) {
-      Cluster& c = h->cl[ch.slot_of_id[own]];
-      ch.pending_p = member_offset(h, c, n, nullptr);
-      if (ch.pending_p < 0) FAIL(h, MOGP_ESTATE, "patient %lld not in its cluster's member list", (long long)n);
-      TRY(rm_gram(h, c, ch.pending_p, (int)ni));
-      ch.gram_ready = true;
-      TRY(own_score(h, c, ch.pending_p, (int)ni, h->d_py + c0, thr_index));
-      RmGeom g = make_geom(c, ch.pending_p, (int)ni);
-      RmWork w;
-      TRY(rm_work(h, g, &w));
-      CK(h, cudaMemcpyAsync(d_own, w.own, sizeof(double) * 3, cudaMemcpyDeviceToDevice, h->stream));
+    {
+      // side stream: the own-cluster (leave-block-out) score and the newcomer's marginal are independent of the
+      // batched scoring pass below and hide under it
+      SideScope side(h);
+      if (own >= 0) {
+        Cluster& c = h->cl[ch.slot_of_id[own]];
+        ch.pending_p = member_offset(h, c, n, nullptr);
+        if (ch.pending_p < 0) FAIL(h, MOGP_ESTATE, "patient %lld not in its cluster's member list", (long long)n);
+        TRY(rm_gram(h, c, ch.pending_p, (int)ni));
+        ch.gram_ready = true;
+        TRY(own_score(h, c, ch.pending_p, (int)ni, h->d_py + c0, thr_index));
+        RmGeom g = make_geom(c, ch.pending_p, (int)ni);
+        RmWork w;
+        TRY(rm_work(h, g, &w));
+        CK(h, cudaMemcpyAsync(d_own, w.own, sizeof(double) * 3, cudaMemcpyDeviceToDevice, h->stream));
+      }
+      // the newcomer: GPobs(x_n, y_n) at A = |a_draw|, l = 4, noise_0 (:246-250)
+      ch.a_dev_val = a_draw;
+      CK(h, cudaMemcpyAsync(h->d_adraw, &ch.a_dev_val, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      h->bytes_h2d += 8;
+      k_new_ll<<<1, 64, 0, h->stream>>>(h->d_off + n, h->d_px + c0, h->d_py + c0, h->d_adraw, newcomer_theta(ch.cfg), d_newll);
+      LAUNCHED(h);
     }
     if (ns > 0)
       TRY(score_device(h, 1, ni, h->d_off + n, h->d_px + c0, h->d_py + c0, ns, ch.score_slots.data(), thr_index, d_score,
                        d_muthr, nullptr, nullptr, nullptr, ch.cfg.fast_updates != 0, &ch.plan));
-    // the newcomer: GPobs(x_n, y_n) at A = |a_draw|, l = 4, noise_0 (:246-250)
-    ch.a_dev_val = a_draw;
-    TRY(ensure(h, &h->d_q, &h->q_elems, 8));
-    CK(h, cudaMemcpyAsync(h->d_q, &ch.a_dev_val, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    h->bytes_h2d += 8;
-    k_new_ll<<<1, 64, 0, h->stream>>>(h->d_off + n, h->d_px + c0, h->d_py + c0, h->d_q, newcomer_theta(ch.cfg), d_newll);
-    LAUNCHED(h);
+    join_side(h);
     CK(h, cudaGetLastError());
   }
   std::vector<double> host(2 * ns + 8, 0.0);
@@ -390,14 +396,24 @@ int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_n
   if (ch.pending_lazy && chosen_id == prev) {
     // stayed: the factor already contains the patient (the reference re-appends the same rows)
   } else {
-    if (ch.pending_lazy) {  // really leaves: delete its rows from the previous cluster
-      Cluster& c = h->cl[ch.slot_of_id[prev]];
+    bool side_busy = false;
+    if (ch.pending_lazy) {  // really leaves: delete its rows from the previous cluster - on the side stream, so that
+      Cluster& c = h->cl[ch.slot_of_id[prev]];  // it overlaps the append to the target cluster below
       size_t idx = 0;
       const int64_t p = member_offset(h, c, n, &idx);
-      if (!ch.gram_ready) TRY(rm_gram(h, c, p, (int)ni));
-      TRY(remove_core(h, c, p, (int)ni));
+      {
+        SideScope side(h);
+        if (!ch.gram_ready) TRY(rm_gram(h, c, p, (int)ni));
+        TRY(remove_core(h, c, p, (int)ni));
+      }
+      side_busy = true;
       c.members.erase(c.members.begin() + idx);
     }
+    struct Joiner {  // whatever path the assignment takes, the main stream ends up ordered after the deletion
+      mogp_engine* h;
+      bool on;
+      ~Joiner() { if (on) join_side(h); }
+    } joiner{h, side_busy};
     if (is_new) {
       int32_t slot;
       double th[4] = {fabs(a_draw), ch.cfg.signal_variance,

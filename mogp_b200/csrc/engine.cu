@@ -87,7 +87,12 @@ struct Chain {
 
 struct mogp_engine {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // the stream every helper launches on (normally `main_stream`)
+  cudaStream_t main_stream = nullptr, side = nullptr;  // side: independent work of a Gibbs step (SideScope)
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+  std::vector<std::pair<int64_t, double*>> pending_release;  // buffers the side stream may still be reading
+  double* d_apart2 = nullptr;  // alpha partials of the side stream
+  int64_t apart2_elems = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   int64_t launches = 0;
@@ -110,6 +115,7 @@ struct mogp_engine {
   int64_t slots_cap = 0;
   double* d_scr = nullptr;
   int64_t scr_elems = 0;
+  double* d_adraw = nullptr;  // the newcomer's randn draw of the current Gibbs step
   double* d_q = nullptr;  // query staging: x | y | a_draw
   int64_t q_elems = 0;
   int64_t* d_qoff = nullptr;
@@ -207,6 +213,28 @@ cudaError_t sync_stream(mogp_engine* h) {
   return e;
 }
 
+// Launches made while a SideScope is alive go to the side stream, ordered after everything already queued on
+// the main stream.  join_side() makes the main stream wait for them (no host wait) and returns the buffers the
+// side stream was still reading to the pool.
+struct SideScope {
+  mogp_engine* h;
+  explicit SideScope(mogp_engine* h_) : h(h_) {
+    cudaEventRecord(h->ev_main, h->main_stream);
+    cudaStreamWaitEvent(h->side, h->ev_main, 0);
+    h->stream = h->side;
+  }
+  ~SideScope() {
+    cudaEventRecord(h->ev_side, h->side);
+    h->stream = h->main_stream;
+  }
+};
+void pool_put(mogp_engine* h, int64_t cap, double* buf);
+void join_side(mogp_engine* h) {
+  cudaStreamWaitEvent(h->main_stream, h->ev_side, 0);
+  for (auto& pb : h->pending_release) pool_put(h, pb.first, pb.second);
+  h->pending_release.clear();
+}
+
 // A fresh range of the upload staging buffer; valid until the next sync_stream().
 int stage_alloc(mogp_engine* h, size_t bytes, char** out) {
   bytes = (bytes + 255) / 256 * 256;
@@ -299,11 +327,13 @@ int cluster_reserve(mogp_engine* h, Cluster& c, int64_t m_new, bool keep) {
 int launch_alpha(mogp_engine* h, Cluster& c) {
   const int64_t mpad = round_up(c.m, TB);
   const int nchunk = (int)((c.m + ALPHA_ROWS - 1) / ALPHA_ROWS);
-  TRY(ensure(h, &h->d_apart, &h->apart_elems, (int64_t)nchunk * mpad));
+  const bool on_side = h->stream == h->side;  // the two streams of a Gibbs step must not share the partials
+  double** buf = on_side ? &h->d_apart2 : &h->d_apart;
+  TRY(ensure(h, buf, on_side ? &h->apart2_elems : &h->apart_elems, (int64_t)nchunk * mpad));
   k_alpha_part<<<dim3((unsigned)(mpad / TB), (unsigned)nchunk), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.z(), (int)c.m,
-                                                                                           (int)mpad, h->d_apart);
+                                                                                           (int)mpad, *buf);
   LAUNCHED(h);
-  k_alpha_reduce<<<(unsigned)((c.m + 255) / 256), 256, 0, h->stream>>>(h->d_apart, nchunk, (int)mpad, c.alpha(), (int)c.m);
+  k_alpha_reduce<<<(unsigned)((c.m + 255) / 256), 256, 0, h->stream>>>(*buf, nchunk, (int)mpad, c.alpha(), (int)c.m);
   LAUNCHED(h);
   return MOGP_OK;
 }
@@ -633,11 +663,16 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
   mogp_engine* h = new mogp_engine();
   h->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
     g_create_error = std::string("engine init failed: ") + cudaGetErrorString(cudaGetLastError());
     delete h;
     return MOGP_ECUDA;
   }
+  h->main_stream = h->stream;
+  cudaMalloc((void**)&h->d_adraw, sizeof(double) * 8);
   cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM);
   cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
   cudaFuncSetAttribute(k_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAIL_SMEM);
