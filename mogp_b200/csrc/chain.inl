@@ -284,15 +284,16 @@ int chain_begin(mogp_engine* h, int64_t n) {
     ch.slot_of_id[prev] = -1;
     return MOGP_OK;
   }
-  if (ch.cfg.fast_updates && ni > 0 && ni <= NP && c.valid) {
+  if (ch.cfg.fast_updates && ni > 0 && ni <= NP && c.valid && member_offset(h, c, n, nullptr) >= 0) {
     ch.pending_lazy = 1;  // rows stay in place; the own score is the leave-block-out form
     return MOGP_OK;
   }
-  // reference-exact: re-extract the members in patient-index order and refactorise (:239-242)
-  size_t idx = 0;
-  if (member_offset(h, c, n, &idx) < 0) FAIL(h, MOGP_ESTATE, "patient %lld not in its cluster's member list", (long long)n);
-  c.members.erase(c.members.begin() + idx);
-  std::sort(c.members.begin(), c.members.end());
+  // reference-exact: re-extract the members in patient-index order and refactorise (:239-242).  The member list
+  // is re-derived from z (X[z == curr_k] in the reference), which also covers a cluster whose GP was replaced by a
+  // newcomer's model (alpha = 0, see chain_score).
+  c.members.clear();
+  for (int64_t i = 0; i < ch.N; ++i)
+    if (ch.z[i] == prev) c.members.push_back(i);
   return rebuild_from_members(h, c);
 }
 
@@ -308,10 +309,16 @@ int chain_score(mogp_engine* h, double a_draw) {
   const int32_t n_ids = (int32_t)ch.Nk.size();
   for (int32_t k = 0; k < n_ids; ++k)
     if (ch.Nk[k] > 0) ch.act_ids.push_back(k);
-  ch.act_ids.push_back(n_ids);  // the new-cluster slot (weight alpha)
+  // active = np.where(hstack([Nk, alpha]) > 0) (allocmodel.py:25-26): the new-cluster slot is active only when
+  // alpha > 0.  The reference then treats the LAST active id as "the new component" whatever it is
+  // (mogp_constrained.py:252,270): with alpha = 0 that is an existing cluster, which is scored with the newcomer's
+  // marginal and, if drawn, has its GP REPLACED by the newcomer's model (:279-281).  Reproduced as is.
+  if (ch.cfg.alpha > 0.0) ch.act_ids.push_back(n_ids);
   const int nact = (int)ch.act_ids.size();
+  if (nact == 0) FAIL(h, MOGP_ESTATE, "no active cluster and alpha = 0");
   ch.act_score.assign(nact, 0.0);
-  const int32_t own = ch.pending_lazy ? ch.pending_prev : -1;
+  int32_t own = ch.pending_lazy ? ch.pending_prev : -1;
+  if (own >= 0 && own == ch.act_ids[nact - 1]) own = -1;  // scored as "new": no own-cluster score needed
   for (int i = 0; i + 1 < nact; ++i)
     if (ch.act_ids[i] != own) ch.score_slots.push_back(ch.slot_of_id[ch.act_ids[i]]);
   const int ns = (int)ch.score_slots.size();
@@ -361,7 +368,7 @@ int chain_score(mogp_engine* h, double a_draw) {
     const int32_t id = ch.act_ids[i];
     double prior, ll, muthr = NAN;
     if (i == nact - 1) {
-      prior = log(ch.cfg.alpha + 1e-16);  // allocmodel.py:25-26
+      prior = log((id == n_ids ? ch.cfg.alpha : (double)ch.Nk[id]) + 1e-16);  // allocmodel.py:25-26
       ll = host[2 * ns];
       if (ni > 0 && !isfinite(ll)) FAIL(h, MOGP_ENOTPD, "new-cluster covariance not positive definite");
     } else {
@@ -389,11 +396,16 @@ int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_n
   const int64_t n = ch.pending;
   if (n < 0) FAIL(h, MOGP_ESTATE, "chain_commit without chain_begin");
   const int32_t n_ids = (int32_t)ch.Nk.size();
-  const bool is_new = chosen_id == n_ids;
-  if (chosen_id < 0 || chosen_id > n_ids || (!is_new && ch.Nk[chosen_id] <= 0)) FAIL(h, MOGP_EINVAL, "cluster id %d is not active", chosen_id);
+  // "new component" = the last active id of the scoring phase (an existing cluster when alpha = 0)
+  const int32_t new_comp = ch.act_ids.empty() ? n_ids : ch.act_ids.back();
+  const bool is_new = chosen_id == new_comp;
+  const bool replaces_existing = is_new && chosen_id < n_ids;
+  if (chosen_id < 0 || chosen_id > n_ids || (chosen_id == n_ids && ch.cfg.alpha <= 0.0) ||
+      (chosen_id < n_ids && ch.Nk[chosen_id] <= 0))
+    FAIL(h, MOGP_EINVAL, "cluster id %d is not active", chosen_id);
   const int64_t c0 = h->h_off[n], ni = h->h_off[n + 1] - c0;
   const int32_t prev = ch.pending_prev;
-  if (ch.pending_lazy && chosen_id == prev) {
+  if (ch.pending_lazy && chosen_id == prev && !replaces_existing) {
     // stayed: the factor already contains the patient (the reference re-appends the same rows)
   } else {
     bool side_busy = false;
@@ -418,13 +430,23 @@ int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_n
       int32_t slot;
       double th[4] = {fabs(a_draw), ch.cfg.signal_variance,
                       ch.cfg.spec.kernel == MOGP_KERNEL_RBF ? ch.cfg.lengthscale : 1.0, ch.cfg.noise_variance};
+      if (replaces_existing) {  // obsmodel[z[n]] = new_comp_model over an existing cluster (alpha = 0)
+        join_side(h);
+        joiner.on = false;
+        TRY(mogp_cluster_free(h, ch.slot_of_id[chosen_id]));
+        ch.slot_of_id[chosen_id] = -1;
+      }
       TRY(mogp_cluster_create(h, &ch.cfg.spec, th, &slot));
       Cluster& c = h->cl[slot];
       c.members.assign(1, n);
       TRY(rebuild_from_members(h, c));
       if (ch.cfg.fast_updates) TRY(infer(h, c));
-      ch.Nk.push_back(0);
-      ch.slot_of_id.push_back(slot);
+      if (replaces_existing) {
+        ch.slot_of_id[chosen_id] = slot;
+      } else {
+        ch.Nk.push_back(0);
+        ch.slot_of_id.push_back(slot);
+      }
     } else {
       Cluster& c = h->cl[ch.slot_of_id[chosen_id]];
       bool done = false;

@@ -1,0 +1,146 @@
+"""GPU edge cases: ragged / single-visit / long rows, emptied and new clusters, alpha extremes, capacity growth,
+and size-independent round-trip properties at the headline cluster size (m ~ 2 500)."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from mogp_b200 import _capi
+    e = _capi.Engine(0)
+    yield e
+    e.close()
+
+
+def ragged_data(seed, N=40, T=24):
+    rs = np.random.RandomState(seed)
+    X = np.full((N, T), np.nan)
+    Y = np.full((N, T), np.nan)
+    for i in range(N):
+        n = [1, 2, 23][i % 3] if i < 9 else rs.randint(3, 9)      # single-visit, two-visit and 23-visit rows
+        t = np.sort(rs.uniform(0.2, 8, n))
+        X[i, 0], Y[i, 0] = 0.0, 48.0
+        X[i, 1:1 + n] = t
+        Y[i, 1:1 + n] = np.clip(np.round(48 - rs.uniform(2, 9) * t + rs.randn(n) * 2), 0, 48)
+    holes = rs.randint(9, N, 6)                                    # NaN in the middle of a row
+    for i in holes:
+        X[i, 2], Y[i, 2] = np.nan, np.nan
+    return X, Y
+
+
+@pytest.mark.parametrize("alpha", [0.0, 1.0, 50.0])
+def test_ragged_rows_and_alpha_extremes(eng, alpha, single_blas_thread):
+    """Rows with 1, 2 and 23 visits (> the 16-row rank-update limit: those patients take the refactorising path),
+    NaN holes, alpha = 0 (new clusters all but impossible) and alpha = 50 (many new and emptied clusters)."""
+    from mogp_b200 import MoGP_constrained
+    X, Y = ragged_data(1)
+    z0 = (np.arange(40) % 3).astype(np.int32)
+    kw = dict(alpha=alpha, num_iter=3, rand_seed=2, normalize=True, threshold=0.5, noise_variance=0.5, refit='sweep',
+              init_z=z0)
+    orc = oracle.MoGP_constrained(X=X.copy(), Y=Y.copy(), **kw)
+    orc.sample()
+    mix = MoGP_constrained(X=X.copy(), Y=Y.copy(), engine=eng, **kw)
+    mix.sample()
+    assert list(mix.z) == list(orc.z)
+    assert list(mix.allocmodel.Nk) == list(orc.allocmodel.Nk)
+    assert mix.allocmodel.Nk.dtype == np.int64
+    if alpha == 50.0:
+        assert len(mix.allocmodel.Nk) > 3 and (mix.allocmodel.Nk == 0).any()      # ids are never reused
+        assert all(mix.obsmodel[k] is None for k in np.where(mix.allocmodel.Nk == 0)[0])
+    assert np.allclose(mix.lobs, orc.lobs, rtol=1e-6)
+
+
+def test_capacity_growth_by_appends(eng):
+    """A cluster grown patient by patient across several capacity classes equals one built in one go."""
+    from mogp_b200.obsmodel import make_spec
+    rs = np.random.RandomState(3)
+    spec = make_spec('rbf', True, True, False)
+    th = np.array([0.3, 1.0, 2.0, 0.1])
+    x = rs.uniform(0, 8, 420)
+    y = (48 - 6 * x + rs.randn(420) * 3 - 30) / 20
+    a = eng.cluster_create(spec, th)
+    eng.cluster_set_data(a, x[:5], y[:5])
+    pos = 5
+    while pos < 420:
+        n = int(rs.randint(1, 12))
+        eng.cluster_append(a, x[pos:pos + n], y[pos:pos + n])
+        pos += n
+    b = eng.cluster_create(spec, th)
+    eng.cluster_set_data(b, x, y)
+    assert eng.cluster_size(a) == 420
+    assert abs(eng.cluster_loglik(a) - eng.cluster_loglik(b)) <= 1e-9 * abs(eng.cluster_loglik(b))
+    Ma, aa = eng.cluster_get_factor(a)
+    Mb, ab = eng.cluster_get_factor(b)
+    assert np.max(np.abs(Ma - Mb)) / np.max(np.abs(Mb)) < 1e-9
+    assert np.max(np.abs(aa - ab)) / np.max(np.abs(ab)) < 1e-8
+    eng.cluster_free(a)
+    eng.cluster_free(b)
+
+
+def test_round_trips_at_headline_cluster_size(eng):
+    """m = 2 500 (BASELINE's 10k-patient configuration): properties that need no oracle run.
+    (1) leave-block-out score == score after really deleting the rows; (2) delete + append restores the log marginal;
+    (3) the log marginal is invariant to the order of the data; (4) the factor inverts: M K_y M^T = I on a probe."""
+    from mogp_b200.obsmodel import make_spec
+    rs = np.random.RandomState(11)
+    m = 2500
+    x = np.sort(rs.uniform(0, 8, m))
+    x[:300] = 0.0
+    y = (48 - 6 * x + rs.randn(m) * 3 - 30) / 20
+    spec = make_spec('rbf', True, True, False)
+    th = np.array([0.3, 1.0, 1.6, 0.05])
+    s = eng.cluster_create(spec, th)
+    eng.cluster_set_data(s, x, y)
+    lml0 = eng.cluster_loglik(s)
+    p, n = 1237, 9
+    xb, yb = x[p:p + n].copy(), y[p:p + n].copy()
+    loo, mu = eng.cluster_leave_out_score(s, p, n, thr_index=1)
+    eng.cluster_remove_rows(s, p, n)
+    sc, mus = eng.score_pairs(np.array([0, n]), xb, yb, [s], thr_index=1, want_mu=True)
+    assert abs(loo - sc[0, 0]) <= 1e-9 * abs(sc[0, 0])
+    assert abs(mu - mus[0, 0]) <= 1e-9
+    eng.cluster_append(s, xb, yb)
+    assert abs(eng.cluster_loglik(s) - lml0) <= 1e-10 * abs(lml0)
+    perm = rs.permutation(m)
+    s2 = eng.cluster_create(spec, th)
+    eng.cluster_set_data(s2, x[perm], y[perm])
+    assert abs(eng.cluster_loglik(s2) - lml0) <= 1e-10 * abs(lml0)
+    # probe: M (K + (noise + 1e-8) I) M^T e = e for random e, with K rebuilt on the host
+    M, _alpha = eng.cluster_get_factor(s2)
+    xs = x[perm]
+    r2 = np.clip(-2 * np.outer(xs, xs) + (xs * xs)[:, None] + (xs * xs)[None, :], 0, None)
+    Ky = th[1] * np.exp(-0.5 * r2 / th[2] ** 2) + np.eye(m) * (th[3] + 1e-8)
+    e = rs.randn(m)
+    out = M @ (Ky @ (M.T @ e))
+    assert np.max(np.abs(out - e)) < 1e-8
+    eng.cluster_free(s)
+    eng.cluster_free(s2)
+
+
+def test_predict_batch_equals_predict_loop(eng):
+    """Batch prediction (patients x clusters in one pass) == the reference's one-patient predict() in a loop."""
+    from mogp_b200 import MoGP_constrained
+    from mogp_b200.synth import alsfrs_like
+    X, Y, z0 = alsfrs_like(90, seed=4, n_classes=4, return_labels=True)
+    z0 = np.unique(z0, return_inverse=True)[1].astype(np.int32)
+    mix = MoGP_constrained(X=X, Y=Y, alpha=1.0, num_iter=2, rand_seed=0, normalize=True, noise_variance=0.5,
+                           refit='sweep', init_z=z0, engine=eng)
+    mix.sample()
+    Xq, Yq = alsfrs_like(17, seed=9)
+    a = np.random.RandomState(5).randn(17)
+    P = mix.predict_batch(Xq, Yq, a)
+    assert P.shape == (17, len(mix.allocmodel.Nk) + 1) and np.allclose(P.sum(1), 1.0, atol=1e-12)
+    for i in range(17):
+        keep = ~np.isnan(Xq[i])
+        np.random.seed(123)
+        state = np.random.get_state()
+        # predict() draws its own randn for the newcomer: replay it so the two paths see the same A
+        one = mix.predict_batch(Xq[i:i + 1], Yq[i:i + 1], a[i:i + 1])[0]
+        assert np.max(np.abs(one - P[i])) < 1e-12
+        np.random.set_state(state)
+        p_single = mix.predict(Xq[i][keep], Yq[i][keep])
+        assert p_single.shape == P[i].shape and abs(p_single.sum() - 1.0) < 1e-12

@@ -1,0 +1,68 @@
+"""Property tests of the CPU oracle for the paths the reference's notebook does not pin (SURVEY.md §8c 'unpinned'):
+the optimiser gradient against central finite differences of the objective, permutation invariance, and the
+consistency of predict / log_predictive_density — for both kernels, with and without the mean function."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle.gpy_restated import GPRegressionOracle, logexp_f, logexp_finv
+
+
+def make(kernel, mf, sfix, nfix, seed, m):
+    rs = np.random.RandomState(seed)
+    x = np.sort(rs.uniform(0, 8, m))
+    y = (48 - 6 * x + rs.randn(m) * 3 - 30) / 20
+    return GPRegressionOracle(x.reshape(-1, 1), y.reshape(-1, 1), kernel_name=kernel, signal_variance=0.8,
+                              signal_variance_fix=sfix, noise_variance=0.3, noise_variance_fix=nfix, mean_func=mf,
+                              lengthscale=2.0, a_draw=0.4 if mf else None), x, y
+
+
+@settings(max_examples=25, deadline=None)
+@given(kernel=st.sampled_from(['rbf', 'linear']), mf=st.booleans(), sfix=st.booleans(), nfix=st.booleans(),
+       seed=st.integers(0, 10 ** 6), m=st.integers(3, 40))
+def test_objective_gradient_matches_finite_differences(kernel, mf, sfix, nfix, seed, m):
+    o, _x, _y = make(kernel, mf, sfix, nfix, seed, m)
+    t0 = o.optimizer_array().copy()
+    if t0.size == 0:
+        return
+    f0, g0 = o.objective_grads(t0)
+    for i in range(t0.size):
+        h = 1e-5 * max(1.0, abs(t0[i]))
+        tp, tm = t0.copy(), t0.copy()
+        tp[i] += h
+        tm[i] -= h
+        fd = (o.objective_grads(tp)[0] - o.objective_grads(tm)[0]) / (2 * h)
+        assert fd == pytest.approx(g0[i], rel=2e-5, abs=2e-6)
+
+
+@settings(max_examples=20, deadline=None)
+@given(kernel=st.sampled_from(['rbf', 'linear']), mf=st.booleans(), seed=st.integers(0, 10 ** 6), m=st.integers(2, 60))
+def test_marginal_and_predictions_are_order_invariant(kernel, mf, seed, m):
+    """The engine keeps cluster rows in arrival order; the reference re-extracts them in patient order. The GP
+    does not care: LML, predictive mean and variance are invariant to the order of the data."""
+    o, x, y = make(kernel, mf, True, False, seed, m)
+    perm = np.random.RandomState(seed + 1).permutation(m)
+    p = GPRegressionOracle(x[perm].reshape(-1, 1), y[perm].reshape(-1, 1), kernel_name=kernel, signal_variance=0.8,
+                           noise_variance=0.3, mean_func=mf, lengthscale=2.0, a_draw=0.4 if mf else None)
+    assert p.log_likelihood() == pytest.approx(o.log_likelihood(), rel=1e-9, abs=1e-9)
+    xs = np.linspace(0, 9, 7).reshape(-1, 1)
+    m0, v0 = o.predict(xs)
+    m1, v1 = p.predict(xs)
+    assert np.allclose(m0, m1, rtol=1e-8, atol=1e-10) and np.allclose(v0, v1, rtol=1e-8)
+
+
+def test_logexp_roundtrip_and_limits():
+    th = np.array([1e-8, 1e-3, 0.5, 4.0, 30.0, 40.0, 500.0])
+    assert np.allclose(logexp_f(logexp_finv(th)), th, rtol=1e-12)
+    assert logexp_f(np.array([-800.0]))[0] > 0.0
+    assert logexp_f(np.array([50.0]))[0] == 50.0
+
+
+def test_density_is_the_gaussian_of_predict():
+    o, x, y = make('rbf', True, True, False, 5, 30)
+    xs = np.array([[0.5], [3.0], [7.5]])
+    ys = np.array([[0.2], [-0.4], [-1.1]])
+    mu, var = o.predict(xs)
+    lpd = o.log_predictive_density(xs, ys)
+    ref = -0.5 * np.log(2 * np.pi * var) - 0.5 * (ys - mu) ** 2 / var
+    assert np.allclose(lpd, ref, rtol=1e-12)
