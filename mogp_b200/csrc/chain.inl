@@ -8,11 +8,11 @@ int pool_get(mogp_engine* h, int64_t cap, double** out) {
     if (h->pool[i].first == cap) {
       *out = h->pool[i].second;
       h->pool.erase(h->pool.begin() + i);
-      if (poison_enabled()) CK(h, cudaMemsetAsync(*out, 0xFF, sizeof(double) * (size_t)(cap * cap + 4 * cap + 16), h->stream));
+      if (poison_enabled()) CK(h, cudaMemsetAsync(*out, 0xFF, sizeof(double) * (size_t)(cap * cap + 4 * cap + STAT), h->stream));
       return MOGP_OK;
     }
-  CK(h, cudaMalloc((void**)out, sizeof(double) * (size_t)(cap * cap + 4 * cap + 16)));
-  if (poison_enabled()) CK(h, cudaMemsetAsync(*out, 0xFF, sizeof(double) * (size_t)(cap * cap + 4 * cap + 16), h->stream));
+  CK(h, cudaMalloc((void**)out, sizeof(double) * (size_t)(cap * cap + 4 * cap + STAT)));
+  if (poison_enabled()) CK(h, cudaMemsetAsync(*out, 0xFF, sizeof(double) * (size_t)(cap * cap + 4 * cap + STAT), h->stream));
   return MOGP_OK;
 }
 void pool_put(mogp_engine* h, int64_t cap, double* buf) {
@@ -21,9 +21,9 @@ void pool_put(mogp_engine* h, int64_t cap, double* buf) {
 
 // z (optional), alpha and the log marginal from the current M; results stay on the device until asked for.
 int refresh_vectors(mogp_engine* h, Cluster& c, bool recompute_z) {
-  Theta th = make_theta(c);
   if (recompute_z) {
-    k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.x(), c.y(), (int)c.m, th, c.z());
+    TRY(sync_theta(h, c));
+    k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.x(), c.y(), (int)c.m, c.theta_dev(), c.z());
     LAUNCHED(h);
   }
   TRY(launch_alpha(h, c));
@@ -176,7 +176,7 @@ int remove_core(mogp_engine* h, Cluster& c, int64_t p, int n) {
   k_rm_vec<<<(unsigned)((g.mnew + 255) / 256), 256, 0, h->stream>>>(c.x(), c.y(), nvec, nvec + c.cap, g);
   LAUNCHED(h);
   // stat block travels with the buffer
-  CK(h, cudaMemcpyAsync(nvec + 4 * c.cap, c.stat(), sizeof(double) * 16, cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(nvec + 4 * c.cap, c.stat(), sizeof(double) * STAT, cudaMemcpyDeviceToDevice, h->stream));
   if (h->stream == h->side) h->pending_release.emplace_back(c.cap, c.M);  // reusable once the main stream has joined
   else pool_put(h, c.cap, c.M);
   c.M = nM;

@@ -37,7 +37,8 @@ struct Cluster {
   int64_t m = 0;     // data points
   int64_t cap = 0;   // allocated edge of M (multiple of 64) = leading dimension
   double* M = nullptr;    // one pooled buffer: M[cap*cap] followed by vec
-  double* vec = nullptr;  // x | y | alpha | z (cap each) | stat[16]   (= M + cap*cap)
+  double* vec = nullptr;  // x | y | alpha | z (cap each) | stat[STAT]   (= M + cap*cap)
+  bool theta_dirty = true;  // device copy of theta (stat + 16) is stale
   std::vector<double> hx, hy;     // host mirror of the data (pickling, jitter mean, get_data)
   std::vector<int64_t> members;   // chain-managed clusters: patient ids in data order
   bool valid = false;             // factor / alpha / lml correspond to (data, theta)
@@ -50,8 +51,11 @@ struct Cluster {
   double* y() const { return vec + cap; }
   double* alpha() const { return vec + 2 * cap; }
   double* z() const { return vec + 3 * cap; }
-  double* stat() const { return vec + 4 * cap; }
+  double* stat() const { return vec + 4 * cap; }  // [0..3] lml, quad, logdet, x.alpha; [8] info; [10..13] grad; [16..] Theta
+  Theta* theta_dev() const { return reinterpret_cast<Theta*>(vec + 4 * cap + 16); }
 };
+
+constexpr int STAT = 32;  // doubles in a cluster's stat block
 
 struct ScorePlan {
   int64_t R = 0, Rpad = 0;
@@ -137,6 +141,12 @@ struct mogp_engine {
   double* d_apw = nullptr;   // append workspace
   int64_t apw_elems = 0;
   std::vector<std::pair<int64_t, double*>> pool;  // free cluster buffers by capacity
+  // CUDA graph of one objective evaluation (inference + gradient, ~3 nb + 8 kernels), relaunched for every
+  // L-BFGS-B evaluation of the same cluster; keyed by the buffers it touches
+  cudaGraph_t eval_graph = nullptr;
+  cudaGraphExec_t eval_exec = nullptr;
+  const void* eval_key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int64_t eval_kernels = 0;
   // accounting (bench.py): bytes moved by the C ABI calls, and device time of the scoring GEMM
   int64_t bytes_h2d = 0, bytes_d2h = 0;
   bool prof_on = false;
@@ -307,19 +317,34 @@ int cluster_reserve(mogp_engine* h, Cluster& c, int64_t m_new, bool keep) {
   TRY(pool_get(h, cap, &buf));
   double* M = buf;
   double* vec = buf + cap * cap;
-  CK(h, cudaMemsetAsync(vec, 0, sizeof(double) * (size_t)(4 * cap + 16), h->stream));
-  if (keep && c.cap > 0) {
+  CK(h, cudaMemsetAsync(vec, 0, sizeof(double) * (size_t)(4 * cap + STAT), h->stream));
+  const bool copied = keep && c.cap > 0;
+  if (copied) {
     const int64_t mp = round_up(c.m, TB);
     CK(h, cudaMemcpy2DAsync(M, cap * sizeof(double), c.M, c.cap * sizeof(double), mp * sizeof(double), mp,
                             cudaMemcpyDeviceToDevice, h->stream));
     for (int q = 0; q < 4; ++q)
       CK(h, cudaMemcpyAsync(vec + q * cap, c.vec + q * c.cap, sizeof(double) * c.m, cudaMemcpyDeviceToDevice, h->stream));
-    CK(h, cudaMemcpyAsync(vec + 4 * cap, c.vec + 4 * c.cap, sizeof(double) * 16, cudaMemcpyDeviceToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(vec + 4 * cap, c.vec + 4 * c.cap, sizeof(double) * STAT, cudaMemcpyDeviceToDevice, h->stream));
   }
   if (c.M) pool_put(h, c.cap, c.M);  // stream-ordered reuse: every consumer runs on h->stream
   c.M = M;
   c.vec = vec;
   c.cap = cap;
+  if (!copied) c.theta_dirty = true;  // a fresh buffer holds no device copy of theta
+  return MOGP_OK;
+}
+
+// Bring the device copy of theta (read by k_build / k_z / k_grad / k_grad_final) up to date.
+int sync_theta(mogp_engine* h, Cluster& c) {
+  if (!c.theta_dirty) return MOGP_OK;
+  char* up = nullptr;
+  TRY(stage_alloc(h, sizeof(Theta), &up));
+  Theta th = make_theta(c);
+  memcpy(up, &th, sizeof(Theta));
+  CK(h, cudaMemcpyAsync(c.theta_dev(), up, sizeof(Theta), cudaMemcpyHostToDevice, h->stream));
+  h->bytes_h2d += (int64_t)sizeof(Theta);
+  c.theta_dirty = false;
   return MOGP_OK;
 }
 
@@ -363,7 +388,8 @@ int infer(mogp_engine* h, Cluster& c) {
   const int nb = (int)(mpad / TB);
   const int64_t ld = c.cap;
   TRY(ensure(h, &h->d_L, &h->L_elems, ld * mpad));
-  Theta th = make_theta(c);
+  TRY(sync_theta(h, c));
+  const Theta* th = c.theta_dev();
   double* st = c.stat();
   int* info = reinterpret_cast<int*>(st + 8);
   TRY(ensure_pin(h, 256));
@@ -430,7 +456,8 @@ int infer_grad(mogp_engine* h, Cluster& c) {
   const int nz = (nb + GRAD_KC - 1) / GRAD_KC;
   const int64_t n_partial = (int64_t)nb * nb * nz;
   TRY(ensure(h, &h->d_partial, &h->partial_elems, n_partial * 3));
-  Theta th = make_theta(c);
+  TRY(sync_theta(h, c));
+  const Theta* th = c.theta_dev();
   double* st = c.stat();
   k_grad<<<dim3(nb, nb, nz), NTHREADS, GRAD_SMEM, h->stream>>>(c.M, c.cap, nb, c.x(), c.alpha(), (int)c.m, th,
                                                                 h->d_partial);
@@ -705,6 +732,8 @@ void mogp_engine_destroy(mogp_engine* h) {
   if (h->pin) cudaFreeHost(h->pin);
   if (h->pin_dn) cudaFreeHost(h->pin_dn);
   if (h->pin_up) cudaFreeHost(h->pin_up);
+  if (h->eval_exec) cudaGraphExecDestroy(h->eval_exec);
+  if (h->eval_graph) cudaGraphDestroy(h->eval_graph);
   for (auto e : h->prof_ev) cudaEventDestroy(e);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
@@ -844,6 +873,7 @@ int mogp_cluster_create(mogp_engine* h, const mogp_model_spec* spec, const doubl
   c.used = true;
   c.spec = *spec;
   memcpy(c.theta, theta, sizeof(double) * 4);
+  c.theta_dirty = true;
   c.m = 0;
   c.valid = c.grad_valid = false;
   c.hx.clear();
@@ -875,6 +905,7 @@ int mogp_cluster_set_theta(mogp_engine* h, int32_t slot, const double theta[4]) 
     if (!(theta[i] > 0.0) && !(i == 2 && c.spec.kernel == MOGP_KERNEL_LINEAR && theta[i] >= 0.0))
       FAIL(h, MOGP_EINVAL, "theta[%d] = %g must be positive", i, theta[i]);
   memcpy(c.theta, theta, sizeof(double) * 4);
+  c.theta_dirty = true;
   c.valid = c.grad_valid = false;
   if (c.m > 0) return infer(h, c);
   return MOGP_OK;
@@ -1027,6 +1058,100 @@ int mogp_cluster_get_optimizer_array(mogp_engine* h, int32_t slot, double* t, in
   return MOGP_OK;
 }
 
+bool graphs_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MOGP_NO_GRAPH");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// One objective evaluation (exact inference + gradient at the cluster's current theta) as a CUDA graph: captured
+// once per (cluster buffers, size), relaunched for each of the ~20 evaluations of a refit.  theta travels through
+// device memory (sync_theta), so the nodes never change.  *ok = false when the factorisation failed: the caller
+// falls back to the eager path with GPy's jitter ladder.
+static int graph_eval(mogp_engine* h, Cluster& c, bool* ok) {
+  *ok = false;
+  const int64_t mpad = round_up(c.m, TB);
+  const int nb = (int)(mpad / TB);
+  const int64_t ld = c.cap;
+  const int nz = (nb + GRAD_KC - 1) / GRAD_KC;
+  const int64_t n_partial = (int64_t)nb * nb * nz;
+  const int nchunk = (int)((c.m + ALPHA_ROWS - 1) / ALPHA_ROWS);
+  TRY(ensure(h, &h->d_L, &h->L_elems, ld * mpad));
+  TRY(ensure(h, &h->d_apart, &h->apart_elems, (int64_t)nchunk * mpad));
+  TRY(ensure(h, &h->d_partial, &h->partial_elems, n_partial * 3));
+  TRY(ensure_pin(h, 256));
+  TRY(sync_theta(h, c));
+  double* st = c.stat();
+  const void* key[6] = {c.M, c.vec, h->d_L, h->d_apart, h->d_partial, reinterpret_cast<const void*>((intptr_t)c.m)};
+  if (!h->eval_exec || memcmp(key, h->eval_key, sizeof key) != 0) {
+    if (h->eval_exec) cudaGraphExecDestroy(h->eval_exec);
+    if (h->eval_graph) cudaGraphDestroy(h->eval_graph);
+    h->eval_exec = nullptr;
+    h->eval_graph = nullptr;
+    const int64_t launches0 = h->launches;
+    CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int* info = reinterpret_cast<int*>(st + 8);
+    const Theta* th = c.theta_dev();
+    cudaMemsetAsync(info, 0, sizeof(int), h->stream);
+    k_build<<<dim3(nb, nb), NTHREADS, 0, h->stream>>>(h->d_L, c.M, ld, c.x(), (int)c.m, th, 0.0);
+    LAUNCHED(h);
+    for (int p = 0; p < nb; ++p) {
+      k_diag<<<1, NTHREADS, DIAG_SMEM, h->stream>>>(h->d_L, c.M, ld, p, info);
+      LAUNCHED(h);
+      if (nb > 1) {
+        k_panel<<<nb - 1, NTHREADS, PANEL_SMEM, h->stream>>>(h->d_L, c.M, ld, p);
+        LAUNCHED(h);
+      }
+      if (p + 1 < nb) {
+        k_trail<<<dim3(nb, nb - p - 1), NTHREADS, TRAIL_SMEM, h->stream>>>(h->d_L, c.M, ld, p);
+        LAUNCHED(h);
+      }
+    }
+    k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, ld, c.x(), c.y(), (int)c.m, th, c.z());
+    LAUNCHED(h);
+    int rc = launch_alpha_lml(h, c);
+    k_grad<<<dim3(nb, nb, nz), NTHREADS, GRAD_SMEM, h->stream>>>(c.M, c.cap, nb, c.x(), c.alpha(), (int)c.m, th, h->d_partial);
+    LAUNCHED(h);
+    k_grad_final<<<1, 256, 0, h->stream>>>(h->d_partial, (int)n_partial, th, st, st + 10);
+    LAUNCHED(h);
+    cudaMemcpyAsync(h->pin, st, sizeof(double) * 14, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t ce = cudaStreamEndCapture(h->stream, &h->eval_graph);
+    h->eval_kernels = h->launches - launches0;
+    h->launches = launches0;  // nothing ran yet
+    if (rc != MOGP_OK) return rc;
+    if (ce != cudaSuccess || !h->eval_graph) {
+      cudaGetLastError();
+      return MOGP_OK;  // *ok stays false: eager path
+    }
+    if (cudaGraphInstantiate(&h->eval_exec, h->eval_graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      h->eval_exec = nullptr;
+      return MOGP_OK;
+    }
+    memcpy(h->eval_key, key, sizeof key);
+  }
+  CK(h, cudaGraphLaunch(h->eval_exec, h->stream));
+  CK(h, sync_stream(h));
+  h->launches += h->eval_kernels;
+  h->bytes_d2h += 14 * 8;
+  const double* hs = reinterpret_cast<const double*>(h->pin);
+  int hinfo;
+  memcpy(&hinfo, hs + 8, sizeof(int));
+  if (hinfo != 0 || !isfinite(hs[0])) return MOGP_OK;  // eager path decides (jitter ladder / not PD)
+  c.lml = hs[0];
+  c.quad = hs[1];
+  c.logdet = hs[2];
+  memcpy(c.grad, hs + 10, sizeof(double) * 4);
+  c.valid = c.grad_valid = true;
+  c.stat_on_device = false;
+  c.lml_dirty = false;
+  *ok = true;
+  return MOGP_OK;
+}
+
 // hw supplies the stream and the workspaces, c is the cluster (of hw itself or of another engine on the device).
 static int objective_impl(mogp_engine* hw, Cluster& c, const double* t, int32_t n_t, double* f, double* g) {
   mogp_engine* h = hw;
@@ -1040,7 +1165,13 @@ static int objective_impl(mogp_engine* hw, Cluster& c, const double* t, int32_t 
     int q = 0;
     for (int i = 0; i < 4; ++i)
       if (!fixed[i]) c.theta[i] = logexp_f(t[q++]);
+    c.theta_dirty = true;
     c.valid = c.grad_valid = false;
+  }
+  if (g && !c.valid && c.m > 0 && graphs_enabled()) {
+    bool ok = false;
+    TRY(graph_eval(h, c, &ok));
+    (void)ok;  // on failure valid stays false and the eager path below runs
   }
   if (!c.valid) TRY(infer(h, c));
   if (g && !c.grad_valid) TRY(infer_grad(h, c));

@@ -48,10 +48,14 @@ __device__ __forceinline__ double kern_diag(const Theta& th, double x) {
 // ---------------------------------------------------------------------------------------------
 // Ky (lower) into L, zero accumulator into M.  Rows >= m are identity padding.
 // grid (nb, nb): x = block column, y = block row; CTAs above the diagonal exit.
+// (theta is read from device memory - the cluster's stat block - so that a captured CUDA graph of the whole
+// evaluation can be relaunched at new hyper-parameters without touching its nodes)
 __global__ void __launch_bounds__(NTHREADS) k_build(double* __restrict__ L, double* __restrict__ M, int64_t ld,
-                                                    const double* __restrict__ x, int m, Theta th, double jitter) {
+                                                    const double* __restrict__ x, int m, const Theta* __restrict__ thp,
+                                                    double jitter) {
   const int bj = blockIdx.x, bi = blockIdx.y;
   if (bj > bi) return;
+  const Theta th = *thp;
   __shared__ double sxi[TB], sxj[TB];
   if (threadIdx.x < TB) {
     int i = bi * TB + threadIdx.x, j = bj * TB + threadIdx.x;
@@ -164,8 +168,9 @@ __global__ void __launch_bounds__(NTHREADS) k_trail(double* __restrict__ L, doub
 // ---------------------------------------------------------------------------------------------
 // z = M r with r = y + A x (residual of the NegLinear mean, neg_linear.py:22-23). Warp per row.
 __global__ void __launch_bounds__(NTHREADS) k_z(const double* __restrict__ M, int64_t ld, const double* __restrict__ x,
-                                                const double* __restrict__ y, int m, Theta th,
+                                                const double* __restrict__ y, int m, const Theta* __restrict__ thp,
                                                 double* __restrict__ z) {
+  const Theta th = *thp;
   const int i = blockIdx.x * (NTHREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= m) return;
   const double A = th.mean_func ? th.A : 0.0;
@@ -266,7 +271,8 @@ constexpr int GRAD_SMEM = (2 * TB * LD_R) * (int)sizeof(double);
 
 __global__ void __launch_bounds__(NTHREADS) k_grad(const double* __restrict__ M, int64_t ld, int nb,
                                                    const double* __restrict__ x, const double* __restrict__ alpha,
-                                                   int m, Theta th, double* __restrict__ partial) {
+                                                   int m, const Theta* __restrict__ thp, double* __restrict__ partial) {
+  const Theta th = *thp;
   const int bj = blockIdx.x, bi = blockIdx.y, kc = blockIdx.z;
   const int cta = (kc * gridDim.y + bi) * gridDim.x + bj;
   const int k0 = bi + kc * GRAD_KC;
@@ -324,8 +330,10 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(const double* __restrict__ M,
 }
 
 // grad_theta[4] = dLML/d[A, k0, k1, noise] from the partial sums (one CTA, fixed order).
-__global__ void __launch_bounds__(256) k_grad_final(const double* __restrict__ partial, int n_partial, Theta th,
-                                                    const double* __restrict__ lml_out, double* __restrict__ grad) {
+__global__ void __launch_bounds__(256) k_grad_final(const double* __restrict__ partial, int n_partial,
+                                                    const Theta* __restrict__ thp, const double* __restrict__ lml_out,
+                                                    double* __restrict__ grad) {
+  const Theta th = *thp;
   __shared__ double red[3][256];
   double s[3] = {0.0, 0.0, 0.0};
   for (int i = threadIdx.x; i < n_partial; i += 256)
