@@ -403,7 +403,7 @@ def run_chains(args):
     K0 = max(1, round(N / 50))
 
     def make(cid):
-        eng = _capi.Engine(local)
+        eng = _capi.Engine(local, blocking_sync=len(mine) > 2)   # many chain threads share the host cores
         X, Y, z0 = alsfrs_like(N, seed=100 + cid, n_classes=K0, return_labels=True)
         z0 = np.unique(z0, return_inverse=True)[1].astype(np.int32)
         mix = MoGP(X=X, Y=Y, alpha=K0 / np.log10(N), rand_seed=cid, normalize=True, noise_variance=0.5,

@@ -59,6 +59,9 @@ const char* mogp_last_error(const mogp_engine* h); /* h may be NULL: error of th
 int mogp_version(void);
 /* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
 int64_t mogp_launch_count(const mogp_engine* h);
+/* Host waits of this engine sleep on an event (cudaEventBlockingSync) instead of spinning: for worker engines
+   that share the host cores with many other threads.  Default off (lowest latency). */
+int mogp_engine_set_blocking_sync(mogp_engine* h, int32_t on);
 /* Block until the engine's stream is idle. */
 int mogp_sync(mogp_engine* h);
 /* Device-side time, in ms, spent between the two most recent mogp_timer_start/stop marks

@@ -45,6 +45,7 @@ SIGNATURES = {
     "mogp_last_error": (C.c_char_p, [_H]),
     "mogp_version": (C.c_int, []),
     "mogp_launch_count": (C.c_int64, [_H]),
+    "mogp_engine_set_blocking_sync": (C.c_int, [_H, C.c_int32]),
     "mogp_sync": (C.c_int, [_H]),
     "mogp_timer_start": (C.c_int, [_H]),
     "mogp_timer_stop": (C.c_int, [_H, _dp]),
@@ -127,7 +128,7 @@ def f64(a):
 class Engine:
     """One engine handle = one CUDA stream + cluster slots (see include/mogp_b200.h)."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, blocking_sync=False):
         self.lib = load_library()
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
@@ -137,6 +138,8 @@ class Engine:
             raise EngineError(rc, self.lib.mogp_last_error(None).decode())
         self.h = h
         self.device = int(device)
+        if blocking_sync:
+            self.lib.mogp_engine_set_blocking_sync(self.h, 1)
 
     def close(self):
         if getattr(self, "h", None):

@@ -93,7 +93,8 @@ struct mogp_engine {
   int device = 0;
   cudaStream_t stream = nullptr;   // the stream every helper launches on (normally `main_stream`)
   cudaStream_t main_stream = nullptr, side = nullptr;  // side: independent work of a Gibbs step (SideScope)
-  cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_block = nullptr;
+  bool blocking_sync = false;
   std::vector<std::pair<int64_t, double*>> pending_release;  // buffers the side stream may still be reading
   double* d_apart2 = nullptr;  // alpha partials of the side stream
   int64_t apart2_elems = 0;
@@ -218,7 +219,13 @@ int ensure_pin(mogp_engine* h, size_t need) {
 
 // Every wait on the stream goes through here: afterwards the upload staging can be reused from the start.
 cudaError_t sync_stream(mogp_engine* h) {
-  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaError_t e;
+  if (h->blocking_sync) {  // worker engines: sleep instead of spinning, many of them share the host cores
+    e = cudaEventRecord(h->ev_block, h->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(h->ev_block);
+  } else {
+    e = cudaStreamSynchronize(h->stream);
+  }
   h->up_off = 0;
   return e;
 }
@@ -693,6 +700,7 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
       cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
     g_create_error = std::string("engine init failed: ") + cudaGetErrorString(cudaGetLastError());
     delete h;
@@ -743,6 +751,12 @@ void mogp_engine_destroy(mogp_engine* h) {
 
 const char* mogp_last_error(const mogp_engine* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 int64_t mogp_launch_count(const mogp_engine* h) { return h ? h->launches : 0; }
+
+int mogp_engine_set_blocking_sync(mogp_engine* h, int32_t on) {
+  if (!h) return MOGP_EINVAL;
+  h->blocking_sync = on != 0;
+  return MOGP_OK;
+}
 
 int mogp_sync(mogp_engine* h) {
   if (!h) return MOGP_EINVAL;

@@ -62,7 +62,12 @@ class MoGP_constrained:
         self.ll = []
         self.burnin = 25
         self.trace = []
-        self.refit_concurrency = 12    # worker engines (streams) for the end-of-sweep refits
+        # worker engines (streams + host threads) for the end-of-sweep refits: bounded by the host cores this
+        # process can count on (several ranks share one box)
+        import os
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 8)
+        ranks_here = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1'))))
+        self.refit_concurrency = int(max(2, min(12, cores // ranks_here)))
         self._workers = None
         self.min_margin = np.inf       # smallest |u - cdf edge| seen (assignment-parity diagnostic)
         self.n_refit_evals = 0
@@ -268,7 +273,7 @@ class MoGP_constrained:
         if not hasattr(self, '_workers') or self._workers is None:
             self._workers = []
         while len(self._workers) < want:
-            self._workers.append(_capi.Engine(self.engine.device))
+            self._workers.append(_capi.Engine(self.engine.device, blocking_sync=True))
         return self._workers[:want]
 
     def _refit_id(self, k):
