@@ -110,6 +110,9 @@ int mogp_cluster_remove_rows(mogp_engine* h, int32_t slot, int64_t p, int64_t n)
    identity, leaving the cluster untouched.  *mu_thr = predictive mean at row p + thr_index (NaN if < 0). */
 int mogp_cluster_leave_out_score(mogp_engine* h, int32_t slot, int64_t p, int64_t n, int32_t thr_index,
                                  double* score, double* mu_thr);
+/* Diagnostics: the cluster's 32-double device stat block ([0..3] LML, r'Ky^-1 r, log det, x.alpha; [8] info;
+   [10..13] dLML/dtheta; [14..15] cycle counts of the diagonal-tile Cholesky / inverse; [16..] theta). */
+int mogp_cluster_debug_stat(mogp_engine* h, int32_t slot, double* out32);
 int64_t mogp_cluster_size(mogp_engine* h, int32_t slot);
 /* Diagnostics: the m x m inverse Cholesky factor M = chol(K + (noise + 1e-8) I)^-1 (row-major, lower) and
    alpha = Ky^-1 (y - m(x)) as currently held on the device.  Either output may be NULL. */

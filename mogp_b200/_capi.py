@@ -62,6 +62,7 @@ SIGNATURES = {
     "mogp_cluster_set_members": (C.c_int, [_H, C.c_int32, C.c_int64, _lp]),
     "mogp_cluster_append": (C.c_int, [_H, C.c_int32, C.c_int64, _dp, _dp]),
     "mogp_cluster_remove_rows": (C.c_int, [_H, C.c_int32, C.c_int64, C.c_int64]),
+    "mogp_cluster_debug_stat": (C.c_int, [_H, C.c_int32, _dp]),
     "mogp_cluster_size": (C.c_int64, [_H, C.c_int32]),
     "mogp_cluster_get_factor": (C.c_int, [_H, C.c_int32, _dp, _dp]),
     "mogp_cluster_get_data": (C.c_int, [_H, C.c_int32, _dp, _dp]),
@@ -231,6 +232,11 @@ class Engine:
         x, y = np.empty(m), np.empty(m)
         self.check(self.lib.mogp_cluster_get_data(self.h, slot, dptr(x), dptr(y)))
         return x, y
+
+    def cluster_debug_stat(self, slot):
+        out = np.empty(32)
+        self.check(self.lib.mogp_cluster_debug_stat(self.h, slot, dptr(out)))
+        return out
 
     def cluster_get_factor(self, slot):
         m = self.cluster_size(slot)

@@ -550,7 +550,7 @@ void prof_mark(mogp_engine* h, bool stop) {
 }
 
 template <int BN>
-void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout) {
+void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotPack& pack, int use_pack) {
   const int smem = ScoreSmem<BN>::BYTES;
   static bool attr_done = false;
   if (!attr_done) {
@@ -559,7 +559,7 @@ void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout) {
   }
   dim3 grid((unsigned)(pl.Rpad / BN), (unsigned)pl.max_nb, (unsigned)pl.n_slots);
   prof_mark(h, false);
-  k_score_gemm<BN><<<grid, NTHREADS, smem, h->stream>>>(h->d_slots, pl.kxT, (int)pl.Rpad, pl.part, Tout);
+  k_score_gemm<BN><<<grid, NTHREADS, smem, h->stream>>>(h->d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout);
   prof_mark(h, true);
   LAUNCHED(h);
 }
@@ -579,9 +579,14 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
     TRY(check_slot(h, slots[s]));
     if (!h->cl[slots[s]].valid) TRY(infer(h, h->cl[slots[s]]));
   }
-  char* up = nullptr;
-  TRY(stage_alloc(h, sizeof(SlotView) * (size_t)n_slots, &up));
-  SlotView* hv = reinterpret_cast<SlotView*>(up);
+  const int use_pack = n_slots <= SLOT_PACK ? 1 : 0;
+  SlotPack pack;
+  SlotView* hv = pack.v;
+  if (!use_pack) {
+    char* up = nullptr;
+    TRY(stage_alloc(h, sizeof(SlotView) * (size_t)n_slots, &up));
+    hv = reinterpret_cast<SlotView*>(up);
+  }
   for (int s = 0; s < n_slots; ++s) {
     Cluster& c = h->cl[slots[s]];
     SlotView v;
@@ -615,19 +620,21 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   pl.mu = pl.part + pl.part_total;
   pl.mupart = pl.mu + mu_total;
   pl.T = keep_T ? pl.mupart + mupart_total : nullptr;
-  CK(h, cudaMemcpyAsync(h->d_slots, hv, sizeof(SlotView) * (size_t)n_slots, cudaMemcpyHostToDevice, h->stream));
-  h->bytes_h2d += (int64_t)sizeof(SlotView) * n_slots;
+  if (!use_pack) {
+    CK(h, cudaMemcpyAsync(h->d_slots, hv, sizeof(SlotView) * (size_t)n_slots, cudaMemcpyHostToDevice, h->stream));
+    h->bytes_h2d += (int64_t)sizeof(SlotView) * n_slots;
+  }
   k_kx<<<dim3((unsigned)pl.max_rblk, (unsigned)((pl.Rpad + KX_COLS - 1) / KX_COLS), (unsigned)n_slots), KX_ROWS, 0,
-         h->stream>>>(h->d_slots, xs_dev, (int)R, (int)pl.Rpad, pl.max_rblk, pl.kxT, pl.mupart);
+         h->stream>>>(h->d_slots, pack, use_pack, xs_dev, (int)R, (int)pl.Rpad, pl.max_rblk, pl.kxT, pl.mupart);
   LAUNCHED(h);
   switch (pl.BN) {
-    case 8: launch_score_gemm<8>(h, pl, pl.T); break;
-    case 16: launch_score_gemm<16>(h, pl, pl.T); break;
-    case 32: launch_score_gemm<32>(h, pl, pl.T); break;
-    default: launch_score_gemm<64>(h, pl, pl.T); break;
+    case 8: launch_score_gemm<8>(h, pl, pl.T, pack, use_pack); break;
+    case 16: launch_score_gemm<16>(h, pl, pl.T, pack, use_pack); break;
+    case 32: launch_score_gemm<32>(h, pl, pl.T, pack, use_pack); break;
+    default: launch_score_gemm<64>(h, pl, pl.T, pack, use_pack); break;
   }
   const int64_t pairs = n_pat * n_slots;
-  k_score_epi<<<(unsigned)((pairs + 7) / 8), 256, 0, h->stream>>>(h->d_slots, n_slots, off_dev, n_pat, xs_dev, ys_dev,
+  k_score_epi<<<(unsigned)((pairs + 7) / 8), 256, 0, h->stream>>>(h->d_slots, pack, use_pack, n_slots, off_dev, n_pat, xs_dev, ys_dev,
                                                                      (int)pl.Rpad, pl.part, pl.mupart, pl.max_rblk, pl.mu,
                                                                      thr_index, score_dev,
                                                                      mu_thr_dev, col_mean, col_var, col_lpd);
@@ -1017,6 +1024,11 @@ int mogp_cluster_get_factor(mogp_engine* h, int32_t slot, double* M_out, double*
     CK(h, sync_stream(h));
   }
   return MOGP_OK;
+}
+
+int mogp_cluster_debug_stat(mogp_engine* h, int32_t slot, double* out32) {
+  TRY(check_slot(h, slot));
+  return copy_back(h, out32, h->cl[slot].stat(), STAT);
 }
 
 int64_t mogp_cluster_size(mogp_engine* h, int32_t slot) {

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(NTHREADS) k_build(double* __restrict__ L, doub
 // The serial 64x64 factorisation runs once per panel on one SM instead of once per CTA: with several clusters
 // refitted concurrently (one stream each) that SM-time is what bounds the throughput.
 // The diagonal tile of L keeps A_pp (L_pp is never needed again: log-determinants come from the diagonal of M).
-constexpr int DIAG_SMEM = (TB * LD_C + TB * LD_C + 2 * TB) * (int)sizeof(double);
+constexpr int DIAG_SMEM = (TB * LD_C + TB * LD_C + 9 * TB) * (int)sizeof(double);
 constexpr int PANEL_SMEM = (TB * LD_C + TB * LD_R) * (int)sizeof(double);
 
 __global__ void __launch_bounds__(NTHREADS) k_diag(const double* __restrict__ L, double* __restrict__ M, int64_t ld, int p,
@@ -96,12 +96,20 @@ __global__ void __launch_bounds__(NTHREADS) k_diag(const double* __restrict__ L,
   extern __shared__ __align__(16) double smem[];
   double* sD = smem;                 // [64][LD_C]  A_pp -> L_pp
   double* sM = sD + TB * LD_C;       // [64][LD_C]  M_pp
-  double* col = sM + TB * LD_C;      // [2][64]
+  double* col = sM + TB * LD_C;      // publish buffers
   const int64_t dpp = (int64_t)p * TB * ld + (int64_t)p * TB;
+  const long long t0 = clock64();
   load_tile<LD_C>(sD, L + dpp, ld);
-  int fail = potrf_tile<LD_C>(sD, col);
+  double* rdiag = col + 8 * TB;      // [64]   (col: [2][4][64] for trtri_tile, [2][64] for potrf_tile)
+  int fail = potrf_tile<LD_C>(sD, col, rdiag);
+  const long long t1 = clock64();
   if (fail && threadIdx.x == 0) atomicCAS(info, 0, p * TB + fail);
-  trtri_tile<LD_C>(sD, sM, col);
+  trtri_tile<LD_C>(sD, sM, col, rdiag);
+  const long long t2 = clock64();
+  if (threadIdx.x == 0 && p == 0) {  // diagnostics: cycles of the two serial phases (stat[14], stat[15] via info + 12)
+    reinterpret_cast<double*>(info)[6] = (double)(t1 - t0);
+    reinterpret_cast<double*>(info)[7] = (double)(t2 - t1);
+  }
   for (int idx = threadIdx.x; idx < TB * TB; idx += NTHREADS) {
     int i = idx >> 6, j = idx & 63;
     M[dpp + (int64_t)i * ld + j] = sM[i * LD_C + j];

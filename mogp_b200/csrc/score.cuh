@@ -28,14 +28,23 @@ struct SlotView {
   int64_t part_off;  // offset (doubles) of this slot's partial block: [rb][Rpad]
 };
 
+// Up to SLOT_PACK views travel inside the kernel parameters (no host->device copy on the critical path of a Gibbs
+// step, where the GPU is idle until the first kernel arrives); larger batches read them from device memory.
+constexpr int SLOT_PACK = 32;
+struct SlotPack {
+  SlotView v[SLOT_PACK];
+};
+#define SLOT_ARGS const SlotView* __restrict__ slots, const __grid_constant__ SlotPack pack, int use_pack
+#define SLOT_AT(i) (use_pack ? pack.v[(i)] : slots[(i)])
+
 // Cross covariance, built once per scoring pass: KxT[slot][col][j] = k(x_slot[j], x*_col) (zero in the padding),
 // and the row-block partials of Kx^T alpha.  grid (ceil(mpad_max/256), ceil(Rpad/16), n_slots): one thread per
 // cluster point j, 16 query columns per CTA, coalesced stores along j.
 constexpr int KX_ROWS = 256, KX_COLS = 16;
-__global__ void __launch_bounds__(KX_ROWS) k_kx(const SlotView* __restrict__ slots, const double* __restrict__ xs, int R,
+__global__ void __launch_bounds__(KX_ROWS) k_kx(SLOT_ARGS, const double* __restrict__ xs, int R,
                                                 int Rpad, int max_rblk, double* __restrict__ kxT,
                                                 double* __restrict__ mupart) {
-  const SlotView sv = slots[blockIdx.z];
+  const SlotView sv = SLOT_AT(blockIdx.z);
   const int j = blockIdx.x * KX_ROWS + threadIdx.x;
   if (blockIdx.x * KX_ROWS >= sv.mpad) return;
   __shared__ double wred[KX_ROWS / 32][KX_COLS];
@@ -94,13 +103,12 @@ struct ScoreSmem {
 // even the unpipelined loop - per-copy overhead of the TMA unit; a single bulk copy per tile needs tile-major
 // storage of M, see DESIGN.md "next".)
 template <int BN>
-__global__ void __launch_bounds__(NTHREADS, 1) k_score_gemm(const SlotView* __restrict__ slots,
-                                                            const double* __restrict__ kxT, int Rpad,
+__global__ void __launch_bounds__(NTHREADS, 1) k_score_gemm(SLOT_ARGS, const double* __restrict__ kxT, int Rpad,
                                                             double* __restrict__ part, double* __restrict__ Tout) {
   using S = ScoreShape<BN>;
   constexpr int NS = ScoreStages<BN>::S;
   constexpr int STAGE = ScoreSmem<BN>::STAGE;
-  const SlotView sv = slots[blockIdx.z];
+  const SlotView sv = SLOT_AT(blockIdx.z);
   const int nb = sv.mpad / TB;
   // heavy row blocks first: block row rb needs rb+1 tile products
   const int rb = nb - 1 - (int)blockIdx.y;
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_score_gemm(const SlotView* __re
 // lanes take the patient's visits (columns), each sums its column's row-block partials in a fixed order, the
 // visit log densities are added across the warp by a shuffle tree (deterministic).
 // Optional per-column outputs (mean, var incl. noise, lpd) serve predict / log_predictive_density.
-__global__ void __launch_bounds__(256) k_score_epi(const SlotView* __restrict__ slots, int n_slots,
+__global__ void __launch_bounds__(256) k_score_epi(SLOT_ARGS, int n_slots,
                                                    const int64_t* __restrict__ off, int64_t n_pat,
                                                    const double* __restrict__ xs, const double* __restrict__ ys,
                                                    int Rpad, const double* __restrict__ part,
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(256) k_score_epi(const SlotView* __restrict__ 
   if (gid >= n_pat * n_slots) return;
   const int64_t p = gid / n_slots;
   const int c = (int)(gid % n_slots);
-  const SlotView sv = slots[c];
+  const SlotView sv = SLOT_AT(c);
   const int nb = sv.mpad / TB;
   const int nrb = (sv.mpad + KX_ROWS - 1) / KX_ROWS;
   const int64_t c0 = off[p] - off[0], c1 = off[p + 1] - off[0];

@@ -150,16 +150,43 @@ __device__ __forceinline__ void for_each_acc64(Acc64& acc, F f) {
 // ---- 64x64 diagonal tile: Cholesky and triangular inverse, patch-distributed in registers -------------------
 // All 256 threads take part: thread (ti, tj) = (tid >> 4, tid & 15) keeps the 4x4 patch rows 4ti.., cols 4tj.. in
 // registers (statically indexed).  Each of the 64 column steps publishes one column (or row) through a
-// double-buffered 64-entry shared array, costs ONE block barrier, and updates every patch with 16 FMAs.
-// The loop over the 16 patch columns is a real loop (compact code: the fully unrolled row-per-thread variant was
-// instruction-fetch bound), the 4 columns inside a patch are unrolled so register indices stay static.
+// double-buffered 64-entry shared array, costs ONE barrier, and updates every patch with 16 FMAs.  The loop over
+// the 16 patch columns is a real loop (compact code: a fully unrolled row-per-thread variant was instruction-fetch
+// bound), the 4 columns inside a patch are unrolled so register indices stay static.
 //
+// The 64 pivots are a serial dependency chain, and FP64 latency on this part is long (measured ~770 cycles per
+// pivot with sqrt + divide on the chain).  So: the factorisation runs as L D L^T - per pivot only a reciprocal
+// (hardware seed + two Newton steps = 4 dependent FMAs) - the square roots are taken for all columns at once at
+// the end; and warps whose rows are all above the pivot leave the loop, so the barrier shrinks as it goes
+// (named barrier with the live thread count).
+
+// 1/d to <= 1 ulp: rcp.approx seed (~2^-23) and two Newton-Raphson steps.
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+// barrier among the warps first..7 of the CTA (they are the ones still in the loop)
+__device__ __forceinline__ void bar_live(int first_warp) {
+  asm volatile("bar.sync 1, %0;" ::"r"((8 - first_warp) * 32) : "memory");
+}
+
 // In-place lower Cholesky of s[64][LD] (lower part valid on entry); strict upper triangle zeroed.
-// Returns 0 or (1 + first non-positive pivot column), uniform across the CTA.
+// rdiag[k] = 1 / L_kk.  Returns 0 or (1 + first non-positive pivot column), uniform across the CTA.
+//
+// Four columns per barrier: the owners of patch column kb publish their (not yet eliminated) 4-column block; after
+// ONE barrier every live thread redoes the tiny 4x4 L D L^T of the diagonal patch in registers (four reciprocals -
+// the serial chain), eliminates the rows it needs through those four pivots, and applies the rank-4 update to its
+// own patch.  16 barriers instead of 64; the pivot chain (64 reciprocals) is what remains.
 template <int LD>
-__device__ int potrf_tile(double* __restrict__ s, double* __restrict__ buf /* >= 128 doubles */) {
-  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+__device__ int potrf_tile(double* __restrict__ s, double* __restrict__ buf /* >= 512 doubles */,
+                          double* __restrict__ rdiag /* 64 */) {
+  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15, warp = tid >> 5;
   __shared__ int s_fail;
+  __shared__ double dpiv[TB];  // the pivots d_k of L D L^T
   if (tid == 0) s_fail = 0;
   __syncthreads();  // the tile was just staged by other threads
   double a[4][4];
@@ -167,96 +194,167 @@ __device__ int potrf_tile(double* __restrict__ s, double* __restrict__ buf /* >=
   for (int e = 0; e < 4; ++e)
 #pragma unroll
     for (int f = 0; f < 4; ++f) a[e][f] = (4 * tj + f <= 4 * ti + e) ? s[(4 * ti + e) * LD + 4 * tj + f] : 0.0;
-  for (int kb = 0; kb < 16; ++kb) {
+  // warp w holds patch rows ti = 2w, 2w+1: it is needed while kb <= 2w + 1
+  for (int kb = 0; kb <= 2 * warp + 1; ++kb) {
+    const int first_warp = kb >> 1;
+    double* pb = buf + (kb & 1) * (4 * TB);  // [64 rows][4]: the column block before its own elimination
+    if (tj == kb && ti >= kb) {
 #pragma unroll
-    for (int kf = 0; kf < 4; ++kf) {
-      const int k = 4 * kb + kf;
-      double* cb = buf + (k & 1) * TB;
-      if (tj == kb) {
+      for (int e = 0; e < 4; ++e)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) cb[4 * ti + e] = a[e][kf];
-      }
-      __syncthreads();
-      double dk = cb[k];
-      if (!(dk > 0.0)) {
-        if (tid == 0 && s_fail == 0) s_fail = k + 1;
-        dk = 1.0;  // keep going with a harmless pivot; the caller discards the result
-      }
-      if (ti >= kb && tj <= ti) {
-        const double inv = 1.0 / dk;
-        double ci[4], cj[4];
+        for (int q = 0; q < 4; ++q) pb[(4 * ti + e) * 4 + q] = a[e][q];
+    }
+    bar_live(first_warp);
+    if (ti >= kb && tj >= kb && tj <= ti) {
+      // 4x4 L D L^T of the diagonal patch (unscaled columns): D4[e][q], e >= q; u[q] = 1 / d_q
+      double D4[4][4], u[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          ci[e] = cb[4 * ti + e] * inv;
-          cj[e] = cb[4 * tj + e];
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) D4[e][q] = (q <= e) ? pb[(4 * kb + e) * 4 + q] : 0.0;
+      bool bad = false;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double dq = D4[q][q];
+        if (!(dq > 0.0)) {
+          bad = true;
+          if (ti == kb && tj == kb && s_fail == 0) s_fail = 4 * kb + q + 1;
+          dq = 1.0;  // keep going with a harmless pivot; the caller discards the result
+          D4[q][q] = dq;
         }
+        u[q] = fast_rcp(dq);
+#pragma unroll
+        for (int e = q + 1; e < 4; ++e) {
+          const double t = D4[e][q] * u[q];
+#pragma unroll
+          for (int f = q + 1; f <= e; ++f) D4[e][f] -= t * D4[f][q];
+        }
+      }
+      (void)bad;
+      if (ti == kb) {  // the diagonal patch itself (tj == kb here)
 #pragma unroll
         for (int e = 0; e < 4; ++e)
 #pragma unroll
-          for (int f = 0; f < 4; ++f) {
-            const int i = 4 * ti + e, j = 4 * tj + f;
-            if (j > k && j <= i) a[e][f] -= ci[e] * cj[f];
-          }
-        if (tj == kb) {
-          const double rs = rsqrt(dk);
+          for (int q = 0; q <= e; ++q) a[e][q] = D4[e][q];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = 4 * ti + e;
-            a[e][kf] = (i == k) ? sqrt(dk) : (i > k ? a[e][kf] * rs : a[e][kf]);
+        for (int q = 0; q < 4; ++q) dpiv[4 * kb + q] = D4[q][q];
+      } else {
+        // eliminate the rows this thread needs through the four pivots: row r of the block, values v[0..3]:
+        //   v[f] -= v[q] * D4[f][q] * u[q]  for f > q
+        double ci[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ci[e][q] = pb[(4 * ti + e) * 4 + q];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const double t = ci[e][q] * u[q];
+#pragma unroll
+            for (int f = q + 1; f < 4; ++f) ci[e][f] -= t * D4[f][q];
           }
+        }
+        if (tj == kb) {  // owner of the column block: these are its final (unscaled) columns
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[e][q] = ci[e][q];
+        } else {
+          double cj[4][4];
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cj[f][q] = pb[(4 * tj + f) * 4 + q];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              const double t = cj[f][q] * u[q];
+#pragma unroll
+              for (int g = q + 1; g < 4; ++g) cj[f][g] -= t * D4[g][q];
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+              if (4 * tj + f <= 4 * ti + e) {
+                double acc = a[e][f];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc -= (ci[e][q] * u[q]) * cj[f][q];
+                a[e][f] = acc;
+              }
+            }
         }
       }
     }
   }
+  __syncthreads();
+  // L = (unscaled columns) * D^-1/2
+  if (tid < TB) rdiag[tid] = rsqrt(dpiv[tid]);
+  __syncthreads();
 #pragma unroll
   for (int e = 0; e < 4; ++e)
 #pragma unroll
-    for (int f = 0; f < 4; ++f) s[(4 * ti + e) * LD + 4 * tj + f] = (4 * tj + f <= 4 * ti + e) ? a[e][f] : 0.0;
+    for (int f = 0; f < 4; ++f) {
+      const int i = 4 * ti + e, j = 4 * tj + f;
+      s[i * LD + j] = (j <= i) ? a[e][f] * rdiag[j] : 0.0;
+    }
   __syncthreads();
   return s_fail;
 }
 
 // sM = inverse of the lower-triangular tile sL (both [64][LD]); upper triangle of sM zeroed.
-// Right-looking on X (= I at the start): step j scales row j by 1/L_jj, publishes it, and every row i > j
-// subtracts L_ij * row j.
+// Right-looking on X (= I at the start), four rows per barrier: the threads that own patch row jb finish its four
+// rows locally (row j scaled by 1/L_jj = rdiag[j], rows j+1.. of the patch reduced by it), publish them, and every
+// patch row below applies the rank-4 update x_i -= sum_q L_{i,4jb+q} * row_q.  16 barriers instead of 64.
 template <int LD>
-__device__ void trtri_tile(const double* __restrict__ sL, double* __restrict__ sM, double* __restrict__ buf /* >= 128 */) {
-  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+__device__ void trtri_tile(const double* __restrict__ sL, double* __restrict__ sM, double* __restrict__ buf /* >= 512 */,
+                           const double* __restrict__ rdiag) {
+  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15, warp = tid >> 5;
   double x[4][4];
 #pragma unroll
   for (int e = 0; e < 4; ++e)
 #pragma unroll
     for (int f = 0; f < 4; ++f) x[e][f] = (4 * ti + e == 4 * tj + f) ? 1.0 : 0.0;
-  for (int jb = 0; jb < 16; ++jb) {
+  for (int jb = 0; jb <= 2 * warp + 1; ++jb) {
+    const int first_warp = jb >> 1;
+    double* rb = buf + (jb & 1) * (4 * TB);  // [4][64]
+    if (ti == jb) {
 #pragma unroll
-    for (int jf = 0; jf < 4; ++jf) {
-      const int j = 4 * jb + jf;
-      double* rb = buf + (j & 1) * TB;
-      if (ti == jb) {
-        const double inv = 1.0 / sL[j * LD + j];
+      for (int q = 0; q < 4; ++q) {
+        const int j = 4 * jb + q;
+        const double inv = rdiag[j];
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          x[jf][f] *= inv;
-          rb[4 * tj + f] = x[jf][f];
+        for (int f = 0; f < 4; ++f) x[q][f] *= inv;
+#pragma unroll
+        for (int e = q + 1; e < 4; ++e) {
+          const double l = sL[(4 * jb + e) * LD + j];
+#pragma unroll
+          for (int f = 0; f < 4; ++f) x[e][f] -= l * x[q][f];
         }
       }
-      __syncthreads();
-      if (ti >= jb && tj <= jb) {  // rows below j; row j has entries only in columns <= j
-        double r[4];
 #pragma unroll
-        for (int f = 0; f < 4; ++f) r[f] = rb[4 * tj + f];
+      for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = 4 * ti + e;
-          if (i > j) {
-            const double l = sL[i * LD + j];
+        for (int f = 0; f < 4; ++f) rb[q * TB + 4 * tj + f] = x[q][f];
+    }
+    bar_live(first_warp);
+    if (ti > jb && tj <= jb) {  // patch rows below; rows of block jb have entries only in columns <= 4jb+3
+      double r[4][4];
 #pragma unroll
-            for (int f = 0; f < 4; ++f) x[e][f] -= l * r[f];
-          }
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) r[q][f] = rb[q * TB + 4 * tj + f];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double l = sL[(4 * ti + e) * LD + 4 * jb + q];
+#pragma unroll
+          for (int f = 0; f < 4; ++f) x[e][f] -= l * r[q][f];
         }
       }
     }
   }
+  __syncthreads();
 #pragma unroll
   for (int e = 0; e < 4; ++e)
 #pragma unroll

@@ -18,3 +18,7 @@ for m in [2600]:
     except Exception as e:
         print(m,"FAIL",e)
     eng.cluster_free(slot)
+slot=eng.cluster_create(spec,np.array([0.3,1.0,4.0,0.5]))
+eng.cluster_set_data(slot,x,y)
+st=eng.cluster_debug_stat(slot)
+print("k_diag cycles: potrf(+load) %.0f  trtri %.0f" % (st[14], st[15]))
