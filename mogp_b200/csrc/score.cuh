@@ -101,7 +101,9 @@ struct ScoreSmem {
 // DMMAs of the current one; one block barrier per tile.
 // (Measured on B200: the same ring fed by 512-byte cp.async.bulk row copies + mbarriers ran 1.45x SLOWER than
 // even the unpipelined loop - per-copy overhead of the TMA unit; a single bulk copy per tile needs tile-major
-// storage of M, see DESIGN.md "next".)
+// storage of M, see DESIGN.md "next".  A persistent one-CTA-per-SM variant whose ring never drains between work
+// items was also measured: 169 us vs 162 us per launch - the hardware CTA scheduler balances the ~1800 items
+// better than a static snake deal, and the per-tile cursor logic costs more than the pipeline refills save.)
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1) k_score_gemm(SLOT_ARGS, const double* __restrict__ kxT, int Rpad,
                                                             double* __restrict__ part, double* __restrict__ Tout) {

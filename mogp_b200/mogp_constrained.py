@@ -341,7 +341,13 @@ class MoGP_constrained:
         score[:, active] += eng.score_pairs(off, x, y, slots)                                # :336-338
         theta0 = initial_theta(self.kernel, self.signal_variance, self.noise_variance, 4., 0.0)
         score[:, -1] += eng.new_cluster_ll(self._spec(mean_func=True), theta0, off, x, y, a_draws)   # :339
-        return np.exp(score - logsumexp(score, axis=1, keepdims=True))                       # :340-341
+        if P == 1:
+            return np.exp(score - logsumexp(score, axis=1, keepdims=True))                   # :340-341
+        # the same softmax for many rows without SciPy's per-call overhead: lse = max + log(sum(exp(s - max)))
+        mx = np.max(score, axis=1, keepdims=True)
+        lse = mx + np.log(np.sum(np.exp(score - mx), axis=1, keepdims=True))
+        np.subtract(score, lse, out=score)
+        return np.exp(score, out=score)
 
 
 class MoGP(MoGP_constrained):
