@@ -160,7 +160,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": ncores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -303,7 +303,7 @@ def run_b200(args):
                                     "sample": "{} consecutive patient-steps ({:.3f} s each) + L-BFGS-B refit of 1 cluster ({:.2f} s, "
                                               "{} evaluations) from the same initial state; sweep = N*step + active*refit"
                                               .format(args.cpu_steps, ts, tr, evals)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -380,7 +380,7 @@ def run_predict(args):
                              "traffic": None, "peak_source": "nominal B200 FP64 (no measured FP64 peak in MEASURED_PEAKS.json)",
                              "share_of_step": prof["ms"] / ms},
                 "check": {"rows_sum_to_one": bool(np.allclose(full.sum(1), 1.0, atol=1e-9)), "shape": list(full.shape)}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -453,12 +453,26 @@ def run_chains(args):
                                        "dealt round-robin to the GPUs".format(args.chains, N, args.chain_refit)},
                 "gpu_launches": int(sum(c[0].launch_count() for c in chains) - l0),
                 "check": {"chains_gathered": len(res), "active_clusters_chain0": int((res[0]['Nk'] > 0).sum())}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """Print THE json line on the process's real stdout (see main: fd 1 is pointed at stderr while the run lasts, so
+    that banners printed from native code - NCCL's version line, for one - cannot add lines to stdout)."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
