@@ -14,8 +14,10 @@
  *   - all `const double*` / `const int64_t*` arguments are HOST pointers unless the
  *     name ends in `_dev`; copies to / from the device happen inside the call on the
  *     engine's stream (so timing a call with host buffers is an end-to-end timing);
- *   - an engine owns one CUDA stream; calls on one engine are not thread-safe, calls
- *     on different engines are (one host thread + one engine per Gibbs chain);
+ *   - an engine owns its CUDA streams (a main one, and a side one on which a Gibbs step runs its
+ *     independent pieces); calls on one engine are not thread-safe, calls on different engines
+ *     are (one host thread + one engine per Gibbs chain; worker engines for concurrent refits,
+ *     see mogp_cluster_objective_on);
  *   - theta is the natural-parameter vector in GPy's order
  *         rbf    : [A, rbf.variance, rbf.lengthscale, Gaussian_noise.variance]
  *         linear : [A, linear.variances, bias.variance, Gaussian_noise.variance]

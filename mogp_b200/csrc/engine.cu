@@ -463,6 +463,7 @@ int infer_grad(mogp_engine* h, Cluster& c) {
   const int nz = (nb + GRAD_KC - 1) / GRAD_KC;
   const int64_t n_partial = (int64_t)nb * nb * nz;
   TRY(ensure(h, &h->d_partial, &h->partial_elems, n_partial * 3));
+  TRY(ensure_pin(h, 256));  // (a worker engine may get here without ever having run an inference itself)
   TRY(sync_theta(h, c));
   const Theta* th = c.theta_dev();
   double* st = c.stat();
@@ -1188,11 +1189,21 @@ static int objective_impl(mogp_engine* hw, Cluster& c, const double* t, int32_t 
   for (int i = 0; i < 4; ++i) nfree += !fixed[i];
   if (t) {
     if (n_t != nfree) FAIL(h, MOGP_EINVAL, "expected %d optimiser coordinates, got %d", nfree, n_t);
+    // paramz re-runs inference whenever the optimiser array is set; the result at an unchanged theta is the
+    // same, so the factor (and gradient) of the last evaluation are kept when t maps to the current theta -
+    // L-BFGS-B's f(x_opt) re-evaluation and the final set (obsmodel.py:94) usually hit this.
     int q = 0;
-    for (int i = 0; i < 4; ++i)
-      if (!fixed[i]) c.theta[i] = logexp_f(t[q++]);
-    c.theta_dirty = true;
-    c.valid = c.grad_valid = false;
+    bool same = true;
+    double th_new[4];
+    for (int i = 0; i < 4; ++i) {
+      th_new[i] = fixed[i] ? c.theta[i] : logexp_f(t[q++]);
+      same = same && th_new[i] == c.theta[i];
+    }
+    if (!same) {
+      memcpy(c.theta, th_new, sizeof th_new);
+      c.theta_dirty = true;
+      c.valid = c.grad_valid = false;
+    }
   }
   if (g && !c.valid && c.m > 0 && graphs_enabled()) {
     bool ok = false;

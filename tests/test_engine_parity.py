@@ -206,3 +206,34 @@ def test_refit_reaches_the_oracle_optimum(eng):
     assert np.allclose(th, o.param_array, rtol=2e-6)
     assert rel(gm.objective_function(), o.objective()) < 1e-9
     eng.cluster_free(slot)
+
+
+def test_worker_engine_objective_and_concurrent_refits(eng):
+    """mogp_cluster_objective_on: a cluster of one engine evaluated on another engine's stream - first at the
+    cluster's CURRENT theta (the owner's factor is reused, only the gradient runs on the worker), then at a new one;
+    and `optimize_many` (concurrent refits on worker engines) lands where sequential `optimize()` does."""
+    from mogp_b200 import _capi
+    from mogp_b200.obsmodel import GPModel, optimize_many
+    worker = _capi.Engine(0, blocking_sync=True)
+    pairs = [build_pair(eng, c, seed=7) for c in (CASES[0], CASES[2], CASES[5])]
+    for o, slot, spec, rs in pairs:
+        t0 = eng.cluster_optimizer_array(slot)
+        f_w, g_w = eng.cluster_objective(slot, t0, worker=worker)          # same theta: no re-inference
+        f_o, g_o = o.objective_grads(o.optimizer_array())
+        assert rel(f_w, f_o) < RTOL and np.max(np.abs(g_w - g_o)) / np.max(np.abs(g_o)) < 1e-8
+        t1 = t0 + 0.05
+        f_w, g_w = eng.cluster_objective(slot, t1, worker=worker)
+        f_o, g_o = o.objective_grads(t1)
+        assert rel(f_w, f_o) < RTOL and np.max(np.abs(g_w - g_o)) / np.max(np.abs(g_o)) < 1e-8
+    models = [GPModel(eng, spec, None, slot=slot) for _o, slot, spec, _r in pairs]
+    start = [eng.cluster_get_theta(m.slot) for m in models]
+    optimize_many(models, [worker, _capi.Engine(0)])
+    conc = [eng.cluster_get_theta(m.slot) for m in models]
+    for m, th in zip(models, start):
+        eng.cluster_set_theta(m.slot, th)
+        m.optimize()
+    for m, th in zip(models, conc):
+        assert np.array_equal(eng.cluster_get_theta(m.slot), th)           # bit-identical: same evaluations
+    for _o, slot, _s, _r in pairs:
+        eng.cluster_free(slot)
+    worker.close()
