@@ -144,3 +144,37 @@ def test_predict_batch_equals_predict_loop(eng):
         np.random.set_state(state)
         p_single = mix.predict(Xq[i][keep], Yq[i][keep])
         assert p_single.shape == P[i].shape and abs(p_single.sum() - 1.0) < 1e-12
+
+
+def test_full_size_sweep_of_rank_updates_matches_refactorisation(eng):
+    """BASELINE's 10k-patient configuration: after a whole sweep (10 000 steps, ~1 700 row deletions + appends per
+    sweep at fixed theta, no refit in between) every cluster's log marginal and a probe score equal those of a fresh
+    factorisation of the same data to 1e-10 - the rank-n updates do not drift."""
+    from mogp_b200 import MoGP_constrained
+    from mogp_b200.synth import alsfrs_like
+    N, K0 = 10000, 30
+    X, Y, z0 = alsfrs_like(N, seed=0, n_classes=K0, return_labels=True)
+    z0 = np.unique(z0, return_inverse=True)[1].astype(np.int32)
+    mix = MoGP_constrained(X=X, Y=Y, alpha=K0 / np.log10(N), num_iter=3, rand_seed=0, normalize=True, threshold=0.5,
+                           noise_variance=0.5, refit='sweep', init_z=z0, engine=eng)
+    mix.initialize_sampler(K0, True)
+    mix.refit_all()
+    perm, a, u = mix._draws_for_sweep(N)
+    eng.chain_sweep(perm, a, u)
+    mix._sync_state()
+    assert mix.allocmodel.Nk.sum() == N and int(np.sum(mix.z != z0)) > 500
+    rs = np.random.RandomState(1)
+    xq, yq = np.sort(np.r_[0.0, rs.uniform(0.3, 8, 8)]), rs.randn(9)
+    for k in mix._active():
+        s = mix.obsmodel[k].model.slot
+        lml_u = eng.cluster_loglik(s)
+        sc_u = eng.score_pairs(np.array([0, 9]), xq, yq, [s])[0, 0]
+        x, y = eng.cluster_get_data(s)
+        members_visits = sum(int((~np.isnan(X[i])).sum()) for i in np.where(mix.z == k)[0])
+        assert x.size == members_visits                      # the factor holds exactly the members' visits
+        f = eng.cluster_create(mix._spec(), eng.cluster_get_theta(s))
+        eng.cluster_set_data(f, x, y)
+        assert abs(lml_u - eng.cluster_loglik(f)) <= 1e-10 * abs(lml_u)
+        sc_f = eng.score_pairs(np.array([0, 9]), xq, yq, [f])[0, 0]
+        assert abs(sc_u - sc_f) <= 1e-10 * abs(sc_f)
+        eng.cluster_free(f)
