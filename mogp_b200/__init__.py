@@ -9,3 +9,4 @@ from .obsmodel import GPobs  # noqa: F401
 from .allocmodel import DPmix  # noqa: F401
 from .mogp_constrained import MoGP_constrained, MoGP  # noqa: F401
 from . import utils  # noqa: F401
+from . import postprocessing  # noqa: F401

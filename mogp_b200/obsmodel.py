@@ -221,17 +221,34 @@ class GPobs:
         spec = make_spec(kernel, mean_func, signal_variance_fix, noise_variance_fix)
         if _slot is not None:               # view of a slot the chain engine already manages
             self.model = GPModel(engine, spec, None, slot=_slot)
-            self.X, self.Y = None, None
+            self._X, self._Y = None, None
         else:
             # GPy.mappings.Linear.__init__ draws A from the global generator (neg_linear.py:19-20)
             a_draw = np.random.randn(1, 1)[0, 0] if mean_func else None
             theta = initial_theta(kernel, signal_variance, noise_variance, lengthscale, a_draw)
             self.model = GPModel(engine, spec, theta, X=_col(X), Y=_col(Y))
-            self.X, self.Y = X, Y
+            self._X, self._Y = X, Y
         self.ll = self.model.log_likelihood()                      # obsmodel.py:56
         self.tempX = None
         self.tempY = None
         self.templl = None
+
+    # X / Y: the arrays the caller handed over, or - for a view of a chain-managed slot - the engine's copy
+    @property
+    def X(self):
+        return self.model.X if self._X is None else self._X
+
+    @X.setter
+    def X(self, v):
+        self._X = v
+
+    @property
+    def Y(self):
+        return self.model.Y if self._Y is None else self._Y
+
+    @Y.setter
+    def Y(self, v):
+        self._Y = v
 
     def calc_ll(self):                                             # obsmodel.py:63-66
         self.ll = self.model.log_likelihood()
@@ -242,7 +259,7 @@ class GPobs:
         self.model.set_XY(_col(X), _col(Y))
 
     def calc_score(self, Xnew, Ynew):                              # obsmodel.py:75-81
-        X, Y = (self.model.X, self.model.Y) if self.X is None else (_col(self.X), _col(self.Y))
+        X, Y = _col(self.X), _col(self.Y)
         self.tempX = np.vstack([X, _col(Xnew)])
         self.tempY = np.vstack([Y, _col(Ynew)])
         return np.sum(self.model.log_predictive_density(_col(Xnew), _col(Ynew), None))
