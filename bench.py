@@ -225,10 +225,13 @@ def run_b200(args):
     split[0] = split[1] = 0.0
     eng.profile(True)
     eng.profile_read(reset=True)
+    cnt0 = eng.chain_counters()
     eng.timer_start()
     for _ in range(args.steps):
         device_sweep()
     ms = eng.timer_stop()
+    cnt1 = eng.chain_counters()
+    counters = {k: cnt1[k] - cnt0[k] for k in cnt1}
     prof = eng.profile_read(reset=True)
     eng.profile(False)
     launches = all_launches() - l0
@@ -268,14 +271,37 @@ def run_b200(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else \
+        hbm_peak, hbm_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else \
             (6650.0, "fallback (B200_PROFILING.md)")
-        achieved = prof["alg_bytes"] / (prof["ms"] * 1e-3) / 1e9 if prof["ms"] > 0 else None
+        # FP64 tensor peak: MEASURED_PEAKS.json holds only HBM and bf16; tcgen05 has no FP64, the FP64 tensor instruction
+        # is DMMA.8x8x4, measured on this pool's B200 by scripts/peaks/fp64_peak.cu (profiles/r1_fp64_peaks.txt)
+        fp64_peak, fp64_src = 37.2, "measured DMMA.8x8x4 peak (profiles/r1_fp64_peaks.txt)"
+        sec = prof["ms"] * 1e-3
+        gbs = prof["alg_bytes"] / sec / 1e9 if sec > 0 else None
+        tfs = prof["alg_flops"] / sec / 1e12 if sec > 0 else None
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "score_gemm_traffic.json"))).get("traffic_bytes_per_launch")
         except Exception:
             pass
+        # one pass over the factors serves several patients (look-ahead window): whichever roof is closer binds
+        hbm_frac = gbs / hbm_peak if gbs else None
+        fp_frac = tfs / fp64_peak if tfs else None
+        tensor_bound = fp_frac is not None and hbm_frac is not None and fp_frac >= hbm_frac
+        if tensor_bound:
+            roof = {"bound": "tensor", "achieved": tfs, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp_frac,
+                    "peak_source": fp64_src}
+        else:
+            roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac,
+                    "peak_source": hbm_src}
+        roof.update({"kernel": "k_score_gemm (T = M Kx, FP64 DMMA)", "traffic": traffic, "launches": prof["launches"],
+                     "avg_launch_us": prof["ms"] / max(prof["launches"], 1) * 1e3,
+                     "alg_bytes_per_launch": prof["alg_bytes"] / max(prof["launches"], 1),
+                     "alg_flops_per_launch": prof["alg_flops"] / max(prof["launches"], 1),
+                     "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac, "peak_source": hbm_src},
+                     "fp64": {"achieved": tfs, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp_frac, "peak_source": fp64_src},
+                     "pairs_per_launch": counters["pairs"] / max(prof["launches"], 1),
+                     "share_of_step": prof["ms"] / ms})
         line = {"metric": "Gibbs sweeps/sec @10k patients", "value": world * args.steps / (ms_max * 1e-3), "unit": "sweeps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -283,18 +309,14 @@ def run_b200(args):
                 "e2e": {"value": world * args.steps / (ms_e2e_max * 1e-3), "unit": "sweeps/s",
                         "h2d_bytes_per_step": (b1[0] - b0[0]) // args.steps, "d2h_bytes_per_step": (b1[1] - b0[1]) // args.steps},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "k_score_gemm (T = M Kx, FP64 DMMA)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                             "peak_source": peak_src, "launches": prof["launches"],
-                             "avg_launch_us": prof["ms"] / max(prof["launches"], 1) * 1e3,
-                             "alg_bytes_per_launch": prof["alg_bytes"] / max(prof["launches"], 1),
-                             "fp64_tflops": prof["alg_flops"] / (prof["ms"] * 1e-3) / 1e12 if prof["ms"] > 0 else None,
-                             "share_of_step": prof["ms"] / ms},
+                "roofline": roof,
                 "clocks": clocks,
                 "chain": {"active_clusters": len(occupancy), "patients_moved_in_timed_sweeps": moved,
                           "pair_logliks_per_s": world * args.steps * N * len(occupancy) / (ms_max * 1e-3),
                           "refit_evals": int(mix.n_refit_evals), "total_loglik": ll,
-                          "steps_s_per_sweep": split_timed[0], "refit_s_per_sweep": split_timed[1]}}
+                          "steps_s_per_sweep": split_timed[0], "refit_s_per_sweep": split_timed[1],
+                          "lookahead": {k: counters[k] for k in ("window_passes", "rescoring_passes", "window_patients",
+                                                                 "open_s", "rescore_s", "commit_s")}}}
         if world == 1 and not args.no_cpu_baseline:
             orc, _t_init = oracle_sample(args, 0)
             ts, tr, nact, evals = oracle_step_times(orc, args.cpu_steps, 1)

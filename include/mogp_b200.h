@@ -90,6 +90,11 @@ int mogp_transfer_bytes(mogp_engine* h, int64_t* h2d, int64_t* d2h);
    8 (m^2/2 + 3m) + 16 n + 8 bytes and n m (m + 10) flops). */
 int mogp_profile(mogp_engine* h, int32_t enable);
 int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg_bytes, double* alg_flops, int32_t reset);
+/* Look-ahead accounting of the attached chain since mogp_chain_init: out[0] = window passes (one pass over every
+   active factor), out[1] = re-scoring passes (clusters that changed), out[2] = patients served from windows,
+   out[3] = (patient, cluster) pairs scored by the profiled launches since the last profile reset,
+   out[4..6] = host seconds spent opening windows / re-scoring / committing moves (each includes its waits). */
+int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out);
 
 /* ---- one cluster's GP = one GPobs object ------------------------------------------------- */
 /* GPobs.__init__ (obsmodel.py:7-61) minus data: allocates a cluster slot. */
@@ -175,7 +180,11 @@ typedef struct mogp_chain_config {
      1: rank-n up/down-dates at fixed theta + leave-block-out score for the patient's own cluster
         (same mathematics, rows kept in arrival order; agrees with mode 0 to rounding). */
   int32_t fast_updates;
-  int32_t reserved;
+  /* mogp_chain_sweep, fast mode: the sweep order is known in advance, so consecutive patients totalling at most
+     `lookahead` visits (query columns) are scored against every active cluster in ONE pass over the factors; the
+     chain stays sequential (a cached score is used only while its cluster is unchanged, the rest is re-scored).
+     0 = engine default (32), negative = off (one pass per patient), capped at 64. */
+  int32_t lookahead;
 } mogp_chain_config;
 
 /* initialize_sampler + calc_suffstats (mogp_constrained.py:187-214,220): z[N] = initial cluster id per patient

@@ -30,7 +30,7 @@ class ChainConfig(C.Structure):
     _fields_ = [("spec", ModelSpec), ("alpha", C.c_double), ("signal_variance", C.c_double),
                 ("noise_variance", C.c_double), ("lengthscale", C.c_double), ("use_threshold", C.c_int32),
                 ("thr_index", C.c_int32), ("threshold", C.c_double), ("fast_updates", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("lookahead", C.c_int32)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -54,6 +54,7 @@ SIGNATURES = {
     "mogp_transfer_bytes": (C.c_int, [_H, _lp, _lp]),
     "mogp_profile": (C.c_int, [_H, C.c_int32]),
     "mogp_profile_read": (C.c_int, [_H, _lp, _dp, _dp, _dp, C.c_int32]),
+    "mogp_chain_counters": (C.c_int, [_H, _dp, C.c_int32]),
     "mogp_cluster_create": (C.c_int, [_H, C.POINTER(ModelSpec), _dp, _ip]),
     "mogp_cluster_free": (C.c_int, [_H, C.c_int32]),
     "mogp_cluster_set_theta": (C.c_int, [_H, C.c_int32, _dp]),
@@ -191,6 +192,12 @@ class Engine:
         n, ms, by, fl = C.c_int64(), C.c_double(), C.c_double(), C.c_double()
         self.check(self.lib.mogp_profile_read(self.h, C.byref(n), C.byref(ms), C.byref(by), C.byref(fl), int(reset)))
         return dict(launches=n.value, ms=ms.value, alg_bytes=by.value, alg_flops=fl.value)
+
+    def chain_counters(self):
+        out = np.zeros(7)
+        self.check(self.lib.mogp_chain_counters(self.h, dptr(out), 7))
+        return dict(window_passes=int(out[0]), rescoring_passes=int(out[1]), window_patients=int(out[2]), pairs=out[3],
+                    open_s=out[4], rescore_s=out[5], commit_s=out[6])
 
     def timer_start(self):
         self.check(self.lib.mogp_timer_start(self.h))

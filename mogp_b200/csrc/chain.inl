@@ -144,11 +144,12 @@ int rm_gram(mogp_engine* h, Cluster& c, int64_t p, int n) {
 }
 
 // Leave-block-out score into w.own[0..2] (device).
-int own_score(mogp_engine* h, Cluster& c, int64_t p, int n, const double* yB_dev, int thr_index) {
+int own_score(mogp_engine* h, Cluster& c, int64_t p, int n, const double* yB_dev, int thr_index, double* out_dev = nullptr) {
   RmGeom g = make_geom(c, p, n);
   RmWork w;
   TRY(rm_work(h, g, &w));
-  k_own_final<<<1, 256, 0, h->stream>>>(c.alpha(), yB_dev, g, w, g.nbn - g.I0, make_theta(c), thr_index, w.own);
+  k_own_final<<<1, 256, 0, h->stream>>>(c.alpha(), yB_dev, g, w, g.nbn - g.I0, make_theta(c), thr_index,
+                                        out_dev ? out_dev : w.own);
   LAUNCHED(h);
   return MOGP_OK;
 }
@@ -390,6 +391,30 @@ int chain_score(mogp_engine* h, double a_draw) {
   return MOGP_OK;
 }
 
+// Where the scoring pass left T = M Kx (and the predictive means) of the pending patient under `slot`.
+void locate_T(mogp_engine* h, int32_t slot, const double** T, const double** mu) {
+  Chain& ch = h->chain;
+  *T = *mu = nullptr;
+  if (ch.win.open) {
+    const Chain::Window& w = ch.win;
+    if (slot >= 0 && slot < (int32_t)w.slot_ok.size() && w.slot_ok[slot] && slot < (int32_t)w.e[w.cur].size()) {
+      *T = w.e[w.cur][slot].T;
+      *mu = w.e[w.cur][slot].mu;
+    }
+    return;
+  }
+  if (!ch.plan.T) return;
+  int64_t kx_off = 0;
+  for (size_t q = 0; q < ch.score_slots.size(); ++q) {
+    if (ch.score_slots[q] == slot) {
+      *T = ch.plan.T + kx_off;
+      *mu = ch.plan.mu + (int64_t)q * ch.plan.Rpad;
+      return;
+    }
+    kx_off += ch.plan.Rpad * round_up(h->cl[ch.score_slots[q]].m, TB);
+  }
+}
+
 // Step phase 3: assign (mogp_constrained.py:277-284 minus the refit).
 int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_new_out) {
   Chain& ch = h->chain;
@@ -450,19 +475,12 @@ int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_n
     } else {
       Cluster& c = h->cl[ch.slot_of_id[chosen_id]];
       bool done = false;
-      if (ch.cfg.fast_updates && c.valid && ni > 0 && ni <= NP && ch.plan.T) {
-        int si = -1;
-        for (size_t q = 0; q < ch.score_slots.size(); ++q)
-          if (ch.score_slots[q] == ch.slot_of_id[chosen_id]) si = (int)q;
-        if (si >= 0) {
-          // T and the predictive means of this cluster are still in the scoring scratch
-          SlotView sv;
-          const int64_t mpad = round_up(c.m, TB);
-          int64_t kx_off = 0;
-          for (int q = 0; q < si; ++q) kx_off += ch.plan.Rpad * round_up(h->cl[ch.score_slots[q]].m, TB);
-          (void)sv;
-          (void)mpad;
-          TRY(append_core(h, c, (int)ni, h->d_px + c0, h->d_py + c0, ch.plan.T + kx_off, ch.plan.mu + (int64_t)si * ch.plan.Rpad));
+      if (ch.cfg.fast_updates && c.valid && ni > 0 && ni <= NP) {
+        // T = M Kx and the predictive means of this cluster are still in the scoring scratch
+        const double *Tc = nullptr, *muc = nullptr;
+        locate_T(h, ch.slot_of_id[chosen_id], &Tc, &muc);
+        if (Tc) {
+          TRY(append_core(h, c, (int)ni, h->d_px + c0, h->d_py + c0, Tc, muc));
           c.hx.insert(c.hx.end(), h->h_x.begin() + c0, h->h_x.begin() + c0 + ni);
           c.hy.insert(c.hy.end(), h->h_y.begin() + c0, h->h_y.begin() + c0 + ni);
           c.members.push_back(n);
@@ -480,6 +498,342 @@ int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_n
   ch.pending = -1;
   ch.plan = ScorePlan();
   if (is_new_out) *is_new_out = is_new ? 1 : 0;
+  return MOGP_OK;
+}
+
+
+// =================================================================================================
+// Look-ahead window (fast mode, mogp_chain_sweep).  One patient's columns use the factors at 2 n flops per 8 bytes:
+// the scoring pass is bound by HBM.  The sweep order and the draws are known in advance, so the next few
+// patients (<= `lookahead` query columns) are scored against EVERY active cluster in the same pass over the
+// factors.  The chain stays strictly sequential: a cached score is used only while its cluster is unchanged; when
+// a patient moves a -> b (or opens a cluster) the remaining patients of the window are re-scored against exactly
+// the clusters that changed.  Same arithmetic per (patient, cluster) as the patient-by-patient path.
+struct PhaseTimer {  // host wall time of a phase, accumulated into the chain's counters
+  double* acc;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseTimer(double* a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  ~PhaseTimer() { *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+int window_cols(const Chain& ch) {
+  static int env = -2;
+  if (env == -2) {
+    const char* e = getenv("MOGP_LOOKAHEAD");
+    env = e ? atoi(e) : -1;
+  }
+  int v = env >= 0 ? env : (ch.cfg.lookahead == 0 ? 32 : ch.cfg.lookahead);
+  return v <= 0 ? 0 : std::min(v, 64);
+}
+
+void win_invalidate(Chain& ch, int32_t slot) {
+  Chain::Window& w = ch.win;
+  if (!w.open || slot < 0) return;
+  if (slot < (int32_t)w.slot_ok.size()) w.slot_ok[slot] = 0;
+  for (size_t v = w.cur; v < w.pat.size(); ++v) {
+    const int32_t id = (w.pat[v] == ch.pending) ? ch.pending_prev : ch.z[w.pat[v]];
+    if (id >= 0 && id < (int32_t)ch.slot_of_id.size() && ch.slot_of_id[id] == slot) w.own_ok[v] = 0;
+  }
+}
+
+// Leave-block-out score of window patient v under its own cluster -> out3 (device).  *launched = false when the
+// patient has no own-cluster score to compute right now (singleton, or its cluster is not rank-updatable).
+int win_launch_own(mogp_engine* h, size_t v, int thr_index, double* out3, bool* launched) {
+  Chain& ch = h->chain;
+  *launched = false;
+  const int64_t n = ch.win.pat[v];
+  const bool is_pending = n == ch.pending;
+  const int32_t id = is_pending ? ch.pending_prev : ch.z[n];
+  if (id < 0 || ch.slot_of_id[id] < 0) return MOGP_OK;
+  if (ch.Nk[id] < (is_pending ? 1 : 2)) return MOGP_OK;  // alone in its cluster: the cluster goes when it is taken out
+  if (is_pending && !ch.pending_lazy) return MOGP_OK;
+  Cluster& c = h->cl[ch.slot_of_id[id]];
+  if (!c.valid) return MOGP_OK;
+  const int64_t c0 = h->h_off[n], ni = h->h_off[n + 1] - c0;
+  const int64_t p = member_offset(h, c, n, nullptr);
+  if (p < 0) return MOGP_OK;
+  TRY(rm_gram(h, c, p, (int)ni));
+  TRY(own_score(h, c, p, (int)ni, h->d_py + c0, thr_index, out3));
+  *launched = true;
+  return MOGP_OK;
+}
+
+void win_store(mogp_engine* h, size_t v0, const std::vector<int32_t>& slots, const ScorePlan& pl, const double* host_score,
+               const double* host_mu) {
+  Chain::Window& w = h->chain.win;
+  const int ns = (int)slots.size();
+  const int64_t cbase = w.col0[v0];
+  int64_t kx_off = 0;
+  for (int si = 0; si < ns; ++si) {
+    const int32_t slot = slots[si];
+    const int64_t mpad = round_up(h->cl[slot].m, TB);
+    for (size_t v = v0; v < w.pat.size(); ++v) {
+      if ((size_t)slot >= w.e[v].size()) w.e[v].resize(h->cl.size());
+      Chain::WinEntry& e = w.e[v][slot];
+      e.score = host_score[(v - v0) * ns + si];
+      e.muthr = host_mu[(v - v0) * ns + si];
+      e.T = pl.T + kx_off + (w.col0[v] - cbase) * mpad;
+      e.mu = pl.mu + (int64_t)si * pl.Rpad + (w.col0[v] - cbase);
+    }
+    if ((size_t)slot >= w.slot_ok.size()) w.slot_ok.resize(h->cl.size(), 0);
+    w.slot_ok[slot] = 1;
+    kx_off += pl.Rpad * mpad;
+  }
+}
+
+// Score patients order[0..cnt) against every active cluster in one pass; own-cluster scores and new-cluster
+// marginals on the side stream.
+int win_open(mogp_engine* h, int64_t cnt, const int64_t* order, const double* a_draw) {
+  Chain& ch = h->chain;
+  Chain::Window& w = ch.win;
+  w.open = false;
+  w.pat.assign(order, order + cnt);
+  w.col0.assign(cnt + 1, 0);
+  for (int64_t v = 0; v < cnt; ++v) w.col0[v + 1] = w.col0[v] + (h->h_off[order[v] + 1] - h->h_off[order[v]]);
+  const int64_t R = w.col0[cnt];
+  w.cur = 0;
+  w.e.assign(cnt, std::vector<Chain::WinEntry>(h->cl.size()));
+  w.slot_ok.assign(h->cl.size(), 0);
+  w.new_ll.assign(cnt, 0.0);
+  w.own_ll.assign(cnt, 0.0);
+  w.own_mu.assign(cnt, 0.0);
+  w.own_flag.assign(cnt, 0.0);
+  w.own_ok.assign(cnt, 0);
+  // packed query: off | x | y | a
+  TRY(ensure(h, &h->d_woff, &h->woff_elems, cnt + 1));
+  TRY(ensure(h, &h->d_wq, &h->wq_elems, 2 * R + cnt));
+  char* up = nullptr;
+  const size_t bytes = sizeof(int64_t) * (cnt + 1) + sizeof(double) * (2 * R + cnt);
+  TRY(stage_alloc(h, bytes, &up));
+  int64_t* so = reinterpret_cast<int64_t*>(up);
+  double* sd = reinterpret_cast<double*>(so + cnt + 1);
+  memcpy(so, w.col0.data(), sizeof(int64_t) * (cnt + 1));
+  for (int64_t v = 0; v < cnt; ++v) {
+    const int64_t c0 = h->h_off[order[v]], ni = w.col0[v + 1] - w.col0[v];
+    memcpy(sd + w.col0[v], h->h_x.data() + c0, sizeof(double) * ni);
+    memcpy(sd + R + w.col0[v], h->h_y.data() + c0, sizeof(double) * ni);
+    sd[2 * R + v] = a_draw ? a_draw[v] : 0.0;
+  }
+  CK(h, cudaMemcpyAsync(h->d_woff, so, sizeof(int64_t) * (cnt + 1), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_wq, sd, sizeof(double) * (2 * R + cnt), cudaMemcpyHostToDevice, h->stream));
+  h->bytes_h2d += (int64_t)bytes;
+  std::vector<int32_t> slots;
+  for (size_t k = 0; k < ch.Nk.size(); ++k)
+    if (ch.Nk[k] > 0 && ch.slot_of_id[k] >= 0) slots.push_back(ch.slot_of_id[k]);
+  const int ns = (int)slots.size();
+  const int thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
+  // device outputs: score[cnt x ns] | mu_thr[cnt x ns] | new_ll[cnt] | own[3 cnt]; a second region of the same shape
+  // (with room for the clusters this window may open) serves the re-scoring passes
+  const int64_t region = 2 * cnt * (int64_t)(ns + cnt + 4) + 4 * cnt + 8;
+  TRY(ensure(h, &h->d_out, &h->out_elems, 2 * region));
+  double* d_score = h->d_out;
+  double* d_mu = d_score + cnt * ns;
+  double* d_new = d_mu + cnt * ns;
+  double* d_own = d_new + cnt;
+  const int64_t total = 2 * cnt * (int64_t)ns + 4 * cnt;
+  w.open = true;  // (win_launch_own reads the window)
+  std::vector<char> own_launched(cnt, 0);
+  {
+    SideScope side(h);
+    for (int64_t v = 0; v < cnt; ++v) {
+      bool l = false;
+      TRY(win_launch_own(h, (size_t)v, thr_index, d_own + 3 * v, &l));
+      own_launched[v] = l ? 1 : 0;
+    }
+    k_new_ll<<<(unsigned)cnt, 64, 0, h->stream>>>(h->d_woff, h->d_wq, h->d_wq + R, h->d_wq + 2 * R, newcomer_theta(ch.cfg), d_new);
+    LAUNCHED(h);
+  }
+  ScorePlan pl;
+  if (ns > 0)
+    TRY(score_device(h, cnt, R, h->d_woff, h->d_wq, h->d_wq + R, ns, slots.data(), thr_index, d_score, d_mu, nullptr, nullptr,
+                     nullptr, true, &pl));
+  join_side(h);
+  CK(h, cudaGetLastError());
+  std::vector<double> host(total);
+  TRY(copy_back(h, host.data(), h->d_out, total));
+  // the stream is idle: the bump scratch of the previous window can be recycled
+  h->scr2_used = 0;
+  for (double* p : h->scr2_retired) cudaFree(p);
+  h->scr2_retired.clear();
+  win_store(h, 0, slots, pl, host.data(), host.data() + cnt * ns);
+  for (int64_t v = 0; v < cnt; ++v) {
+    w.new_ll[v] = host[2 * cnt * ns + v];
+    if (own_launched[v]) {
+      w.own_ll[v] = host[2 * cnt * ns + cnt + 3 * v];
+      w.own_mu[v] = host[2 * cnt * ns + cnt + 3 * v + 1];
+      w.own_flag[v] = host[2 * cnt * ns + cnt + 3 * v + 2];
+      w.own_ok[v] = 1;
+    }
+  }
+  ch.win_passes += 1;
+  ch.win_patients += cnt;
+  return MOGP_OK;
+}
+
+// Bring the cache up to date for the current patient (and, in the same launches, for the rest of the window):
+// re-score against the clusters that changed since they were scored, refresh stale own-cluster scores.
+int win_ensure(mogp_engine* h, int32_t own_id) {
+  Chain& ch = h->chain;
+  Chain::Window& w = ch.win;
+  const size_t cur = w.cur, cnt = w.pat.size();
+  if (w.slot_ok.size() < h->cl.size()) w.slot_ok.resize(h->cl.size(), 0);
+  std::vector<int32_t> bad;
+  for (size_t k = 0; k < ch.Nk.size(); ++k) {
+    if (ch.Nk[k] <= 0 || (int32_t)k == own_id) continue;
+    const int32_t slot = ch.slot_of_id[k];
+    if (!w.slot_ok[slot]) bad.push_back(slot);
+  }
+  const bool need_own = own_id >= 0 && !w.own_ok[cur];
+  if (bad.empty() && !need_own) return MOGP_OK;
+  const int nb = (int)bad.size();
+  const int64_t rem = (int64_t)(cnt - cur), Rrem = w.col0[cnt] - w.col0[cur];
+  const int thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
+  const int64_t region = h->out_elems / 2;
+  if (2 * rem * nb + 3 * rem > region) FAIL(h, MOGP_ESTATE, "look-ahead output region too small");
+  double* d_score = h->d_out + region;
+  double* d_mu = d_score + rem * nb;
+  double* d_own = d_mu + rem * nb;
+  std::vector<char> own_launched(rem, 0);
+  {
+    SideScope side(h);
+    for (size_t v = cur; v < cnt; ++v) {
+      if (w.own_ok[v]) continue;
+      bool l = false;
+      TRY(win_launch_own(h, v, thr_index, d_own + 3 * (v - cur), &l));
+      own_launched[v - cur] = l ? 1 : 0;
+    }
+  }
+  ScorePlan pl;
+  if (nb > 0) {
+    for (size_t v = cur; v < cnt; ++v)
+      if (w.e[v].size() < h->cl.size()) w.e[v].resize(h->cl.size());
+    TRY(score_device(h, rem, Rrem, h->d_woff + cur, h->d_wq + w.col0[cur], h->d_wq + w.col0[cnt] + w.col0[cur], nb, bad.data(),
+                     thr_index, d_score, d_mu, nullptr, nullptr, nullptr, true, &pl, true));
+    ch.win_rescores += 1;
+  }
+  join_side(h);
+  CK(h, cudaGetLastError());
+  const int64_t total = 2 * rem * nb + 3 * rem;
+  std::vector<double> host(total);
+  TRY(copy_back(h, host.data(), d_score, total));
+  if (nb > 0) win_store(h, cur, bad, pl, host.data(), host.data() + rem * nb);
+  for (size_t v = cur; v < cnt; ++v)
+    if (own_launched[v - cur]) {
+      const double* o = host.data() + 2 * rem * nb + 3 * (v - cur);
+      w.own_ll[v] = o[0];
+      w.own_mu[v] = o[1];
+      w.own_flag[v] = o[2];
+      w.own_ok[v] = 1;
+    }
+  if (need_own && !w.own_ok[cur]) FAIL(h, MOGP_ESTATE, "own-cluster score of patient %lld unavailable", (long long)w.pat[cur]);
+  return MOGP_OK;
+}
+
+// One Gibbs step of the current window patient from the cache (begin / score / draw / commit).
+int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out) {
+  Chain& ch = h->chain;
+  Chain::Window& w = ch.win;
+  const int64_t n = w.pat[w.cur];
+  const int32_t zn = ch.z[n];
+  const int32_t prev_slot = (zn >= 0 && zn < (int32_t)ch.slot_of_id.size()) ? ch.slot_of_id[zn] : -1;
+  TRY(chain_begin(h, n));
+  const int32_t prev = ch.pending_prev;
+  if (ch.slot_of_id[prev] < 0 || !ch.pending_lazy) win_invalidate(ch, prev_slot);  // freed, or rebuilt without the patient
+  const int64_t ni = h->h_off[n + 1] - h->h_off[n];
+  const int32_t n_ids = (int32_t)ch.Nk.size();
+  ch.act_ids.clear();
+  for (int32_t k = 0; k < n_ids; ++k)
+    if (ch.Nk[k] > 0) ch.act_ids.push_back(k);
+  ch.act_ids.push_back(n_ids);  // alpha > 0 in window mode: the new-cluster slot is always active
+  const int nact = (int)ch.act_ids.size();
+  ch.act_score.assign(nact, 0.0);
+  const int32_t own = ch.pending_lazy ? prev : -1;
+  {
+    PhaseTimer pt(&ch.t_ensure);
+    TRY(win_ensure(h, own));
+  }
+  const double ythr = (ch.cfg.use_threshold && !h->h_ythr.empty()) ? h->h_ythr[n] : NAN;
+  for (int i = 0; i < nact; ++i) {
+    const int32_t id = ch.act_ids[i];
+    double prior, ll, muthr = NAN;
+    if (i == nact - 1) {
+      prior = log(ch.cfg.alpha + 1e-16);  // allocmodel.py:25-26
+      ll = w.new_ll[w.cur];
+      if (!isfinite(ll)) FAIL(h, MOGP_ENOTPD, "new-cluster covariance not positive definite");
+    } else {
+      prior = log((double)ch.Nk[id] + 1e-16);
+      if (id == own) {
+        if (w.own_flag[w.cur] != 1.0) FAIL(h, MOGP_ENOTPD, "leave-out block not positive definite");
+        ll = w.own_ll[w.cur];
+        muthr = w.own_mu[w.cur];
+      } else {
+        const Chain::WinEntry& e = w.e[w.cur][ch.slot_of_id[id]];
+        ll = e.score;
+        muthr = e.muthr;
+      }
+      if (ch.cfg.use_threshold && (ythr - muthr > ch.cfg.threshold)) ll = -INFINITY;  // monotonicity rule (:254-263)
+    }
+    ch.act_score[i] = prior + ll;
+  }
+  (void)ni;
+  int idx = 0;
+  int rc = host_choice(ch.act_score.data(), nact, u, nullptr, &idx, &ch.last_margin);
+  if (rc != MOGP_OK) FAIL(h, rc, "probabilities contain NaN (patient %lld)", (long long)n);
+  const int32_t chosen = ch.act_ids[idx];
+  const bool stays = ch.pending_lazy && chosen == prev;
+  int32_t is_new = 0;
+  {
+    PhaseTimer pt(&ch.t_commit);
+    TRY(chain_commit(h, chosen, a_draw, &is_new));
+  }
+  if (!stays) {
+    if (ch.slot_of_id[prev] >= 0) win_invalidate(ch, ch.slot_of_id[prev]);
+    win_invalidate(ch, ch.slot_of_id[chosen]);
+  }
+  if (chosen_out) *chosen_out = chosen;
+  w.cur += 1;
+  return MOGP_OK;
+}
+
+// The whole sweep with look-ahead windows; patients the window cannot take go through the single-step path.
+int sweep_windowed(mogp_engine* h, int64_t n_steps, const int64_t* order, const double* a_draw, const double* u,
+                   int32_t* chosen_ids, double* mm, int max_cols) {
+  Chain& ch = h->chain;
+  int64_t s = 0;
+  while (s < n_steps) {
+    int64_t cnt = 0, cols = 0;
+    while (s + cnt < n_steps && cnt < 16) {
+      const int64_t n = order[s + cnt];
+      if (n < 0 || n >= ch.N) break;
+      const int64_t ni = h->h_off[n + 1] - h->h_off[n];
+      if (ni <= 0 || ni > NP || cols + ni > max_cols) break;
+      bool dup = false;
+      for (int64_t q = 0; q < cnt; ++q) dup = dup || order[s + q] == n;
+      if (dup) break;
+      cols += ni;
+      ++cnt;
+    }
+    if (cnt < 2) {
+      int32_t chosen = -1;
+      TRY(mogp_chain_step(h, order[s], a_draw ? a_draw[s] : 0.0, u[s], &chosen, nullptr, nullptr, nullptr, nullptr, 0));
+      if (chosen_ids) chosen_ids[s] = chosen;
+      *mm = std::min(*mm, ch.last_margin);
+      ++s;
+      continue;
+    }
+    {
+      PhaseTimer pt(&ch.t_open);
+      TRY(win_open(h, cnt, order + s, a_draw ? a_draw + s : nullptr));
+    }
+    for (int64_t q = 0; q < cnt; ++q) {
+      int32_t chosen = -1;
+      TRY(win_step(h, a_draw ? a_draw[s + q] : 0.0, u[s + q], &chosen));
+      if (chosen_ids) chosen_ids[s + q] = chosen;
+      *mm = std::min(*mm, ch.last_margin);
+    }
+    ch.win.open = false;
+    s += cnt;
+  }
   return MOGP_OK;
 }
 
@@ -589,6 +943,15 @@ int mogp_chain_sweep(mogp_engine* h, int64_t n_steps, const int64_t* order, cons
   if (!order || !u || n_steps < 0) FAIL(h, MOGP_EINVAL, "null argument");
   if (h->chain.active && h->chain.cfg.spec.mean_func && !a_draw) FAIL(h, MOGP_EINVAL, "mean_func needs a_draw");
   double mm = INFINITY;
+  h->chain.win.open = false;
+  const int max_cols = h->chain.active && h->chain.cfg.fast_updates && h->chain.cfg.alpha > 0.0 ? window_cols(h->chain) : 0;
+  if (max_cols >= 2) {
+    int rc = sweep_windowed(h, n_steps, order, a_draw, u, chosen_ids, &mm, max_cols);
+    h->chain.win.open = false;
+    if (rc != MOGP_OK) return rc;
+    if (min_margin) *min_margin = mm;
+    return MOGP_OK;
+  }
   for (int64_t s = 0; s < n_steps; ++s) {
     int32_t chosen = -1;
     TRY(mogp_chain_step(h, order[s], a_draw ? a_draw[s] : 0.0, u[s], &chosen, nullptr, nullptr, nullptr, nullptr, 0));

@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -85,6 +86,26 @@ struct Chain {
   double last_margin = 0.0;
   std::vector<int32_t> act_ids;
   std::vector<double> act_score;
+  // ---- look-ahead window of mogp_chain_sweep (fast mode): several consecutive patients are scored against every
+  // active cluster in ONE pass over the factors; a cached score stays valid until its cluster changes ----
+  struct WinEntry {
+    double score = 0.0, muthr = 0.0;
+    const double* T = nullptr;   // the patient's columns of T = M Kx under that slot (stride = mpad when scored)
+    const double* mu = nullptr;  // ... and their predictive means
+  };
+  struct Window {
+    bool open = false;
+    std::vector<int64_t> pat;    // patient ids, in sweep order
+    std::vector<int64_t> col0;   // first column of each patient in the packed query (+ total at the end)
+    size_t cur = 0;              // patient being processed
+    std::vector<std::vector<WinEntry>> e;  // [w][slot]
+    std::vector<char> slot_ok;   // [slot]: e[w][slot] is current for every w >= cur
+    std::vector<double> new_ll;  // [w]
+    std::vector<double> own_ll, own_mu, own_flag;  // [w] leave-block-out score under the patient's own cluster
+    std::vector<char> own_ok;
+  } win;
+  int64_t win_passes = 0, win_rescores = 0, win_patients = 0;  // accounting
+  double t_open = 0.0, t_ensure = 0.0, t_commit = 0.0;         // host seconds spent in the three phases of windowed steps
 };
 
 }  // namespace
@@ -120,6 +141,15 @@ struct mogp_engine {
   int64_t slots_cap = 0;
   double* d_scr = nullptr;
   int64_t scr_elems = 0;
+  // second scratch of the look-ahead window (chain.inl): bump-allocated, so that the T = M Kx blocks of several
+  // re-scoring passes stay alive until the window closes; blocks outgrown mid-window are retired, not freed
+  double* d_scr2 = nullptr;
+  int64_t scr2_elems = 0, scr2_used = 0;
+  std::vector<double*> scr2_retired;
+  double* d_wq = nullptr;  // packed query of the window: x | y | a_draw
+  int64_t wq_elems = 0;
+  int64_t* d_woff = nullptr;
+  int64_t woff_elems = 0;
   double* d_adraw = nullptr;  // the newcomer's randn draw of the current Gibbs step
   double* d_q = nullptr;  // query staging: x | y | a_draw
   int64_t q_elems = 0;
@@ -153,7 +183,7 @@ struct mogp_engine {
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop), recycled
   size_t prof_used = 0;
-  double prof_ms = 0.0, prof_bytes = 0.0, prof_flops = 0.0;
+  double prof_ms = 0.0, prof_bytes = 0.0, prof_flops = 0.0, prof_pairs = 0.0;
   int64_t prof_launches = 0;
 };
 
@@ -551,16 +581,33 @@ void prof_mark(mogp_engine* h, bool stop) {
 }
 
 template <int BN>
-void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotPack& pack, int use_pack) {
+void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotPack& pack, int use_pack,
+                       const ChunkPlan& cp) {
   const int smem = ScoreSmem<BN>::BYTES;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(k_score_gemm<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_done = true;
   }
-  dim3 grid((unsigned)(pl.Rpad / BN), (unsigned)pl.max_nb, (unsigned)pl.n_slots);
+  dim3 grid((unsigned)(pl.Rpad / BN), (unsigned)pl.n_slots, (unsigned)(pl.max_nb * cp.maxch));
   prof_mark(h, false);
-  k_score_gemm<BN><<<grid, NTHREADS, smem, h->stream>>>(h->d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout);
+  k_score_gemm<BN><<<grid, NTHREADS, smem, h->stream>>>(h->d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout, cp);
+  prof_mark(h, true);
+  LAUNCHED(h);
+}
+
+template <int NS>
+void launch_score_wide(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotPack& pack, int use_pack,
+                       const ChunkPlan& cp) {
+  const int smem = WideSmem<NS>::BYTES;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_score_wide<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_done = true;
+  }
+  dim3 grid((unsigned)(pl.Rpad / (8 * NS)), (unsigned)pl.n_slots, (unsigned)(pl.max_nb * cp.maxch));
+  prof_mark(h, false);
+  k_score_wide<NS><<<grid, WIDE_THREADS, smem, h->stream>>>(h->d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout, cp);
   prof_mark(h, true);
   LAUNCHED(h);
 }
@@ -569,11 +616,12 @@ void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout, const 
 // column).  Runs k_kx -> k_score_gemm -> k_score_epi; outputs stay on the device.
 int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_dev, const double* xs_dev,
                  const double* ys_dev, int32_t n_slots, const int32_t* slots, int32_t thr_index, double* score_dev,
-                 double* mu_thr_dev, double* col_mean, double* col_var, double* col_lpd, bool keep_T, ScorePlan* plan_out) {
+                 double* mu_thr_dev, double* col_mean, double* col_var, double* col_lpd, bool keep_T, ScorePlan* plan_out,
+                 bool bump = false) {
   if (n_slots <= 0 || n_pat <= 0 || R <= 0) return MOGP_OK;
   ScorePlan pl;
   pl.R = R;
-  pl.BN = R <= 8 ? 8 : (R <= 16 ? 16 : (R <= 32 ? 32 : 64));
+  pl.BN = R <= 64 ? (int)round_up(R, 8) : 64;  // one column tile of 8..64 columns; wider queries: tiles of 64
   pl.Rpad = round_up(R, pl.BN);
   pl.n_slots = n_slots;
   for (int s = 0; s < n_slots; ++s) {  // (inference synchronises: do it before staging anything)
@@ -605,22 +653,46 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
     pl.max_nb = std::max(pl.max_nb, v.mpad / TB);
     pl.max_rblk = std::max(pl.max_rblk, (v.mpad + KX_ROWS - 1) / KX_ROWS);
     hv[s] = v;
-    if (h->prof_on) {  // B_pair = 8 (m^2/2 + 3m) + 16 n + 8 per (patient, cluster); F = n m (m + 10)
+    if (h->prof_on) {  // B_pair = 8 (m^2/2 + 3m) + 16 n + 8 per (patient, cluster); F = n m (m + 10).
+      // One launch scores n_pat patients against the cluster: the factor term is charged ONCE per launch (what the
+      // launch must move), the per-pair terms per patient; prof_pairs counts the (patient, cluster) units.
       const double m = (double)c.m;
-      h->prof_bytes += (double)n_pat * (8.0 * (m * m / 2 + 3 * m) + 8.0) + 16.0 * (double)R;
+      h->prof_bytes += 8.0 * (m * m / 2 + 3 * m) + 8.0 * (double)n_pat + 16.0 * (double)R;
       h->prof_flops += (double)R * m * (m + 10.0);
+      h->prof_pairs += (double)n_pat;
     }
   }
   if (h->prof_on) h->prof_launches += 1;
   TRY(ensure(h, &h->d_slots, &h->slots_cap, n_slots));
   const int64_t mu_total = (int64_t)n_slots * pl.Rpad, mupart_total = mu_total * pl.max_rblk;
-  const int64_t need = pl.kx_total * (keep_T ? 2 : 1) + pl.part_total + mu_total + mupart_total;
-  TRY(ensure(h, &h->d_scr, &h->scr_elems, need));
-  pl.kxT = h->d_scr;
+  // few (slot, row block) items and one column tile: split the contraction across CTAs (see ChunkPlan)
+  ChunkPlan cp;
+  if (pl.Rpad == pl.BN && (int64_t)n_slots * pl.max_nb <= 2 * 148 && pl.max_nb > 8) {
+    cp.kc = 8;
+    cp.maxch = (pl.max_nb + cp.kc - 1) / cp.kc;
+  }
+  const int64_t tpart_total = cp.kc > 0 ? pl.kx_total * cp.maxch : 0;
+  const int64_t need = pl.kx_total * (keep_T ? 2 : 1) + pl.part_total + mu_total + mupart_total + tpart_total;
+  if (bump) {
+    if (h->scr2_used + need > h->scr2_elems) {  // outgrown: earlier blocks of this window are still referenced
+      if (h->d_scr2) h->scr2_retired.push_back(h->d_scr2);
+      h->d_scr2 = nullptr;
+      h->scr2_elems = h->scr2_used = 0;
+      const int64_t want = std::max<int64_t>(4 * need, (int64_t)1 << 21);
+      CK(h, cudaMalloc((void**)&h->d_scr2, sizeof(double) * (size_t)want));
+      h->scr2_elems = want;
+    }
+    pl.kxT = h->d_scr2 + h->scr2_used;
+    h->scr2_used += need;
+  } else {
+    TRY(ensure(h, &h->d_scr, &h->scr_elems, need));
+    pl.kxT = h->d_scr;
+  }
   pl.part = pl.kxT + pl.kx_total;
   pl.mu = pl.part + pl.part_total;
   pl.mupart = pl.mu + mu_total;
   pl.T = keep_T ? pl.mupart + mupart_total : nullptr;
+  cp.Tpart = cp.kc > 0 ? pl.mupart + mupart_total + (keep_T ? pl.kx_total : 0) : nullptr;
   if (!use_pack) {
     CK(h, cudaMemcpyAsync(h->d_slots, hv, sizeof(SlotView) * (size_t)n_slots, cudaMemcpyHostToDevice, h->stream));
     h->bytes_h2d += (int64_t)sizeof(SlotView) * n_slots;
@@ -628,11 +700,20 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   k_kx<<<dim3((unsigned)pl.max_rblk, (unsigned)((pl.Rpad + KX_COLS - 1) / KX_COLS), (unsigned)n_slots), KX_ROWS, 0,
          h->stream>>>(h->d_slots, pack, use_pack, xs_dev, (int)R, (int)pl.Rpad, pl.max_rblk, pl.kxT, pl.mupart);
   LAUNCHED(h);
-  switch (pl.BN) {
-    case 8: launch_score_gemm<8>(h, pl, pl.T, pack, use_pack); break;
-    case 16: launch_score_gemm<16>(h, pl, pl.T, pack, use_pack); break;
-    case 32: launch_score_gemm<32>(h, pl, pl.T, pack, use_pack); break;
-    default: launch_score_gemm<64>(h, pl, pl.T, pack, use_pack); break;
+  switch (pl.BN) {  // <= 16 columns: bound by HBM (8-warp ring); wider: bound by the FP64 tensor pipe (16 warps)
+    case 8: launch_score_gemm<8>(h, pl, pl.T, pack, use_pack, cp); break;
+    case 16: launch_score_gemm<16>(h, pl, pl.T, pack, use_pack, cp); break;
+    case 24: launch_score_wide<3>(h, pl, pl.T, pack, use_pack, cp); break;
+    case 32: launch_score_wide<4>(h, pl, pl.T, pack, use_pack, cp); break;
+    case 40: launch_score_wide<5>(h, pl, pl.T, pack, use_pack, cp); break;
+    case 48: launch_score_wide<6>(h, pl, pl.T, pack, use_pack, cp); break;
+    case 56: launch_score_wide<7>(h, pl, pl.T, pack, use_pack, cp); break;
+    default: launch_score_wide<8>(h, pl, pl.T, pack, use_pack, cp); break;
+  }
+  if (cp.kc > 0) {
+    k_score_reduce<<<dim3((unsigned)n_slots, (unsigned)pl.max_nb), 256, 0, h->stream>>>(h->d_slots, pack, use_pack, (int)pl.Rpad, cp,
+                                                                                      pl.part, pl.T);
+    LAUNCHED(h);
   }
   const int64_t pairs = n_pat * n_slots;
   k_score_epi<<<(unsigned)((pairs + 7) / 8), 256, 0, h->stream>>>(h->d_slots, pack, use_pack, n_slots, off_dev, n_pat, xs_dev, ys_dev,
@@ -739,6 +820,10 @@ void mogp_engine_destroy(mogp_engine* h) {
   cudaFree(h->d_apart);
   cudaFree(h->d_slots);
   cudaFree(h->d_scr);
+  cudaFree(h->d_scr2);
+  for (double* p : h->scr2_retired) cudaFree(p);
+  cudaFree(h->d_wq);
+  cudaFree(h->d_woff);
   cudaFree(h->d_q);
   cudaFree(h->d_qoff);
   cudaFree(h->d_out);
@@ -862,8 +947,16 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
   if (alg_flops) *alg_flops = h->prof_flops;
   if (reset) {
     h->prof_launches = 0;
-    h->prof_ms = h->prof_bytes = h->prof_flops = 0.0;
+    h->prof_ms = h->prof_bytes = h->prof_flops = h->prof_pairs = 0.0;
   }
+  return MOGP_OK;
+}
+
+int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out) {
+  if (!h || !out) return MOGP_EINVAL;
+  const double v[7] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
+                       h->chain.t_open, h->chain.t_ensure, h->chain.t_commit};
+  for (int i = 0; i < n_out && i < 7; ++i) out[i] = v[i];
   return MOGP_OK;
 }
 

@@ -73,8 +73,42 @@ __global__ void __launch_bounds__(KX_ROWS) k_kx(SLOT_ARGS, const double* __restr
   }
 }
 
+// Launches with few clusters (re-scoring the one or two clusters a move changed) have too few (slot, row block)
+// items for 148 SMs, and the heaviest item is a chain of ~40 dependent tile products.  They run with the
+// contraction split: a CTA takes at most kc tiles of its row block and stores its partial T in a scratch,
+// k_score_reduce adds the partials of a row block in a fixed order and emits T and the column sums of squares.
+struct ChunkPlan {
+  int kc = 0;        // tiles per CTA (0 = whole row block per CTA, epilogue in the same kernel)
+  int maxch = 1;     // chunks of the longest row block
+  double* Tpart = nullptr;  // [slot: kx_off * maxch][chunk][col][mpad]
+};
+
+__global__ void __launch_bounds__(256) k_score_reduce(SLOT_ARGS, int Rpad, const ChunkPlan cp, double* __restrict__ part,
+                                                      double* __restrict__ Tout) {
+  const SlotView sv = SLOT_AT(blockIdx.x);
+  const int nb = sv.mpad / TB;
+  const int rb = (int)blockIdx.y;
+  if (rb >= nb) return;
+  __shared__ double sq[64][TB + 1];  // [col][row]
+  const int nch = rb / cp.kc + 1;
+  const double* base = cp.Tpart + sv.kx_off * cp.maxch;
+  const int row = threadIdx.x & 63;
+  for (int c = threadIdx.x >> 6; c < Rpad; c += 4) {
+    double v = 0.0;
+    for (int q = 0; q < nch; ++q) v += base[((int64_t)q * Rpad + c) * sv.mpad + rb * TB + row];
+    if (Tout) Tout[sv.kx_off + (int64_t)c * sv.mpad + rb * TB + row] = v;
+    sq[c][row] = v * v;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < Rpad) {
+    double s = 0.0;
+    for (int r = 0; r < TB; ++r) s += sq[threadIdx.x][r];
+    part[sv.part_off + (int64_t)rb * Rpad + threadIdx.x] = s;
+  }
+}
+
 // T = M Kx for a 64-row block and a BN-column tile; emits column sums of squares per row block.
-// grid (n_col_tiles, max_nb, n_slots).  BN in {8,16,32,64}.
+// grid (n_col_tiles, n_slots, max_nb).  BN in {8,16,32,64}.
 template <int BN>
 struct ScoreShape;
 template <>
@@ -106,24 +140,30 @@ struct ScoreSmem {
 // better than a static snake deal, and the per-tile cursor logic costs more than the pipeline refills save.)
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1) k_score_gemm(SLOT_ARGS, const double* __restrict__ kxT, int Rpad,
-                                                            double* __restrict__ part, double* __restrict__ Tout) {
+                                                            double* __restrict__ part, double* __restrict__ Tout,
+                                                            const ChunkPlan cp) {
   using S = ScoreShape<BN>;
   constexpr int NS = ScoreStages<BN>::S;
   constexpr int STAGE = ScoreSmem<BN>::STAGE;
-  const SlotView sv = SLOT_AT(blockIdx.z);
+  const SlotView sv = SLOT_AT(blockIdx.y);
   const int nb = sv.mpad / TB;
-  // heavy row blocks first: block row rb needs rb+1 tile products
-  const int rb = nb - 1 - (int)blockIdx.y;
+  // heavy row blocks first, ACROSS the slots (the slot index varies fastest in launch order): block row rb needs
+  // rb+1 tile products, so the CTA scheduler sees the work items longest-first
+  const int zi = cp.kc > 0 ? (int)blockIdx.z / cp.maxch : (int)blockIdx.z;
+  const int chunk = cp.kc > 0 ? (int)blockIdx.z % cp.maxch : 0;
+  const int rb = nb - 1 - zi;
   if (rb < 0) return;
+  const int t_begin = chunk * cp.kc;
+  if (cp.kc > 0 && t_begin > rb) return;
   const int c0 = blockIdx.x * BN;
   extern __shared__ __align__(16) double smem[];
   __shared__ double red[S::WM][BN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int wm = warp / S::WN, wn = warp % S::WN;
   const int rbase = wm * 8 * S::MS, cbase = wn * 8 * S::NS;
-  const double* Mrow = sv.M + (int64_t)rb * TB * sv.ld;
-  const double* kx = kxT + sv.kx_off + (int64_t)c0 * sv.mpad;
-  const int ntiles = rb + 1;
+  const double* Mrow = sv.M + (int64_t)rb * TB * sv.ld + (int64_t)t_begin * TB;
+  const double* kx = kxT + sv.kx_off + (int64_t)c0 * sv.mpad + (int64_t)t_begin * TB;
+  const int ntiles = cp.kc > 0 ? min(cp.kc, rb + 1 - t_begin) : rb + 1;
   auto issue = [&](int tile) {
     if (tile < ntiles) {
       double* sA = smem + (tile % NS) * STAGE;
@@ -144,6 +184,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_score_gemm(SLOT_ARGS, const dou
     warp_mma<S::MS, S::NS, true, true>(acc, sA, sA + TB * LD_C, rbase, cbase);
   }
   cp_async_wait<0>();
+  if (cp.kc > 0) {  // split contraction: this CTA's partial product goes to the scratch, k_score_reduce finishes
+    double* o = cp.Tpart + sv.kx_off * cp.maxch + (int64_t)chunk * Rpad * sv.mpad;
+#pragma unroll
+    for (int i = 0; i < S::MS; ++i)
+#pragma unroll
+      for (int j = 0; j < S::NS; ++j) {
+        int r = rb * TB + rbase + 8 * i + g, c = c0 + cbase + 8 * j + 2 * t;
+        o[(int64_t)c * sv.mpad + r] = acc.v[i][j][0];
+        o[(int64_t)(c + 1) * sv.mpad + r] = acc.v[i][j][1];
+      }
+    return;
+  }
   if (Tout) {  // optional: keep T (= L^-1 Kx) for the rank-n append of the chosen cluster
     double* o = Tout + sv.kx_off;
 #pragma unroll
@@ -179,6 +231,142 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_score_gemm(SLOT_ARGS, const dou
     double s = 0.0;
 #pragma unroll
     for (int q = 0; q < S::WM; ++q) s += red[q][threadIdx.x];
+    part[sv.part_off + (int64_t)rb * Rpad + c0 + threadIdx.x] = s;
+  }
+}
+
+// The same product for wider column tiles (several patients per pass, batch prediction): there it is bound by the
+// FP64 tensor pipe, not by HBM.  16 warps = 4 row groups x 4 k groups: a warp owns 16 rows x BN columns of the
+// output and a quarter of every tile's contraction range (4 of the 16 DMMA k-steps), which keeps the fragment loads
+// at (2 + NS) / (2 NS) shared-memory loads per DMMA for ANY BN = 8 NS, and gives each scheduler four warps to cover
+// the fragment-load latency with (ncu, 8-warp version at BN = 32: tensor pipe 67 % busy, two warps per scheduler,
+// 34 % of the stall samples on fixed-latency dependencies).  The four k-group partials are added once per CTA, in a
+// fixed order, through the (then idle) stage buffers.
+constexpr int WIDE_THREADS = 512;
+template <int NS>
+struct WideSmem {
+  static constexpr int BN = 8 * NS;
+  static constexpr int STAGE = (TB + BN) * LD_C;  // doubles per stage
+  static constexpr int S = (4 * STAGE * 8 <= 227 * 1024) ? 4 : 3;
+  static constexpr int BYTES = S * STAGE * (int)sizeof(double);
+};
+
+template <int NS>
+__global__ void __launch_bounds__(WIDE_THREADS, 1) k_score_wide(SLOT_ARGS, const double* __restrict__ kxT, int Rpad,
+                                                               double* __restrict__ part, double* __restrict__ Tout,
+                                                               const ChunkPlan cp) {
+  constexpr int BN = 8 * NS, MS = 2, WM = 4;
+  constexpr int NST = WideSmem<NS>::S, STAGE = WideSmem<NS>::STAGE;
+  const SlotView sv = SLOT_AT(blockIdx.y);
+  const int nb = sv.mpad / TB;
+  const int zi = cp.kc > 0 ? (int)blockIdx.z / cp.maxch : (int)blockIdx.z;
+  const int chunk = cp.kc > 0 ? (int)blockIdx.z % cp.maxch : 0;
+  const int rb = nb - 1 - zi;  // heavy row blocks first, across the slots
+  if (rb < 0) return;
+  const int t_begin = chunk * cp.kc;
+  if (cp.kc > 0 && t_begin > rb) return;
+  const int c0 = blockIdx.x * BN;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double red[WM][BN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp & 3, kg = warp >> 2;  // row group, k group
+  const int rbase = wm * 16;
+  const double* Mrow = sv.M + (int64_t)rb * TB * sv.ld + (int64_t)t_begin * TB;
+  const double* kx = kxT + sv.kx_off + (int64_t)c0 * sv.mpad + (int64_t)t_begin * TB;
+  const int ntiles = cp.kc > 0 ? min(cp.kc, rb + 1 - t_begin) : rb + 1;
+  auto issue = [&](int tile) {
+    if (tile < ntiles) {
+      double* sA = smem + (tile % NST) * STAGE;
+      load_tile_async<LD_C, TB, WIDE_THREADS>(sA, Mrow + (int64_t)tile * TB, sv.ld);
+      load_tile_async<LD_C, BN, WIDE_THREADS>(sA + TB * LD_C, kx + (int64_t)tile * TB, sv.mpad);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int tile = 0; tile < NST - 1; ++tile) issue(tile);
+  Acc<MS, NS> acc;
+  acc.zero();
+  for (int tile = 0; tile < ntiles; ++tile) {
+    cp_async_wait<NST - 2>();
+    __syncthreads();
+    issue(tile + NST - 1);
+    const double* sA = smem + (tile % NST) * STAGE;
+    warp_mma<MS, NS, true, true, TB / 4>(acc, sA + kg * (TB / 4), sA + TB * LD_C + kg * (TB / 4), rbase, 0);
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // every warp is done with the stage buffers: reuse them for the k-group reduction
+  constexpr int LDP = BN + 2;  // partial tile [64][LDP] per k group 1..3
+  if (kg > 0) {
+    double* o = smem + (kg - 1) * (TB * LDP);
+#pragma unroll
+    for (int i = 0; i < MS; ++i)
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int r = rbase + 8 * i + g, c = 8 * j + 2 * t;
+        *reinterpret_cast<double2*>(o + r * LDP + c) = make_double2(acc.v[i][j][0], acc.v[i][j][1]);
+      }
+  }
+  __syncthreads();
+  if (kg == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const double* o = smem + q * (TB * LDP);
+#pragma unroll
+      for (int i = 0; i < MS; ++i)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          const int r = rbase + 8 * i + g, c = 8 * j + 2 * t;
+          const double2 v = *reinterpret_cast<const double2*>(o + r * LDP + c);
+          acc.v[i][j][0] += v.x;
+          acc.v[i][j][1] += v.y;
+        }
+    }
+    if (cp.kc > 0) {  // split contraction: partial product to the scratch (k_score_reduce finishes)
+      double* o = cp.Tpart + sv.kx_off * cp.maxch + (int64_t)chunk * Rpad * sv.mpad;
+#pragma unroll
+      for (int i = 0; i < MS; ++i)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          const int r = rb * TB + rbase + 8 * i + g, c = c0 + 8 * j + 2 * t;
+          o[(int64_t)c * sv.mpad + r] = acc.v[i][j][0];
+          o[(int64_t)(c + 1) * sv.mpad + r] = acc.v[i][j][1];
+        }
+    } else if (Tout) {
+      double* o = Tout + sv.kx_off;
+#pragma unroll
+      for (int i = 0; i < MS; ++i)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          const int r = rb * TB + rbase + 8 * i + g, c = c0 + 8 * j + 2 * t;
+          o[(int64_t)c * sv.mpad + r] = acc.v[i][j][0];
+          o[(int64_t)(c + 1) * sv.mpad + r] = acc.v[i][j][1];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < MS; ++i) {
+        s0 += acc.v[i][j][0] * acc.v[i][j][0];
+        s1 += acc.v[i][j][1] * acc.v[i][j][1];
+      }
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      }
+      if (g == 0) {
+        red[wm][8 * j + 2 * t] = s0;
+        red[wm][8 * j + 2 * t + 1] = s1;
+      }
+    }
+  }
+  if (cp.kc > 0) return;
+  __syncthreads();
+  if (threadIdx.x < BN) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < WM; ++q) s += red[q][threadIdx.x];
     part[sv.part_off + (int64_t)rb * Rpad + c0 + threadIdx.x] = s;
   }
 }

@@ -68,12 +68,12 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 // Asynchronous version of load_tile: ROWS x 64 tile into s[ROWS][LD].
-template <int LD, int ROWS = TB>
+template <int LD, int ROWS = TB, int NT = NTHREADS>
 __device__ __forceinline__ void load_tile_async(double* __restrict__ s, const double* __restrict__ g, int64_t ld) {
 #pragma unroll
-  for (int q = 0; q < (ROWS * TB / 2 + NTHREADS - 1) / NTHREADS; ++q) {
-    int idx = threadIdx.x + q * NTHREADS;
-    if ((ROWS * TB / 2) % NTHREADS == 0 || idx < ROWS * TB / 2) {
+  for (int q = 0; q < (ROWS * TB / 2 + NT - 1) / NT; ++q) {
+    int idx = threadIdx.x + q * NT;
+    if ((ROWS * TB / 2) % NT == 0 || idx < ROWS * TB / 2) {
       int r = idx >> 5, c = (idx & 31) << 1;
       cp_async16(s + r * LD + c, g + (int64_t)r * ld + c);
     }

@@ -31,7 +31,7 @@ class MoGP_constrained:
                  savename='MoGP_constrained', save_iter=25, kernel='rbf', signal_variance=1.,
                  signal_variance_fix=True, noise_variance=1., noise_variance_fix=False, mean_func=True,
                  threshold=None, onset_anchor=True, normalize=False, Y_mean=None, Y_std=None,
-                 refit='move', init_z=None, fast_updates=None, engine=None):
+                 refit='move', init_z=None, fast_updates=None, engine=None, lookahead=0):
         self.X, self.Y = X, Y
         self.allocmodel = DPmix(alpha)
         self.num_iter, self.num_init_clusters, self.rand_seed = num_iter, num_init_clusters, rand_seed
@@ -47,6 +47,8 @@ class MoGP_constrained:
         self.refit, self.init_z = refit, init_z
         self.fast_updates = (refit == 'sweep') if fast_updates is None else bool(fast_updates)
         self._engine = engine
+        # refit='sweep' only: visits scored ahead per pass over the factors (0 = engine default, < 0 = off)
+        self.lookahead = int(lookahead)
 
         self._check_validity_of_instance()
         self._initialize_normalizer()
@@ -172,6 +174,7 @@ class MoGP_constrained:
         cfg.threshold = float(self.threshold) if self.threshold is not None else 0.0
         cfg.thr_index = 1 if self.onset_anchor else 0              # mogp_constrained.py:256
         cfg.fast_updates = int(self.fast_updates)
+        cfg.lookahead = int(getattr(self, 'lookahead', 0))
         return cfg
 
     def _view(self, slot):
