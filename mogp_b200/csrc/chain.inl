@@ -123,8 +123,11 @@ RmGeom make_geom(const Cluster& c, int64_t p, int n) {
 int rm_work(mogp_engine* h, const RmGeom& g, RmWork* w) {
   const int64_t nT = g.nbn - g.I0, rows = nT * TB;
   const int64_t ph = nT * g.nbn * (int64_t)(NP * TB);  // P and H tiles of the deletion
-  TRY(ensure(h, &h->d_upd, &h->upd_elems, rows * NP * 2 + rows + nT * NG + NG + 8 + 2 * ph));
-  w->Bt = h->d_upd;
+  // (the look-ahead streams compute own-cluster scores while the side stream may be deleting rows: own workspace)
+  const bool la = h->stream == h->ahead || h->stream == h->ahead2;
+  double** buf = la ? &h->d_upd2 : &h->d_upd;
+  TRY(ensure(h, buf, la ? &h->upd2_elems : &h->upd_elems, rows * NP * 2 + rows + nT * NG + NG + 8 + 2 * ph));
+  w->Bt = *buf;
   w->Gt = w->Bt + rows * NP;
   w->u = w->Gt + rows * NP;
   w->Pgram = w->u + rows;
@@ -395,7 +398,7 @@ int chain_score(mogp_engine* h, double a_draw) {
 void locate_T(mogp_engine* h, int32_t slot, const double** T, const double** mu) {
   Chain& ch = h->chain;
   *T = *mu = nullptr;
-  if (ch.win.open) {
+  if (ch.win.in_step) {
     const Chain::Window& w = ch.win;
     if (slot >= 0 && slot < (int32_t)w.slot_ok.size() && w.slot_ok[slot] && slot < (int32_t)w.e[w.cur].size()) {
       *T = w.e[w.cur][slot].T;
@@ -503,12 +506,17 @@ int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_n
 
 
 // =================================================================================================
-// Look-ahead window (fast mode, mogp_chain_sweep).  One patient's columns use the factors at 2 n flops per 8 bytes:
-// the scoring pass is bound by HBM.  The sweep order and the draws are known in advance, so the next few
-// patients (<= `lookahead` query columns) are scored against EVERY active cluster in the same pass over the
-// factors.  The chain stays strictly sequential: a cached score is used only while its cluster is unchanged; when
-// a patient moves a -> b (or opens a cluster) the remaining patients of the window are re-scored against exactly
-// the clusters that changed.  Same arithmetic per (patient, cluster) as the patient-by-patient path.
+// Look-ahead pipeline (fast mode, mogp_chain_sweep).  One patient's columns use the factors at 2 n flops per 8 bytes:
+// patient by patient the scoring pass is bound by HBM and every step pays a device round trip.  The sweep order and
+// the draws are known in advance, so
+//   * consecutive patients totalling <= `lookahead` query columns form a BATCH that is scored against EVERY active
+//     cluster in one pass over the factors (FP64-tensor bound instead of HBM bound);
+//   * while the host draws and moves the patients of batch i, the pass of batch i+1 already runs on a low-priority
+//     stream and fills the SMs the short dependent kernels of the moves leave idle.
+// The chain stays strictly sequential: a cached score is used only if its cluster has not changed since it was
+// computed (per-slot change counters); when a patient moves a -> b (or opens / empties a cluster) every launched
+// position still ahead is re-scored against exactly the clusters that changed, before the next draw.  Same
+// arithmetic per (patient, cluster) as the patient-by-patient path.
 struct PhaseTimer {  // host wall time of a phase, accumulated into the chain's counters
   double* acc;
   std::chrono::steady_clock::time_point t0;
@@ -516,49 +524,292 @@ struct PhaseTimer {  // host wall time of a phase, accumulated into the chain's 
   ~PhaseTimer() { *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 int window_cols(const Chain& ch) {
-  static int env = -2;
-  if (env == -2) {
-    const char* e = getenv("MOGP_LOOKAHEAD");
-    env = e ? atoi(e) : -1;
-  }
+  const int env = env_int("MOGP_LOOKAHEAD", -1);  // (read per sweep: tests and tuning runs toggle it)
   int v = env >= 0 ? env : (ch.cfg.lookahead == 0 ? 32 : ch.cfg.lookahead);
   return v <= 0 ? 0 : std::min(v, 64);
 }
+int pipeline_depth() {  // 2: the next batch's pass overlaps the current batch's moves; 1: one batch at a time
+  const int env = env_int("MOGP_PIPELINE", 2);
+  return env >= 2 ? 2 : 1;
+}
 
+// The cluster in `slot` changed (rows appended / deleted, freed, created): cached scores under it are stale.
 void win_invalidate(Chain& ch, int32_t slot) {
   Chain::Window& w = ch.win;
   if (!w.open || slot < 0) return;
-  if (slot < (int32_t)w.slot_ok.size()) w.slot_ok[slot] = 0;
-  for (size_t v = w.cur; v < w.pat.size(); ++v) {
+  if ((size_t)slot >= w.slot_ok.size()) {
+    w.slot_ok.resize(slot + 1, 0);
+    w.slot_epoch.resize(slot + 1, 0);
+  }
+  w.slot_ok[slot] = 0;
+  w.slot_epoch[slot] += 1;
+  for (int64_t v = w.cur; v < w.end_launched; ++v) {
     const int32_t id = (w.pat[v] == ch.pending) ? ch.pending_prev : ch.z[w.pat[v]];
     if (id >= 0 && id < (int32_t)ch.slot_of_id.size() && ch.slot_of_id[id] == slot) w.own_ok[v] = 0;
   }
 }
+void win_invalidate_all(Chain& ch) {
+  Chain::Window& w = ch.win;
+  for (size_t s = 0; s < w.slot_ok.size(); ++s) {
+    w.slot_ok[s] = 0;
+    w.slot_epoch[s] += 1;
+  }
+  for (int64_t v = w.cur; v < w.end_launched; ++v) w.own_ok[v] = 0;
+}
 
-// Leave-block-out score of window patient v under its own cluster -> out3 (device).  *launched = false when the
-// patient has no own-cluster score to compute right now (singleton, or its cluster is not rank-updatable).
-int win_launch_own(mogp_engine* h, size_t v, int thr_index, double* out3, bool* launched) {
+// Leave-block-out scores of positions [v0, v1) that need one (own_ok clear when `only_stale`), in ONE launch pair on the
+// current stream; out3 + 3 (v - v0) receives (score, mean at the threshold visit, ok flag); slot_out[v - v0] = the
+// cluster slot scored or -1.
+int win_launch_own_batch(mogp_engine* h, int64_t v0, int64_t v1, bool only_stale, int thr_index, double* out3, int32_t* slot_out) {
   Chain& ch = h->chain;
-  *launched = false;
-  const int64_t n = ch.win.pat[v];
-  const bool is_pending = n == ch.pending;
-  const int32_t id = is_pending ? ch.pending_prev : ch.z[n];
-  if (id < 0 || ch.slot_of_id[id] < 0) return MOGP_OK;
-  if (ch.Nk[id] < (is_pending ? 1 : 2)) return MOGP_OK;  // alone in its cluster: the cluster goes when it is taken out
-  if (is_pending && !ch.pending_lazy) return MOGP_OK;
-  Cluster& c = h->cl[ch.slot_of_id[id]];
-  if (!c.valid) return MOGP_OK;
-  const int64_t c0 = h->h_off[n], ni = h->h_off[n + 1] - c0;
-  const int64_t p = member_offset(h, c, n, nullptr);
-  if (p < 0) return MOGP_OK;
-  TRY(rm_gram(h, c, p, (int)ni));
-  TRY(own_score(h, c, p, (int)ni, h->d_py + c0, thr_index, out3));
-  *launched = true;
+  Chain::Window& w = ch.win;
+  const bool la = h->stream == h->ahead || h->stream == h->ahead2;
+  double** buf = la ? &h->d_own2 : &h->d_own1;
+  int64_t* have = la ? &h->own2_elems : &h->own1_elems;
+  for (int64_t base = v0; base < v1; base += OWN_BATCH) {
+    OwnJobs jobs;
+    int nj = 0, max_nT = 0;
+    int64_t need = 0;
+    const int64_t top = std::min<int64_t>(v1, base + OWN_BATCH);
+    for (int64_t v = base; v < top; ++v) {
+      slot_out[v - v0] = -1;
+      if (only_stale && w.own_ok[v]) continue;
+      const int64_t n = w.pat[v];
+      const bool is_pending = n == ch.pending;
+      const int32_t id = is_pending ? ch.pending_prev : ch.z[n];
+      if (id < 0 || ch.slot_of_id[id] < 0) continue;
+      if (ch.Nk[id] < (is_pending ? 1 : 2)) continue;  // alone in its cluster: the cluster goes when it is taken out
+      if (is_pending && !ch.pending_lazy) continue;
+      Cluster& c = h->cl[ch.slot_of_id[id]];
+      if (!c.valid) continue;
+      const int64_t c0 = h->h_off[n], ni = h->h_off[n + 1] - c0;
+      const int64_t p = member_offset(h, c, n, nullptr);
+      if (p < 0) continue;
+      OwnJob& jb = jobs.j[nj++];
+      jb.M = c.M;
+      jb.alpha = c.alpha();
+      jb.yB = h->d_py + c0;
+      jb.out = out3 + 3 * (v - v0);
+      jb.g = make_geom(c, p, (int)ni);
+      jb.th = make_theta(c);
+      jb.nT = jb.g.nbn - jb.g.I0;
+      jb.w = RmWork{nullptr, nullptr, nullptr, reinterpret_cast<double*>((intptr_t)need), nullptr, nullptr};  // offsets first
+      need += (int64_t)jb.nT * NG + NG;
+      max_nT = std::max(max_nT, jb.nT);
+      slot_out[v - v0] = ch.slot_of_id[id];
+    }
+    if (nj == 0) continue;
+    TRY(ensure(h, buf, have, need));
+    for (int q = 0; q < nj; ++q) {
+      const int64_t off = (int64_t)(intptr_t)jobs.j[q].w.Pgram;
+      jobs.j[q].w.Pgram = *buf + off;
+      jobs.j[q].w.Gc = jobs.j[q].w.Pgram + (int64_t)jobs.j[q].nT * NG;
+    }
+    k_own_gram_batch<<<dim3((unsigned)max_nT, (unsigned)nj), 256, 0, h->stream>>>(jobs);
+    LAUNCHED(h);
+    k_own_final_batch<<<(unsigned)nj, 256, 0, h->stream>>>(jobs, thr_index);
+    LAUNCHED(h);
+  }
   return MOGP_OK;
 }
 
-void win_store(mogp_engine* h, size_t v0, const std::vector<int32_t>& slots, const ScorePlan& pl, const double* host_score,
+// Pack the whole sweep's query (patients in sweep order) on the device: x | y | a_draw, offsets per position.
+int win_prepare(mogp_engine* h, int64_t n_steps, const int64_t* order, const double* a_draw) {
+  Chain& ch = h->chain;
+  Chain::Window& w = ch.win;
+  w.open = false;
+  w.in_step = false;
+  w.n = n_steps;
+  w.pat.assign(order, order + n_steps);
+  w.col0.assign(n_steps + 1, 0);
+  for (int64_t v = 0; v < n_steps; ++v) {
+    const int64_t n = order[v];
+    const int64_t ni = (n >= 0 && n < ch.N) ? h->h_off[n + 1] - h->h_off[n] : 0;
+    w.col0[v + 1] = w.col0[v] + ni;
+  }
+  const int64_t R = w.col0[n_steps];
+  w.cur = w.end_launched = 0;
+  w.e.assign(n_steps, std::vector<Chain::WinEntry>());
+  w.slot_ok.assign(h->cl.size(), 0);
+  w.slot_epoch.assign(h->cl.size(), 0);
+  w.new_ll.assign(n_steps, 0.0);
+  w.own_ll.assign(n_steps, 0.0);
+  w.own_mu.assign(n_steps, 0.0);
+  w.own_flag.assign(n_steps, 0.0);
+  w.own_ok.assign(n_steps, 0);
+  TRY(ensure(h, &h->d_woff, &h->woff_elems, n_steps + 1));
+  TRY(ensure(h, &h->d_wq, &h->wq_elems, 2 * R + n_steps + 1));
+  char* up = nullptr;
+  const size_t bytes = sizeof(int64_t) * (n_steps + 1) + sizeof(double) * (2 * R + n_steps);
+  TRY(stage_alloc(h, bytes, &up));
+  int64_t* so = reinterpret_cast<int64_t*>(up);
+  double* sd = reinterpret_cast<double*>(so + n_steps + 1);
+  memcpy(so, w.col0.data(), sizeof(int64_t) * (n_steps + 1));
+  for (int64_t v = 0; v < n_steps; ++v) {
+    const int64_t ni = w.col0[v + 1] - w.col0[v];
+    if (ni > 0) {
+      const int64_t c0 = h->h_off[order[v]];
+      memcpy(sd + w.col0[v], h->h_x.data() + c0, sizeof(double) * ni);
+      memcpy(sd + R + w.col0[v], h->h_y.data() + c0, sizeof(double) * ni);
+    }
+    sd[2 * R + v] = a_draw ? a_draw[v] : 0.0;
+  }
+  CK(h, cudaMemcpyAsync(h->d_woff, so, sizeof(int64_t) * (n_steps + 1), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_wq, sd, sizeof(double) * (2 * R + n_steps), cudaMemcpyHostToDevice, h->stream));
+  h->bytes_h2d += (int64_t)bytes;
+  w.open = true;
+  return MOGP_OK;
+}
+
+// How many consecutive positions from `pos` form a batch (0: the patient there cannot be served from a batch).
+int64_t batch_form(mogp_engine* h, int64_t pos, int max_cols) {
+  const Chain::Window& w = h->chain.win;
+  int64_t cnt = 0, cols = 0;
+  while (pos + cnt < w.n && cnt < 16) {
+    const int64_t n = w.pat[pos + cnt];
+    if (n < 0 || n >= h->chain.N) break;
+    const int64_t ni = w.col0[pos + cnt + 1] - w.col0[pos + cnt];
+    if (ni <= 0 || ni > NP || (cnt > 0 && cols + ni > max_cols)) break;
+    cols += ni;
+    ++cnt;
+  }
+  return cnt;
+}
+
+template <typename T>
+int ensure_pinned(mogp_engine* h, T** p, int64_t* have, int64_t need) {
+  if (need <= *have) return MOGP_OK;
+  if (*p) CK(h, cudaFreeHost(*p));
+  *p = nullptr;
+  *have = 0;
+  const int64_t want = need + need / 2 + 64;
+  CK(h, cudaMallocHost((void**)p, sizeof(T) * (size_t)want));
+  *have = want;
+  return MOGP_OK;
+}
+
+// Launch the pass of batch `bi` = positions [s0, s0 + cnt) on the look-ahead streams: every active cluster x the
+// batch's columns, the patients' own-cluster scores and new-cluster marginals; results travel to pinned memory.
+// Ordered after everything enqueued so far on the main stream; no host wait.
+int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
+  Chain& ch = h->chain;
+  Chain::Window& w = ch.win;
+  Chain::Batch& b = w.b[bi];
+  BatchBuf& bf = h->bb[bi];
+  b.s0 = s0;
+  b.cnt = cnt;
+  b.slots.clear();
+  b.epoch.clear();
+  b.mpad.clear();
+  if (w.slot_ok.size() < h->cl.size()) {
+    w.slot_ok.resize(h->cl.size(), 0);
+    w.slot_epoch.resize(h->cl.size(), 0);
+  }
+  for (size_t k = 0; k < ch.Nk.size(); ++k)
+    if (ch.Nk[k] > 0 && ch.slot_of_id[k] >= 0) {
+      const int32_t slot = ch.slot_of_id[k];
+      if (!h->cl[slot].valid) {  // (synchronises: before anything is queued on the look-ahead streams)
+        TRY(infer(h, h->cl[slot]));
+        w.slot_epoch[slot] += 1;
+      }
+      b.slots.push_back(slot);
+      b.epoch.push_back(w.slot_epoch[slot]);
+      b.mpad.push_back(round_up(h->cl[slot].m, TB));
+    }
+  const int ns = (int)b.slots.size();
+  const int thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
+  const int64_t total = 2 * cnt * (int64_t)ns + 4 * cnt;
+  TRY(ensure(h, &bf.d_out, &bf.out_elems, total));
+  TRY(ensure_pinned(h, &bf.h_out, &bf.hout_elems, total));
+  double* d_score = bf.d_out;
+  double* d_mu = d_score + cnt * ns;
+  double* d_new = d_mu + cnt * ns;
+  double* d_own = d_new + cnt;
+  for (int64_t v = s0; v < s0 + cnt; ++v) w.e[v].assign(h->cl.size(), Chain::WinEntry());
+  const int64_t Rtot = w.col0[w.n], cb = w.col0[s0], R = w.col0[s0 + cnt] - cb;
+  CK(h, cudaEventRecord(h->ev_fork, h->main_stream));
+  CK(h, cudaStreamWaitEvent(h->ahead, h->ev_fork, 0));
+  CK(h, cudaStreamWaitEvent(h->ahead2, h->ev_fork, 0));
+  b.own_slot.assign(cnt, -1);
+  b.own_epoch.assign(cnt, 0);
+  struct StreamGuard {
+    mogp_engine* h;
+    ~StreamGuard() { h->stream = h->main_stream; }
+  } guard{h};
+  h->stream = h->ahead2;
+  TRY(win_launch_own_batch(h, s0, s0 + cnt, false, thr_index, d_own, b.own_slot.data()));
+  for (int64_t v = 0; v < cnt; ++v)
+    if (b.own_slot[v] >= 0) b.own_epoch[v] = w.slot_epoch[b.own_slot[v]];
+  k_new_ll<<<(unsigned)cnt, 64, 0, h->stream>>>(h->d_woff + s0, h->d_wq + cb, h->d_wq + Rtot + cb, h->d_wq + 2 * Rtot + s0,
+                                                newcomer_theta(ch.cfg), d_new);
+  LAUNCHED(h);
+  CK(h, cudaEventRecord(h->ev_ahead2, h->ahead2));
+  h->stream = h->ahead;
+  b.pl = ScorePlan();
+  if (ns > 0)
+    TRY(score_device(h, cnt, R, h->d_woff + s0, h->d_wq + cb, h->d_wq + Rtot + cb, ns, b.slots.data(), thr_index, d_score, d_mu,
+                     nullptr, nullptr, nullptr, true, &b.pl, &bf.res));
+  CK(h, cudaStreamWaitEvent(h->ahead, h->ev_ahead2, 0));
+  CK(h, cudaMemcpyAsync(bf.h_out, bf.d_out, sizeof(double) * total, cudaMemcpyDeviceToHost, h->ahead));
+  CK(h, cudaEventRecord(bf.done, h->ahead));
+  CK(h, cudaGetLastError());
+  h->bytes_d2h += (int64_t)sizeof(double) * total;
+  w.end_launched = s0 + cnt;
+  ch.win_passes += 1;
+  ch.win_patients += cnt;
+  return MOGP_OK;
+}
+
+// Wait for the pass of batch `bi` and take over what is still current: scores under clusters that have not changed
+// since the pass was launched (the others have been, or will be, re-scored), own-cluster scores likewise.
+int batch_absorb(mogp_engine* h, int bi) {
+  Chain& ch = h->chain;
+  Chain::Window& w = ch.win;
+  Chain::Batch& b = w.b[bi];
+  BatchBuf& bf = h->bb[bi];
+  CK(h, cudaEventSynchronize(bf.done));
+  const int ns = (int)b.slots.size();
+  const int64_t cnt = b.cnt, cb = w.col0[b.s0];
+  const double* hs = bf.h_out;
+  const double* hm = hs + cnt * ns;
+  const double* hn = hm + cnt * ns;
+  const double* ho = hn + cnt;
+  int64_t kx_off = 0;
+  for (int si = 0; si < ns; ++si) {
+    const int32_t slot = b.slots[si];
+    const int64_t mpad = b.mpad[si];
+    if (w.slot_epoch[slot] == b.epoch[si]) {
+      for (int64_t v = 0; v < cnt; ++v) {
+        Chain::WinEntry& e = w.e[b.s0 + v][slot];
+        e.score = hs[v * ns + si];
+        e.muthr = hm[v * ns + si];
+        e.T = b.pl.T + kx_off + (w.col0[b.s0 + v] - cb) * mpad;
+        e.mu = b.pl.mu + (int64_t)si * b.pl.Rpad + (w.col0[b.s0 + v] - cb);
+      }
+      w.slot_ok[slot] = 1;
+    }
+    kx_off += b.pl.Rpad * mpad;
+  }
+  for (int64_t v = 0; v < cnt; ++v) {
+    w.new_ll[b.s0 + v] = hn[v];
+    if (b.own_slot[v] >= 0 && w.slot_epoch[b.own_slot[v]] == b.own_epoch[v]) {
+      w.own_ll[b.s0 + v] = ho[3 * v];
+      w.own_mu[b.s0 + v] = ho[3 * v + 1];
+      w.own_flag[b.s0 + v] = ho[3 * v + 2];
+      w.own_ok[b.s0 + v] = 1;
+    }
+  }
+  return MOGP_OK;
+}
+
+// Cache entries of positions [v0, end_launched) under `slots`, from a re-scoring pass.
+void win_store(mogp_engine* h, int64_t v0, const std::vector<int32_t>& slots, const ScorePlan& pl, const double* host_score,
                const double* host_mu) {
   Chain::Window& w = h->chain.win;
   const int ns = (int)slots.size();
@@ -567,7 +818,7 @@ void win_store(mogp_engine* h, size_t v0, const std::vector<int32_t>& slots, con
   for (int si = 0; si < ns; ++si) {
     const int32_t slot = slots[si];
     const int64_t mpad = round_up(h->cl[slot].m, TB);
-    for (size_t v = v0; v < w.pat.size(); ++v) {
+    for (int64_t v = v0; v < w.end_launched; ++v) {
       if ((size_t)slot >= w.e[v].size()) w.e[v].resize(h->cl.size());
       Chain::WinEntry& e = w.e[v][slot];
       e.score = host_score[(v - v0) * ns + si];
@@ -575,108 +826,21 @@ void win_store(mogp_engine* h, size_t v0, const std::vector<int32_t>& slots, con
       e.T = pl.T + kx_off + (w.col0[v] - cbase) * mpad;
       e.mu = pl.mu + (int64_t)si * pl.Rpad + (w.col0[v] - cbase);
     }
-    if ((size_t)slot >= w.slot_ok.size()) w.slot_ok.resize(h->cl.size(), 0);
     w.slot_ok[slot] = 1;
     kx_off += pl.Rpad * mpad;
   }
 }
 
-// Score patients order[0..cnt) against every active cluster in one pass; own-cluster scores and new-cluster
-// marginals on the side stream.
-int win_open(mogp_engine* h, int64_t cnt, const int64_t* order, const double* a_draw) {
+// Bring the cache up to date for the current patient and, in the same launches, for every launched position
+// ahead: re-score against the clusters that changed since they were scored, refresh stale own-cluster scores.
+int win_ensure(mogp_engine* h, int32_t own_id, ScoreRes* arena) {
   Chain& ch = h->chain;
   Chain::Window& w = ch.win;
-  w.open = false;
-  w.pat.assign(order, order + cnt);
-  w.col0.assign(cnt + 1, 0);
-  for (int64_t v = 0; v < cnt; ++v) w.col0[v + 1] = w.col0[v] + (h->h_off[order[v] + 1] - h->h_off[order[v]]);
-  const int64_t R = w.col0[cnt];
-  w.cur = 0;
-  w.e.assign(cnt, std::vector<Chain::WinEntry>(h->cl.size()));
-  w.slot_ok.assign(h->cl.size(), 0);
-  w.new_ll.assign(cnt, 0.0);
-  w.own_ll.assign(cnt, 0.0);
-  w.own_mu.assign(cnt, 0.0);
-  w.own_flag.assign(cnt, 0.0);
-  w.own_ok.assign(cnt, 0);
-  // packed query: off | x | y | a
-  TRY(ensure(h, &h->d_woff, &h->woff_elems, cnt + 1));
-  TRY(ensure(h, &h->d_wq, &h->wq_elems, 2 * R + cnt));
-  char* up = nullptr;
-  const size_t bytes = sizeof(int64_t) * (cnt + 1) + sizeof(double) * (2 * R + cnt);
-  TRY(stage_alloc(h, bytes, &up));
-  int64_t* so = reinterpret_cast<int64_t*>(up);
-  double* sd = reinterpret_cast<double*>(so + cnt + 1);
-  memcpy(so, w.col0.data(), sizeof(int64_t) * (cnt + 1));
-  for (int64_t v = 0; v < cnt; ++v) {
-    const int64_t c0 = h->h_off[order[v]], ni = w.col0[v + 1] - w.col0[v];
-    memcpy(sd + w.col0[v], h->h_x.data() + c0, sizeof(double) * ni);
-    memcpy(sd + R + w.col0[v], h->h_y.data() + c0, sizeof(double) * ni);
-    sd[2 * R + v] = a_draw ? a_draw[v] : 0.0;
+  const int64_t cur = w.cur, end = w.end_launched;
+  if (w.slot_ok.size() < h->cl.size()) {
+    w.slot_ok.resize(h->cl.size(), 0);
+    w.slot_epoch.resize(h->cl.size(), 0);
   }
-  CK(h, cudaMemcpyAsync(h->d_woff, so, sizeof(int64_t) * (cnt + 1), cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->d_wq, sd, sizeof(double) * (2 * R + cnt), cudaMemcpyHostToDevice, h->stream));
-  h->bytes_h2d += (int64_t)bytes;
-  std::vector<int32_t> slots;
-  for (size_t k = 0; k < ch.Nk.size(); ++k)
-    if (ch.Nk[k] > 0 && ch.slot_of_id[k] >= 0) slots.push_back(ch.slot_of_id[k]);
-  const int ns = (int)slots.size();
-  const int thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
-  // device outputs: score[cnt x ns] | mu_thr[cnt x ns] | new_ll[cnt] | own[3 cnt]; a second region of the same shape
-  // (with room for the clusters this window may open) serves the re-scoring passes
-  const int64_t region = 2 * cnt * (int64_t)(ns + cnt + 4) + 4 * cnt + 8;
-  TRY(ensure(h, &h->d_out, &h->out_elems, 2 * region));
-  double* d_score = h->d_out;
-  double* d_mu = d_score + cnt * ns;
-  double* d_new = d_mu + cnt * ns;
-  double* d_own = d_new + cnt;
-  const int64_t total = 2 * cnt * (int64_t)ns + 4 * cnt;
-  w.open = true;  // (win_launch_own reads the window)
-  std::vector<char> own_launched(cnt, 0);
-  {
-    SideScope side(h);
-    for (int64_t v = 0; v < cnt; ++v) {
-      bool l = false;
-      TRY(win_launch_own(h, (size_t)v, thr_index, d_own + 3 * v, &l));
-      own_launched[v] = l ? 1 : 0;
-    }
-    k_new_ll<<<(unsigned)cnt, 64, 0, h->stream>>>(h->d_woff, h->d_wq, h->d_wq + R, h->d_wq + 2 * R, newcomer_theta(ch.cfg), d_new);
-    LAUNCHED(h);
-  }
-  ScorePlan pl;
-  if (ns > 0)
-    TRY(score_device(h, cnt, R, h->d_woff, h->d_wq, h->d_wq + R, ns, slots.data(), thr_index, d_score, d_mu, nullptr, nullptr,
-                     nullptr, true, &pl));
-  join_side(h);
-  CK(h, cudaGetLastError());
-  std::vector<double> host(total);
-  TRY(copy_back(h, host.data(), h->d_out, total));
-  // the stream is idle: the bump scratch of the previous window can be recycled
-  h->scr2_used = 0;
-  for (double* p : h->scr2_retired) cudaFree(p);
-  h->scr2_retired.clear();
-  win_store(h, 0, slots, pl, host.data(), host.data() + cnt * ns);
-  for (int64_t v = 0; v < cnt; ++v) {
-    w.new_ll[v] = host[2 * cnt * ns + v];
-    if (own_launched[v]) {
-      w.own_ll[v] = host[2 * cnt * ns + cnt + 3 * v];
-      w.own_mu[v] = host[2 * cnt * ns + cnt + 3 * v + 1];
-      w.own_flag[v] = host[2 * cnt * ns + cnt + 3 * v + 2];
-      w.own_ok[v] = 1;
-    }
-  }
-  ch.win_passes += 1;
-  ch.win_patients += cnt;
-  return MOGP_OK;
-}
-
-// Bring the cache up to date for the current patient (and, in the same launches, for the rest of the window):
-// re-score against the clusters that changed since they were scored, refresh stale own-cluster scores.
-int win_ensure(mogp_engine* h, int32_t own_id) {
-  Chain& ch = h->chain;
-  Chain::Window& w = ch.win;
-  const size_t cur = w.cur, cnt = w.pat.size();
-  if (w.slot_ok.size() < h->cl.size()) w.slot_ok.resize(h->cl.size(), 0);
   std::vector<int32_t> bad;
   for (size_t k = 0; k < ch.Nk.size(); ++k) {
     if (ch.Nk[k] <= 0 || (int32_t)k == own_id) continue;
@@ -686,39 +850,31 @@ int win_ensure(mogp_engine* h, int32_t own_id) {
   const bool need_own = own_id >= 0 && !w.own_ok[cur];
   if (bad.empty() && !need_own) return MOGP_OK;
   const int nb = (int)bad.size();
-  const int64_t rem = (int64_t)(cnt - cur), Rrem = w.col0[cnt] - w.col0[cur];
+  const int64_t rem = end - cur, Rrem = w.col0[end] - w.col0[cur], Rtot = w.col0[w.n];
   const int thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
-  const int64_t region = h->out_elems / 2;
-  if (2 * rem * nb + 3 * rem > region) FAIL(h, MOGP_ESTATE, "look-ahead output region too small");
-  double* d_score = h->d_out + region;
+  const int64_t total = 2 * rem * nb + 3 * rem;
+  TRY(ensure(h, &h->d_out, &h->out_elems, total + 8));
+  double* d_score = h->d_out;
   double* d_mu = d_score + rem * nb;
   double* d_own = d_mu + rem * nb;
-  std::vector<char> own_launched(rem, 0);
+  std::vector<int32_t> own_slot(rem, -1);
   {
     SideScope side(h);
-    for (size_t v = cur; v < cnt; ++v) {
-      if (w.own_ok[v]) continue;
-      bool l = false;
-      TRY(win_launch_own(h, v, thr_index, d_own + 3 * (v - cur), &l));
-      own_launched[v - cur] = l ? 1 : 0;
-    }
+    TRY(win_launch_own_batch(h, cur, end, true, thr_index, d_own, own_slot.data()));
   }
   ScorePlan pl;
   if (nb > 0) {
-    for (size_t v = cur; v < cnt; ++v)
-      if (w.e[v].size() < h->cl.size()) w.e[v].resize(h->cl.size());
-    TRY(score_device(h, rem, Rrem, h->d_woff + cur, h->d_wq + w.col0[cur], h->d_wq + w.col0[cnt] + w.col0[cur], nb, bad.data(),
-                     thr_index, d_score, d_mu, nullptr, nullptr, nullptr, true, &pl, true));
+    TRY(score_device(h, rem, Rrem, h->d_woff + cur, h->d_wq + w.col0[cur], h->d_wq + Rtot + w.col0[cur], nb, bad.data(), thr_index,
+                     d_score, d_mu, nullptr, nullptr, nullptr, true, &pl, arena));
     ch.win_rescores += 1;
   }
   join_side(h);
   CK(h, cudaGetLastError());
-  const int64_t total = 2 * rem * nb + 3 * rem;
   std::vector<double> host(total);
   TRY(copy_back(h, host.data(), d_score, total));
   if (nb > 0) win_store(h, cur, bad, pl, host.data(), host.data() + rem * nb);
-  for (size_t v = cur; v < cnt; ++v)
-    if (own_launched[v - cur]) {
+  for (int64_t v = cur; v < end; ++v)
+    if (own_slot[v - cur] >= 0) {
       const double* o = host.data() + 2 * rem * nb + 3 * (v - cur);
       w.own_ll[v] = o[0];
       w.own_mu[v] = o[1];
@@ -729,8 +885,8 @@ int win_ensure(mogp_engine* h, int32_t own_id) {
   return MOGP_OK;
 }
 
-// One Gibbs step of the current window patient from the cache (begin / score / draw / commit).
-int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out) {
+// One Gibbs step of the patient at position w.cur from the cache (begin / score / draw / commit).
+int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, ScoreRes* arena) {
   Chain& ch = h->chain;
   Chain::Window& w = ch.win;
   const int64_t n = w.pat[w.cur];
@@ -739,18 +895,17 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out) {
   TRY(chain_begin(h, n));
   const int32_t prev = ch.pending_prev;
   if (ch.slot_of_id[prev] < 0 || !ch.pending_lazy) win_invalidate(ch, prev_slot);  // freed, or rebuilt without the patient
-  const int64_t ni = h->h_off[n + 1] - h->h_off[n];
   const int32_t n_ids = (int32_t)ch.Nk.size();
   ch.act_ids.clear();
   for (int32_t k = 0; k < n_ids; ++k)
     if (ch.Nk[k] > 0) ch.act_ids.push_back(k);
-  ch.act_ids.push_back(n_ids);  // alpha > 0 in window mode: the new-cluster slot is always active
+  ch.act_ids.push_back(n_ids);  // alpha > 0 in this mode: the new-cluster slot is always active
   const int nact = (int)ch.act_ids.size();
   ch.act_score.assign(nact, 0.0);
   const int32_t own = ch.pending_lazy ? prev : -1;
   {
     PhaseTimer pt(&ch.t_ensure);
-    TRY(win_ensure(h, own));
+    TRY(win_ensure(h, own, arena));
   }
   const double ythr = (ch.cfg.use_threshold && !h->h_ythr.empty()) ? h->h_ythr[n] : NAN;
   for (int i = 0; i < nact; ++i) {
@@ -775,7 +930,6 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out) {
     }
     ch.act_score[i] = prior + ll;
   }
-  (void)ni;
   int idx = 0;
   int rc = host_choice(ch.act_score.data(), nact, u, nullptr, &idx, &ch.last_margin);
   if (rc != MOGP_OK) FAIL(h, rc, "probabilities contain NaN (patient %lld)", (long long)n);
@@ -784,57 +938,89 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out) {
   int32_t is_new = 0;
   {
     PhaseTimer pt(&ch.t_commit);
-    TRY(chain_commit(h, chosen, a_draw, &is_new));
+    w.in_step = true;
+    rc = chain_commit(h, chosen, a_draw, &is_new);
+    w.in_step = false;
+    if (rc != MOGP_OK) return rc;
   }
   if (!stays) {
     if (ch.slot_of_id[prev] >= 0) win_invalidate(ch, ch.slot_of_id[prev]);
     win_invalidate(ch, ch.slot_of_id[chosen]);
   }
   if (chosen_out) *chosen_out = chosen;
+  std::vector<Chain::WinEntry>().swap(w.e[w.cur]);
   w.cur += 1;
   return MOGP_OK;
 }
 
-// The whole sweep with look-ahead windows; patients the window cannot take go through the single-step path.
-int sweep_windowed(mogp_engine* h, int64_t n_steps, const int64_t* order, const double* a_draw, const double* u,
-                   int32_t* chosen_ids, double* mm, int max_cols) {
+// The whole sweep through the look-ahead pipeline; patients a batch cannot take go through the single-step path.
+int sweep_pipelined(mogp_engine* h, int64_t n_steps, const int64_t* order, const double* a_draw, const double* u,
+                    int32_t* chosen_ids, double* mm, int max_cols) {
   Chain& ch = h->chain;
-  int64_t s = 0;
-  while (s < n_steps) {
-    int64_t cnt = 0, cols = 0;
-    while (s + cnt < n_steps && cnt < 16) {
-      const int64_t n = order[s + cnt];
-      if (n < 0 || n >= ch.N) break;
-      const int64_t ni = h->h_off[n + 1] - h->h_off[n];
-      if (ni <= 0 || ni > NP || cols + ni > max_cols) break;
-      bool dup = false;
-      for (int64_t q = 0; q < cnt; ++q) dup = dup || order[s + q] == n;
-      if (dup) break;
-      cols += ni;
-      ++cnt;
+  Chain::Window& w = ch.win;
+  TRY(win_prepare(h, n_steps, order, a_draw));
+  const int depth = pipeline_depth();
+  int64_t pos = 0, jb = 0;
+  bool have_next = false;
+  while (pos < n_steps) {
+    if (!have_next) {
+      const int64_t cnt = batch_form(h, pos, max_cols);
+      if (cnt == 0) {  // no visits / too many for a rank update: patient-by-patient step; the cache starts over
+        int32_t chosen = -1;
+        w.cur = w.end_launched = pos + 1;
+        TRY(mogp_chain_step(h, order[pos], a_draw ? a_draw[pos] : 0.0, u[pos], &chosen, nullptr, nullptr, nullptr, nullptr, 0));
+        win_invalidate_all(ch);
+        if (chosen_ids) chosen_ids[pos] = chosen;
+        *mm = std::min(*mm, ch.last_margin);
+        ++pos;
+        continue;
+      }
+      w.cur = pos;
+      TRY(batch_launch(h, (int)(jb & 1), pos, cnt));
     }
-    if (cnt < 2) {
-      int32_t chosen = -1;
-      TRY(mogp_chain_step(h, order[s], a_draw ? a_draw[s] : 0.0, u[s], &chosen, nullptr, nullptr, nullptr, nullptr, 0));
-      if (chosen_ids) chosen_ids[s] = chosen;
-      *mm = std::min(*mm, ch.last_margin);
-      ++s;
-      continue;
-    }
+    Chain::Batch& B = w.b[jb & 1];
     {
       PhaseTimer pt(&ch.t_open);
-      TRY(win_open(h, cnt, order + s, a_draw ? a_draw + s : nullptr));
+      TRY(batch_absorb(h, (int)(jb & 1)));
     }
-    for (int64_t q = 0; q < cnt; ++q) {
+    w.cur = pos;
+    // re-scoring blocks written two batches ago are no longer referenced
+    ScoreRes& arena = h->res_bump[jb & 1];
+    arena.scr_used = 0;
+    for (double* p : arena.retired) cudaFree(p);
+    arena.retired.clear();
+    have_next = false;
+    if (depth >= 2) {
+      const int64_t np = pos + B.cnt;
+      const int64_t cnt2 = np < n_steps ? batch_form(h, np, max_cols) : 0;
+      if (cnt2 > 0) {
+        TRY(batch_launch(h, (int)((jb + 1) & 1), np, cnt2));
+        have_next = true;
+      }
+    }
+    const int64_t bcnt = B.cnt;
+    for (int64_t q = 0; q < bcnt; ++q) {
       int32_t chosen = -1;
-      TRY(win_step(h, a_draw ? a_draw[s + q] : 0.0, u[s + q], &chosen));
-      if (chosen_ids) chosen_ids[s + q] = chosen;
+      TRY(win_step(h, a_draw ? a_draw[pos + q] : 0.0, u[pos + q], &chosen, &arena));
+      if (chosen_ids) chosen_ids[pos + q] = chosen;
       *mm = std::min(*mm, ch.last_margin);
     }
-    ch.win.open = false;
-    s += cnt;
+    pos += bcnt;
+    ++jb;
   }
   return MOGP_OK;
+}
+
+// True when order[] visits every patient at most once (the reference sweeps over a permutation).
+bool order_is_duplicate_free(const Chain& ch, int64_t n_steps, const int64_t* order) {
+  std::vector<char> seen(ch.N, 0);
+  for (int64_t s = 0; s < n_steps; ++s) {
+    const int64_t n = order[s];
+    if (n < 0 || n >= ch.N) return false;
+    if (seen[n]) return false;
+    seen[n] = 1;
+  }
+  return true;
 }
 
 }  // namespace
@@ -943,11 +1129,14 @@ int mogp_chain_sweep(mogp_engine* h, int64_t n_steps, const int64_t* order, cons
   if (!order || !u || n_steps < 0) FAIL(h, MOGP_EINVAL, "null argument");
   if (h->chain.active && h->chain.cfg.spec.mean_func && !a_draw) FAIL(h, MOGP_EINVAL, "mean_func needs a_draw");
   double mm = INFINITY;
-  h->chain.win.open = false;
+  h->chain.win.open = h->chain.win.in_step = false;
   const int max_cols = h->chain.active && h->chain.cfg.fast_updates && h->chain.cfg.alpha > 0.0 ? window_cols(h->chain) : 0;
-  if (max_cols >= 2) {
-    int rc = sweep_windowed(h, n_steps, order, a_draw, u, chosen_ids, &mm, max_cols);
-    h->chain.win.open = false;
+  if (max_cols >= 2 && n_steps > 0 && order_is_duplicate_free(h->chain, n_steps, order)) {
+    int rc = sweep_pipelined(h, n_steps, order, a_draw, u, chosen_ids, &mm, max_cols);
+    // whatever happened, nothing of the pipeline stays in flight or cached
+    cudaStreamSynchronize(h->ahead);
+    cudaStreamSynchronize(h->ahead2);
+    h->chain.win.open = h->chain.win.in_step = false;
     if (rc != MOGP_OK) return rc;
     if (min_margin) *min_margin = mm;
     return MOGP_OK;

@@ -93,19 +93,56 @@ struct Chain {
     const double* T = nullptr;   // the patient's columns of T = M Kx under that slot (stride = mpad when scored)
     const double* mu = nullptr;  // ... and their predictive means
   };
+  struct Batch {                   // consecutive sweep positions scored by one pass
+    int64_t s0 = 0, cnt = 0;
+    std::vector<int32_t> slots;    // slots the pass scored ...
+    std::vector<int64_t> epoch;    // ... their change counters when it was launched ...
+    std::vector<int64_t> mpad;     // ... and their padded sizes (layout of T in the pass's scratch)
+    std::vector<int32_t> own_slot; // [cnt] slot whose leave-block-out score was launched with the pass (-1: none)
+    std::vector<int64_t> own_epoch;
+    ScorePlan pl;
+  };
   struct Window {
-    bool open = false;
-    std::vector<int64_t> pat;    // patient ids, in sweep order
-    std::vector<int64_t> col0;   // first column of each patient in the packed query (+ total at the end)
-    size_t cur = 0;              // patient being processed
-    std::vector<std::vector<WinEntry>> e;  // [w][slot]
-    std::vector<char> slot_ok;   // [slot]: e[w][slot] is current for every w >= cur
-    std::vector<double> new_ll;  // [w]
-    std::vector<double> own_ll, own_mu, own_flag;  // [w] leave-block-out score under the patient's own cluster
+    bool open = false;             // a pipelined sweep is running: cluster changes must be recorded (win_invalidate)
+    bool in_step = false;          // the pending patient is served from the cache (locate_T)
+    int64_t n = 0;                 // steps of the sweep
+    std::vector<int64_t> pat;      // patient ids, in sweep order
+    std::vector<int64_t> col0;     // [n + 1] first column of each position in the packed query
+    int64_t cur = 0;               // position being processed
+    int64_t end_launched = 0;      // positions below have a pass launched (their cache entries exist or are on the way)
+    std::vector<std::vector<WinEntry>> e;  // [position][slot]
+    std::vector<char> slot_ok;     // [slot]: entries current for every position in [cur, end_launched)
+    std::vector<int64_t> slot_epoch;  // [slot]: incremented whenever the cluster in that slot changes
+    std::vector<double> new_ll;    // [position]
+    std::vector<double> own_ll, own_mu, own_flag;  // [position] leave-block-out score under the patient's own cluster
     std::vector<char> own_ok;
+    Batch b[2];
   } win;
   int64_t win_passes = 0, win_rescores = 0, win_patients = 0;  // accounting
   double t_open = 0.0, t_ensure = 0.0, t_commit = 0.0;         // host seconds spent in the three phases of windowed steps
+};
+
+// Device scratch + slot-view staging of a scoring pass.  Several passes can be in flight (the next batch's pass on the
+// look-ahead stream, a re-scoring pass on the main stream), each on its own resources.
+struct ScoreRes {
+  double* scr = nullptr;
+  int64_t scr_elems = 0, scr_used = 0;
+  bool bump = false;               // bump-allocate: blocks stay alive (T = M Kx of earlier passes is still referenced)
+  std::vector<double*> retired;    // bump blocks outgrown while still referenced
+  SlotView* d_slots = nullptr;     // views of launches with more than SLOT_PACK slots
+  int64_t slots_cap = 0;
+  SlotView* h_slots = nullptr;     // own pinned staging of those views (null: the engine's upload staging)
+  int64_t hslots_cap = 0;
+};
+
+// One batch of the look-ahead pipeline (chain.inl): outputs of its scoring pass, device and pinned host.
+struct BatchBuf {
+  ScoreRes res;
+  double* d_out = nullptr;
+  int64_t out_elems = 0;
+  double* h_out = nullptr;
+  int64_t hout_elems = 0;
+  cudaEvent_t done = nullptr;
 };
 
 }  // namespace
@@ -137,16 +174,16 @@ struct mogp_engine {
   double* d_apart = nullptr;  // row-chunk partials of alpha = M^T z
   int64_t apart_elems = 0;
   // scoring scratch
-  SlotView* d_slots = nullptr;
-  int64_t slots_cap = 0;
-  double* d_scr = nullptr;
-  int64_t scr_elems = 0;
-  // second scratch of the look-ahead window (chain.inl): bump-allocated, so that the T = M Kx blocks of several
-  // re-scoring passes stay alive until the window closes; blocks outgrown mid-window are retired, not freed
-  double* d_scr2 = nullptr;
-  int64_t scr2_elems = 0, scr2_used = 0;
-  std::vector<double*> scr2_retired;
-  double* d_wq = nullptr;  // packed query of the window: x | y | a_draw
+  ScoreRes res_main;        // patient-by-patient steps, predict, append
+  ScoreRes res_bump[2];     // re-scoring passes of the look-ahead pipeline (alternate per batch)
+  BatchBuf bb[2];           // the two batches in flight
+  cudaStream_t ahead = nullptr, ahead2 = nullptr;  // low priority: the next batch's pass / its own-cluster scores
+  cudaEvent_t ev_fork = nullptr, ev_ahead2 = nullptr;
+  double* d_upd2 = nullptr;  // row-deletion workspace of the look-ahead streams (own-cluster scores)
+  int64_t upd2_elems = 0;
+  double *d_own1 = nullptr, *d_own2 = nullptr;  // Gram partials of the batched own-cluster scores (main-side / look-ahead)
+  int64_t own1_elems = 0, own2_elems = 0;
+  double* d_wq = nullptr;  // packed query of the whole sweep, in sweep order: x | y | a_draw
   int64_t wq_elems = 0;
   int64_t* d_woff = nullptr;
   int64_t woff_elems = 0;
@@ -581,8 +618,8 @@ void prof_mark(mogp_engine* h, bool stop) {
 }
 
 template <int BN>
-void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotPack& pack, int use_pack,
-                       const ChunkPlan& cp) {
+void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotView* d_slots, const SlotPack& pack,
+                       int use_pack, const ChunkPlan& cp) {
   const int smem = ScoreSmem<BN>::BYTES;
   static bool attr_done = false;
   if (!attr_done) {
@@ -591,14 +628,14 @@ void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout, const 
   }
   dim3 grid((unsigned)(pl.Rpad / BN), (unsigned)pl.n_slots, (unsigned)(pl.max_nb * cp.maxch));
   prof_mark(h, false);
-  k_score_gemm<BN><<<grid, NTHREADS, smem, h->stream>>>(h->d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout, cp);
+  k_score_gemm<BN><<<grid, NTHREADS, smem, h->stream>>>(d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout, cp);
   prof_mark(h, true);
   LAUNCHED(h);
 }
 
 template <int NS>
-void launch_score_wide(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotPack& pack, int use_pack,
-                       const ChunkPlan& cp) {
+void launch_score_wide(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotView* d_slots, const SlotPack& pack,
+                       int use_pack, const ChunkPlan& cp) {
   const int smem = WideSmem<NS>::BYTES;
   static bool attr_done = false;
   if (!attr_done) {
@@ -607,7 +644,7 @@ void launch_score_wide(mogp_engine* h, const ScorePlan& pl, double* Tout, const 
   }
   dim3 grid((unsigned)(pl.Rpad / (8 * NS)), (unsigned)pl.n_slots, (unsigned)(pl.max_nb * cp.maxch));
   prof_mark(h, false);
-  k_score_wide<NS><<<grid, WIDE_THREADS, smem, h->stream>>>(h->d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout, cp);
+  k_score_wide<NS><<<grid, WIDE_THREADS, smem, h->stream>>>(d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout, cp);
   prof_mark(h, true);
   LAUNCHED(h);
 }
@@ -617,7 +654,8 @@ void launch_score_wide(mogp_engine* h, const ScorePlan& pl, double* Tout, const 
 int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_dev, const double* xs_dev,
                  const double* ys_dev, int32_t n_slots, const int32_t* slots, int32_t thr_index, double* score_dev,
                  double* mu_thr_dev, double* col_mean, double* col_var, double* col_lpd, bool keep_T, ScorePlan* plan_out,
-                 bool bump = false) {
+                 ScoreRes* res_in = nullptr) {
+  ScoreRes& res = res_in ? *res_in : h->res_main;
   if (n_slots <= 0 || n_pat <= 0 || R <= 0) return MOGP_OK;
   ScorePlan pl;
   pl.R = R;
@@ -632,9 +670,20 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   SlotPack pack;
   SlotView* hv = pack.v;
   if (!use_pack) {
-    char* up = nullptr;
-    TRY(stage_alloc(h, sizeof(SlotView) * (size_t)n_slots, &up));
-    hv = reinterpret_cast<SlotView*>(up);
+    if (res_in && res_in != &h->res_main && !res.bump) {  // a pass on the look-ahead stream: own pinned staging
+      if (res.hslots_cap < n_slots) {
+        if (res.h_slots) CK(h, cudaFreeHost(res.h_slots));
+        res.h_slots = nullptr;
+        res.hslots_cap = 0;
+        CK(h, cudaMallocHost((void**)&res.h_slots, sizeof(SlotView) * (size_t)(n_slots + 16)));
+        res.hslots_cap = n_slots + 16;
+      }
+      hv = res.h_slots;
+    } else {
+      char* up = nullptr;
+      TRY(stage_alloc(h, sizeof(SlotView) * (size_t)n_slots, &up));
+      hv = reinterpret_cast<SlotView*>(up);
+    }
   }
   for (int s = 0; s < n_slots; ++s) {
     Cluster& c = h->cl[slots[s]];
@@ -663,7 +712,7 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
     }
   }
   if (h->prof_on) h->prof_launches += 1;
-  TRY(ensure(h, &h->d_slots, &h->slots_cap, n_slots));
+  TRY(ensure(h, &res.d_slots, &res.slots_cap, n_slots));
   const int64_t mu_total = (int64_t)n_slots * pl.Rpad, mupart_total = mu_total * pl.max_rblk;
   // few (slot, row block) items and one column tile: split the contraction across CTAs (see ChunkPlan)
   ChunkPlan cp;
@@ -673,20 +722,20 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   }
   const int64_t tpart_total = cp.kc > 0 ? pl.kx_total * cp.maxch : 0;
   const int64_t need = pl.kx_total * (keep_T ? 2 : 1) + pl.part_total + mu_total + mupart_total + tpart_total;
-  if (bump) {
-    if (h->scr2_used + need > h->scr2_elems) {  // outgrown: earlier blocks of this window are still referenced
-      if (h->d_scr2) h->scr2_retired.push_back(h->d_scr2);
-      h->d_scr2 = nullptr;
-      h->scr2_elems = h->scr2_used = 0;
+  if (res.bump) {
+    if (res.scr_used + need > res.scr_elems) {  // outgrown: earlier blocks are still referenced by the pipeline
+      if (res.scr) res.retired.push_back(res.scr);
+      res.scr = nullptr;
+      res.scr_elems = res.scr_used = 0;
       const int64_t want = std::max<int64_t>(4 * need, (int64_t)1 << 21);
-      CK(h, cudaMalloc((void**)&h->d_scr2, sizeof(double) * (size_t)want));
-      h->scr2_elems = want;
+      CK(h, cudaMalloc((void**)&res.scr, sizeof(double) * (size_t)want));
+      res.scr_elems = want;
     }
-    pl.kxT = h->d_scr2 + h->scr2_used;
-    h->scr2_used += need;
+    pl.kxT = res.scr + res.scr_used;
+    res.scr_used += need;
   } else {
-    TRY(ensure(h, &h->d_scr, &h->scr_elems, need));
-    pl.kxT = h->d_scr;
+    TRY(ensure(h, &res.scr, &res.scr_elems, need));
+    pl.kxT = res.scr;
   }
   pl.part = pl.kxT + pl.kx_total;
   pl.mu = pl.part + pl.part_total;
@@ -694,29 +743,29 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   pl.T = keep_T ? pl.mupart + mupart_total : nullptr;
   cp.Tpart = cp.kc > 0 ? pl.mupart + mupart_total + (keep_T ? pl.kx_total : 0) : nullptr;
   if (!use_pack) {
-    CK(h, cudaMemcpyAsync(h->d_slots, hv, sizeof(SlotView) * (size_t)n_slots, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(res.d_slots, hv, sizeof(SlotView) * (size_t)n_slots, cudaMemcpyHostToDevice, h->stream));
     h->bytes_h2d += (int64_t)sizeof(SlotView) * n_slots;
   }
   k_kx<<<dim3((unsigned)pl.max_rblk, (unsigned)((pl.Rpad + KX_COLS - 1) / KX_COLS), (unsigned)n_slots), KX_ROWS, 0,
-         h->stream>>>(h->d_slots, pack, use_pack, xs_dev, (int)R, (int)pl.Rpad, pl.max_rblk, pl.kxT, pl.mupart);
+         h->stream>>>(res.d_slots, pack, use_pack, xs_dev, (int)R, (int)pl.Rpad, pl.max_rblk, pl.kxT, pl.mupart);
   LAUNCHED(h);
   switch (pl.BN) {  // <= 16 columns: bound by HBM (8-warp ring); wider: bound by the FP64 tensor pipe (16 warps)
-    case 8: launch_score_gemm<8>(h, pl, pl.T, pack, use_pack, cp); break;
-    case 16: launch_score_gemm<16>(h, pl, pl.T, pack, use_pack, cp); break;
-    case 24: launch_score_wide<3>(h, pl, pl.T, pack, use_pack, cp); break;
-    case 32: launch_score_wide<4>(h, pl, pl.T, pack, use_pack, cp); break;
-    case 40: launch_score_wide<5>(h, pl, pl.T, pack, use_pack, cp); break;
-    case 48: launch_score_wide<6>(h, pl, pl.T, pack, use_pack, cp); break;
-    case 56: launch_score_wide<7>(h, pl, pl.T, pack, use_pack, cp); break;
-    default: launch_score_wide<8>(h, pl, pl.T, pack, use_pack, cp); break;
+    case 8: launch_score_gemm<8>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
+    case 16: launch_score_gemm<16>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
+    case 24: launch_score_wide<3>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
+    case 32: launch_score_wide<4>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
+    case 40: launch_score_wide<5>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
+    case 48: launch_score_wide<6>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
+    case 56: launch_score_wide<7>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
+    default: launch_score_wide<8>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
   }
   if (cp.kc > 0) {
-    k_score_reduce<<<dim3((unsigned)n_slots, (unsigned)pl.max_nb), 256, 0, h->stream>>>(h->d_slots, pack, use_pack, (int)pl.Rpad, cp,
+    k_score_reduce<<<dim3((unsigned)n_slots, (unsigned)pl.max_nb), 256, 0, h->stream>>>(res.d_slots, pack, use_pack, (int)pl.Rpad, cp,
                                                                                       pl.part, pl.T);
     LAUNCHED(h);
   }
   const int64_t pairs = n_pat * n_slots;
-  k_score_epi<<<(unsigned)((pairs + 7) / 8), 256, 0, h->stream>>>(h->d_slots, pack, use_pack, n_slots, off_dev, n_pat, xs_dev, ys_dev,
+  k_score_epi<<<(unsigned)((pairs + 7) / 8), 256, 0, h->stream>>>(res.d_slots, pack, use_pack, n_slots, off_dev, n_pat, xs_dev, ys_dev,
                                                                      (int)pl.Rpad, pl.part, pl.mupart, pl.max_rblk, pl.mu,
                                                                      thr_index, score_dev,
                                                                      mu_thr_dev, col_mean, col_var, col_lpd);
@@ -785,8 +834,19 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
   }
   mogp_engine* h = new mogp_engine();
   h->device = device;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+  int prio_least = 0, prio_greatest = 0;
+  if (cudaSetDevice(device) == cudaSuccess) cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  // main / side carry the dependent chain of a Gibbs step (highest priority); the look-ahead streams carry the next
+  // batch's scoring pass, which fills the SMs the chain leaves idle (lowest priority)
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->ahead, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->ahead2, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_ahead2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->bb[0].done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->bb[1].done, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess ||
@@ -796,6 +856,7 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
     return MOGP_ECUDA;
   }
   h->main_stream = h->stream;
+  h->res_bump[0].bump = h->res_bump[1].bump = true;
   cudaMalloc((void**)&h->d_adraw, sizeof(double) * 8);
   cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM);
   cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
@@ -818,10 +879,25 @@ void mogp_engine_destroy(mogp_engine* h) {
   cudaFree(h->d_L);
   cudaFree(h->d_partial);
   cudaFree(h->d_apart);
-  cudaFree(h->d_slots);
-  cudaFree(h->d_scr);
-  cudaFree(h->d_scr2);
-  for (double* p : h->scr2_retired) cudaFree(p);
+  auto free_res = [](ScoreRes& r) {
+    cudaFree(r.scr);
+    for (double* p : r.retired) cudaFree(p);
+    cudaFree(r.d_slots);
+    if (r.h_slots) cudaFreeHost(r.h_slots);
+  };
+  free_res(h->res_main);
+  for (int i = 0; i < 2; ++i) {
+    free_res(h->res_bump[i]);
+    free_res(h->bb[i].res);
+    cudaFree(h->bb[i].d_out);
+    if (h->bb[i].h_out) cudaFreeHost(h->bb[i].h_out);
+    if (h->bb[i].done) cudaEventDestroy(h->bb[i].done);
+  }
+  cudaFree(h->d_upd2);
+  cudaFree(h->d_own1);
+  cudaFree(h->d_own2);
+  if (h->ahead) cudaStreamDestroy(h->ahead);
+  if (h->ahead2) cudaStreamDestroy(h->ahead2);
   cudaFree(h->d_wq);
   cudaFree(h->d_woff);
   cudaFree(h->d_q);

@@ -243,57 +243,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_score_gemm(SLOT_ARGS, const dou
 // 34 % of the stall samples on fixed-latency dependencies).  The four k-group partials are added once per CTA, in a
 // fixed order, through the (then idle) stage buffers.
 constexpr int WIDE_THREADS = 512;
+constexpr int LD_K = 72;  // smem ld of both operands of the wide kernel (8 mod 16: conflict-free 128-bit fragment loads)
 template <int NS>
 struct WideSmem {
   static constexpr int BN = 8 * NS;
-  static constexpr int STAGE = (TB + BN) * LD_C;  // doubles per stage
-  static constexpr int S = (4 * STAGE * 8 <= 227 * 1024) ? 4 : 3;
-  static constexpr int BYTES = S * STAGE * (int)sizeof(double);
+  static constexpr int STAGE = (TB + BN) * LD_K;  // doubles per stage
+  static constexpr int S = (4 * STAGE * 8 + 64 <= 227 * 1024) ? 4 : 3;
+  static constexpr int BYTES = S * STAGE * (int)sizeof(double) + 64;  // + full/empty mbarriers of the ring
 };
 
 template <int NS>
-__global__ void __launch_bounds__(WIDE_THREADS, 1) k_score_wide(SLOT_ARGS, const double* __restrict__ kxT, int Rpad,
-                                                               double* __restrict__ part, double* __restrict__ Tout,
-                                                               const ChunkPlan cp) {
+__device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk, int c0, const double* __restrict__ kxT, int Rpad,
+                                          double* __restrict__ part, double* __restrict__ Tout, const ChunkPlan& cp,
+                                          double* smem, double (*red)[8 * NS]) {
   constexpr int BN = 8 * NS, MS = 2, WM = 4;
   constexpr int NST = WideSmem<NS>::S, STAGE = WideSmem<NS>::STAGE;
-  const SlotView sv = SLOT_AT(blockIdx.y);
-  const int nb = sv.mpad / TB;
-  const int zi = cp.kc > 0 ? (int)blockIdx.z / cp.maxch : (int)blockIdx.z;
-  const int chunk = cp.kc > 0 ? (int)blockIdx.z % cp.maxch : 0;
-  const int rb = nb - 1 - zi;  // heavy row blocks first, across the slots
-  if (rb < 0) return;
   const int t_begin = chunk * cp.kc;
   if (cp.kc > 0 && t_begin > rb) return;
-  const int c0 = blockIdx.x * BN;
-  extern __shared__ __align__(16) double smem[];
-  __shared__ double red[WM][BN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int wm = warp & 3, kg = warp >> 2;  // row group, k group
   const int rbase = wm * 16;
   const double* Mrow = sv.M + (int64_t)rb * TB * sv.ld + (int64_t)t_begin * TB;
   const double* kx = kxT + sv.kx_off + (int64_t)c0 * sv.mpad + (int64_t)t_begin * TB;
   const int ntiles = cp.kc > 0 ? min(cp.kc, rb + 1 - t_begin) : rb + 1;
+  // Ring of NST stages, synchronised per stage instead of per CTA: full[s] completes when every thread's copies of
+  // the tile in stage s have landed (cp.async -> mbarrier), empty[s] when all 16 warps are done reading it.  The tile
+  // DIST ahead is requested while the current one is multiplied, into the stage that was consumed NST - DIST tiles
+  // ago, so a warp may run a whole tile ahead of the slowest one without anybody waiting: the tensor pipe keeps
+  // working across tile boundaries (ncu on the __syncthreads version: 65 % busy, warps parked at the barrier).
+  constexpr int DIST = NST - 2 > 0 ? NST - 2 : 1;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * STAGE);
+  uint64_t* empty = full + NST;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NST; ++q) {
+      mbar_init(full + q, WIDE_THREADS);
+      mbar_init(empty + q, WIDE_THREADS / 32);
+    }
+    mbar_init_fence();
+  }
+  __syncthreads();
   auto issue = [&](int tile) {
     if (tile < ntiles) {
-      double* sA = smem + (tile % NST) * STAGE;
-      load_tile_async<LD_C, TB, WIDE_THREADS>(sA, Mrow + (int64_t)tile * TB, sv.ld);
-      load_tile_async<LD_C, BN, WIDE_THREADS>(sA + TB * LD_C, kx + (int64_t)tile * TB, sv.mpad);
+      const int st = tile % NST, use = tile / NST;
+      if (use > 0) mbar_wait(empty + st, (use - 1) & 1);
+      double* sA = smem + st * STAGE;
+      load_tile_async<LD_K, TB, WIDE_THREADS>(sA, Mrow + (int64_t)tile * TB, sv.ld);
+      load_tile_async<LD_K, BN, WIDE_THREADS>(sA + TB * LD_K, kx + (int64_t)tile * TB, sv.mpad);
+      cp_async_mbar_arrive(full + st);
     }
-    cp_async_commit();
   };
 #pragma unroll
-  for (int tile = 0; tile < NST - 1; ++tile) issue(tile);
+  for (int tile = 0; tile < DIST; ++tile) issue(tile);
   Acc<MS, NS> acc;
   acc.zero();
   for (int tile = 0; tile < ntiles; ++tile) {
-    cp_async_wait<NST - 2>();
-    __syncthreads();
-    issue(tile + NST - 1);
-    const double* sA = smem + (tile % NST) * STAGE;
-    warp_mma<MS, NS, true, true, TB / 4>(acc, sA + kg * (TB / 4), sA + TB * LD_C + kg * (TB / 4), rbase, 0);
+    issue(tile + DIST);
+    const int st = tile % NST;
+    mbar_wait(full + st, (tile / NST) & 1);
+    const double* sA = smem + st * STAGE;
+    warp_mma_k8<MS, NS, TB / 4, LD_K>(acc, sA + kg * (TB / 4), sA + TB * LD_K + kg * (TB / 4), rbase, 0);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + st);
   }
-  cp_async_wait<0>();
   __syncthreads();  // every warp is done with the stage buffers: reuse them for the k-group reduction
   constexpr int LDP = BN + 2;  // partial tile [64][LDP] per k group 1..3
   if (kg > 0) {
@@ -369,6 +381,22 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_score_wide(SLOT_ARGS, const
     for (int q = 0; q < WM; ++q) s += red[q][threadIdx.x];
     part[sv.part_off + (int64_t)rb * Rpad + c0 + threadIdx.x] = s;
   }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(WIDE_THREADS, 1) k_score_wide(SLOT_ARGS, const double* __restrict__ kxT, int Rpad,
+                                                               double* __restrict__ part, double* __restrict__ Tout,
+                                                               const ChunkPlan cp) {
+  constexpr int BN = 8 * NS;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double red[4][BN];
+  const SlotView sv = SLOT_AT(blockIdx.y);
+  const int nb = sv.mpad / TB;
+  const int zi = cp.kc > 0 ? (int)blockIdx.z / cp.maxch : (int)blockIdx.z;
+  const int chunk = cp.kc > 0 ? (int)blockIdx.z % cp.maxch : 0;
+  const int rb = nb - 1 - zi;  // heavy row blocks first, across the slots
+  if (rb < 0) return;
+  wide_item<NS>(sv, rb, chunk, blockIdx.x * BN, kxT, Rpad, part, Tout, cp, smem, red);
 }
 
 // Per (patient, slot): finish the predictive moments and sum the per-visit log densities.  One warp per pair:

@@ -92,6 +92,15 @@ __device__ __forceinline__ void load_tile(double* __restrict__ s, const double* 
   }
 }
 
+// cp.async completion tracked by an mbarrier: the arrive fires when all cp.async this thread has issued so far have
+// landed (.noinc: it counts as one of the barrier's expected arrivals).
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // Accumulators of one warp for a (8*MS) x (8*NS) patch.
 template <int MS, int NS>
 struct Acc {
@@ -125,6 +134,33 @@ __device__ __forceinline__ void warp_mma(Acc<MS, NS>& acc, const double* __restr
     for (int i = 0; i < MS; ++i)
 #pragma unroll
       for (int j = 0; j < NS; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+  }
+}
+
+// The same product with 16-byte fragment loads: DMMA contracts 4 k-indices per instruction and any 4 will do as long as
+// A and B agree, so lane t takes k = kb + 2t and kb + 2t + 1 from ONE 128-bit load and feeds them to two consecutive
+// DMMAs (k = kb + {0,2,4,6}, then kb + {1,3,5,7}): half the shared-memory load instructions per DMMA.  Both operands
+// are stored with the contraction index contiguous ([row][LD], [col][LD]); LD = 8 mod 16 keeps the 128-bit loads of a
+// quarter warp (two rows x 64 bytes) on distinct banks.
+template <int MS, int NS, int KDIM, int LD>
+__device__ __forceinline__ void warp_mma_k8(Acc<MS, NS>& acc, const double* __restrict__ sA, const double* __restrict__ sB,
+                                            int rb, int cb) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kb = 0; kb < KDIM; kb += 8) {
+    double2 a[MS], b[NS];
+#pragma unroll
+    for (int i = 0; i < MS; ++i) a[i] = *reinterpret_cast<const double2*>(sA + (rb + 8 * i + g) * LD + kb + 2 * t);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) b[j] = *reinterpret_cast<const double2*>(sB + (cb + 8 * j + g) * LD + kb + 2 * t);
+#pragma unroll
+    for (int i = 0; i < MS; ++i)
+#pragma unroll
+      for (int j = 0; j < NS; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+    for (int i = 0; i < MS; ++i)
+#pragma unroll
+      for (int j = 0; j < NS; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i].y, b[j].y);
   }
 }
 

@@ -81,16 +81,17 @@ struct RmWork {
 
 // ---------------------------------------------------------------------------------------------
 // Per 64-row tile (new space, tiles I0..nbn-1): stage b rows, partial Gram of the tile, carriers' Gram.
-__global__ void __launch_bounds__(256) k_rm_gram(const double* __restrict__ M, RmGeom g, RmWork w) {
+__device__ __forceinline__ void rm_gram_tile(const double* __restrict__ M, const RmGeom& g, const RmWork& w, int bx,
+                                             bool write_bt) {
   __shared__ double sb[TB][NP + 1];
-  const int I = g.I0 + blockIdx.x;
+  const int I = g.I0 + bx;
   for (int idx = threadIdx.x; idx < TB * NP; idx += 256) {
     int r = idx / NP, a = idx % NP;
     int ip = I * TB + r;
     double v = 0.0;
     if (a < g.n && ip >= g.p && ip < g.mnew) v = M[(int64_t)(ip + g.n) * g.ld + g.p + a];
     sb[r][a] = v;
-    w.Bt[((int64_t)blockIdx.x * TB + r) * NP + a] = v;
+    if (write_bt) w.Bt[((int64_t)bx * TB + r) * NP + a] = v;
   }
   __syncthreads();
   if (threadIdx.x < NG) {
@@ -99,8 +100,8 @@ __global__ void __launch_bounds__(256) k_rm_gram(const double* __restrict__ M, R
     double s = 0.0;
 #pragma unroll 8
     for (int r = 0; r < TB; ++r) s += sb[r][a] * sb[r][b];
-    w.Pgram[(int64_t)blockIdx.x * NG + threadIdx.x] = s;
-    if (blockIdx.x == 0) {  // carriers: rows p..p+n-1 of the block columns (lower triangular M_BB)
+    w.Pgram[(int64_t)bx * NG + threadIdx.x] = s;
+    if (bx == 0) {  // carriers: rows p..p+n-1 of the block columns (lower triangular M_BB)
       double c = 0.0;
       if (a < g.n)
         for (int q = a; q < g.n; ++q) c += M[(int64_t)(g.p + q) * g.ld + g.p + a] * M[(int64_t)(g.p + q) * g.ld + g.p + b];
@@ -108,11 +109,15 @@ __global__ void __launch_bounds__(256) k_rm_gram(const double* __restrict__ M, R
     }
   }
 }
+__global__ void __launch_bounds__(256) k_rm_gram(const double* __restrict__ M, RmGeom g, RmWork w) {
+  rm_gram_tile(M, g, w, (int)blockIdx.x, true);
+}
 
 // Leave-block-out score of the block's own patient under the cluster that still contains it.
 //   out[0] = sum_i log N(y_i | mu_i, v_i), out[1] = predictive mean at visit thr_index, out[2] = ok flag
-__global__ void __launch_bounds__(256) k_own_final(const double* __restrict__ alpha, const double* __restrict__ yB, RmGeom g,
-                                                   RmWork w, int nT, Theta th, int thr_index, double* __restrict__ out) {
+__device__ __forceinline__ void own_final_body(const double* __restrict__ alpha, const double* __restrict__ yB, const RmGeom& g,
+                                               const RmWork& w, int nT, const Theta& th, int thr_index,
+                                               double* __restrict__ out) {
   __shared__ double G[NG], C[NP][NP], v[NP];
   __shared__ int ok;
   if (threadIdx.x < NG) {
@@ -148,6 +153,36 @@ __global__ void __launch_bounds__(256) k_own_final(const double* __restrict__ al
     out[1] = (thr_index >= 0 && thr_index < g.n) ? yB[thr_index] - v[thr_index] : nan("");
     out[2] = ok ? 1.0 : 0.0;
   }
+}
+__global__ void __launch_bounds__(256) k_own_final(const double* __restrict__ alpha, const double* __restrict__ yB, RmGeom g,
+                                                   RmWork w, int nT, Theta th, int thr_index, double* __restrict__ out) {
+  own_final_body(alpha, yB, g, w, nT, th, thr_index, out);
+}
+
+// The same two kernels for several patients at once (the own-cluster scores of a look-ahead batch): one launch pair
+// instead of one pair per patient.  The jobs travel in the kernel parameters.
+constexpr int OWN_BATCH = 16;
+struct OwnJob {
+  const double* M;
+  const double* alpha;
+  const double* yB;
+  double* out;   // [3]
+  RmGeom g;
+  RmWork w;      // only Pgram / Gc are used
+  Theta th;
+  int nT;
+};
+struct OwnJobs {
+  OwnJob j[OWN_BATCH];
+};
+__global__ void __launch_bounds__(256) k_own_gram_batch(const __grid_constant__ OwnJobs jobs) {
+  const OwnJob& jb = jobs.j[blockIdx.y];
+  if ((int)blockIdx.x >= jb.nT) return;
+  rm_gram_tile(jb.M, jb.g, jb.w, (int)blockIdx.x, false);
+}
+__global__ void __launch_bounds__(256) k_own_final_batch(const __grid_constant__ OwnJobs jobs, int thr_index) {
+  const OwnJob& jb = jobs.j[blockIdx.x];
+  own_final_body(jb.alpha, jb.yB, jb.g, jb.w, jb.nT, jb.th, thr_index, jb.out);
 }
 
 // Per tile: G_{i-1} for each of its rows (running Gram, snapshots in shared memory), then one thread per

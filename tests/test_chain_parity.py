@@ -112,14 +112,16 @@ def test_fast_sweeps_match_oracle(eng, kernel, mean_func, threshold, single_blas
     assert np.allclose(mix.lalloc, orc.lalloc, rtol=1e-13)
 
 
-@pytest.mark.parametrize("lookahead", [16, 32, 64])
-def test_lookahead_window_equals_patient_by_patient(eng, lookahead):
-    """mogp_chain_sweep with a look-ahead window (several patients scored per pass over the factors, re-scored
-    against the clusters that change) walks the same chain as one pass per patient: identical choices per step,
+@pytest.mark.parametrize("lookahead,pipeline", [(16, 2), (32, 2), (64, 2), (32, 1)])
+def test_lookahead_window_equals_patient_by_patient(eng, lookahead, pipeline, monkeypatch):
+    """mogp_chain_sweep with the look-ahead pipeline (batches of patients scored per pass over the factors, the next
+    batch's pass running while the current batch moves, everything re-scored against the clusters that change) walks
+    the same chain as one pass per patient: identical choices per step,
     identical counts, cluster log marginals within 1e-9 relative (after an L-BFGS-B refit in between), on a first sweep where most patients move (every
     window sees invalidations, new clusters and emptied clusters)."""
     from mogp_b200 import MoGP_constrained
     from mogp_b200.synth import alsfrs_like, block_init
+    monkeypatch.setenv("MOGP_PIPELINE", str(pipeline))   # 2: the next batch's pass overlaps the current batch's moves
     N = 400
     X, Y = alsfrs_like(N, seed=5)
     z0 = block_init(N, 6, X)
