@@ -258,6 +258,34 @@ def run_b200(args):
     ms_e2e_max = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
+    # the dominant kernel on its own (no concurrent work): one batch of the look-ahead pipeline = the first patients of a
+    # permutation up to the pipeline's column budget, against every active cluster of the final state
+    iso = None
+    if rank == 0:
+        cols = int(os.environ.get("MOGP_LOOKAHEAD", "48"))
+        take, tot = [], 0
+        for n in np.random.RandomState(1).permutation(N):
+            ni = int(off[n + 1] - off[n])
+            if tot + ni > cols:
+                break
+            take.append(n); tot += ni
+        qoff = np.zeros(len(take) + 1, dtype=np.int64)
+        qx, qy = [], []
+        for i, n in enumerate(take):
+            qx.append(px[off[n]:off[n + 1]]); qy.append(py[off[n]:off[n + 1]])
+            qoff[i + 1] = qoff[i] + (off[n + 1] - off[n])
+        qx, qy = np.concatenate(qx), np.concatenate(qy)
+        _z, _Nk, slots_now = eng.chain_state(N)
+        act = np.array([s for s in slots_now if s >= 0], dtype=np.int32)
+        eng.profile(True); eng.profile_read(reset=True)
+        for rep in range(10):
+            eng.score_pairs(qoff, qx, qy, act)
+            if rep == 1:
+                eng.profile_read(reset=True)
+        pi = eng.profile_read(reset=True); eng.profile(False)
+        iso = {"columns": int(tot), "patients": len(take), "avg_launch_us": pi["ms"] / max(pi["launches"], 1) * 1e3,
+               "fp64_tflops": pi["alg_flops"] / (pi["ms"] * 1e-3) / 1e12, "hbm_gbs": pi["alg_bytes"] / (pi["ms"] * 1e-3) / 1e9}
+
     # gather the chains' results (the only collective of this mode)
     occupancy = [int(v) for v in mix.allocmodel.Nk[mix.allocmodel.Nk > 0]]
     if world > 1:
@@ -301,7 +329,17 @@ def run_b200(args):
                      "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac, "peak_source": hbm_src},
                      "fp64": {"achieved": tfs, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp_frac, "peak_source": fp64_src},
                      "pairs_per_launch": counters["pairs"] / max(prof["launches"], 1),
-                     "share_of_step": prof["ms"] / ms})
+                     "share_of_step": prof["ms"] / ms,
+                     "note": "achieved = whole passes (every active cluster) timed live in the sweeps, where they share the SMs "
+                             "with the moves of the previous batch; 'isolated' = the same kernel alone; 'rescoring' = the short "
+                             "passes against the one or two clusters a move changed (latency bound, accounted apart)",
+                     "isolated": iso,
+                     "rescoring": {"launches": counters["rescoring_launches"],
+                                   "avg_launch_us": counters["rescoring_ms"] / max(counters["rescoring_launches"], 1) * 1e3,
+                                   "share_of_step": counters["rescoring_ms"] / ms}})
+        if iso:
+            roof["isolated"]["frac_fp64"] = iso["fp64_tflops"] / fp64_peak
+            roof["isolated"]["frac_hbm"] = iso["hbm_gbs"] / hbm_peak
         line = {"metric": "Gibbs sweeps/sec @10k patients", "value": world * args.steps / (ms_max * 1e-3), "unit": "sweeps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -316,7 +354,7 @@ def run_b200(args):
                           "refit_evals": int(mix.n_refit_evals), "total_loglik": ll,
                           "steps_s_per_sweep": split_timed[0], "refit_s_per_sweep": split_timed[1],
                           "lookahead": {k: counters[k] for k in ("window_passes", "rescoring_passes", "window_patients",
-                                                                 "open_s", "rescore_s", "commit_s")}}}
+                                                                 "open_s", "rescore_s", "commit_s", "rank_corrections", "correct_s")}}}
         if world == 1 and not args.no_cpu_baseline:
             orc, _t_init = oracle_sample(args, 0)
             ts, tr, nact, evals = oracle_step_times(orc, args.cpu_steps, 1)

@@ -93,7 +93,10 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
 /* Look-ahead accounting of the attached chain since mogp_chain_init: out[0] = window passes (one pass over every
    active factor), out[1] = re-scoring passes (clusters that changed), out[2] = patients served from windows,
    out[3] = (patient, cluster) pairs scored by the profiled launches since the last profile reset,
-   out[4..6] = host seconds spent opening windows / re-scoring / committing moves (each includes its waits). */
+   out[4..6] = host seconds spent waiting for batches / re-scoring / committing moves (each includes its waits),
+   out[7..10] = launches, device ms, algorithmic bytes and flops of the profiled RE-SCORING launches of the scoring
+   product since the last profile reset (mogp_profile_read reports the whole passes only),
+   out[11] = moves whose effect on the cached scores was a rank-n correction, out[12] = host seconds in them. */
 int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out);
 
 /* ---- one cluster's GP = one GPobs object ------------------------------------------------- */
@@ -183,7 +186,9 @@ typedef struct mogp_chain_config {
   /* mogp_chain_sweep, fast mode: the sweep order is known in advance, so consecutive patients totalling at most
      `lookahead` visits (query columns) are scored against every active cluster in ONE pass over the factors; the
      chain stays sequential (a cached score is used only while its cluster is unchanged, the rest is re-scored).
-     0 = engine default (32), negative = off (one pass per patient), capped at 64. */
+     0 = engine default (48), negative = off (one pass per patient), capped at 64.  While the host draws and moves the
+     patients of one batch, the pass of the next batch already runs on a low-priority stream (MOGP_PIPELINE=1 in the
+     environment turns that overlap off; MOGP_LOOKAHEAD overrides this field: tuning and tests). */
   int32_t lookahead;
 } mogp_chain_config;
 

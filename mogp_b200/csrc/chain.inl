@@ -35,6 +35,7 @@ int refresh_vectors(mogp_engine* h, Cluster& c, bool recompute_z) {
 
 int fetch_stat(mogp_engine* h, Cluster& c) {
   if (!c.stat_on_device) return MOGP_OK;
+  order_after_side(h, c);
   if (c.lml_dirty) {
     TRY(launch_alpha_lml(h, c));
     c.lml_dirty = false;
@@ -61,21 +62,56 @@ int fetch_stat(mogp_engine* h, Cluster& c) {
 int append_core(mogp_engine* h, Cluster& c, int n, const double* xB_dev, const double* yB_dev, const double* T_dev,
                 const double* mu_dev) {
   const int64_t m = c.m, mpad_old = round_up(m, TB), mnew = m + n, mpad_new = round_up(mnew, TB);
-  if (mnew > c.cap) TRY(cluster_reserve(h, c, mnew, true));
+  order_after_side(h, c);
+  const bool reserved = mnew > c.cap;
+  if (reserved) TRY(cluster_reserve(h, c, mnew, true));
   const int nb = (int)(mpad_old / TB);
   const int nblk = (int)((mpad_old + AP_GRAM_ROWS - 1) / AP_GRAM_ROWS);
+  const bool ring = nblk <= AP_RING_NBLK;
   TRY(ensure(h, &h->d_apw, &h->apw_elems, NP * NP + NP + (int64_t)nblk * NG + APPEND_KS * NP * mpad_old));
   ApWork w;
-  w.Li = h->d_apw;
-  w.znew = w.Li + NP * NP;
-  w.gpart = w.znew + NP;
-  w.part = w.gpart + (int64_t)nblk * NG;
+  if (ring) {
+    w.Li = h->d_apring + (int64_t)h->apring_next * AP_RING_SLOT;
+    h->apring_next = (h->apring_next + 1) % AP_RING;
+    w.znew = w.Li + NP * NP;
+    w.gpart = w.znew + NP;
+    w.part = h->d_apw;
+  } else {
+    w.Li = h->d_apw;
+    w.znew = w.Li + NP * NP;
+    w.gpart = w.znew + NP;
+    w.part = w.gpart + (int64_t)nblk * NG;
+  }
   Theta th = make_theta(c);
   int* info = reinterpret_cast<int*>(c.stat() + 8);
-  k_append_gram<<<nblk, 256, 0, h->stream>>>(T_dev, (int)mpad_old, n, w);
+  // Gram of T, Ls and z_B depend only on what the scoring pass left behind, not on the factor: with a join-side score
+  // correction waiting for them (look-ahead pipeline) they run on the quick stream, ahead of whatever is still queued
+  // on the main stream, which picks up from there
+  AlgHook* hk = (h->alg_hook && !h->alg_hook->fired && h->stream == h->main_stream) ? h->alg_hook : nullptr;
+  const bool on_quick = hk && ring && !reserved;
+  cudaStream_t s1 = on_quick ? h->quick : h->stream;
+  if (hk) {
+    hk->ntiles = (int)(mpad_old / TB);
+    TRY(ensure(h, &h->d_algw2, &h->algw2_elems, (int64_t)hk->npos * hk->ntiles * NP * NP));
+    k_alg_join_part<<<dim3((unsigned)hk->ntiles, (unsigned)hk->npos), 256, 0, s1>>>(hk->jobs, h->d_algw2);
+    LAUNCHED(h);
+  }
+  k_append_gram<<<nblk, 256, 0, s1>>>(T_dev, (int)mpad_old, n, w);
   LAUNCHED(h);
-  k_append_small<<<1, 256, 0, h->stream>>>(mu_dev, nblk, xB_dev, yB_dev, n, th, w, info);
+  k_append_small<<<1, 256, 0, s1>>>(mu_dev, nblk, xB_dev, yB_dev, n, th, w, info);
   LAUNCHED(h);
+  if (on_quick) {
+    CK(h, cudaEventRecord(h->ev_apq, h->quick));
+    CK(h, cudaStreamWaitEvent(h->main_stream, h->ev_apq, 0));
+  }
+  if (hk) {
+    hk->jobs.Li = w.Li;
+    hk->jobs.znew = w.znew;
+    k_alg_join_fin<<<hk->npos, 256, 0, s1>>>(hk->jobs, h->d_algw2, hk->ntiles);
+    LAUNCHED(h);
+    CK(h, cudaEventRecord(h->ev_alg, s1));
+    hk->fired = true;
+  }
   k_append_rows<<<dim3(nb, APPEND_KS), NTHREADS, AP_ROWS_SMEM, h->stream>>>(c.M, c.cap, nb, (int)mpad_old, T_dev, n, w);
   LAUNCHED(h);
   if (mpad_new > mpad_old) {
@@ -400,7 +436,8 @@ void locate_T(mogp_engine* h, int32_t slot, const double** T, const double** mu)
   *T = *mu = nullptr;
   if (ch.win.in_step) {
     const Chain::Window& w = ch.win;
-    if (slot >= 0 && slot < (int32_t)w.slot_ok.size() && w.slot_ok[slot] && slot < (int32_t)w.e[w.cur].size()) {
+    if (slot >= 0 && slot < (int32_t)w.slot_upto.size() && w.slot_upto[slot] > w.cur && w.slot_T_ok[slot] &&
+        slot < (int32_t)w.e[w.cur].size()) {
       *T = w.e[w.cur][slot].T;
       *mu = w.e[w.cur][slot].mu;
     }
@@ -449,11 +486,22 @@ int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_n
       side_busy = true;
       c.members.erase(c.members.begin() + idx);
     }
-    struct Joiner {  // whatever path the assignment takes, the main stream ends up ordered after the deletion
+    // whatever path the assignment takes, the main stream ends up ordered after the deletion - at once, or (look-ahead
+    // pipeline) when main-stream work next touches that cluster (order_after_side), opens a batch or re-scores
+    struct Joiner {
       mogp_engine* h;
       bool on;
-      ~Joiner() { if (on) join_side(h); }
-    } joiner{h, side_busy};
+      int32_t slot;
+      ~Joiner() {
+        if (!on) return;
+        if (h->chain.win.in_step && slot >= 0 && h->cl[slot].used) {
+          h->cl[slot].side_busy = true;
+          h->side_pending = true;
+        } else {
+          join_side(h);
+        }
+      }
+    } joiner{h, side_busy, ch.pending_lazy ? ch.slot_of_id[prev] : -1};
     if (is_new) {
       int32_t slot;
       double th[4] = {fabs(a_draw), ch.cfg.signal_variance,
@@ -482,6 +530,16 @@ int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_n
         // T = M Kx and the predictive means of this cluster are still in the scoring scratch
         const double *Tc = nullptr, *muc = nullptr;
         locate_T(h, ch.slot_of_id[chosen_id], &Tc, &muc);
+        if (!Tc && ch.win.in_step) {
+          // the cached T under this cluster is stale (its scores were corrected by a rank-n formula): one product
+          // against this cluster alone, queued behind the update that made it stale
+          int32_t sl = ch.slot_of_id[chosen_id];
+          ScorePlan pl1;
+          TRY(score_device(h, 1, ni, h->d_off + n, h->d_px + c0, h->d_py + c0, 1, &sl, -1, nullptr, nullptr, nullptr, nullptr,
+                           nullptr, true, &pl1));
+          Tc = pl1.T;
+          muc = pl1.mu;
+        }
         if (Tc) {
           TRY(append_core(h, c, (int)ni, h->d_px + c0, h->d_py + c0, Tc, muc));
           c.hx.insert(c.hx.end(), h->h_x.begin() + c0, h->h_x.begin() + c0 + ni);
@@ -531,7 +589,7 @@ int env_int(const char* name, int dflt) {
 
 int window_cols(const Chain& ch) {
   const int env = env_int("MOGP_LOOKAHEAD", -1);  // (read per sweep: tests and tuning runs toggle it)
-  int v = env >= 0 ? env : (ch.cfg.lookahead == 0 ? 32 : ch.cfg.lookahead);
+  int v = env >= 0 ? env : (ch.cfg.lookahead == 0 ? 48 : ch.cfg.lookahead);
   return v <= 0 ? 0 : std::min(v, 64);
 }
 int pipeline_depth() {  // 2: the next batch's pass overlaps the current batch's moves; 1: one batch at a time
@@ -539,15 +597,21 @@ int pipeline_depth() {  // 2: the next batch's pass overlaps the current batch's
   return env >= 2 ? 2 : 1;
 }
 
+void win_size_slots(Chain::Window& w, size_t n) {
+  if (w.slot_upto.size() >= n) return;
+  w.slot_upto.resize(n, 0);
+  w.slot_T_ok.resize(n, 0);
+  w.slot_alg.resize(n, 0);
+  w.slot_epoch.resize(n, 0);
+}
+
 // The cluster in `slot` changed (rows appended / deleted, freed, created): cached scores under it are stale.
 void win_invalidate(Chain& ch, int32_t slot) {
   Chain::Window& w = ch.win;
   if (!w.open || slot < 0) return;
-  if ((size_t)slot >= w.slot_ok.size()) {
-    w.slot_ok.resize(slot + 1, 0);
-    w.slot_epoch.resize(slot + 1, 0);
-  }
-  w.slot_ok[slot] = 0;
+  win_size_slots(w, (size_t)slot + 1);
+  w.slot_upto[slot] = 0;
+  w.slot_T_ok[slot] = 0;
   w.slot_epoch[slot] += 1;
   for (int64_t v = w.cur; v < w.end_launched; ++v) {
     const int32_t id = (w.pat[v] == ch.pending) ? ch.pending_prev : ch.z[w.pat[v]];
@@ -556,8 +620,9 @@ void win_invalidate(Chain& ch, int32_t slot) {
 }
 void win_invalidate_all(Chain& ch) {
   Chain::Window& w = ch.win;
-  for (size_t s = 0; s < w.slot_ok.size(); ++s) {
-    w.slot_ok[s] = 0;
+  for (size_t s = 0; s < w.slot_upto.size(); ++s) {
+    w.slot_upto[s] = 0;
+    w.slot_T_ok[s] = 0;
     w.slot_epoch[s] += 1;
   }
   for (int64_t v = w.cur; v < w.end_launched; ++v) w.own_ok[v] = 0;
@@ -636,8 +701,11 @@ int win_prepare(mogp_engine* h, int64_t n_steps, const int64_t* order, const dou
   const int64_t R = w.col0[n_steps];
   w.cur = w.end_launched = 0;
   w.e.assign(n_steps, std::vector<Chain::WinEntry>());
-  w.slot_ok.assign(h->cl.size(), 0);
+  w.slot_upto.assign(h->cl.size(), 0);
+  w.slot_T_ok.assign(h->cl.size(), 0);
+  w.slot_alg.assign(h->cl.size(), 0);
   w.slot_epoch.assign(h->cl.size(), 0);
+  w.batch_end = 0;
   w.new_ll.assign(n_steps, 0.0);
   w.own_ll.assign(n_steps, 0.0);
   w.own_mu.assign(n_steps, 0.0);
@@ -707,10 +775,7 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   b.slots.clear();
   b.epoch.clear();
   b.mpad.clear();
-  if (w.slot_ok.size() < h->cl.size()) {
-    w.slot_ok.resize(h->cl.size(), 0);
-    w.slot_epoch.resize(h->cl.size(), 0);
-  }
+  win_size_slots(w, h->cl.size());
   for (size_t k = 0; k < ch.Nk.size(); ++k)
     if (ch.Nk[k] > 0 && ch.slot_of_id[k] >= 0) {
       const int32_t slot = ch.slot_of_id[k];
@@ -733,6 +798,7 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   double* d_own = d_new + cnt;
   for (int64_t v = s0; v < s0 + cnt; ++v) w.e[v].assign(h->cl.size(), Chain::WinEntry());
   const int64_t Rtot = w.col0[w.n], cb = w.col0[s0], R = w.col0[s0 + cnt] - cb;
+  if (h->side_pending) join_side(h);
   CK(h, cudaEventRecord(h->ev_fork, h->main_stream));
   CK(h, cudaStreamWaitEvent(h->ahead, h->ev_fork, 0));
   CK(h, cudaStreamWaitEvent(h->ahead2, h->ev_fork, 0));
@@ -752,6 +818,7 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   CK(h, cudaEventRecord(h->ev_ahead2, h->ahead2));
   h->stream = h->ahead;
   b.pl = ScorePlan();
+  bf.res.zigzag = pipeline_depth() >= 2 ? env_int("MOGP_ZIGZAG", 0) : 0;
   if (ns > 0)
     TRY(score_device(h, cnt, R, h->d_woff + s0, h->d_wq + cb, h->d_wq + Rtot + cb, ns, b.slots.data(), thr_index, d_score, d_mu,
                      nullptr, nullptr, nullptr, true, &b.pl, &bf.res));
@@ -791,8 +858,10 @@ int batch_absorb(mogp_engine* h, int bi) {
         e.muthr = hm[v * ns + si];
         e.T = b.pl.T + kx_off + (w.col0[b.s0 + v] - cb) * mpad;
         e.mu = b.pl.mu + (int64_t)si * b.pl.Rpad + (w.col0[b.s0 + v] - cb);
+        e.ss = b.pl.ss + (int64_t)si * b.pl.Rpad + (w.col0[b.s0 + v] - cb);
       }
-      w.slot_ok[slot] = 1;
+      w.slot_upto[slot] = b.s0 + cnt;
+      w.slot_T_ok[slot] = 1;
     }
     kx_off += b.pl.Rpad * mpad;
   }
@@ -808,7 +877,7 @@ int batch_absorb(mogp_engine* h, int bi) {
   return MOGP_OK;
 }
 
-// Cache entries of positions [v0, end_launched) under `slots`, from a re-scoring pass.
+// Cache entries of positions [v0, batch_end) under `slots`, from a re-scoring pass.
 void win_store(mogp_engine* h, int64_t v0, const std::vector<int32_t>& slots, const ScorePlan& pl, const double* host_score,
                const double* host_mu) {
   Chain::Window& w = h->chain.win;
@@ -818,34 +887,35 @@ void win_store(mogp_engine* h, int64_t v0, const std::vector<int32_t>& slots, co
   for (int si = 0; si < ns; ++si) {
     const int32_t slot = slots[si];
     const int64_t mpad = round_up(h->cl[slot].m, TB);
-    for (int64_t v = v0; v < w.end_launched; ++v) {
+    for (int64_t v = v0; v < w.batch_end; ++v) {
       if ((size_t)slot >= w.e[v].size()) w.e[v].resize(h->cl.size());
       Chain::WinEntry& e = w.e[v][slot];
       e.score = host_score[(v - v0) * ns + si];
       e.muthr = host_mu[(v - v0) * ns + si];
       e.T = pl.T + kx_off + (w.col0[v] - cbase) * mpad;
       e.mu = pl.mu + (int64_t)si * pl.Rpad + (w.col0[v] - cbase);
+      e.ss = pl.ss + (int64_t)si * pl.Rpad + (w.col0[v] - cbase);
     }
-    w.slot_ok[slot] = 1;
+    w.slot_upto[slot] = w.batch_end;
+    w.slot_T_ok[slot] = 1;
+    w.slot_alg[slot] = 0;
     kx_off += pl.Rpad * mpad;
   }
 }
 
-// Bring the cache up to date for the current patient and, in the same launches, for every launched position
-// ahead: re-score against the clusters that changed since they were scored, refresh stale own-cluster scores.
+// Bring the cache up to date for the current patient and, in the same launches, for the rest of its batch: re-score
+// against the clusters whose cached scores are stale, refresh stale own-cluster scores.  (The positions of the next
+// batch, whose pass may be in flight, are brought up to date when their batch starts.)
 int win_ensure(mogp_engine* h, int32_t own_id, ScoreRes* arena) {
   Chain& ch = h->chain;
   Chain::Window& w = ch.win;
-  const int64_t cur = w.cur, end = w.end_launched;
-  if (w.slot_ok.size() < h->cl.size()) {
-    w.slot_ok.resize(h->cl.size(), 0);
-    w.slot_epoch.resize(h->cl.size(), 0);
-  }
+  const int64_t cur = w.cur, end = w.batch_end;
+  win_size_slots(w, h->cl.size());
   std::vector<int32_t> bad;
   for (size_t k = 0; k < ch.Nk.size(); ++k) {
     if (ch.Nk[k] <= 0 || (int32_t)k == own_id) continue;
     const int32_t slot = ch.slot_of_id[k];
-    if (!w.slot_ok[slot]) bad.push_back(slot);
+    if (w.slot_upto[slot] <= cur) bad.push_back(slot);
   }
   const bool need_own = own_id >= 0 && !w.own_ok[cur];
   if (bad.empty() && !need_own) return MOGP_OK;
@@ -935,17 +1005,113 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
   if (rc != MOGP_OK) FAIL(h, rc, "probabilities contain NaN (patient %lld)", (long long)n);
   const int32_t chosen = ch.act_ids[idx];
   const bool stays = ch.pending_lazy && chosen == prev;
+  // A move changes two clusters.  The scores of the patients still ahead in this batch under them are corrected by
+  // rank-n formulas from what the pass left on the device (k_alg_leave / k_alg_join) and read back at once; the
+  // O(m^2) updates of the two factors are queued behind and nobody waits for them.  One correction per cluster and
+  // batch: a second change, a cluster without current T, a new or emptied cluster go the long way (re-scoring).
+  const int64_t npos = w.batch_end - (w.cur + 1);
+  const bool alg_on = !stays && npos > 0 && npos <= OWN_BATCH && ch.pending_lazy && env_int("MOGP_RANK_RESCORE", 1) != 0;
+  auto alg_ok = [&](int32_t slot) {
+    return slot >= 0 && slot < (int32_t)w.slot_upto.size() && w.slot_upto[slot] >= w.batch_end && w.slot_T_ok[slot] &&
+           !w.slot_alg[slot];
+  };
+  auto fill_pos = [&](AlgJobs& J, int32_t slot) {
+    for (int64_t q = 0; q < npos; ++q) {
+      const int64_t v = w.cur + 1 + q;
+      const Chain::WinEntry& e = w.e[v][slot];
+      AlgPos& P = J.pos[q];
+      P.T = e.T;
+      P.ss = e.ss;
+      P.mu = e.mu;
+      P.stride = round_up(h->cl[slot].m, TB);
+      P.x = h->d_wq + w.col0[v];
+      P.y = h->d_wq + w.col0[w.n] + w.col0[v];
+      P.ncols = (int)(w.col0[v + 1] - w.col0[v]);
+    }
+    J.th = make_theta(h->cl[slot]);
+    J.thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
+  };
+  const int64_t c0n = h->h_off[n], nin = h->h_off[n + 1] - c0n;
+  int32_t a_slot = -1, b_slot = -1;
+  bool a_alg = false;
+  AlgHook hook;
+  if (alg_on) {
+    if (ch.slot_of_id[prev] >= 0 && alg_ok(ch.slot_of_id[prev])) {  // leave side, from the factor as it is now
+      a_slot = ch.slot_of_id[prev];
+      Cluster& ca = h->cl[a_slot];
+      const int64_t p = member_offset(h, ca, n, nullptr);
+      if (p >= 0) {
+        AlgJobs J{};
+        fill_pos(J, a_slot);
+        J.out = h->d_alg;
+        J.M = ca.M;
+        J.alpha = ca.alpha();
+        J.ld = ca.cap;
+        J.p = (int)p;
+        J.n = (int)nin;
+        J.m = (int)ca.m;
+        const int ntiles = (int)((ca.m - p + TB - 1) / TB);
+        TRY(ensure(h, &h->d_algw, &h->algw_elems, (int64_t)npos * ntiles * ALG_ENTRIES));
+        k_alg_leave_part<<<dim3((unsigned)ntiles, (unsigned)npos), 256, 0, h->quick2>>>(J, h->d_algw);
+        LAUNCHED(h);
+        k_alg_leave_fin<<<(unsigned)npos, 256, 0, h->quick2>>>(J, h->d_algw, ntiles);
+        LAUNCHED(h);
+        CK(h, cudaEventRecord(h->ev_q2, h->quick2));
+        a_alg = true;
+      }
+    }
+    if (chosen < n_ids && alg_ok(ch.slot_of_id[chosen])) {  // join side: launched by append_core once Ls, z_B exist
+      b_slot = ch.slot_of_id[chosen];
+      const Chain::WinEntry& en = w.e[w.cur][b_slot];
+      fill_pos(hook.jobs, b_slot);
+      hook.jobs.out = h->d_alg + 2 * OWN_BATCH;
+      hook.jobs.n = (int)nin;
+      hook.jobs.Tn = en.T;
+      hook.jobs.stride_n = round_up(h->cl[b_slot].m, TB);
+      hook.jobs.xn = h->d_px + c0n;
+      hook.npos = (int)npos;
+      h->alg_hook = &hook;
+    }
+  }
   int32_t is_new = 0;
   {
     PhaseTimer pt(&ch.t_commit);
     w.in_step = true;
     rc = chain_commit(h, chosen, a_draw, &is_new);
     w.in_step = false;
+    h->alg_hook = nullptr;
     if (rc != MOGP_OK) return rc;
   }
   if (!stays) {
-    if (ch.slot_of_id[prev] >= 0) win_invalidate(ch, ch.slot_of_id[prev]);
-    win_invalidate(ch, ch.slot_of_id[chosen]);
+    const bool b_alg = hook.fired;
+    if (a_alg || b_alg) {
+      PhaseTimer pt(&ch.t_alg);
+      if (b_alg) CK(h, cudaStreamWaitEvent(h->quick, h->ev_alg, 0));
+      if (a_alg) CK(h, cudaStreamWaitEvent(h->quick, h->ev_q2, 0));
+      CK(h, cudaMemcpyAsync(h->h_alg, h->d_alg, sizeof(double) * 4 * OWN_BATCH, cudaMemcpyDeviceToHost, h->quick));
+      CK(h, cudaStreamSynchronize(h->quick));
+      h->bytes_d2h += (int64_t)sizeof(double) * 4 * OWN_BATCH;
+      ch.win_algebra += 1;
+    }
+    auto corrected = [&](int32_t slot, const double* out) {  // scores current, T stale, next batch's pass dirty
+      for (int64_t q = 0; q < npos; ++q) {
+        Chain::WinEntry& e = w.e[w.cur + 1 + q][slot];
+        e.score = out[2 * q];
+        e.muthr = out[2 * q + 1];
+      }
+      w.slot_T_ok[slot] = 0;
+      w.slot_alg[slot] = 1;
+      w.slot_epoch[slot] += 1;
+      for (int64_t v = w.cur + 1; v < w.end_launched; ++v) {
+        const int32_t id = ch.z[w.pat[v]];
+        if (id >= 0 && ch.slot_of_id[id] == slot) w.own_ok[v] = 0;
+      }
+    };
+    const int32_t slot_prev = ch.slot_of_id[prev];
+    if (a_alg && slot_prev == a_slot) corrected(a_slot, h->h_alg);
+    else if (slot_prev >= 0) win_invalidate(ch, slot_prev);
+    if (b_alg && ch.slot_of_id[chosen] == b_slot) corrected(b_slot, h->h_alg + 2 * OWN_BATCH);
+    else win_invalidate(ch, ch.slot_of_id[chosen]);
   }
   if (chosen_out) *chosen_out = chosen;
   std::vector<Chain::WinEntry>().swap(w.e[w.cur]);
@@ -984,22 +1150,28 @@ int sweep_pipelined(mogp_engine* h, int64_t n_steps, const int64_t* order, const
       TRY(batch_absorb(h, (int)(jb & 1)));
     }
     w.cur = pos;
+    w.batch_end = pos + B.cnt;
+    std::fill(w.slot_alg.begin(), w.slot_alg.end(), 0);
     // re-scoring blocks written two batches ago are no longer referenced
     ScoreRes& arena = h->res_bump[jb & 1];
     arena.scr_used = 0;
     for (double* p : arena.retired) cudaFree(p);
     arena.retired.clear();
     have_next = false;
-    if (depth >= 2) {
-      const int64_t np = pos + B.cnt;
-      const int64_t cnt2 = np < n_steps ? batch_form(h, np, max_cols) : 0;
-      if (cnt2 > 0) {
-        TRY(batch_launch(h, (int)((jb + 1) & 1), np, cnt2));
-        have_next = true;
-      }
-    }
     const int64_t bcnt = B.cnt;
+    const int launch_after = env_int("MOGP_LAUNCH_AFTER", 0);  // steps of this batch before the next pass is launched
     for (int64_t q = 0; q < bcnt; ++q) {
+      // The next batch's pass goes out after the first step: that step starts by re-scoring this batch against the
+      // clusters the previous batch changed (waiting for their updates), which is quicker on a GPU that is not
+      // filling up with the next pass at the same moment.
+      if (depth >= 2 && !have_next && q == std::min<int64_t>(launch_after, bcnt - 1)) {
+        const int64_t np = pos + bcnt;
+        const int64_t cnt2 = np < n_steps ? batch_form(h, np, max_cols) : 0;
+        if (cnt2 > 0) {
+          TRY(batch_launch(h, (int)((jb + 1) & 1), np, cnt2));
+          have_next = true;
+        }
+      }
       int32_t chosen = -1;
       TRY(win_step(h, a_draw ? a_draw[pos + q] : 0.0, u[pos + q], &chosen, &arena));
       if (chosen_ids) chosen_ids[pos + q] = chosen;
@@ -1134,6 +1306,7 @@ int mogp_chain_sweep(mogp_engine* h, int64_t n_steps, const int64_t* order, cons
   if (max_cols >= 2 && n_steps > 0 && order_is_duplicate_free(h->chain, n_steps, order)) {
     int rc = sweep_pipelined(h, n_steps, order, a_draw, u, chosen_ids, &mm, max_cols);
     // whatever happened, nothing of the pipeline stays in flight or cached
+    join_side(h);
     cudaStreamSynchronize(h->ahead);
     cudaStreamSynchronize(h->ahead2);
     h->chain.win.open = h->chain.win.in_step = false;

@@ -46,6 +46,7 @@ struct Cluster {
   double lml = 0.0, quad = 0.0, logdet = 0.0;
   double grad[4] = {0, 0, 0, 0};
   bool grad_valid = false;
+  bool side_busy = false;         // a row deletion of this cluster may still be running on the side stream
   bool stat_on_device = false;    // lml / quad / logdet of the last rank update not fetched yet
   bool lml_dirty = false;         // ... and not even reduced yet (k_lml runs when somebody asks)
   double* x() const { return vec; }
@@ -65,7 +66,7 @@ struct ScorePlan {
   int max_nb = 0;
   int64_t kx_total = 0, part_total = 0;
   int max_rblk = 0;  // row blocks (of KX_ROWS) of the largest slot
-  double *kxT = nullptr, *part = nullptr, *mupart = nullptr, *mu = nullptr, *T = nullptr;
+  double *kxT = nullptr, *part = nullptr, *mupart = nullptr, *mu = nullptr, *T = nullptr, *ss = nullptr;
 };
 
 struct Chain {
@@ -91,7 +92,8 @@ struct Chain {
   struct WinEntry {
     double score = 0.0, muthr = 0.0;
     const double* T = nullptr;   // the patient's columns of T = M Kx under that slot (stride = mpad when scored)
-    const double* mu = nullptr;  // ... and their predictive means
+    const double* mu = nullptr;  // ... their predictive means
+    const double* ss = nullptr;  // ... and their k*^T Ky^-1 k* (device, as mu)
   };
   struct Batch {                   // consecutive sweep positions scored by one pass
     int64_t s0 = 0, cnt = 0;
@@ -111,15 +113,18 @@ struct Chain {
     int64_t cur = 0;               // position being processed
     int64_t end_launched = 0;      // positions below have a pass launched (their cache entries exist or are on the way)
     std::vector<std::vector<WinEntry>> e;  // [position][slot]
-    std::vector<char> slot_ok;     // [slot]: entries current for every position in [cur, end_launched)
+    int64_t batch_end = 0;         // end of the batch being processed
+    std::vector<int64_t> slot_upto;   // [slot]: the cached SCORES are current for the positions in [cur, slot_upto)
+    std::vector<char> slot_T_ok;      // [slot]: ... and so are the cached T / mu / ss on the device
+    std::vector<char> slot_alg;       // [slot]: the slot took a rank-n score correction in this batch (one per batch)
     std::vector<int64_t> slot_epoch;  // [slot]: incremented whenever the cluster in that slot changes
     std::vector<double> new_ll;    // [position]
     std::vector<double> own_ll, own_mu, own_flag;  // [position] leave-block-out score under the patient's own cluster
     std::vector<char> own_ok;
     Batch b[2];
   } win;
-  int64_t win_passes = 0, win_rescores = 0, win_patients = 0;  // accounting
-  double t_open = 0.0, t_ensure = 0.0, t_commit = 0.0;         // host seconds spent in the three phases of windowed steps
+  int64_t win_passes = 0, win_rescores = 0, win_patients = 0, win_algebra = 0;  // accounting
+  double t_open = 0.0, t_ensure = 0.0, t_commit = 0.0, t_alg = 0.0;         // host seconds spent in the three phases of windowed steps
 };
 
 // Device scratch + slot-view staging of a scoring pass.  Several passes can be in flight (the next batch's pass on the
@@ -131,6 +136,7 @@ struct ScoreRes {
   std::vector<double*> retired;    // bump blocks outgrown while still referenced
   SlotView* d_slots = nullptr;     // views of launches with more than SLOT_PACK slots
   int64_t slots_cap = 0;
+  int zigzag = 0;                  // launch order of the wide kernel's row blocks (ChunkPlan::zigzag)
   SlotView* h_slots = nullptr;     // own pinned staging of those views (null: the engine's upload staging)
   int64_t hslots_cap = 0;
 };
@@ -147,6 +153,18 @@ struct BatchBuf {
 
 }  // namespace
 
+// Small append workspaces: up to AP_RING appends may be queued on the main stream while the next one's Gram / Ls are
+// already computed on the quick stream (a batch holds at most 16 patients, and every batch start waits for the main
+// stream).  A slot serves clusters of up to AP_RING_NBLK * 256 points; larger ones use the shared workspace.
+constexpr int AP_RING = 20, AP_RING_NBLK = 256;
+constexpr int64_t AP_RING_SLOT = NP * NP + NP + (int64_t)AP_RING_NBLK * NG;
+
+// The join-side score correction a commit launches right after k_append_small (append_core), see update.cuh.
+struct AlgHook {
+  AlgJobs jobs;
+  int npos = 0, ntiles = 0;
+  bool fired = false;
+};
 struct mogp_engine {
   int device = 0;
   cudaStream_t stream = nullptr;   // the stream every helper launches on (normally `main_stream`)
@@ -154,6 +172,7 @@ struct mogp_engine {
   cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_block = nullptr;
   bool blocking_sync = false;
   std::vector<std::pair<int64_t, double*>> pending_release;  // buffers the side stream may still be reading
+  bool side_pending = false;       // some cluster has side_busy set
   double* d_apart2 = nullptr;  // alpha partials of the side stream
   int64_t apart2_elems = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -179,6 +198,18 @@ struct mogp_engine {
   BatchBuf bb[2];           // the two batches in flight
   cudaStream_t ahead = nullptr, ahead2 = nullptr;  // low priority: the next batch's pass / its own-cluster scores
   cudaEvent_t ev_fork = nullptr, ev_ahead2 = nullptr;
+  cudaStream_t quick = nullptr, quick2 = nullptr;  // high priority: rank-n score corrections after a move (join / leave side)
+  cudaEvent_t ev_q2 = nullptr;
+  double* d_algw2 = nullptr;      // partial sums of the join-side correction
+  int64_t algw2_elems = 0;
+  cudaEvent_t ev_alg = nullptr, ev_apq = nullptr;
+  double* d_algw = nullptr;       // partial sums of the leave-side correction
+  int64_t algw_elems = 0;
+  double* d_apring = nullptr;     // ring of small append workspaces (Li | z_B | Gram partials): several appends in flight
+  int apring_next = 0;
+  double* d_alg = nullptr;        // their outputs [2 slots][OWN_BATCH positions][2]
+  double* h_alg = nullptr;        // ... pinned
+  AlgHook* alg_hook = nullptr;  // set while a commit should launch the append-side correction (append_core)
   double* d_upd2 = nullptr;  // row-deletion workspace of the look-ahead streams (own-cluster scores)
   int64_t upd2_elems = 0;
   double *d_own1 = nullptr, *d_own2 = nullptr;  // Gram partials of the batched own-cluster scores (main-side / look-ahead)
@@ -220,8 +251,12 @@ struct mogp_engine {
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop), recycled
   size_t prof_used = 0;
-  double prof_ms = 0.0, prof_bytes = 0.0, prof_flops = 0.0, prof_pairs = 0.0;
-  int64_t prof_launches = 0;
+  // class 0: whole passes (a batch or a patient against every active cluster, batch prediction); class 1: the
+  // re-scoring passes of the look-ahead pipeline (one or two clusters, latency bound) - kept apart in the accounts
+  std::vector<char> prof_tag;
+  int prof_cls = 0;
+  double prof_ms_c[2] = {0.0, 0.0}, prof_bytes_c[2] = {0.0, 0.0}, prof_flops_c[2] = {0.0, 0.0}, prof_pairs = 0.0;
+  int64_t prof_launches_c[2] = {0, 0};
 };
 
 namespace {
@@ -317,6 +352,15 @@ void join_side(mogp_engine* h) {
   cudaStreamWaitEvent(h->main_stream, h->ev_side, 0);
   for (auto& pb : h->pending_release) pool_put(h, pb.first, pb.second);
   h->pending_release.clear();
+  if (h->side_pending) {
+    for (auto& c : h->cl) c.side_busy = false;
+    h->side_pending = false;
+  }
+}
+// Before main-stream work on cluster c: a deletion of its rows queued on the side stream (look-ahead pipeline: the
+// main stream does not wait for those by default) must be ordered first.
+inline void order_after_side(mogp_engine* h, const Cluster& c) {
+  if (c.side_busy) join_side(h);
 }
 
 // A fresh range of the upload staging buffer; valid until the next sync_stream().
@@ -364,6 +408,7 @@ int check_slot(mogp_engine* h, int32_t slot) {
   if (!h) return MOGP_EINVAL;
   cudaSetDevice(h->device);  // every cluster entry point comes through here; callers may be on any host thread
   if (slot < 0 || slot >= (int32_t)h->cl.size() || !h->cl[slot].used) FAIL(h, MOGP_EINVAL, "bad cluster slot %d", slot);
+  if (h->cl[slot].side_busy && h->stream == h->main_stream) join_side(h);
   return MOGP_OK;
 }
 
@@ -602,7 +647,7 @@ void prof_drain(mogp_engine* h) {
   cudaEventSynchronize(h->prof_ev[h->prof_used - 1]);
   for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) h->prof_ms += ms;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) h->prof_ms_c[(int)h->prof_tag[i]] += ms;
   }
   h->prof_used = 0;
 }
@@ -613,7 +658,9 @@ void prof_mark(mogp_engine* h, bool stop) {
     cudaEvent_t e;
     cudaEventCreate(&e);
     h->prof_ev.push_back(e);
+    h->prof_tag.push_back(0);
   }
+  h->prof_tag[h->prof_used] = (char)h->prof_cls;
   cudaEventRecord(h->prof_ev[h->prof_used++], h->stream);
 }
 
@@ -656,6 +703,7 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
                  double* mu_thr_dev, double* col_mean, double* col_var, double* col_lpd, bool keep_T, ScorePlan* plan_out,
                  ScoreRes* res_in = nullptr) {
   ScoreRes& res = res_in ? *res_in : h->res_main;
+  h->prof_cls = res.bump ? 1 : 0;
   if (n_slots <= 0 || n_pat <= 0 || R <= 0) return MOGP_OK;
   ScorePlan pl;
   pl.R = R;
@@ -706,12 +754,12 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
       // One launch scores n_pat patients against the cluster: the factor term is charged ONCE per launch (what the
       // launch must move), the per-pair terms per patient; prof_pairs counts the (patient, cluster) units.
       const double m = (double)c.m;
-      h->prof_bytes += 8.0 * (m * m / 2 + 3 * m) + 8.0 * (double)n_pat + 16.0 * (double)R;
-      h->prof_flops += (double)R * m * (m + 10.0);
-      h->prof_pairs += (double)n_pat;
+      h->prof_bytes_c[h->prof_cls] += 8.0 * (m * m / 2 + 3 * m) + 8.0 * (double)n_pat + 16.0 * (double)R;
+      h->prof_flops_c[h->prof_cls] += (double)R * m * (m + 10.0);
+      if (h->prof_cls == 0) h->prof_pairs += (double)n_pat;
     }
   }
-  if (h->prof_on) h->prof_launches += 1;
+  if (h->prof_on) h->prof_launches_c[h->prof_cls] += 1;
   TRY(ensure(h, &res.d_slots, &res.slots_cap, n_slots));
   const int64_t mu_total = (int64_t)n_slots * pl.Rpad, mupart_total = mu_total * pl.max_rblk;
   // few (slot, row block) items and one column tile: split the contraction across CTAs (see ChunkPlan)
@@ -720,8 +768,9 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
     cp.kc = 8;
     cp.maxch = (pl.max_nb + cp.kc - 1) / cp.kc;
   }
+  cp.zigzag = cp.kc == 0 ? res.zigzag : 0;
   const int64_t tpart_total = cp.kc > 0 ? pl.kx_total * cp.maxch : 0;
-  const int64_t need = pl.kx_total * (keep_T ? 2 : 1) + pl.part_total + mu_total + mupart_total + tpart_total;
+  const int64_t need = pl.kx_total * (keep_T ? 2 : 1) + pl.part_total + 2 * mu_total + mupart_total + tpart_total;
   if (res.bump) {
     if (res.scr_used + need > res.scr_elems) {  // outgrown: earlier blocks are still referenced by the pipeline
       if (res.scr) res.retired.push_back(res.scr);
@@ -742,6 +791,7 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   pl.mupart = pl.mu + mu_total;
   pl.T = keep_T ? pl.mupart + mupart_total : nullptr;
   cp.Tpart = cp.kc > 0 ? pl.mupart + mupart_total + (keep_T ? pl.kx_total : 0) : nullptr;
+  pl.ss = pl.mupart + mupart_total + (keep_T ? pl.kx_total : 0) + tpart_total;
   if (!use_pack) {
     CK(h, cudaMemcpyAsync(res.d_slots, hv, sizeof(SlotView) * (size_t)n_slots, cudaMemcpyHostToDevice, h->stream));
     h->bytes_h2d += (int64_t)sizeof(SlotView) * n_slots;
@@ -768,7 +818,7 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   k_score_epi<<<(unsigned)((pairs + 7) / 8), 256, 0, h->stream>>>(res.d_slots, pack, use_pack, n_slots, off_dev, n_pat, xs_dev, ys_dev,
                                                                      (int)pl.Rpad, pl.part, pl.mupart, pl.max_rblk, pl.mu,
                                                                      thr_index, score_dev,
-                                                                     mu_thr_dev, col_mean, col_var, col_lpd);
+                                                                     mu_thr_dev, col_mean, col_var, col_lpd, pl.ss);
   LAUNCHED(h);
   CK(h, cudaGetLastError());
   if (plan_out) *plan_out = pl;
@@ -843,6 +893,14 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
       cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
       cudaStreamCreateWithPriority(&h->ahead, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
       cudaStreamCreateWithPriority(&h->ahead2, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->quick, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->quick2, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_q2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_alg, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_apq, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMalloc((void**)&h->d_apring, sizeof(double) * AP_RING * AP_RING_SLOT) != cudaSuccess ||
+      cudaMalloc((void**)&h->d_alg, sizeof(double) * 4 * 16) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_alg, sizeof(double) * 4 * 16) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_ahead2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->bb[0].done, cudaEventDisableTiming) != cudaSuccess ||
@@ -896,6 +954,13 @@ void mogp_engine_destroy(mogp_engine* h) {
   cudaFree(h->d_upd2);
   cudaFree(h->d_own1);
   cudaFree(h->d_own2);
+  if (h->quick) cudaStreamDestroy(h->quick);
+  if (h->quick2) cudaStreamDestroy(h->quick2);
+  cudaFree(h->d_algw2);
+  cudaFree(h->d_alg);
+  cudaFree(h->d_algw);
+  cudaFree(h->d_apring);
+  if (h->h_alg) cudaFreeHost(h->h_alg);
   if (h->ahead) cudaStreamDestroy(h->ahead);
   if (h->ahead2) cudaStreamDestroy(h->ahead2);
   cudaFree(h->d_wq);
@@ -1017,22 +1082,29 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
   if (!h) return MOGP_EINVAL;
   cudaSetDevice(h->device);  // entry points may be called from any host thread
   prof_drain(h);
-  if (launches) *launches = h->prof_launches;
-  if (ms) *ms = h->prof_ms;
-  if (alg_bytes) *alg_bytes = h->prof_bytes;
-  if (alg_flops) *alg_flops = h->prof_flops;
+  if (launches) *launches = h->prof_launches_c[0];
+  if (ms) *ms = h->prof_ms_c[0];
+  if (alg_bytes) *alg_bytes = h->prof_bytes_c[0];
+  if (alg_flops) *alg_flops = h->prof_flops_c[0];
   if (reset) {
-    h->prof_launches = 0;
-    h->prof_ms = h->prof_bytes = h->prof_flops = h->prof_pairs = 0.0;
+    // (the re-scoring class is read through mogp_chain_counters before the reset)
+    for (int c = 0; c < 2; ++c) {
+      h->prof_launches_c[c] = 0;
+      h->prof_ms_c[c] = h->prof_bytes_c[c] = h->prof_flops_c[c] = 0.0;
+    }
+    h->prof_pairs = 0.0;
   }
   return MOGP_OK;
 }
 
 int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out) {
   if (!h || !out) return MOGP_EINVAL;
-  const double v[7] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
-                       h->chain.t_open, h->chain.t_ensure, h->chain.t_commit};
-  for (int i = 0; i < n_out && i < 7; ++i) out[i] = v[i];
+  prof_drain(h);
+  const double v[13] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
+                        h->chain.t_open, h->chain.t_ensure, h->chain.t_commit,
+                        (double)h->prof_launches_c[1], h->prof_ms_c[1], h->prof_bytes_c[1], h->prof_flops_c[1],
+                        (double)h->chain.win_algebra, h->chain.t_alg};
+  for (int i = 0; i < n_out && i < 13; ++i) out[i] = v[i];
   return MOGP_OK;
 }
 

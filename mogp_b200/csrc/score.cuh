@@ -81,6 +81,10 @@ struct ChunkPlan {
   int kc = 0;        // tiles per CTA (0 = whole row block per CTA, epilogue in the same kernel)
   int maxch = 1;     // chunks of the longest row block
   double* Tpart = nullptr;  // [slot: kx_off * maxch][chunk][col][mpad]
+  // 0: longest row blocks first (best balance when the pass has the GPU to itself).  1: long and short row blocks
+  // alternate in launch order, so that CTAs retire all the time instead of in waves of equal length - the pass of
+  // the next batch runs beside short high-priority kernels that need an SM NOW (look-ahead pipeline)
+  int zigzag = 0;
 };
 
 __global__ void __launch_bounds__(256) k_score_reduce(SLOT_ARGS, int Rpad, const ChunkPlan cp, double* __restrict__ part,
@@ -394,8 +398,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_score_wide(SLOT_ARGS, const
   const int nb = sv.mpad / TB;
   const int zi = cp.kc > 0 ? (int)blockIdx.z / cp.maxch : (int)blockIdx.z;
   const int chunk = cp.kc > 0 ? (int)blockIdx.z % cp.maxch : 0;
-  const int rb = nb - 1 - zi;  // heavy row blocks first, across the slots
-  if (rb < 0) return;
+  if (zi >= nb) return;
+  const int rb = cp.zigzag ? ((zi & 1) ? (zi >> 1) : nb - 1 - (zi >> 1)) : nb - 1 - zi;  // heavy row blocks first, across the slots
   wide_item<NS>(sv, rb, chunk, blockIdx.x * BN, kxT, Rpad, part, Tout, cp, smem, red);
 }
 
@@ -411,7 +415,7 @@ __global__ void __launch_bounds__(256) k_score_epi(SLOT_ARGS, int n_slots,
                                                    double* __restrict__ mu, int thr_index,
                                                    double* __restrict__ score, double* __restrict__ mu_thr,
                                                    double* __restrict__ col_mean, double* __restrict__ col_var,
-                                                   double* __restrict__ col_lpd) {
+                                                   double* __restrict__ col_lpd, double* __restrict__ col_ss) {
   const int64_t gid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (gid >= n_pat * n_slots) return;
@@ -432,6 +436,7 @@ __global__ void __launch_bounds__(256) k_score_epi(SLOT_ARGS, int n_slots,
     for (int rb = 0; rb < nrb; ++rb) m += mupart[((int64_t)c * max_rblk + rb) * Rpad + col];
     if (sv.th.mean_func) m += xs[col] * (-sv.th.A);  // + m(x*) = -A x*  (neg_linear.py:22-23)
     mu[(int64_t)c * Rpad + col] = m;
+    if (col_ss) col_ss[(int64_t)c * Rpad + col] = ss;  // k*^T Ky^-1 k* before the clip (rank-n corrections start here)
     const double d = ys ? ys[col] - m : 0.0;
     const double lpd = -0.5 * LOG_2_PI - 0.5 * log(vn) - 0.5 * (d * d) / vn;
     total += lpd;

@@ -185,6 +185,186 @@ __global__ void __launch_bounds__(256) k_own_final_batch(const __grid_constant__
   own_final_body(jb.alpha, jb.yB, jb.g, jb.w, jb.nT, jb.th, thr_index, jb.out);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Rank-n corrections of CACHED scores (look-ahead pipeline, chain.inl).  When a patient's block B leaves cluster a,
+// or joins cluster b, the scores of the patients still ahead in the batch under a / b follow from what the scoring
+// pass left on the device for them - T_q = M k_q, s_q = |T_q|^2 = k_q^T Ky^-1 k_q, mu_q - in O(m n) per visit,
+// without waiting for the O(m^2) update of the factor itself (which proceeds on its own streams):
+//   leave:  u = (M^T T_q)_B,  G = W_BB = sum_k b_k b_k^T:   s_q' = s_q - u^T G^-1 u,   mu_q' = mu_q - u^T G^-1 alpha_B
+//           (block elimination of (K + s2 I)^-1; the same quantities as the leave-block-out score above);
+//   join:   t = Ls^-1 (k(x_B, x_q) - T_B^T T_q)  (the rows the append adds to T_q):   s_q' = s_q + |t|^2,
+//           mu_q' = mu_q + t . z_B,  Ls and z_B = Ls^-1 (y_B - mu_B) from k_append_small.
+// One CTA per patient ahead; out[2 i] = its new score, out[2 i + 1] = its new mean at the threshold visit.
+struct AlgPos {
+  const double *T, *ss, *mu;  // the patient's columns: T[c * stride + k], ss[c], mu[c]
+  int64_t stride;
+  const double *x, *y;        // its visits
+  int ncols;
+};
+struct AlgJobs {
+  AlgPos pos[OWN_BATCH];
+  Theta th;
+  int thr_index;
+  double* out;
+  // leave
+  const double* M;      // the factor BEFORE the deletion (its buffer is not reused until the host has read the result)
+  const double* alpha;
+  int64_t ld;
+  int p, n, m;
+  // join
+  const double* Tn;     // T of the joining block, Tn[a * stride_n + k]
+  int64_t stride_n;
+  const double *Li, *znew, *xn;
+};
+
+__device__ __forceinline__ void alg_finish(const AlgJobs& J, const AlgPos& P, const double* ssn, const double* mun,
+                                           double* lpd /* smem [NP] */) {
+  const int q = threadIdx.x;
+  if (q < P.ncols) {
+    double v = kern_diag(J.th, P.x[q]) - ssn[q];
+    v = v > 1e-15 ? v : 1e-15;
+    const double vn = v + J.th.noise, d = P.y[q] - mun[q];
+    lpd[q] = -0.5 * LOG_2_PI - 0.5 * log(vn) - 0.5 * (d * d) / vn;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // the scoring epilogue adds the visits by a shuffle tree over 32 lanes (lane q = visit q): same order here
+    double tr[32];
+    for (int i = 0; i < 32; ++i) tr[i] = i < P.ncols ? lpd[i] : 0.0;
+    for (int o = 16; o; o >>= 1)
+      for (int i = 0; i < o; ++i) tr[i] += tr[i + o];
+    J.out[2 * blockIdx.x] = tr[0];
+    J.out[2 * blockIdx.x + 1] = (J.thr_index >= 0 && J.thr_index < P.ncols) ? mun[J.thr_index] : nan("");
+  }
+}
+
+constexpr int ALG_THREADS = 512;
+constexpr int ALG_ENTRIES = NG + NP * NP;  // G (packed) | U[a][q]
+// leave, step 1: grid (row tiles from p, patients ahead): partial G and U over 64 rows of the block's columns
+__global__ void __launch_bounds__(256) k_alg_leave_part(const __grid_constant__ AlgJobs J, double* __restrict__ partial) {
+  const AlgPos& P = J.pos[blockIdx.y];
+  __shared__ double sb[TB][NP + 1], sT[TB][NP + 1];
+  const int tid = threadIdx.x, n = J.n, nc = P.ncols;
+  const int k0 = J.p + blockIdx.x * TB;
+  for (int idx = tid; idx < TB * NP; idx += 256) {
+    const int r = idx / NP, a = idx % NP, k = k0 + r;
+    double v = 0.0;
+    if (a < n && k < J.m && J.p + a <= k) v = J.M[(int64_t)k * J.ld + J.p + a];
+    sb[r][a] = v;
+  }
+  for (int idx = tid; idx < TB * NP; idx += 256) {
+    const int c = idx / TB, r = idx % TB, k = k0 + r;
+    sT[r][c] = (c < nc && k < J.m) ? P.T[(int64_t)c * P.stride + k] : 0.0;
+  }
+  __syncthreads();
+  double* out = partial + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * ALG_ENTRIES;
+  for (int e = tid; e < ALG_ENTRIES; e += 256) {
+    double acc = 0.0;
+    if (e < NG) {
+      int ea, eb;
+      tri_unpack(e, ea, eb);
+      if (ea < n) {
+#pragma unroll 8
+        for (int r = 0; r < TB; ++r) acc += sb[r][ea] * sb[r][eb];
+      }
+    } else {
+      const int ea = (e - NG) / NP, eb = (e - NG) % NP;
+      if (ea < n && eb < nc) {
+#pragma unroll 8
+        for (int r = 0; r < TB; ++r) acc += sb[r][ea] * sT[r][eb];
+      }
+    }
+    out[e] = acc;
+  }
+}
+// leave, step 2: one CTA per patient ahead: add the partials in a fixed order, G^-1 u, new moments, new score
+__global__ void __launch_bounds__(256) k_alg_leave_fin(const __grid_constant__ AlgJobs J, const double* __restrict__ partial,
+                                                       int ntiles) {
+  const AlgPos& P = J.pos[blockIdx.x];
+  __shared__ double G[NG], U[NP][NP + 1], ssn[NP], mun[NP], lpd[NP];
+  __shared__ int ok;
+  const int tid = threadIdx.x, n = J.n, nc = P.ncols;
+  for (int e = tid; e < ALG_ENTRIES; e += 256) {
+    double acc = 0.0;
+    for (int t = 0; t < ntiles; ++t) acc += partial[((int64_t)blockIdx.x * ntiles + t) * ALG_ENTRIES + e];
+    if (e < NG) {
+      int ea, eb;
+      tri_unpack(e, ea, eb);
+      G[e] = (ea < n) ? acc : (ea == eb ? 1.0 : 0.0);  // unused rows: identity keeps chol happy
+    } else {
+      U[(e - NG) / NP][(e - NG) % NP] = acc;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) ok = chol_packed(G, n, 1) ? 1 : 0;
+  __syncthreads();
+  if (tid < nc) {
+    double g[NP];
+    for (int a = 0; a < n; ++a) g[a] = U[a][tid];
+    chol_solve_packed(G, n, 1, g);
+    double ds = 0.0, dm = 0.0;
+    for (int a = 0; a < n; ++a) {
+      ds += g[a] * U[a][tid];
+      dm += g[a] * J.alpha[J.p + a];
+    }
+    ssn[tid] = ok ? P.ss[tid] - ds : nan("");
+    mun[tid] = P.mu[tid] - dm;
+  }
+  __syncthreads();
+  alg_finish(J, P, ssn, mun, lpd);
+}
+
+// join, step 1: grid (row tiles, patients ahead): partial C[a][q] = sum_k T_B[a][k] T_q[k] over 64 rows
+__global__ void __launch_bounds__(256) k_alg_join_part(const __grid_constant__ AlgJobs J, double* __restrict__ partial) {
+  const AlgPos& P = J.pos[blockIdx.y];
+  __shared__ double sa[TB][NP + 1], sT[TB][NP + 1];
+  const int tid = threadIdx.x, n = J.n, nc = P.ncols;
+  const int64_t len = P.stride < J.stride_n ? P.stride : J.stride_n;  // both are the cluster's padded size
+  const int64_t k0 = (int64_t)blockIdx.x * TB;
+  for (int idx = tid; idx < TB * NP; idx += 256) {
+    const int c = idx / TB, r = idx % TB;
+    const int64_t k = k0 + r;
+    sa[r][c] = (c < n && k < len) ? J.Tn[(int64_t)c * J.stride_n + k] : 0.0;
+    sT[r][c] = (c < nc && k < len) ? P.T[(int64_t)c * P.stride + k] : 0.0;
+  }
+  __syncthreads();
+  const int ea = tid / NP, eb = tid % NP;  // NP * NP = 256 entries
+  double acc = 0.0;
+  if (ea < n && eb < nc) {
+#pragma unroll 8
+    for (int r = 0; r < TB; ++r) acc += sa[r][ea] * sT[r][eb];
+  }
+  partial[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * (NP * NP) + tid] = acc;
+}
+// join, step 2 (after k_append_small): one CTA per patient ahead
+__global__ void __launch_bounds__(256) k_alg_join_fin(const __grid_constant__ AlgJobs J, const double* __restrict__ partial,
+                                                      int ntiles) {
+  const AlgPos& P = J.pos[blockIdx.x];
+  __shared__ double C[NP][NP + 1], ssn[NP], mun[NP], lpd[NP];
+  const int tid = threadIdx.x, n = J.n, nc = P.ncols;
+  {
+    double acc = 0.0;
+    for (int t = 0; t < ntiles; ++t) acc += partial[((int64_t)blockIdx.x * ntiles + t) * (NP * NP) + tid];
+    C[tid / NP][tid % NP] = acc;
+  }
+  __syncthreads();
+  if (tid < nc) {
+    double w[NP];
+    for (int a = 0; a < n; ++a) w[a] = kern_eval(J.th, J.xn[a], P.x[tid], false, nullptr) - C[a][tid];
+    double s2 = 0.0, dm = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double t = 0.0;
+      for (int c = 0; c <= i; ++c) t += J.Li[i * NP + c] * w[c];
+      s2 += t * t;
+      dm += t * J.znew[i];
+    }
+    ssn[tid] = P.ss[tid] + s2;
+    mun[tid] = P.mu[tid] + dm;
+  }
+  __syncthreads();
+  alg_finish(J, P, ssn, mun, lpd);
+}
+
 // Per tile: G_{i-1} for each of its rows (running Gram, snapshots in shared memory), then one thread per
 // row solves g_i = G_{i-1}^-1 b_i and u_i = (1 + b_i.g_i)^-1/2.
 constexpr int RM_PREP_SMEM = (NG * (TB + 1) + TB * (NP + 1)) * (int)sizeof(double);
