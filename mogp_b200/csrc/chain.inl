@@ -19,14 +19,11 @@ void pool_put(mogp_engine* h, int64_t cap, double* buf) {
   if (buf) h->pool.emplace_back(cap, buf);
 }
 
-// z (optional), alpha and the log marginal from the current M; results stay on the device until asked for.
-int refresh_vectors(mogp_engine* h, Cluster& c, bool recompute_z) {
-  if (recompute_z) {
-    TRY(sync_theta(h, c));
-    k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.x(), c.y(), (int)c.m, c.theta_dev(), c.z());
-    LAUNCHED(h);
-  }
-  TRY(launch_alpha(h, c));
+// After a rank-n update alpha is kept current in closed form by the update itself (k_append_finalize / k_rm_alpha);
+// z (after a deletion) and the log marginal are recomputed from the current M when somebody asks (fetch_stat).
+int mark_updated(mogp_engine* h, Cluster& c, bool z_stale) {
+  (void)h;
+  if (z_stale) c.z_dirty = true;
   c.stat_on_device = true;
   c.lml_dirty = true;
   c.grad_valid = false;
@@ -36,6 +33,13 @@ int refresh_vectors(mogp_engine* h, Cluster& c, bool recompute_z) {
 int fetch_stat(mogp_engine* h, Cluster& c) {
   if (!c.stat_on_device) return MOGP_OK;
   order_after_side(h, c);
+  if (c.z_dirty) {
+    TRY(sync_theta(h, c));
+    k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.x(), c.y(), (int)c.m, c.theta_dev(), c.z());
+    LAUNCHED(h);
+    c.z_dirty = false;
+    c.lml_dirty = true;
+  }
   if (c.lml_dirty) {
     TRY(launch_alpha_lml(h, c));
     c.lml_dirty = false;
@@ -120,11 +124,11 @@ int append_core(mogp_engine* h, Cluster& c, int n, const double* xB_dev, const d
   }
   k_append_finalize<<<(unsigned)((mpad_new + 255) / 256), 256, 0, h->stream>>>(c.M, c.cap, (int)m, n, (int)mpad_old,
                                                                                (int)mpad_new, w, xB_dev, yB_dev, c.x(), c.y(),
-                                                                               c.z());
+                                                                               c.z(), c.alpha());
   LAUNCHED(h);
   c.m = mnew;
   CK(h, cudaGetLastError());
-  return refresh_vectors(h, c, false);
+  return mark_updated(h, c, false);
 }
 
 // mogp_cluster_append: host points, any n (chunks of NP).
@@ -162,13 +166,14 @@ int rm_work(mogp_engine* h, const RmGeom& g, RmWork* w) {
   // (the look-ahead streams compute own-cluster scores while the side stream may be deleting rows: own workspace)
   const bool la = h->stream == h->ahead || h->stream == h->ahead2;
   double** buf = la ? &h->d_upd2 : &h->d_upd;
-  TRY(ensure(h, buf, la ? &h->upd2_elems : &h->upd_elems, rows * NP * 2 + rows + nT * NG + NG + 8 + 2 * ph));
+  TRY(ensure(h, buf, la ? &h->upd2_elems : &h->upd_elems, rows * NP * 2 + rows + nT * NG + NG + 8 + NP + 2 * ph));
   w->Bt = *buf;
   w->Gt = w->Bt + rows * NP;
   w->u = w->Gt + rows * NP;
   w->Pgram = w->u + rows;
   w->Gc = w->Pgram + nT * NG;
   w->own = w->Gc + NG;
+  w->gsol = w->own + 8;
   return MOGP_OK;
 }
 
@@ -199,13 +204,13 @@ int remove_core(mogp_engine* h, Cluster& c, int64_t p, int n) {
   RmWork w;
   TRY(rm_work(h, g, &w));
   const int nT = g.nbn - g.I0;
-  k_rm_prep<<<nT, 256, RM_PREP_SMEM, h->stream>>>(g, w);
+  k_rm_prep<<<nT, 256, RM_PREP_SMEM, h->stream>>>(g, w, c.alpha());
   LAUNCHED(h);
   double* nbuf = nullptr;
   TRY(pool_get(h, c.cap, &nbuf));
   double* nM = nbuf;
   double* nvec = nbuf + c.cap * c.cap;
-  double* P = w.own + 8;
+  double* P = w.own + 8 + NP;
   double* H = P + (int64_t)nT * g.nbn * (NP * TB);
   k_rm_hpart<<<dim3(g.nbn, nT), NTHREADS, 0, h->stream>>>(c.M, g, w, P);
   LAUNCHED(h);
@@ -214,6 +219,8 @@ int remove_core(mogp_engine* h, Cluster& c, int64_t p, int n) {
   k_rm_apply<<<dim3(g.nbn, g.nbn), NTHREADS, RM_APPLY_SMEM, h->stream>>>(c.M, nM, g, w, H);
   LAUNCHED(h);
   k_rm_vec<<<(unsigned)((g.mnew + 255) / 256), 256, 0, h->stream>>>(c.x(), c.y(), nvec, nvec + c.cap, g);
+  LAUNCHED(h);
+  k_rm_alpha<<<(unsigned)((g.mnew + 255) / 256), 256, 0, h->stream>>>(c.alpha(), nvec + 2 * c.cap, H, P, g, w.gsol);
   LAUNCHED(h);
   // stat block travels with the buffer
   CK(h, cudaMemcpyAsync(nvec + 4 * c.cap, c.stat(), sizeof(double) * STAT, cudaMemcpyDeviceToDevice, h->stream));
@@ -225,7 +232,7 @@ int remove_core(mogp_engine* h, Cluster& c, int64_t p, int n) {
   c.hx.erase(c.hx.begin() + p, c.hx.begin() + p + n);
   c.hy.erase(c.hy.begin() + p, c.hy.begin() + p + n);
   CK(h, cudaGetLastError());
-  return refresh_vectors(h, c, true);
+  return mark_updated(h, c, true);
 }
 
 // ---- the draw: np.exp(s - logsumexp(s)) then np.random.choice(active, p=p) (mogp_constrained.py:272-277) ----

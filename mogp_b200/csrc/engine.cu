@@ -49,6 +49,7 @@ struct Cluster {
   bool side_busy = false;         // a row deletion of this cluster may still be running on the side stream
   bool stat_on_device = false;    // lml / quad / logdet of the last rank update not fetched yet
   bool lml_dirty = false;         // ... and not even reduced yet (k_lml runs when somebody asks)
+  bool z_dirty = false;           // z = M r not recomputed after a row deletion (k_z runs when somebody asks)
   double* x() const { return vec; }
   double* y() const { return vec + cap; }
   double* alpha() const { return vec + 2 * cap; }
@@ -467,21 +468,6 @@ int sync_theta(mogp_engine* h, Cluster& c) {
   return MOGP_OK;
 }
 
-// alpha = M^T z only (after a rank update): the log marginal is reduced lazily, see fetch_stat.
-int launch_alpha(mogp_engine* h, Cluster& c) {
-  const int64_t mpad = round_up(c.m, TB);
-  const int nchunk = (int)((c.m + ALPHA_ROWS - 1) / ALPHA_ROWS);
-  const bool on_side = h->stream == h->side;  // the two streams of a Gibbs step must not share the partials
-  double** buf = on_side ? &h->d_apart2 : &h->d_apart;
-  TRY(ensure(h, buf, on_side ? &h->apart2_elems : &h->apart_elems, (int64_t)nchunk * mpad));
-  k_alpha_part<<<dim3((unsigned)(mpad / TB), (unsigned)nchunk), NTHREADS, 0, h->stream>>>(c.M, c.cap, c.z(), (int)c.m,
-                                                                                           (int)mpad, *buf);
-  LAUNCHED(h);
-  k_alpha_reduce<<<(unsigned)((c.m + 255) / 256), 256, 0, h->stream>>>(*buf, nchunk, (int)mpad, c.alpha(), (int)c.m);
-  LAUNCHED(h);
-  return MOGP_OK;
-}
-
 // alpha = M^T z (two stages) and the log marginal likelihood from the current M and z.
 int launch_alpha_lml(mogp_engine* h, Cluster& c) {
   const int64_t mpad = round_up(c.m, TB);
@@ -545,6 +531,7 @@ int infer(mogp_engine* h, Cluster& c) {
       c.logdet = hs[2];
       c.valid = true;
       c.stat_on_device = false;
+      c.z_dirty = false;
       c.lml_dirty = false;
       return MOGP_OK;
     }
@@ -1415,6 +1402,7 @@ static int graph_eval(mogp_engine* h, Cluster& c, bool* ok) {
   memcpy(c.grad, hs + 10, sizeof(double) * 4);
   c.valid = c.grad_valid = true;
   c.stat_on_device = false;
+  c.z_dirty = false;
   c.lml_dirty = false;
   *ok = true;
   return MOGP_OK;

@@ -74,9 +74,10 @@ struct RmGeom {
   int64_t ld;
 };
 
-// Workspace (doubles): Bt[nrows][NP] | Gt[nrows][NP] | u[nrows] | Pgram[nT][NG] | Gc[NG] | own[4]
+// Workspace (doubles): Bt[nrows][NP] | Gt[nrows][NP] | u[nrows] | Pgram[nT][NG] | Gc[NG] | own[8] | gsol[NP]
 struct RmWork {
   double *Bt, *Gt, *u, *Pgram, *Gc, *own;
+  double* gsol = nullptr;  // W_BB^-1 alpha_B (k_rm_prep, last tile) for the closed-form alpha of the result
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -122,6 +123,7 @@ __device__ __forceinline__ void own_final_body(const double* __restrict__ alpha,
   __shared__ int ok;
   if (threadIdx.x < NG) {
     double s = w.Gc[threadIdx.x];
+#pragma unroll 8
     for (int I = 0; I < nT; ++I) s += w.Pgram[(int64_t)I * NG + threadIdx.x];
     G[threadIdx.x] = s;
   }
@@ -286,6 +288,7 @@ __global__ void __launch_bounds__(256) k_alg_leave_fin(const __grid_constant__ A
   const int tid = threadIdx.x, n = J.n, nc = P.ncols;
   for (int e = tid; e < ALG_ENTRIES; e += 256) {
     double acc = 0.0;
+#pragma unroll 8
     for (int t = 0; t < ntiles; ++t) acc += partial[((int64_t)blockIdx.x * ntiles + t) * ALG_ENTRIES + e];
     if (e < NG) {
       int ea, eb;
@@ -344,6 +347,7 @@ __global__ void __launch_bounds__(256) k_alg_join_fin(const __grid_constant__ Al
   const int tid = threadIdx.x, n = J.n, nc = P.ncols;
   {
     double acc = 0.0;
+#pragma unroll 8
     for (int t = 0; t < ntiles; ++t) acc += partial[((int64_t)blockIdx.x * ntiles + t) * (NP * NP) + tid];
     C[tid / NP][tid % NP] = acc;
   }
@@ -368,8 +372,9 @@ __global__ void __launch_bounds__(256) k_alg_join_fin(const __grid_constant__ Al
 // Per tile: G_{i-1} for each of its rows (running Gram, snapshots in shared memory), then one thread per
 // row solves g_i = G_{i-1}^-1 b_i and u_i = (1 + b_i.g_i)^-1/2.
 constexpr int RM_PREP_SMEM = (NG * (TB + 1) + TB * (NP + 1)) * (int)sizeof(double);
-__global__ void __launch_bounds__(256) k_rm_prep(RmGeom g, RmWork w) {
+__global__ void __launch_bounds__(256) k_rm_prep(RmGeom g, RmWork w, const double* __restrict__ alpha_old) {
   extern __shared__ __align__(16) double smem[];
+  __shared__ double Gfull[NG];
   double* snap = smem;                  // [NG][TB+1]
   double* sb = snap + NG * (TB + 1);    // [TB][NP+1]
   const int I = g.I0 + blockIdx.x;
@@ -382,13 +387,23 @@ __global__ void __launch_bounds__(256) k_rm_prep(RmGeom g, RmWork w) {
     int a, b;
     tri_unpack(threadIdx.x, a, b);
     double run = w.Gc[threadIdx.x];
+#pragma unroll 8
     for (int J = 0; J < (int)blockIdx.x; ++J) run += w.Pgram[(int64_t)J * NG + threadIdx.x];
     for (int k = 0; k < TB; ++k) {
       snap[threadIdx.x * (TB + 1) + k] = run;
       run += sb[k * (NP + 1) + a] * sb[k * (NP + 1) + b];
     }
+    Gfull[threadIdx.x] = (a < g.n) ? run : (a == b ? 1.0 : 0.0);  // the last tile ends with G = W_BB
   }
   __syncthreads();
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255 && w.gsol) {
+    // alpha of the result in closed form: alpha'_R = alpha_R - W_RB W_BB^-1 alpha_B (k_rm_alpha); here W_BB^-1 alpha_B
+    double v[NP];
+    const bool ok = chol_packed(Gfull, g.n, 1);
+    for (int q = 0; q < g.n; ++q) v[q] = alpha_old[g.p + q];
+    if (ok) chol_solve_packed(Gfull, g.n, 1, v);
+    for (int q = 0; q < NP; ++q) w.gsol[q] = (q < g.n) ? (ok ? v[q] : nan("")) : 0.0;
+  }
   if (threadIdx.x < TB) {
     const int r = threadIdx.x, ip = I * TB + r;
     double gv[NP];
@@ -536,6 +551,19 @@ __global__ void k_rm_vec(const double* __restrict__ xo, const double* __restrict
   yn[ip] = yo[i];
 }
 
+// alpha of the result without another pass over the factor: W_{B,j} = sum_k M[k,B] M[k,j] is the LAST prefix of the
+// deletion's row sums (H + P of the last row tile), so alpha'_j = alpha_j - W_{B,j} . (W_BB^-1 alpha_B).
+__global__ void k_rm_alpha(const double* __restrict__ alpha_old, double* __restrict__ alpha_new, const double* __restrict__ H,
+                           const double* __restrict__ P, RmGeom g, const double* __restrict__ gsol) {
+  const int jp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (jp >= g.mnew) return;
+  const int j = jp < g.p ? jp : jp + g.n;
+  const int64_t base = ((int64_t)(g.nbn - 1 - g.I0) * g.nbn + (jp >> 6)) * (NP * TB) + (jp & 63);
+  double s = 0.0;
+  for (int a = 0; a < g.n; ++a) s += (H[base + (int64_t)a * TB] + P[base + (int64_t)a * TB]) * gsol[a];
+  alpha_new[jp] = alpha_old[j] - s;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Identity padding for block rows/cols [from, to) of M (to, from multiples of 64).
 __global__ void k_pad_identity(double* __restrict__ M, int64_t ld, int from, int to) {
@@ -594,6 +622,7 @@ __global__ void __launch_bounds__(256) k_append_small(const double* __restrict__
     tri_unpack(threadIdx.x, a, b);
     if (a < n) {
       double s = 0.0;
+#pragma unroll 8
       for (int q = 0; q < nblk; ++q) s += w.gpart[(int64_t)q * NG + threadIdx.x];
       double k = kern_eval(th, xB[a], xB[b], a == b, nullptr);
       if (a == b) k = __dadd_rn(k, __dadd_rn(th.noise, GPY_JITTER));
@@ -682,9 +711,11 @@ __global__ void __launch_bounds__(NTHREADS) k_append_rows(const double* __restri
 // Write the n new rows of M, extend x, y, z.  grid: ceil(mpad_new / 256).
 __global__ void k_append_finalize(double* __restrict__ M, int64_t ld, int m, int n, int mpad_old, int mpad_new, ApWork w,
                                   const double* __restrict__ xB, const double* __restrict__ yB, double* __restrict__ x,
-                                  double* __restrict__ y, double* __restrict__ z) {
+                                  double* __restrict__ y, double* __restrict__ z, double* __restrict__ alpha) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= mpad_new) return;
+  // alpha' = M'^T z' = [alpha + R^T z_B ; Ls^-T z_B] with R the new rows: no pass over the factor
+  double da = 0.0;
   for (int i = 0; i < n; ++i) {
     double v;
     if (j < m) {
@@ -698,7 +729,9 @@ __global__ void k_append_finalize(double* __restrict__ M, int64_t ld, int m, int
       v = 0.0;
     }
     M[(int64_t)(m + i) * ld + j] = v;
+    da += v * w.znew[i];
   }
+  if (j < m + n) alpha[j] = (j < m ? alpha[j] : 0.0) + da;
   if (j < n) {
     x[m + j] = xB[j];
     y[m + j] = yB[j];

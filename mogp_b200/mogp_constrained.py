@@ -70,6 +70,8 @@ class MoGP_constrained:
         cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 8)
         ranks_here = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1'))))
         self.refit_concurrency = int(max(2, min(12, cores // ranks_here)))
+        if os.environ.get('MOGP_REFIT_CONCURRENCY'):               # 1 = refit in the calling thread (profilers)
+            self.refit_concurrency = max(1, int(os.environ['MOGP_REFIT_CONCURRENCY']))
         self._workers = None
         self.min_margin = np.inf       # smallest |u - cdf edge| seen (assignment-parity diagnostic)
         self.n_refit_evals = 0
