@@ -584,7 +584,7 @@ __global__ void k_pad_identity(double* __restrict__ M, int64_t ld, int from, int
 }
 
 // Workspace of an append: Li [NP*NP] | znew [NP] | gpart [nblk][NG] | part [KS][NP][mpad]
-constexpr int APPEND_KS = 4;
+constexpr int APPEND_KS = 8;
 constexpr int AP_GRAM_ROWS = 256;
 struct ApWork {
   double *Li, *znew, *gpart, *part;
