@@ -166,7 +166,7 @@ int rm_work(mogp_engine* h, const RmGeom& g, RmWork* w) {
   // (the look-ahead streams compute own-cluster scores while the side stream may be deleting rows: own workspace)
   const bool la = h->stream == h->ahead || h->stream == h->ahead2;
   double** buf = la ? &h->d_upd2 : &h->d_upd;
-  TRY(ensure(h, buf, la ? &h->upd2_elems : &h->upd_elems, rows * NP * 2 + rows + nT * NG + NG + 8 + NP + 2 * ph));
+  TRY(ensure(h, buf, la ? &h->upd2_elems : &h->upd_elems, rows * NP * 2 + rows + nT * NG + NG + 8 + NP + nT * TB * TB + 2 * ph));
   w->Bt = *buf;
   w->Gt = w->Bt + rows * NP;
   w->u = w->Gt + rows * NP;
@@ -174,6 +174,7 @@ int rm_work(mogp_engine* h, const RmGeom& g, RmWork* w) {
   w->Gc = w->Pgram + nT * NG;
   w->own = w->Gc + NG;
   w->gsol = w->own + 8;
+  w->S = w->gsol + NP;
   return MOGP_OK;
 }
 
@@ -210,7 +211,7 @@ int remove_core(mogp_engine* h, Cluster& c, int64_t p, int n) {
   TRY(pool_get(h, c.cap, &nbuf));
   double* nM = nbuf;
   double* nvec = nbuf + c.cap * c.cap;
-  double* P = w.own + 8 + NP;
+  double* P = w.S + (int64_t)nT * TB * TB;
   double* H = P + (int64_t)nT * g.nbn * (NP * TB);
   k_rm_hpart<<<dim3(g.nbn, nT), NTHREADS, 0, h->stream>>>(c.M, g, w, P);
   LAUNCHED(h);

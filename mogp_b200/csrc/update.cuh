@@ -78,6 +78,7 @@ struct RmGeom {
 struct RmWork {
   double *Bt, *Gt, *u, *Pgram, *Gc, *own;
   double* gsol = nullptr;  // W_BB^-1 alpha_B (k_rm_prep, last tile) for the closed-form alpha of the result
+  double* S = nullptr;     // [row tile][64][64]: strict_lower(G_I B_I^T), once per row tile (k_rm_prep) for every column tile
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -371,12 +372,13 @@ __global__ void __launch_bounds__(256) k_alg_join_fin(const __grid_constant__ Al
 
 // Per tile: G_{i-1} for each of its rows (running Gram, snapshots in shared memory), then one thread per
 // row solves g_i = G_{i-1}^-1 b_i and u_i = (1 + b_i.g_i)^-1/2.
-constexpr int RM_PREP_SMEM = (NG * (TB + 1) + TB * (NP + 1)) * (int)sizeof(double);
+constexpr int RM_PREP_SMEM = (NG * (TB + 1) + 2 * TB * (NP + 1)) * (int)sizeof(double);
 __global__ void __launch_bounds__(256) k_rm_prep(RmGeom g, RmWork w, const double* __restrict__ alpha_old) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double Gfull[NG];
   double* snap = smem;                  // [NG][TB+1]
   double* sb = snap + NG * (TB + 1);    // [TB][NP+1]
+  double* sg = sb + TB * (NP + 1);      // [TB][NP+1]: g_i
   const int I = g.I0 + blockIdx.x;
   for (int idx = threadIdx.x; idx < TB * NP; idx += 256) {
     int r = idx / NP, a = idx % NP;
@@ -423,8 +425,25 @@ __global__ void __launch_bounds__(256) k_rm_prep(RmGeom g, RmWork w, const doubl
         u = nan("");
       }
     }
-    for (int a = 0; a < NP; ++a) w.Gt[((int64_t)blockIdx.x * TB + r) * NP + a] = (a < g.n) ? gv[a] : 0.0;
+    for (int a = 0; a < NP; ++a) {
+      const double ga = (a < g.n) ? gv[a] : 0.0;
+      w.Gt[((int64_t)blockIdx.x * TB + r) * NP + a] = ga;
+      sg[r * (NP + 1) + a] = ga;
+    }
     w.u[(int64_t)blockIdx.x * TB + r] = u;
+  }
+  __syncthreads();
+  if (w.S) {  // S_I = strict_lower(G_I B_I^T): the in-tile part of the prefix, the same for every column tile
+    double* So = w.S + (int64_t)blockIdx.x * (TB * TB);
+    for (int idx = threadIdx.x; idx < TB * TB; idx += 256) {
+      const int r = idx >> 6, k = idx & 63;
+      double sv = 0.0;
+      if (k < r) {
+#pragma unroll
+        for (int a = 0; a < NP; ++a) sv += sg[r * (NP + 1) + a] * sb[k * (NP + 1) + a];
+      }
+      So[idx] = sv;
+    }
   }
 }
 
@@ -491,7 +510,7 @@ __global__ void __launch_bounds__(NP * TB) k_rm_hscan(const double* __restrict__
   }
 }
 
-constexpr int RM_APPLY_SMEM = (TB * LD_W + (TB + NP) * LD_R + TB * (NP + 1) + TB) * (int)sizeof(double);
+constexpr int RM_APPLY_SMEM = (TB * LD_W + (TB + NP) * LD_R + TB) * (int)sizeof(double);
 __global__ void __launch_bounds__(NTHREADS) k_rm_apply(const double* __restrict__ Mo, double* __restrict__ Mn, RmGeom g,
                                                        RmWork w, const double* __restrict__ H) {
   const int J = blockIdx.x, I = blockIdx.y, tid = threadIdx.x;
@@ -507,31 +526,21 @@ __global__ void __launch_bounds__(NTHREADS) k_rm_apply(const double* __restrict_
   extern __shared__ __align__(16) double smem[];
   double* sA = smem;                       // [64][LD_W]: S (cols 0..63) | G (cols 64..64+NP)
   double* sB = sA + TB * LD_W;             // [64+NP][LD_R]: old tile (rows 0..63) ; H (rows 64..64+NP)
-  double* sb = sB + (TB + NP) * LD_R;      // [64][NP+1]
-  double* su = sb + TB * (NP + 1);         // [64]
+  double* su = sB + (TB + NP) * LD_R;      // [64]
   const int64_t wrow = (int64_t)(I - g.I0) * TB;
   const double* Hs = H + ((int64_t)(I - g.I0) * g.nbn + J) * (NP * TB);
+  const double* Ss = w.S + (int64_t)(I - g.I0) * (TB * TB);
   for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
     int r = idx >> 6, c = idx & 63;
     sB[r * LD_R + c] = rm_src(Mo, g, I * TB + r, J * TB + c);
+    sA[r * LD_W + c] = Ss[idx];
   }
   for (int idx = tid; idx < NP * TB; idx += NTHREADS) sB[(TB + (idx >> 6)) * LD_R + (idx & 63)] = Hs[idx];
   for (int idx = tid; idx < TB * NP; idx += NTHREADS) {
     int r = idx / NP, a = idx % NP;
-    sb[r * (NP + 1) + a] = w.Bt[(wrow + r) * NP + a];
     sA[r * LD_W + TB + a] = w.Gt[(wrow + r) * NP + a];
   }
   if (tid < TB) su[tid] = w.u[wrow + tid];
-  __syncthreads();
-  for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
-    int r = idx >> 6, k = idx & 63;
-    double s = 0.0;
-    if (k < r) {
-#pragma unroll
-      for (int a = 0; a < NP; ++a) s += sA[r * LD_W + TB + a] * sb[k * (NP + 1) + a];
-    }
-    sA[r * LD_W + k] = s;
-  }
   __syncthreads();
   Acc64 acc;
   acc.zero();
