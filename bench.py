@@ -354,7 +354,7 @@ def run_b200(args):
                           "refit_evals": int(mix.n_refit_evals), "total_loglik": ll,
                           "steps_s_per_sweep": split_timed[0], "refit_s_per_sweep": split_timed[1],
                           "lookahead": {k: counters[k] for k in ("window_passes", "rescoring_passes", "window_patients",
-                                                                 "open_s", "rescore_s", "commit_s", "rank_corrections", "correct_s")}}}
+                                                                 "open_s", "rescore_s", "commit_s", "rank_corrections", "correct_s", "replayed")}}}
         if world == 1 and not args.no_cpu_baseline:
             orc, _t_init = oracle_sample(args, 0)
             ts, tr, nact, evals = oracle_step_times(orc, args.cpu_steps, 1)

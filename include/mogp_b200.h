@@ -96,7 +96,8 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
    out[4..6] = host seconds spent waiting for batches / re-scoring / committing moves (each includes its waits),
    out[7..10] = launches, device ms, algorithmic bytes and flops of the profiled RE-SCORING launches of the scoring
    product since the last profile reset (mogp_profile_read reports the whole passes only),
-   out[11] = moves whose effect on the cached scores was a rank-n correction, out[12] = host seconds in them. */
+   out[11] = moves whose effect on the cached scores was a rank-n correction, out[12] = host seconds in them,
+   out[13] = (cluster, batch) corrections replayed for the next batch's positions. */
 int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out);
 
 /* ---- one cluster's GP = one GPobs object ------------------------------------------------- */

@@ -96,9 +96,12 @@ int append_core(mogp_engine* h, Cluster& c, int n, const double* xB_dev, const d
   cudaStream_t s1 = on_quick ? h->quick : h->stream;
   if (hk) {
     hk->ntiles = (int)(mpad_old / TB);
-    TRY(ensure(h, &h->d_algw2, &h->algw2_elems, (int64_t)hk->npos * hk->ntiles * NP * NP));
-    k_alg_join_part<<<dim3((unsigned)hk->ntiles, (unsigned)hk->npos), 256, 0, s1>>>(hk->jobs, h->d_algw2);
-    LAUNCHED(h);
+    hk->on_quick = on_quick;
+    if (hk->npos > 0) {
+      TRY(ensure(h, &h->d_algw2, &h->algw2_elems, (int64_t)hk->npos * hk->ntiles * NP * NP));
+      k_alg_join_part<<<dim3((unsigned)hk->ntiles, (unsigned)hk->npos), 256, 0, s1>>>(hk->jobs, h->d_algw2);
+      LAUNCHED(h);
+    }
   }
   k_append_gram<<<nblk, 256, 0, s1>>>(T_dev, (int)mpad_old, n, w);
   LAUNCHED(h);
@@ -111,8 +114,10 @@ int append_core(mogp_engine* h, Cluster& c, int n, const double* xB_dev, const d
   if (hk) {
     hk->jobs.Li = w.Li;
     hk->jobs.znew = w.znew;
-    k_alg_join_fin<<<hk->npos, 256, 0, s1>>>(hk->jobs, h->d_algw2, hk->ntiles);
-    LAUNCHED(h);
+    if (hk->npos > 0) {
+      k_alg_join_fin<<<hk->npos, 256, 0, s1>>>(hk->jobs, h->d_algw2, hk->ntiles);
+      LAUNCHED(h);
+    }
     CK(h, cudaEventRecord(h->ev_alg, s1));
     hk->fired = true;
   }
@@ -859,15 +864,21 @@ int batch_absorb(mogp_engine* h, int bi) {
   for (int si = 0; si < ns; ++si) {
     const int32_t slot = b.slots[si];
     const int64_t mpad = b.mpad[si];
-    if (w.slot_epoch[slot] == b.epoch[si]) {
+    const bool clean = w.slot_epoch[slot] == b.epoch[si];
+    // (a slot that changed since the pass was launched keeps the pass's T / ss / mu for win_replay, not its scores)
+    if (clean || w.slot_upto[slot] <= b.s0) {
       for (int64_t v = 0; v < cnt; ++v) {
         Chain::WinEntry& e = w.e[b.s0 + v][slot];
-        e.score = hs[v * ns + si];
-        e.muthr = hm[v * ns + si];
+        if (clean) {
+          e.score = hs[v * ns + si];
+          e.muthr = hm[v * ns + si];
+        }
         e.T = b.pl.T + kx_off + (w.col0[b.s0 + v] - cb) * mpad;
         e.mu = b.pl.mu + (int64_t)si * b.pl.Rpad + (w.col0[b.s0 + v] - cb);
         e.ss = b.pl.ss + (int64_t)si * b.pl.Rpad + (w.col0[b.s0 + v] - cb);
       }
+    }
+    if (clean) {
       w.slot_upto[slot] = b.s0 + cnt;
       w.slot_T_ok[slot] = 1;
     }
@@ -882,6 +893,90 @@ int batch_absorb(mogp_engine* h, int bi) {
       w.own_ok[b.s0 + v] = 1;
     }
   }
+  return MOGP_OK;
+}
+
+// The pass of the batch just absorbed was launched BEFORE the previous batch made its moves.  For a cluster that took
+// exactly one logged rank-n change since, the same correction is applied to this batch's positions from what its own
+// pass left on the device - instead of waiting for the factor update and re-scoring.  Everything else that changed
+// stays stale and is re-scored at the batch's first step.
+int win_replay(mogp_engine* h, int bi) {
+  Chain& ch = h->chain;
+  Chain::Window& w = ch.win;
+  Chain::Batch& b = w.b[bi];
+  if (w.log.empty() || b.cnt <= 0 || b.cnt > OWN_BATCH) return MOGP_OK;
+  struct Item {
+    const ChangeLog* cl;
+    int si;
+  };
+  std::vector<Item> items;
+  for (size_t i = 0; i < w.log.size() && (int)items.size() < ALG_OUT_SLOTS - 2; ++i) {
+    const ChangeLog& L = w.log[i];
+    int same = 0;
+    for (const ChangeLog& o : w.log) same += o.slot == L.slot;
+    if (same != 1 || L.slot < 0 || L.slot >= (int32_t)w.slot_epoch.size()) continue;
+    int si = -1;
+    for (size_t q = 0; q < b.slots.size(); ++q)
+      if (b.slots[q] == L.slot) si = (int)q;
+    if (si < 0 || b.epoch[si] != L.epoch_before || w.slot_epoch[L.slot] != L.epoch_before + 1) continue;
+    if (w.slot_upto[L.slot] > b.s0 || !h->cl[L.slot].used) continue;
+    items.push_back(Item{&L, si});
+  }
+  if (items.empty()) return MOGP_OK;
+  PhaseTimer pt(&ch.t_alg);
+  int64_t wneed = 0;
+  for (const Item& it : items) wneed += b.cnt * (int64_t)it.cl->ntiles * (it.cl->kind == 0 ? ALG_ENTRIES : NP * NP);
+  TRY(ensure(h, &h->d_algw, &h->algw_elems, wneed));
+  CK(h, cudaStreamWaitEvent(h->quick, h->ev_q2, 0));  // the logged copies were written on the other quick stream
+  int64_t woff = 0;
+  for (size_t idx = 0; idx < items.size(); ++idx) {
+    const ChangeLog& L = *items[idx].cl;
+    AlgJobs J = L.J;
+    for (int64_t q = 0; q < b.cnt; ++q) {
+      const int64_t v = b.s0 + q;
+      const Chain::WinEntry& e = w.e[v][L.slot];
+      AlgPos& P = J.pos[q];
+      P.T = e.T;
+      P.ss = e.ss;
+      P.mu = e.mu;
+      P.stride = b.mpad[items[idx].si];
+      P.x = h->d_wq + w.col0[v];
+      P.y = h->d_wq + w.col0[w.n] + w.col0[v];
+      P.ncols = (int)(w.col0[v + 1] - w.col0[v]);
+    }
+    J.out = h->d_alg + (2 + (int64_t)idx) * 2 * OWN_BATCH;
+    J.logB = J.logAlpha = nullptr;
+    double* part = h->d_algw + woff;
+    if (L.kind == 0) {
+      k_alg_leave_part<<<dim3((unsigned)L.ntiles, (unsigned)b.cnt), 256, 0, h->quick>>>(J, part);
+      LAUNCHED(h);
+      k_alg_leave_fin<<<(unsigned)b.cnt, 256, 0, h->quick>>>(J, part, L.ntiles);
+      LAUNCHED(h);
+      woff += b.cnt * (int64_t)L.ntiles * ALG_ENTRIES;
+    } else {
+      k_alg_join_part<<<dim3((unsigned)L.ntiles, (unsigned)b.cnt), 256, 0, h->quick>>>(J, part);
+      LAUNCHED(h);
+      k_alg_join_fin<<<(unsigned)b.cnt, 256, 0, h->quick>>>(J, part, L.ntiles);
+      LAUNCHED(h);
+      woff += b.cnt * (int64_t)L.ntiles * NP * NP;
+    }
+  }
+  const int64_t nout = (2 + (int64_t)items.size()) * 2 * OWN_BATCH;
+  CK(h, cudaMemcpyAsync(h->h_alg, h->d_alg, sizeof(double) * nout, cudaMemcpyDeviceToHost, h->quick));
+  CK(h, cudaStreamSynchronize(h->quick));
+  h->bytes_d2h += (int64_t)sizeof(double) * nout;
+  for (size_t idx = 0; idx < items.size(); ++idx) {
+    const int32_t slot = items[idx].cl->slot;
+    const double* out = h->h_alg + (2 + (int64_t)idx) * 2 * OWN_BATCH;
+    for (int64_t q = 0; q < b.cnt; ++q) {
+      Chain::WinEntry& e = w.e[b.s0 + q][slot];
+      e.score = out[2 * q];
+      e.muthr = out[2 * q + 1];
+    }
+    w.slot_upto[slot] = b.s0 + b.cnt;  // scores current for this batch; its T / ss / mu are those of the old factor
+    w.slot_T_ok[slot] = 0;
+  }
+  ch.win_replayed += (int64_t)items.size();
   return MOGP_OK;
 }
 
@@ -1018,7 +1113,8 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
   // O(m^2) updates of the two factors are queued behind and nobody waits for them.  One correction per cluster and
   // batch: a second change, a cluster without current T, a new or emptied cluster go the long way (re-scoring).
   const int64_t npos = w.batch_end - (w.cur + 1);
-  const bool alg_on = !stays && npos > 0 && npos <= OWN_BATCH && ch.pending_lazy && env_int("MOGP_RANK_RESCORE", 1) != 0;
+  const bool alg_on = !stays && npos >= 0 && npos <= OWN_BATCH && ch.pending_lazy && env_int("MOGP_RANK_RESCORE", 1) != 0;
+  const bool log_on = alg_on && w.end_launched > w.batch_end && env_int("MOGP_REPLAY", 0) != 0;  // a next batch is in flight (off by default: measured neutral)
   auto alg_ok = [&](int32_t slot) {
     return slot >= 0 && slot < (int32_t)w.slot_upto.size() && w.slot_upto[slot] >= w.batch_end && w.slot_T_ok[slot] &&
            !w.slot_alg[slot];
@@ -1059,16 +1155,45 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
         J.n = (int)nin;
         J.m = (int)ca.m;
         const int ntiles = (int)((ca.m - p + TB - 1) / TB);
-        TRY(ensure(h, &h->d_algw, &h->algw_elems, (int64_t)npos * ntiles * ALG_ENTRIES));
-        k_alg_leave_part<<<dim3((unsigned)ntiles, (unsigned)npos), 256, 0, h->quick2>>>(J, h->d_algw);
-        LAUNCHED(h);
-        k_alg_leave_fin<<<(unsigned)npos, 256, 0, h->quick2>>>(J, h->d_algw, ntiles);
-        LAUNCHED(h);
-        CK(h, cudaEventRecord(h->ev_q2, h->quick2));
+        if (log_on) {  // keep what the correction reads from the cluster: replayed for the next batch (win_replay)
+          const int64_t need = (int64_t)(ca.m - p) * NP + NP;
+          if (w.blog_used + need <= h->blog_elems) {
+            J.logB = h->d_blog + w.blog_used;
+            J.logAlpha = J.logB + (int64_t)(ca.m - p) * NP;
+            w.blog_used += need;
+          }
+        }
+        if (npos > 0 || J.logB) {
+          TRY(ensure(h, &h->d_algw, &h->algw_elems, (int64_t)std::max<int64_t>(npos, 1) * ntiles * ALG_ENTRIES));
+          if (npos == 0) J.pos[0].ncols = 0;  // log only
+          k_alg_leave_part<<<dim3((unsigned)ntiles, (unsigned)std::max<int64_t>(npos, 1)), 256, 0, h->quick2>>>(J, h->d_algw);
+          LAUNCHED(h);
+          if (npos > 0) {
+            k_alg_leave_fin<<<(unsigned)npos, 256, 0, h->quick2>>>(J, h->d_algw, ntiles);
+            LAUNCHED(h);
+          }
+          CK(h, cudaEventRecord(h->ev_q2, h->quick2));
+          // the cluster's old buffer must outlive these reads: the streams that may recycle it wait for them
+          CK(h, cudaStreamWaitEvent(h->main_stream, h->ev_q2, 0));
+          CK(h, cudaStreamWaitEvent(h->side, h->ev_q2, 0));
+        }
         a_alg = true;
+        if (J.logB) {
+          ChangeLog cl;
+          cl.slot = a_slot;
+          cl.kind = 0;
+          cl.J = J;
+          cl.J.M = J.logB - ((int64_t)p * NP + p);  // J.M[k * ld + p + a] with ld = NP reads logB[(k - p) * NP + a]
+          cl.J.ld = NP;
+          cl.J.alpha = J.logAlpha - p;
+          cl.J.logB = cl.J.logAlpha = nullptr;
+          cl.ntiles = ntiles;
+          cl.epoch_before = w.slot_epoch[a_slot];
+          w.log.push_back(cl);
+        }
       }
     }
-    if (chosen < n_ids && alg_ok(ch.slot_of_id[chosen])) {  // join side: launched by append_core once Ls, z_B exist
+    if (chosen < n_ids && alg_ok(ch.slot_of_id[chosen]) && (npos > 0 || log_on)) {  // join side: launched by append_core once Ls, z_B exist
       b_slot = ch.slot_of_id[chosen];
       const Chain::WinEntry& en = w.e[w.cur][b_slot];
       fill_pos(hook.jobs, b_slot);
@@ -1092,7 +1217,16 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
   }
   if (!stays) {
     const bool b_alg = hook.fired;
-    if (a_alg || b_alg) {
+    if (b_alg && log_on && hook.on_quick) {
+      ChangeLog cl;
+      cl.slot = b_slot;
+      cl.kind = 1;
+      cl.J = hook.jobs;  // Tn, Li, znew, xn stay valid until the next batch has been absorbed
+      cl.ntiles = hook.ntiles;
+      cl.epoch_before = w.slot_epoch[b_slot];
+      w.log.push_back(cl);
+    }
+    if ((a_alg || b_alg) && npos > 0) {
       PhaseTimer pt(&ch.t_alg);
       if (b_alg) CK(h, cudaStreamWaitEvent(h->quick, h->ev_alg, 0));
       if (a_alg) CK(h, cudaStreamWaitEvent(h->quick, h->ev_q2, 0));
@@ -1159,6 +1293,15 @@ int sweep_pipelined(mogp_engine* h, int64_t n_steps, const int64_t* order, const
     }
     w.cur = pos;
     w.batch_end = pos + B.cnt;
+    TRY(win_replay(h, (int)(jb & 1)));
+    w.log.clear();
+    w.blog_used = 0;
+    {  // room for the logged block columns of this batch's leave-side changes
+      int64_t maxm = 0;
+      for (const Cluster& c : h->cl)
+        if (c.used) maxm = std::max(maxm, c.m);
+      TRY(ensure(h, &h->d_blog, &h->blog_elems, (int64_t)(OWN_BATCH + 1) * ((maxm + (int64_t)OWN_BATCH * NP) * NP + NP)));
+    }
     std::fill(w.slot_alg.begin(), w.slot_alg.end(), 0);
     // re-scoring blocks written two batches ago are no longer referenced
     ScoreRes& arena = h->res_bump[jb & 1];

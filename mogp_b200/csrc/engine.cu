@@ -25,6 +25,23 @@
 
 using namespace mogp;
 
+constexpr int ALG_OUT_SLOTS = 2 + 30;  // outputs of the two within-batch corrections + of a replay (one region per slot)
+
+// The join-side score correction a commit launches right after k_append_small (append_core), see update.cuh.
+struct AlgHook {
+  AlgJobs jobs;
+  int npos = 0, ntiles = 0;
+  bool fired = false, on_quick = false;
+};
+// One rank-n change of the batch being processed, kept so that the same correction can be applied to the NEXT batch's
+// positions when their pass (launched before the change) is absorbed.
+struct ChangeLog {
+  int32_t slot = -1;
+  int kind = 0;            // 0 leave, 1 join
+  AlgJobs J;               // everything but pos[] / out; leave: M / alpha point at the logged copies
+  int ntiles = 0;
+  int64_t epoch_before = 0;
+};
 namespace {
 
 thread_local std::string g_create_error;
@@ -123,8 +140,10 @@ struct Chain {
     std::vector<double> own_ll, own_mu, own_flag;  // [position] leave-block-out score under the patient's own cluster
     std::vector<char> own_ok;
     Batch b[2];
+    std::vector<ChangeLog> log;    // rank-n changes of the current batch (replayed for the next one)
+    int64_t blog_used = 0;         // doubles used in the engine's d_blog
   } win;
-  int64_t win_passes = 0, win_rescores = 0, win_patients = 0, win_algebra = 0;  // accounting
+  int64_t win_passes = 0, win_rescores = 0, win_patients = 0, win_algebra = 0, win_replayed = 0;  // accounting
   double t_open = 0.0, t_ensure = 0.0, t_commit = 0.0, t_alg = 0.0;         // host seconds spent in the three phases of windowed steps
 };
 
@@ -160,12 +179,6 @@ struct BatchBuf {
 constexpr int AP_RING = 20, AP_RING_NBLK = 256;
 constexpr int64_t AP_RING_SLOT = NP * NP + NP + (int64_t)AP_RING_NBLK * NG;
 
-// The join-side score correction a commit launches right after k_append_small (append_core), see update.cuh.
-struct AlgHook {
-  AlgJobs jobs;
-  int npos = 0, ntiles = 0;
-  bool fired = false;
-};
 struct mogp_engine {
   int device = 0;
   cudaStream_t stream = nullptr;   // the stream every helper launches on (normally `main_stream`)
@@ -208,8 +221,10 @@ struct mogp_engine {
   int64_t algw_elems = 0;
   double* d_apring = nullptr;     // ring of small append workspaces (Li | z_B | Gram partials): several appends in flight
   int apring_next = 0;
-  double* d_alg = nullptr;        // their outputs [2 slots][OWN_BATCH positions][2]
+  double* d_alg = nullptr;        // their outputs [ALG_OUT_SLOTS][OWN_BATCH positions][2]
   double* h_alg = nullptr;        // ... pinned
+  double* d_blog = nullptr;       // logged block columns / alpha_B of the current batch's leave-side changes
+  int64_t blog_elems = 0;
   AlgHook* alg_hook = nullptr;  // set while a commit should launch the append-side correction (append_core)
   double* d_upd2 = nullptr;  // row-deletion workspace of the look-ahead streams (own-cluster scores)
   int64_t upd2_elems = 0;
@@ -886,8 +901,8 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
       cudaEventCreateWithFlags(&h->ev_alg, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_apq, cudaEventDisableTiming) != cudaSuccess ||
       cudaMalloc((void**)&h->d_apring, sizeof(double) * AP_RING * AP_RING_SLOT) != cudaSuccess ||
-      cudaMalloc((void**)&h->d_alg, sizeof(double) * 4 * 16) != cudaSuccess ||
-      cudaMallocHost((void**)&h->h_alg, sizeof(double) * 4 * 16) != cudaSuccess ||
+      cudaMalloc((void**)&h->d_alg, sizeof(double) * ALG_OUT_SLOTS * 2 * OWN_BATCH) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_alg, sizeof(double) * ALG_OUT_SLOTS * 2 * OWN_BATCH) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_ahead2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->bb[0].done, cudaEventDisableTiming) != cudaSuccess ||
@@ -945,6 +960,7 @@ void mogp_engine_destroy(mogp_engine* h) {
   if (h->quick2) cudaStreamDestroy(h->quick2);
   cudaFree(h->d_algw2);
   cudaFree(h->d_alg);
+  cudaFree(h->d_blog);
   cudaFree(h->d_algw);
   cudaFree(h->d_apring);
   if (h->h_alg) cudaFreeHost(h->h_alg);
@@ -1087,11 +1103,11 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
 int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out) {
   if (!h || !out) return MOGP_EINVAL;
   prof_drain(h);
-  const double v[13] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
+  const double v[14] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
                         h->chain.t_open, h->chain.t_ensure, h->chain.t_commit,
                         (double)h->prof_launches_c[1], h->prof_ms_c[1], h->prof_bytes_c[1], h->prof_flops_c[1],
-                        (double)h->chain.win_algebra, h->chain.t_alg};
-  for (int i = 0; i < n_out && i < 13; ++i) out[i] = v[i];
+                        (double)h->chain.win_algebra, h->chain.t_alg, (double)h->chain.win_replayed};
+  for (int i = 0; i < n_out && i < 14; ++i) out[i] = v[i];
   return MOGP_OK;
 }
 

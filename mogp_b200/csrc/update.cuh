@@ -218,6 +218,10 @@ struct AlgJobs {
   const double* Tn;     // T of the joining block, Tn[a * stride_n + k]
   int64_t stride_n;
   const double *Li, *znew, *xn;
+  // leave: optional copy of what the correction reads from the cluster (block columns of rows p.., alpha_B), so that
+  // it can be replayed for the NEXT batch's positions after the cluster's buffer has moved on (chain.inl)
+  double* logB;         // [(k - p) * NP + a]
+  double* logAlpha;     // [NP]
 };
 
 __device__ __forceinline__ void alg_finish(const AlgJobs& J, const AlgPos& P, const double* ssn, const double* mun,
@@ -254,7 +258,10 @@ __global__ void __launch_bounds__(256) k_alg_leave_part(const __grid_constant__ 
     double v = 0.0;
     if (a < n && k < J.m && J.p + a <= k) v = J.M[(int64_t)k * J.ld + J.p + a];
     sb[r][a] = v;
+    if (J.logB && blockIdx.y == 0 && k < J.m) J.logB[(int64_t)(k - J.p) * NP + a] = v;
   }
+  if (J.logAlpha && blockIdx.y == 0 && blockIdx.x == 0 && tid < NP) J.logAlpha[tid] = tid < n ? J.alpha[J.p + tid] : 0.0;
+  if (nc == 0) return;  // log only
   for (int idx = tid; idx < TB * NP; idx += 256) {
     const int c = idx / TB, r = idx % TB, k = k0 + r;
     sT[r][c] = (c < nc && k < J.m) ? P.T[(int64_t)c * P.stride + k] : 0.0;

@@ -112,16 +112,21 @@ def test_fast_sweeps_match_oracle(eng, kernel, mean_func, threshold, single_blas
     assert np.allclose(mix.lalloc, orc.lalloc, rtol=1e-13)
 
 
-@pytest.mark.parametrize("lookahead,pipeline", [(16, 2), (32, 2), (64, 2), (32, 1)])
-def test_lookahead_window_equals_patient_by_patient(eng, lookahead, pipeline, monkeypatch):
+@pytest.mark.parametrize("lookahead,pipeline,env", [(16, 2, {}), (32, 2, {}), (48, 2, {}), (64, 2, {}), (32, 1, {}),
+                                                    (48, 2, {"MOGP_RANK_RESCORE": "0"}),   # every change re-scored
+                                                    (48, 2, {"MOGP_REPLAY": "1"}),         # corrections replayed for the next batch
+                                                    (48, 2, {"MOGP_LAUNCH_AFTER": "1", "MOGP_ZIGZAG": "1"})])
+def test_lookahead_window_equals_patient_by_patient(eng, lookahead, pipeline, env, monkeypatch):
     """mogp_chain_sweep with the look-ahead pipeline (batches of patients scored per pass over the factors, the next
-    batch's pass running while the current batch moves, everything re-scored against the clusters that change) walks
-    the same chain as one pass per patient: identical choices per step,
+    batch's pass running while the current batch moves, cached scores corrected by rank-n formulas or re-scored against
+    the clusters that change) walks the same chain as one pass per patient: identical choices per step,
     identical counts, cluster log marginals within 1e-9 relative (after an L-BFGS-B refit in between), on a first sweep where most patients move (every
     window sees invalidations, new clusters and emptied clusters)."""
     from mogp_b200 import MoGP_constrained
     from mogp_b200.synth import alsfrs_like, block_init
     monkeypatch.setenv("MOGP_PIPELINE", str(pipeline))   # 2: the next batch's pass overlaps the current batch's moves
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     N = 400
     X, Y = alsfrs_like(N, seed=5)
     z0 = block_init(N, 6, X)
