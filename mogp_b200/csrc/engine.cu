@@ -956,6 +956,9 @@ void mogp_engine_destroy(mogp_engine* h) {
   cudaFree(h->d_upd2);
   cudaFree(h->d_own1);
   cudaFree(h->d_own2);
+  for (cudaEvent_t e : {h->ev_main, h->ev_side, h->ev_block, h->ev_fork, h->ev_ahead2, h->ev_alg, h->ev_apq, h->ev_q2})
+    if (e) cudaEventDestroy(e);
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->quick) cudaStreamDestroy(h->quick);
   if (h->quick2) cudaStreamDestroy(h->quick2);
   cudaFree(h->d_algw2);
