@@ -496,6 +496,34 @@ int launch_alpha_lml(mogp_engine* h, Cluster& c) {
   return MOGP_OK;
 }
 
+// Blocked right-looking Cholesky + inverse factor, panels grouped FACTOR_KB at a time (factor.cuh).
+void launch_factor(mogp_engine* h, double* L, double* M, int64_t ld, int nb, int* info) {
+  static const int kb = [] {
+    const char* e = getenv("MOGP_FACTOR_KB");  // panels per group (tuning)
+    const int v = e ? atoi(e) : FACTOR_KB;
+    return v >= 1 ? v : FACTOR_KB;
+  }();
+  for (int P0 = 0; P0 < nb; P0 += kb) {
+    const int P1 = std::min(P0 + kb, nb);
+    for (int p = P0; p < P1; ++p) {
+      k_diag<<<1, NTHREADS, DIAG_SMEM, h->stream>>>(L, M, ld, p, info);
+      LAUNCHED(h);
+      if (nb > 1) {
+        k_panel<<<nb - 1, NTHREADS, PANEL_SMEM, h->stream>>>(L, M, ld, p);
+        LAUNCHED(h);
+      }
+      if (p + 1 < nb && !(p == P1 - 1 && P1 < nb)) {  // (the group's last panel leaves everything to k_trail_blk)
+        k_trail<<<dim3(nb, nb - p - 1), NTHREADS, TRAIL_SMEM, h->stream>>>(L, M, ld, p, P1);
+        LAUNCHED(h);
+      }
+    }
+    if (P1 < nb) {
+      k_trail_blk<<<dim3(nb, (nb - P1 + 1) / 2), NTHREADS, TRAILB_SMEM, h->stream>>>(L, M, ld, P0, P1, nb);
+      LAUNCHED(h);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Exact inference at (data, theta): ExactGaussianInference.inference as reached by GPy's
 // GPRegression.__init__ / set_XY / every optimiser evaluation (obsmodel.py:46,73,92,94).
@@ -518,18 +546,7 @@ int infer(mogp_engine* h, Cluster& c) {
     CK(h, cudaMemsetAsync(info, 0, sizeof(int), h->stream));
     k_build<<<dim3(nb, nb), NTHREADS, 0, h->stream>>>(h->d_L, c.M, ld, c.x(), (int)c.m, th, jitter);
     LAUNCHED(h);
-    for (int p = 0; p < nb; ++p) {
-      k_diag<<<1, NTHREADS, DIAG_SMEM, h->stream>>>(h->d_L, c.M, ld, p, info);
-      LAUNCHED(h);
-      if (nb > 1) {
-        k_panel<<<nb - 1, NTHREADS, PANEL_SMEM, h->stream>>>(h->d_L, c.M, ld, p);
-        LAUNCHED(h);
-      }
-      if (p + 1 < nb) {
-        k_trail<<<dim3(nb, nb - p - 1), NTHREADS, TRAIL_SMEM, h->stream>>>(h->d_L, c.M, ld, p);
-        LAUNCHED(h);
-      }
-    }
+    launch_factor(h, h->d_L, c.M, ld, nb, info);
     k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, ld, c.x(), c.y(), (int)c.m, th, c.z());
     LAUNCHED(h);
     TRY(launch_alpha_lml(h, c));
@@ -921,6 +938,7 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
   cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM);
   cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
   cudaFuncSetAttribute(k_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAIL_SMEM);
+  cudaFuncSetAttribute(k_trail_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAILB_SMEM);
   cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM);
   update_set_attributes();
   *out = h;
@@ -1372,18 +1390,7 @@ static int graph_eval(mogp_engine* h, Cluster& c, bool* ok) {
     cudaMemsetAsync(info, 0, sizeof(int), h->stream);
     k_build<<<dim3(nb, nb), NTHREADS, 0, h->stream>>>(h->d_L, c.M, ld, c.x(), (int)c.m, th, 0.0);
     LAUNCHED(h);
-    for (int p = 0; p < nb; ++p) {
-      k_diag<<<1, NTHREADS, DIAG_SMEM, h->stream>>>(h->d_L, c.M, ld, p, info);
-      LAUNCHED(h);
-      if (nb > 1) {
-        k_panel<<<nb - 1, NTHREADS, PANEL_SMEM, h->stream>>>(h->d_L, c.M, ld, p);
-        LAUNCHED(h);
-      }
-      if (p + 1 < nb) {
-        k_trail<<<dim3(nb, nb - p - 1), NTHREADS, TRAIL_SMEM, h->stream>>>(h->d_L, c.M, ld, p);
-        LAUNCHED(h);
-      }
-    }
+    launch_factor(h, h->d_L, c.M, ld, nb, info);
     k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, ld, c.x(), c.y(), (int)c.m, th, c.z());
     LAUNCHED(h);
     int rc = launch_alpha_lml(h, c);
