@@ -518,7 +518,9 @@ void launch_factor(mogp_engine* h, double* L, double* M, int64_t ld, int nb, int
       }
     }
     if (P1 < nb) {
-      k_trail_blk<<<dim3(nb, (nb - P1 + 1) / 2), NTHREADS, TRAILB_SMEM, h->stream>>>(L, M, ld, P0, P1, nb);
+      static const int rows = getenv("MOGP_TRAIL_ROWS") ? atoi(getenv("MOGP_TRAIL_ROWS")) : 2;
+      if (rows == 1) k_trail_blk<1><<<dim3(nb, nb - P1), NTHREADS, TRAIL_SMEM, h->stream>>>(L, M, ld, P0, P1, nb);
+      else k_trail_blk<2><<<dim3(nb, (nb - P1 + 1) / 2), NTHREADS, TRAILB_SMEM, h->stream>>>(L, M, ld, P0, P1, nb);
       LAUNCHED(h);
     }
   }
@@ -938,7 +940,8 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
   cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM);
   cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
   cudaFuncSetAttribute(k_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAIL_SMEM);
-  cudaFuncSetAttribute(k_trail_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAILB_SMEM);
+  cudaFuncSetAttribute(k_trail_blk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAILB_SMEM);
+  cudaFuncSetAttribute(k_trail_blk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAIL_SMEM);
   cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM);
   update_set_attributes();
   *out = h;

@@ -183,15 +183,16 @@ __global__ void __launch_bounds__(NTHREADS) k_trail(double* __restrict__ L, doub
 // After the panels [P0, P1) of a group: rows bi >= P1, two row tiles per CTA (they share the second operand):
 //   bj >= P1 : A_ij -= sum_p L_ip L_jp^T          bj < P1 : Acc_ij += sum_{p >= max(P0, bj)} L_ip M_pj
 constexpr int TRAILB_SMEM = (2 * TB * LD_C + TB * LD_R) * (int)sizeof(double);
+template <int ROWS>  // row tiles per CTA: 2 (shared second operand, 2 CTAs per SM) or 1 (3 CTAs per SM)
 __global__ void __launch_bounds__(NTHREADS) k_trail_blk(double* __restrict__ L, double* __restrict__ M, int64_t ld, int P0, int P1,
                                                         int nb) {
-  const int bj = blockIdx.x, bi0 = P1 + 2 * (int)blockIdx.y, bi1 = bi0 + 1;
-  const bool do0 = bj <= bi0, do1 = bi1 < nb && bj <= bi1;
+  const int bj = blockIdx.x, bi0 = P1 + ROWS * (int)blockIdx.y, bi1 = bi0 + 1;
+  const bool do0 = bj <= bi0, do1 = ROWS == 2 && bi1 < nb && bj <= bi1;
   if (!do0 && !do1) return;
   extern __shared__ __align__(16) double smem[];
   double* sA0 = smem;               // L_{bi0,p}  [64][LD_C]
-  double* sA1 = sA0 + TB * LD_C;    // L_{bi1,p}
-  double* sB = sA1 + TB * LD_C;     // L_jp [64][LD_C]  or  M_pj [64][LD_R]
+  double* sA1 = sA0 + TB * LD_C;    // L_{bi1,p}   (ROWS == 2)
+  double* sB = ROWS == 2 ? sA1 + TB * LD_C : sA1;  // L_jp [64][LD_C]  or  M_pj [64][LD_R]
   const bool lpart = bj >= P1;
   Acc64 acc0, acc1;
   acc0.zero();

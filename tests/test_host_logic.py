@@ -108,3 +108,19 @@ def test_sweep_draw_ledger_matches_reference_order():
         assert a[s] == np.random.randn(1, 1)[0, 0]
         assert u[s] == np.random.random_sample()
     assert np.array_equal(perm, perm_ref)
+
+
+def test_chain_config_carries_the_sampler_options():
+    """The Python facade hands the engine the reference's model constants and the look-ahead option; the struct
+    layout is the C header's (include/mogp_b200.h: mogp_chain_config)."""
+    import ctypes as C
+    from mogp_b200 import MoGP_constrained
+    X, Y = generate_toy_data(seed=0)
+    mix = MoGP_constrained(X=X, Y=Y, alpha=1.5, threshold=0.5, noise_variance=0.5, refit='sweep', lookahead=24)
+    cfg = mix._chain_config()
+    assert (cfg.alpha, cfg.noise_variance, cfg.signal_variance, cfg.lengthscale) == (1.5, 0.5, 1.0, 4.0)
+    assert (cfg.use_threshold, cfg.thr_index, cfg.threshold, cfg.fast_updates, cfg.lookahead) == (1, 1, 0.5, 1, 24)
+    assert MoGP_constrained(X=X, Y=Y, alpha=1.)._chain_config().lookahead == 0      # engine default
+    assert MoGP_constrained(X=X, Y=Y, alpha=1.)._chain_config().fast_updates == 0   # refit='move': reference-exact updates
+    # spec (4 x int32) | 4 doubles | 2 x int32 | double | 2 x int32
+    assert C.sizeof(_capi.ChainConfig) == 16 + 32 + 8 + 8 + 8
