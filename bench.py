@@ -435,7 +435,7 @@ def run_predict(args):
                 "e2e": {"value": pairs / (float(t.item()) * 1e-3), "unit": "logliks/s",
                         "h2d_bytes_per_step": (b1[0] - b0[0]) // args.steps, "d2h_bytes_per_step": (b1[1] - b0[1]) // args.steps},
                 "gpu_launches": int(eng.launch_count() - l0),
-                "roofline": {"kernel": "k_score_gemm<64>", "bound": "fp64", "achieved": prof["alg_flops"] / (prof["ms"] * 1e-3) / 1e12,
+                "roofline": {"kernel": "k_score_wide<8> (64-column tiles)", "bound": "fp64", "achieved": prof["alg_flops"] / (prof["ms"] * 1e-3) / 1e12,
                              "peak": peak, "unit": "TFLOP/s", "frac": prof["alg_flops"] / (prof["ms"] * 1e-3) / 1e12 / peak,
                              "traffic": None, "peak_source": "measured DMMA.8x8x4 register-loop peak (profiles/r1_fp64_peaks.txt)",
                              "share_of_step": prof["ms"] / ms},
