@@ -496,6 +496,17 @@ int launch_alpha_lml(mogp_engine* h, Cluster& c) {
   return MOGP_OK;
 }
 
+// Row tiles of the contraction W = M^T M per CTA of the gradient kernel: every chunk CTA repeats the kernel-derivative
+// epilogue of its tile pair, so fewer, longer chunks do less redundant work (MOGP_GRAD_KC: tuning).
+int grad_kc() {
+  static const int v = [] {
+    const char* e = getenv("MOGP_GRAD_KC");
+    const int k = e ? atoi(e) : GRAD_KC;
+    return k >= 1 ? k : GRAD_KC;
+  }();
+  return v;
+}
+
 // Blocked right-looking Cholesky + inverse factor, panels grouped FACTOR_KB at a time (factor.cuh).
 void launch_factor(mogp_engine* h, double* L, double* M, int64_t ld, int nb, int* info) {
   static const int kb = [] {
@@ -593,7 +604,7 @@ int infer_grad(mogp_engine* h, Cluster& c) {
   TRY(fetch_stat(h, c));  // x.alpha of a rank-updated cluster is reduced lazily
   const int64_t mpad = round_up(c.m, TB);
   const int nb = (int)(mpad / TB);
-  const int nz = (nb + GRAD_KC - 1) / GRAD_KC;
+  const int nz = (nb + grad_kc() - 1) / grad_kc();
   const int64_t n_partial = (int64_t)nb * nb * nz;
   TRY(ensure(h, &h->d_partial, &h->partial_elems, n_partial * 3));
   TRY(ensure_pin(h, 256));  // (a worker engine may get here without ever having run an inference itself)
@@ -601,7 +612,7 @@ int infer_grad(mogp_engine* h, Cluster& c) {
   const Theta* th = c.theta_dev();
   double* st = c.stat();
   k_grad<<<dim3(nb, nb, nz), NTHREADS, GRAD_SMEM, h->stream>>>(c.M, c.cap, nb, c.x(), c.alpha(), (int)c.m, th,
-                                                                h->d_partial);
+                                                                h->d_partial, grad_kc());
   LAUNCHED(h);
   k_grad_final<<<1, 256, 0, h->stream>>>(h->d_partial, (int)n_partial, th, st, st + 10);
   LAUNCHED(h);
@@ -1371,7 +1382,7 @@ static int graph_eval(mogp_engine* h, Cluster& c, bool* ok) {
   const int64_t mpad = round_up(c.m, TB);
   const int nb = (int)(mpad / TB);
   const int64_t ld = c.cap;
-  const int nz = (nb + GRAD_KC - 1) / GRAD_KC;
+  const int nz = (nb + grad_kc() - 1) / grad_kc();
   const int64_t n_partial = (int64_t)nb * nb * nz;
   const int nchunk = (int)((c.m + ALPHA_ROWS - 1) / ALPHA_ROWS);
   TRY(ensure(h, &h->d_L, &h->L_elems, ld * mpad));
@@ -1397,7 +1408,7 @@ static int graph_eval(mogp_engine* h, Cluster& c, bool* ok) {
     k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, ld, c.x(), c.y(), (int)c.m, th, c.z());
     LAUNCHED(h);
     int rc = launch_alpha_lml(h, c);
-    k_grad<<<dim3(nb, nb, nz), NTHREADS, GRAD_SMEM, h->stream>>>(c.M, c.cap, nb, c.x(), c.alpha(), (int)c.m, th, h->d_partial);
+    k_grad<<<dim3(nb, nb, nz), NTHREADS, GRAD_SMEM, h->stream>>>(c.M, c.cap, nb, c.x(), c.alpha(), (int)c.m, th, h->d_partial, grad_kc());
     LAUNCHED(h);
     k_grad_final<<<1, 256, 0, h->stream>>>(h->d_partial, (int)n_partial, th, st, st + 10);
     LAUNCHED(h);

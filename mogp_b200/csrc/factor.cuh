@@ -340,16 +340,18 @@ __global__ void __launch_bounds__(1024) k_lml(const double* __restrict__ M, int6
 //   S2 = trace(dL_dK)               (-> d/d noise)
 // with dL_dK = (alpha alpha^T - W)/2 (GPy ExactGaussianInference).  Partials are written per CTA
 // and summed in a fixed order by k_grad_final, so the result is run-to-run deterministic.
-constexpr int GRAD_KC = 4;
+constexpr int GRAD_KC = 64;  // contraction chunk (row tiles per CTA; 4 -> 64: 334 -> 245 us at m = 2600, every chunk CTA
+                            // repeats the kernel-derivative epilogue of its tile pair); grad_kc() in engine.cu may override it
 constexpr int GRAD_SMEM = (2 * TB * LD_R) * (int)sizeof(double);
 
 __global__ void __launch_bounds__(NTHREADS) k_grad(const double* __restrict__ M, int64_t ld, int nb,
                                                    const double* __restrict__ x, const double* __restrict__ alpha,
-                                                   int m, const Theta* __restrict__ thp, double* __restrict__ partial) {
+                                                   int m, const Theta* __restrict__ thp, double* __restrict__ partial,
+                                                   int kchunk) {
   const Theta th = *thp;
   const int bj = blockIdx.x, bi = blockIdx.y, kc = blockIdx.z;
   const int cta = (kc * gridDim.y + bi) * gridDim.x + bj;
-  const int k0 = bi + kc * GRAD_KC;
+  const int k0 = bi + kc * kchunk;
   __shared__ double red[3][NTHREADS / 32];
   if (bj > bi || k0 >= nb) {
     if (threadIdx.x < 3) partial[(int64_t)cta * 3 + threadIdx.x] = 0.0;
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(const double* __restrict__ M,
   double* sB = sA + TB * LD_R;
   Acc64 acc;
   acc.zero();
-  const int k1 = min(nb, k0 + GRAD_KC);
+  const int k1 = min(nb, k0 + kchunk);
   for (int k = k0; k < k1; ++k) {
     __syncthreads();
     load_tile<LD_R>(sA, M + (int64_t)k * TB * ld + (int64_t)bi * TB, ld);
