@@ -1254,6 +1254,38 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
     else if (slot_prev >= 0) win_invalidate(ch, slot_prev);
     if (b_alg && ch.slot_of_id[chosen] == b_slot) corrected(b_slot, h->h_alg + 2 * OWN_BATCH);
     else win_invalidate(ch, ch.slot_of_id[chosen]);
+    if (npos > 0 && env_int("MOGP_CHECK_CORRECTIONS", 0) != 0) {
+      // Test mode: re-score the corrected positions the long way (from the UPDATED factors, waiting for them) and
+      // record the worst disagreement with the rank-n formulas; the re-scored values take over.
+      std::vector<int32_t> chk;
+      if (a_alg && slot_prev == a_slot) chk.push_back(a_slot);
+      if (b_alg && ch.slot_of_id[chosen] == b_slot) chk.push_back(b_slot);
+      if (!chk.empty()) {
+        const int64_t v0 = w.cur + 1, rem = w.batch_end - v0, Rrem = w.col0[w.batch_end] - w.col0[v0], Rtot = w.col0[w.n];
+        const int nb = (int)chk.size();
+        const int thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
+        TRY(ensure(h, &h->d_out, &h->out_elems, 2 * rem * nb + 8));
+        join_side(h);
+        ScorePlan pl;
+        TRY(score_device(h, rem, Rrem, h->d_woff + v0, h->d_wq + w.col0[v0], h->d_wq + Rtot + w.col0[v0], nb, chk.data(), thr_index,
+                         h->d_out, h->d_out + rem * nb, nullptr, nullptr, nullptr, true, &pl, arena));
+        std::vector<double> host(2 * rem * nb);
+        TRY(copy_back(h, host.data(), h->d_out, 2 * rem * nb));
+        for (int si = 0; si < nb; ++si)
+          for (int64_t q = 0; q < rem; ++q) {
+            const Chain::WinEntry& e = w.e[v0 + q][chk[si]];
+            const double s_ref = host[q * nb + si], m_ref = host[rem * nb + q * nb + si];
+            double err = fabs(e.score - s_ref) / std::max(1.0, fabs(s_ref));
+            if (!(isnan(m_ref) && isnan(e.muthr))) err = std::max(err, fabs(e.muthr - m_ref) / std::max(1.0, fabs(m_ref)));
+            if (!(err <= ch.max_corr_err)) ch.max_corr_err = err;  // (NaN sticks)
+          }
+        const int64_t keep_cur = w.cur;
+        w.cur = v0;  // win_store fills [v0, batch_end)
+        win_store(h, v0, chk, pl, host.data(), host.data() + rem * nb);
+        w.cur = keep_cur;
+        ch.corr_checked += rem * nb;
+      }
+    }
   }
   if (chosen_out) *chosen_out = chosen;
   std::vector<Chain::WinEntry>().swap(w.e[w.cur]);

@@ -144,7 +144,9 @@ struct Chain {
     int64_t blog_used = 0;         // doubles used in the engine's d_blog
   } win;
   int64_t win_passes = 0, win_rescores = 0, win_patients = 0, win_algebra = 0, win_replayed = 0;  // accounting
-  double t_open = 0.0, t_ensure = 0.0, t_commit = 0.0, t_alg = 0.0;         // host seconds spent in the three phases of windowed steps
+  double t_open = 0.0, t_ensure = 0.0, t_commit = 0.0, t_alg = 0.0;
+  double max_corr_err = 0.0;     // MOGP_CHECK_CORRECTIONS: worst |rank-n corrected - re-scored| (relative)
+  int64_t corr_checked = 0;         // host seconds spent in the three phases of windowed steps
 };
 
 // Device scratch + slot-view staging of a scoring pass.  Several passes can be in flight (the next batch's pass on the
@@ -1138,11 +1140,12 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
 int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out) {
   if (!h || !out) return MOGP_EINVAL;
   prof_drain(h);
-  const double v[14] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
+  const double v[16] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
                         h->chain.t_open, h->chain.t_ensure, h->chain.t_commit,
                         (double)h->prof_launches_c[1], h->prof_ms_c[1], h->prof_bytes_c[1], h->prof_flops_c[1],
-                        (double)h->chain.win_algebra, h->chain.t_alg, (double)h->chain.win_replayed};
-  for (int i = 0; i < n_out && i < 14; ++i) out[i] = v[i];
+                        (double)h->chain.win_algebra, h->chain.t_alg, (double)h->chain.win_replayed,
+                        h->chain.max_corr_err, (double)h->chain.corr_checked};
+  for (int i = 0; i < n_out && i < 16; ++i) out[i] = v[i];
   return MOGP_OK;
 }
 

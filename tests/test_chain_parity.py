@@ -156,6 +156,29 @@ def test_lookahead_window_equals_patient_by_patient(eng, lookahead, pipeline, en
         assert abs(l0[k] - l1[k]) <= 1e-9 * max(1.0, abs(l0[k]))
 
 
+def test_rank_n_score_corrections_equal_rescoring(eng, monkeypatch):
+    """After a move the cached scores of the patients ahead under the two clusters it changed are corrected by rank-n
+    formulas (k_alg_leave / k_alg_join) while the factors are still being updated.  In check mode every corrected pair is
+    re-scored from the UPDATED factor: log-likelihoods and threshold means agree within 1e-9 relative."""
+    from mogp_b200 import MoGP_constrained
+    from mogp_b200.synth import alsfrs_like, block_init
+    monkeypatch.setenv("MOGP_CHECK_CORRECTIONS", "1")
+    N = 600
+    X, Y = alsfrs_like(N, seed=11)
+    z0 = block_init(N, 5, X)
+    mix = MoGP_constrained(X=X.copy(), Y=Y.copy(), engine=eng, alpha=1.5, num_iter=3, rand_seed=4, normalize=True,
+                           threshold=0.5, noise_variance=0.5, refit='sweep', init_z=z0)
+    mix.initialize_sampler(mix.num_init_clusters, True)
+    c0 = eng.chain_counters()
+    for _ in range(2):
+        mix.sweep()
+    c1 = eng.chain_counters()
+    checked = c1["corrections_checked"] - c0["corrections_checked"]
+    print("pairs checked:", checked, "worst relative disagreement:", c1["max_correction_err"])
+    assert c1["rank_corrections"] - c0["rank_corrections"] > 50 and checked > 200
+    assert c1["max_correction_err"] <= 1e-9
+
+
 @pytest.mark.slow
 def test_cfg1_reference_schedule_200_patients(eng):
     """BASELINE configs[0] shape (MoGP_constrained, 200 sparse ALSFRS-R-like patients, rbf, threshold 0.5, refit after
