@@ -7,7 +7,8 @@
 // packed as columns):
 //   KxT[c][col][j] = k(x_c[j], x*_col)                       k_kx   (cross covariance, built once)
 //   mu[c][col]     = sum_j KxT alpha_c[j]  - A_c x*_col      k_kx
-//   T = M_c Kx  (DMMA), part[c][rb][col] = sum_{i in row block rb} T[i][col]^2      k_score_gemm
+//   T = M_c Kx  (DMMA), part[c][rb][col] = sum_{i in row block rb} T[i][col]^2      k_score_gemm (<= 16 columns) /
+//                                                                                   k_score_wide (24..64 columns)
 //   v* = kdiag - sum_rb part, clipped at 1e-15;  lpd = -ln(2pi)/2 - ln(v*+s2)/2 - (y-mu)^2/(2(v*+s2))
 //   score[p][c] = sum over the patient's visits                                    k_score_epi
 // Only the diagonal predictive variance is used, visits are scored independently.
@@ -112,21 +113,17 @@ __global__ void __launch_bounds__(256) k_score_reduce(SLOT_ARGS, int Rpad, const
 }
 
 // T = M Kx for a 64-row block and a BN-column tile; emits column sums of squares per row block.
-// grid (n_col_tiles, n_slots, max_nb).  BN in {8,16,32,64}.
+// grid (n_col_tiles, n_slots, max_nb).  BN in {8, 16}: the HBM-bound widths (wider tiles: k_score_wide below).
 template <int BN>
 struct ScoreShape;
 template <>
 struct ScoreShape<8> { static constexpr int MS = 1, NS = 1, WM = 8, WN = 1; };
 template <>
 struct ScoreShape<16> { static constexpr int MS = 1, NS = 2, WM = 8, WN = 1; };
-template <>
-struct ScoreShape<32> { static constexpr int MS = 2, NS = 2, WM = 4, WN = 2; };
-template <>
-struct ScoreShape<64> { static constexpr int MS = 2, NS = 4, WM = 4, WN = 2; };
 
 // Stages of the tile pipeline by column-tile width (one CTA per SM; a stage = one 64x64 tile of M + BN x 64 of KxT).
 template <int BN>
-struct ScoreStages { static constexpr int S = BN <= 16 ? 5 : (BN == 32 ? 4 : 3); };
+struct ScoreStages { static constexpr int S = 5; };
 template <int BN>
 struct ScoreSmem {
   static constexpr int STAGE = (TB + BN) * LD_C;  // doubles per stage
