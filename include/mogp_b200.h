@@ -80,6 +80,13 @@ int mogp_set_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, co
 
 /* Re-send the same table (same offsets) from host memory without disturbing an attached chain. */
 int mogp_refresh_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x, const double* y);
+/* The same table built ON THE DEVICE from the reference's own data format: X, Y are the NaN-padded n_patients x T
+   row-major matrices a caller hands to MoGP_constrained (mogp_constrained.py:28; rows compacted per patient at
+   :246-247); thr_col = index_to_eval (1 with an onset anchor, :256).  A row whose X and Y have different numbers of
+   non-NaN cells is MOGP_EINVAL.  Optional outputs (host, caller-allocated: off_out[n_patients + 1], x_out / y_out
+   [n_patients * T]) receive the compacted table, *n_visits_out its length. */
+int mogp_set_patients_matrix(mogp_engine* h, int64_t n_patients, int32_t T, const double* X, const double* Y, int32_t thr_col,
+                             int64_t* off_out, double* x_out, double* y_out, int64_t* n_visits_out);
 
 /* ---- accounting for bench.py ------------------------------------------------------------------ */
 /* Bytes this engine has copied host->device / device->host since creation. */

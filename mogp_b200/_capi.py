@@ -51,6 +51,7 @@ SIGNATURES = {
     "mogp_timer_stop": (C.c_int, [_H, _dp]),
     "mogp_set_patients": (C.c_int, [_H, C.c_int64, _lp, _dp, _dp, _dp]),
     "mogp_refresh_patients": (C.c_int, [_H, C.c_int64, _lp, _dp, _dp]),
+    "mogp_set_patients_matrix": (C.c_int, [_H, C.c_int64, C.c_int32, _dp, _dp, C.c_int32, _lp, _dp, _dp, _lp]),
     "mogp_transfer_bytes": (C.c_int, [_H, _lp, _lp]),
     "mogp_profile": (C.c_int, [_H, C.c_int32]),
     "mogp_profile_read": (C.c_int, [_H, _lp, _dp, _dp, _dp, C.c_int32]),
@@ -176,6 +177,23 @@ class Engine:
         x, y = f64(x), f64(y)
         y_thr = None if y_thr is None else f64(y_thr)
         self.check(self.lib.mogp_set_patients(self.h, len(off) - 1, lptr(off), dptr(x), dptr(y), dptr(y_thr)))
+
+    def set_patients_matrix(self, X, Y, thr_col=-1):
+        """Patient table from the reference's NaN-padded N x T matrices, compacted on the device; returns the CSR
+        (off, x, y) it built (== utils.pack_patients(X, Y), bit for bit)."""
+        X, Y = f64(X), f64(Y)
+        if X.ndim != 2 or X.shape != Y.shape:
+            raise ValueError("X and Y must be N x T matrices of the same shape")
+        N, T = X.shape
+        off = np.zeros(N + 1, dtype=np.int64)
+        x, y = np.empty(N * T), np.empty(N * T)
+        nv = C.c_int64()
+        rc = self.lib.mogp_set_patients_matrix(self.h, N, T, dptr(X), dptr(Y), int(thr_col), lptr(off), dptr(x), dptr(y),
+                                               C.cast(C.byref(nv), _lp))
+        if rc == MOGP_EINVAL and b"different numbers" in self.lib.mogp_last_error(self.h):
+            raise ValueError("X and Y have different numbers of non-NaN cells in some row")
+        self.check(rc)
+        return off, x[:nv.value].copy(), y[:nv.value].copy()
 
     def refresh_patients(self, off, x, y):
         self.check(self.lib.mogp_refresh_patients(self.h, len(off) - 1, lptr(off), dptr(x), dptr(y)))

@@ -1100,6 +1100,80 @@ int mogp_set_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, co
   return MOGP_OK;
 }
 
+int mogp_set_patients_matrix(mogp_engine* h, int64_t n_patients, int32_t T, const double* X, const double* Y, int32_t thr_col,
+                             int64_t* off_out, double* x_out, double* y_out, int64_t* n_visits_out) {
+  if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
+  if (n_patients <= 0 || T <= 0 || !X || !Y) FAIL(h, MOGP_EINVAL, "bad patient matrices");
+  const int64_t cells = n_patients * (int64_t)T;
+  double *dX = nullptr, *dthr = nullptr;
+  int64_t* dcnt = nullptr;
+  int* dflag = nullptr;
+  struct Guard {
+    double *&a, *&b;
+    int64_t*& c;
+    int*& d;
+    ~Guard() {
+      cudaFree(a);
+      cudaFree(b);
+      cudaFree(c);
+      cudaFree(d);
+    }
+  } guard{dX, dthr, dcnt, dflag};
+  CK(h, cudaMalloc((void**)&dX, sizeof(double) * 2 * cells));
+  CK(h, cudaMalloc((void**)&dthr, sizeof(double) * n_patients));
+  CK(h, cudaMalloc((void**)&dcnt, sizeof(int64_t) * n_patients));
+  CK(h, cudaMalloc((void**)&dflag, sizeof(int)));
+  double* dY = dX + cells;
+  CK(h, cudaMemcpyAsync(dX, X, sizeof(double) * cells, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(dY, Y, sizeof(double) * cells, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemsetAsync(dflag, 0, sizeof(int), h->stream));
+  h->bytes_h2d += (int64_t)sizeof(double) * 2 * cells;
+  cudaFree(h->d_off);
+  cudaFree(h->d_px);
+  cudaFree(h->d_py);
+  h->d_off = nullptr;
+  h->d_px = h->d_py = nullptr;
+  h->P = 0;
+  h->chain.active = false;
+  CK(h, cudaMalloc((void**)&h->d_off, sizeof(int64_t) * (n_patients + 1)));
+  CK(h, cudaMalloc((void**)&h->d_px, sizeof(double) * cells));
+  CK(h, cudaMalloc((void**)&h->d_py, sizeof(double) * cells));
+  const unsigned gb = (unsigned)((n_patients + 255) / 256);
+  k_pack_count<<<gb, 256, 0, h->stream>>>(dX, dY, n_patients, T, dcnt, dflag);
+  LAUNCHED(h);
+  k_pack_scan<<<1, 1024, 0, h->stream>>>(dcnt, n_patients, h->d_off);
+  LAUNCHED(h);
+  k_pack_scatter<<<gb, 256, 0, h->stream>>>(dX, dY, n_patients, T, h->d_off, thr_col, h->d_px, h->d_py, dthr);
+  LAUNCHED(h);
+  int flag = 0;
+  h->h_off.assign(n_patients + 1, 0);
+  h->h_ythr.assign(n_patients, 0.0);
+  CK(h, cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(h->h_off.data(), h->d_off, sizeof(int64_t) * (n_patients + 1), cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(h->h_ythr.data(), dthr, sizeof(double) * n_patients, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, sync_stream(h));
+  CK(h, cudaGetLastError());
+  if (flag) FAIL(h, MOGP_EINVAL, "X and Y have different numbers of non-NaN cells in some row");
+  const int64_t V = h->h_off[n_patients];
+  h->h_x.assign(V, 0.0);
+  h->h_y.assign(V, 0.0);
+  if (V > 0) {
+    CK(h, cudaMemcpyAsync(h->h_x.data(), h->d_px, sizeof(double) * V, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(h->h_y.data(), h->d_py, sizeof(double) * V, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, sync_stream(h));
+  }
+  h->bytes_d2h += (int64_t)(sizeof(int64_t) * (n_patients + 1) + sizeof(double) * (2 * V + n_patients));
+  h->P = n_patients;
+  h->V = V;
+  if (thr_col < 0) h->h_ythr.clear();
+  if (off_out) memcpy(off_out, h->h_off.data(), sizeof(int64_t) * (n_patients + 1));
+  if (x_out && V > 0) memcpy(x_out, h->h_x.data(), sizeof(double) * V);
+  if (y_out && V > 0) memcpy(y_out, h->h_y.data(), sizeof(double) * V);
+  if (n_visits_out) *n_visits_out = V;
+  return MOGP_OK;
+}
+
 /* Re-send the same patient table (same offsets) from the host without disturbing the chain: the per-sweep
    host->device copy of an end-to-end run whose data live in host memory. */
 int mogp_refresh_patients(mogp_engine* h, int64_t n_patients, const int64_t* off, const double* x, const double* y) {

@@ -400,6 +400,57 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_score_wide(SLOT_ARGS, const
   wide_item<NS>(sv, rb, chunk, blockIdx.x * BN, kxT, Rpad, part, Tout, cp, smem, red);
 }
 
+// ---- patient table from the NaN-padded N x T matrices (mogp_constrained.py:246-247) -------------------------------
+// counts per row, exclusive scan (one CTA walks the rows in chunks of 1024: not a hot path), compaction per row.
+__global__ void k_pack_count(const double* __restrict__ X, const double* __restrict__ Y, int64_t N, int T,
+                             int64_t* __restrict__ cnt, int* __restrict__ mismatch) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int cx = 0, cy = 0;
+  for (int t = 0; t < T; ++t) {
+    cx += !isnan(X[n * T + t]);
+    cy += !isnan(Y[n * T + t]);
+  }
+  cnt[n] = cx;
+  if (cx != cy) atomicExch(mismatch, 1);
+}
+__global__ void __launch_bounds__(1024) k_pack_scan(const int64_t* __restrict__ cnt, int64_t N, int64_t* __restrict__ off) {
+  __shared__ int64_t buf[1024];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < N; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    int64_t v = i < N ? cnt[i] : 0;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // inclusive Hillis-Steele scan of the chunk
+      int64_t add = (int)threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (i < N) off[i] = carry + buf[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[N] = carry;
+}
+__global__ void k_pack_scatter(const double* __restrict__ X, const double* __restrict__ Y, int64_t N, int T,
+                               const int64_t* __restrict__ off, int thr_col, double* __restrict__ x, double* __restrict__ y,
+                               double* __restrict__ ythr) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int64_t ox = off[n], oy = off[n];
+  for (int t = 0; t < T; ++t) {
+    const double xv = X[n * T + t], yv = Y[n * T + t];
+    if (!isnan(xv)) x[ox++] = xv;
+    if (!isnan(yv)) y[oy++] = yv;
+  }
+  ythr[n] = (thr_col >= 0 && thr_col < T) ? Y[n * T + thr_col] : nan("");
+}
+
 // Per (patient, slot): finish the predictive moments and sum the per-visit log densities.  One warp per pair:
 // lanes take the patient's visits (columns), each sums its column's row-block partials in a fixed order, the
 // visit log densities are added across the warp by a shuffle tree (deterministic).

@@ -215,10 +215,9 @@ class MoGP_constrained:
         for k in range(n_ids):
             a = np.random.randn(1, 1)[0, 0] if self.mean_func else None
             theta[k] = initial_theta(self.kernel, self.signal_variance, self.noise_variance, 4., a)
-        off, x, y = pack_patients(self.X, self.Y)
-        idx = 1 if onset_anchor else 0
-        y_thr = self.Y[:, idx] if self.Y.shape[1] > idx else np.full(self.Y.shape[0], np.nan)
-        self.engine.set_patients(off, x, y, y_thr)
+        # the NaN-padded matrices go to the engine as they are: compaction to the per-patient rows of
+        # mogp_constrained.py:246-247 and the threshold cells Y[:, index_to_eval] (:256) are built on the device
+        self.engine.set_patients_matrix(self.X, self.Y, 1 if onset_anchor else 0)
         self.engine.chain_init(self._chain_config(), z, theta)
         self.obsmodel = dict()
         self._sync_state()

@@ -178,3 +178,31 @@ def test_full_size_sweep_of_rank_updates_matches_refactorisation(eng):
         sc_f = eng.score_pairs(np.array([0, 9]), xq, yq, [f])[0, 0]
         assert abs(sc_u - sc_f) <= 1e-10 * abs(sc_f)
         eng.cluster_free(f)
+
+
+def test_patient_table_built_on_the_device_equals_numpy_compaction(eng):
+    """mogp_set_patients_matrix compacts the reference's NaN-padded N x T matrices on the device
+    (mogp_constrained.py:246-247): the CSR it builds equals utils.pack_patients bit for bit - ragged rows, NaN in the
+    middle of a row, empty rows, one column, many rows (the scan walks 1024-row chunks) - and a row whose X and Y
+    disagree in their NaN pattern is refused like the host packer refuses it."""
+    from mogp_b200.utils import pack_patients
+    rs = np.random.RandomState(7)
+    for N, T in ((1, 1), (3, 4), (1025, 11), (5000, 11), (257, 23)):
+        X = rs.uniform(0, 8, (N, T))
+        Y = rs.randn(N, T)
+        drop = rs.uniform(size=(N, T)) < 0.35
+        if N > 2:
+            drop[1, :] = True                                   # a patient without visits
+            drop[2, :] = False
+        X[drop] = np.nan
+        Y[drop] = np.nan
+        off, x, y = eng.set_patients_matrix(X, Y, thr_col=1)
+        off0, x0, y0 = pack_patients(X, Y)
+        assert np.array_equal(off, off0)
+        assert x.tobytes() == x0.tobytes() and y.tobytes() == y0.tobytes()
+    X = np.array([[0., 1., np.nan], [0., 1., 2.]])
+    Y = np.array([[48., np.nan, np.nan], [48., 40., 30.]])
+    with pytest.raises(ValueError, match="different numbers of non-NaN cells"):
+        eng.set_patients_matrix(X, Y)
+    with pytest.raises(ValueError, match="different numbers of non-NaN cells"):
+        pack_patients(X, Y)
