@@ -483,7 +483,9 @@ def run_chains(args):
         mix.sweep(perm, np.zeros(N), u)
         return eng.launch_count()
 
-    pool = ThreadPoolExecutor(max_workers=max(1, len(chains)))
+    # every chain has its own engine and streams; the host threads that drive them are bounded by the cores
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
+    pool = ThreadPoolExecutor(max_workers=max(1, min(len(chains), max(4, 2 * cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))))))
     for _ in range(args.warmup):
         list(pool.map(sweep, chains))
     torch.cuda.synchronize()

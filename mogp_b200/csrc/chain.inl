@@ -837,7 +837,7 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
                      nullptr, nullptr, nullptr, true, &b.pl, &bf.res));
   CK(h, cudaStreamWaitEvent(h->ahead, h->ev_ahead2, 0));
   CK(h, cudaMemcpyAsync(bf.h_out, bf.d_out, sizeof(double) * total, cudaMemcpyDeviceToHost, h->ahead));
-  CK(h, cudaEventRecord(bf.done, h->ahead));
+  CK(h, cudaEventRecord(h->blocking_sync ? bf.done_blk : bf.done, h->ahead));
   CK(h, cudaGetLastError());
   h->bytes_d2h += (int64_t)sizeof(double) * total;
   w.end_launched = s0 + cnt;
@@ -853,7 +853,7 @@ int batch_absorb(mogp_engine* h, int bi) {
   Chain::Window& w = ch.win;
   Chain::Batch& b = w.b[bi];
   BatchBuf& bf = h->bb[bi];
-  CK(h, cudaEventSynchronize(bf.done));
+  CK(h, cudaEventSynchronize(h->blocking_sync ? bf.done_blk : bf.done));
   const int ns = (int)b.slots.size();
   const int64_t cnt = b.cnt, cb = w.col0[b.s0];
   const double* hs = bf.h_out;
@@ -963,7 +963,7 @@ int win_replay(mogp_engine* h, int bi) {
   }
   const int64_t nout = (2 + (int64_t)items.size()) * 2 * OWN_BATCH;
   CK(h, cudaMemcpyAsync(h->h_alg, h->d_alg, sizeof(double) * nout, cudaMemcpyDeviceToHost, h->quick));
-  CK(h, cudaStreamSynchronize(h->quick));
+  CK(h, sync_helper_stream(h, h->quick));
   h->bytes_d2h += (int64_t)sizeof(double) * nout;
   for (size_t idx = 0; idx < items.size(); ++idx) {
     const int32_t slot = items[idx].cl->slot;
@@ -1231,7 +1231,7 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
       if (b_alg) CK(h, cudaStreamWaitEvent(h->quick, h->ev_alg, 0));
       if (a_alg) CK(h, cudaStreamWaitEvent(h->quick, h->ev_q2, 0));
       CK(h, cudaMemcpyAsync(h->h_alg, h->d_alg, sizeof(double) * 4 * OWN_BATCH, cudaMemcpyDeviceToHost, h->quick));
-      CK(h, cudaStreamSynchronize(h->quick));
+      CK(h, sync_helper_stream(h, h->quick));
       h->bytes_d2h += (int64_t)sizeof(double) * 4 * OWN_BATCH;
       ch.win_algebra += 1;
     }

@@ -170,7 +170,8 @@ struct BatchBuf {
   int64_t out_elems = 0;
   double* h_out = nullptr;
   int64_t hout_elems = 0;
-  cudaEvent_t done = nullptr;
+  cudaEvent_t done = nullptr;      // the pass and its read-back have finished (host spins on it)
+  cudaEvent_t done_blk = nullptr;  // the same for engines in blocking-sync mode (host sleeps: many chains per process)
 };
 
 }  // namespace
@@ -348,6 +349,13 @@ cudaError_t sync_stream(mogp_engine* h) {
   }
   h->up_off = 0;
   return e;
+}
+
+// Host wait for everything queued on stream s (one of the engine's helper streams), in the engine's waiting mode.
+cudaError_t sync_helper_stream(mogp_engine* h, cudaStream_t s) {
+  if (!h->blocking_sync) return cudaStreamSynchronize(s);
+  cudaError_t e = cudaEventRecord(h->ev_block, s);
+  return e == cudaSuccess ? cudaEventSynchronize(h->ev_block) : e;
 }
 
 // Launches made while a SideScope is alive go to the side stream, ordered after everything already queued on
@@ -939,6 +947,8 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
       cudaEventCreateWithFlags(&h->ev_ahead2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->bb[0].done, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->bb[1].done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->bb[0].done_blk, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->bb[1].done_blk, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess ||
@@ -986,6 +996,7 @@ void mogp_engine_destroy(mogp_engine* h) {
     cudaFree(h->bb[i].d_out);
     if (h->bb[i].h_out) cudaFreeHost(h->bb[i].h_out);
     if (h->bb[i].done) cudaEventDestroy(h->bb[i].done);
+    if (h->bb[i].done_blk) cudaEventDestroy(h->bb[i].done_blk);
   }
   cudaFree(h->d_upd2);
   cudaFree(h->d_own1);
