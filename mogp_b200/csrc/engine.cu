@@ -820,6 +820,7 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
       res.scr_elems = res.scr_used = 0;
       const int64_t want = std::max<int64_t>(4 * need, (int64_t)1 << 21);
       CK(h, cudaMalloc((void**)&res.scr, sizeof(double) * (size_t)want));
+      if (poison_enabled()) CK(h, cudaMemsetAsync(res.scr, 0xFF, sizeof(double) * (size_t)want, h->stream));
       res.scr_elems = want;
     }
     pl.kxT = res.scr + res.scr_used;
