@@ -193,8 +193,8 @@ typedef struct mogp_chain_config {
      1: rank-n up/down-dates at fixed theta + leave-block-out score for the patient's own cluster
         (same mathematics, rows kept in arrival order; agrees with mode 0 to rounding). */
   int32_t fast_updates;
-  /* mogp_chain_sweep, fast mode: the sweep order is known in advance, so consecutive patients totalling at most
-     `lookahead` visits (query columns) are scored against every active cluster in ONE pass over the factors; the
+  /* mogp_chain_sweep, fast mode: the sweep order is known in advance, so consecutive patients totalling about
+     `lookahead` visits (query columns; the cut is placed where the last group of 8 columns is fullest) are scored against every active cluster in ONE pass over the factors; the
      chain stays sequential (a cached score is used only while its cluster is unchanged, the rest is re-scored).
      0 = engine default (48), negative = off (one pass per patient), capped at 64.  While the host draws and moves the
      patients of one batch, the pass of the next batch already runs on a low-priority stream (MOGP_PIPELINE=1 in the
