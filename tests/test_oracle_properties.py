@@ -66,3 +66,47 @@ def test_density_is_the_gaussian_of_predict():
     lpd = o.log_predictive_density(xs, ys)
     ref = -0.5 * np.log(2 * np.pi * var) - 0.5 * (ys - mu) ** 2 / var
     assert np.allclose(lpd, ref, rtol=1e-12)
+
+
+def test_rank_n_score_identities_against_refactorisation():
+    """The identities behind the engine's rank-n score corrections (oracle/rank_updates.py):
+    predictive moments of query visits after a block of the cluster's data leaves / joins, computed from the OLD factor
+    and the cached T = M k, equal those of a refactorised GP on the changed data (GPRegressionOracle) to 1e-10."""
+    from oracle import rank_updates
+    from oracle.gpy_restated import GPRegressionOracle, GPY_JITTER
+    rs = np.random.RandomState(3)
+    for kernel in ('rbf', 'linear'):
+        m, nq = 90, 7
+        x = np.sort(rs.uniform(0, 8, m)); y = (40 - 5 * x + rs.randn(m) * 3 - 25) / 15
+        xq = rs.uniform(0.2, 8, nq)
+        gp = GPRegressionOracle(x, y, kernel_name=kernel, noise_variance=0.3, a_draw=0.4, lengthscale=2.5)
+        L = gp._L
+        M = np.linalg.inv(L)
+        alpha = gp._alpha[:, 0]
+        Kx, _ = gp._K(gp.X, xq.reshape(-1, 1))
+        T_q = M @ Kx
+        s_q = np.sum(T_q * T_q, axis=0)
+        mu_q = Kx.T @ alpha                                       # without the mean function (as the engine caches it)
+        kdiag = gp._Kdiag(xq.reshape(-1, 1))
+        # --- a block leaves
+        rows = np.arange(31, 40)
+        keep = np.setdiff1d(np.arange(m), rows)
+        s1, mu1 = rank_updates.leave_block(M, alpha, T_q, s_q, mu_q, rows)
+        ref = GPRegressionOracle(x[keep], y[keep], kernel_name=kernel, noise_variance=0.3, a_draw=0.4, lengthscale=2.5)
+        mu_ref, var_ref = ref._raw_predict(xq)
+        assert np.allclose(kdiag - s1, var_ref[:, 0], rtol=1e-10, atol=1e-12)
+        assert np.allclose(mu1 + ref._mean(xq.reshape(-1, 1))[:, 0], mu_ref[:, 0], rtol=1e-10, atol=1e-12)
+        # --- a block joins
+        xb = rs.uniform(0.3, 8, 6); yb = (40 - 5 * xb + rs.randn(6) * 3 - 25) / 15
+        Kb, _ = gp._K(gp.X, xb.reshape(-1, 1))
+        T_B = M @ Kb
+        Kbb, _ = gp._K(xb.reshape(-1, 1))
+        S_BB = Kbb + (gp.noise + GPY_JITTER) * np.eye(6) - T_B.T @ T_B
+        mu_b = Kb.T @ alpha + gp._mean(xb.reshape(-1, 1))[:, 0]
+        K_Bq, _ = gp._K(xb.reshape(-1, 1), xq.reshape(-1, 1))
+        s2, mu2 = rank_updates.join_block(T_q, s_q, mu_q, T_B, K_Bq, S_BB, yb - mu_b)
+        ref = GPRegressionOracle(np.concatenate([x, xb]), np.concatenate([y, yb]), kernel_name=kernel, noise_variance=0.3,
+                                 a_draw=0.4, lengthscale=2.5)
+        mu_ref, var_ref = ref._raw_predict(xq)
+        assert np.allclose(kdiag - s2, var_ref[:, 0], rtol=1e-10, atol=1e-12)
+        assert np.allclose(mu2 + ref._mean(xq.reshape(-1, 1))[:, 0], mu_ref[:, 0], rtol=1e-10, atol=1e-12)
