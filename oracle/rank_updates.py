@@ -29,3 +29,23 @@ def join_block(T_q, s_q, mu_q, T_B, K_Bq, S_BB, r_B):
     t = np.linalg.solve(Ls, K_Bq - T_B.T @ T_q)
     z_B = np.linalg.solve(Ls, r_B)
     return s_q + np.sum(t * t, axis=0), mu_q + t.T @ z_B
+
+
+def alpha_after_leave(M, alpha, rows):
+    """alpha = Ky^-1 r of the cluster without block B, from the old factor (k_rm_alpha):
+       alpha'_R = alpha_R - W_RB W_BB^-1 alpha_B with W = M^T M."""
+    B = np.asarray(rows)
+    keep = np.setdiff1d(np.arange(M.shape[0]), B)
+    b = M[:, B]
+    W_B = b.T @ M                         # W_{B,:}
+    g = np.linalg.solve(W_B[:, B], alpha[B])
+    return alpha[keep] - W_B[:, keep].T @ g
+
+
+def alpha_after_join(M, alpha, T_B, S_BB, r_B):
+    """alpha of the cluster with block B appended (k_append_finalize): new rows of the inverse factor
+       R = -Ls^-1 T_B^T M, z_B = Ls^-1 r_B:  alpha' = [alpha + R^T z_B ; Ls^-T z_B]."""
+    Ls = np.linalg.cholesky(S_BB)
+    z_B = np.linalg.solve(Ls, r_B)
+    R = -np.linalg.solve(Ls, T_B.T @ M)
+    return np.concatenate([alpha + R.T @ z_B, np.linalg.solve(Ls.T, z_B)])

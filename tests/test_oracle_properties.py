@@ -110,3 +110,7 @@ def test_rank_n_score_identities_against_refactorisation():
         mu_ref, var_ref = ref._raw_predict(xq)
         assert np.allclose(kdiag - s2, var_ref[:, 0], rtol=1e-10, atol=1e-12)
         assert np.allclose(mu2 + ref._mean(xq.reshape(-1, 1))[:, 0], mu_ref[:, 0], rtol=1e-10, atol=1e-12)
+        # --- alpha of the changed clusters in closed form (k_append_finalize / k_rm_alpha): no pass over the factor
+        assert np.allclose(rank_updates.alpha_after_join(M, alpha, T_B, S_BB, yb - mu_b), ref._alpha[:, 0], rtol=1e-9, atol=1e-11)
+        ref = GPRegressionOracle(x[keep], y[keep], kernel_name=kernel, noise_variance=0.3, a_draw=0.4, lengthscale=2.5)
+        assert np.allclose(rank_updates.alpha_after_leave(M, alpha, rows), ref._alpha[:, 0], rtol=1e-9, atol=1e-11)
