@@ -231,10 +231,14 @@ class MoGP_constrained:
         perm = np.random.permutation(np.arange(N))
         a = np.zeros(N)
         u = np.zeros(N)
-        for s in range(N):
-            if self.mean_func:
-                a[s] = np.random.randn(1, 1)[0, 0]
-            u[s] = np.random.random_sample()
+        if self.mean_func:
+            # standard_normal() is the draw behind randn(1, 1) (same legacy gauss stream, cached second variate included)
+            gauss, unif = np.random.standard_normal, np.random.random_sample
+            for s in range(N):
+                a[s] = gauss()
+                u[s] = unif()
+        else:
+            u[:] = np.random.random_sample(N)      # N consecutive doubles of the same stream
         return perm, a, u
 
     def sweep(self, perm=None, a=None, u=None):
