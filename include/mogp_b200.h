@@ -233,6 +233,20 @@ double mogp_chain_last_margin(const mogp_engine* h);
    choice(): cdf = cumsum(p); cdf /= cdf[-1]; index = searchsorted(cdf, u, 'right')  (mogp_constrained.py:272-277). */
 int mogp_host_choice(const double* score, int32_t n, double u, double* p_out, int32_t* index_out, double* margin_out);
 
+/* ---- the optimiser of model.optimize() as a host-side state machine (no device) -------------------------------- */
+/* paramz's default optimiser (obsmodel.py:94, mogp_constrained.py:333) is scipy.optimize.fmin_l_bfgs_b(f_fp, x0,
+   maxfun=1000, maxiter=1000): L-BFGS-B 3.0 without bounds, m = 10, factr = 1e7, pgtol = 1e-5, maxls = 20.  The engine
+   carries its own restatement (csrc/lbfgsb.hpp) so that the refits of many clusters can be driven by ONE host thread
+   while their evaluations run on the device (mogp_refit_clusters); these entry points expose it in reverse-communication
+   form for tests against SciPy.  mogp_lbfgsb_step: on entry *f, g[n] hold the objective at x when the previous call
+   returned 1; returns 1 = evaluate (f, g) at x[n] and call again, 2 = new iterate (call again), 3 / 4 = converged
+   (projected gradient <= pgtol / relative reduction <= factr * eps), 5 = abnormal termination in the line search,
+   6 = iteration or evaluation limit. */
+typedef struct mogp_lbfgsb mogp_lbfgsb;
+int mogp_lbfgsb_create(int32_t n, int32_t m, double factr, double pgtol, int32_t maxls, const double* x0, mogp_lbfgsb** out);
+int mogp_lbfgsb_step(mogp_lbfgsb* s, double* x, double* f, double* g);
+void mogp_lbfgsb_destroy(mogp_lbfgsb* s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,9 @@ SIGNATURES = {
     "mogp_chain_get_state": (C.c_int, [_H, _ip, _lp, _ip, C.c_int32, _ip]),
     "mogp_chain_last_margin": (C.c_double, [_H]),
     "mogp_host_choice": (C.c_int, [_dp, C.c_int32, C.c_double, _dp, _ip, _dp]),
+    "mogp_lbfgsb_create": (C.c_int, [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, _dp, C.POINTER(_H)]),
+    "mogp_lbfgsb_step": (C.c_int, [_H, _dp, _dp, _dp]),
+    "mogp_lbfgsb_destroy": (None, [_H]),
 }
 
 _lib = None
@@ -418,6 +421,37 @@ def host_choice(score, u):
     if rc != MOGP_OK:
         raise EngineError(rc, "mogp_host_choice")
     return idx.value, p, margin.value
+
+
+def lbfgsb_minimize(fun, x0, m=10, factr=1e7, pgtol=1e-5, maxls=20):
+    """Drive the engine's L-BFGS-B state machine (csrc/lbfgsb.hpp) with a Python objective `fun(x) -> (f, g)`:
+    the counterpart of scipy.optimize.fmin_l_bfgs_b(fun, x0) for tests.  Returns (x, f, info)."""
+    lib = load_library()
+    x = f64(x0).copy()
+    n = x.size
+    h = _H()
+    rc = lib.mogp_lbfgsb_create(n, m, float(factr), float(pgtol), int(maxls), dptr(x), C.byref(h))
+    if rc != MOGP_OK:
+        raise EngineError(rc, "mogp_lbfgsb_create")
+    f = C.c_double(0.0)
+    g = np.zeros(n)
+    evals, iters, xs = 0, 0, []
+    try:
+        while True:
+            task = lib.mogp_lbfgsb_step(h, dptr(x), C.byref(f), dptr(g))
+            if task == 1:
+                fv, gv = fun(x.copy())
+                xs.append(x.copy())
+                f.value = float(fv)
+                g[:] = np.asarray(gv, dtype=np.float64)
+                evals += 1
+            elif task == 2:
+                iters += 1
+            else:
+                break
+    finally:
+        lib.mogp_lbfgsb_destroy(h)
+    return x.copy(), f.value, dict(task=task, funcalls=evals, nit=iters, points=xs, grad=g.copy())
 
 
 _default_engine = None

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/mogp_b200.h"
+#include "lbfgsb.hpp"
 #include "score.cuh"
 #include "update.cuh"
 
@@ -1703,5 +1704,31 @@ int mogp_new_cluster_ll(mogp_engine* h, const mogp_model_spec* spec, const doubl
   CK(h, cudaGetLastError());
   return copy_back(h, ll, h->d_out, n_patients);
 }
+
+// ---- L-BFGS-B state machine, reverse communication (tests against SciPy; the refit driver uses the same class) ----
+struct mogp_lbfgsb {
+  Lbfgsb opt;
+};
+int mogp_lbfgsb_create(int32_t n, int32_t m, double factr, double pgtol, int32_t maxls, const double* x0, mogp_lbfgsb** out) {
+  if (!out || !x0 || n <= 0 || n > Lbfgsb::NMAX || m <= 0 || m > Lbfgsb::MMAX || maxls <= 0) return MOGP_EINVAL;
+  mogp_lbfgsb* s = new mogp_lbfgsb();
+  s->opt.init(n, x0, m, factr, pgtol, maxls);
+  *out = s;
+  return MOGP_OK;
+}
+int mogp_lbfgsb_step(mogp_lbfgsb* s, double* x, double* f, double* g) {
+  if (!s || !x || !f || !g) return MOGP_EINVAL;
+  Lbfgsb& o = s->opt;
+  if (o.task == Lbfgsb::T_FG) {
+    o.f = *f;
+    memcpy(o.g, g, sizeof(double) * o.n);
+  }
+  const int task = (int)o.step();
+  memcpy(x, o.x, sizeof(double) * o.n);
+  *f = o.f;
+  memcpy(g, o.g, sizeof(double) * o.n);
+  return task;
+}
+void mogp_lbfgsb_destroy(mogp_lbfgsb* s) { delete s; }
 
 }  // extern "C"

@@ -141,6 +141,8 @@ class MoGP_constrained:
         self.burnin = 25
         self.trace = []            # per-sweep occupancies (what the reference logs at :286)
         self.step_log = None       # optional per-step record, see gibbs_step
+        self.track_margin = False  # keep the smallest |u - cdf edge| of the chain in min_margin
+        self.min_margin = np.inf
 
     # -- validation, mogp_constrained.py:92-144 (same messages) --------------------------
     def _check_validity_of_instance(self):
@@ -261,6 +263,16 @@ class MoGP_constrained:
         score[new_id] += newcomer.ll
         s = score[active]
         self.p[n] = np.exp(s - logsumexp(s))
+        margin = None
+        if self.step_log is not None or self.track_margin:
+            # the uniform np.random.choice is about to consume, peeked without disturbing the stream: distance of the
+            # draw from the nearest cdf edge (how much score error the assignment tolerates)
+            st = np.random.get_state()
+            u = np.random.random_sample()
+            np.random.set_state(st)
+            cdf = np.cumsum(self.p[n])
+            margin = float(np.min(np.abs(cdf / cdf[-1] - u)))
+            self.min_margin = min(self.min_margin, margin)
         self.z[n] = np.random.choice(active, p=self.p[n])
         self.allocmodel.update_suffstats(self.z[n])
         if self.z[n] == new_id:
@@ -269,7 +281,7 @@ class MoGP_constrained:
             self.obsmodel[self.z[n]].update_suffstats(optimize_params=(self.refit == 'move'))
         if self.step_log is not None:
             self.step_log.append(dict(n=int(n), curr_k=int(curr_k), active=active.copy(), score=s.copy(),
-                                      p=self.p[n].copy(), z=int(self.z[n])))
+                                      p=self.p[n].copy(), z=int(self.z[n]), margin=margin))
 
     def end_of_sweep_refit(self):
         """refit='sweep' only: one L-BFGS-B refit per active cluster, in id order."""
