@@ -150,6 +150,18 @@ int mogp_cluster_objective(mogp_engine* h, int32_t slot, const double* t, int32_
    (mogp_sync) and no two threads touch the same slot. */
 int mogp_cluster_objective_on(mogp_engine* worker, mogp_engine* owner, int32_t slot, const double* t, int32_t n_t,
                               double* f, double* g);
+/* model.optimize() for several clusters at once (obsmodel.py:94 per cluster; the end-of-sweep refit of refit='sweep', or
+   one cluster after a move): each listed cluster is re-optimised exactly as its own sequential optimize() would -
+   L-BFGS-B (the engine's restatement of SciPy's, mogp_lbfgsb_*) on mogp_cluster_objective, warm-started at its current
+   hyper-parameters, then f(x_opt) and the final set - but the evaluations of different clusters are in flight together:
+   one lane (stream + factorisation workspace + captured graph) per cluster, at most max_concurrent of them (0 = default,
+   32), all driven by the calling thread.  n_evals_out[i] (optional) = objective evaluations cluster i asked for (what
+   paramz counts).  A cluster whose covariance stays non-positive-definite through GPy's jitter ladder 11 times in a row
+   ends the call with MOGP_ENOTPD (paramz re-raises the LinAlgError after 10 swallowed failures). */
+int mogp_refit_clusters(mogp_engine* h, int32_t n_slots, const int32_t* slots, int32_t max_concurrent, int32_t* n_evals_out);
+/* Objective evaluations requested by mogp_refit_clusters since creation / those that ran on the device (the rest hit the
+   "same hyper-parameters as the last evaluation" shortcut). */
+int mogp_refit_counters(mogp_engine* h, int64_t* evaluations, int64_t* launched);
 int mogp_cluster_n_free(mogp_engine* h, int32_t slot);
 /* Current optimiser coordinates t = Logexp^-1(theta) of the free parameters. */
 int mogp_cluster_get_optimizer_array(mogp_engine* h, int32_t slot, double* t, int32_t* n_t);
@@ -229,6 +241,13 @@ int mogp_chain_get_state(mogp_engine* h, int32_t* z /*N*/, int64_t* Nk, int32_t*
                          int32_t* n_ids);
 /* Last step's minimum |u - cdf edge|. */
 double mogp_chain_last_margin(const mogp_engine* h);
+/* self.p[n] (mogp_constrained.py:276): with recording on, every step of mogp_chain_sweep / mogp_chain_step keeps its
+   membership probabilities; mogp_chain_get_probs returns those of the steps since the last mogp_chain_sweep began: step
+   s covers [off[s], off[s+1]) of ids[] (active ids in the reference's order, last = the new cluster) and p[].  With
+   off = ids = p = NULL only *n_steps and *total are written (call twice). */
+int mogp_chain_record_probs(mogp_engine* h, int32_t on);
+int mogp_chain_get_probs(mogp_engine* h, int64_t* n_steps, int64_t* total, int64_t* off, int32_t* ids, double* p,
+                         int64_t cap_steps, int64_t cap_total);
 /* The draw alone (host arithmetic, no device): p = exp(score - logsumexp(score)) and NumPy's
    choice(): cdf = cumsum(p); cdf /= cdf[-1]; index = searchsorted(cdf, u, 'right')  (mogp_constrained.py:272-277). */
 int mogp_host_choice(const double* score, int32_t n, double u, double* p_out, int32_t* index_out, double* margin_out);

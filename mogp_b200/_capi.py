@@ -71,6 +71,8 @@ SIGNATURES = {
     "mogp_cluster_loglik": (C.c_int, [_H, C.c_int32, _dp]),
     "mogp_cluster_objective": (C.c_int, [_H, C.c_int32, _dp, C.c_int32, _dp, _dp]),
     "mogp_cluster_objective_on": (C.c_int, [_H, _H, C.c_int32, _dp, C.c_int32, _dp, _dp]),
+    "mogp_refit_clusters": (C.c_int, [_H, C.c_int32, _ip, C.c_int32, _ip]),
+    "mogp_refit_counters": (C.c_int, [_H, _lp, _lp]),
     "mogp_cluster_n_free": (C.c_int, [_H, C.c_int32]),
     "mogp_cluster_get_optimizer_array": (C.c_int, [_H, C.c_int32, _dp, _ip]),
     "mogp_cluster_lml_grad": (C.c_int, [_H, C.c_int32, _dp]),
@@ -89,6 +91,8 @@ SIGNATURES = {
     "mogp_chain_sweep": (C.c_int, [_H, C.c_int64, _lp, _dp, _dp, _ip, _dp]),
     "mogp_chain_get_state": (C.c_int, [_H, _ip, _lp, _ip, C.c_int32, _ip]),
     "mogp_chain_last_margin": (C.c_double, [_H]),
+    "mogp_chain_record_probs": (C.c_int, [_H, C.c_int32]),
+    "mogp_chain_get_probs": (C.c_int, [_H, _lp, _lp, _lp, _ip, _dp, C.c_int64, C.c_int64]),
     "mogp_host_choice": (C.c_int, [_dp, C.c_int32, C.c_double, _dp, _ip, _dp]),
     "mogp_lbfgsb_create": (C.c_int, [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, _dp, C.POINTER(_H)]),
     "mogp_lbfgsb_step": (C.c_int, [_H, _dp, _dp, _dp]),
@@ -302,11 +306,27 @@ class Engine:
         self.check(self.lib.mogp_cluster_get_optimizer_array(self.h, slot, dptr(t), C.byref(n)))
         return t[:n.value].copy()
 
-    def cluster_objective(self, slot, t=None, want_grad=True, worker=None):
+    def refit_clusters(self, slots, max_concurrent=0):
+        """model.optimize() of every listed cluster (obsmodel.py:94), their evaluations in flight together, driven by this
+        thread (mogp_refit_clusters).  Returns the objective evaluations each cluster asked for."""
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        n_evals = np.zeros(slots.size, dtype=np.int32)
+        if slots.size:
+            self.check(self.lib.mogp_refit_clusters(self.h, slots.size, iptr(slots), int(max_concurrent), iptr(n_evals)))
+        return n_evals
+
+    def refit_counters(self):
+        a, b = C.c_int64(), C.c_int64()
+        self.check(self.lib.mogp_refit_counters(self.h, C.byref(a), C.byref(b)))
+        return dict(evaluations=a.value, launched=b.value)
+
+    def cluster_objective(self, slot, t=None, want_grad=True, worker=None, nfree=None):
         """(f, df/dt) of cluster `slot`; with `worker` (another Engine on the same device) the evaluation runs
-        on the worker's stream and workspaces, so several clusters can be refitted concurrently."""
+        on the worker's stream and workspaces, so several clusters can be refitted concurrently (`nfree` given: the
+        owner engine is not touched from the worker's thread)."""
         f = C.c_double()
-        nfree = self.cluster_n_free(slot)
+        if nfree is None:
+            nfree = self.cluster_n_free(slot)
         g = np.empty(max(nfree, 1))
         if t is not None:
             t = f64(t)
@@ -397,6 +417,20 @@ class Engine:
         self.check(self.lib.mogp_chain_sweep(self.h, order.size, lptr(order), dptr(a_draw), dptr(u), iptr(chosen),
                                              C.byref(mm)))
         return chosen, mm.value
+
+    def chain_record_probs(self, on=True):
+        self.check(self.lib.mogp_chain_record_probs(self.h, int(bool(on))))
+
+    def chain_probs(self):
+        """Membership probabilities of every step of the last chain_sweep (needs chain_record_probs): off, ids, p."""
+        ns, tot = C.c_int64(), C.c_int64()
+        self.check(self.lib.mogp_chain_get_probs(self.h, C.byref(ns), C.byref(tot), None, None, None, 0, 0))
+        off = np.zeros(ns.value + 1, dtype=np.int64)
+        ids = np.zeros(max(tot.value, 1), dtype=np.int32)
+        p = np.zeros(max(tot.value, 1))
+        self.check(self.lib.mogp_chain_get_probs(self.h, C.byref(ns), C.byref(tot), lptr(off), iptr(ids), dptr(p),
+                                                 ns.value, max(tot.value, 1)))
+        return off, ids[:tot.value], p[:tot.value]
 
     def chain_state(self, N):
         n_ids = C.c_int32()

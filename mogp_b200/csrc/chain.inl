@@ -275,6 +275,15 @@ int host_choice(const double* score, int n, double u, double* p_out, int* index_
   return MOGP_OK;
 }
 
+// self.p[n] (mogp_constrained.py:276) of one step, kept for mogp_chain_get_probs
+void record_step_probs(mogp_engine* h, const std::vector<int32_t>& ids, const double* p) {
+  if (!h->record_probs) return;
+  if (h->rec_off.empty()) h->rec_off.push_back(0);
+  h->rec_ids.insert(h->rec_ids.end(), ids.begin(), ids.end());
+  h->rec_p.insert(h->rec_p.end(), p, p + ids.size());
+  h->rec_off.push_back((int64_t)h->rec_ids.size());
+}
+
 Theta newcomer_theta(const mogp_chain_config& cfg) {
   Theta th;
   th.A = 0.0;
@@ -333,7 +342,7 @@ int chain_begin(mogp_engine* h, int64_t n) {
   Cluster& c = h->cl[ch.slot_of_id[prev]];
   const int64_t ni = h->h_off[n + 1] - h->h_off[n];
   if (ch.Nk[prev] == 0) {  // obsmodel[curr_k] = None (:235-237)
-    TRY(mogp_cluster_free(h, ch.slot_of_id[prev]));
+    TRY(cluster_free_i(h, ch.slot_of_id[prev]));
     ch.slot_of_id[prev] = -1;
     return MOGP_OK;
   }
@@ -415,6 +424,14 @@ int chain_score(mogp_engine* h, double a_draw) {
   }
   std::vector<double> host(2 * ns + 8, 0.0);
   if (ni > 0) TRY(copy_back(h, host.data(), h->d_out, 2 * ns + 4));
+  if (ni > 64) {  // a row longer than k_new_ll's shared-memory tile: the general cluster path (any length)
+    const double th4[4] = {fabs(a_draw), ch.cfg.signal_variance,
+                           ch.cfg.spec.kernel == MOGP_KERNEL_RBF ? ch.cfg.lengthscale : 1.0, ch.cfg.noise_variance};
+    double ll_long = NAN;
+    int rc = newcomer_ll_general(h, ch.cfg.spec, th4, ni, h->h_x.data() + c0, h->h_y.data() + c0, &ll_long);
+    if (rc != MOGP_OK && rc != MOGP_ENOTPD) return rc;
+    host[2 * ns] = rc == MOGP_OK ? ll_long : NAN;
+  }
   const double ythr = (ch.cfg.use_threshold && !h->h_ythr.empty()) ? h->h_ythr[n] : NAN;
   int si = 0;
   for (int i = 0; i < nact; ++i) {
@@ -522,10 +539,10 @@ int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_n
       if (replaces_existing) {  // obsmodel[z[n]] = new_comp_model over an existing cluster (alpha = 0)
         join_side(h);
         joiner.on = false;
-        TRY(mogp_cluster_free(h, ch.slot_of_id[chosen_id]));
+        TRY(cluster_free_i(h, ch.slot_of_id[chosen_id]));
         ch.slot_of_id[chosen_id] = -1;
       }
-      TRY(mogp_cluster_create(h, &ch.cfg.spec, th, &slot));
+      TRY(cluster_create_i(h, &ch.cfg.spec, th, &slot));
       Cluster& c = h->cl[slot];
       c.members.assign(1, n);
       TRY(rebuild_from_members(h, c));
@@ -1118,8 +1135,10 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
     ch.act_score[i] = prior + ll;
   }
   int idx = 0;
-  int rc = host_choice(ch.act_score.data(), nact, u, nullptr, &idx, &ch.last_margin);
+  std::vector<double> pvec(h->record_probs ? nact : 0);
+  int rc = host_choice(ch.act_score.data(), nact, u, h->record_probs ? pvec.data() : nullptr, &idx, &ch.last_margin);
   if (rc != MOGP_OK) FAIL(h, rc, "probabilities contain NaN (patient %lld)", (long long)n);
+  record_step_probs(h, ch.act_ids, pvec.data());
   const int32_t chosen = ch.act_ids[idx];
   const bool stays = ch.pending_lazy && chosen == prev;
   // A move changes two clusters.  The scores of the patients still ahead in this batch under them are corrected by
@@ -1415,7 +1434,7 @@ int mogp_chain_init(mogp_engine* h, const mogp_chain_config* cfg, int64_t n_pati
   // release the clusters of a previous chain
   if (ch.active)
     for (int32_t s : ch.slot_of_id)
-      if (s >= 0 && s < (int32_t)h->cl.size() && h->cl[s].used) mogp_cluster_free(h, s);
+      if (s >= 0 && s < (int32_t)h->cl.size() && h->cl[s].used) cluster_free_i(h, s);
   ch = Chain();
   ch.cfg = *cfg;
   ch.N = n_patients;
@@ -1431,9 +1450,9 @@ int mogp_chain_init(mogp_engine* h, const mogp_chain_config* cfg, int64_t n_pati
   for (int32_t k = 0; k < n_ids; ++k) {
     if (ch.Nk[k] == 0) continue;
     int32_t slot;
-    TRY(mogp_cluster_create(h, &cfg->spec, theta_of_id + 4 * k, &slot));
+    TRY(cluster_create_i(h, &cfg->spec, theta_of_id + 4 * k, &slot));
     ch.slot_of_id[k] = slot;
-    TRY(mogp_cluster_set_members(h, slot, (int64_t)mem[k].size(), mem[k].data()));
+    TRY(cluster_set_members_i(h, slot, (int64_t)mem[k].size(), mem[k].data()));
   }
   ch.active = true;
   return MOGP_OK;
@@ -1478,6 +1497,7 @@ int mogp_chain_step(mogp_engine* h, int64_t n, double a_draw, double u, int32_t*
   int idx = 0;
   int rc = host_choice(ch.act_score.data(), nact, u, p.data(), &idx, &ch.last_margin);
   if (rc != MOGP_OK) FAIL(h, rc, "probabilities contain NaN (patient %lld)", (long long)n);
+  record_step_probs(h, ch.act_ids, p.data());
   if (n_active) *n_active = nact;
   if (ids_out || p_out) {
     if (cap_out < nact) FAIL(h, MOGP_EINVAL, "output capacity %d < %d active ids", cap_out, nact);
@@ -1498,6 +1518,9 @@ int mogp_chain_sweep(mogp_engine* h, int64_t n_steps, const int64_t* order, cons
   if (!order || !u || n_steps < 0) FAIL(h, MOGP_EINVAL, "null argument");
   if (h->chain.active && h->chain.cfg.spec.mean_func && !a_draw) FAIL(h, MOGP_EINVAL, "mean_func needs a_draw");
   double mm = INFINITY;
+  h->rec_off.clear();
+  h->rec_ids.clear();
+  h->rec_p.clear();
   h->chain.win.open = h->chain.win.in_step = false;
   const int max_cols = h->chain.active && h->chain.cfg.fast_updates && h->chain.cfg.alpha > 0.0 ? window_cols(h->chain) : 0;
   if (max_cols >= 2 && n_steps > 0 && order_is_duplicate_free(h->chain, n_steps, order)) {
@@ -1533,12 +1556,41 @@ int mogp_chain_get_state(mogp_engine* h, int32_t* z, int64_t* Nk, int32_t* slot_
     if (cap_ids < k) FAIL(h, MOGP_EINVAL, "capacity %d < %d cluster ids", cap_ids, k);
     for (int32_t i = 0; i < k; ++i) {
       if (Nk) Nk[i] = ch.Nk[i];
-      if (slot_of_id) slot_of_id[i] = ch.slot_of_id[i];
+      if (slot_of_id) slot_of_id[i] = slot_handle(h, ch.slot_of_id[i]);
     }
   }
   return MOGP_OK;
 }
 
 double mogp_chain_last_margin(const mogp_engine* h) { return h ? h->chain.last_margin : NAN; }
+
+int mogp_chain_record_probs(mogp_engine* h, int32_t on) {
+  if (!h) return MOGP_EINVAL;
+  h->record_probs = on != 0;
+  if (!h->record_probs) {
+    h->rec_off.clear();
+    h->rec_ids.clear();
+    h->rec_p.clear();
+  }
+  return MOGP_OK;
+}
+
+int mogp_chain_get_probs(mogp_engine* h, int64_t* n_steps, int64_t* total, int64_t* off, int32_t* ids, double* p,
+                         int64_t cap_steps, int64_t cap_total) {
+  if (!h) return MOGP_EINVAL;
+  const int64_t ns = h->rec_off.empty() ? 0 : (int64_t)h->rec_off.size() - 1, tot = (int64_t)h->rec_ids.size();
+  if (n_steps) *n_steps = ns;
+  if (total) *total = tot;
+  if (!off && !ids && !p) return MOGP_OK;
+  if (cap_steps < ns || cap_total < tot) FAIL(h, MOGP_EINVAL, "capacity (%lld steps, %lld entries) < (%lld, %lld)",
+                                              (long long)cap_steps, (long long)cap_total, (long long)ns, (long long)tot);
+  if (off) {
+    if (ns == 0) off[0] = 0;
+    else memcpy(off, h->rec_off.data(), sizeof(int64_t) * (ns + 1));
+  }
+  if (ids && tot) memcpy(ids, h->rec_ids.data(), sizeof(int32_t) * tot);
+  if (p && tot) memcpy(p, h->rec_p.data(), sizeof(double) * tot);
+  return MOGP_OK;
+}
 
 }  // extern "C"

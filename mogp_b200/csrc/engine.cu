@@ -51,6 +51,7 @@ inline int64_t round_up(int64_t v, int64_t q) { return (v + q - 1) / q * q; }
 
 struct Cluster {
   bool used = false;
+  int32_t gen = 0;   // bumped every time the slot is freed: part of the handle the ABI hands out (slot_handle)
   mogp_model_spec spec{};
   double theta[4] = {0, 0, 0, 0};
   int64_t m = 0;     // data points
@@ -254,6 +255,17 @@ struct mogp_engine {
   char* pin_up = nullptr;
   size_t up_bytes = 0, up_off = 0;
   Chain chain;
+  // lanes of the refit driver (mogp_refit_clusters): light worker engines (one stream + factorisation workspace each),
+  // all driven by the caller's thread
+  bool light = false;
+  std::vector<mogp_engine*> lanes;
+  std::vector<cudaEvent_t> lane_ev;
+  int64_t refit_evals = 0, refit_launched = 0;   // objective evaluations requested / actually run on the device
+  // membership probabilities of every step of the last mogp_chain_sweep (self.p[n], mogp_constrained.py:276)
+  bool record_probs = false;
+  std::vector<int64_t> rec_off;
+  std::vector<int32_t> rec_ids;
+  std::vector<double> rec_p;
   // update workspace (update.cuh)
   double* d_upd = nullptr;
   int64_t upd_elems = 0;
@@ -431,12 +443,31 @@ Theta make_theta(const Cluster& c) {
   return th;
 }
 
-int check_slot(mogp_engine* h, int32_t slot) {
+int check_slot(mogp_engine* h, int32_t slot) {  // slot = INDEX into h->cl (internal callers)
   if (!h) return MOGP_EINVAL;
   cudaSetDevice(h->device);  // every cluster entry point comes through here; callers may be on any host thread
   if (slot < 0 || slot >= (int32_t)h->cl.size() || !h->cl[slot].used) FAIL(h, MOGP_EINVAL, "bad cluster slot %d", slot);
   if (h->cl[slot].side_busy && h->stream == h->main_stream) join_side(h);
   return MOGP_OK;
+}
+
+// What crosses the ABI is a HANDLE: the slot's index in the low 16 bits, its generation above.  A slot index is reused
+// after mogp_cluster_free / a new chain; a caller still holding the old handle (a GPobs view of a cluster that has since
+// been emptied, or of a previous chain) gets MOGP_EINVAL instead of silently reading the cluster that now lives there.
+constexpr int32_t SLOT_INDEX_BITS = 16, SLOT_INDEX_MASK = (1 << SLOT_INDEX_BITS) - 1, SLOT_GEN_MASK = 0x7FFF;
+inline int32_t slot_handle(const mogp_engine* h, int32_t idx) {
+  return idx < 0 ? idx : (idx | ((h->cl[idx].gen & SLOT_GEN_MASK) << SLOT_INDEX_BITS));
+}
+// handle -> index, checked (replaces *slot)
+int slot_in(mogp_engine* h, int32_t* slot) {
+  if (!h) return MOGP_EINVAL;
+  const int32_t hd = *slot;
+  const int32_t idx = hd & SLOT_INDEX_MASK;
+  if (hd < 0 || idx >= (int32_t)h->cl.size() || !h->cl[idx].used) FAIL(h, MOGP_EINVAL, "bad cluster slot %d", hd);
+  if (((hd >> SLOT_INDEX_BITS) & SLOT_GEN_MASK) != (h->cl[idx].gen & SLOT_GEN_MASK))
+    FAIL(h, MOGP_EINVAL, "stale cluster handle %d: the slot has been freed and reused since it was handed out", hd);
+  *slot = idx;
+  return check_slot(h, idx);
 }
 
 // Capacity classes (x1.25 steps, multiples of 64) so that buffers can be pooled and ping-ponged.
@@ -710,12 +741,7 @@ void prof_mark(mogp_engine* h, bool stop) {
 template <int BN>
 void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotView* d_slots, const SlotPack& pack,
                        int use_pack, const ChunkPlan& cp) {
-  const int smem = ScoreSmem<BN>::BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_score_gemm<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_done = true;
-  }
+  const int smem = ScoreSmem<BN>::BYTES;  // (opted into in mogp_engine_create, per device)
   dim3 grid((unsigned)(pl.Rpad / BN), (unsigned)pl.n_slots, (unsigned)(pl.max_nb * cp.maxch));
   prof_mark(h, false);
   k_score_gemm<BN><<<grid, NTHREADS, smem, h->stream>>>(d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout, cp);
@@ -726,12 +752,7 @@ void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout, const 
 template <int NS>
 void launch_score_wide(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotView* d_slots, const SlotPack& pack,
                        int use_pack, const ChunkPlan& cp) {
-  const int smem = WideSmem<NS>::BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_score_wide<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_done = true;
-  }
+  const int smem = WideSmem<NS>::BYTES;  // (opted into in mogp_engine_create, per device)
   dim3 grid((unsigned)(pl.Rpad / (8 * NS)), (unsigned)pl.n_slots, (unsigned)(pl.max_nb * cp.maxch));
   prof_mark(h, false);
   k_score_wide<NS><<<grid, WIDE_THREADS, smem, h->stream>>>(d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout, cp);
@@ -904,6 +925,94 @@ int copy_back(mogp_engine* h, double* dst, const double* src_dev, int64_t n) {
   return MOGP_OK;
 }
 
+
+// ---- cluster slots (internal: indices; the extern "C" wrappers translate handles) ----------------------------------
+int upload_data(mogp_engine* h, Cluster& c, int64_t m, const double* x, const double* y);
+int cluster_create_i(mogp_engine* h, const mogp_model_spec* spec, const double theta[4], int32_t* slot_out) {
+  if (!spec || !theta || !slot_out) FAIL(h, MOGP_EINVAL, "null argument");
+  if (spec->kernel != MOGP_KERNEL_RBF && spec->kernel != MOGP_KERNEL_LINEAR) FAIL(h, MOGP_EINVAL, "unknown kernel %d", spec->kernel);
+  int32_t slot = -1;
+  for (size_t i = 0; i < h->cl.size(); ++i)
+    if (!h->cl[i].used) {
+      slot = (int32_t)i;
+      break;
+    }
+  if (slot < 0) {
+    if ((int32_t)h->cl.size() > SLOT_INDEX_MASK) FAIL(h, MOGP_ENOMEM, "more than %d cluster slots", SLOT_INDEX_MASK + 1);
+    h->cl.emplace_back();
+    slot = (int32_t)h->cl.size() - 1;
+  }
+  Cluster& c = h->cl[slot];
+  c.used = true;
+  c.spec = *spec;
+  memcpy(c.theta, theta, sizeof(double) * 4);
+  c.theta_dirty = true;
+  c.m = 0;
+  c.valid = c.grad_valid = false;
+  c.hx.clear();
+  c.hy.clear();
+  c.members.clear();
+  *slot_out = slot;
+  return MOGP_OK;
+}
+
+int cluster_free_i(mogp_engine* h, int32_t slot) {
+  TRY(check_slot(h, slot));
+  Cluster& c = h->cl[slot];
+  if (c.M) pool_put(h, c.cap, c.M);  // stream-ordered reuse by the next cluster of that capacity class
+  c.M = c.vec = nullptr;
+  c.cap = 0;
+  c.used = false;
+  c.gen += 1;  // handles to the cluster that lived here are stale from now on
+  c.m = 0;
+  c.valid = c.grad_valid = false;
+  c.hx.clear();
+  c.hy.clear();
+  c.members.clear();
+  return MOGP_OK;
+}
+
+int cluster_set_data_i(mogp_engine* h, int32_t slot, int64_t m, const double* x, const double* y) {
+  TRY(check_slot(h, slot));
+  if (m <= 0 || !x || !y) FAIL(h, MOGP_EINVAL, "cluster data must be non-empty");
+  Cluster& c = h->cl[slot];
+  c.members.clear();
+  TRY(upload_data(h, c, m, x, y));
+  return infer(h, c);
+}
+
+int cluster_set_members_i(mogp_engine* h, int32_t slot, int64_t n_members, const int64_t* ids) {
+  TRY(check_slot(h, slot));
+  if (n_members <= 0 || !ids) FAIL(h, MOGP_EINVAL, "member list must be non-empty");
+  if (h->P <= 0) FAIL(h, MOGP_ESTATE, "no patient table");
+  std::vector<double> xs, ys;
+  for (int64_t i = 0; i < n_members; ++i) {
+    if (ids[i] < 0 || ids[i] >= h->P) FAIL(h, MOGP_EINVAL, "patient id %lld out of range", (long long)ids[i]);
+    xs.insert(xs.end(), h->h_x.begin() + h->h_off[ids[i]], h->h_x.begin() + h->h_off[ids[i] + 1]);
+    ys.insert(ys.end(), h->h_y.begin() + h->h_off[ids[i]], h->h_y.begin() + h->h_off[ids[i] + 1]);
+  }
+  if (xs.empty()) FAIL(h, MOGP_EINVAL, "members have no visits");
+  Cluster& c = h->cl[slot];
+  TRY(upload_data(h, c, (int64_t)xs.size(), xs.data(), ys.data()));
+  c.members.assign(ids, ids + n_members);
+  return infer(h, c);
+}
+
+// New-cluster marginal of a row too long for k_new_ll's shared-memory Cholesky (more than 64 visits): the general
+// cluster path - a temporary slot and exact inference (GPobs(x_n, y_n).ll, obsmodel.py:56, for any row length).
+int newcomer_ll_general(mogp_engine* h, const mogp_model_spec& spec, const double th4[4], int64_t n, const double* x,
+                        const double* y, double* ll) {
+  int32_t slot = -1;
+  TRY(cluster_create_i(h, &spec, th4, &slot));
+  int rc = upload_data(h, h->cl[slot], n, x, y);
+  if (rc == MOGP_OK) rc = infer(h, h->cl[slot]);
+  if (rc == MOGP_OK) *ll = h->cl[slot].lml;
+  const std::string keep = h->err;
+  cluster_free_i(h, slot);
+  h->err = keep;
+  return rc;
+}
+
 }  // namespace
 
 #include "chain.inl"
@@ -913,7 +1022,9 @@ extern "C" {
 
 int mogp_version(void) { return 100; }
 
-int mogp_engine_create(int32_t device, mogp_engine** out) {
+// light = a lane of the refit driver: the main stream and the factorisation workspaces only (no look-ahead streams,
+// no append ring, no correction buffers).
+static int engine_create_impl(int32_t device, bool light, mogp_engine** out) {
   if (!out) return MOGP_EINVAL;
   *out = nullptr;
   int n = 0;
@@ -928,6 +1039,7 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
   }
   mogp_engine* h = new mogp_engine();
   h->device = device;
+  h->light = light;
   int prio_least = 0, prio_greatest = 0;
   if (cudaSetDevice(device) == cudaSuccess) cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
   // main / side carry the dependent chain of a Gibbs step (highest priority); the look-ahead streams carry the next
@@ -935,16 +1047,16 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
       cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&h->ahead, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&h->ahead2, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&h->quick, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&h->quick2, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+      (!light && (cudaStreamCreateWithPriority(&h->ahead, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+                  cudaStreamCreateWithPriority(&h->ahead2, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+                  cudaStreamCreateWithPriority(&h->quick, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+                  cudaStreamCreateWithPriority(&h->quick2, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+                  cudaMalloc((void**)&h->d_apring, sizeof(double) * AP_RING * AP_RING_SLOT) != cudaSuccess ||
+                  cudaMalloc((void**)&h->d_alg, sizeof(double) * ALG_OUT_SLOTS * 2 * OWN_BATCH) != cudaSuccess ||
+                  cudaMallocHost((void**)&h->h_alg, sizeof(double) * ALG_OUT_SLOTS * 2 * OWN_BATCH) != cudaSuccess)) ||
       cudaEventCreateWithFlags(&h->ev_q2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_alg, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_apq, cudaEventDisableTiming) != cudaSuccess ||
-      cudaMalloc((void**)&h->d_apring, sizeof(double) * AP_RING * AP_RING_SLOT) != cudaSuccess ||
-      cudaMalloc((void**)&h->d_alg, sizeof(double) * ALG_OUT_SLOTS * 2 * OWN_BATCH) != cudaSuccess ||
-      cudaMallocHost((void**)&h->h_alg, sizeof(double) * ALG_OUT_SLOTS * 2 * OWN_BATCH) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_ahead2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->bb[0].done, cudaEventDisableTiming) != cudaSuccess ||
@@ -968,15 +1080,30 @@ int mogp_engine_create(int32_t device, mogp_engine** out) {
   cudaFuncSetAttribute(k_trail_blk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAILB_SMEM);
   cudaFuncSetAttribute(k_trail_blk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAIL_SMEM);
   cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM);
+  // (function attributes are per device: set for every kernel whenever an engine is created, on its device)
+  cudaFuncSetAttribute(k_score_gemm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScoreSmem<8>::BYTES);
+  cudaFuncSetAttribute(k_score_gemm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScoreSmem<16>::BYTES);
+  cudaFuncSetAttribute(k_score_wide<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<3>::BYTES);
+  cudaFuncSetAttribute(k_score_wide<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<4>::BYTES);
+  cudaFuncSetAttribute(k_score_wide<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<5>::BYTES);
+  cudaFuncSetAttribute(k_score_wide<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<6>::BYTES);
+  cudaFuncSetAttribute(k_score_wide<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<7>::BYTES);
+  cudaFuncSetAttribute(k_score_wide<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideSmem<8>::BYTES);
   update_set_attributes();
   *out = h;
   return MOGP_OK;
 }
 
+int mogp_engine_create(int32_t device, mogp_engine** out) { return engine_create_impl(device, false, out); }
+
 void mogp_engine_destroy(mogp_engine* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   sync_stream(h);
+  for (mogp_engine* l : h->lanes) mogp_engine_destroy(l);
+  h->lanes.clear();
+  for (cudaEvent_t e : h->lane_ev) cudaEventDestroy(e);
+  h->lane_ev.clear();
   for (auto& c : h->cl)
     if (c.M) cudaFree(c.M);
   cudaFree(h->d_off);
@@ -1000,6 +1127,7 @@ void mogp_engine_destroy(mogp_engine* h) {
     if (h->bb[i].done) cudaEventDestroy(h->bb[i].done);
     if (h->bb[i].done_blk) cudaEventDestroy(h->bb[i].done_blk);
   }
+  cudaFree(h->d_adraw);
   cudaFree(h->d_upd2);
   cudaFree(h->d_own1);
   cudaFree(h->d_own2);
@@ -1248,49 +1376,19 @@ int mogp_transfer_bytes(mogp_engine* h, int64_t* h2d, int64_t* d2h) {
 int mogp_cluster_create(mogp_engine* h, const mogp_model_spec* spec, const double theta[4], int32_t* slot_out) {
   if (!h) return MOGP_EINVAL;
   cudaSetDevice(h->device);  // entry points may be called from any host thread
-  if (!spec || !theta || !slot_out) FAIL(h, MOGP_EINVAL, "null argument");
-  if (spec->kernel != MOGP_KERNEL_RBF && spec->kernel != MOGP_KERNEL_LINEAR) FAIL(h, MOGP_EINVAL, "unknown kernel %d", spec->kernel);
-  int32_t slot = -1;
-  for (size_t i = 0; i < h->cl.size(); ++i)
-    if (!h->cl[i].used) {
-      slot = (int32_t)i;
-      break;
-    }
-  if (slot < 0) {
-    h->cl.emplace_back();
-    slot = (int32_t)h->cl.size() - 1;
-  }
-  Cluster& c = h->cl[slot];
-  c.used = true;
-  c.spec = *spec;
-  memcpy(c.theta, theta, sizeof(double) * 4);
-  c.theta_dirty = true;
-  c.m = 0;
-  c.valid = c.grad_valid = false;
-  c.hx.clear();
-  c.hy.clear();
-  c.members.clear();
-  *slot_out = slot;
+  int32_t idx = -1;
+  TRY(cluster_create_i(h, spec, theta, &idx));
+  *slot_out = slot_handle(h, idx);
   return MOGP_OK;
 }
 
 int mogp_cluster_free(mogp_engine* h, int32_t slot) {
-  TRY(check_slot(h, slot));
-  Cluster& c = h->cl[slot];
-  if (c.M) pool_put(h, c.cap, c.M);  // stream-ordered reuse by the next cluster of that capacity class
-  c.M = c.vec = nullptr;
-  c.cap = 0;
-  c.used = false;
-  c.m = 0;
-  c.valid = c.grad_valid = false;
-  c.hx.clear();
-  c.hy.clear();
-  c.members.clear();
-  return MOGP_OK;
+  TRY(slot_in(h, &slot));
+  return cluster_free_i(h, slot);
 }
 
 int mogp_cluster_set_theta(mogp_engine* h, int32_t slot, const double theta[4]) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   Cluster& c = h->cl[slot];
   for (int i = 1; i < 4; ++i)
     if (!(theta[i] > 0.0) && !(i == 2 && c.spec.kernel == MOGP_KERNEL_LINEAR && theta[i] >= 0.0))
@@ -1303,48 +1401,32 @@ int mogp_cluster_set_theta(mogp_engine* h, int32_t slot, const double theta[4]) 
 }
 
 int mogp_cluster_get_theta(mogp_engine* h, int32_t slot, double theta[4]) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   memcpy(theta, h->cl[slot].theta, sizeof(double) * 4);
   return MOGP_OK;
 }
 
 int mogp_cluster_set_data(mogp_engine* h, int32_t slot, int64_t m, const double* x, const double* y) {
-  TRY(check_slot(h, slot));
-  if (m <= 0 || !x || !y) FAIL(h, MOGP_EINVAL, "cluster data must be non-empty");
-  Cluster& c = h->cl[slot];
-  c.members.clear();
-  TRY(upload_data(h, c, m, x, y));
-  return infer(h, c);
+  TRY(slot_in(h, &slot));
+  return cluster_set_data_i(h, slot, m, x, y);
 }
 
 int mogp_cluster_set_members(mogp_engine* h, int32_t slot, int64_t n_members, const int64_t* ids) {
-  TRY(check_slot(h, slot));
-  if (n_members <= 0 || !ids) FAIL(h, MOGP_EINVAL, "member list must be non-empty");
-  if (h->P <= 0) FAIL(h, MOGP_ESTATE, "no patient table");
-  std::vector<double> xs, ys;
-  for (int64_t i = 0; i < n_members; ++i) {
-    if (ids[i] < 0 || ids[i] >= h->P) FAIL(h, MOGP_EINVAL, "patient id %lld out of range", (long long)ids[i]);
-    xs.insert(xs.end(), h->h_x.begin() + h->h_off[ids[i]], h->h_x.begin() + h->h_off[ids[i] + 1]);
-    ys.insert(ys.end(), h->h_y.begin() + h->h_off[ids[i]], h->h_y.begin() + h->h_off[ids[i] + 1]);
-  }
-  if (xs.empty()) FAIL(h, MOGP_EINVAL, "members have no visits");
-  Cluster& c = h->cl[slot];
-  TRY(upload_data(h, c, (int64_t)xs.size(), xs.data(), ys.data()));
-  c.members.assign(ids, ids + n_members);
-  return infer(h, c);
+  TRY(slot_in(h, &slot));
+  return cluster_set_members_i(h, slot, n_members, ids);
 }
 
 int mogp_cluster_append(mogp_engine* h, int32_t slot, int64_t n, const double* x, const double* y) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   if (n <= 0 || !x || !y) FAIL(h, MOGP_EINVAL, "nothing to append");
   Cluster& c = h->cl[slot];
-  if (c.m == 0) return mogp_cluster_set_data(h, slot, n, x, y);
+  if (c.m == 0) return cluster_set_data_i(h, slot, n, x, y);
   if (!c.valid) TRY(infer(h, c));
   return append_points(h, c, n, x, y);
 }
 
 int mogp_cluster_remove_rows(mogp_engine* h, int32_t slot, int64_t p, int64_t n) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   Cluster& c = h->cl[slot];
   if (p < 0 || n <= 0 || p + n > c.m) FAIL(h, MOGP_EINVAL, "rows [%lld, %lld) outside the cluster (m=%lld)", (long long)p, (long long)(p + n), (long long)c.m);
   if (n == c.m) FAIL(h, MOGP_EINVAL, "cannot remove every row; free the cluster instead");
@@ -1363,7 +1445,7 @@ int mogp_cluster_remove_rows(mogp_engine* h, int32_t slot, int64_t p, int64_t n)
 
 int mogp_cluster_leave_out_score(mogp_engine* h, int32_t slot, int64_t p, int64_t n, int32_t thr_index, double* score,
                                  double* mu_thr) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   Cluster& c = h->cl[slot];
   if (p < 0 || n <= 0 || n > NP || p + n > c.m || n == c.m) FAIL(h, MOGP_EINVAL, "bad leave-out block");
   if (!c.valid) TRY(infer(h, c));
@@ -1381,7 +1463,7 @@ int mogp_cluster_leave_out_score(mogp_engine* h, int32_t slot, int64_t p, int64_
 }
 
 int mogp_cluster_get_factor(mogp_engine* h, int32_t slot, double* M_out, double* alpha_out) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   Cluster& c = h->cl[slot];
   if (!c.valid) TRY(infer(h, c));
   if (M_out) {
@@ -1397,17 +1479,17 @@ int mogp_cluster_get_factor(mogp_engine* h, int32_t slot, double* M_out, double*
 }
 
 int mogp_cluster_debug_stat(mogp_engine* h, int32_t slot, double* out32) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   return copy_back(h, out32, h->cl[slot].stat(), STAT);
 }
 
 int64_t mogp_cluster_size(mogp_engine* h, int32_t slot) {
-  if (check_slot(h, slot) != MOGP_OK) return -1;
+  if (slot_in(h, &slot) != MOGP_OK) return -1;
   return h->cl[slot].m;
 }
 
 int mogp_cluster_get_data(mogp_engine* h, int32_t slot, double* x, double* y) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   Cluster& c = h->cl[slot];
   if (x) memcpy(x, c.hx.data(), sizeof(double) * c.m);
   if (y) memcpy(y, c.hy.data(), sizeof(double) * c.m);
@@ -1415,7 +1497,7 @@ int mogp_cluster_get_data(mogp_engine* h, int32_t slot, double* x, double* y) {
 }
 
 int mogp_cluster_loglik(mogp_engine* h, int32_t slot, double* lml) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   Cluster& c = h->cl[slot];
   if (!c.valid) TRY(infer(h, c));
   TRY(fetch_stat(h, c));
@@ -1424,7 +1506,7 @@ int mogp_cluster_loglik(mogp_engine* h, int32_t slot, double* lml) {
 }
 
 int mogp_cluster_lml_grad(mogp_engine* h, int32_t slot, double grad_theta[4]) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   Cluster& c = h->cl[slot];
   if (!c.grad_valid) TRY(infer_grad(h, c));
   memcpy(grad_theta, c.grad, sizeof(double) * 4);
@@ -1432,7 +1514,7 @@ int mogp_cluster_lml_grad(mogp_engine* h, int32_t slot, double grad_theta[4]) {
 }
 
 int mogp_cluster_n_free(mogp_engine* h, int32_t slot) {
-  if (check_slot(h, slot) != MOGP_OK) return MOGP_EINVAL;
+  if (slot_in(h, &slot) != MOGP_OK) return MOGP_EINVAL;
   Gamma pr[4];
   bool fixed[4];
   priors_of(h->cl[slot].spec, pr, fixed);
@@ -1442,7 +1524,7 @@ int mogp_cluster_n_free(mogp_engine* h, int32_t slot) {
 }
 
 int mogp_cluster_get_optimizer_array(mogp_engine* h, int32_t slot, double* t, int32_t* n_t) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   Cluster& c = h->cl[slot];
   Gamma pr[4];
   bool fixed[4];
@@ -1465,10 +1547,12 @@ bool graphs_enabled() {
 
 // One objective evaluation (exact inference + gradient at the cluster's current theta) as a CUDA graph: captured
 // once per (cluster buffers, size), relaunched for each of the ~20 evaluations of a refit.  theta travels through
-// device memory (sync_theta), so the nodes never change.  *ok = false when the factorisation failed: the caller
-// falls back to the eager path with GPy's jitter ladder.
-static int graph_eval(mogp_engine* h, Cluster& c, bool* ok) {
-  *ok = false;
+// device memory (sync_theta), so the nodes never change.  Split in two so that one host thread can keep the
+// evaluations of many clusters in flight (refit driver below): eval_launch queues the work on h->stream without
+// waiting, eval_collect reads the results once the stream has been waited for.  *ok = false when the factorisation
+// failed: the caller falls back to the eager path with GPy's jitter ladder.
+static int eval_launch(mogp_engine* h, Cluster& c, bool* launched) {
+  *launched = false;
   const int64_t mpad = round_up(c.m, TB);
   const int nb = (int)(mpad / TB);
   const int64_t ld = c.cap;
@@ -1483,9 +1567,7 @@ static int graph_eval(mogp_engine* h, Cluster& c, bool* ok) {
   double* st = c.stat();
   const void* key[6] = {c.M, c.vec, h->d_L, h->d_apart, h->d_partial, reinterpret_cast<const void*>((intptr_t)c.m)};
   if (!h->eval_exec || memcmp(key, h->eval_key, sizeof key) != 0) {
-    if (h->eval_exec) cudaGraphExecDestroy(h->eval_exec);
     if (h->eval_graph) cudaGraphDestroy(h->eval_graph);
-    h->eval_exec = nullptr;
     h->eval_graph = nullptr;
     const int64_t launches0 = h->launches;
     CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -1509,9 +1591,24 @@ static int graph_eval(mogp_engine* h, Cluster& c, bool* ok) {
     if (rc != MOGP_OK) return rc;
     if (ce != cudaSuccess || !h->eval_graph) {
       cudaGetLastError();
-      return MOGP_OK;  // *ok stays false: eager path
+      if (h->eval_exec) cudaGraphExecDestroy(h->eval_exec);
+      h->eval_exec = nullptr;
+      return MOGP_OK;  // not launched: eager path
     }
-    if (cudaGraphInstantiate(&h->eval_exec, h->eval_graph, 0) != cudaSuccess) {
+    // the same topology with other buffers (the next cluster of the same tile count): update the executable graph
+    // in place, which is much cheaper than instantiating a new one
+    bool have = false;
+    if (h->eval_exec) {
+      cudaGraphExecUpdateResultInfo ui;
+      if (cudaGraphExecUpdate(h->eval_exec, h->eval_graph, &ui) == cudaSuccess) {
+        have = true;
+      } else {
+        cudaGetLastError();
+        cudaGraphExecDestroy(h->eval_exec);
+        h->eval_exec = nullptr;
+      }
+    }
+    if (!have && cudaGraphInstantiate(&h->eval_exec, h->eval_graph, 0) != cudaSuccess) {
       cudaGetLastError();
       h->eval_exec = nullptr;
       return MOGP_OK;
@@ -1519,7 +1616,12 @@ static int graph_eval(mogp_engine* h, Cluster& c, bool* ok) {
     memcpy(h->eval_key, key, sizeof key);
   }
   CK(h, cudaGraphLaunch(h->eval_exec, h->stream));
-  CK(h, sync_stream(h));
+  *launched = true;
+  return MOGP_OK;
+}
+
+static int eval_collect(mogp_engine* h, Cluster& c, bool* ok) {
+  *ok = false;
   h->launches += h->eval_kernels;
   h->bytes_d2h += 14 * 8;
   const double* hs = reinterpret_cast<const double*>(h->pin);
@@ -1539,8 +1641,12 @@ static int graph_eval(mogp_engine* h, Cluster& c, bool* ok) {
 }
 
 // hw supplies the stream and the workspaces, c is the cluster (of hw itself or of another engine on the device).
-static int objective_impl(mogp_engine* hw, Cluster& c, const double* t, int32_t n_t, double* f, double* g) {
+// objective_begin maps the optimiser coordinates to theta and, when a full evaluation is needed, queues it on
+// hw->stream without waiting (*launched); objective_end - after that stream has been waited for - finishes:
+// eager fallback with the jitter ladder if the queued factorisation failed, priors, Jacobian, chain rule.
+static int objective_begin(mogp_engine* hw, Cluster& c, const double* t, int32_t n_t, bool want_grad, bool* launched) {
   mogp_engine* h = hw;
+  *launched = false;
   Gamma pr[4];
   bool fixed[4];
   priors_of(c.spec, pr, fixed);
@@ -1564,9 +1670,18 @@ static int objective_impl(mogp_engine* hw, Cluster& c, const double* t, int32_t 
       c.valid = c.grad_valid = false;
     }
   }
-  if (g && !c.valid && c.m > 0 && graphs_enabled()) {
+  if (want_grad && !c.valid && c.m > 0 && graphs_enabled()) TRY(eval_launch(h, c, launched));
+  return MOGP_OK;
+}
+
+static int objective_end(mogp_engine* hw, Cluster& c, bool launched, double* f, double* g) {
+  mogp_engine* h = hw;
+  Gamma pr[4];
+  bool fixed[4];
+  priors_of(c.spec, pr, fixed);
+  if (launched) {
     bool ok = false;
-    TRY(graph_eval(h, c, &ok));
+    TRY(eval_collect(h, c, &ok));
     (void)ok;  // on failure valid stays false and the eager path below runs
   }
   if (!c.valid) TRY(infer(h, c));
@@ -1590,8 +1705,15 @@ static int objective_impl(mogp_engine* hw, Cluster& c, const double* t, int32_t 
   return MOGP_OK;
 }
 
+static int objective_impl(mogp_engine* hw, Cluster& c, const double* t, int32_t n_t, double* f, double* g) {
+  bool launched = false;
+  TRY(objective_begin(hw, c, t, n_t, g != nullptr, &launched));
+  if (launched) CK(hw, sync_stream(hw));
+  return objective_end(hw, c, launched, f, g);
+}
+
 int mogp_cluster_objective(mogp_engine* h, int32_t slot, const double* t, int32_t n_t, double* f, double* g) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   return objective_impl(h, h->cl[slot], t, n_t, f, g);
 }
 
@@ -1600,13 +1722,19 @@ int mogp_cluster_objective_on(mogp_engine* worker, mogp_engine* owner, int32_t s
   if (!worker || !owner) return MOGP_EINVAL;
   cudaSetDevice(worker->device);
   if (worker->device != owner->device) FAIL(worker, MOGP_EINVAL, "worker and owner engines must be on the same device");
-  if (slot < 0 || slot >= (int32_t)owner->cl.size() || !owner->cl[slot].used) FAIL(worker, MOGP_EINVAL, "bad cluster slot %d", slot);
-  return objective_impl(worker, owner->cl[slot], t, n_t, f, g);
+  // (the owner is only read here: no check_slot / join_side on it from a worker's thread)
+  const int32_t idx = slot & SLOT_INDEX_MASK;
+  if (slot < 0 || idx >= (int32_t)owner->cl.size() || !owner->cl[idx].used ||
+      ((slot >> SLOT_INDEX_BITS) & SLOT_GEN_MASK) != (owner->cl[idx].gen & SLOT_GEN_MASK))
+    FAIL(worker, MOGP_EINVAL, "bad cluster slot %d", slot);
+  return objective_impl(worker, owner->cl[idx], t, n_t, f, g);
 }
+
+#include "refit.inl"
 
 int mogp_cluster_log_predictive_density(mogp_engine* h, int32_t slot, int64_t n, const double* xs, const double* ys,
                                         double* lpd) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   if (n <= 0 || !xs || !ys || !lpd) FAIL(h, MOGP_EINVAL, "bad query");
   int64_t off[2] = {0, n};
   TRY(stage_query(h, 1, off, xs, ys, nullptr));
@@ -1619,7 +1747,7 @@ int mogp_cluster_log_predictive_density(mogp_engine* h, int32_t slot, int64_t n,
 }
 
 int mogp_cluster_predict(mogp_engine* h, int32_t slot, int64_t n, const double* xs, double* mean, double* var) {
-  TRY(check_slot(h, slot));
+  TRY(slot_in(h, &slot));
   if (n <= 0 || !xs) FAIL(h, MOGP_EINVAL, "bad query");
   int64_t off[2] = {0, n};
   TRY(stage_query(h, 1, off, xs, nullptr, nullptr));
@@ -1640,7 +1768,9 @@ int mogp_score_pairs_dev(mogp_engine* h, int64_t n_patients, int64_t n_visits, c
   cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (n_patients <= 0 || n_visits <= 0 || !off_dev || !x_dev || !y_dev || n_slots <= 0 || !slots || !score_dev)
     FAIL(h, MOGP_EINVAL, "bad arguments");
-  return score_device(h, n_patients, n_visits, off_dev, x_dev, y_dev, n_slots, slots, thr_index, score_dev, mu_thr_dev,
+  std::vector<int32_t> idx(slots, slots + n_slots);
+  for (int32_t& q : idx) TRY(slot_in(h, &q));
+  return score_device(h, n_patients, n_visits, off_dev, x_dev, y_dev, n_slots, idx.data(), thr_index, score_dev, mu_thr_dev,
                       nullptr, nullptr, nullptr, false, nullptr);
 }
 
@@ -1650,11 +1780,11 @@ int mogp_score_pairs(mogp_engine* h, int64_t n_patients, const int64_t* off, con
   cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (n_patients <= 0 || !off || !x || !y || n_slots <= 0 || !slots || !score) FAIL(h, MOGP_EINVAL, "bad arguments");
   // Chunk the patients so the cross-covariance scratch stays bounded (~2 GiB).
+  std::vector<int32_t> idx(slots, slots + n_slots);
+  for (int32_t& q : idx) TRY(slot_in(h, &q));
+  slots = idx.data();
   int64_t msum = 0;
-  for (int s = 0; s < n_slots; ++s) {
-    TRY(check_slot(h, slots[s]));
-    msum += round_up(h->cl[slots[s]].m, TB);
-  }
+  for (int s = 0; s < n_slots; ++s) msum += round_up(h->cl[slots[s]].m, TB);
   const int64_t max_cols = std::max<int64_t>(64, ((int64_t)1 << 28) / std::max<int64_t>(msum, 1));
   int64_t p0 = 0;
   while (p0 < n_patients) {
@@ -1687,8 +1817,11 @@ int mogp_new_cluster_ll(mogp_engine* h, const mogp_model_spec* spec, const doubl
   cudaSetDevice(h->device);  // entry points may be called from any host thread
   if (!spec || !theta || n_patients <= 0 || !off || !x || !y || !ll) FAIL(h, MOGP_EINVAL, "bad arguments");
   if (spec->mean_func && !a_draw) FAIL(h, MOGP_EINVAL, "mean_func needs the randn draws of the NegLinear mapping");
-  for (int64_t p = 0; p < n_patients; ++p)
-    if (off[p + 1] - off[p] > 64 || off[p + 1] - off[p] <= 0) FAIL(h, MOGP_EINVAL, "new-cluster model needs 1..64 visits per patient");
+  bool any_long = false;
+  for (int64_t p = 0; p < n_patients; ++p) {
+    if (off[p + 1] - off[p] <= 0) FAIL(h, MOGP_EINVAL, "new-cluster model needs at least one visit per patient");
+    any_long = any_long || off[p + 1] - off[p] > 64;
+  }
   TRY(stage_query(h, n_patients, off, x, y, a_draw));
   const int64_t R = off[n_patients] - off[0];
   Theta th;
@@ -1702,7 +1835,17 @@ int mogp_new_cluster_ll(mogp_engine* h, const mogp_model_spec* spec, const doubl
   k_new_ll<<<(unsigned)n_patients, 64, 0, h->stream>>>(h->d_qoff, h->d_q, h->d_q + R, h->d_q + 2 * R, th, h->d_out);
   LAUNCHED(h);
   CK(h, cudaGetLastError());
-  return copy_back(h, ll, h->d_out, n_patients);
+  TRY(copy_back(h, ll, h->d_out, n_patients));
+  if (any_long)  // rows longer than the kernel's shared-memory tile (64 visits): the general cluster path
+    for (int64_t p = 0; p < n_patients; ++p) {
+      const int64_t n = off[p + 1] - off[p];
+      if (n <= 64) continue;
+      const double th4[4] = {spec->mean_func ? fabs(a_draw[p]) : 0.0, theta[1], theta[2], theta[3]};
+      int rc = newcomer_ll_general(h, *spec, th4, n, x + off[p], y + off[p], &ll[p]);
+      if (rc == MOGP_ENOTPD) ll[p] = NAN;
+      else if (rc != MOGP_OK) return rc;
+    }
+  return MOGP_OK;
 }
 
 // ---- L-BFGS-B state machine, reverse communication (tests against SciPy; the refit driver uses the same class) ----

@@ -1,0 +1,211 @@
+// refit.inl — the hyper-parameter refit of many clusters, driven by ONE host thread (included by engine.cu).
+//
+// Reference: GPobs.update_suffstats -> model.optimize() (mogp/obsmodel.py:87-94): paramz runs SciPy's L-BFGS-B on
+// the objective -(LML + log prior + log Jacobian), warm-started at the cluster's current hyper-parameters, then
+// evaluates f(x_opt) once more and sets the optimiser array to x_opt.  One refit is a chain of ~10-25 dependent
+// objective evaluations, each a captured graph of ~130 kernels whose diagonal-tile steps run on a single SM: one
+// cluster cannot fill the GPU, thirty can.  The refits of different clusters are independent, so every cluster gets
+// a LANE (a light worker engine: stream + factorisation workspace + graph) and its own L-BFGS-B state machine
+// (lbfgsb.hpp, same evaluation points as SciPy); the caller's thread polls the lanes' events, feeds (f, g) of a
+// finished evaluation to that cluster's state machine and queues its next evaluation at once.  No host thread per
+// cluster, no Python between evaluations; every cluster sees exactly the evaluations of its own sequential optimize().
+struct RefitJob {
+  int32_t slot = -1;
+  Lbfgsb opt;
+  int nfree = 0;
+  int evals = 0, fails = 0;
+  double last_g[4] = {0, 0, 0, 0};
+  bool have_g = false;
+  int phase = 0;          // 0: optimiser running, 1: f(x_opt) re-evaluation requested, 2: done
+  bool launched = false;  // an evaluation is in flight on the lane
+  int lane = -1;
+  int64_t seq = 0;        // launch order (the oldest launch is waited for when nothing has finished)
+  int rc = MOGP_OK;
+};
+
+static int refit_lanes(mogp_engine* h, int want) {
+  while ((int)h->lanes.size() < want) {
+    mogp_engine* l = nullptr;
+    int rc = engine_create_impl(h->device, true, &l);
+    if (rc != MOGP_OK) FAIL(h, rc, "refit lane: %s", g_create_error.c_str());
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) {
+      mogp_engine_destroy(l);
+      FAIL(h, MOGP_ECUDA, "refit lane: event");
+    }
+    h->lanes.push_back(l);
+    h->lane_ev.push_back(e);
+  }
+  for (mogp_engine* l : h->lanes) l->blocking_sync = h->blocking_sync;
+  return MOGP_OK;
+}
+
+// Run job j forward until it has an evaluation in flight (returns with j.launched) or is done.
+static int refit_advance(mogp_engine* h, RefitJob& j, int64_t* seq) {
+  mogp_engine* lane = h->lanes[j.lane];
+  Cluster& c = h->cl[j.slot];
+  for (;;) {
+    if (j.phase == 2) return MOGP_OK;
+    double f = 0.0, g[4] = {0, 0, 0, 0};
+    int rc;
+    if (!j.launched) {  // queue the evaluation at the optimiser's current point
+      bool launched = false;
+      rc = objective_begin(lane, c, j.opt.x, j.nfree, true, &launched);
+      j.evals += 1;
+      h->refit_evals += 1;
+      if (rc == MOGP_OK && launched) {
+        if (cudaEventRecord(h->lane_ev[j.lane], lane->stream) != cudaSuccess) FAIL(h, MOGP_ECUDA, "refit: event record");
+        j.launched = true;
+        j.seq = (*seq)++;
+        h->refit_launched += 1;
+        return MOGP_OK;
+      }
+      if (rc == MOGP_OK) rc = objective_end(lane, c, false, &f, g);  // cached (same theta) or eager
+    } else {  // the caller has seen the lane's event complete
+      j.launched = false;
+      lane->up_off = 0;  // the lane's stream is idle: its upload staging can be reused from the start
+      rc = objective_end(lane, c, true, &f, g);
+    }
+    if (rc == MOGP_ENOTPD) {
+      // paramz Model._objective_grads: a failed evaluation returns a huge objective and the clipped last gradient,
+      // up to 10 times in a row; then the LinAlgError goes up
+      if (j.fails >= 10) {
+        h->err = lane->err;
+        return j.rc = rc;
+      }
+      j.fails += 1;
+      f = 1.7976931348623157e308;
+      for (int i = 0; i < j.nfree; ++i) g[i] = j.have_g ? std::min(1e10, std::max(-1e10, j.last_g[i])) : 0.0;
+    } else if (rc != MOGP_OK) {
+      h->err = lane->err;
+      return j.rc = rc;
+    } else {
+      j.fails = 0;
+      memcpy(j.last_g, g, sizeof(double) * 4);
+      j.have_g = true;
+    }
+    if (j.phase == 1) {  // that was f(x_opt); the final `optimizer_array = x_opt` finds the cluster at theta(x_opt)
+      j.phase = 2;
+      return MOGP_OK;
+    }
+    j.opt.f = f;
+    memcpy(j.opt.g, g, sizeof(double) * j.nfree);
+    Lbfgsb::Task task;
+    do task = j.opt.step();
+    while (task == Lbfgsb::T_NEW_X);
+    if (task != Lbfgsb::T_FG) j.phase = 1;  // finished: opt.x = x_opt, evaluated once more (usually the cached point)
+  }
+}
+
+/* see include/mogp_b200.h */
+int mogp_refit_clusters(mogp_engine* h, int32_t n_slots, const int32_t* slots, int32_t max_concurrent, int32_t* n_evals_out) {
+  if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
+  if (n_slots <= 0 || !slots) FAIL(h, MOGP_EINVAL, "no clusters to refit");
+  std::vector<RefitJob> jobs(n_slots);
+  for (int i = 0; i < n_slots; ++i) {
+    int32_t idx = slots[i];
+    TRY(slot_in(h, &idx));
+    for (int q = 0; q < i; ++q)
+      if (jobs[q].slot == idx) FAIL(h, MOGP_EINVAL, "cluster %d listed twice", slots[i]);
+    jobs[i].slot = idx;
+    if (h->cl[idx].m <= 0) FAIL(h, MOGP_ESTATE, "cluster has no data");
+  }
+  // the lanes read the owner's clusters: everything queued on the owner's streams must have finished
+  join_side(h);
+  CK(h, sync_stream(h));
+  static const int env_lanes = [] {
+    const char* e = getenv("MOGP_REFIT_LANES");
+    return e ? atoi(e) : 0;
+  }();
+  int n_lanes = max_concurrent > 0 ? max_concurrent : (env_lanes > 0 ? env_lanes : 32);
+  n_lanes = std::max(1, std::min(n_lanes, (int)n_slots));
+  TRY(refit_lanes(h, n_lanes));
+  // largest clusters first: the longest chains of evaluations start earliest
+  std::vector<int> order(n_slots);
+  for (int i = 0; i < n_slots; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->cl[jobs[a].slot].m > h->cl[jobs[b].slot].m; });
+  std::vector<int> lane_job(n_lanes, -1);
+  int next = 0, done = 0, rc_all = MOGP_OK;
+  int64_t seq = 0;
+  auto start_job = [&](int lane) -> int {
+    while (next < n_slots) {
+      RefitJob& j = jobs[order[next++]];
+      Cluster& c = h->cl[j.slot];
+      Gamma pr[4];
+      bool fixed[4];
+      priors_of(c.spec, pr, fixed);
+      double t0[4];
+      j.nfree = 0;
+      for (int i = 0; i < 4; ++i)
+        if (!fixed[i]) t0[j.nfree++] = logexp_finv(c.theta[i]);
+      if (j.nfree == 0) {  // nothing to optimise (paramz returns at once)
+        j.phase = 2;
+        ++done;
+        continue;
+      }
+      j.opt.init(j.nfree, t0);
+      j.opt.step();  // -> T_FG at t0
+      j.lane = lane;
+      lane_job[lane] = (int)(&j - jobs.data());
+      int rc = refit_advance(h, j, &seq);
+      if (rc != MOGP_OK) return rc;
+      if (j.phase == 2) {  // finished without ever waiting (every evaluation cached or eager)
+        lane_job[lane] = -1;
+        ++done;
+        continue;
+      }
+      return MOGP_OK;
+    }
+    lane_job[lane] = -1;
+    return MOGP_OK;
+  };
+  for (int l = 0; l < n_lanes && rc_all == MOGP_OK; ++l) rc_all = start_job(l);
+  while (rc_all == MOGP_OK && done < n_slots) {
+    bool progressed = false;
+    int oldest = -1;
+    for (int l = 0; l < n_lanes && rc_all == MOGP_OK; ++l) {
+      const int ji = lane_job[l];
+      if (ji < 0) continue;
+      RefitJob& j = jobs[ji];
+      const cudaError_t q = cudaEventQuery(h->lane_ev[l]);
+      if (q == cudaErrorNotReady) {
+        if (oldest < 0 || j.seq < jobs[lane_job[oldest]].seq) oldest = l;
+        continue;
+      }
+      if (q != cudaSuccess) FAIL(h, MOGP_ECUDA, "refit: %s", cudaGetErrorString(q));
+      progressed = true;
+      rc_all = refit_advance(h, j, &seq);
+      if (rc_all == MOGP_OK && j.phase == 2) {
+        ++done;
+        rc_all = start_job(l);
+      }
+    }
+    if (rc_all != MOGP_OK) break;
+    if (!progressed && oldest >= 0 && h->blocking_sync) cudaEventSynchronize(h->lane_ev[oldest]);  // sleep, not spin
+  }
+  // whatever happened, nothing stays in flight on the lanes
+  for (int l = 0; l < n_lanes; ++l) {
+    cudaStreamSynchronize(h->lanes[l]->stream);
+    h->lanes[l]->up_off = 0;
+    h->launches += h->lanes[l]->launches;
+    h->lanes[l]->launches = 0;
+    h->bytes_h2d += h->lanes[l]->bytes_h2d;
+    h->bytes_d2h += h->lanes[l]->bytes_d2h;
+    h->lanes[l]->bytes_h2d = h->lanes[l]->bytes_d2h = 0;
+  }
+  if (n_evals_out)
+    for (int i = 0; i < n_slots; ++i) n_evals_out[i] = jobs[i].evals;
+  if (rc_all != MOGP_OK) {  // a cluster whose evaluation is abandoned mid-flight has no valid factor
+    for (RefitJob& j : jobs)
+      if (j.launched) h->cl[j.slot].valid = h->cl[j.slot].grad_valid = false;
+  }
+  return rc_all;
+}
+
+int mogp_refit_counters(mogp_engine* h, int64_t* evaluations, int64_t* launched) {
+  if (!h) return MOGP_EINVAL;
+  if (evaluations) *evaluations = h->refit_evals;
+  if (launched) *launched = h->refit_launched;
+  return MOGP_OK;
+}

@@ -12,7 +12,11 @@ Additions (all default to the reference's behaviour):
   init_z       initial partition instead of k-means (sklearn label numbering differs between versions)
   fast_updates None -> True for refit='sweep' (rank-n up/down-dates + leave-block-out own score),
                False for refit='move' (reference-exact data order; every move refactorises anyway)
-  engine       an explicit `_capi.Engine` (one per chain / per GPU)
+  engine       an explicit `_capi.Engine` (one per chain / per GPU); by default every model creates its own
+  optimizer    'native' (default: the engine's L-BFGS-B state machine, mogp_refit_clusters - the evaluation points of
+               SciPy's fmin_l_bfgs_b, all clusters' refits in flight together) or 'scipy' (SciPy drives the objective)
+  savepath     None (default) writes no checkpoints; the reference always saves (its default path is relative to its
+               own source tree) - pass a directory to get its init / iter / MAP / final files
 """
 import numbers
 from pathlib import Path
@@ -22,7 +26,7 @@ from scipy.special import logsumexp
 
 from . import _capi
 from .allocmodel import DPmix
-from .obsmodel import GPobs, Standardize, make_spec, initial_theta, optimize_many
+from .obsmodel import GPobs, Standardize, make_spec, initial_theta, optimize_many, default_optimizer
 from .utils import pack_patients
 
 
@@ -31,7 +35,7 @@ class MoGP_constrained:
                  savename='MoGP_constrained', save_iter=25, kernel='rbf', signal_variance=1.,
                  signal_variance_fix=True, noise_variance=1., noise_variance_fix=False, mean_func=True,
                  threshold=None, onset_anchor=True, normalize=False, Y_mean=None, Y_std=None,
-                 refit='move', init_z=None, fast_updates=None, engine=None, lookahead=0):
+                 refit='move', init_z=None, fast_updates=None, engine=None, lookahead=0, optimizer=None):
         self.X, self.Y = X, Y
         self.allocmodel = DPmix(alpha)
         self.num_iter, self.num_init_clusters, self.rand_seed = num_iter, num_init_clusters, rand_seed
@@ -47,6 +51,9 @@ class MoGP_constrained:
         self.refit, self.init_z = refit, init_z
         self.fast_updates = (refit == 'sweep') if fast_updates is None else bool(fast_updates)
         self._engine = engine
+        if optimizer not in (None, 'native', 'scipy'):
+            raise ValueError("optimizer must be 'native' or 'scipy'")
+        self.optimizer = optimizer
         # refit='sweep' only: visits scored ahead per pass over the factors (0 = engine default, < 0 = off)
         self.lookahead = int(lookahead)
 
@@ -159,8 +166,10 @@ class MoGP_constrained:
     # -- engine plumbing ---------------------------------------------------------------------------------
     @property
     def engine(self):
+        # one private engine per model: an engine holds ONE chain, so two models trained in one process (the reference's
+        # tutorial trains a constrained and an unconstrained one) must not share the process-wide default engine
         if self._engine is None:
-            self._engine = _capi.default_engine()
+            self._engine = _capi.Engine()
         return self._engine
 
     def _spec(self, mean_func=None):
@@ -184,7 +193,7 @@ class MoGP_constrained:
     def _view(self, slot):
         return GPobs(None, None, kernel=self.kernel, signal_variance_fix=self.signal_variance_fix,
                      noise_variance_fix=self.noise_variance_fix, mean_func=self.mean_func, engine=self.engine,
-                     _slot=int(slot))
+                     _slot=int(slot), optimizer=getattr(self, 'optimizer', None))
 
     def _sync_state(self):
         """Mirror z / Nk / obsmodel from the engine's chain."""
@@ -263,15 +272,22 @@ class MoGP_constrained:
         else:
             if perm is None:
                 perm, a, u = self._draws_for_sweep(N)
+            eng.chain_record_probs(True)
             _chosen, mm = eng.chain_sweep(perm, a if self.mean_func else None, u)
             self.min_margin = min(self.min_margin, mm)
+            off, _ids, p = eng.chain_probs()                       # self.p[n] of every step (:276)
+            for s, n in enumerate(perm):
+                self.p[n] = p[off[s]:off[s + 1]]
             self._sync_state()
             self.refit_all()
 
     def refit_all(self):
         """refit='sweep': one L-BFGS-B refit per active cluster (independent; run concurrently on worker engines)."""
         models = [self.obsmodel[k].model for k in self._active()]
-        optimize_many(models, self._refit_workers(len(models)))
+        native = (getattr(self, 'optimizer', None) or default_optimizer()) == 'native'
+        import os
+        optimize_many(models, [] if native else self._refit_workers(len(models)), 'native' if native else 'scipy',
+                      max_concurrent=int(os.environ.get('MOGP_REFIT_CONCURRENCY', '0')))
         for m in models:
             self.n_refit_evals += m.n_evals
             m.n_evals = 0
@@ -329,12 +345,16 @@ class MoGP_constrained:
         self._check_validity_of_predict_inputs(x_new, y_new)
         if self.normalize:
             y_new = (y_new - self.mean) / self.std
+            self._reset_normalizer()                               # :325-328
         # GPobs(x, y) with mean_func NOT forwarded -> default True -> one randn (:330-332); the optimize()
         # the reference runs next (:333) does not change the cached .ll it reads (:339) and draws nothing.
         a = np.random.randn(1, 1)[0, 0]
-        return self.predict_batch(np.asarray(x_new, dtype=np.float64).reshape(1, -1),
-                                  np.asarray(y_new, dtype=np.float64).reshape(1, -1), np.array([a]),
-                                  _normalized=True)[0]
+        p = self.predict_batch(np.asarray(x_new, dtype=np.float64).reshape(1, -1),
+                               np.asarray(y_new, dtype=np.float64).reshape(1, -1), np.array([a]),
+                               _normalized=True)[0]
+        if self.normalize:
+            self._apply_normalizer()                               # :343-345: the per-cluster normalisers end up attached
+        return p
 
     def predict_batch(self, X_new, Y_new, a_draws, _normalized=False):
         """`predict` for P patients at once: NaN-padded P x T matrices -> P x (len(Nk)+1) probabilities.

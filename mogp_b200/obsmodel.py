@@ -39,9 +39,10 @@ class GPModel:
     without the leading A when mean_func=False (obsmodel.py:48-49).
     """
 
-    def __init__(self, engine, spec, theta, slot=None, X=None, Y=None):
+    def __init__(self, engine, spec, theta, slot=None, X=None, Y=None, optimizer=None):
         self._engine = engine
         self._spec = spec
+        self.optimizer = optimizer     # 'native' | 'scipy' | None (= default_optimizer())
         self.normalizer = None
         self.n_evals = 0
         self._fail_count = 0
@@ -107,12 +108,18 @@ class GPModel:
     def objective_function(self):
         return self._engine.cluster_objective(self._slot, None, want_grad=False)[0]
 
+    @property
+    def n_free(self):
+        """Free hyper-parameters: absent A (mean_func=False) and fixed variances are excluded (obsmodel.py:29-30, 51-52)."""
+        s = self._spec
+        return int(bool(s.mean_func)) + int(not s.signal_variance_fix) + 1 + int(not s.noise_variance_fix)
+
     def objective_grads(self, t, worker=None):
         """paramz Model._objective_grads: (f, df/dt) in Logexp space; a non-PD covariance returns a huge
         objective up to 10 times in a row, as paramz does."""
         self.n_evals += 1
         try:
-            f, g = self._engine.cluster_objective(self._slot, t, worker=worker)
+            f, g = self._engine.cluster_objective(self._slot, t, worker=worker, nfree=self.n_free)
             self._fail_count = 0
             self._last_grad = g
         except np.linalg.LinAlgError:
@@ -123,16 +130,23 @@ class GPModel:
             g = np.clip(self._last_grad if self._last_grad is not None else np.zeros(len(t)), -1e10, 1e10)
         return f, g
 
-    def optimize(self, worker=None):                              # obsmodel.py:94, mogp_constrained.py:333
-        """paramz Model.optimize() default = scipy L-BFGS-B (maxfun = maxiter = 1000, m=10, factr=1e7,
+    def optimize(self, worker=None, t0=None):                     # obsmodel.py:94, mogp_constrained.py:333
+        """paramz Model.optimize() default = L-BFGS-B (SciPy's fmin_l_bfgs_b: maxfun = maxiter = 1000, m=10, factr=1e7,
         pgtol=1e-5), warm-started at the current hyper-parameters; then f(x_opt) and a final set.
-        `worker`: run the evaluations on another engine's stream (see `optimize_many`)."""
-        if self._engine.cluster_n_free(self._slot) == 0:
+        optimizer 'native' (default): the engine's own L-BFGS-B state machine behind mogp_refit_clusters - the same
+        evaluation points as SciPy's (tests/test_lbfgsb.py), no Python between evaluations; 'scipy': SciPy drives
+        mogp_cluster_objective (`worker`: on another engine's stream, see `optimize_many`; `t0`: the starting point read by
+        the caller's thread)."""
+        if self.n_free == 0:
             return
-        t0 = self._engine.cluster_optimizer_array(self._slot)
+        if (self.optimizer or default_optimizer()) == 'native' and worker is None:
+            self.n_evals += int(self._engine.refit_clusters([self._slot])[0])
+            return
+        if t0 is None:
+            t0 = self._engine.cluster_optimizer_array(self._slot)
         x_opt, _f, _d = _sciopt.fmin_l_bfgs_b(lambda t: self.objective_grads(t, worker), t0, maxfun=1000, maxiter=1000)
         self.objective_grads(x_opt, worker)
-        self._engine.cluster_objective(self._slot, x_opt, want_grad=False, worker=worker)
+        self._engine.cluster_objective(self._slot, x_opt, want_grad=False, worker=worker, nfree=self.n_free)
 
     def plot_mean(self, *a, **k):
         raise NotImplementedError("GPy/matplotlib plotting is outside the likelihood engine")
@@ -162,18 +176,36 @@ class GPModel:
         self._spec = _capi.ModelSpec(*st['spec'])
         self.normalizer = st['normalizer']
         self.n_evals, self._fail_count, self._last_grad = 0, 0, None
+        self.optimizer = None
         self._slot = self._engine.cluster_create(self._spec, st['theta'])
         self._owns_slot = True
         self.set_XY(st['x'], st['y'])
 
 
-def optimize_many(models, workers):
+def default_optimizer():
+    """'native' (the engine's L-BFGS-B, mogp_refit_clusters) unless MOGP_OPTIMIZER=scipy."""
+    import os
+    v = os.environ.get('MOGP_OPTIMIZER', 'native')
+    if v not in ('native', 'scipy'):
+        raise ValueError("MOGP_OPTIMIZER must be 'native' or 'scipy'")
+    return v
+
+
+def optimize_many(models, workers, optimizer=None, max_concurrent=0):
     """Refit several clusters of one engine concurrently: the L-BFGS-B runs are independent (the reference
-    refits one cluster at a time, obsmodel.py:94; the result per cluster is the same), each runs in its own host
-    thread on a worker engine's stream so that the small factorisation kernels of different clusters overlap on
-    the GPU.  Deterministic: every cluster sees exactly the evaluations of its own sequential `optimize()`."""
+    refits one cluster at a time, obsmodel.py:94; the result per cluster is the same).
+    'native' (default): one call of mogp_refit_clusters - a lane (stream + workspace) and an L-BFGS-B state machine per
+    cluster, all driven by this thread.  'scipy' (parity mode): each cluster runs SciPy's optimiser in its own host thread
+    on a worker engine's stream.  Either way every cluster sees exactly the evaluations of its own sequential `optimize()`."""
     models = list(models)
     if not models:
+        return
+    if (optimizer or default_optimizer()) == 'native':
+        live = [m for m in models if m.n_free > 0]
+        if live:
+            n = live[0]._engine.refit_clusters([m.slot for m in live], max_concurrent)
+            for m, k in zip(live, n):
+                m.n_evals += int(k)
         return
     if not workers or len(models) == 1:
         for m in models:
@@ -186,10 +218,14 @@ def optimize_many(models, workers):
     for w in workers:
         free.put(w)
 
+    # the owner engine is only touched from this thread: the starting points are read here, before the dispatch
+    starts = {id(m): m._engine.cluster_optimizer_array(m.slot) for m in models if m.n_free > 0}
+
     def run(m):
         w = free.get()
         try:
-            m.optimize(worker=w)
+            if m.n_free > 0:
+                m.optimize(worker=w, t0=starts[id(m)])
         finally:
             free.put(w)
 
@@ -216,17 +252,17 @@ class GPobs:
     """Reference signature: obsmodel.py:7-8."""
 
     def __init__(self, X, Y, kernel='rbf', signal_variance=1., signal_variance_fix=True, noise_variance=1.,
-                 noise_variance_fix=False, mean_func=True, lengthscale=4., engine=None, _slot=None):
+                 noise_variance_fix=False, mean_func=True, lengthscale=4., engine=None, _slot=None, optimizer=None):
         engine = engine or _capi.default_engine()
         spec = make_spec(kernel, mean_func, signal_variance_fix, noise_variance_fix)
         if _slot is not None:               # view of a slot the chain engine already manages
-            self.model = GPModel(engine, spec, None, slot=_slot)
+            self.model = GPModel(engine, spec, None, slot=_slot, optimizer=optimizer)
             self._X, self._Y = None, None
         else:
             # GPy.mappings.Linear.__init__ draws A from the global generator (neg_linear.py:19-20)
             a_draw = np.random.randn(1, 1)[0, 0] if mean_func else None
             theta = initial_theta(kernel, signal_variance, noise_variance, lengthscale, a_draw)
-            self.model = GPModel(engine, spec, theta, X=_col(X), Y=_col(Y))
+            self.model = GPModel(engine, spec, theta, X=_col(X), Y=_col(Y), optimizer=optimizer)
             self._X, self._Y = X, Y
         self.ll = self.model.log_likelihood()                      # obsmodel.py:56
         self.tempX = None

@@ -68,8 +68,16 @@ def predict_sharded(score_fn, X_new, Y_new, a_draws):
     P = X_new.shape[0]
     lo, hi = shard_bounds(P, world, rank)
     local = score_fn(X_new[lo:hi], Y_new[lo:hi], np.asarray(a_draws)[lo:hi]) if hi > lo else None
+    # a rank whose shard is empty (fewer patients than ranks) contributes a 0-row block: every rank takes the same path
+    # through the collectives, the column count comes from the ranks that scored something
+    cols = local.shape[1] if local is not None else 0
+    if dist is not None and world > 1:
+        import torch
+        t = torch.tensor([cols], dtype=torch.int64, device=_device_for_backend())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cols = int(t.item())
     if local is None:
-        raise ValueError("fewer patients than ranks")
+        local = np.zeros((0, cols))
     return all_gather_rows(local, P)
 
 

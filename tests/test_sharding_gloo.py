@@ -53,6 +53,9 @@ WORKER = textwrap.dedent("""
     full = parallel.predict_sharded(scorer, X, Y, a)
     ref = scorer(X, Y, a)
     assert full.shape == ref.shape and np.array_equal(full, ref), "sharded prediction differs"
+    # fewer patients than ranks: the rank with an empty shard contributes a 0-row block instead of raising / hanging
+    one = parallel.predict_sharded(scorer, X[:1], Y[:1], a[:1])
+    assert one.shape == (1, K + 1) and np.array_equal(one, scorer(X[:1], Y[:1], a[:1])), "one-patient sharded prediction differs"
     mine = {{c: dict(z=np.full(4, c, dtype=np.int32), ll=np.array([c * 0.5])) for c in parallel.chains_for_rank(7, world, rank)}}
     allc = parallel.gather_chain_results(mine, 7)
     assert [int(r['z'][0]) for r in allc] == list(range(7))
