@@ -208,6 +208,25 @@ class MoGP_constrained:
                 self.obsmodel[k] = self._view(slots[k])
         self._slots = slots
 
+    # -- chain snapshots (bench.py times different legs from the same state; not in the reference) ----------
+    def snapshot(self):
+        """Assignments, per-id hyper-parameters and the generator state of the running chain."""
+        eng = self.engine
+        z, Nk, slots = eng.chain_state(self.allocmodel.N)
+        theta = np.zeros((len(Nk), 4))
+        for k in range(len(Nk)):
+            if Nk[k] > 0:
+                theta[k] = eng.cluster_get_theta(int(slots[k]))
+        return dict(z=z.copy(), theta=theta, rng=np.random.get_state())
+
+    def restore(self, snap):
+        """Re-attach the chain at a snapshot: every active cluster is refactorised from its members (in patient-index
+        order) at the snapshot's hyper-parameters."""
+        self.engine.chain_init(self._chain_config(), snap['z'], snap['theta'])
+        np.random.set_state(snap['rng'])
+        self.obsmodel = dict()
+        self._sync_state()
+
     # -- initialisation: mogp_constrained.py:182-214 -----------------------------------------------------
     def initialize_sampler(self, init_K, onset_anchor):
         np.random.seed(self.rand_seed)

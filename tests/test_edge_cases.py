@@ -206,3 +206,81 @@ def test_patient_table_built_on_the_device_equals_numpy_compaction(eng):
         eng.set_patients_matrix(X, Y)
     with pytest.raises(ValueError, match="different numbers of non-NaN cells"):
         pack_patients(X, Y)
+
+
+def test_two_models_in_one_process_do_not_share_an_engine():
+    """The reference's tutorial trains a constrained and an unconstrained model in one process.  A model built without an
+    explicit engine gets its OWN engine (an engine holds one chain): training B must not change what A predicts."""
+    from mogp_b200 import MoGP_constrained, MoGP
+    from mogp_b200.synth import alsfrs_like, block_init
+    X, Y = alsfrs_like(60, seed=13)
+    z0 = block_init(60, 3, X)
+    kw = dict(alpha=1.0, num_iter=3, rand_seed=1, normalize=True, noise_variance=0.5, refit='sweep', init_z=z0)
+    A = MoGP_constrained(X=X.copy(), Y=Y.copy(), threshold=0.5, **kw)
+    A.sample()
+    xs = np.linspace(0.0, 6.0, 7).reshape(-1, 1)
+    before = {int(k): A.obsmodel[k].model.predict(xs) for k in A._active()}
+    x_new, y_new = np.array([0.0, 0.5, 1.0, 2.4]), np.array([48., 44., 41., 19.])
+    np.random.seed(5)
+    p_before = A.predict(x_new, y_new)
+    B = MoGP(X=X.copy(), Y=Y.copy(), **kw)
+    B.sample()
+    assert A.engine is not B.engine
+    for k, (m0, v0) in before.items():
+        m1, v1 = A.obsmodel[k].model.predict(xs)
+        assert np.array_equal(m0, m1) and np.array_equal(v0, v1)
+    np.random.seed(5)
+    assert np.array_equal(A.predict(x_new, y_new), p_before)
+
+
+def test_stale_cluster_handles_raise(eng):
+    """A slot index is reused after a cluster is freed; the handle carries the slot's generation, so a view of the cluster
+    that used to live there raises instead of reading its successor."""
+    from mogp_b200 import _capi
+    from mogp_b200.obsmodel import make_spec
+    spec = make_spec('rbf', True, True, False)
+    th = np.array([0.3, 1.0, 2.0, 0.3])
+    x = np.linspace(0, 5, 20)
+    s1 = eng.cluster_create(spec, th)
+    eng.cluster_set_data(s1, x, np.sin(x))
+    ll1 = eng.cluster_loglik(s1)
+    eng.cluster_free(s1)
+    s2 = eng.cluster_create(spec, th)
+    eng.cluster_set_data(s2, x, np.cos(x))
+    assert (s1 & 0xFFFF) == (s2 & 0xFFFF) and s1 != s2            # same slot index, new generation
+    with pytest.raises(_capi.EngineError, match="stale cluster handle"):
+        eng.cluster_loglik(s1)
+    assert eng.cluster_loglik(s2) != ll1
+    eng.cluster_free(s2)
+
+
+def test_rows_longer_than_the_fast_paths(eng):
+    """The rank-update fast path takes rows of up to 16 visits, the one-patient marginal kernel up to 64; longer rows go
+    through the general cluster path (the reference accepts any row length) - same assignments as the oracle."""
+    import oracle
+    from mogp_b200 import MoGP_constrained
+    rs = np.random.RandomState(3)
+    N, T = 12, 80
+    X = np.full((N, T), np.nan)
+    Y = np.full((N, T), np.nan)
+    for i, nv in enumerate([5, 70, 8, 20, 6, 75, 9, 4, 30, 7, 66, 5]):
+        t = np.sort(rs.uniform(0.1, 8.0, nv))
+        X[i, 0], Y[i, 0] = 0.0, 48.0
+        X[i, 1:nv + 1] = t
+        Y[i, 1:nv + 1] = np.clip(np.round(48 - (3 + 2 * (i % 3)) * t + rs.randn(nv) * 1.5), 0, 48)
+    z0 = (np.arange(N) % 2).astype(np.int32)
+    for refit in ('sweep', 'move'):
+        kw = dict(alpha=1.0, num_iter=3, rand_seed=2, normalize=True, noise_variance=0.5, threshold=0.5, refit=refit, init_z=z0)
+        orc = oracle.MoGP_constrained(X=X.copy(), Y=Y.copy(), **kw)
+        orc.sample()
+        mix = MoGP_constrained(X=X.copy(), Y=Y.copy(), engine=eng, **kw)
+        mix.sample()
+        assert list(mix.z) == list(orc.z) and list(mix.allocmodel.Nk) == list(orc.allocmodel.Nk)
+        assert np.allclose(mix.lobs, orc.lobs, rtol=1e-6)
+    x_new = np.sort(rs.uniform(0.1, 8, 70))
+    y_new = np.clip(48 - 5 * x_new, 0, 48)
+    np.random.seed(9)
+    po = orc.predict(x_new, y_new)
+    np.random.seed(9)
+    pe = mix.predict(x_new, y_new)
+    assert np.max(np.abs(pe - po)) < 1e-8
