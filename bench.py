@@ -666,6 +666,7 @@ def leg_chains(args, D, steps, warmup, n_chains=None):
         mix = MoGP(X=X, Y=Y, alpha=K0 / np.log10(N), rand_seed=cid, normalize=True, noise_variance=0.5,
                    refit=args.chain_refit, init_z=z0, engine=eng)
         mix.refit_concurrency = 1          # the chains themselves already run concurrently
+        mix.refit_lanes = 4
         np.random.seed(cid)
         mix.initialize_sampler(K0, True)
         rs = np.random.RandomState(cid)

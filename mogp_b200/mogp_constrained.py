@@ -82,6 +82,9 @@ class MoGP_constrained:
         if os.environ.get('MOGP_REFIT_CONCURRENCY'):               # 1 = refit in the calling thread (profilers)
             self.refit_concurrency = max(1, int(os.environ['MOGP_REFIT_CONCURRENCY']))
         self._workers = None
+        # native optimiser: clusters refitted together by mogp_refit_clusters (0 = the engine's default, 32 lanes); a process
+        # that runs many chains at once gives each of them a few
+        self.refit_lanes = int(os.environ.get('MOGP_REFIT_CONCURRENCY', '0'))
         self.min_margin = np.inf       # smallest |u - cdf edge| seen (assignment-parity diagnostic)
         self.n_refit_evals = 0
 
@@ -304,9 +307,8 @@ class MoGP_constrained:
         """refit='sweep': one L-BFGS-B refit per active cluster (independent; run concurrently on worker engines)."""
         models = [self.obsmodel[k].model for k in self._active()]
         native = (getattr(self, 'optimizer', None) or default_optimizer()) == 'native'
-        import os
         optimize_many(models, [] if native else self._refit_workers(len(models)), 'native' if native else 'scipy',
-                      max_concurrent=int(os.environ.get('MOGP_REFIT_CONCURRENCY', '0')))
+                      max_concurrent=int(getattr(self, 'refit_lanes', 0)))
         for m in models:
             self.n_refit_evals += m.n_evals
             m.n_evals = 0

@@ -216,10 +216,21 @@ def test_jitchol_ladder_matches_the_oracle(eng):
     eng.cluster_free(slot)
 
 
-def test_not_positive_definite_raises_linalgerror_and_ten_failures_are_swallowed(eng):
+def test_not_positive_definite_raises_linalgerror_and_ten_failures_are_swallowed(eng, monkeypatch):
     """A covariance that stays non-PD through the ladder raises numpy.linalg.LinAlgError (what GPy's jitchol raises); inside
-    optimize() paramz swallows up to 10 consecutive failures (huge objective, clipped gradient) and re-raises the 11th."""
+    optimize() paramz swallows up to 10 consecutive failures (huge objective, clipped gradient) and re-raises the 11th.
+    The failure is provoked with a NaN hyper-parameter.  The engine treats a non-finite factorisation as failed; LAPACK's
+    dpotrf as built into OpenBLAS lets NaN through without an error code, so the oracle's jitchol is given the same check
+    here - the semantics under test are the ladder's exit and paramz's counting, not who notices a NaN first."""
+    import oracle.gpy_restated as gr
     from mogp_b200.obsmodel import GPobs
+    plain_jitchol = gr.jitchol
+
+    def jitchol_checked(A, maxtries=5):
+        if not np.all(np.isfinite(A)):
+            raise np.linalg.LinAlgError("not positive definite, even with jitter.")
+        return plain_jitchol(A, maxtries)
+    monkeypatch.setattr(gr, "jitchol", jitchol_checked)
     rs = np.random.RandomState(2)
     x = np.sort(rs.uniform(0, 8, 40))
     y = (48 - 6 * x + rs.randn(40) * 3 - 30) / 20
