@@ -190,6 +190,19 @@ int mogp_score_pairs_dev(mogp_engine* h, int64_t n_patients, int64_t n_visits, c
 int mogp_new_cluster_ll(mogp_engine* h, const mogp_model_spec* spec, const double theta[4], int64_t n_patients,
                         const int64_t* off, const double* x, const double* y, const double* a_draw, double* ll);
 
+/* ---- the sampler's initial partition (mogp_constrained.py:182-207) ------------------------------------------------ */
+/* KMeans(n_clusters=K, random_state=seed, n_init=n_init).fit(x.reshape(-1, 1)).labels_ for the one-dimensional data the
+   reference clusters (each patient's first-visit time, X[:, 1] with an onset anchor, :198-205), on the device: data
+   centring, k-means++ seeding and Lloyd iterations with scikit-learn's float64 arithmetic and stopping rules (tol is the
+   relative tolerance, 1e-4 in sklearn; max_iter 300), the best of n_init runs by inertia.  u[n_u] = the uniforms sklearn
+   would take from RandomState(seed), i.e. RandomState(seed).random_sample(n_init * (1 + (K - 1) * (2 + int(ln K)))):
+   like every other draw of the chain they are made on the host.  Outputs: labels_out[n] (cluster id per point, centres
+   numbered in the order the seeding chose them - sklearn's numbering), optional centers_out[K], *inertia_out,
+   *best_run_out, *n_iter_out. */
+int mogp_kmeans_init(mogp_engine* h, int64_t n, const double* x, int32_t K, int32_t n_init, int32_t max_iter, double tol,
+                     const double* u, int64_t n_u, int32_t* labels_out, double* centers_out, double* inertia_out,
+                     int32_t* best_run_out, int32_t* n_iter_out);
+
 /* ---- collapsed Gibbs sweep (mogp_constrained.py:231-284 + allocmodel.py:22-34) ------------- */
 typedef struct mogp_chain_config {
   mogp_model_spec spec;

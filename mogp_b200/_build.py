@@ -3,9 +3,9 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, "libmogp_b200.so")
+LIB = os.environ.get("MOGP_B200_LIB") or os.path.join(HERE, "libmogp_b200.so")   # (override: sanitizer builds)
 SOURCES = [os.path.join(HERE, "csrc", f) for f in
-           ("engine.cu", "chain.inl", "refit.inl", "lbfgsb.hpp", "tile.cuh", "factor.cuh", "score.cuh", "update.cuh")]
+           ("engine.cu", "chain.inl", "refit.inl", "lbfgsb.hpp", "tile.cuh", "factor.cuh", "score.cuh", "update.cuh", "kmeans.cuh")]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "mogp_b200.h")
 
 

@@ -83,6 +83,8 @@ SIGNATURES = {
     "mogp_score_pairs_dev": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, _ip,
                                        C.c_int32, C.c_void_p, C.c_void_p]),
     "mogp_new_cluster_ll": (C.c_int, [_H, C.POINTER(ModelSpec), _dp, C.c_int64, _lp, _dp, _dp, _dp, _dp]),
+    "mogp_kmeans_init": (C.c_int, [_H, C.c_int64, _dp, C.c_int32, C.c_int32, C.c_int32, C.c_double, _dp, C.c_int64, _ip, _dp,
+                                   _dp, _ip, _ip]),
     "mogp_chain_init": (C.c_int, [_H, C.POINTER(ChainConfig), C.c_int64, _ip, C.c_int32, _dp]),
     "mogp_chain_step_begin": (C.c_int, [_H, C.c_int64]),
     "mogp_chain_step_score": (C.c_int, [_H, C.c_double, _ip, _ip, _dp, C.c_int32]),
@@ -377,6 +379,25 @@ class Engine:
         self.check(self.lib.mogp_new_cluster_ll(self.h, C.byref(spec), dptr(theta), len(off) - 1, lptr(off), dptr(x),
                                                 dptr(y), dptr(a_draw), dptr(out)))
         return out
+
+    def kmeans_init(self, x, n_clusters, seed, n_init=10, max_iter=300, tol=1e-4, details=False):
+        """sklearn.cluster.KMeans(n_clusters, random_state=seed, n_init=n_init).fit(x[:, None]).labels_ on the device
+        (mogp_constrained.py:182-207; 1-D data).  The uniforms sklearn's k-means++ would draw from RandomState(seed) are
+        made here, in its order."""
+        x = f64(x).ravel()
+        K = int(n_clusters)
+        trials = 2 + int(np.log(K))
+        u = np.random.RandomState(seed).random_sample(int(n_init) * (1 + (K - 1) * trials))
+        labels = np.empty(x.size, dtype=np.int32)
+        centers = np.empty(K)
+        inertia = C.c_double()
+        best, it = C.c_int32(), C.c_int32()
+        self.check(self.lib.mogp_kmeans_init(self.h, x.size, dptr(x), K, int(n_init), int(max_iter), float(tol), dptr(u),
+                                             u.size, iptr(labels), dptr(centers), C.byref(inertia), C.byref(best),
+                                             C.byref(it)))
+        if details:
+            return labels, dict(centers=centers, inertia=inertia.value, best_run=best.value, n_iter=it.value)
+        return labels
 
     # -- chain ----------------------------------------------------------------------------------
     def chain_init(self, cfg, z, theta_of_id):

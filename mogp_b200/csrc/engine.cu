@@ -23,6 +23,7 @@
 #include "lbfgsb.hpp"
 #include "score.cuh"
 #include "update.cuh"
+#include "kmeans.cuh"
 
 using namespace mogp;
 
@@ -1731,6 +1732,107 @@ int mogp_cluster_objective_on(mogp_engine* worker, mogp_engine* owner, int32_t s
 }
 
 #include "refit.inl"
+
+// ---- k-means initialisation (mogp_constrained.py:182-207), see kmeans.cuh ------------------------------------------
+int mogp_kmeans_init(mogp_engine* h, int64_t n, const double* x, int32_t K, int32_t n_init, int32_t max_iter, double tol,
+                     const double* u, int64_t n_u, int32_t* labels_out, double* centers_out, double* inertia_out,
+                     int32_t* best_run_out, int32_t* n_iter_out) {
+  if (!h) return MOGP_EINVAL;
+  cudaSetDevice(h->device);  // entry points may be called from any host thread
+  if (n <= 0 || !x || K <= 0 || K > n || K > 4096 || n_init <= 0 || max_iter <= 0 || !u || !labels_out)
+    FAIL(h, MOGP_EINVAL, "bad k-means arguments (n=%lld, K=%d)", (long long)n, K);
+  const int trials = 2 + (int)log((double)K);  // n_local_trials of sklearn's _kmeans_plusplus
+  const int64_t per = 1 + (int64_t)(K - 1) * trials;
+  if (trials > 16 || n_u < per * n_init) FAIL(h, MOGP_EINVAL, "k-means needs %lld uniforms, got %lld", (long long)(per * n_init), (long long)n_u);
+  // first centre of every run: RandomState.choice(n, p = 1/n): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, 'right')
+  std::vector<int64_t> first(n_init);
+  {
+    std::vector<double> cdf(n);
+    const double p = 1.0 / (double)n;
+    double run = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+      run += p;
+      cdf[i] = run;
+    }
+    const double last = cdf[n - 1];
+    for (int64_t i = 0; i < n; ++i) cdf[i] /= last;
+    for (int r = 0; r < n_init; ++r) {
+      const double uv = u[(int64_t)r * per];
+      first[r] = std::min<int64_t>(n - 1, std::upper_bound(cdf.begin(), cdf.end(), uv) - cdf.begin());
+    }
+  }
+  double *d_x = nullptr, *d_u = nullptr;
+  int64_t* d_first = nullptr;
+  int32_t* d_lab = nullptr;
+  struct Guard {
+    double *&a, *&b;
+    int64_t*& c;
+    int32_t*& d;
+    ~Guard() {
+      cudaFree(a);
+      cudaFree(b);
+      cudaFree(c);
+      cudaFree(d);
+    }
+  } guard{d_x, d_u, d_first, d_lab};
+  // d_x: x | xc | stat[2] | closest[n_init][n] | centers[n_init][K] | inertia[n_init]
+  const int64_t nx = 2 * n + 2 + (int64_t)n_init * n + (int64_t)n_init * K + n_init;
+  CK(h, cudaMalloc((void**)&d_x, sizeof(double) * nx));
+  CK(h, cudaMalloc((void**)&d_u, sizeof(double) * per * n_init));
+  CK(h, cudaMalloc((void**)&d_first, sizeof(int64_t) * n_init));
+  CK(h, cudaMalloc((void**)&d_lab, sizeof(int32_t) * (2 * (int64_t)n_init * n + n_init)));
+  double* d_xc = d_x + n;
+  double* d_stat = d_xc + n;
+  double* d_closest = d_stat + 2;
+  double* d_centers = d_closest + (int64_t)n_init * n;
+  double* d_inertia = d_centers + (int64_t)n_init * K;
+  int32_t* d_lab_old = d_lab + (int64_t)n_init * n;
+  int32_t* d_iters = d_lab_old + (int64_t)n_init * n;
+  CK(h, cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(d_u, u, sizeof(double) * per * n_init, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(d_first, first.data(), sizeof(int64_t) * n_init, cudaMemcpyHostToDevice, h->stream));
+  h->bytes_h2d += (int64_t)(sizeof(double) * (n + per * n_init) + sizeof(int64_t) * n_init);
+  k_kmeans_center<<<1, KM_THREADS, 0, h->stream>>>(d_x, n, d_xc, d_stat);
+  LAUNCHED(h);
+  k_kmeans_seed<<<n_init, KM_THREADS, 0, h->stream>>>(d_xc, n, K, trials, d_u, per, d_first, d_closest, d_centers);
+  LAUNCHED(h);
+  const int S = K >= KM_THREADS ? 1 : KM_THREADS / K;
+  const size_t smem = sizeof(double) * (3 * (size_t)K + 2 * (size_t)S * K);
+  if (smem > 48 * 1024) CK(h, cudaFuncSetAttribute(k_kmeans_lloyd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_kmeans_lloyd<<<n_init, KM_THREADS, smem, h->stream>>>(d_xc, n, K, max_iter, d_stat, tol, d_centers, d_lab, d_lab_old, d_inertia,
+                                                          d_iters);
+  LAUNCHED(h);
+  CK(h, cudaGetLastError());
+  std::vector<int32_t> lab((size_t)n_init * n), iters(n_init);
+  std::vector<double> inertia(n_init), centers((size_t)n_init * K);
+  double stat[2];
+  CK(h, cudaMemcpyAsync(lab.data(), d_lab, sizeof(int32_t) * (size_t)n_init * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(iters.data(), d_iters, sizeof(int32_t) * n_init, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(inertia.data(), d_inertia, sizeof(double) * n_init, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(centers.data(), d_centers, sizeof(double) * (size_t)n_init * K, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(stat, d_stat, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, sync_stream(h));
+  h->bytes_d2h += (int64_t)(sizeof(int32_t) * ((size_t)n_init * n + n_init) + sizeof(double) * (n_init + (size_t)n_init * K + 2));
+  // KMeans.fit: keep a run if its inertia is lower AND its clustering is not the same up to a relabelling
+  auto same_clustering = [&](const int32_t* a, const int32_t* b) {
+    std::vector<int32_t> map(K, -1);
+    for (int64_t i = 0; i < n; ++i) {
+      if (map[a[i]] == -1) map[a[i]] = b[i];
+      else if (map[a[i]] != b[i]) return false;
+    }
+    return true;
+  };
+  int best = 0;
+  for (int r = 1; r < n_init; ++r)
+    if (inertia[r] < inertia[best] && !same_clustering(lab.data() + (size_t)r * n, lab.data() + (size_t)best * n)) best = r;
+  memcpy(labels_out, lab.data() + (size_t)best * n, sizeof(int32_t) * n);
+  if (centers_out)
+    for (int j = 0; j < K; ++j) centers_out[j] = centers[(size_t)best * K + j] + stat[0];  // back on the data's scale
+  if (inertia_out) *inertia_out = inertia[best];
+  if (best_run_out) *best_run_out = best;
+  if (n_iter_out) *n_iter_out = iters[best];
+  return MOGP_OK;
+}
 
 int mogp_cluster_log_predictive_density(mogp_engine* h, int32_t slot, int64_t n, const double* xs, const double* ys,
                                         double* lpd) {

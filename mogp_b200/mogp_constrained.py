@@ -236,10 +236,10 @@ class MoGP_constrained:
         if self.init_z is not None:
             z = np.asarray(self.init_z).astype(np.int32).copy()
         else:
-            from sklearn.cluster import KMeans
+            # KMeans(n_clusters=init_K, random_state=rand_seed, n_init=10) on each patient's first-visit time (:198-205),
+            # on the device (mogp_kmeans_init: sklearn's arithmetic, draws and label numbering)
             col = 1 if onset_anchor else 0
-            km = KMeans(n_clusters=init_K, random_state=self.rand_seed, n_init=10).fit(self.X[:, col].reshape(-1, 1))
-            z = km.labels_.astype(np.int32)
+            z = self.engine.kmeans_init(self.X[:, col], init_K, self.rand_seed, n_init=10).astype(np.int32)
         n_ids = len(np.unique(z))
         if z.max() + 1 != n_ids:
             raise ValueError("initial cluster ids must be 0..K-1 without gaps")
