@@ -440,7 +440,8 @@ def run_b200(args):
                           "optimizer": mix.optimizer or os.environ.get("MOGP_OPTIMIZER", "native"),
                           "start": "sweeps {}..{} of a chain started from the generator's classes".format(args.warmup + 1, args.warmup + args.steps),
                           "lookahead": {k: counters[k] for k in ("window_passes", "rescoring_passes", "window_patients",
-                                                                 "open_s", "rescore_s", "commit_s", "rank_corrections", "correct_s", "replayed")}}}
+                                                                 "open_s", "rescore_s", "commit_s", "rank_corrections", "correct_s", "replayed",
+                                                                 "window_pairs", "pruned_pairs")}}}
         if world == 1 and not args.no_cpu_baseline:
             line.update(cpu_and_parity(args, local))
     secondary = {}

@@ -106,7 +106,9 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
    out[11] = moves whose effect on the cached scores was a rank-n correction, out[12] = host seconds in them,
    out[13] = (cluster, batch) corrections replayed for the next batch's positions,
    out[14] = with MOGP_CHECK_CORRECTIONS=1 in the environment: worst relative disagreement between a rank-n corrected
-   score / threshold mean and the same pair re-scored from the updated factor, out[15] = pairs checked. */
+   score / threshold mean and the same pair re-scored from the updated factor, out[15] = pairs checked,
+   out[16] = (patient, cluster) pairs of the window passes, out[17] = those the monotonicity rule excluded on the device
+   before the O(m^2) product (their mean alone decides, mogp_constrained.py:254-266). */
 int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out);
 
 /* ---- one cluster's GP = one GPobs object ------------------------------------------------- */

@@ -742,9 +742,9 @@ int win_prepare(mogp_engine* h, int64_t n_steps, const int64_t* order, const dou
   w.own_flag.assign(n_steps, 0.0);
   w.own_ok.assign(n_steps, 0);
   TRY(ensure(h, &h->d_woff, &h->woff_elems, n_steps + 1));
-  TRY(ensure(h, &h->d_wq, &h->wq_elems, 2 * R + n_steps + 1));
+  TRY(ensure(h, &h->d_wq, &h->wq_elems, 2 * R + 2 * n_steps + 1));
   char* up = nullptr;
-  const size_t bytes = sizeof(int64_t) * (n_steps + 1) + sizeof(double) * (2 * R + n_steps);
+  const size_t bytes = sizeof(int64_t) * (n_steps + 1) + sizeof(double) * (2 * R + 2 * n_steps);
   TRY(stage_alloc(h, bytes, &up));
   int64_t* so = reinterpret_cast<int64_t*>(up);
   double* sd = reinterpret_cast<double*>(so + n_steps + 1);
@@ -757,9 +757,12 @@ int win_prepare(mogp_engine* h, int64_t n_steps, const int64_t* order, const dou
       memcpy(sd + R + w.col0[v], h->h_y.data() + c0, sizeof(double) * ni);
     }
     sd[2 * R + v] = a_draw ? a_draw[v] : 0.0;
+    // the raw cell Y[n, index_to_eval] of the monotonicity rule (NaN: the rule never fires), for the device-side pruning
+    const int64_t pn = order[v];
+    sd[2 * R + n_steps + v] = (!h->h_ythr.empty() && pn >= 0 && pn < ch.N) ? h->h_ythr[pn] : NAN;
   }
   CK(h, cudaMemcpyAsync(h->d_woff, so, sizeof(int64_t) * (n_steps + 1), cudaMemcpyHostToDevice, h->stream));
-  CK(h, cudaMemcpyAsync(h->d_wq, sd, sizeof(double) * (2 * R + n_steps), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_wq, sd, sizeof(double) * (2 * R + 2 * n_steps), cudaMemcpyHostToDevice, h->stream));
   h->bytes_h2d += (int64_t)bytes;
   w.open = true;
   return MOGP_OK;
@@ -819,6 +822,8 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   b.slots.clear();
   b.epoch.clear();
   b.mpad.clear();
+  b.msz.clear();
+  b.prof = h->prof_on;
   win_size_slots(w, h->cl.size());
   for (size_t k = 0; k < ch.Nk.size(); ++k)
     if (ch.Nk[k] > 0 && ch.slot_of_id[k] >= 0) {
@@ -830,6 +835,7 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
       b.slots.push_back(slot);
       b.epoch.push_back(w.slot_epoch[slot]);
       b.mpad.push_back(round_up(h->cl[slot].m, TB));
+      b.msz.push_back(h->cl[slot].m);
     }
   const int ns = (int)b.slots.size();
   const int thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
@@ -863,9 +869,12 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   h->stream = h->ahead;
   b.pl = ScorePlan();
   bf.res.zigzag = pipeline_depth() >= 2 ? env_int("MOGP_ZIGZAG", 0) : 0;
+  // the monotonicity rule applied on the device before the O(m^2) product (MOGP_PRUNE=0: after it, on the host only)
+  PruneSpec prune{h->d_wq + 2 * Rtot + w.n + s0, ch.cfg.threshold};
+  const bool do_prune = ch.cfg.use_threshold && env_int("MOGP_PRUNE", 1) != 0 && env_int("MOGP_REPLAY", 0) == 0;
   if (ns > 0)
     TRY(score_device(h, cnt, R, h->d_woff + s0, h->d_wq + cb, h->d_wq + Rtot + cb, ns, b.slots.data(), thr_index, d_score, d_mu,
-                     nullptr, nullptr, nullptr, true, &b.pl, &bf.res));
+                     nullptr, nullptr, nullptr, true, &b.pl, &bf.res, do_prune ? &prune : nullptr));
   CK(h, cudaStreamWaitEvent(h->ahead, h->ev_ahead2, 0));
   CK(h, cudaMemcpyAsync(bf.h_out, bf.d_out, sizeof(double) * total, cudaMemcpyDeviceToHost, h->ahead));
   CK(h, cudaEventRecord(h->blocking_sync ? bf.done_blk : bf.done, h->ahead));
@@ -904,6 +913,7 @@ int batch_absorb(mogp_engine* h, int bi) {
           e.score = hs[v * ns + si];
           e.muthr = hm[v * ns + si];
         }
+        e.pruned = hs[v * ns + si] == -INFINITY;  // (a computed score is finite)
         e.T = b.pl.T + kx_off + (w.col0[b.s0 + v] - cb) * mpad;
         e.mu = b.pl.mu + (int64_t)si * b.pl.Rpad + (w.col0[b.s0 + v] - cb);
         e.ss = b.pl.ss + (int64_t)si * b.pl.Rpad + (w.col0[b.s0 + v] - cb);
@@ -915,6 +925,15 @@ int batch_absorb(mogp_engine* h, int bi) {
     }
     kx_off += b.pl.Rpad * mpad;
   }
+  // accounting: pairs the rule excluded before the product, and the columns (flops) the pass did not compute for them
+  for (int si = 0; si < ns; ++si)
+    for (int64_t v = 0; v < cnt; ++v) {
+      ch.win_pairs += 1;
+      if (hs[v * ns + si] != -INFINITY) continue;
+      ch.win_pruned += 1;
+      const double mm = (double)b.msz[si], ni = (double)(w.col0[b.s0 + v + 1] - w.col0[b.s0 + v]);
+      if (b.prof && h->prof_on) h->prof_flops_c[0] -= (ni - 1.0) * mm * (mm + 10.0);
+    }
   for (int64_t v = 0; v < cnt; ++v) {
     w.new_ll[b.s0 + v] = hn[v];
     if (b.own_slot[v] >= 0 && w.slot_epoch[b.own_slot[v]] == b.own_epoch[v]) {
@@ -974,6 +993,7 @@ int win_replay(mogp_engine* h, int bi) {
       P.x = h->d_wq + w.col0[v];
       P.y = h->d_wq + w.col0[w.n] + w.col0[v];
       P.ncols = (int)(w.col0[v + 1] - w.col0[v]);
+      P.thr = J.thr_index;
     }
     J.out = h->d_alg + (2 + (int64_t)idx) * 2 * OWN_BATCH;
     J.logB = J.logAlpha = nullptr;
@@ -1026,6 +1046,7 @@ void win_store(mogp_engine* h, int64_t v0, const std::vector<int32_t>& slots, co
       Chain::WinEntry& e = w.e[v][slot];
       e.score = host_score[(v - v0) * ns + si];
       e.muthr = host_mu[(v - v0) * ns + si];
+      e.pruned = false;
       e.T = pl.T + kx_off + (w.col0[v] - cbase) * mpad;
       e.mu = pl.mu + (int64_t)si * pl.Rpad + (w.col0[v] - cbase);
       e.ss = pl.ss + (int64_t)si * pl.Rpad + (w.col0[v] - cbase);
@@ -1157,13 +1178,17 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
       const int64_t v = w.cur + 1 + q;
       const Chain::WinEntry& e = w.e[v][slot];
       AlgPos& P = J.pos[q];
-      P.T = e.T;
-      P.ss = e.ss;
-      P.mu = e.mu;
       P.stride = round_up(h->cl[slot].m, TB);
-      P.x = h->d_wq + w.col0[v];
-      P.y = h->d_wq + w.col0[w.n] + w.col0[v];
-      P.ncols = (int)(w.col0[v + 1] - w.col0[v]);
+      const int thr = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
+      // a pair excluded before the product has its threshold column only: the correction re-derives that mean
+      const int64_t skip = e.pruned ? thr : 0;
+      P.T = e.T + skip * P.stride;
+      P.ss = e.ss + skip;
+      P.mu = e.mu + skip;
+      P.x = h->d_wq + w.col0[v] + skip;
+      P.y = h->d_wq + w.col0[w.n] + w.col0[v] + skip;
+      P.ncols = e.pruned ? 1 : (int)(w.col0[v + 1] - w.col0[v]);
+      P.thr = e.pruned ? 0 : thr;
     }
     J.th = make_theta(h->cl[slot]);
     J.thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
@@ -1269,14 +1294,24 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
       ch.win_algebra += 1;
     }
     auto corrected = [&](int32_t slot, const double* out) {  // scores current, T stale, next batch's pass dirty
+      bool reopened = false;
       for (int64_t q = 0; q < npos; ++q) {
         Chain::WinEntry& e = w.e[w.cur + 1 + q][slot];
-        e.score = out[2 * q];
         e.muthr = out[2 * q + 1];
+        if (!e.pruned) {
+          e.score = out[2 * q];
+          continue;
+        }
+        // excluded before the product: only the mean was corrected.  Still excluded -> still -inf; if the move has
+        // brought the mean back within the threshold the pair needs a real score: the slot is re-scored the long way
+        const int64_t pn = w.pat[w.cur + 1 + q];
+        const double yt = h->h_ythr.empty() ? NAN : h->h_ythr[pn];
+        if (!(yt - e.muthr > ch.cfg.threshold)) reopened = true;
       }
       w.slot_T_ok[slot] = 0;
       w.slot_alg[slot] = 1;
       w.slot_epoch[slot] += 1;
+      if (reopened) w.slot_upto[slot] = 0;
       for (int64_t v = w.cur + 1; v < w.end_launched; ++v) {
         const int32_t id = ch.z[w.pat[v]];
         if (id >= 0 && ch.slot_of_id[id] == slot) w.own_ok[v] = 0;
@@ -1308,7 +1343,7 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
           for (int64_t q = 0; q < rem; ++q) {
             const Chain::WinEntry& e = w.e[v0 + q][chk[si]];
             const double s_ref = host[q * nb + si], m_ref = host[rem * nb + q * nb + si];
-            double err = fabs(e.score - s_ref) / std::max(1.0, fabs(s_ref));
+            double err = e.pruned ? 0.0 : fabs(e.score - s_ref) / std::max(1.0, fabs(s_ref));
             if (!(isnan(m_ref) && isnan(e.muthr))) err = std::max(err, fabs(e.muthr - m_ref) / std::max(1.0, fabs(m_ref)));
             if (!(err <= ch.max_corr_err)) ch.max_corr_err = err;  // (NaN sticks)
           }

@@ -112,6 +112,7 @@ struct Chain {
   // active cluster in ONE pass over the factors; a cached score stays valid until its cluster changes ----
   struct WinEntry {
     double score = 0.0, muthr = 0.0;
+    bool pruned = false;         // excluded by the monotonicity rule before the product: only its threshold column has T / ss / mu
     const double* T = nullptr;   // the patient's columns of T = M Kx under that slot (stride = mpad when scored)
     const double* mu = nullptr;  // ... their predictive means
     const double* ss = nullptr;  // ... and their k*^T Ky^-1 k* (device, as mu)
@@ -121,6 +122,8 @@ struct Chain {
     std::vector<int32_t> slots;    // slots the pass scored ...
     std::vector<int64_t> epoch;    // ... their change counters when it was launched ...
     std::vector<int64_t> mpad;     // ... and their padded sizes (layout of T in the pass's scratch)
+    std::vector<int64_t> msz;      // ... and their sizes (accounting of the pruned columns)
+    bool prof = false;             // the pass was launched with profiling on
     std::vector<int32_t> own_slot; // [cnt] slot whose leave-block-out score was launched with the pass (-1: none)
     std::vector<int64_t> own_epoch;
     ScorePlan pl;
@@ -147,6 +150,7 @@ struct Chain {
     int64_t blog_used = 0;         // doubles used in the engine's d_blog
   } win;
   int64_t win_passes = 0, win_rescores = 0, win_patients = 0, win_algebra = 0, win_replayed = 0;  // accounting
+  int64_t win_pairs = 0, win_pruned = 0;   // (patient, cluster) pairs of the window passes / those excluded before the product
   double t_open = 0.0, t_ensure = 0.0, t_commit = 0.0, t_alg = 0.0;
   double max_corr_err = 0.0;     // MOGP_CHECK_CORRECTIONS: worst |rank-n corrected - re-scored| (relative)
   int64_t corr_checked = 0;         // host seconds spent in the three phases of windowed steps
@@ -752,21 +756,28 @@ void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout, const 
 
 template <int NS>
 void launch_score_wide(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotView* d_slots, const SlotPack& pack,
-                       int use_pack, const ChunkPlan& cp) {
+                       int use_pack, const ChunkPlan& cp, const int* colmap = nullptr, const int* ncols = nullptr) {
   const int smem = WideSmem<NS>::BYTES;  // (opted into in mogp_engine_create, per device)
   dim3 grid((unsigned)(pl.Rpad / (8 * NS)), (unsigned)pl.n_slots, (unsigned)(pl.max_nb * cp.maxch));
   prof_mark(h, false);
-  k_score_wide<NS><<<grid, WIDE_THREADS, smem, h->stream>>>(d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout, cp);
+  k_score_wide<NS><<<grid, WIDE_THREADS, smem, h->stream>>>(d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout, cp, colmap,
+                                                            ncols);
   prof_mark(h, true);
   LAUNCHED(h);
 }
 
 // Device-resident query (off_dev[n_pat+1] with off_dev[0] = first column, xs/ys indexed from 0 = that
 // column).  Runs k_kx -> k_score_gemm -> k_score_epi; outputs stay on the device.
+// prune (optional; batch passes of the look-ahead pipeline): apply the monotonicity rule on the device BEFORE the O(m^2)
+// product - pairs it excludes (score -inf) keep only their threshold column in the product (k_prune).
+struct PruneSpec {
+  const double* ythr_dev;  // [n_pat] the raw cells Y[n, index_to_eval] of the query's patients
+  double threshold;
+};
 int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_dev, const double* xs_dev,
                  const double* ys_dev, int32_t n_slots, const int32_t* slots, int32_t thr_index, double* score_dev,
                  double* mu_thr_dev, double* col_mean, double* col_var, double* col_lpd, bool keep_T, ScorePlan* plan_out,
-                 ScoreRes* res_in = nullptr) {
+                 ScoreRes* res_in = nullptr, const PruneSpec* prune = nullptr) {
   ScoreRes& res = res_in ? *res_in : h->res_main;
   h->prof_cls = res.bump ? 1 : 0;
   if (n_slots <= 0 || n_pat <= 0 || R <= 0) return MOGP_OK;
@@ -835,7 +846,11 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   }
   cp.zigzag = cp.kc == 0 ? res.zigzag : 0;
   const int64_t tpart_total = cp.kc > 0 ? pl.kx_total * cp.maxch : 0;
-  const int64_t need = pl.kx_total * (keep_T ? 2 : 1) + pl.part_total + 2 * mu_total + mupart_total + tpart_total;
+  const bool do_prune = prune && thr_index >= 0 && cp.kc == 0 && pl.Rpad == pl.BN && pl.BN >= 24 && n_pat <= PRUNE_MAX_PAT;
+  // colmap[n_slots][Rpad] | ncols[n_slots] (ints) | flag[n_pat * n_slots] (bytes), carved out of the same scratch
+  const int64_t prune_ints = do_prune ? (int64_t)n_slots * pl.Rpad + n_slots : 0;
+  const int64_t prune_total = do_prune ? (prune_ints + 1) / 2 + (n_pat * n_slots + 7) / 8 + 2 : 0;
+  const int64_t need = pl.kx_total * (keep_T ? 2 : 1) + pl.part_total + 2 * mu_total + mupart_total + tpart_total + prune_total;
   if (res.bump) {
     if (res.scr_used + need > res.scr_elems) {  // outgrown: earlier blocks are still referenced by the pipeline
       if (res.scr) res.retired.push_back(res.scr);
@@ -858,6 +873,10 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   pl.T = keep_T ? pl.mupart + mupart_total : nullptr;
   cp.Tpart = cp.kc > 0 ? pl.mupart + mupart_total + (keep_T ? pl.kx_total : 0) : nullptr;
   pl.ss = pl.mupart + mupart_total + (keep_T ? pl.kx_total : 0) + tpart_total;
+  // (pl.ss has mu_total entries and is the second "mu_total" of `need`; the pruning lists come after it)
+  int* d_colmap = do_prune ? reinterpret_cast<int*>(pl.ss + mu_total) : nullptr;
+  int* d_ncols = do_prune ? d_colmap + (int64_t)n_slots * pl.Rpad : nullptr;
+  unsigned char* d_flag = do_prune ? reinterpret_cast<unsigned char*>(pl.ss + mu_total + (prune_ints + 1) / 2 + 1) : nullptr;
   if (!use_pack) {
     CK(h, cudaMemcpyAsync(res.d_slots, hv, sizeof(SlotView) * (size_t)n_slots, cudaMemcpyHostToDevice, h->stream));
     h->bytes_h2d += (int64_t)sizeof(SlotView) * n_slots;
@@ -865,15 +884,21 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   k_kx<<<dim3((unsigned)pl.max_rblk, (unsigned)((pl.Rpad + KX_COLS - 1) / KX_COLS), (unsigned)n_slots), KX_ROWS, 0,
          h->stream>>>(res.d_slots, pack, use_pack, xs_dev, (int)R, (int)pl.Rpad, pl.max_rblk, pl.kxT, pl.mupart);
   LAUNCHED(h);
+  if (do_prune) {
+    k_prune<<<(unsigned)n_slots, 64, 0, h->stream>>>(res.d_slots, pack, use_pack, n_slots, off_dev, (int)n_pat, xs_dev, (int)pl.Rpad,
+                                                     pl.mupart, pl.max_rblk, thr_index, prune->ythr_dev, prune->threshold, d_colmap,
+                                                     d_ncols, d_flag);
+    LAUNCHED(h);
+  }
   switch (pl.BN) {  // <= 16 columns: bound by HBM (8-warp ring); wider: bound by the FP64 tensor pipe (16 warps)
     case 8: launch_score_gemm<8>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
     case 16: launch_score_gemm<16>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
-    case 24: launch_score_wide<3>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
-    case 32: launch_score_wide<4>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
-    case 40: launch_score_wide<5>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
-    case 48: launch_score_wide<6>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
-    case 56: launch_score_wide<7>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
-    default: launch_score_wide<8>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
+    case 24: launch_score_wide<3>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols); break;
+    case 32: launch_score_wide<4>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols); break;
+    case 40: launch_score_wide<5>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols); break;
+    case 48: launch_score_wide<6>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols); break;
+    case 56: launch_score_wide<7>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols); break;
+    default: launch_score_wide<8>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols); break;
   }
   if (cp.kc > 0) {
     k_score_reduce<<<dim3((unsigned)n_slots, (unsigned)pl.max_nb), 256, 0, h->stream>>>(res.d_slots, pack, use_pack, (int)pl.Rpad, cp,
@@ -884,7 +909,7 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   k_score_epi<<<(unsigned)((pairs + 7) / 8), 256, 0, h->stream>>>(res.d_slots, pack, use_pack, n_slots, off_dev, n_pat, xs_dev, ys_dev,
                                                                      (int)pl.Rpad, pl.part, pl.mupart, pl.max_rblk, pl.mu,
                                                                      thr_index, score_dev,
-                                                                     mu_thr_dev, col_mean, col_var, col_lpd, pl.ss);
+                                                                     mu_thr_dev, col_mean, col_var, col_lpd, pl.ss, d_flag);
   LAUNCHED(h);
   CK(h, cudaGetLastError());
   if (plan_out) *plan_out = pl;
@@ -1356,12 +1381,13 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
 int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out) {
   if (!h || !out) return MOGP_EINVAL;
   prof_drain(h);
-  const double v[16] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
+  const double v[18] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
                         h->chain.t_open, h->chain.t_ensure, h->chain.t_commit,
                         (double)h->prof_launches_c[1], h->prof_ms_c[1], h->prof_bytes_c[1], h->prof_flops_c[1],
                         (double)h->chain.win_algebra, h->chain.t_alg, (double)h->chain.win_replayed,
-                        h->chain.max_corr_err, (double)h->chain.corr_checked};
-  for (int i = 0; i < n_out && i < 16; ++i) out[i] = v[i];
+                        h->chain.max_corr_err, (double)h->chain.corr_checked, (double)h->chain.win_pairs,
+                        (double)h->chain.win_pruned};
+  for (int i = 0; i < n_out && i < 18; ++i) out[i] = v[i];
   return MOGP_OK;
 }
 

@@ -253,14 +253,20 @@ struct WideSmem {
   static constexpr int BYTES = S * STAGE * (int)sizeof(double) + 64;  // + full/empty mbarriers of the ring
 };
 
+// cmap (optional, shared memory): the pass computes only ncol columns of this slot, cmap[c'] = the query column behind
+// computed column c' (pairs the monotonicity rule excludes keep their threshold column only, see k_prune).  Column
+// groups of 8 beyond ncol are skipped altogether (no operand loads, no DMMAs); T and the sums of squares land at the
+// query columns' own positions, so everything downstream addresses them as in an unpruned pass.
 template <int NS>
 __device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk, int c0, const double* __restrict__ kxT, int Rpad,
                                           double* __restrict__ part, double* __restrict__ Tout, const ChunkPlan& cp,
-                                          double* smem, double (*red)[8 * NS]) {
+                                          double* smem, double (*red)[8 * NS], const int* cmap, int ncol) {
   constexpr int BN = 8 * NS, MS = 2, WM = 4;
   constexpr int NST = WideSmem<NS>::S, STAGE = WideSmem<NS>::STAGE;
   const int t_begin = chunk * cp.kc;
   if (cp.kc > 0 && t_begin > rb) return;
+  const int nsa = cmap ? (ncol + 7) >> 3 : NS;  // live column groups (uniform over the CTA)
+  if (nsa == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int wm = warp & 3, kg = warp >> 2;  // row group, k group
   const int rbase = wm * 16;
@@ -290,7 +296,17 @@ __device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk,
       if (use > 0) mbar_wait(empty + st, (use - 1) & 1);
       double* sA = smem + st * STAGE;
       load_tile_async<LD_K, TB, WIDE_THREADS>(sA, Mrow + (int64_t)tile * TB, sv.ld);
-      load_tile_async<LD_K, BN, WIDE_THREADS>(sA + TB * LD_K, kx + (int64_t)tile * TB, sv.mpad);
+      if (!cmap) {
+        load_tile_async<LD_K, BN, WIDE_THREADS>(sA + TB * LD_K, kx + (int64_t)tile * TB, sv.mpad);
+      } else {  // the live groups' columns, gathered through the map
+        const double* kxb = kxT + sv.kx_off + (int64_t)(t_begin + tile) * TB;
+#pragma unroll
+        for (int q = 0; q < (BN * TB / 2 + WIDE_THREADS - 1) / WIDE_THREADS; ++q) {
+          const int idx = threadIdx.x + q * WIDE_THREADS;
+          const int r = idx >> 5, c = (idx & 31) << 1;
+          if (r < 8 * nsa) cp_async16(sA + TB * LD_K + r * LD_K + c, kxb + (int64_t)cmap[r] * sv.mpad + c);
+        }
+      }
       cp_async_mbar_arrive(full + st);
     }
   };
@@ -303,7 +319,8 @@ __device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk,
     const int st = tile % NST;
     mbar_wait(full + st, (tile / NST) & 1);
     const double* sA = smem + st * STAGE;
-    warp_mma_k8<MS, NS, TB / 4, LD_K>(acc, sA + kg * (TB / 4), sA + TB * LD_K + kg * (TB / 4), rbase, 0);
+    if (nsa == NS) warp_mma_k8<MS, NS, TB / 4, LD_K>(acc, sA + kg * (TB / 4), sA + TB * LD_K + kg * (TB / 4), rbase, 0);
+    else warp_mma_k8_part<MS, NS, TB / 4, LD_K>(acc, sA + kg * (TB / 4), sA + TB * LD_K + kg * (TB / 4), rbase, nsa);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + st);
   }
@@ -315,6 +332,7 @@ __device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk,
     for (int i = 0; i < MS; ++i)
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
+        if (j >= nsa) continue;
         const int r = rbase + 8 * i + g, c = 8 * j + 2 * t;
         *reinterpret_cast<double2*>(o + r * LDP + c) = make_double2(acc.v[i][j][0], acc.v[i][j][1]);
       }
@@ -328,6 +346,7 @@ __device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk,
       for (int i = 0; i < MS; ++i)
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
+          if (j >= nsa) continue;
           const int r = rbase + 8 * i + g, c = 8 * j + 2 * t;
           const double2 v = *reinterpret_cast<const double2*>(o + r * LDP + c);
           acc.v[i][j][0] += v.x;
@@ -350,13 +369,20 @@ __device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk,
       for (int i = 0; i < MS; ++i)
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-          const int r = rb * TB + rbase + 8 * i + g, c = c0 + 8 * j + 2 * t;
-          o[(int64_t)c * sv.mpad + r] = acc.v[i][j][0];
-          o[(int64_t)(c + 1) * sv.mpad + r] = acc.v[i][j][1];
+          if (j >= nsa) continue;
+          const int r = rb * TB + rbase + 8 * i + g, cl = 8 * j + 2 * t;
+          if (!cmap) {
+            o[(int64_t)(c0 + cl) * sv.mpad + r] = acc.v[i][j][0];
+            o[(int64_t)(c0 + cl + 1) * sv.mpad + r] = acc.v[i][j][1];
+          } else {
+            if (cl < ncol) o[(int64_t)cmap[cl] * sv.mpad + r] = acc.v[i][j][0];
+            if (cl + 1 < ncol) o[(int64_t)cmap[cl + 1] * sv.mpad + r] = acc.v[i][j][1];
+          }
         }
     }
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
+      if (j >= nsa) continue;
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll
       for (int i = 0; i < MS; ++i) {
@@ -376,28 +402,82 @@ __device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk,
   }
   if (cp.kc > 0) return;
   __syncthreads();
-  if (threadIdx.x < BN) {
+  if ((int)threadIdx.x < (cmap ? ncol : BN)) {
     double s = 0.0;
 #pragma unroll
     for (int q = 0; q < WM; ++q) s += red[q][threadIdx.x];
-    part[sv.part_off + (int64_t)rb * Rpad + c0 + threadIdx.x] = s;
+    part[sv.part_off + (int64_t)rb * Rpad + (cmap ? cmap[threadIdx.x] : c0 + (int)threadIdx.x)] = s;
   }
 }
 
+// colmap / ncols (optional, one column tile only): per-slot lists of the columns to compute, see k_prune.
 template <int NS>
 __global__ void __launch_bounds__(WIDE_THREADS, 1) k_score_wide(SLOT_ARGS, const double* __restrict__ kxT, int Rpad,
                                                                double* __restrict__ part, double* __restrict__ Tout,
-                                                               const ChunkPlan cp) {
+                                                               const ChunkPlan cp, const int* __restrict__ colmap,
+                                                               const int* __restrict__ ncols) {
   constexpr int BN = 8 * NS;
   extern __shared__ __align__(16) double smem[];
   __shared__ double red[4][BN];
+  __shared__ int s_cmap[BN];
   const SlotView sv = SLOT_AT(blockIdx.y);
   const int nb = sv.mpad / TB;
   const int zi = cp.kc > 0 ? (int)blockIdx.z / cp.maxch : (int)blockIdx.z;
   const int chunk = cp.kc > 0 ? (int)blockIdx.z % cp.maxch : 0;
   if (zi >= nb) return;
   const int rb = cp.zigzag ? ((zi & 1) ? (zi >> 1) : nb - 1 - (zi >> 1)) : nb - 1 - zi;  // heavy row blocks first, across the slots
-  wide_item<NS>(sv, rb, chunk, blockIdx.x * BN, kxT, Rpad, part, Tout, cp, smem, red);
+  int ncol = BN;
+  if (colmap) {
+    if (threadIdx.x < BN) s_cmap[threadIdx.x] = colmap[(int64_t)blockIdx.y * Rpad + threadIdx.x];
+    ncol = ncols[blockIdx.y];
+    __syncthreads();
+  }
+  wide_item<NS>(sv, rb, chunk, blockIdx.x * BN, kxT, Rpad, part, Tout, cp, smem, red, colmap ? s_cmap : nullptr, ncol);
+}
+
+// The monotonicity rule (mogp_constrained.py:254-266) needs only the predictive MEAN at the patient's first real visit:
+// a pair with Y[n, idx] - mean > threshold gets probability 0 and the reference never calls calc_score for it.  The mean
+// is O(m) per visit from k_kx's partial sums, the score O(m^2).  So before the O(m^2) product of a batch pass, one CTA
+// per slot decides which (patient, slot) pairs are excluded - from exactly the sums the epilogue will add up, in the
+// same order, so both agree bit for bit - and lists the columns the product has to compute for that slot: every column
+// of the patients still in the race, and the threshold column alone of the excluded ones (its T, sum of squares and
+// mean are what the rank-n corrections of a later move need to re-derive that mean).
+constexpr int PRUNE_MAX_PAT = 64;
+__global__ void __launch_bounds__(64) k_prune(SLOT_ARGS, int n_slots, const int64_t* __restrict__ off, int n_pat,
+                                              const double* __restrict__ xs, int Rpad, const double* __restrict__ mupart,
+                                              int max_rblk, int thr_index, const double* __restrict__ ythr, double threshold,
+                                              int* __restrict__ colmap, int* __restrict__ ncols,
+                                              unsigned char* __restrict__ flag) {
+  const int c = blockIdx.x, p = threadIdx.x;
+  const SlotView sv = SLOT_AT(c);
+  const int nrb = (sv.mpad + KX_ROWS - 1) / KX_ROWS;
+  __shared__ unsigned char sflag[PRUNE_MAX_PAT];
+  if (p < n_pat) {
+    const int64_t c0 = off[p] - off[0], c1 = off[p + 1] - off[0];
+    unsigned char f = 0;
+    if (thr_index >= 0 && c0 + thr_index < c1) {
+      const int64_t col = c0 + thr_index;
+      double m = 0.0;
+      for (int rb = 0; rb < nrb; ++rb) m += mupart[((int64_t)c * max_rblk + rb) * Rpad + col];
+      if (sv.th.mean_func) m += xs[col] * (-sv.th.A);
+      f = (ythr[p] - m > threshold) ? 1 : 0;
+    }
+    sflag[p] = f;
+    flag[(int64_t)p * n_slots + c] = f;
+  }
+  __syncthreads();
+  if (p == 0) {
+    int k = 0;
+    int* cm = colmap + (int64_t)c * Rpad;
+    for (int q = 0; q < n_pat; ++q) {
+      const int c0 = (int)(off[q] - off[0]), c1 = (int)(off[q + 1] - off[0]);
+      for (int col = c0; col < c1; ++col)
+        if (!sflag[q] || col == c0 + thr_index) cm[k++] = col;
+    }
+    ncols[c] = k;
+    const int fill = k > 0 ? cm[0] : 0;
+    for (; k < Rpad; ++k) cm[k] = fill;
+  }
 }
 
 // ---- patient table from the NaN-padded N x T matrices (mogp_constrained.py:246-247) -------------------------------
@@ -463,10 +543,12 @@ __global__ void __launch_bounds__(256) k_score_epi(SLOT_ARGS, int n_slots,
                                                    double* __restrict__ mu, int thr_index,
                                                    double* __restrict__ score, double* __restrict__ mu_thr,
                                                    double* __restrict__ col_mean, double* __restrict__ col_var,
-                                                   double* __restrict__ col_lpd, double* __restrict__ col_ss) {
+                                                   double* __restrict__ col_lpd, double* __restrict__ col_ss,
+                                                   const unsigned char* __restrict__ pruned) {
   const int64_t gid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (gid >= n_pat * n_slots) return;
+  const bool excl = pruned && pruned[gid];  // excluded by the monotonicity rule: only its threshold column was computed
   const int64_t p = gid / n_slots;
   const int c = (int)(gid % n_slots);
   const SlotView sv = SLOT_AT(c);
@@ -475,6 +557,7 @@ __global__ void __launch_bounds__(256) k_score_epi(SLOT_ARGS, int n_slots,
   const int64_t c0 = off[p] - off[0], c1 = off[p + 1] - off[0];
   double total = 0.0;
   for (int64_t col = c0 + lane; col < c1; col += 32) {
+    if (excl && col != c0 + thr_index) continue;
     double ss = 0.0;
     for (int rb = 0; rb < nb; ++rb) ss += part[sv.part_off + (int64_t)rb * Rpad + col];
     double v = kern_diag(sv.th, xs[col]) - ss;
@@ -496,7 +579,7 @@ __global__ void __launch_bounds__(256) k_score_epi(SLOT_ARGS, int n_slots,
 #pragma unroll
   for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
   if (lane == 0) {
-    if (score) score[gid] = total;
+    if (score) score[gid] = excl ? -INFINITY : total;
     if (mu_thr && !(thr_index >= 0 && c0 + thr_index < c1)) mu_thr[gid] = nan("");
   }
 }

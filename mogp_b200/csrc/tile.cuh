@@ -164,6 +164,33 @@ __device__ __forceinline__ void warp_mma_k8(Acc<MS, NS>& acc, const double* __re
   }
 }
 
+// The same with only the first `nsa` of the NS column groups live (uniform over the warp): the others cost neither
+// fragment loads nor DMMAs.  Column base 0.
+template <int MS, int NS, int KDIM, int LD>
+__device__ __forceinline__ void warp_mma_k8_part(Acc<MS, NS>& acc, const double* __restrict__ sA, const double* __restrict__ sB,
+                                                 int rb, int nsa) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kb = 0; kb < KDIM; kb += 8) {
+    double2 a[MS], b[NS];
+#pragma unroll
+    for (int i = 0; i < MS; ++i) a[i] = *reinterpret_cast<const double2*>(sA + (rb + 8 * i + g) * LD + kb + 2 * t);
+#pragma unroll
+    for (int j = 0; j < NS; ++j)
+      if (j < nsa) b[j] = *reinterpret_cast<const double2*>(sB + (8 * j + g) * LD + kb + 2 * t);
+#pragma unroll
+    for (int i = 0; i < MS; ++i)
+#pragma unroll
+      for (int j = 0; j < NS; ++j)
+        if (j < nsa) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+    for (int i = 0; i < MS; ++i)
+#pragma unroll
+      for (int j = 0; j < NS; ++j)
+        if (j < nsa) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i].y, b[j].y);
+  }
+}
+
 // The standard 64x64 CTA tile: 8 warps as 4 (rows) x 2 (cols), each warp 16 x 32.
 using Acc64 = Acc<2, 4>;
 __device__ __forceinline__ int warp_rb64() { return ((threadIdx.x >> 5) >> 1) * 16; }

@@ -203,6 +203,7 @@ struct AlgPos {
   int64_t stride;
   const double *x, *y;        // its visits
   int ncols;
+  int thr;                    // which of those columns is the threshold visit (-1: none)
 };
 struct AlgJobs {
   AlgPos pos[OWN_BATCH];
@@ -241,7 +242,7 @@ __device__ __forceinline__ void alg_finish(const AlgJobs& J, const AlgPos& P, co
     for (int o = 16; o; o >>= 1)
       for (int i = 0; i < o; ++i) tr[i] += tr[i + o];
     J.out[2 * blockIdx.x] = tr[0];
-    J.out[2 * blockIdx.x + 1] = (J.thr_index >= 0 && J.thr_index < P.ncols) ? mun[J.thr_index] : nan("");
+    J.out[2 * blockIdx.x + 1] = (P.thr >= 0 && P.thr < P.ncols) ? mun[P.thr] : nan("");
   }
 }
 
