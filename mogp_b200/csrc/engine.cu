@@ -1929,9 +1929,21 @@ int mogp_score_pairs(mogp_engine* h, int64_t n_patients, const int64_t* off, con
     }
     TRY(stage_query(h, np, off + p0, x, y, nullptr));
     const int64_t pairs = np * n_slots;
-    TRY(ensure(h, &h->d_out, &h->out_elems, 2 * pairs));
+    TRY(ensure(h, &h->d_out, &h->out_elems, 2 * pairs + np));
+    // MOGP_PROBE_PRUNE=k (diagnostic, timing probes of the pruned product on its own): every k-th patient is treated as
+    // excluded by the monotonicity rule under every cluster (its score comes back -inf)
+    static const int probe = getenv("MOGP_PROBE_PRUNE") ? atoi(getenv("MOGP_PROBE_PRUNE")) : 0;
+    PruneSpec ps{h->d_out + 2 * pairs, 0.0};
+    if (probe > 0 && thr_index >= 0) {
+      char* up = nullptr;
+      TRY(stage_alloc(h, sizeof(double) * np, &up));
+      double* yt = reinterpret_cast<double*>(up);
+      for (int64_t q = 0; q < np; ++q) yt[q] = (q % probe == 0) ? 1e300 : -1e300;
+      CK(h, cudaMemcpyAsync(h->d_out + 2 * pairs, yt, sizeof(double) * np, cudaMemcpyHostToDevice, h->stream));
+    }
     TRY(score_device(h, np, R, h->d_qoff, h->d_q, h->d_q + R, n_slots, slots, thr_index, h->d_out,
-                     mu_thr ? h->d_out + pairs : nullptr, nullptr, nullptr, nullptr, false, nullptr));
+                     mu_thr ? h->d_out + pairs : nullptr, nullptr, nullptr, nullptr, false, nullptr, nullptr,
+                     (probe > 0 && thr_index >= 0) ? &ps : nullptr));
     TRY(copy_back(h, score + p0 * n_slots, h->d_out, pairs));
     if (mu_thr) TRY(copy_back(h, mu_thr + p0 * n_slots, h->d_out + pairs, pairs));
     p0 = p1;

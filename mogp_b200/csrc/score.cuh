@@ -319,8 +319,7 @@ __device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk,
     const int st = tile % NST;
     mbar_wait(full + st, (tile / NST) & 1);
     const double* sA = smem + st * STAGE;
-    if (nsa == NS) warp_mma_k8<MS, NS, TB / 4, LD_K>(acc, sA + kg * (TB / 4), sA + TB * LD_K + kg * (TB / 4), rbase, 0);
-    else warp_mma_k8_part<MS, NS, TB / 4, LD_K>(acc, sA + kg * (TB / 4), sA + TB * LD_K + kg * (TB / 4), rbase, nsa);
+    warp_mma_k8_first<MS, NS, TB / 4, LD_K>(acc, sA + kg * (TB / 4), sA + TB * LD_K + kg * (TB / 4), rbase, nsa);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + st);
   }

@@ -164,30 +164,42 @@ __device__ __forceinline__ void warp_mma_k8(Acc<MS, NS>& acc, const double* __re
   }
 }
 
-// The same with only the first `nsa` of the NS column groups live (uniform over the warp): the others cost neither
-// fragment loads nor DMMAs.  Column base 0.
-template <int MS, int NS, int KDIM, int LD>
-__device__ __forceinline__ void warp_mma_k8_part(Acc<MS, NS>& acc, const double* __restrict__ sA, const double* __restrict__ sB,
-                                                 int rb, int nsa) {
+// The same with only the first NA (compile time) of the NS column groups live: the others cost neither fragment loads
+// nor DMMAs.  Column base 0.  warp_mma_k8_first dispatches a run-time count (uniform over the warp) to these
+// straight-line bodies - per-instruction predicates around the DMMAs cost more issue slots than the skipped work saves.
+template <int MS, int NS, int NA, int KDIM, int LD>
+__device__ __forceinline__ void warp_mma_k8_na(Acc<MS, NS>& acc, const double* __restrict__ sA, const double* __restrict__ sB,
+                                               int rb) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int kb = 0; kb < KDIM; kb += 8) {
-    double2 a[MS], b[NS];
+    double2 a[MS], b[NA];
 #pragma unroll
     for (int i = 0; i < MS; ++i) a[i] = *reinterpret_cast<const double2*>(sA + (rb + 8 * i + g) * LD + kb + 2 * t);
 #pragma unroll
-    for (int j = 0; j < NS; ++j)
-      if (j < nsa) b[j] = *reinterpret_cast<const double2*>(sB + (8 * j + g) * LD + kb + 2 * t);
+    for (int j = 0; j < NA; ++j) b[j] = *reinterpret_cast<const double2*>(sB + (8 * j + g) * LD + kb + 2 * t);
 #pragma unroll
     for (int i = 0; i < MS; ++i)
 #pragma unroll
-      for (int j = 0; j < NS; ++j)
-        if (j < nsa) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i].x, b[j].x);
+      for (int j = 0; j < NA; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i].x, b[j].x);
 #pragma unroll
     for (int i = 0; i < MS; ++i)
 #pragma unroll
-      for (int j = 0; j < NS; ++j)
-        if (j < nsa) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i].y, b[j].y);
+      for (int j = 0; j < NA; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i].y, b[j].y);
+  }
+}
+template <int MS, int NS, int KDIM, int LD>
+__device__ __forceinline__ void warp_mma_k8_first(Acc<MS, NS>& acc, const double* __restrict__ sA, const double* __restrict__ sB,
+                                                  int rb, int nsa) {
+  switch (nsa) {
+    case 1: warp_mma_k8_na<MS, NS, 1, KDIM, LD>(acc, sA, sB, rb); break;
+    case 2: if constexpr (NS >= 2) warp_mma_k8_na<MS, NS, 2, KDIM, LD>(acc, sA, sB, rb); break;
+    case 3: if constexpr (NS >= 3) warp_mma_k8_na<MS, NS, 3, KDIM, LD>(acc, sA, sB, rb); break;
+    case 4: if constexpr (NS >= 4) warp_mma_k8_na<MS, NS, 4, KDIM, LD>(acc, sA, sB, rb); break;
+    case 5: if constexpr (NS >= 5) warp_mma_k8_na<MS, NS, 5, KDIM, LD>(acc, sA, sB, rb); break;
+    case 6: if constexpr (NS >= 6) warp_mma_k8_na<MS, NS, 6, KDIM, LD>(acc, sA, sB, rb); break;
+    case 7: if constexpr (NS >= 7) warp_mma_k8_na<MS, NS, 7, KDIM, LD>(acc, sA, sB, rb); break;
+    default: if constexpr (NS >= 8) warp_mma_k8_na<MS, NS, 8, KDIM, LD>(acc, sA, sB, rb); break;
   }
 }
 
