@@ -2,6 +2,11 @@
 // (mogp/mogp_constrained.py:231-284 + mogp/allocmodel.py:22-34).  Included by engine.cu.
 namespace {
 
+int env_int_once(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 // ---- buffer pool: clusters own one buffer of cap*cap + 4*cap + 16 doubles; row deletions ping-pong ----
 int pool_get(mogp_engine* h, int64_t cap, double** out) {
   for (size_t i = 0; i < h->pool.size(); ++i)
@@ -216,6 +221,21 @@ int remove_core(mogp_engine* h, Cluster& c, int64_t p, int n) {
   TRY(pool_get(h, c.cap, &nbuf));
   double* nM = nbuf;
   double* nvec = nbuf + c.cap * c.cap;
+  static const int legacy = env_int_once("MOGP_RM_LEGACY", 0);  // 1: the three-pass deletion (hpart / hscan / apply)
+  if (!legacy) {
+    // one pass over the factor: strip walk with the prefix carried along (k_rm_strip), alpha / x / y / stat in its epilogue
+    k_rm_strip<<<g.nbn, NTHREADS, RM_STRIP_SMEM, h->stream>>>(c.M, nM, g, w, c.vec, nvec, c.cap);
+    LAUNCHED(h);
+    if (h->stream == h->side) h->pending_release.emplace_back(c.cap, c.M);  // reusable once the main stream has joined
+    else pool_put(h, c.cap, c.M);
+    c.M = nM;
+    c.vec = nvec;
+    c.m = g.mnew;
+    c.hx.erase(c.hx.begin() + p, c.hx.begin() + p + n);
+    c.hy.erase(c.hy.begin() + p, c.hy.begin() + p + n);
+    CK(h, cudaGetLastError());
+    return mark_updated(h, c, true);
+  }
   double* P = w.S + (int64_t)nT * TB * TB;
   double* H = P + (int64_t)nT * g.nbn * (NP * TB);
   k_rm_hpart<<<dim3(g.nbn, nT), NTHREADS, 0, h->stream>>>(c.M, g, w, P);

@@ -558,6 +558,125 @@ __global__ void __launch_bounds__(NTHREADS) k_rm_apply(const double* __restrict_
   });
 }
 
+// The deletion in ONE pass over the factor (replaces k_rm_hpart + k_rm_hscan + k_rm_apply + k_rm_vec + k_rm_alpha): one CTA
+// per 64-column strip J walks down the row tiles I = max(J, I0) .. nbn-1 with the prefix h (n x 64) carried along:
+//     new tile = diag(u) (old - [S_I | G_I] [old ; H]),   then   H += B_I^T old
+// (both products on the FP64 tensor pipe), the next row tile's operands already in flight (cp.async double buffer; the
+// sources are shifted by the deleted block, so the old tile is gathered in 8-byte pieces).  Every element of M is read
+// once and written once.  The rows above the block are a plain copy (same CTA, before the walk).  After the last tile H
+// is W_{B, strip}: alpha of the result in closed form, alpha'_j = alpha_j - W_{B,j} . (W_BB^-1 alpha_B), and x, y of the
+// strip move to their new places.
+constexpr int LD_BT = 20;  // smem ld of the [64][NP] block rows of the second product
+struct RmStripStage {      // one row tile's operands in shared memory
+  double sB[(TB + NP) * LD_R];   // old tile (rows 0..63) ; H (rows 64..64+NP)
+  double sA[TB * LD_W];          // S (cols 0..63) | G (cols 64..64+NP)
+  double sBt[TB * LD_BT];        // b rows of the tile: [k][a]
+  double su[TB];
+};
+constexpr int RM_STRIP_SMEM = 2 * (int)sizeof(RmStripStage);
+
+__global__ void __launch_bounds__(NTHREADS) k_rm_strip(const double* __restrict__ Mo, double* __restrict__ Mn, RmGeom g, RmWork w,
+                                                       const double* __restrict__ vec_old, double* __restrict__ vec_new,
+                                                       int64_t cap) {
+  extern __shared__ __align__(16) unsigned char rm_smem_raw[];
+  RmStripStage* st = reinterpret_cast<RmStripStage*>(rm_smem_raw);
+  __shared__ double sH[NP][TB];  // the prefix carried down the strip
+  const int J = blockIdx.x, tid = threadIdx.x;
+  const int64_t ld = g.ld;
+  // rows above the deleted block: neither rows nor columns move (j <= i < p)
+  for (int I = J; I < g.I0; ++I)
+    for (int idx = tid; idx < TB * TB / 2; idx += NTHREADS) {
+      const int r = idx >> 5, c = (idx & 31) << 1;
+      const int64_t o = (int64_t)(I * TB + r) * ld + J * TB + c;
+      double2 v = *reinterpret_cast<const double2*>(Mo + o);
+      if (I == J) {  // (tiles above the diagonal hold nothing; inside the diagonal tile the upper part is kept at zero)
+        if (c > r) v.x = 0.0;
+        if (c + 1 > r) v.y = 0.0;
+      }
+      *reinterpret_cast<double2*>(Mn + o) = v;
+    }
+  const int Ifirst = max(J, g.I0);
+  // carriers: rows p..p+n-1 of the block's own columns contribute b_k[q] M[k, j] to every prefix
+  for (int idx = tid; idx < NP * TB; idx += NTHREADS) {
+    const int q = idx >> 6, c = idx & 63, jp = J * TB + c;
+    double run = 0.0;
+    if (q < g.n && jp < g.mnew) {
+      const int j = jp < g.p ? jp : jp + g.n;
+      for (int a = q; a < g.n; ++a)
+        if (j <= g.p + a) run += Mo[(int64_t)(g.p + a) * ld + g.p + q] * Mo[(int64_t)(g.p + a) * ld + j];
+    }
+    sH[q][c] = run;
+  }
+  auto issue = [&](int I, RmStripStage& S) {  // operands of row tile I (cp.async; constants stored directly)
+    const int bx = I - g.I0;
+    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+      const int r = idx >> 6, c = idx & 63, ip = I * TB + r, jp = J * TB + c;
+      double* dst = S.sB + r * LD_R + c;
+      if (ip >= g.mnew || jp >= g.mnew) {
+        *dst = (ip == jp) ? 1.0 : 0.0;
+      } else {
+        const int i = ip < g.p ? ip : ip + g.n, j = jp < g.p ? jp : jp + g.n;
+        if (j > i) *dst = 0.0;
+        else cp_async8(dst, Mo + (int64_t)i * ld + j);
+      }
+    }
+    const double* Ss = w.S + (int64_t)bx * (TB * TB);
+    for (int idx = tid; idx < TB * TB / 2; idx += NTHREADS) {
+      const int r = idx >> 5, c = (idx & 31) << 1;
+      cp_async16(S.sA + r * LD_W + c, Ss + r * TB + c);
+    }
+    for (int idx = tid; idx < TB * NP / 2; idx += NTHREADS) {
+      const int r = idx / (NP / 2), a = (idx % (NP / 2)) * 2;
+      cp_async16(S.sA + r * LD_W + TB + a, w.Gt + ((int64_t)bx * TB + r) * NP + a);
+      cp_async16(S.sBt + r * LD_BT + a, w.Bt + ((int64_t)bx * TB + r) * NP + a);
+    }
+    if (tid < TB / 2) cp_async16(S.su + 2 * tid, w.u + (int64_t)bx * TB + 2 * tid);
+  };
+  const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  if (Ifirst < g.nbn) issue(Ifirst, st[0]);
+  cp_async_commit();
+  int cur = 0;
+  for (int I = Ifirst; I < g.nbn; ++I, cur ^= 1) {
+    RmStripStage& S = st[cur];
+    if (I + 1 < g.nbn) issue(I + 1, st[cur ^ 1]);
+    cp_async_commit();
+    cp_async_wait<1>();  // this thread's copies of tile I have landed ...
+    for (int idx = tid; idx < NP * TB; idx += NTHREADS) S.sB[(TB + (idx >> 6)) * LD_R + (idx & 63)] = sH[idx >> 6][idx & 63];
+    __syncthreads();     // ... everybody's have, and H is in place
+    Acc64 acc;
+    acc.zero();
+    warp_mma<2, 4, true, false, TB + NP, LD_W, LD_R>(acc, S.sA, S.sB, warp_rb64(), warp_cb64());
+    for_each_acc64(acc, [&](int r, int c, double& v) {
+      Mn[(int64_t)(I * TB + r) * ld + J * TB + c] = S.su[r] * (S.sB[r * LD_R + c] - v);
+    });
+    // H += B_I^T old: 16 x 64, warp w owns columns [8w, 8w + 8)
+    Acc<2, 1> hp;
+    hp.zero();
+    warp_mma<2, 1, false, false, TB, LD_BT, LD_R>(hp, S.sBt, S.sB, 0, warp * 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int q = 8 * i + gq, c = warp * 8 + 2 * tq;
+      sH[q][c] += hp.v[i][0][0];
+      sH[q][c + 1] += hp.v[i][0][1];
+    }
+    __syncthreads();  // the stage may be refilled, H is complete for the next tile
+  }
+  cp_async_wait<0>();
+  // closed-form alpha of the result and the strip's share of x, y  (vec = x | y | alpha | z, `cap` doubles each)
+  if (tid < TB) {
+    const int jp = J * TB + tid;
+    if (jp < g.mnew) {
+      const int j = jp < g.p ? jp : jp + g.n;
+      double sdot = 0.0;
+      for (int a = 0; a < g.n; ++a) sdot += sH[a][tid] * w.gsol[a];
+      vec_new[jp] = vec_old[j];
+      vec_new[cap + jp] = vec_old[cap + j];
+      vec_new[2 * cap + jp] = vec_old[2 * cap + j] - sdot;
+    }
+  }
+  if (J == 0 && tid < 32) vec_new[4 * cap + tid] = vec_old[4 * cap + tid];  // the stat block travels with the buffer
+}
+
 // x, y of the result (new order = old order with the block dropped).
 __global__ void k_rm_vec(const double* __restrict__ xo, const double* __restrict__ yo, double* __restrict__ xn,
                          double* __restrict__ yn, RmGeom g) {
@@ -685,27 +804,39 @@ __global__ void __launch_bounds__(256) k_append_small(const double* __restrict__
 }
 
 // part[s][i][j] = sum over row blocks kb = J + s, J + s + KS, ... of (Li T^T)[i][kb-block] * M[kb-block][J-block].
-constexpr int AP_ROWS_SMEM = (TB * LD_R + NP * LD_C + NP * LD_C) * (int)sizeof(double);
+// The tiles of M (one read of the factor in all) and the matching slices of T stream through a two-stage cp.async
+// ring: the next row block is in flight while the current one is multiplied.
+constexpr int AP_STAGE = TB * LD_R + NP * LD_C;  // doubles per stage: M tile [k][c] | raw T slice [q][k]
+constexpr int AP_ROWS_SMEM = (2 * AP_STAGE + NP * LD_C) * (int)sizeof(double);
 __global__ void __launch_bounds__(NTHREADS) k_append_rows(const double* __restrict__ M, int64_t ld, int nb, int mpad,
                                                           const double* __restrict__ T, int n, ApWork w) {
   extern __shared__ __align__(16) double smem[];
-  double* sT = smem;               // M tile [k][c], LD_R
-  double* sC = sT + TB * LD_R;     // (Li T^T) tile [i][k], LD_C
-  double* sR = sC + NP * LD_C;     // raw T tile [q][k], LD_C
+  double* sC = smem + 2 * AP_STAGE;  // (Li T^T) tile [i][k], LD_C
   __shared__ double sLi[NP][NP + 1];
   const int J = blockIdx.x, s = blockIdx.y;
   if (threadIdx.x < NP * NP) sLi[threadIdx.x / NP][threadIdx.x % NP] = w.Li[threadIdx.x];
   Acc<2, 1> acc;
   acc.zero();
   const int warp = threadIdx.x >> 5;
-  for (int kb = J + s; kb < nb; kb += APPEND_KS) {
-    __syncthreads();
-    load_tile<LD_R>(sT, M + (int64_t)kb * TB * ld + (int64_t)J * TB, ld);
-    for (int idx = threadIdx.x; idx < NP * TB; idx += NTHREADS) {
-      int q = idx >> 6, k = idx & 63;
-      sR[q * LD_C + k] = q < n ? T[(int64_t)q * mpad + kb * TB + k] : 0.0;
+  auto issue = [&](int kb, int stage) {
+    double* sT = smem + stage * AP_STAGE;
+    double* sR = sT + TB * LD_R;
+    load_tile_async<LD_R>(sT, M + (int64_t)kb * TB * ld + (int64_t)J * TB, ld);
+    for (int idx = threadIdx.x; idx < NP * TB / 2; idx += NTHREADS) {
+      const int q = idx >> 5, k = (idx & 31) << 1;
+      if (q < n) cp_async16(sR + q * LD_C + k, T + (int64_t)q * mpad + kb * TB + k);
     }
-    __syncthreads();
+  };
+  int stage = 0;
+  if (J + s < nb) issue(J + s, 0);
+  cp_async_commit();
+  for (int kb = J + s; kb < nb; kb += APPEND_KS, stage ^= 1) {
+    cp_async_wait<0>();
+    __syncthreads();  // this row block has landed for everybody; the other stage and sC are free
+    if (kb + APPEND_KS < nb) issue(kb + APPEND_KS, stage ^ 1);
+    cp_async_commit();
+    const double* sT = smem + stage * AP_STAGE;
+    const double* sR = sT + TB * LD_R;
     for (int idx = threadIdx.x; idx < NP * TB; idx += NTHREADS) {
       int i = idx >> 6, k = idx & 63;
       double v = 0.0;
@@ -715,6 +846,7 @@ __global__ void __launch_bounds__(NTHREADS) k_append_rows(const double* __restri
     __syncthreads();
     warp_mma<2, 1, true, false>(acc, sC, sT, 0, warp * 8);
   }
+  cp_async_wait<0>();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -759,6 +891,7 @@ __global__ void k_append_finalize(double* __restrict__ M, int64_t ld, int m, int
 inline void update_set_attributes() {
   cudaFuncSetAttribute(k_rm_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_PREP_SMEM);
   cudaFuncSetAttribute(k_rm_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_APPLY_SMEM);
+  cudaFuncSetAttribute(k_rm_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_STRIP_SMEM);
   cudaFuncSetAttribute(k_append_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_ROWS_SMEM);
 }
 
