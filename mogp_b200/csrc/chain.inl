@@ -224,7 +224,7 @@ int remove_core(mogp_engine* h, Cluster& c, int64_t p, int n) {
   static const int legacy = env_int_once("MOGP_RM_LEGACY", 0);  // 1: the three-pass deletion (hpart / hscan / apply)
   if (!legacy) {
     // one pass over the factor: strip walk with the prefix carried along (k_rm_strip), alpha / x / y / stat in its epilogue
-    k_rm_strip<<<g.nbn, NTHREADS, RM_STRIP_SMEM, h->stream>>>(c.M, nM, g, w, c.vec, nvec, c.cap);
+    k_rm_strip<<<g.nbn * (TB / RM_SW), NTHREADS, RM_STRIP_SMEM, h->stream>>>(c.M, nM, g, w, c.vec, nvec, c.cap);
     LAUNCHED(h);
     if (h->stream == h->side) h->pending_release.emplace_back(c.cap, c.M);  // reusable once the main stream has joined
     else pool_put(h, c.cap, c.M);

@@ -566,9 +566,14 @@ __global__ void __launch_bounds__(NTHREADS) k_rm_apply(const double* __restrict_
 // once and written once.  The rows above the block are a plain copy (same CTA, before the walk).  After the last tile H
 // is W_{B, strip}: alpha of the result in closed form, alpha'_j = alpha_j - W_{B,j} . (W_BB^-1 alpha_B), and x, y of the
 // strip move to their new places.
+// Strips are RM_SW = 16 columns wide: the walk of a strip is a chain of dependent row tiles (each needs the prefix of
+// the one above), its length - not the traffic - is what a waiting re-scoring pass sees, and a narrow strip makes every
+// link short (64 x 80 x 16 products) while 4 nb strips keep every SM busy.
 constexpr int LD_BT = 20;  // smem ld of the [64][NP] block rows of the second product
+constexpr int RM_SW = 16;  // strip width
+constexpr int LD_SW = 20;  // smem ld of the strip's [64 + NP][RM_SW] operand (4 mod 16: conflict-free fragment loads)
 struct RmStripStage {      // one row tile's operands in shared memory
-  double sB[(TB + NP) * LD_R];   // old tile (rows 0..63) ; H (rows 64..64+NP)
+  double sB[(TB + NP) * LD_SW];  // old tile slice (rows 0..63) ; H (rows 64..64+NP)
   double sA[TB * LD_W];          // S (cols 0..63) | G (cols 64..64+NP)
   double sBt[TB * LD_BT];        // b rows of the tile: [k][a]
   double su[TB];
@@ -580,25 +585,25 @@ __global__ void __launch_bounds__(NTHREADS) k_rm_strip(const double* __restrict_
                                                        int64_t cap) {
   extern __shared__ __align__(16) unsigned char rm_smem_raw[];
   RmStripStage* st = reinterpret_cast<RmStripStage*>(rm_smem_raw);
-  __shared__ double sH[NP][TB];  // the prefix carried down the strip
-  const int J = blockIdx.x, tid = threadIdx.x;
+  __shared__ double sH[NP][RM_SW];  // the prefix carried down the strip
+  const int strip = blockIdx.x, tid = threadIdx.x;
+  const int col0 = strip * RM_SW, J = col0 / TB;  // first column, block column
   const int64_t ld = g.ld;
   // rows above the deleted block: neither rows nor columns move (j <= i < p)
   for (int I = J; I < g.I0; ++I)
-    for (int idx = tid; idx < TB * TB / 2; idx += NTHREADS) {
-      const int r = idx >> 5, c = (idx & 31) << 1;
-      const int64_t o = (int64_t)(I * TB + r) * ld + J * TB + c;
+    for (int idx = tid; idx < TB * RM_SW / 2; idx += NTHREADS) {
+      const int r = idx / (RM_SW / 2), c = (idx % (RM_SW / 2)) * 2;
+      const int i = I * TB + r, j = col0 + c;
+      const int64_t o = (int64_t)i * ld + j;
       double2 v = *reinterpret_cast<const double2*>(Mo + o);
-      if (I == J) {  // (tiles above the diagonal hold nothing; inside the diagonal tile the upper part is kept at zero)
-        if (c > r) v.x = 0.0;
-        if (c + 1 > r) v.y = 0.0;
-      }
+      if (j > i) v.x = 0.0;  // (inside the diagonal tile the upper part is kept at zero)
+      if (j + 1 > i) v.y = 0.0;
       *reinterpret_cast<double2*>(Mn + o) = v;
     }
   const int Ifirst = max(J, g.I0);
   // carriers: rows p..p+n-1 of the block's own columns contribute b_k[q] M[k, j] to every prefix
-  for (int idx = tid; idx < NP * TB; idx += NTHREADS) {
-    const int q = idx >> 6, c = idx & 63, jp = J * TB + c;
+  {
+    const int q = tid / RM_SW, c = tid % RM_SW, jp = col0 + c;  // NP * RM_SW = 256 = NTHREADS entries
     double run = 0.0;
     if (q < g.n && jp < g.mnew) {
       const int j = jp < g.p ? jp : jp + g.n;
@@ -609,9 +614,9 @@ __global__ void __launch_bounds__(NTHREADS) k_rm_strip(const double* __restrict_
   }
   auto issue = [&](int I, RmStripStage& S) {  // operands of row tile I (cp.async; constants stored directly)
     const int bx = I - g.I0;
-    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
-      const int r = idx >> 6, c = idx & 63, ip = I * TB + r, jp = J * TB + c;
-      double* dst = S.sB + r * LD_R + c;
+    for (int idx = tid; idx < TB * RM_SW; idx += NTHREADS) {
+      const int r = idx / RM_SW, c = idx % RM_SW, ip = I * TB + r, jp = col0 + c;
+      double* dst = S.sB + r * LD_SW + c;
       if (ip >= g.mnew || jp >= g.mnew) {
         *dst = (ip == jp) ? 1.0 : 0.0;
       } else {
@@ -641,30 +646,37 @@ __global__ void __launch_bounds__(NTHREADS) k_rm_strip(const double* __restrict_
     if (I + 1 < g.nbn) issue(I + 1, st[cur ^ 1]);
     cp_async_commit();
     cp_async_wait<1>();  // this thread's copies of tile I have landed ...
-    for (int idx = tid; idx < NP * TB; idx += NTHREADS) S.sB[(TB + (idx >> 6)) * LD_R + (idx & 63)] = sH[idx >> 6][idx & 63];
+    S.sB[(TB + tid / RM_SW) * LD_SW + tid % RM_SW] = sH[tid / RM_SW][tid % RM_SW];
     __syncthreads();     // ... everybody's have, and H is in place
-    Acc64 acc;
+    // new = diag(u) (old - [S | G] [old ; H]): 64 x 16, warp w owns rows [8w, 8w + 8)
+    Acc<1, 2> acc;
     acc.zero();
-    warp_mma<2, 4, true, false, TB + NP, LD_W, LD_R>(acc, S.sA, S.sB, warp_rb64(), warp_cb64());
-    for_each_acc64(acc, [&](int r, int c, double& v) {
-      Mn[(int64_t)(I * TB + r) * ld + J * TB + c] = S.su[r] * (S.sB[r * LD_R + c] - v);
-    });
-    // H += B_I^T old: 16 x 64, warp w owns columns [8w, 8w + 8)
-    Acc<2, 1> hp;
-    hp.zero();
-    warp_mma<2, 1, false, false, TB, LD_BT, LD_R>(hp, S.sBt, S.sB, 0, warp * 8);
+    warp_mma<1, 2, true, false, TB + NP, LD_W, LD_SW>(acc, S.sA, S.sB, 8 * warp, 0);
+    {
+      const int r = 8 * warp + gq;
+      double* orow = Mn + (int64_t)(I * TB + r) * ld + col0;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int q = 8 * i + gq, c = warp * 8 + 2 * tq;
-      sH[q][c] += hp.v[i][0][0];
-      sH[q][c + 1] += hp.v[i][0][1];
+      for (int j = 0; j < 2; ++j) {
+        const int c = 8 * j + 2 * tq;
+        orow[c] = S.su[r] * (S.sB[r * LD_SW + c] - acc.v[0][j][0]);
+        orow[c + 1] = S.su[r] * (S.sB[r * LD_SW + c + 1] - acc.v[0][j][1]);
+      }
+    }
+    // H += B_I^T old: 16 x 16 in four 8 x 8 blocks (warps 0..3)
+    if (warp < 4) {
+      Acc<1, 1> hp;
+      hp.zero();
+      warp_mma<1, 1, false, false, TB, LD_BT, LD_SW>(hp, S.sBt, S.sB, 8 * (warp >> 1), 8 * (warp & 1));
+      const int q = 8 * (warp >> 1) + gq, c = 8 * (warp & 1) + 2 * tq;
+      sH[q][c] += hp.v[0][0][0];
+      sH[q][c + 1] += hp.v[0][0][1];
     }
     __syncthreads();  // the stage may be refilled, H is complete for the next tile
   }
   cp_async_wait<0>();
   // closed-form alpha of the result and the strip's share of x, y  (vec = x | y | alpha | z, `cap` doubles each)
-  if (tid < TB) {
-    const int jp = J * TB + tid;
+  if (tid < RM_SW) {
+    const int jp = col0 + tid;
     if (jp < g.mnew) {
       const int j = jp < g.p ? jp : jp + g.n;
       double sdot = 0.0;
@@ -674,7 +686,7 @@ __global__ void __launch_bounds__(NTHREADS) k_rm_strip(const double* __restrict_
       vec_new[2 * cap + jp] = vec_old[2 * cap + j] - sdot;
     }
   }
-  if (J == 0 && tid < 32) vec_new[4 * cap + tid] = vec_old[4 * cap + tid];  // the stat block travels with the buffer
+  if (strip == 0 && tid < 32) vec_new[4 * cap + tid] = vec_old[4 * cap + tid];  // the stat block travels with the buffer
 }
 
 // x, y of the result (new order = old order with the block dropped).
