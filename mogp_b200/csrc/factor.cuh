@@ -239,6 +239,130 @@ __global__ void __launch_bounds__(NTHREADS) k_trail_blk(double* __restrict__ L, 
   }
 }
 
+// The same group update with 128 x 128 output blocks (two row tiles x two column tiles per CTA): every operand slice
+// loaded serves four tile products instead of two (the update streams L and M from HBM when ~30 clusters are refitted at
+// once: arithmetic intensity is what it is short of), a warp owns 32 x 64 of the block (32 DMMAs per 12 fragment
+// loads), and the contraction runs through a two-stage cp.async ring in 32-deep slices - the next slice is in flight
+// while the current one is multiplied.  Fragments of the K-contiguous operands (rows of L) come from 128-bit loads (lane
+// t supplies k = 2t, 2t+1 to two consecutive DMMAs, as in the scoring kernel); the rows of M of the inverse part are
+// stored [k][column] and read with the matching k.
+constexpr int TBIG_BK = 32;                       // contraction slice
+constexpr int TBIG_LDA = 40;                      // smem ld of a K-contiguous slice [128][32] (8 mod 16)
+constexpr int TBIG_LDM = 130;                     // smem ld of a slice of M [32][128] (2 mod 16: k = 2t, 2t+1 conflict free)
+constexpr int TBIG_STAGE = 2 * 128 * TBIG_LDA;    // doubles per stage: A slice | B slice
+constexpr int TBIG_SMEM = 2 * TBIG_STAGE * (int)sizeof(double);
+__global__ void __launch_bounds__(NTHREADS, 1) k_trail_big(double* __restrict__ L, double* __restrict__ M, int64_t ld, int P0, int P1,
+                                                           int nb) {
+  const int bj0 = 2 * (int)blockIdx.x, bi0 = P1 + 2 * (int)blockIdx.y;  // first column / row tile of the block
+  if (bi0 >= nb || bj0 > bi0 + 1 || bj0 >= nb) return;
+  const bool lpart = bj0 >= P1;
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int rb = 32 * (warp >> 1), cb = 64 * (warp & 1);
+  const int rows_ok = min(128, (nb - bi0) * TB), cols_ok = min(128, (nb - bj0) * TB);  // the block may overhang the matrix
+  const int p_first = lpart ? P0 : max(P0, bj0);
+  const int nslice = (P1 - p_first) * (TB / TBIG_BK);
+  auto issue = [&](int sl, int stage) {
+    double* sA = smem + stage * TBIG_STAGE;
+    double* sB = sA + 128 * TBIG_LDA;
+    const int p = p_first + sl / (TB / TBIG_BK), k0 = p * TB + (sl % (TB / TBIG_BK)) * TBIG_BK;  // panel, first contraction index
+#pragma unroll
+    for (int q = 0; q < 128 * TBIG_BK / 2 / NTHREADS; ++q) {
+      const int idx = tid + q * NTHREADS, r = idx >> 4, c = (idx & 15) << 1;
+      double* d = sA + r * TBIG_LDA + c;
+      if (r < rows_ok) cp_async16(d, L + (int64_t)(bi0 * TB + r) * ld + k0 + c);
+      else *reinterpret_cast<double2*>(d) = make_double2(0.0, 0.0);
+    }
+    if (lpart) {
+#pragma unroll
+      for (int q = 0; q < 128 * TBIG_BK / 2 / NTHREADS; ++q) {
+        const int idx = tid + q * NTHREADS, r = idx >> 4, c = (idx & 15) << 1;
+        double* d = sB + r * TBIG_LDA + c;
+        if (r < cols_ok) cp_async16(d, L + (int64_t)(bj0 * TB + r) * ld + k0 + c);
+        else *reinterpret_cast<double2*>(d) = make_double2(0.0, 0.0);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < TBIG_BK * 128 / 2 / NTHREADS; ++q) {
+        const int idx = tid + q * NTHREADS, k = idx >> 6, c = (idx & 63) << 1;
+        double* d = sB + k * TBIG_LDM + c;
+        // M_pj is lower triangular by tiles: nothing above the diagonal (never written: do not read it)
+        const bool live = c < cols_ok && (bj0 + (c >> 6)) <= p;
+        if (live) cp_async16(d, M + (int64_t)(k0 + k) * ld + bj0 * TB + c);
+        else *reinterpret_cast<double2*>(d) = make_double2(0.0, 0.0);
+      }
+    }
+  };
+  Acc<4, 8> acc;
+  acc.zero();
+  if (nslice > 0) issue(0, 0);
+  cp_async_commit();
+  for (int sl = 0; sl < nslice; ++sl) {
+    cp_async_wait<0>();
+    __syncthreads();  // slice sl has landed for everybody; the other stage is free
+    if (sl + 1 < nslice) issue(sl + 1, (sl + 1) & 1);
+    cp_async_commit();
+    const double* sA = smem + (sl & 1) * TBIG_STAGE;
+    const double* sB = sA + 128 * TBIG_LDA;
+#pragma unroll
+    for (int kb = 0; kb < TBIG_BK; kb += 8) {
+      double2 a[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double2*>(sA + (rb + 8 * i + g) * TBIG_LDA + kb + 2 * t);
+      if (lpart) {
+        double2 b[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = *reinterpret_cast<const double2*>(sB + (cb + 8 * j + g) * TBIG_LDA + kb + 2 * t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i].y, b[j].y);
+      } else {
+        double b0[8], b1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          b0[j] = sB[(kb + 2 * t) * TBIG_LDM + cb + 8 * j + g];
+          b1[j] = sB[(kb + 2 * t + 1) * TBIG_LDM + cb + 8 * j + g];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i].x, b0[j]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i].y, b1[j]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  double* out = lpart ? L : M;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = rb + 8 * i + g, c = cb + 8 * j + 2 * t;
+      if (r >= rows_ok || c >= cols_ok) continue;
+      const int bi = bi0 + (r >> 6), bj = bj0 + (c >> 6);
+      if (bj > bi) continue;  // a tile above the diagonal
+      double2* o = reinterpret_cast<double2*>(out + (int64_t)(bi0 * TB + r) * ld + bj0 * TB + c);
+      double2 v = *o;
+      if (lpart) {
+        const int gr = bi0 * TB + r, gc = bj0 * TB + c;  // inside a diagonal tile only the lower part is kept
+        if (gc <= gr) v.x -= acc.v[i][j][0];
+        if (gc + 1 <= gr) v.y -= acc.v[i][j][1];
+      } else {
+        v.x += acc.v[i][j][0];
+        v.y += acc.v[i][j][1];
+      }
+      *o = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // z = M r with r = y + A x (residual of the NegLinear mean, neg_linear.py:22-23). Warp per row.
 __global__ void __launch_bounds__(NTHREADS) k_z(const double* __restrict__ M, int64_t ld, const double* __restrict__ x,
