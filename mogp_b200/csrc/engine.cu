@@ -576,7 +576,11 @@ void launch_factor(mogp_engine* h, double* L, double* M, int64_t ld, int nb, int
       }
     }
     if (P1 < nb) {
-      static const int rows = getenv("MOGP_TRAIL_ROWS") ? atoi(getenv("MOGP_TRAIL_ROWS")) : 4;  // 4: 128 x 128 blocks (k_trail_big)
+      // 2 (default): two row tiles per CTA sharing the second operand; 1: one; 4: 128 x 128 blocks (k_trail_big - measured
+      // slower here, 898 vs 657 us per evaluation at m = 2 600 and 0.50 vs 0.44 s per 30-cluster refit: one 8-warp CTA
+      // per SM with 164 KB of operands leaves the prologue / read-modify-write epilogue of every block uncovered, and
+      // its ~200-block launches quantise badly on 148 SMs; kept for experiments, profiles/README.md)
+      static const int rows = getenv("MOGP_TRAIL_ROWS") ? atoi(getenv("MOGP_TRAIL_ROWS")) : 2;
       if (rows == 4 && (P1 & 1) == 0)
         k_trail_big<<<dim3((nb + 1) / 2, (nb - P1 + 1) / 2), NTHREADS, TBIG_SMEM, h->stream>>>(L, M, ld, P0, P1, nb);
       else if (rows == 1) k_trail_blk<1><<<dim3(nb, nb - P1), NTHREADS, TRAIL_SMEM, h->stream>>>(L, M, ld, P0, P1, nb);

@@ -377,28 +377,58 @@ class MoGP_constrained:
             self._apply_normalizer()                               # :343-345: the per-cluster normalisers end up attached
         return p
 
+    PREDICT_BLOCK = 50000     # patients per block of the pipelined batch prediction
+
     def predict_batch(self, X_new, Y_new, a_draws, _normalized=False):
         """`predict` for P patients at once: NaN-padded P x T matrices -> P x (len(Nk)+1) probabilities.
-        a_draws[p] = the randn the reference would draw for patient p's new-cluster model."""
+        a_draws[p] = the randn the reference would draw for patient p's new-cluster model.
+        Large batches go through in blocks: while the device scores block b (one host thread inside the engine, the GIL
+        released), this thread compacts the rows of block b + 1 and turns the scores of block b - 1 into probabilities."""
         if self.normalize and not _normalized:
             Y_new = (Y_new - self.mean) / self.std
-        off, x, y = pack_patients(X_new, Y_new)
         eng = self.engine
         Nk = self.allocmodel.Nk
         active = self._active()
         slots = np.array([self.obsmodel[k].model.slot for k in active], dtype=np.int32)
-        P = len(off) - 1
-        score = np.tile(np.log(np.hstack([Nk, self.allocmodel.alpha]) + 1e-16), (P, 1))      # :335
-        score[:, active] += eng.score_pairs(off, x, y, slots)                                # :336-338
+        prior = np.log(np.hstack([Nk, self.allocmodel.alpha]) + 1e-16)                       # :335
         theta0 = initial_theta(self.kernel, self.signal_variance, self.noise_variance, 4., 0.0)
-        score[:, -1] += eng.new_cluster_ll(self._spec(mean_func=True), theta0, off, x, y, a_draws)   # :339
-        if P == 1:
-            return np.exp(score - logsumexp(score, axis=1, keepdims=True))                   # :340-341
-        # the same softmax for many rows without SciPy's per-call overhead: lse = max + log(sum(exp(s - max)))
-        mx = np.max(score, axis=1, keepdims=True)
-        lse = mx + np.log(np.sum(np.exp(score - mx), axis=1, keepdims=True))
-        np.subtract(score, lse, out=score)
-        return np.exp(score, out=score)
+        spec_new = self._spec(mean_func=True)
+        a_draws = np.asarray(a_draws, dtype=np.float64)
+
+        def device(packed, a):
+            off, x, y = packed
+            return eng.score_pairs(off, x, y, slots), eng.new_cluster_ll(spec_new, theta0, off, x, y, a)   # :336-339
+
+        def finish(res):
+            pair, new = res
+            score = np.tile(prior, (pair.shape[0], 1))
+            score[:, active] += pair
+            score[:, -1] += new
+            if score.shape[0] == 1:
+                return np.exp(score - logsumexp(score, axis=1, keepdims=True))               # :340-341
+            # the same softmax for many rows without SciPy's per-call overhead: lse = max + log(sum(exp(s - max)))
+            mx = np.max(score, axis=1, keepdims=True)
+            lse = mx + np.log(np.sum(np.exp(score - mx), axis=1, keepdims=True))
+            np.subtract(score, lse, out=score)
+            return np.exp(score, out=score)
+
+        P = X_new.shape[0]
+        B = self.PREDICT_BLOCK
+        if P <= B:
+            return finish(device(pack_patients(X_new, Y_new), a_draws))
+        from concurrent.futures import ThreadPoolExecutor
+        out = np.empty((P, len(Nk) + 1))
+        with ThreadPoolExecutor(max_workers=1) as gpu:
+            pending = None                                         # (rows, future) of the block on the device
+            for lo in range(0, P, B):
+                hi = min(P, lo + B)
+                packed = pack_patients(X_new[lo:hi], Y_new[lo:hi])
+                fut = gpu.submit(device, packed, a_draws[lo:hi])
+                if pending is not None:
+                    out[pending[0]:pending[1]] = finish(pending[2].result())
+                pending = (lo, hi, fut)
+            out[pending[0]:pending[1]] = finish(pending[2].result())
+        return out
 
 
 class MoGP(MoGP_constrained):
