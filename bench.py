@@ -306,10 +306,15 @@ def run_b200(args):
     eng.profile_read(reset=True)
     cnt0 = eng.chain_counters()
     rc0 = eng.refit_counters()
+    prof_range = os.environ.get("MOGP_PROFILE_RANGE") == "1"   # ncu --profile-from-start off: capture the timed sweeps only
+    if prof_range:
+        torch.cuda.profiler.start()
     eng.timer_start()
     for _ in range(args.steps):
         device_sweep()
     ms = eng.timer_stop()
+    if prof_range:
+        torch.cuda.profiler.stop()
     cnt1 = eng.chain_counters()
     rc1 = eng.refit_counters()
     counters = {k: cnt1[k] - cnt0[k] for k in cnt1}
