@@ -583,7 +583,7 @@ void launch_factor(mogp_engine* h, double* L, double* M, int64_t ld, int nb, int
       static const int rows = getenv("MOGP_TRAIL_ROWS") ? atoi(getenv("MOGP_TRAIL_ROWS")) : 2;
       if (rows == 4 && (P1 & 1) == 0)
         k_trail_big<<<dim3((nb + 1) / 2, (nb - P1 + 1) / 2), NTHREADS, TBIG_SMEM, h->stream>>>(L, M, ld, P0, P1, nb);
-      else if (rows == 1) k_trail_blk<1><<<dim3(nb, nb - P1), NTHREADS, TRAIL_SMEM, h->stream>>>(L, M, ld, P0, P1, nb);
+      else if (rows == 1) k_trail_blk<1><<<dim3(nb, nb - P1), NTHREADS, TRAILB_SMEM, h->stream>>>(L, M, ld, P0, P1, nb);
       else k_trail_blk<2><<<dim3(nb, (nb - P1 + 1) / 2), NTHREADS, TRAILB_SMEM, h->stream>>>(L, M, ld, P0, P1, nb);
       LAUNCHED(h);
     }
@@ -1110,7 +1110,7 @@ static int engine_create_impl(int32_t device, bool light, mogp_engine** out) {
   cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
   cudaFuncSetAttribute(k_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAIL_SMEM);
   cudaFuncSetAttribute(k_trail_blk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAILB_SMEM);
-  cudaFuncSetAttribute(k_trail_blk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAIL_SMEM);
+  cudaFuncSetAttribute(k_trail_blk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAILB_SMEM);
   cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAD_SMEM);
   cudaFuncSetAttribute(k_trail_big, cudaFuncAttributeMaxDynamicSharedMemorySize, TBIG_SMEM);
   // (function attributes are per device: set for every kernel whenever an engine is created, on its device)

@@ -182,36 +182,68 @@ __global__ void __launch_bounds__(NTHREADS) k_trail(double* __restrict__ L, doub
 
 // After the panels [P0, P1) of a group: rows bi >= P1, two row tiles per CTA (they share the second operand):
 //   bj >= P1 : A_ij -= sum_p L_ip L_jp^T          bj < P1 : Acc_ij += sum_{p >= max(P0, bj)} L_ip M_pj
-constexpr int TRAILB_SMEM = (2 * TB * LD_C + TB * LD_R) * (int)sizeof(double);
-template <int ROWS>  // row tiles per CTA: 2 (shared second operand, 2 CTAs per SM) or 1 (3 CTAs per SM)
+// The contraction over the group's panels runs in 32-deep slices through a two-stage cp.async ring: the next slice is
+// in flight while the current one is multiplied (ncu on the synchronous version: 30 % of the warp stalls on the global
+// loads of the operand tiles, tensor pipe 51 % of the elapsed cycles), and the two stages of 2-row-tile CTAs still fit
+// twice on an SM.
+constexpr int TSL = 32;              // contraction slice
+constexpr int LD_S = 36;             // smem ld of a K-contiguous slice [64][32] (4 mod 16)
+constexpr int TSL_TILE = TB * LD_S;  // doubles per operand slice (>= 32 * LD_R for a [32][64] slice of M)
+static_assert(TSL * LD_R <= TSL_TILE, "slice of M does not fit");
+constexpr int TRAILB_SMEM = 2 * 3 * TSL_TILE * (int)sizeof(double);
+template <int ROWS>  // row tiles per CTA: 2 (shared second operand) or 1
 __global__ void __launch_bounds__(NTHREADS) k_trail_blk(double* __restrict__ L, double* __restrict__ M, int64_t ld, int P0, int P1,
                                                         int nb) {
   const int bj = blockIdx.x, bi0 = P1 + ROWS * (int)blockIdx.y, bi1 = bi0 + 1;
   const bool do0 = bj <= bi0, do1 = ROWS == 2 && bi1 < nb && bj <= bi1;
   if (!do0 && !do1) return;
   extern __shared__ __align__(16) double smem[];
-  double* sA0 = smem;               // L_{bi0,p}  [64][LD_C]
-  double* sA1 = sA0 + TB * LD_C;    // L_{bi1,p}   (ROWS == 2)
-  double* sB = ROWS == 2 ? sA1 + TB * LD_C : sA1;  // L_jp [64][LD_C]  or  M_pj [64][LD_R]
   const bool lpart = bj >= P1;
+  const int p_first = lpart ? P0 : max(P0, bj);
+  const int nslice = (P1 - p_first) * (TB / TSL);
+  auto issue = [&](int sl, int stage) {
+    double* sA0 = smem + stage * (3 * TSL_TILE);
+    double* sA1 = sA0 + TSL_TILE;
+    double* sB = sA1 + TSL_TILE;
+    const int p = p_first + sl / (TB / TSL);
+    const int64_t k0 = (int64_t)p * TB + (sl % (TB / TSL)) * TSL;
+#pragma unroll
+    for (int q = 0; q < TB * TSL / 2 / NTHREADS; ++q) {  // [64][32] slices, 16 chunks of 16 bytes per row
+      const int idx = threadIdx.x + q * NTHREADS, r = idx >> 4, c = (idx & 15) << 1;
+      if (do0) cp_async16(sA0 + r * LD_S + c, L + ((int64_t)bi0 * TB + r) * ld + k0 + c);
+      if (do1) cp_async16(sA1 + r * LD_S + c, L + ((int64_t)bi1 * TB + r) * ld + k0 + c);
+      if (lpart) cp_async16(sB + r * LD_S + c, L + ((int64_t)bj * TB + r) * ld + k0 + c);
+    }
+    if (!lpart) {
+#pragma unroll
+      for (int q = 0; q < TSL * TB / 2 / NTHREADS; ++q) {  // [32][64] slice of M: 32 chunks per row
+        const int idx = threadIdx.x + q * NTHREADS, k = idx >> 5, c = (idx & 31) << 1;
+        cp_async16(sB + k * LD_R + c, M + (k0 + k) * ld + (int64_t)bj * TB + c);
+      }
+    }
+  };
   Acc64 acc0, acc1;
   acc0.zero();
   acc1.zero();
-  for (int p = lpart ? P0 : max(P0, bj); p < P1; ++p) {
-    __syncthreads();  // the previous step's fragments have been read
-    if (do0) load_tile<LD_C>(sA0, L + (int64_t)bi0 * TB * ld + (int64_t)p * TB, ld);
-    if (do1) load_tile<LD_C>(sA1, L + (int64_t)bi1 * TB * ld + (int64_t)p * TB, ld);
-    if (lpart) load_tile<LD_C>(sB, L + (int64_t)bj * TB * ld + (int64_t)p * TB, ld);
-    else load_tile<LD_R>(sB, M + (int64_t)p * TB * ld + (int64_t)bj * TB, ld);
-    __syncthreads();
+  if (nslice > 0) issue(0, 0);
+  cp_async_commit();
+  for (int sl = 0; sl < nslice; ++sl) {
+    cp_async_wait<0>();
+    __syncthreads();  // slice sl has landed for everybody; the other stage is free
+    if (sl + 1 < nslice) issue(sl + 1, (sl + 1) & 1);
+    cp_async_commit();
+    const double* sA0 = smem + (sl & 1) * (3 * TSL_TILE);
+    const double* sA1 = sA0 + TSL_TILE;
+    const double* sB = sA1 + TSL_TILE;
     if (lpart) {
-      if (do0) warp_mma<2, 4, true, true>(acc0, sA0, sB, warp_rb64(), warp_cb64());
-      if (do1) warp_mma<2, 4, true, true>(acc1, sA1, sB, warp_rb64(), warp_cb64());
+      if (do0) warp_mma<2, 4, true, true, TSL, LD_S, LD_S>(acc0, sA0, sB, warp_rb64(), warp_cb64());
+      if (do1) warp_mma<2, 4, true, true, TSL, LD_S, LD_S>(acc1, sA1, sB, warp_rb64(), warp_cb64());
     } else {
-      if (do0) warp_mma<2, 4, true, false>(acc0, sA0, sB, warp_rb64(), warp_cb64());
-      if (do1) warp_mma<2, 4, true, false>(acc1, sA1, sB, warp_rb64(), warp_cb64());
+      if (do0) warp_mma<2, 4, true, false, TSL, LD_S, LD_R>(acc0, sA0, sB, warp_rb64(), warp_cb64());
+      if (do1) warp_mma<2, 4, true, false, TSL, LD_S, LD_R>(acc1, sA1, sB, warp_rb64(), warp_cb64());
     }
   }
+  cp_async_wait<0>();
   if (lpart) {
     if (do0) {
       double* out = L + (int64_t)bi0 * TB * ld + (int64_t)bj * TB;
@@ -482,18 +514,34 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(const double* __restrict__ M,
     return;
   }
   extern __shared__ __align__(16) double smem[];
-  double* sA = smem;
-  double* sB = sA + TB * LD_R;
   Acc64 acc;
   acc.zero();
   const int k1 = min(nb, k0 + kchunk);
-  for (int k = k0; k < k1; ++k) {
-    __syncthreads();
-    load_tile<LD_R>(sA, M + (int64_t)k * TB * ld + (int64_t)bi * TB, ld);
-    load_tile<LD_R>(sB, M + (int64_t)k * TB * ld + (int64_t)bj * TB, ld);
-    __syncthreads();
-    warp_mma<2, 4, false, false>(acc, sA, sB, warp_rb64(), warp_cb64());
+  // the rows of the contraction stream through a two-stage cp.async ring in 32-row slices of the two column strips
+  constexpr int GSL = 32, GST = 2 * GSL * LD_R;  // slice depth, doubles per stage
+  const int nslice = (k1 - k0) * (TB / GSL);
+  auto issue = [&](int sl, int stage) {
+    double* sA = smem + stage * GST;
+    double* sB = sA + GSL * LD_R;
+    const int64_t r0 = (int64_t)(k0 + sl / (TB / GSL)) * TB + (sl % (TB / GSL)) * GSL;
+#pragma unroll
+    for (int q = 0; q < GSL * TB / 2 / NTHREADS; ++q) {
+      const int idx = threadIdx.x + q * NTHREADS, k = idx >> 5, c = (idx & 31) << 1;
+      cp_async16(sA + k * LD_R + c, M + (r0 + k) * ld + (int64_t)bi * TB + c);
+      cp_async16(sB + k * LD_R + c, M + (r0 + k) * ld + (int64_t)bj * TB + c);
+    }
+  };
+  issue(0, 0);
+  cp_async_commit();
+  for (int sl = 0; sl < nslice; ++sl) {
+    cp_async_wait<0>();
+    __syncthreads();  // slice sl has landed for everybody; the other stage is free
+    if (sl + 1 < nslice) issue(sl + 1, (sl + 1) & 1);
+    cp_async_commit();
+    const double* sA = smem + (sl & 1) * GST;
+    warp_mma<2, 4, false, false, GSL, LD_R, LD_R>(acc, sA, sA + GSL * LD_R, warp_rb64(), warp_cb64());
   }
+  cp_async_wait<0>();
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
   for_each_acc64(acc, [&](int r, int c, double& w) {
     int i = bi * TB + r, j = bj * TB + c;

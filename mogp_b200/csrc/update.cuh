@@ -651,7 +651,19 @@ __global__ void __launch_bounds__(NTHREADS) k_rm_strip(const double* __restrict_
     // new = diag(u) (old - [S | G] [old ; H]): 64 x 16, warp w owns rows [8w, 8w + 8)
     Acc<1, 2> acc;
     acc.zero();
-    warp_mma<1, 2, true, false, TB + NP, LD_W, LD_SW>(acc, S.sA, S.sB, 8 * warp, 0);
+    {
+      // S is STRICTLY lower triangular: rows [8w, 8w + 8) only see k < 8w + 8 of it; then the G H part (k = 64 .. 64 + NP)
+      const double* arow = S.sA + (8 * warp + gq) * LD_W;
+      auto kstep = [&](int kb) {
+        const double a = arow[kb + tq];
+        const double b0 = S.sB[(kb + tq) * LD_SW + gq], b1 = S.sB[(kb + tq) * LD_SW + 8 + gq];
+        dmma884(acc.v[0][0][0], acc.v[0][0][1], a, b0);
+        dmma884(acc.v[0][1][0], acc.v[0][1][1], a, b1);
+      };
+      for (int kb = 0; kb < 8 * warp + 8; kb += 4) kstep(kb);
+#pragma unroll
+      for (int kb = TB; kb < TB + NP; kb += 4) kstep(kb);
+    }
     {
       const int r = 8 * warp + gq;
       double* orow = Mn + (int64_t)(I * TB + r) * ld + col0;
