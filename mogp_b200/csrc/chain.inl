@@ -756,6 +756,15 @@ int win_prepare(mogp_engine* h, int64_t n_steps, const int64_t* order, const dou
   w.slot_alg.assign(h->cl.size(), 0);
   w.slot_epoch.assign(h->cl.size(), 0);
   w.batch_end = 0;
+  w.async_items.clear();
+  w.rpw_used = 0;
+  w.cur_bi = 0;
+  {  // partial sums of the corrections queued ahead: room for REPLAY_MAX of them against the largest cluster
+    int64_t maxcap = TB;
+    for (const Cluster& c : h->cl)
+      if (c.used) maxcap = std::max(maxcap, c.cap);
+    TRY(ensure(h, &h->d_rpw, &h->rpw_elems, (int64_t)REPLAY_MAX * OWN_BATCH * (maxcap / TB + 8) * ALG_ENTRIES));
+  }
   w.new_ll.assign(n_steps, 0.0);
   w.own_ll.assign(n_steps, 0.0);
   w.own_mu.assign(n_steps, 0.0);
@@ -891,7 +900,7 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   bf.res.zigzag = pipeline_depth() >= 2 ? env_int("MOGP_ZIGZAG", 0) : 0;
   // the monotonicity rule applied on the device before the O(m^2) product (MOGP_PRUNE=0: after it, on the host only)
   PruneSpec prune{h->d_wq + 2 * Rtot + w.n + s0, ch.cfg.threshold};
-  const bool do_prune = ch.cfg.use_threshold && env_int("MOGP_PRUNE", 1) != 0 && env_int("MOGP_REPLAY", 0) == 0;
+  const bool do_prune = ch.cfg.use_threshold && env_int("MOGP_PRUNE", 1) != 0;
   if (ns > 0)
     TRY(score_device(h, cnt, R, h->d_woff + s0, h->d_wq + cb, h->d_wq + Rtot + cb, ns, b.slots.data(), thr_index, d_score, d_mu,
                      nullptr, nullptr, nullptr, true, &b.pl, &bf.res, do_prune ? &prune : nullptr));
@@ -966,88 +975,119 @@ int batch_absorb(mogp_engine* h, int bi) {
   return MOGP_OK;
 }
 
-// The pass of the batch just absorbed was launched BEFORE the previous batch made its moves.  For a cluster that took
-// exactly one logged rank-n change since, the same correction is applied to this batch's positions from what its own
-// pass left on the device - instead of waiting for the factor update and re-scoring.  Everything else that changed
-// stays stale and is re-scored at the batch's first step.
+// The pass of the NEXT batch is launched before the current batch makes its moves, so every cluster a move changes is
+// stale in it.  Re-scoring those clusters at the next batch's start costs a wait for the factor updates plus O(m^2)
+// products that compete with the pass after next.  Instead, the rank-n correction a move applies to the positions still
+// ahead in ITS batch (k_alg_leave / k_alg_join) is queued a second time, for the positions of the next batch, on the
+// look-ahead stream right behind that batch's pass: it works from the T / ss / mu the pass leaves on the device (the
+// pass saw the cluster before the change, which is what the formulas start from) and from copies of what the move
+// itself contributes (the block columns and alpha_B of a leave, Ls^-1 and z_B of a join).  By the time the batch is
+// absorbed the corrected scores are in pinned memory: no launch, no wait.  One correction per cluster: a cluster that
+// changes twice before the next batch starts, or that is new / emptied, is re-scored the long way as before.
+int replay_launch(mogp_engine* h, const ChangeLog& L, cudaEvent_t dep) {
+  Chain& ch = h->chain;
+  Chain::Window& w = ch.win;
+  if (w.end_launched <= w.batch_end) return MOGP_OK;  // no pass in flight
+  for (auto& it : w.async_items)
+    if (it.slot == L.slot) {  // second change of this cluster since that pass was launched
+      it.dead = true;
+      return MOGP_OK;
+    }
+  const int nbi = w.cur_bi ^ 1;
+  const Chain::Batch& nb = w.b[nbi];
+  const BatchBuf& nbf = h->bb[nbi];
+  if (nb.cnt <= 0 || nb.cnt > OWN_BATCH || (int)w.async_items.size() >= REPLAY_MAX || L.ntiles <= 0) return MOGP_OK;
+  int si = -1;
+  for (size_t q = 0; q < nb.slots.size(); ++q)
+    if (nb.slots[q] == L.slot) si = (int)q;
+  if (si < 0 || nb.epoch[si] != L.epoch_before) return MOGP_OK;  // not in that pass, or changed before it was launched
+  const int64_t wneed = nb.cnt * (int64_t)L.ntiles * (L.kind == 0 ? ALG_ENTRIES : NP * NP);
+  if (w.rpw_used + wneed > h->rpw_elems) return MOGP_OK;
+  AlgJobs J = L.J;
+  int64_t kx_off = 0;
+  for (int q = 0; q < si; ++q) kx_off += nb.pl.Rpad * nb.mpad[q];
+  const int64_t cb = w.col0[nb.s0];
+  const int ns = (int)nb.slots.size();
+  for (int64_t q = 0; q < nb.cnt; ++q) {
+    const int64_t v = nb.s0 + q, c = w.col0[v] - cb;
+    AlgPos& P = J.pos[q];
+    P.stride = nb.mpad[si];
+    P.T = nb.pl.T + kx_off + c * P.stride;
+    P.mu = nb.pl.mu + (int64_t)si * nb.pl.Rpad + c;
+    P.ss = nb.pl.ss + (int64_t)si * nb.pl.Rpad + c;
+    P.x = h->d_wq + w.col0[v];
+    P.y = h->d_wq + w.col0[w.n] + w.col0[v];
+    P.ncols = (int)(w.col0[v + 1] - w.col0[v]);
+    P.thr = J.thr_index;
+    P.flag = nbf.d_out + q * ns + si;  // the pair's score as the pass leaves it: -inf = excluded before the product
+  }
+  const int k = (int)w.async_items.size();
+  J.out = h->d_replay + (int64_t)k * 2 * OWN_BATCH;
+  J.logB = J.logAlpha = nullptr;
+  double* part = h->d_rpw + w.rpw_used;
+  w.rpw_used += wneed;
+  CK(h, cudaStreamWaitEvent(h->ahead, dep, 0));  // what the move contributes (logged copies / Ls^-1, z_B) is in place
+  if (L.kind == 0) {
+    k_alg_leave_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, h->ahead>>>(J, part);
+    LAUNCHED(h);
+    k_alg_leave_fin<<<(unsigned)nb.cnt, 256, 0, h->ahead>>>(J, part, L.ntiles);
+    LAUNCHED(h);
+  } else {
+    k_alg_join_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, h->ahead>>>(J, part);
+    LAUNCHED(h);
+    k_alg_join_fin<<<(unsigned)nb.cnt, 256, 0, h->ahead>>>(J, part, L.ntiles);
+    LAUNCHED(h);
+  }
+  CK(h, cudaMemcpyAsync(h->h_replay + (int64_t)k * 2 * OWN_BATCH, J.out, sizeof(double) * 2 * OWN_BATCH, cudaMemcpyDeviceToHost,
+                        h->ahead));
+  CK(h, cudaEventRecord(h->ev_replay, h->ahead));
+  h->bytes_d2h += (int64_t)sizeof(double) * 2 * OWN_BATCH;
+  Chain::Window::AsyncItem it;
+  it.slot = L.slot;
+  it.epoch_before = L.epoch_before;
+  it.out_idx = k;
+  w.async_items.push_back(it);
+  return MOGP_OK;
+}
+
+// Take over the corrections queued ahead for the batch just absorbed (see replay_launch).
 int win_replay(mogp_engine* h, int bi) {
   Chain& ch = h->chain;
   Chain::Window& w = ch.win;
   Chain::Batch& b = w.b[bi];
-  if (w.log.empty() || b.cnt <= 0 || b.cnt > OWN_BATCH) return MOGP_OK;
-  struct Item {
-    const ChangeLog* cl;
-    int si;
-  };
-  std::vector<Item> items;
-  for (size_t i = 0; i < w.log.size() && (int)items.size() < ALG_OUT_SLOTS - 2; ++i) {
-    const ChangeLog& L = w.log[i];
-    int same = 0;
-    for (const ChangeLog& o : w.log) same += o.slot == L.slot;
-    if (same != 1 || L.slot < 0 || L.slot >= (int32_t)w.slot_epoch.size()) continue;
+  if (w.async_items.empty()) return MOGP_OK;
+  {
+    PhaseTimer pt(&ch.t_alg);
+    CK(h, cudaEventSynchronize(h->ev_replay));
+  }
+  for (const auto& it : w.async_items) {
+    const int32_t slot = it.slot;
+    if (it.dead || slot < 0 || slot >= (int32_t)w.slot_epoch.size() || !h->cl[slot].used) continue;
     int si = -1;
     for (size_t q = 0; q < b.slots.size(); ++q)
-      if (b.slots[q] == L.slot) si = (int)q;
-    if (si < 0 || b.epoch[si] != L.epoch_before || w.slot_epoch[L.slot] != L.epoch_before + 1) continue;
-    if (w.slot_upto[L.slot] > b.s0 || !h->cl[L.slot].used) continue;
-    items.push_back(Item{&L, si});
-  }
-  if (items.empty()) return MOGP_OK;
-  PhaseTimer pt(&ch.t_alg);
-  int64_t wneed = 0;
-  for (const Item& it : items) wneed += b.cnt * (int64_t)it.cl->ntiles * (it.cl->kind == 0 ? ALG_ENTRIES : NP * NP);
-  TRY(ensure(h, &h->d_algw, &h->algw_elems, wneed));
-  CK(h, cudaStreamWaitEvent(h->quick, h->ev_q2, 0));  // the logged copies were written on the other quick stream
-  int64_t woff = 0;
-  for (size_t idx = 0; idx < items.size(); ++idx) {
-    const ChangeLog& L = *items[idx].cl;
-    AlgJobs J = L.J;
-    for (int64_t q = 0; q < b.cnt; ++q) {
-      const int64_t v = b.s0 + q;
-      const Chain::WinEntry& e = w.e[v][L.slot];
-      AlgPos& P = J.pos[q];
-      P.T = e.T;
-      P.ss = e.ss;
-      P.mu = e.mu;
-      P.stride = b.mpad[items[idx].si];
-      P.x = h->d_wq + w.col0[v];
-      P.y = h->d_wq + w.col0[w.n] + w.col0[v];
-      P.ncols = (int)(w.col0[v + 1] - w.col0[v]);
-      P.thr = J.thr_index;
-    }
-    J.out = h->d_alg + (2 + (int64_t)idx) * 2 * OWN_BATCH;
-    J.logB = J.logAlpha = nullptr;
-    double* part = h->d_algw + woff;
-    if (L.kind == 0) {
-      k_alg_leave_part<<<dim3((unsigned)L.ntiles, (unsigned)b.cnt), 256, 0, h->quick>>>(J, part);
-      LAUNCHED(h);
-      k_alg_leave_fin<<<(unsigned)b.cnt, 256, 0, h->quick>>>(J, part, L.ntiles);
-      LAUNCHED(h);
-      woff += b.cnt * (int64_t)L.ntiles * ALG_ENTRIES;
-    } else {
-      k_alg_join_part<<<dim3((unsigned)L.ntiles, (unsigned)b.cnt), 256, 0, h->quick>>>(J, part);
-      LAUNCHED(h);
-      k_alg_join_fin<<<(unsigned)b.cnt, 256, 0, h->quick>>>(J, part, L.ntiles);
-      LAUNCHED(h);
-      woff += b.cnt * (int64_t)L.ntiles * NP * NP;
-    }
-  }
-  const int64_t nout = (2 + (int64_t)items.size()) * 2 * OWN_BATCH;
-  CK(h, cudaMemcpyAsync(h->h_alg, h->d_alg, sizeof(double) * nout, cudaMemcpyDeviceToHost, h->quick));
-  CK(h, sync_helper_stream(h, h->quick));
-  h->bytes_d2h += (int64_t)sizeof(double) * nout;
-  for (size_t idx = 0; idx < items.size(); ++idx) {
-    const int32_t slot = items[idx].cl->slot;
-    const double* out = h->h_alg + (2 + (int64_t)idx) * 2 * OWN_BATCH;
+      if (b.slots[q] == slot) si = (int)q;
+    // exactly one change since the pass was launched, and nobody has re-scored the cluster in the meantime
+    if (si < 0 || b.epoch[si] != it.epoch_before || w.slot_epoch[slot] != it.epoch_before + 1 || w.slot_upto[slot] > b.s0) continue;
+    const double* out = h->h_replay + (int64_t)it.out_idx * 2 * OWN_BATCH;
+    bool reopened = false;
     for (int64_t q = 0; q < b.cnt; ++q) {
       Chain::WinEntry& e = w.e[b.s0 + q][slot];
-      e.score = out[2 * q];
       e.muthr = out[2 * q + 1];
+      if (!e.pruned) {
+        e.score = out[2 * q];
+        continue;
+      }
+      e.score = -INFINITY;  // excluded before the product: stays excluded unless the move brought its mean back
+      const double yt = h->h_ythr.empty() ? NAN : h->h_ythr[w.pat[b.s0 + q]];
+      if (!(yt - e.muthr > ch.cfg.threshold)) reopened = true;
     }
+    if (reopened) continue;  // (the cluster stays stale and is re-scored at the batch's first step)
     w.slot_upto[slot] = b.s0 + b.cnt;  // scores current for this batch; its T / ss / mu are those of the old factor
     w.slot_T_ok[slot] = 0;
+    ch.win_replayed += 1;
   }
-  ch.win_replayed += (int64_t)items.size();
+  w.async_items.clear();
+  w.rpw_used = 0;
   return MOGP_OK;
 }
 
@@ -1188,7 +1228,7 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
   // batch: a second change, a cluster without current T, a new or emptied cluster go the long way (re-scoring).
   const int64_t npos = w.batch_end - (w.cur + 1);
   const bool alg_on = !stays && npos >= 0 && npos <= OWN_BATCH && ch.pending_lazy && env_int("MOGP_RANK_RESCORE", 1) != 0;
-  const bool log_on = alg_on && w.end_launched > w.batch_end && env_int("MOGP_REPLAY", 0) != 0;  // a next batch is in flight (off by default: measured neutral)
+  const bool log_on = alg_on && w.end_launched > w.batch_end && env_int("MOGP_REPLAY", 1) != 0;  // a next batch's pass is in flight
   auto alg_ok = [&](int32_t slot) {
     return slot >= 0 && slot < (int32_t)w.slot_upto.size() && w.slot_upto[slot] >= w.batch_end && w.slot_T_ok[slot] &&
            !w.slot_alg[slot];
@@ -1209,6 +1249,7 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
       P.y = h->d_wq + w.col0[w.n] + w.col0[v] + skip;
       P.ncols = e.pruned ? 1 : (int)(w.col0[v + 1] - w.col0[v]);
       P.thr = e.pruned ? 0 : thr;
+      P.flag = nullptr;
     }
     J.th = make_theta(h->cl[slot]);
     J.thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
@@ -1267,7 +1308,7 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
           cl.J.logB = cl.J.logAlpha = nullptr;
           cl.ntiles = ntiles;
           cl.epoch_before = w.slot_epoch[a_slot];
-          w.log.push_back(cl);
+          TRY(replay_launch(h, cl, h->ev_q2));
         }
       }
     }
@@ -1302,7 +1343,7 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
       cl.J = hook.jobs;  // Tn, Li, znew, xn stay valid until the next batch has been absorbed
       cl.ntiles = hook.ntiles;
       cl.epoch_before = w.slot_epoch[b_slot];
-      w.log.push_back(cl);
+      TRY(replay_launch(h, cl, h->ev_alg));
     }
     if ((a_alg || b_alg) && npos > 0) {
       PhaseTimer pt(&ch.t_alg);
@@ -1413,8 +1454,8 @@ int sweep_pipelined(mogp_engine* h, int64_t n_steps, const int64_t* order, const
     }
     w.cur = pos;
     w.batch_end = pos + B.cnt;
+    w.cur_bi = (int)(jb & 1);
     TRY(win_replay(h, (int)(jb & 1)));
-    w.log.clear();
     w.blog_used = 0;
     {  // room for the logged block columns of this batch's leave-side changes
       int64_t maxm = 0;

@@ -28,6 +28,7 @@
 using namespace mogp;
 
 constexpr int ALG_OUT_SLOTS = 2 + 30;  // outputs of the two within-batch corrections + of a replay (one region per slot)
+constexpr int REPLAY_MAX = 12;         // corrections queued ahead for the next batch's positions, per batch
 
 // The join-side score correction a commit launches right after k_append_small (append_core), see update.cuh.
 struct AlgHook {
@@ -146,7 +147,17 @@ struct Chain {
     std::vector<double> own_ll, own_mu, own_flag;  // [position] leave-block-out score under the patient's own cluster
     std::vector<char> own_ok;
     Batch b[2];
-    std::vector<ChangeLog> log;    // rank-n changes of the current batch (replayed for the next one)
+    // rank-n corrections of the NEXT batch's positions, queued on the look-ahead stream behind that batch's pass at the
+    // moment a move of the current batch changes a cluster (replay_launch); harvested when that batch is absorbed
+    struct AsyncItem {
+      int32_t slot = -1;
+      int64_t epoch_before = 0;
+      int out_idx = 0;
+      bool dead = false;           // the slot changed a second time: the correction does not describe it any more
+    };
+    std::vector<AsyncItem> async_items;
+    int64_t rpw_used = 0;          // doubles used in the engine's d_rpw
+    int cur_bi = 0;                // buffer index of the batch being processed
     int64_t blog_used = 0;         // doubles used in the engine's d_blog
   } win;
   int64_t win_passes = 0, win_rescores = 0, win_patients = 0, win_algebra = 0, win_replayed = 0;  // accounting
@@ -235,6 +246,11 @@ struct mogp_engine {
   double* h_alg = nullptr;        // ... pinned
   double* d_blog = nullptr;       // logged block columns / alpha_B of the current batch's leave-side changes
   int64_t blog_elems = 0;
+  double* d_replay = nullptr;     // outputs of the corrections queued ahead [REPLAY_MAX][OWN_BATCH][2] ...
+  double* h_replay = nullptr;     // ... pinned
+  double* d_rpw = nullptr;        // ... their partial sums
+  int64_t rpw_elems = 0;
+  cudaEvent_t ev_replay = nullptr;
   AlgHook* alg_hook = nullptr;  // set while a commit should launch the append-side correction (append_core)
   double* d_upd2 = nullptr;  // row-deletion workspace of the look-ahead streams (own-cluster scores)
   int64_t upd2_elems = 0;
@@ -1085,7 +1101,10 @@ static int engine_create_impl(int32_t device, bool light, mogp_engine** out) {
                   cudaStreamCreateWithPriority(&h->quick2, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
                   cudaMalloc((void**)&h->d_apring, sizeof(double) * AP_RING * AP_RING_SLOT) != cudaSuccess ||
                   cudaMalloc((void**)&h->d_alg, sizeof(double) * ALG_OUT_SLOTS * 2 * OWN_BATCH) != cudaSuccess ||
-                  cudaMallocHost((void**)&h->h_alg, sizeof(double) * ALG_OUT_SLOTS * 2 * OWN_BATCH) != cudaSuccess)) ||
+                  cudaMallocHost((void**)&h->h_alg, sizeof(double) * ALG_OUT_SLOTS * 2 * OWN_BATCH) != cudaSuccess ||
+                  cudaMalloc((void**)&h->d_replay, sizeof(double) * REPLAY_MAX * 2 * OWN_BATCH) != cudaSuccess ||
+                  cudaMallocHost((void**)&h->h_replay, sizeof(double) * REPLAY_MAX * 2 * OWN_BATCH) != cudaSuccess ||
+                  cudaEventCreateWithFlags(&h->ev_replay, cudaEventDisableTiming) != cudaSuccess)) ||
       cudaEventCreateWithFlags(&h->ev_q2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_alg, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_apq, cudaEventDisableTiming) != cudaSuccess ||
@@ -1172,6 +1191,10 @@ void mogp_engine_destroy(mogp_engine* h) {
   cudaFree(h->d_algw2);
   cudaFree(h->d_alg);
   cudaFree(h->d_blog);
+  cudaFree(h->d_replay);
+  cudaFree(h->d_rpw);
+  if (h->h_replay) cudaFreeHost(h->h_replay);
+  if (h->ev_replay) cudaEventDestroy(h->ev_replay);
   cudaFree(h->d_algw);
   cudaFree(h->d_apring);
   if (h->h_alg) cudaFreeHost(h->h_alg);

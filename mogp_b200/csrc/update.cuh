@@ -204,7 +204,25 @@ struct AlgPos {
   const double *x, *y;        // its visits
   int ncols;
   int thr;                    // which of those columns is the threshold visit (-1: none)
+  // optional: the pair's score as its scoring pass left it ON THE DEVICE.  -inf = excluded before the product (k_prune): only
+  // the threshold column carries T / ss / mu.  (Corrections queued for a batch whose pass is still in flight cannot know
+  // on the host which pairs were excluded; within a batch the host narrows the fields itself and leaves this null.)
+  const double* flag;
 };
+// The columns a correction works on: all of the patient's, or the threshold column alone of an excluded pair.
+__device__ __forceinline__ AlgPos alg_eff(const AlgPos& P) {
+  AlgPos E = P;
+  if (P.flag && *P.flag == -INFINITY && P.thr >= 0 && P.thr < P.ncols) {
+    E.T += (int64_t)P.thr * P.stride;
+    E.ss += P.thr;
+    E.mu += P.thr;
+    E.x += P.thr;
+    E.y += P.thr;
+    E.ncols = 1;
+    E.thr = 0;
+  }
+  return E;
+}
 struct AlgJobs {
   AlgPos pos[OWN_BATCH];
   Theta th;
@@ -250,7 +268,7 @@ constexpr int ALG_THREADS = 512;
 constexpr int ALG_ENTRIES = NG + NP * NP;  // G (packed) | U[a][q]
 // leave, step 1: grid (row tiles from p, patients ahead): partial G and U over 64 rows of the block's columns
 __global__ void __launch_bounds__(256) k_alg_leave_part(const __grid_constant__ AlgJobs J, double* __restrict__ partial) {
-  const AlgPos& P = J.pos[blockIdx.y];
+  const AlgPos P = alg_eff(J.pos[blockIdx.y]);
   __shared__ double sb[TB][NP + 1], sT[TB][NP + 1];
   const int tid = threadIdx.x, n = J.n, nc = P.ncols;
   const int k0 = J.p + blockIdx.x * TB;
@@ -291,7 +309,7 @@ __global__ void __launch_bounds__(256) k_alg_leave_part(const __grid_constant__ 
 // leave, step 2: one CTA per patient ahead: add the partials in a fixed order, G^-1 u, new moments, new score
 __global__ void __launch_bounds__(256) k_alg_leave_fin(const __grid_constant__ AlgJobs J, const double* __restrict__ partial,
                                                        int ntiles) {
-  const AlgPos& P = J.pos[blockIdx.x];
+  const AlgPos P = alg_eff(J.pos[blockIdx.x]);
   __shared__ double G[NG], U[NP][NP + 1], ssn[NP], mun[NP], lpd[NP];
   __shared__ int ok;
   const int tid = threadIdx.x, n = J.n, nc = P.ncols;
@@ -328,7 +346,7 @@ __global__ void __launch_bounds__(256) k_alg_leave_fin(const __grid_constant__ A
 
 // join, step 1: grid (row tiles, patients ahead): partial C[a][q] = sum_k T_B[a][k] T_q[k] over 64 rows
 __global__ void __launch_bounds__(256) k_alg_join_part(const __grid_constant__ AlgJobs J, double* __restrict__ partial) {
-  const AlgPos& P = J.pos[blockIdx.y];
+  const AlgPos P = alg_eff(J.pos[blockIdx.y]);
   __shared__ double sa[TB][NP + 1], sT[TB][NP + 1];
   const int tid = threadIdx.x, n = J.n, nc = P.ncols;
   const int64_t len = P.stride < J.stride_n ? P.stride : J.stride_n;  // both are the cluster's padded size
@@ -351,7 +369,7 @@ __global__ void __launch_bounds__(256) k_alg_join_part(const __grid_constant__ A
 // join, step 2 (after k_append_small): one CTA per patient ahead
 __global__ void __launch_bounds__(256) k_alg_join_fin(const __grid_constant__ AlgJobs J, const double* __restrict__ partial,
                                                       int ntiles) {
-  const AlgPos& P = J.pos[blockIdx.x];
+  const AlgPos P = alg_eff(J.pos[blockIdx.x]);
   __shared__ double C[NP][NP + 1], ssn[NP], mun[NP], lpd[NP];
   const int tid = threadIdx.x, n = J.n, nc = P.ncols;
   {
