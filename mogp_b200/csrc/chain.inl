@@ -904,6 +904,7 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   if (ns > 0)
     TRY(score_device(h, cnt, R, h->d_woff + s0, h->d_wq + cb, h->d_wq + Rtot + cb, ns, b.slots.data(), thr_index, d_score, d_mu,
                      nullptr, nullptr, nullptr, true, &b.pl, &bf.res, do_prune ? &prune : nullptr));
+  CK(h, cudaEventRecord(bf.scored, h->ahead));  // (corrections queued ahead for this batch start from here, replay_launch)
   CK(h, cudaStreamWaitEvent(h->ahead, h->ev_ahead2, 0));
   CK(h, cudaMemcpyAsync(bf.h_out, bf.d_out, sizeof(double) * total, cudaMemcpyDeviceToHost, h->ahead));
   CK(h, cudaEventRecord(h->blocking_sync ? bf.done_blk : bf.done, h->ahead));
@@ -1026,21 +1027,24 @@ int replay_launch(mogp_engine* h, const ChangeLog& L, cudaEvent_t dep) {
   J.logB = J.logAlpha = nullptr;
   double* part = h->d_rpw + w.rpw_used;
   w.rpw_used += wneed;
-  CK(h, cudaStreamWaitEvent(h->ahead, dep, 0));  // what the move contributes (logged copies / Ls^-1, z_B) is in place
+  // on a high-priority stream of their own: behind the pass they correct (its kernels, not its read-back) and behind what
+  // the move contributes (logged copies / Ls^-1, z_B)
+  CK(h, cudaStreamWaitEvent(h->rq, nbf.scored, 0));
+  CK(h, cudaStreamWaitEvent(h->rq, dep, 0));
   if (L.kind == 0) {
-    k_alg_leave_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, h->ahead>>>(J, part);
+    k_alg_leave_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, h->rq>>>(J, part);
     LAUNCHED(h);
-    k_alg_leave_fin<<<(unsigned)nb.cnt, 256, 0, h->ahead>>>(J, part, L.ntiles);
+    k_alg_leave_fin<<<(unsigned)nb.cnt, 256, 0, h->rq>>>(J, part, L.ntiles);
     LAUNCHED(h);
   } else {
-    k_alg_join_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, h->ahead>>>(J, part);
+    k_alg_join_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, h->rq>>>(J, part);
     LAUNCHED(h);
-    k_alg_join_fin<<<(unsigned)nb.cnt, 256, 0, h->ahead>>>(J, part, L.ntiles);
+    k_alg_join_fin<<<(unsigned)nb.cnt, 256, 0, h->rq>>>(J, part, L.ntiles);
     LAUNCHED(h);
   }
   CK(h, cudaMemcpyAsync(h->h_replay + (int64_t)k * 2 * OWN_BATCH, J.out, sizeof(double) * 2 * OWN_BATCH, cudaMemcpyDeviceToHost,
-                        h->ahead));
-  CK(h, cudaEventRecord(h->ev_replay, h->ahead));
+                        h->rq));
+  CK(h, cudaEventRecord(h->ev_replay, h->rq));
   h->bytes_d2h += (int64_t)sizeof(double) * 2 * OWN_BATCH;
   Chain::Window::AsyncItem it;
   it.slot = L.slot;
@@ -1625,6 +1629,7 @@ int mogp_chain_sweep(mogp_engine* h, int64_t n_steps, const int64_t* order, cons
     join_side(h);
     cudaStreamSynchronize(h->ahead);
     cudaStreamSynchronize(h->ahead2);
+    cudaStreamSynchronize(h->rq);
     h->chain.win.open = h->chain.win.in_step = false;
     if (rc != MOGP_OK) return rc;
     if (min_margin) *min_margin = mm;

@@ -188,6 +188,7 @@ struct BatchBuf {
   int64_t out_elems = 0;
   double* h_out = nullptr;
   int64_t hout_elems = 0;
+  cudaEvent_t scored = nullptr;    // the pass's kernels have finished (T / ss / mu of the batch are on the device)
   cudaEvent_t done = nullptr;      // the pass and its read-back have finished (host spins on it)
   cudaEvent_t done_blk = nullptr;  // the same for engines in blocking-sync mode (host sleeps: many chains per process)
 };
@@ -251,6 +252,7 @@ struct mogp_engine {
   double* d_rpw = nullptr;        // ... their partial sums
   int64_t rpw_elems = 0;
   cudaEvent_t ev_replay = nullptr;
+  cudaStream_t rq = nullptr;      // high priority: the corrections queued ahead run as soon as the pass they correct has finished
   AlgHook* alg_hook = nullptr;  // set while a commit should launch the append-side correction (append_core)
   double* d_upd2 = nullptr;  // row-deletion workspace of the look-ahead streams (own-cluster scores)
   int64_t upd2_elems = 0;
@@ -1104,7 +1106,10 @@ static int engine_create_impl(int32_t device, bool light, mogp_engine** out) {
                   cudaMallocHost((void**)&h->h_alg, sizeof(double) * ALG_OUT_SLOTS * 2 * OWN_BATCH) != cudaSuccess ||
                   cudaMalloc((void**)&h->d_replay, sizeof(double) * REPLAY_MAX * 2 * OWN_BATCH) != cudaSuccess ||
                   cudaMallocHost((void**)&h->h_replay, sizeof(double) * REPLAY_MAX * 2 * OWN_BATCH) != cudaSuccess ||
-                  cudaEventCreateWithFlags(&h->ev_replay, cudaEventDisableTiming) != cudaSuccess)) ||
+                  cudaEventCreateWithFlags(&h->ev_replay, cudaEventDisableTiming) != cudaSuccess ||
+                  cudaStreamCreateWithPriority(&h->rq, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+                  cudaEventCreateWithFlags(&h->bb[0].scored, cudaEventDisableTiming) != cudaSuccess ||
+                  cudaEventCreateWithFlags(&h->bb[1].scored, cudaEventDisableTiming) != cudaSuccess)) ||
       cudaEventCreateWithFlags(&h->ev_q2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_alg, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_apq, cudaEventDisableTiming) != cudaSuccess ||
@@ -1177,6 +1182,7 @@ void mogp_engine_destroy(mogp_engine* h) {
     cudaFree(h->bb[i].d_out);
     if (h->bb[i].h_out) cudaFreeHost(h->bb[i].h_out);
     if (h->bb[i].done) cudaEventDestroy(h->bb[i].done);
+    if (h->bb[i].scored) cudaEventDestroy(h->bb[i].scored);
     if (h->bb[i].done_blk) cudaEventDestroy(h->bb[i].done_blk);
   }
   cudaFree(h->d_adraw);
@@ -1195,6 +1201,7 @@ void mogp_engine_destroy(mogp_engine* h) {
   cudaFree(h->d_rpw);
   if (h->h_replay) cudaFreeHost(h->h_replay);
   if (h->ev_replay) cudaEventDestroy(h->ev_replay);
+  if (h->rq) cudaStreamDestroy(h->rq);
   cudaFree(h->d_algw);
   cudaFree(h->d_apring);
   if (h->h_alg) cudaFreeHost(h->h_alg);
