@@ -1232,7 +1232,12 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
   // batch: a second change, a cluster without current T, a new or emptied cluster go the long way (re-scoring).
   const int64_t npos = w.batch_end - (w.cur + 1);
   const bool alg_on = !stays && npos >= 0 && npos <= OWN_BATCH && ch.pending_lazy && env_int("MOGP_RANK_RESCORE", 1) != 0;
-  const bool log_on = alg_on && w.end_launched > w.batch_end && env_int("MOGP_REPLAY", 1) != 0;  // a next batch's pass is in flight
+  // a next batch's pass is in flight: MOGP_REPLAY=1 queues the same corrections for ITS positions (replay_launch).  Off by
+  // default: measured on the 10k-patient chain it removes 58 % of the re-scoring passes and shortens the live pass (426 ->
+  // 385 us), but a cluster corrected that way has no current T for the whole next batch - every patient joining it needs
+  // a product against it first (+6 % launches on the critical path) and no in-batch correction is possible for it -
+  // and the sweep ends up 5 % slower (0.807 vs 0.848 sweeps/s, profiles/README.md).
+  const bool log_on = alg_on && w.end_launched > w.batch_end && env_int("MOGP_REPLAY", 0) != 0;
   auto alg_ok = [&](int32_t slot) {
     return slot >= 0 && slot < (int32_t)w.slot_upto.size() && w.slot_upto[slot] >= w.batch_end && w.slot_T_ok[slot] &&
            !w.slot_alg[slot];

@@ -114,7 +114,7 @@ def test_fast_sweeps_match_oracle(eng, kernel, mean_func, threshold, single_blas
 
 @pytest.mark.parametrize("lookahead,pipeline,env", [(16, 2, {}), (32, 2, {}), (48, 2, {}), (64, 2, {}), (32, 1, {}),
                                                     (48, 2, {"MOGP_RANK_RESCORE": "0"}),   # every change re-scored
-                                                    (48, 2, {"MOGP_REPLAY": "0"}),         # no corrections queued ahead for the next batch
+                                                    (48, 2, {"MOGP_REPLAY": "1"}),         # corrections queued ahead for the next batch's positions
                                                     (48, 2, {"MOGP_LAUNCH_AFTER": "1", "MOGP_ZIGZAG": "1"}),
                                                     (48, 2, {"MOGP_PRUNE": "0"}),          # threshold rule after the product only
                                                     (64, 2, {"MOGP_CHECK_CORRECTIONS": "1"})])
