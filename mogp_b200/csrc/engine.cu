@@ -8,6 +8,7 @@
 //
 // Nothing here falls back to the CPU: every numerical entry point launches kernels of this library
 // and fails with MOGP_ECUDA when there is no device.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -67,6 +68,9 @@ struct Cluster {
   double lml = 0.0, quad = 0.0, logdet = 0.0;
   double grad[4] = {0, 0, 0, 0};
   bool grad_valid = false;
+  TensorMap tmap;                 // 2-D tensor map over M (64-row x 72-double boxes) for the scoring kernel's TMA loads ...
+  const double* tmap_M = nullptr; // ... encoded for this buffer
+  int64_t tmap_cap = 0;           // ... and this leading dimension
   bool side_busy = false;         // a row deletion of this cluster may still be running on the side stream
   bool stat_on_device = false;    // lml / quad / logdet of the last rank update not fetched yet
   bool lml_dirty = false;         // ... and not even reduced yet (k_lml runs when somebody asks)
@@ -179,6 +183,10 @@ struct ScoreRes {
   int zigzag = 0;                  // launch order of the wide kernel's row blocks (ChunkPlan::zigzag)
   SlotView* h_slots = nullptr;     // own pinned staging of those views (null: the engine's upload staging)
   int64_t hslots_cap = 0;
+  TensorMap* d_tmaps = nullptr;    // tensor maps of the launch's slots (TMA loads of the factor tiles)
+  int64_t tmaps_cap = 0;
+  TensorMap* h_tmaps = nullptr;    // own pinned staging of those (passes on the look-ahead stream)
+  int64_t htmaps_cap = 0;
 };
 
 // One batch of the look-ahead pipeline (chain.inl): outputs of its scoring pass, device and pinned host.
@@ -767,6 +775,45 @@ void prof_mark(mogp_engine* h, bool stop) {
   cudaEventRecord(h->prof_ev[h->prof_used++], h->stream);
 }
 
+// ---- tensor maps for the TMA loads of the scoring kernel --------------------------------------------------------------
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn tmap_encoder() {  // the driver entry point, through the runtime (no link against libcuda); null: no TMA path
+  static const TmapEncodeFn fn = [] {
+    const char* e = getenv("MOGP_TMA");
+    if (e && e[0] == '0') return (TmapEncodeFn) nullptr;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) {
+      cudaGetLastError();
+      return (TmapEncodeFn) nullptr;
+    }
+    return (TmapEncodeFn)p;
+  }();
+  return fn;
+}
+// The map of cluster c's factor: a 2-D FP64 tensor (cap x cap, row pitch cap), boxes of 64 rows x LD_K = 72 doubles - the
+// padded shared-memory row of k_score_wide, so a box lands exactly as the [64][LD_K] tile its fragment loads expect.
+bool cluster_tmap(Cluster& c) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc || !c.M) return false;
+  if (c.tmap_M == c.M && c.tmap_cap == c.cap) return true;
+  static_assert(sizeof(TensorMap) == sizeof(CUtensorMap), "tensor map size");
+  const cuuint64_t dims[2] = {(cuuint64_t)c.cap, (cuuint64_t)c.cap};
+  const cuuint64_t strides[1] = {(cuuint64_t)c.cap * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)LD_K, (cuuint32_t)TB}, estr[2] = {1, 1};
+  if (enc(reinterpret_cast<CUtensorMap*>(&c.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, c.M, dims, strides, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    c.tmap_M = nullptr;
+    return false;
+  }
+  c.tmap_M = c.M;
+  c.tmap_cap = c.cap;
+  return true;
+}
+
 template <int BN>
 void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotView* d_slots, const SlotPack& pack,
                        int use_pack, const ChunkPlan& cp) {
@@ -780,12 +827,13 @@ void launch_score_gemm(mogp_engine* h, const ScorePlan& pl, double* Tout, const 
 
 template <int NS>
 void launch_score_wide(mogp_engine* h, const ScorePlan& pl, double* Tout, const SlotView* d_slots, const SlotPack& pack,
-                       int use_pack, const ChunkPlan& cp, const int* colmap = nullptr, const int* ncols = nullptr) {
+                       int use_pack, const ChunkPlan& cp, const int* colmap = nullptr, const int* ncols = nullptr,
+                       const TensorMap* tmaps = nullptr) {
   const int smem = WideSmem<NS>::BYTES;  // (opted into in mogp_engine_create, per device)
   dim3 grid((unsigned)(pl.Rpad / (8 * NS)), (unsigned)pl.n_slots, (unsigned)(pl.max_nb * cp.maxch));
   prof_mark(h, false);
   k_score_wide<NS><<<grid, WIDE_THREADS, smem, h->stream>>>(d_slots, pack, use_pack, pl.kxT, (int)pl.Rpad, pl.part, Tout, cp, colmap,
-                                                            ncols);
+                                                            ncols, tmaps);
   prof_mark(h, true);
   LAUNCHED(h);
 }
@@ -905,6 +953,37 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
     CK(h, cudaMemcpyAsync(res.d_slots, hv, sizeof(SlotView) * (size_t)n_slots, cudaMemcpyHostToDevice, h->stream));
     h->bytes_h2d += (int64_t)sizeof(SlotView) * n_slots;
   }
+  // tensor maps of the slots' factors for the wide kernel's TMA loads (cached per cluster, re-encoded when its buffer moves)
+  const TensorMap* d_tmaps = nullptr;
+  if (pl.BN >= 24 && tmap_encoder()) {
+    TensorMap* hm = nullptr;
+    if (res_in && res_in != &h->res_main && !res.bump) {  // a pass on the look-ahead stream: own pinned staging
+      if (res.htmaps_cap < n_slots) {
+        if (res.h_tmaps) CK(h, cudaFreeHost(res.h_tmaps));
+        res.h_tmaps = nullptr;
+        res.htmaps_cap = 0;
+        CK(h, cudaMallocHost((void**)&res.h_tmaps, sizeof(TensorMap) * (size_t)(n_slots + 16)));
+        res.htmaps_cap = n_slots + 16;
+      }
+      hm = res.h_tmaps;
+    } else {
+      char* up = nullptr;
+      TRY(stage_alloc(h, sizeof(TensorMap) * (size_t)n_slots, &up));
+      hm = reinterpret_cast<TensorMap*>(up);
+    }
+    bool ok = true;
+    for (int s = 0; s < n_slots && ok; ++s) {
+      Cluster& c = h->cl[slots[s]];
+      ok = cluster_tmap(c);
+      if (ok) hm[s] = c.tmap;
+    }
+    if (ok) {
+      TRY(ensure(h, &res.d_tmaps, &res.tmaps_cap, n_slots));
+      CK(h, cudaMemcpyAsync(res.d_tmaps, hm, sizeof(TensorMap) * (size_t)n_slots, cudaMemcpyHostToDevice, h->stream));
+      h->bytes_h2d += (int64_t)sizeof(TensorMap) * n_slots;
+      d_tmaps = res.d_tmaps;
+    }
+  }
   k_kx<<<dim3((unsigned)pl.max_rblk, (unsigned)((pl.Rpad + KX_COLS - 1) / KX_COLS), (unsigned)n_slots), KX_ROWS, 0,
          h->stream>>>(res.d_slots, pack, use_pack, xs_dev, (int)R, (int)pl.Rpad, pl.max_rblk, pl.kxT, pl.mupart);
   LAUNCHED(h);
@@ -917,12 +996,12 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   switch (pl.BN) {  // <= 16 columns: bound by HBM (8-warp ring); wider: bound by the FP64 tensor pipe (16 warps)
     case 8: launch_score_gemm<8>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
     case 16: launch_score_gemm<16>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
-    case 24: launch_score_wide<3>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols); break;
-    case 32: launch_score_wide<4>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols); break;
-    case 40: launch_score_wide<5>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols); break;
-    case 48: launch_score_wide<6>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols); break;
-    case 56: launch_score_wide<7>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols); break;
-    default: launch_score_wide<8>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols); break;
+    case 24: launch_score_wide<3>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols, d_tmaps); break;
+    case 32: launch_score_wide<4>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols, d_tmaps); break;
+    case 40: launch_score_wide<5>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols, d_tmaps); break;
+    case 48: launch_score_wide<6>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols, d_tmaps); break;
+    case 56: launch_score_wide<7>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols, d_tmaps); break;
+    default: launch_score_wide<8>(h, pl, pl.T, res.d_slots, pack, use_pack, cp, d_colmap, d_ncols, d_tmaps); break;
   }
   if (cp.kc > 0) {
     k_score_reduce<<<dim3((unsigned)n_slots, (unsigned)pl.max_nb), 256, 0, h->stream>>>(res.d_slots, pack, use_pack, (int)pl.Rpad, cp,
@@ -1174,6 +1253,8 @@ void mogp_engine_destroy(mogp_engine* h) {
     for (double* p : r.retired) cudaFree(p);
     cudaFree(r.d_slots);
     if (r.h_slots) cudaFreeHost(r.h_slots);
+    cudaFree(r.d_tmaps);
+    if (r.h_tmaps) cudaFreeHost(r.h_tmaps);
   };
   free_res(h->res_main);
   for (int i = 0; i < 2; ++i) {

@@ -17,6 +17,12 @@
 
 namespace mogp {
 
+// A CUtensorMap as the device sees it (128 opaque bytes, 64-byte aligned): the host encodes one per cluster factor
+// (cuTensorMapEncodeTiled, engine.cu) and hands the kernel an array of them, one per slot of the launch.
+struct alignas(64) TensorMap {
+  unsigned char opaque[128];
+};
+
 // Per-slot view used by the batched scoring kernels (array of these lives in device memory).
 struct SlotView {
   const double* M;      // inverse factor, row-major lower, ld
@@ -260,7 +266,7 @@ struct WideSmem {
 template <int NS>
 __device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk, int c0, const double* __restrict__ kxT, int Rpad,
                                           double* __restrict__ part, double* __restrict__ Tout, const ChunkPlan& cp,
-                                          double* smem, double (*red)[8 * NS], const int* cmap, int ncol) {
+                                          double* smem, double (*red)[8 * NS], const int* cmap, int ncol, const void* tmap) {
   constexpr int BN = 8 * NS, MS = 2, WM = 4;
   constexpr int NST = WideSmem<NS>::S, STAGE = WideSmem<NS>::STAGE;
   const int t_begin = chunk * cp.kc;
@@ -284,7 +290,7 @@ __device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk,
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int q = 0; q < NST; ++q) {
-      mbar_init(full + q, WIDE_THREADS);
+      mbar_init(full + q, WIDE_THREADS + (tmap ? 1 : 0));  // every thread's cp.async arrival (+ the TMA issuer's expect_tx)
       mbar_init(empty + q, WIDE_THREADS / 32);
     }
     mbar_init_fence();
@@ -295,7 +301,17 @@ __device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk,
       const int st = tile % NST, use = tile / NST;
       if (use > 0) mbar_wait(empty + st, (use - 1) & 1);
       double* sA = smem + st * STAGE;
-      load_tile_async<LD_K, TB, WIDE_THREADS>(sA, Mrow + (int64_t)tile * TB, sv.ld);
+      if (tmap) {
+        // the 64 x 64 tile of M by TMA: one thread, one instruction - a 64-row x 72-double box of the 2-D map over the
+        // row-major factor lands as the padded [64][LD_K] rows the fragment loads expect (the 8 spill columns fall
+        // into the padding; beyond the matrix edge the unit fills zeros)
+        if (threadIdx.x == 0) {
+          mbar_expect_tx(full + st, TB * LD_K * (uint32_t)sizeof(double));
+          tma_load_2d(sA, tmap, (t_begin + tile) * TB, rb * TB, full + st);
+        }
+      } else {
+        load_tile_async<LD_K, TB, WIDE_THREADS>(sA, Mrow + (int64_t)tile * TB, sv.ld);
+      }
       if (!cmap) {
         load_tile_async<LD_K, BN, WIDE_THREADS>(sA + TB * LD_K, kx + (int64_t)tile * TB, sv.mpad);
       } else {  // the live groups' columns, gathered through the map
@@ -414,9 +430,10 @@ template <int NS>
 __global__ void __launch_bounds__(WIDE_THREADS, 1) k_score_wide(SLOT_ARGS, const double* __restrict__ kxT, int Rpad,
                                                                double* __restrict__ part, double* __restrict__ Tout,
                                                                const ChunkPlan cp, const int* __restrict__ colmap,
-                                                               const int* __restrict__ ncols) {
+                                                               const int* __restrict__ ncols, const TensorMap* __restrict__ tmaps) {
   constexpr int BN = 8 * NS;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem_wide[];  // (128-byte aligned: destination of the TMA boxes)
+  double* smem = smem_wide;
   __shared__ double red[4][BN];
   __shared__ int s_cmap[BN];
   const SlotView sv = SLOT_AT(blockIdx.y);
@@ -431,7 +448,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) k_score_wide(SLOT_ARGS, const
     ncol = ncols[blockIdx.y];
     __syncthreads();
   }
-  wide_item<NS>(sv, rb, chunk, blockIdx.x * BN, kxT, Rpad, part, Tout, cp, smem, red, colmap ? s_cmap : nullptr, ncol);
+  wide_item<NS>(sv, rb, chunk, blockIdx.x * BN, kxT, Rpad, part, Tout, cp, smem, red, colmap ? s_cmap : nullptr, ncol,
+                tmaps ? static_cast<const void*>(tmaps + blockIdx.y) : nullptr);
 }
 
 // The monotonicity rule (mogp_constrained.py:254-266) needs only the predictive MEAN at the patient's first real visit:

@@ -27,8 +27,7 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
-// ---- TMA bulk copies + mbarrier (sm_90+/sm_100a): cp.async.bulk moves whole 512-byte tile rows from global
-// to (padded) shared-memory rows and signals an mbarrier with the byte count; SASS: UBLKCP + SYNCS. ----
+// ---- mbarriers and TMA (sm_90+/sm_100a) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -40,10 +39,12 @@ __device__ __forceinline__ void mbar_init_fence() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+// TMA tile load: one box of the 2-D tensor map (coordinates: c0 = column, c1 = row of its first element) into shared
+// memory, completion counted in bytes on the mbarrier (SASS: UTMALDG).  Issued by ONE thread.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tensor_map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                    smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
