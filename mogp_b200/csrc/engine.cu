@@ -242,6 +242,7 @@ struct mogp_engine {
   BatchBuf bb[2];           // the two batches in flight
   cudaStream_t ahead = nullptr, ahead2 = nullptr;  // low priority: the next batch's pass / its own-cluster scores
   cudaEvent_t ev_fork = nullptr, ev_ahead2 = nullptr;
+  cudaEvent_t ev_pre0 = nullptr, ev_pre1 = nullptr;  // hand-over between the look-ahead stream and the high-priority one (score_device)
   cudaStream_t quick = nullptr, quick2 = nullptr;  // high priority: rank-n score corrections after a move (join / leave side)
   cudaEvent_t ev_q2 = nullptr;
   double* d_algw2 = nullptr;      // partial sums of the join-side correction
@@ -984,14 +985,28 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
       d_tmaps = res.d_tmaps;
     }
   }
-  k_kx<<<dim3((unsigned)pl.max_rblk, (unsigned)((pl.Rpad + KX_COLS - 1) / KX_COLS), (unsigned)n_slots), KX_ROWS, 0,
-         h->stream>>>(res.d_slots, pack, use_pack, xs_dev, (int)R, (int)pl.Rpad, pl.max_rblk, pl.kxT, pl.mupart);
+  // A pass on the look-ahead (lowest priority) stream: its short preamble - the cross covariances and the pruning lists -
+  // runs on the high-priority stream instead, so that it does not queue behind everything else on a busy GPU; only the
+  // long product itself yields to the chain's urgent kernels.  (MOGP_PRE_HI=0: everything on the look-ahead stream.)
+  static const bool pre_hi_on = !(getenv("MOGP_PRE_HI") && getenv("MOGP_PRE_HI")[0] == '0');
+  const bool pre_hi = pre_hi_on && h->rq && res_in && res_in != &h->res_main && !res.bump;
+  cudaStream_t pre = pre_hi ? h->rq : h->stream;
+  if (pre_hi) {
+    CK(h, cudaEventRecord(h->ev_pre0, h->stream));
+    CK(h, cudaStreamWaitEvent(h->rq, h->ev_pre0, 0));
+  }
+  k_kx<<<dim3((unsigned)pl.max_rblk, (unsigned)((pl.Rpad + KX_COLS - 1) / KX_COLS), (unsigned)n_slots), KX_ROWS, 0, pre>>>(
+      res.d_slots, pack, use_pack, xs_dev, (int)R, (int)pl.Rpad, pl.max_rblk, pl.kxT, pl.mupart);
   LAUNCHED(h);
   if (do_prune) {
-    k_prune<<<(unsigned)n_slots, 64, 0, h->stream>>>(res.d_slots, pack, use_pack, n_slots, off_dev, (int)n_pat, xs_dev, (int)pl.Rpad,
-                                                     pl.mupart, pl.max_rblk, thr_index, prune->ythr_dev, prune->threshold, d_colmap,
-                                                     d_ncols, d_flag);
+    k_prune<<<(unsigned)n_slots, 64, 0, pre>>>(res.d_slots, pack, use_pack, n_slots, off_dev, (int)n_pat, xs_dev, (int)pl.Rpad,
+                                               pl.mupart, pl.max_rblk, thr_index, prune->ythr_dev, prune->threshold, d_colmap,
+                                               d_ncols, d_flag);
     LAUNCHED(h);
+  }
+  if (pre_hi) {
+    CK(h, cudaEventRecord(h->ev_pre1, h->rq));
+    CK(h, cudaStreamWaitEvent(h->stream, h->ev_pre1, 0));
   }
   switch (pl.BN) {  // <= 16 columns: bound by HBM (8-warp ring); wider: bound by the FP64 tensor pipe (16 warps)
     case 8: launch_score_gemm<8>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
@@ -1009,11 +1024,19 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
     LAUNCHED(h);
   }
   const int64_t pairs = n_pat * n_slots;
-  k_score_epi<<<(unsigned)((pairs + 7) / 8), 256, 0, h->stream>>>(res.d_slots, pack, use_pack, n_slots, off_dev, n_pat, xs_dev, ys_dev,
+  if (pre_hi) {  // the short epilogue of a look-ahead pass: high priority again (the host is usually waiting for it)
+    CK(h, cudaEventRecord(h->ev_pre0, h->stream));
+    CK(h, cudaStreamWaitEvent(h->rq, h->ev_pre0, 0));
+  }
+  k_score_epi<<<(unsigned)((pairs + 7) / 8), 256, 0, pre>>>(res.d_slots, pack, use_pack, n_slots, off_dev, n_pat, xs_dev, ys_dev,
                                                                      (int)pl.Rpad, pl.part, pl.mupart, pl.max_rblk, pl.mu,
                                                                      thr_index, score_dev,
                                                                      mu_thr_dev, col_mean, col_var, col_lpd, pl.ss, d_flag);
   LAUNCHED(h);
+  if (pre_hi) {
+    CK(h, cudaEventRecord(h->ev_pre1, h->rq));
+    CK(h, cudaStreamWaitEvent(h->stream, h->ev_pre1, 0));
+  }
   CK(h, cudaGetLastError());
   if (plan_out) *plan_out = pl;
   return MOGP_OK;
@@ -1193,6 +1216,8 @@ static int engine_create_impl(int32_t device, bool light, mogp_engine** out) {
       cudaEventCreateWithFlags(&h->ev_alg, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_apq, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_pre0, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_pre1, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_ahead2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->bb[0].done, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->bb[1].done, cudaEventDisableTiming) != cudaSuccess ||
@@ -1270,7 +1295,7 @@ void mogp_engine_destroy(mogp_engine* h) {
   cudaFree(h->d_upd2);
   cudaFree(h->d_own1);
   cudaFree(h->d_own2);
-  for (cudaEvent_t e : {h->ev_main, h->ev_side, h->ev_block, h->ev_fork, h->ev_ahead2, h->ev_alg, h->ev_apq, h->ev_q2})
+  for (cudaEvent_t e : {h->ev_main, h->ev_side, h->ev_block, h->ev_fork, h->ev_ahead2, h->ev_alg, h->ev_apq, h->ev_q2, h->ev_pre0, h->ev_pre1})
     if (e) cudaEventDestroy(e);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->quick) cudaStreamDestroy(h->quick);
