@@ -346,7 +346,7 @@ def run_b200(args):
     # permutation up to the pipeline's column budget, against every active cluster of the final state
     iso = None
     if rank == 0:
-        cols = int(os.environ.get("MOGP_LOOKAHEAD", "48"))
+        cols = int(os.environ.get("MOGP_LOOKAHEAD", "64"))
         take, tot = [], 0
         for n in np.random.RandomState(1).permutation(N):
             ni = int(off[n + 1] - off[n])

@@ -223,7 +223,7 @@ typedef struct mogp_chain_config {
   /* mogp_chain_sweep, fast mode: the sweep order is known in advance, so consecutive patients totalling about
      `lookahead` visits (query columns; the cut is placed where the last group of 8 columns is fullest) are scored against every active cluster in ONE pass over the factors; the
      chain stays sequential (a cached score is used only while its cluster is unchanged, the rest is re-scored).
-     0 = engine default (48), negative = off (one pass per patient), capped at 64.  While the host draws and moves the
+     0 = engine default (64), negative = off (one pass per patient), capped at 64.  While the host draws and moves the
      patients of one batch, the pass of the next batch already runs on a low-priority stream (MOGP_PIPELINE=1 in the
      environment turns that overlap off; MOGP_LOOKAHEAD overrides this field: tuning and tests). */
   int32_t lookahead;

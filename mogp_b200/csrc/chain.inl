@@ -639,7 +639,7 @@ int env_int(const char* name, int dflt) {
 
 int window_cols(const Chain& ch) {
   const int env = env_int("MOGP_LOOKAHEAD", -1);  // (read per sweep: tests and tuning runs toggle it)
-  int v = env >= 0 ? env : (ch.cfg.lookahead == 0 ? 48 : ch.cfg.lookahead);
+  int v = env >= 0 ? env : (ch.cfg.lookahead == 0 ? 64 : ch.cfg.lookahead);
   return v <= 0 ? 0 : std::min(v, 64);
 }
 int pipeline_depth() {  // 2: the next batch's pass overlaps the current batch's moves; 1: one batch at a time
