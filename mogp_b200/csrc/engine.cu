@@ -913,8 +913,9 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   const int64_t mu_total = (int64_t)n_slots * pl.Rpad, mupart_total = mu_total * pl.max_rblk;
   // few (slot, row block) items and one column tile: split the contraction across CTAs (see ChunkPlan)
   ChunkPlan cp;
-  if (pl.Rpad == pl.BN && (int64_t)n_slots * pl.max_nb <= 2 * 148 && pl.max_nb > 8) {
-    cp.kc = 8;
+  static const int split_kc = getenv("MOGP_RESCORE_KC") ? atoi(getenv("MOGP_RESCORE_KC")) : 8;  // tiles per CTA (0: no split)
+  if (split_kc > 0 && pl.Rpad == pl.BN && (int64_t)n_slots * pl.max_nb <= 2 * 148 && pl.max_nb > split_kc) {
+    cp.kc = split_kc;
     cp.maxch = (pl.max_nb + cp.kc - 1) / cp.kc;
   }
   cp.zigzag = cp.kc == 0 ? res.zigzag : 0;
