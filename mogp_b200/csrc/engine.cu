@@ -68,6 +68,10 @@ struct Cluster {
   double lml = 0.0, quad = 0.0, logdet = 0.0;
   double grad[4] = {0, 0, 0, 0};
   bool grad_valid = false;
+  // a collapsed shadow of another cluster (refit lanes): wt = device multiplicities of its points, corr_* = the closed-form
+  // terms that turn its log marginal into the full cluster's (objective_end)
+  const double* wt = nullptr;
+  double corr_n1 = 0.0, corr_logn = 0.0, corr_ss = 0.0;
   TensorMap tmap;                 // 2-D tensor map over M (64-row x 72-double boxes) for the scoring kernel's TMA loads ...
   const double* tmap_M = nullptr; // ... encoded for this buffer
   int64_t tmap_cap = 0;           // ... and this leading dimension
@@ -290,6 +294,8 @@ struct mogp_engine {
   // lanes of the refit driver (mogp_refit_clusters): light worker engines (one stream + factorisation workspace each),
   // all driven by the caller's thread
   bool light = false;
+  double* d_wt = nullptr;  // a lane's copy of the multiplicities of the collapsed cluster it is evaluating
+  int64_t wt_elems = 0;
   std::vector<mogp_engine*> lanes;
   std::vector<cudaEvent_t> lane_ev;
   int64_t refit_evals = 0, refit_launched = 0;   // objective evaluations requested / actually run on the device
@@ -308,7 +314,7 @@ struct mogp_engine {
   // L-BFGS-B evaluation of the same cluster; keyed by the buffers it touches
   cudaGraph_t eval_graph = nullptr;
   cudaGraphExec_t eval_exec = nullptr;
-  const void* eval_key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const void* eval_key[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int64_t eval_kernels = 0;
   // accounting (bench.py): bytes moved by the C ABI calls, and device time of the scoring GEMM
   int64_t bytes_h2d = 0, bytes_d2h = 0;
@@ -637,7 +643,7 @@ int infer(mogp_engine* h, Cluster& c) {
   double jitter = 0.0;
   for (int attempt = 0;; ++attempt) {
     CK(h, cudaMemsetAsync(info, 0, sizeof(int), h->stream));
-    k_build<<<dim3(nb, nb), NTHREADS, 0, h->stream>>>(h->d_L, c.M, ld, c.x(), (int)c.m, th, jitter);
+    k_build<<<dim3(nb, nb), NTHREADS, 0, h->stream>>>(h->d_L, c.M, ld, c.x(), (int)c.m, th, jitter, c.wt);
     LAUNCHED(h);
     launch_factor(h, h->d_L, c.M, ld, nb, info);
     k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, ld, c.x(), c.y(), (int)c.m, th, c.z());
@@ -692,7 +698,7 @@ int infer_grad(mogp_engine* h, Cluster& c) {
   const Theta* th = c.theta_dev();
   double* st = c.stat();
   k_grad<<<dim3(nb, nb, nz), NTHREADS, GRAD_SMEM, h->stream>>>(c.M, c.cap, nb, c.x(), c.alpha(), (int)c.m, th,
-                                                                h->d_partial, grad_kc());
+                                                                h->d_partial, grad_kc(), c.wt);
   LAUNCHED(h);
   k_grad_final<<<1, 256, 0, h->stream>>>(h->d_partial, (int)n_partial, th, st, st + 10);
   LAUNCHED(h);
@@ -1293,6 +1299,7 @@ void mogp_engine_destroy(mogp_engine* h) {
     if (h->bb[i].done_blk) cudaEventDestroy(h->bb[i].done_blk);
   }
   cudaFree(h->d_adraw);
+  cudaFree(h->d_wt);
   cudaFree(h->d_upd2);
   cudaFree(h->d_own1);
   cudaFree(h->d_own2);
@@ -1736,7 +1743,7 @@ static int eval_launch(mogp_engine* h, Cluster& c, bool* launched) {
   TRY(ensure_pin(h, 256));
   TRY(sync_theta(h, c));
   double* st = c.stat();
-  const void* key[6] = {c.M, c.vec, h->d_L, h->d_apart, h->d_partial, reinterpret_cast<const void*>((intptr_t)c.m)};
+  const void* key[7] = {c.M, c.vec, h->d_L, h->d_apart, h->d_partial, reinterpret_cast<const void*>((intptr_t)c.m), c.wt};
   if (!h->eval_exec || memcmp(key, h->eval_key, sizeof key) != 0) {
     if (h->eval_graph) cudaGraphDestroy(h->eval_graph);
     h->eval_graph = nullptr;
@@ -1745,13 +1752,13 @@ static int eval_launch(mogp_engine* h, Cluster& c, bool* launched) {
     int* info = reinterpret_cast<int*>(st + 8);
     const Theta* th = c.theta_dev();
     cudaMemsetAsync(info, 0, sizeof(int), h->stream);
-    k_build<<<dim3(nb, nb), NTHREADS, 0, h->stream>>>(h->d_L, c.M, ld, c.x(), (int)c.m, th, 0.0);
+    k_build<<<dim3(nb, nb), NTHREADS, 0, h->stream>>>(h->d_L, c.M, ld, c.x(), (int)c.m, th, 0.0, c.wt);
     LAUNCHED(h);
     launch_factor(h, h->d_L, c.M, ld, nb, info);
     k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, ld, c.x(), c.y(), (int)c.m, th, c.z());
     LAUNCHED(h);
     int rc = launch_alpha_lml(h, c);
-    k_grad<<<dim3(nb, nb, nz), NTHREADS, GRAD_SMEM, h->stream>>>(c.M, c.cap, nb, c.x(), c.alpha(), (int)c.m, th, h->d_partial, grad_kc());
+    k_grad<<<dim3(nb, nb, nz), NTHREADS, GRAD_SMEM, h->stream>>>(c.M, c.cap, nb, c.x(), c.alpha(), (int)c.m, th, h->d_partial, grad_kc(), c.wt);
     LAUNCHED(h);
     k_grad_final<<<1, 256, 0, h->stream>>>(h->d_partial, (int)n_partial, th, st, st + 10);
     LAUNCHED(h);
@@ -1867,11 +1874,16 @@ static int objective_end(mogp_engine* hw, Cluster& c, bool launched, double* f, 
     dlp[i] = (pr[i].a - 1.0) / th - pr[i].b + 1.0 / expm1(th);
   }
   TRY(fetch_stat(h, c));
-  if (f) *f = -c.lml - lp;
+  // a collapsed shadow: n identical observations = one with noise s / n, times (2 pi s)^-(n-1)/2 n^-1/2 exp(-SS / 2s) per
+  // group, s = noise + 1e-8 (zeros for an ordinary cluster)
+  const double sn = c.theta[3] + GPY_JITTER;
+  const double corr = -(0.5 * c.corr_n1 * log(2.0 * M_PI * sn) + c.corr_logn + 0.5 * c.corr_ss / sn);
+  const double dcorr = -(0.5 * c.corr_n1 / sn - 0.5 * c.corr_ss / (sn * sn));
+  if (f) *f = -(c.lml + corr) - lp;
   if (g) {
     int q = 0;
     for (int i = 0; i < 4; ++i)
-      if (!fixed[i]) g[q++] = -(c.grad[i] + dlp[i]) * logexp_gradfactor(c.theta[i]);
+      if (!fixed[i]) g[q++] = -(c.grad[i] + (i == 3 ? dcorr : 0.0) + dlp[i]) * logexp_gradfactor(c.theta[i]);
   }
   return MOGP_OK;
 }

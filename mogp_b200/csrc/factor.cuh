@@ -50,9 +50,13 @@ __device__ __forceinline__ double kern_diag(const Theta& th, double x) {
 // grid (nb, nb): x = block column, y = block row; CTAs above the diagonal exit.
 // (theta is read from device memory - the cluster's stat block - so that a captured CUDA graph of the whole
 // evaluation can be relaunched at new hyper-parameters without touching its nodes)
+// wt (optional): multiplicity of each point.  n identical observations (same input, here also the same residual mean) are
+// ONE pseudo-observation with noise (noise + 1e-8) / n (plus closed-form terms in the log marginal, engine.cu): the refit's
+// evaluations run on the cluster with its repeated inputs collapsed - every patient brings the same onset anchor, ~13 % of a
+// cluster's rows - and on nothing else.
 __global__ void __launch_bounds__(NTHREADS) k_build(double* __restrict__ L, double* __restrict__ M, int64_t ld,
                                                     const double* __restrict__ x, int m, const Theta* __restrict__ thp,
-                                                    double jitter) {
+                                                    double jitter, const double* __restrict__ wt) {
   const int bj = blockIdx.x, bi = blockIdx.y;
   if (bj > bi) return;
   const Theta th = *thp;
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(NTHREADS) k_build(double* __restrict__ L, doub
     if (j <= i) {
       if (i < m) {
         v = kern_eval(th, sxi[a], sxj[b], i == j, nullptr);
-        if (i == j) v = __dadd_rn(v, __dadd_rn(th.noise, GPY_JITTER)) + jitter;
+        if (i == j) v = (wt ? v + __dadd_rn(th.noise, GPY_JITTER) / wt[i] : __dadd_rn(v, __dadd_rn(th.noise, GPY_JITTER))) + jitter;
       } else {
         v = (i == j) ? 1.0 : 0.0;
       }
@@ -503,7 +507,7 @@ constexpr int GRAD_SMEM = (2 * TB * LD_R) * (int)sizeof(double);
 __global__ void __launch_bounds__(NTHREADS) k_grad(const double* __restrict__ M, int64_t ld, int nb,
                                                    const double* __restrict__ x, const double* __restrict__ alpha,
                                                    int m, const Theta* __restrict__ thp, double* __restrict__ partial,
-                                                   int kchunk) {
+                                                   int kchunk, const double* __restrict__ wt) {
   const Theta th = *thp;
   const int bj = blockIdx.x, bi = blockIdx.y, kc = blockIdx.z;
   const int cta = (kc * gridDim.y + bi) * gridDim.x + bj;
@@ -554,7 +558,7 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(const double* __restrict__ M,
       if (th.kernel == 1) kij = 1.0;
       s0 += f * dl * kij;
       s1 += f * dl * kij * r2;
-      if (i == j) s2 += dl;
+      if (i == j) s2 += wt ? dl / wt[i] : dl;  // d Ky_ii / d noise = 1 / multiplicity
     }
   });
 #pragma unroll

@@ -21,7 +21,66 @@ struct RefitJob {
   int lane = -1;
   int64_t seq = 0;        // launch order (the oldest launch is waited for when nothing has finished)
   int rc = MOGP_OK;
+  bool collapsed = false; // the optimiser's evaluations run on the lane's shadow of the cluster (repeated inputs merged)
 };
+
+// Repeated inputs.  Every patient contributes the same onset anchor (x = 0), so ~1/8 of a cluster's points share one input;
+// n observations at the same input are ONE observation of their mean with noise s / n, times a factor that does not involve
+// the GP: prod_i N(y_i | f, s) = N(ybar | f, s / n) (2 pi s)^-(n-1)/2 n^-1/2 exp(-SS / 2s), s = noise + 1e-8.  The optimiser's
+// evaluations - full factorisations, O(m^3) - therefore run on a SHADOW of the cluster with every group of identical inputs
+// merged (m' ~ 0.87 m: a third fewer flops), owned by the lane: weights in k_build / k_grad, the closed-form factor and its
+// noise derivative added on the host (objective_end).  Same objective and gradient as the full cluster to rounding (~1e-12);
+// the last evaluation, f(x_opt), runs on the cluster itself and leaves it with its factor at the optimum.
+static int refit_make_shadow(mogp_engine* lane, const Cluster& c, bool* made) {
+  *made = false;
+  static const bool on = !(getenv("MOGP_COLLAPSE") && getenv("MOGP_COLLAPSE")[0] == '0');
+  const int64_t m = c.m;
+  if (!on || m < 2 * TB || (int64_t)c.hx.size() != m || (int64_t)c.hy.size() != m) return MOGP_OK;
+  std::vector<int64_t> idx(m);
+  for (int64_t i = 0; i < m; ++i) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return c.hx[a] < c.hx[b]; });
+  std::vector<double> xg, yg, wg;
+  double n1 = 0.0, logn = 0.0, ss = 0.0;
+  for (int64_t i = 0; i < m;) {
+    int64_t j = i;
+    double sum = 0.0;
+    while (j < m && c.hx[idx[j]] == c.hx[idx[i]]) sum += c.hy[idx[j++]];
+    const double n = (double)(j - i), mean = sum / n;
+    double dev = 0.0;
+    for (int64_t q = i; q < j; ++q) dev += (c.hy[idx[q]] - mean) * (c.hy[idx[q]] - mean);
+    xg.push_back(c.hx[idx[i]]);
+    yg.push_back(mean);
+    wg.push_back(n);
+    n1 += n - 1.0;
+    logn += 0.5 * log(n);
+    ss += dev;
+    i = j;
+  }
+  const int64_t m2 = (int64_t)xg.size();
+  if (m2 * 20 > m * 19) return MOGP_OK;  // fewer than 5 % of the points merge: not worth a second factor at the end
+  mogp_engine* h = lane;
+  if (lane->cl.empty()) {
+    int32_t slot = -1;
+    TRY(cluster_create_i(lane, &c.spec, c.theta, &slot));
+  }
+  Cluster& sh = lane->cl[0];
+  sh.spec = c.spec;
+  memcpy(sh.theta, c.theta, sizeof(double) * 4);
+  sh.theta_dirty = true;
+  TRY(upload_data(lane, sh, m2, xg.data(), yg.data()));
+  TRY(ensure(lane, &lane->d_wt, &lane->wt_elems, m2));
+  char* up = nullptr;
+  TRY(stage_alloc(lane, sizeof(double) * (size_t)m2, &up));
+  memcpy(up, wg.data(), sizeof(double) * (size_t)m2);
+  CK(h, cudaMemcpyAsync(lane->d_wt, up, sizeof(double) * (size_t)m2, cudaMemcpyHostToDevice, lane->stream));
+  lane->bytes_h2d += (int64_t)sizeof(double) * m2;
+  sh.wt = lane->d_wt;
+  sh.corr_n1 = n1;
+  sh.corr_logn = logn;
+  sh.corr_ss = ss;
+  *made = true;
+  return MOGP_OK;
+}
 
 static int refit_lanes(mogp_engine* h, int want) {
   while ((int)h->lanes.size() < want) {
@@ -43,9 +102,10 @@ static int refit_lanes(mogp_engine* h, int want) {
 // Run job j forward until it has an evaluation in flight (returns with j.launched) or is done.
 static int refit_advance(mogp_engine* h, RefitJob& j, int64_t* seq) {
   mogp_engine* lane = h->lanes[j.lane];
-  Cluster& c = h->cl[j.slot];
   for (;;) {
     if (j.phase == 2) return MOGP_OK;
+    // the optimiser's evaluations on the lane's collapsed shadow, the closing f(x_opt) on the cluster itself
+    Cluster& c = (j.collapsed && j.phase == 0) ? lane->cl[0] : h->cl[j.slot];
     double f = 0.0, g[4] = {0, 0, 0, 0};
     int rc;
     if (!j.launched) {  // queue the evaluation at the optimiser's current point
@@ -147,6 +207,13 @@ int mogp_refit_clusters(mogp_engine* h, int32_t n_slots, const int32_t* slots, i
       j.opt.init(j.nfree, t0);
       j.opt.step();  // -> T_FG at t0
       j.lane = lane;
+      {
+        int rcs = refit_make_shadow(h->lanes[lane], c, &j.collapsed);
+        if (rcs != MOGP_OK) {
+          h->err = h->lanes[lane]->err;
+          return rcs;
+        }
+      }
       lane_job[lane] = (int)(&j - jobs.data());
       int rc = refit_advance(h, j, &seq);
       if (rc != MOGP_OK) return rc;

@@ -208,6 +208,33 @@ def test_refit_reaches_the_oracle_optimum(eng):
     eng.cluster_free(slot)
 
 
+@pytest.mark.parametrize("case", [('rbf', True, True, False, (0.3, 1.0, 3.0, 0.3), 300),
+                                  ('rbf', False, False, False, (0.0, 0.8, 2.0, 0.1), 520),
+                                  ('linear', True, True, False, (0.4, 1.0, 1.0, 0.5), 260)],
+                         ids=lambda c: "{}-mf{}-m{}".format(c[0], int(c[1]), c[5]))
+def test_refit_with_repeated_inputs_collapsed(eng, case):
+    """Clusters of >= 128 points with > 5 % repeated inputs (every patient's onset anchor): the native refit evaluates
+    the optimiser's points on a collapsed shadow (refit.inl: one weighted observation per distinct input + a closed-form
+    factor) and the closing f(x_opt) on the cluster itself.  Same optimum, same objective, same number of evaluations
+    as the oracle's SciPy L-BFGS-B on the full data; the cluster is left with a valid factor at the optimum."""
+    o, slot, spec, rs = build_pair(eng, case, seed=11)
+    n0 = o.n_evals
+    o.optimize()
+    c0 = eng.refit_counters()
+    evals = eng.refit_clusters([slot])
+    c1 = eng.refit_counters()
+    assert c1["launched"] > c0["launched"]
+    th = eng.cluster_get_theta(slot)
+    assert np.allclose(th, o.param_array, rtol=2e-6)
+    assert rel(eng.cluster_loglik(slot), o.log_likelihood()) < 1e-9
+    assert int(evals[0]) == o.n_evals - n0          # the optimiser's evaluations + the closing f(x_opt)
+    xs = rs.uniform(0, 8, 5)
+    mu, var = eng.cluster_predict(slot, xs)
+    mo, vo = o.predict(xs.reshape(-1, 1))
+    assert rel(mu, mo.ravel()) < 1e-7 and rel(var, vo.ravel()) < 1e-7
+    eng.cluster_free(slot)
+
+
 def test_worker_engine_objective_and_concurrent_refits(eng):
     """mogp_cluster_objective_on: a cluster of one engine evaluated on another engine's stream - first at the
     cluster's CURRENT theta (the owner's factor is reused, only the gradient runs on the worker), then at a new one;

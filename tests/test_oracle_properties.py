@@ -114,3 +114,42 @@ def test_rank_n_score_identities_against_refactorisation():
         assert np.allclose(rank_updates.alpha_after_join(M, alpha, T_B, S_BB, yb - mu_b), ref._alpha[:, 0], rtol=1e-9, atol=1e-11)
         ref = GPRegressionOracle(x[keep], y[keep], kernel_name=kernel, noise_variance=0.3, a_draw=0.4, lengthscale=2.5)
         assert np.allclose(rank_updates.alpha_after_leave(M, alpha, rows), ref._alpha[:, 0], rtol=1e-9, atol=1e-11)
+
+
+def test_repeated_inputs_collapse_identity():
+    """The identity the native refit's shadow clusters rest on (mogp_b200/csrc/refit.inl): n observations at one input are one
+    observation of their mean with noise s / n, times (2 pi s)^-(n-1)/2 n^-1/2 exp(-SS / 2s), s = noise + 1e-8 (GPy's diagonal
+    jitter rides with the noise).  LML and d LML / d noise of the oracle on the full data = weighted GP on the merged data +
+    the closed-form term."""
+    rs = np.random.RandomState(5)
+    m = 90
+    x = np.sort(rs.uniform(0, 8, m))
+    x[:20] = 0.0
+    x[40:43] = x[40]
+    y = (48 - 6 * x + rs.randn(m) * 3 - 30) / 20
+    o = GPRegressionOracle(x.reshape(-1, 1), y.reshape(-1, 1), kernel_name='rbf', signal_variance=0.8,
+                           signal_variance_fix=False, noise_variance=0.3, noise_variance_fix=False, mean_func=False,
+                           lengthscale=2.0, a_draw=None)
+    lml_full = o.log_likelihood()
+    d_noise_full = o._grad_lml[-1]
+    xu, inv, cnt = np.unique(x, return_inverse=True, return_counts=True)
+    ybar = np.bincount(inv, weights=y) / cnt
+    ss = np.sum((y - ybar[inv]) ** 2)
+    s = 0.3 + 1e-8
+    K = 0.8 * np.exp(-0.5 * (xu[:, None] - xu[None, :]) ** 2 / 2.0 ** 2)
+
+    def collapsed(s):
+        Ky = K + np.diag(s / cnt)
+        L = np.linalg.cholesky(Ky)
+        a = np.linalg.solve(Ky, ybar)
+        lml = -0.5 * len(xu) * np.log(2 * np.pi) - np.sum(np.log(np.diag(L))) - 0.5 * ybar @ a
+        n1 = np.sum(cnt - 1.0)
+        corr = -(0.5 * n1 * np.log(2 * np.pi * s) + 0.5 * np.sum(np.log(cnt)) + 0.5 * ss / s)
+        Ki = np.linalg.inv(Ky)
+        dl = 0.5 * (np.outer(a, a) - Ki)
+        d = np.sum(np.diag(dl) / cnt) - (0.5 * n1 / s - 0.5 * ss / s ** 2)
+        return lml + corr, d
+
+    lml_c, d_c = collapsed(s)
+    assert lml_c == pytest.approx(lml_full, rel=1e-11)
+    assert d_c == pytest.approx(d_noise_full, rel=1e-9)
