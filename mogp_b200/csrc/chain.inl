@@ -7,6 +7,73 @@ int env_int_once(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+// ---- cached columns kept current on the device (look-ahead pipeline, MOGP_TMAINT) ----
+// A move changes two clusters.  The columns T_q = M k_q (and ss, mu) the scoring passes left on the device for the patients
+// still ahead are brought to the changed cluster by O(m n) kernels - k_alg_leave_fin / k_alg_join_fin write ss', mu' (and the
+// rows a join adds) back, k_T_leave applies a deletion's row operations - instead of being recomputed by an O(m^2) product
+// against the updated factor.  Readers and writers of the columns of one (batch, slot) run on several streams; each waits
+// for the event of the one before it (t_wait) and leaves its own (t_mark).
+bool tmaint_on() {  // (read per call: tests toggle it)
+  const char* e = getenv("MOGP_TMAINT");
+  return !(e && e[0] == '0');
+}
+int t_wait(mogp_engine* h, cudaStream_t s, int bi, int32_t slot) {
+  const std::vector<int>& v = h->chain.win.slot_tev[bi];
+  if (slot < 0 || (size_t)slot >= v.size() || v[slot] < 0) return MOGP_OK;
+  CK(h, cudaStreamWaitEvent(s, h->tev[v[slot]], 0));
+  return MOGP_OK;
+}
+int t_mark(mogp_engine* h, cudaStream_t s, int bi, int32_t slot) {
+  std::vector<int>& v = h->chain.win.slot_tev[bi];
+  if (slot < 0) return MOGP_OK;
+  if ((size_t)slot >= v.size()) v.resize((size_t)slot + 1, -1);
+  const int k = h->tev_next;
+  h->tev_next = (k + 1) % TEV_RING;
+  if (!h->tev[k]) CK(h, cudaEventCreateWithFlags(&h->tev[k], cudaEventDisableTiming));
+  CK(h, cudaEventRecord(h->tev[k], s));
+  v[slot] = k;
+  return MOGP_OK;
+}
+
+// remove_core, right after k_rm_prep: k_T_leave for the targets the step asked for, from a private copy of the deletion's
+// operands (the workspace itself is rewritten by the next patient's Gram).
+int fire_leave_hook(mogp_engine* h, const RmGeom& g, const RmWork& w, int nT) {
+  LeaveHook* hk = h->leave_hook;
+  h->leave_hook = nullptr;
+  if (hk->npos[0] <= 0 && hk->npos[1] <= 0) return MOGP_OK;
+  const int64_t used = (w.S + (int64_t)nT * TB * TB) - w.Bt;
+  if (!h->d_tsw || used > h->tsw_slot) return MOGP_OK;  // not fired: the step falls back to re-scoring
+  const int k = h->tsw_next;
+  h->tsw_next = (k + 1) % TS_RING;
+  for (int t = 0; t < 2; ++t)
+    if (h->tsw_done[k][t]) CK(h, cudaStreamWaitEvent(h->stream, h->tsw_done[k][t], 0));
+  double* dst = h->d_tsw + (int64_t)k * h->tsw_slot;
+  CK(h, cudaMemcpyAsync(dst, w.Bt, sizeof(double) * (size_t)used, cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaEventRecord(h->tsw_cp, h->stream));
+  RmWork wc = w;
+  wc.Bt = dst;
+  wc.Gt = dst + (w.Gt - w.Bt);
+  wc.u = dst + (w.u - w.Bt);
+  wc.Pgram = dst + (w.Pgram - w.Bt);
+  wc.Gc = dst + (w.Gc - w.Bt);
+  wc.own = dst + (w.own - w.Bt);
+  wc.gsol = dst + (w.gsol - w.Bt);
+  wc.S = dst + (w.S - w.Bt);
+  for (int t = 0; t < 2; ++t) {
+    if (hk->npos[t] <= 0) continue;
+    cudaStream_t s = t == 0 ? h->ts0 : h->ts1;
+    CK(h, cudaStreamWaitEvent(s, h->tsw_cp, 0));
+    TRY(t_wait(h, s, hk->bi[t], hk->slot));
+    k_T_leave<<<(unsigned)hk->npos[t], NTHREADS, RM_STRIP_SMEM, s>>>(hk->J[t], g, wc);
+    LAUNCHED(h);
+    TRY(t_mark(h, s, hk->bi[t], hk->slot));
+    if (!h->tsw_done[k][t]) CK(h, cudaEventCreateWithFlags(&h->tsw_done[k][t], cudaEventDisableTiming));
+    CK(h, cudaEventRecord(h->tsw_done[k][t], s));
+    hk->fired[t] = true;
+  }
+  return MOGP_OK;
+}
+
 // ---- buffer pool: clusters own one buffer of cap*cap + 4*cap + 16 doubles; row deletions ping-pong ----
 int pool_get(mogp_engine* h, int64_t cap, double** out) {
   for (size_t i = 0; i < h->pool.size(); ++i)
@@ -69,8 +136,9 @@ int fetch_stat(mogp_engine* h, Cluster& c) {
 
 // Append n <= NP points whose T = M Kx (n columns x mpad) and predictive means are already on the device.
 int append_core(mogp_engine* h, Cluster& c, int n, const double* xB_dev, const double* yB_dev, const double* T_dev,
-                const double* mu_dev) {
+                const double* mu_dev, int64_t t_stride = 0) {
   const int64_t m = c.m, mpad_old = round_up(m, TB), mnew = m + n, mpad_new = round_up(mnew, TB);
+  if (t_stride <= 0) t_stride = mpad_old;  // (columns kept current across changes keep the stride they were computed with)
   order_after_side(h, c);
   const bool reserved = mnew > c.cap;
   if (reserved) TRY(cluster_reserve(h, c, mnew, true));
@@ -104,11 +172,12 @@ int append_core(mogp_engine* h, Cluster& c, int n, const double* xB_dev, const d
     hk->on_quick = on_quick;
     if (hk->npos > 0) {
       TRY(ensure(h, &h->d_algw2, &h->algw2_elems, (int64_t)hk->npos * hk->ntiles * NP * NP));
+      TRY(t_wait(h, s1, hk->bi, hk->slot));
       k_alg_join_part<<<dim3((unsigned)hk->ntiles, (unsigned)hk->npos), 256, 0, s1>>>(hk->jobs, h->d_algw2);
       LAUNCHED(h);
     }
   }
-  k_append_gram<<<nblk, 256, 0, s1>>>(T_dev, (int)mpad_old, n, w);
+  k_append_gram<<<nblk, 256, 0, s1>>>(T_dev, (int)mpad_old, t_stride, n, w);
   LAUNCHED(h);
   k_append_small<<<1, 256, 0, s1>>>(mu_dev, nblk, xB_dev, yB_dev, n, th, w, info);
   LAUNCHED(h);
@@ -122,11 +191,12 @@ int append_core(mogp_engine* h, Cluster& c, int n, const double* xB_dev, const d
     if (hk->npos > 0) {
       k_alg_join_fin<<<hk->npos, 256, 0, s1>>>(hk->jobs, h->d_algw2, hk->ntiles);
       LAUNCHED(h);
+      if (hk->jobs.maintain) TRY(t_mark(h, s1, hk->bi, hk->slot));
     }
     CK(h, cudaEventRecord(h->ev_alg, s1));
     hk->fired = true;
   }
-  k_append_rows<<<dim3(nb, APPEND_KS), NTHREADS, AP_ROWS_SMEM, h->stream>>>(c.M, c.cap, nb, (int)mpad_old, T_dev, n, w);
+  k_append_rows<<<dim3(nb, APPEND_KS), NTHREADS, AP_ROWS_SMEM, h->stream>>>(c.M, c.cap, nb, (int)mpad_old, T_dev, t_stride, n, w);
   LAUNCHED(h);
   if (mpad_new > mpad_old) {
     k_pad_identity<<<64, 256, 0, h->stream>>>(c.M, c.cap, (int)mpad_old, (int)mpad_new);
@@ -222,6 +292,7 @@ int remove_core(mogp_engine* h, Cluster& c, int64_t p, int n) {
   double* nM = nbuf;
   double* nvec = nbuf + c.cap * c.cap;
   static const int legacy = env_int_once("MOGP_RM_LEGACY", 0);  // 1: the three-pass deletion (hpart / hscan / apply)
+  if (h->leave_hook) TRY(fire_leave_hook(h, g, w, nT));
   if (!legacy) {
     // one pass over the factor: strip walk with the prefix carried along (k_rm_strip), alpha / x / y / stat in its epilogue
     k_rm_strip<<<g.nbn * (TB / RM_SW), NTHREADS, RM_STRIP_SMEM, h->stream>>>(c.M, nM, g, w, c.vec, nvec, c.cap);
@@ -481,15 +552,17 @@ int chain_score(mogp_engine* h, double a_draw) {
 }
 
 // Where the scoring pass left T = M Kx (and the predictive means) of the pending patient under `slot`.
-void locate_T(mogp_engine* h, int32_t slot, const double** T, const double** mu) {
+void locate_T(mogp_engine* h, int32_t slot, const double** T, const double** mu, int64_t* stride) {
   Chain& ch = h->chain;
   *T = *mu = nullptr;
+  *stride = 0;  // (0: the slot's padded size, append_core)
   if (ch.win.in_step) {
     const Chain::Window& w = ch.win;
     if (slot >= 0 && slot < (int32_t)w.slot_upto.size() && w.slot_upto[slot] > w.cur && w.slot_T_ok[slot] &&
-        slot < (int32_t)w.e[w.cur].size()) {
+        slot < (int32_t)w.e[w.cur].size() && !w.e[w.cur][slot].pruned) {
       *T = w.e[w.cur][slot].T;
       *mu = w.e[w.cur][slot].mu;
+      *stride = w.e[w.cur][slot].stride;
     }
     return;
   }
@@ -579,7 +652,12 @@ int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_n
       if (ch.cfg.fast_updates && c.valid && ni > 0 && ni <= NP) {
         // T = M Kx and the predictive means of this cluster are still in the scoring scratch
         const double *Tc = nullptr, *muc = nullptr;
-        locate_T(h, ch.slot_of_id[chosen_id], &Tc, &muc);
+        int64_t t_stride = 0;
+        locate_T(h, ch.slot_of_id[chosen_id], &Tc, &muc, &t_stride);
+        if (Tc && ch.win.in_step) {  // columns kept current by kernels on other streams: behind the last of them
+          TRY(t_wait(h, h->main_stream, ch.win.cur_bi, ch.slot_of_id[chosen_id]));
+          TRY(t_wait(h, h->quick, ch.win.cur_bi, ch.slot_of_id[chosen_id]));
+        }
         if (!Tc && ch.win.in_step) {
           // the cached T under this cluster is stale (its scores were corrected by a rank-n formula): one product
           // against this cluster alone, queued behind the update that made it stale
@@ -589,9 +667,10 @@ int chain_commit(mogp_engine* h, int32_t chosen_id, double a_draw, int32_t* is_n
                            nullptr, true, &pl1));
           Tc = pl1.T;
           muc = pl1.mu;
+          t_stride = 0;
         }
         if (Tc) {
-          TRY(append_core(h, c, (int)ni, h->d_px + c0, h->d_py + c0, Tc, muc));
+          TRY(append_core(h, c, (int)ni, h->d_px + c0, h->d_py + c0, Tc, muc, t_stride));
           c.hx.insert(c.hx.end(), h->h_x.begin() + c0, h->h_x.begin() + c0 + ni);
           c.hy.insert(c.hy.end(), h->h_y.begin() + c0, h->h_y.begin() + c0 + ni);
           c.members.push_back(n);
@@ -653,6 +732,10 @@ void win_size_slots(Chain::Window& w, size_t n) {
   w.slot_T_ok.resize(n, 0);
   w.slot_alg.resize(n, 0);
   w.slot_epoch.resize(n, 0);
+  w.slot_tev[0].resize(n, -1);
+  w.slot_tev[1].resize(n, -1);
+  w.rp_epoch.resize(n, -1);
+  w.rp_last.resize(n, -1);
 }
 
 // The cluster in `slot` changed (rows appended / deleted, freed, created): cached scores under it are stale.
@@ -755,6 +838,10 @@ int win_prepare(mogp_engine* h, int64_t n_steps, const int64_t* order, const dou
   w.slot_T_ok.assign(h->cl.size(), 0);
   w.slot_alg.assign(h->cl.size(), 0);
   w.slot_epoch.assign(h->cl.size(), 0);
+  w.slot_tev[0].assign(h->cl.size(), -1);
+  w.slot_tev[1].assign(h->cl.size(), -1);
+  w.rp_epoch.assign(h->cl.size(), -1);
+  w.rp_last.assign(h->cl.size(), -1);
   w.batch_end = 0;
   w.async_items.clear();
   w.rpw_used = 0;
@@ -764,6 +851,15 @@ int win_prepare(mogp_engine* h, int64_t n_steps, const int64_t* order, const dou
     for (const Cluster& c : h->cl)
       if (c.used) maxcap = std::max(maxcap, c.cap);
     TRY(ensure(h, &h->d_rpw, &h->rpw_elems, (int64_t)REPLAY_MAX * OWN_BATCH * (maxcap / TB + 8) * ALG_ENTRIES));
+    if (tmaint_on()) {  // private copies of the deletions' operands for k_T_leave (fire_leave_hook)
+      const int64_t nT = maxcap / TB + 2, rows = nT * TB;
+      const int64_t per = rows * NP * 2 + rows + nT * NG + NG + 8 + NP + nT * TB * TB;
+      if (per > h->tsw_slot) {
+        int64_t have = h->tsw_slot * TS_RING;
+        TRY(ensure(h, &h->d_tsw, &have, per * TS_RING));
+        h->tsw_slot = have / TS_RING;
+      }
+    }
   }
   w.new_ll.assign(n_steps, 0.0);
   w.own_ll.assign(n_steps, 0.0);
@@ -863,6 +959,9 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
       }
       b.slots.push_back(slot);
       b.epoch.push_back(w.slot_epoch[slot]);
+      w.rp_epoch[slot] = w.slot_epoch[slot];  // the pass sees the cluster as it is now; corrections may be chained behind it
+      w.rp_last[slot] = -1;
+      w.slot_tev[bi][slot] = -1;
       b.mpad.push_back(round_up(h->cl[slot].m, TB));
       b.msz.push_back(h->cl[slot].m);
     }
@@ -881,6 +980,14 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   CK(h, cudaEventRecord(h->ev_fork, h->main_stream));
   CK(h, cudaStreamWaitEvent(h->ahead, h->ev_fork, 0));
   CK(h, cudaStreamWaitEvent(h->ahead2, h->ev_fork, 0));
+  if (tmaint_on()) {  // this pass overwrites columns the maintenance kernels of the batch before last may still be working on
+    cudaStream_t ms[3] = {h->ts0, h->ts1, h->tq};
+    for (int q = 0; q < 3; ++q) {
+      if (!h->ev_ts[q]) CK(h, cudaEventCreateWithFlags(&h->ev_ts[q], cudaEventDisableTiming));
+      CK(h, cudaEventRecord(h->ev_ts[q], ms[q]));
+      CK(h, cudaStreamWaitEvent(h->ahead, h->ev_ts[q], 0));
+    }
+  }
   b.own_slot.assign(cnt, -1);
   b.own_epoch.assign(cnt, 0);
   struct StreamGuard {
@@ -944,6 +1051,7 @@ int batch_absorb(mogp_engine* h, int bi) {
           e.muthr = hm[v * ns + si];
         }
         e.pruned = hs[v * ns + si] == -INFINITY;  // (a computed score is finite)
+        e.stride = mpad;
         e.T = b.pl.T + kx_off + (w.col0[b.s0 + v] - cb) * mpad;
         e.mu = b.pl.mu + (int64_t)si * b.pl.Rpad + (w.col0[b.s0 + v] - cb);
         e.ss = b.pl.ss + (int64_t)si * b.pl.Rpad + (w.col0[b.s0 + v] - cb);
@@ -979,32 +1087,39 @@ int batch_absorb(mogp_engine* h, int bi) {
 // The pass of the NEXT batch is launched before the current batch makes its moves, so every cluster a move changes is
 // stale in it.  Re-scoring those clusters at the next batch's start costs a wait for the factor updates plus O(m^2)
 // products that compete with the pass after next.  Instead, the rank-n correction a move applies to the positions still
-// ahead in ITS batch (k_alg_leave / k_alg_join) is queued a second time, for the positions of the next batch, on the
-// look-ahead stream right behind that batch's pass: it works from the T / ss / mu the pass leaves on the device (the
+// ahead in ITS batch (k_alg_leave / k_alg_join) is queued a second time, for the positions of the next batch, on a
+// high-priority stream right behind that batch's pass: it works from the T / ss / mu the pass leaves on the device (the
 // pass saw the cluster before the change, which is what the formulas start from) and from copies of what the move
-// itself contributes (the block columns and alpha_B of a leave, Ls^-1 and z_B of a join).  By the time the batch is
-// absorbed the corrected scores are in pinned memory: no launch, no wait.  One correction per cluster: a cluster that
-// changes twice before the next batch starts, or that is new / emptied, is re-scored the long way as before.
-int replay_launch(mogp_engine* h, const ChangeLog& L, cudaEvent_t dep) {
+// itself contributes (the block columns and alpha_B of a leave, Ls^-1 and z_B of a join), and it leaves T / ss / mu as a
+// pass over the changed cluster would (maintain), so that the next change of the same cluster can be chained behind it
+// and the batch, once absorbed, finds current columns.  By the time the batch is absorbed the corrected scores are in
+// pinned memory: no launch, no wait.  A cluster whose chain breaks (new / emptied, no room, a change that could not be
+// expressed) is re-scored the long way as before.
+int replay_launch(mogp_engine* h, const ChangeLog& L, cudaEvent_t dep, AlgJobs* Jout, int* npos_out, bool* queued) {
   Chain& ch = h->chain;
   Chain::Window& w = ch.win;
+  *queued = false;
   if (w.end_launched <= w.batch_end) return MOGP_OK;  // no pass in flight
-  for (auto& it : w.async_items)
-    if (it.slot == L.slot) {  // second change of this cluster since that pass was launched
-      it.dead = true;
-      return MOGP_OK;
-    }
+  const int32_t slot = L.slot;
+  if (slot < 0 || slot >= (int32_t)w.rp_epoch.size()) return MOGP_OK;
+  auto broken = [&]() {
+    w.rp_epoch[slot] = -1;
+    return MOGP_OK;
+  };
+  if (w.rp_epoch[slot] < 0 || w.rp_epoch[slot] != L.epoch_before) return broken();
   const int nbi = w.cur_bi ^ 1;
   const Chain::Batch& nb = w.b[nbi];
   const BatchBuf& nbf = h->bb[nbi];
-  if (nb.cnt <= 0 || nb.cnt > OWN_BATCH || (int)w.async_items.size() >= REPLAY_MAX || L.ntiles <= 0) return MOGP_OK;
+  if (nb.cnt <= 0 || nb.cnt > OWN_BATCH || (int)w.async_items.size() >= REPLAY_MAX || L.ntiles <= 0) return broken();
   int si = -1;
   for (size_t q = 0; q < nb.slots.size(); ++q)
-    if (nb.slots[q] == L.slot) si = (int)q;
-  if (si < 0 || nb.epoch[si] != L.epoch_before) return MOGP_OK;  // not in that pass, or changed before it was launched
+    if (nb.slots[q] == slot) si = (int)q;
+  if (si < 0) return broken();  // not in that pass
   const int64_t wneed = nb.cnt * (int64_t)L.ntiles * (L.kind == 0 ? ALG_ENTRIES : NP * NP);
-  if (w.rpw_used + wneed > h->rpw_elems) return MOGP_OK;
+  if (w.rpw_used + wneed > h->rpw_elems) return broken();
+  if (L.kind == 1 && (int64_t)L.J.m + L.J.n > nb.mpad[si]) return broken();  // no room for the rows the join adds
   AlgJobs J = L.J;
+  J.maintain = 1;
   int64_t kx_off = 0;
   for (int q = 0; q < si; ++q) kx_off += nb.pl.Rpad * nb.mpad[q];
   const int64_t cb = w.col0[nb.s0];
@@ -1027,34 +1142,43 @@ int replay_launch(mogp_engine* h, const ChangeLog& L, cudaEvent_t dep) {
   J.logB = J.logAlpha = nullptr;
   double* part = h->d_rpw + w.rpw_used;
   w.rpw_used += wneed;
-  // on a high-priority stream of their own: behind the pass they correct (its kernels, not its read-back) and behind what
-  // the move contributes (logged copies / Ls^-1, z_B)
-  CK(h, cudaStreamWaitEvent(h->rq, nbf.scored, 0));
-  CK(h, cudaStreamWaitEvent(h->rq, dep, 0));
+  // behind the pass they correct (its kernels, not its read-back), behind what the move contributes (logged copies /
+  // Ls^-1, z_B) and behind whatever last touched these columns
+  CK(h, cudaStreamWaitEvent(h->tq, nbf.scored, 0));
+  CK(h, cudaStreamWaitEvent(h->tq, dep, 0));
+  TRY(t_wait(h, h->tq, nbi, slot));
   if (L.kind == 0) {
-    k_alg_leave_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, h->rq>>>(J, part);
+    k_alg_leave_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, h->tq>>>(J, part);
     LAUNCHED(h);
-    k_alg_leave_fin<<<(unsigned)nb.cnt, 256, 0, h->rq>>>(J, part, L.ntiles);
+    k_alg_leave_fin<<<(unsigned)nb.cnt, 256, 0, h->tq>>>(J, part, L.ntiles);
     LAUNCHED(h);
   } else {
-    k_alg_join_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, h->rq>>>(J, part);
+    k_alg_join_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, h->tq>>>(J, part);
     LAUNCHED(h);
-    k_alg_join_fin<<<(unsigned)nb.cnt, 256, 0, h->rq>>>(J, part, L.ntiles);
+    k_alg_join_fin<<<(unsigned)nb.cnt, 256, 0, h->tq>>>(J, part, L.ntiles);
     LAUNCHED(h);
   }
+  TRY(t_mark(h, h->tq, nbi, slot));
   CK(h, cudaMemcpyAsync(h->h_replay + (int64_t)k * 2 * OWN_BATCH, J.out, sizeof(double) * 2 * OWN_BATCH, cudaMemcpyDeviceToHost,
-                        h->rq));
-  CK(h, cudaEventRecord(h->ev_replay, h->rq));
+                        h->tq));
+  CK(h, cudaEventRecord(h->ev_replay, h->tq));
   h->bytes_d2h += (int64_t)sizeof(double) * 2 * OWN_BATCH;
   Chain::Window::AsyncItem it;
-  it.slot = L.slot;
+  it.slot = slot;
   it.epoch_before = L.epoch_before;
   it.out_idx = k;
   w.async_items.push_back(it);
+  w.rp_epoch[slot] = L.epoch_before + 1;
+  w.rp_last[slot] = k;
+  if (Jout) *Jout = J;
+  if (npos_out) *npos_out = (int)nb.cnt;
+  *queued = true;
   return MOGP_OK;
 }
 
-// Take over the corrections queued ahead for the batch just absorbed (see replay_launch).
+// Take over the corrections queued behind the pass of the batch just absorbed (see replay_launch): a cluster that changed
+// since the pass was launched and whose every change was chained behind the pass has current scores (the last
+// correction's) and current T / ss / mu.
 int win_replay(mogp_engine* h, int bi) {
   Chain& ch = h->chain;
   Chain::Window& w = ch.win;
@@ -1064,15 +1188,12 @@ int win_replay(mogp_engine* h, int bi) {
     PhaseTimer pt(&ch.t_alg);
     CK(h, cudaEventSynchronize(h->ev_replay));
   }
-  for (const auto& it : w.async_items) {
-    const int32_t slot = it.slot;
-    if (it.dead || slot < 0 || slot >= (int32_t)w.slot_epoch.size() || !h->cl[slot].used) continue;
-    int si = -1;
-    for (size_t q = 0; q < b.slots.size(); ++q)
-      if (b.slots[q] == slot) si = (int)q;
-    // exactly one change since the pass was launched, and nobody has re-scored the cluster in the meantime
-    if (si < 0 || b.epoch[si] != it.epoch_before || w.slot_epoch[slot] != it.epoch_before + 1 || w.slot_upto[slot] > b.s0) continue;
-    const double* out = h->h_replay + (int64_t)it.out_idx * 2 * OWN_BATCH;
+  for (size_t si = 0; si < b.slots.size(); ++si) {
+    const int32_t slot = b.slots[si];
+    if (slot < 0 || slot >= (int32_t)w.slot_epoch.size() || !h->cl[slot].used) continue;
+    if (w.slot_epoch[slot] == b.epoch[si]) continue;  // unchanged: batch_absorb took the pass's own scores
+    if (w.rp_epoch[slot] != w.slot_epoch[slot] || w.rp_last[slot] < 0 || w.slot_upto[slot] > b.s0) continue;
+    const double* out = h->h_replay + (int64_t)w.rp_last[slot] * 2 * OWN_BATCH;
     bool reopened = false;
     for (int64_t q = 0; q < b.cnt; ++q) {
       Chain::WinEntry& e = w.e[b.s0 + q][slot];
@@ -1081,13 +1202,13 @@ int win_replay(mogp_engine* h, int bi) {
         e.score = out[2 * q];
         continue;
       }
-      e.score = -INFINITY;  // excluded before the product: stays excluded unless the move brought its mean back
+      e.score = -INFINITY;  // excluded before the product: stays excluded unless the moves brought its mean back
       const double yt = h->h_ythr.empty() ? NAN : h->h_ythr[w.pat[b.s0 + q]];
       if (!(yt - e.muthr > ch.cfg.threshold)) reopened = true;
     }
     if (reopened) continue;  // (the cluster stays stale and is re-scored at the batch's first step)
-    w.slot_upto[slot] = b.s0 + b.cnt;  // scores current for this batch; its T / ss / mu are those of the old factor
-    w.slot_T_ok[slot] = 0;
+    w.slot_upto[slot] = b.s0 + b.cnt;
+    w.slot_T_ok[slot] = 1;
     ch.win_replayed += 1;
   }
   w.async_items.clear();
@@ -1111,6 +1232,7 @@ void win_store(mogp_engine* h, int64_t v0, const std::vector<int32_t>& slots, co
       e.score = host_score[(v - v0) * ns + si];
       e.muthr = host_mu[(v - v0) * ns + si];
       e.pruned = false;
+      e.stride = mpad;
       e.T = pl.T + kx_off + (w.col0[v] - cbase) * mpad;
       e.mu = pl.mu + (int64_t)si * pl.Rpad + (w.col0[v] - cbase);
       e.ss = pl.ss + (int64_t)si * pl.Rpad + (w.col0[v] - cbase);
@@ -1118,6 +1240,7 @@ void win_store(mogp_engine* h, int64_t v0, const std::vector<int32_t>& slots, co
     w.slot_upto[slot] = w.batch_end;
     w.slot_T_ok[slot] = 1;
     w.slot_alg[slot] = 0;
+    w.slot_tev[w.cur_bi][slot] = -1;  // fresh columns (the host has waited for them)
     kx_off += pl.Rpad * mpad;
   }
 }
@@ -1171,6 +1294,43 @@ int win_ensure(mogp_engine* h, int32_t own_id, ScoreRes* arena) {
       w.own_ok[v] = 1;
     }
   if (need_own && !w.own_ok[cur]) FAIL(h, MOGP_ESTATE, "own-cluster score of patient %lld unavailable", (long long)w.pat[cur]);
+  return MOGP_OK;
+}
+
+// Test mode (MOGP_CHECK_CORRECTIONS): re-score positions [v0, batch_end) under `slots` the long way (from the UPDATED
+// factors, waiting for them) and record the worst disagreement with the cached - corrected - scores.  take_over (= 1): the
+// re-scored values and columns replace the cached ones; 2: compare only, so that chains of corrections on maintained
+// columns are checked at every link.
+int win_check_slots(mogp_engine* h, int64_t v0, const std::vector<int32_t>& chk, ScoreRes* arena, bool take_over) {
+  Chain& ch = h->chain;
+  Chain::Window& w = ch.win;
+  const int64_t rem = w.batch_end - v0;
+  if (chk.empty() || rem <= 0) return MOGP_OK;
+  const int64_t Rrem = w.col0[w.batch_end] - w.col0[v0], Rtot = w.col0[w.n];
+  const int nb = (int)chk.size();
+  const int thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
+  TRY(ensure(h, &h->d_out, &h->out_elems, 2 * rem * nb + 8));
+  join_side(h);
+  ScorePlan pl;
+  TRY(score_device(h, rem, Rrem, h->d_woff + v0, h->d_wq + w.col0[v0], h->d_wq + Rtot + w.col0[v0], nb, chk.data(), thr_index,
+                   h->d_out, h->d_out + rem * nb, nullptr, nullptr, nullptr, true, &pl, arena));
+  std::vector<double> host(2 * rem * nb);
+  TRY(copy_back(h, host.data(), h->d_out, 2 * rem * nb));
+  for (int si = 0; si < nb; ++si)
+    for (int64_t q = 0; q < rem; ++q) {
+      const Chain::WinEntry& e = w.e[v0 + q][chk[si]];
+      const double s_ref = host[q * nb + si], m_ref = host[rem * nb + q * nb + si];
+      double err = e.pruned ? 0.0 : fabs(e.score - s_ref) / std::max(1.0, fabs(s_ref));
+      if (!(isnan(m_ref) && isnan(e.muthr))) err = std::max(err, fabs(e.muthr - m_ref) / std::max(1.0, fabs(m_ref)));
+      if (!(err <= ch.max_corr_err)) ch.max_corr_err = err;  // (NaN sticks)
+    }
+  if (take_over) {
+    const int64_t keep_cur = w.cur;
+    w.cur = v0;  // win_store fills [v0, batch_end)
+    win_store(h, v0, chk, pl, host.data(), host.data() + rem * nb);
+    w.cur = keep_cur;
+  }
+  ch.corr_checked += rem * nb;
   return MOGP_OK;
 }
 
@@ -1228,53 +1388,61 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
   const bool stays = ch.pending_lazy && chosen == prev;
   // A move changes two clusters.  The scores of the patients still ahead in this batch under them are corrected by
   // rank-n formulas from what the pass left on the device (k_alg_leave / k_alg_join) and read back at once; the
-  // O(m^2) updates of the two factors are queued behind and nobody waits for them.  One correction per cluster and
-  // batch: a second change, a cluster without current T, a new or emptied cluster go the long way (re-scoring).
+  // O(m^2) updates of the two factors are queued behind and nobody waits for them.  With MOGP_TMAINT (default) the
+  // corrections also leave the cached T / ss / mu current (the leave's T by k_T_leave, fired from remove_core), for this
+  // batch's positions and - queued behind its pass - for the next batch's (replay_launch): further changes of the same
+  // cluster are corrected the same way and the next batch starts with current scores.  Without it: one correction per
+  // cluster and batch, and everything else - a cluster without current T, a new or emptied cluster - goes the long way
+  // (re-scoring against the updated factor).
   const int64_t npos = w.batch_end - (w.cur + 1);
   const bool alg_on = !stays && npos >= 0 && npos <= OWN_BATCH && ch.pending_lazy && env_int("MOGP_RANK_RESCORE", 1) != 0;
-  // a next batch's pass is in flight: MOGP_REPLAY=1 queues the same corrections for ITS positions (replay_launch).  Off by
-  // default: measured on the 10k-patient chain it removes 58 % of the re-scoring passes and shortens the live pass (426 ->
-  // 385 us), but a cluster corrected that way has no current T for the whole next batch - every patient joining it needs
-  // a product against it first (+6 % launches on the critical path) and no in-batch correction is possible for it -
-  // and the sweep ends up 5 % slower (0.807 vs 0.848 sweeps/s, profiles/README.md).
-  const bool log_on = alg_on && w.end_launched > w.batch_end && env_int("MOGP_REPLAY", 0) != 0;
+  const bool tm = tmaint_on();
+  const bool log_on = alg_on && tm && w.end_launched > w.batch_end;  // a next batch's pass is in flight
+  const int thr_cfg = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
   auto alg_ok = [&](int32_t slot) {
     return slot >= 0 && slot < (int32_t)w.slot_upto.size() && w.slot_upto[slot] >= w.batch_end && w.slot_T_ok[slot] &&
-           !w.slot_alg[slot];
+           (tm || !w.slot_alg[slot]);
+  };
+  auto replay_ready = [&](int32_t slot) {  // every change since the next batch's pass was launched is chained behind it
+    return log_on && slot >= 0 && slot < (int32_t)w.rp_epoch.size() && w.rp_epoch[slot] >= 0 &&
+           w.rp_epoch[slot] == w.slot_epoch[slot];
   };
   auto fill_pos = [&](AlgJobs& J, int32_t slot) {
     for (int64_t q = 0; q < npos; ++q) {
       const int64_t v = w.cur + 1 + q;
       const Chain::WinEntry& e = w.e[v][slot];
       AlgPos& P = J.pos[q];
-      P.stride = round_up(h->cl[slot].m, TB);
-      const int thr = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
+      P.stride = e.stride;
       // a pair excluded before the product has its threshold column only: the correction re-derives that mean
-      const int64_t skip = e.pruned ? thr : 0;
+      const int64_t skip = e.pruned ? thr_cfg : 0;
       P.T = e.T + skip * P.stride;
       P.ss = e.ss + skip;
       P.mu = e.mu + skip;
       P.x = h->d_wq + w.col0[v] + skip;
       P.y = h->d_wq + w.col0[w.n] + w.col0[v] + skip;
       P.ncols = e.pruned ? 1 : (int)(w.col0[v + 1] - w.col0[v]);
-      P.thr = e.pruned ? 0 : thr;
+      P.thr = e.pruned ? 0 : thr_cfg;
       P.flag = nullptr;
     }
-    J.th = make_theta(h->cl[slot]);
-    J.thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
   };
   const int64_t c0n = h->h_off[n], nin = h->h_off[n + 1] - c0n;
   int32_t a_slot = -1, b_slot = -1;
-  bool a_alg = false;
-  AlgHook hook;
+  bool a_alg = false, a_maint = false, a_rp = false;
+  AlgHook hook{};
+  LeaveHook lhook{};
   if (alg_on) {
-    if (ch.slot_of_id[prev] >= 0 && alg_ok(ch.slot_of_id[prev])) {  // leave side, from the factor as it is now
-      a_slot = ch.slot_of_id[prev];
+    const int32_t sl_a = ch.slot_of_id[prev];
+    const bool a0 = alg_ok(sl_a), a1 = replay_ready(sl_a);
+    if (sl_a >= 0 && (a0 || a1)) {  // leave side, from the factor as it is now
+      a_slot = sl_a;
       Cluster& ca = h->cl[a_slot];
       const int64_t p = member_offset(h, ca, n, nullptr);
       if (p >= 0) {
+        const int64_t np0 = a0 ? npos : 0;
         AlgJobs J{};
-        fill_pos(J, a_slot);
+        if (np0 > 0) fill_pos(J, a_slot);
+        J.th = make_theta(ca);
+        J.thr_index = thr_cfg;
         J.out = h->d_alg;
         J.M = ca.M;
         J.alpha = ca.alpha();
@@ -1283,54 +1451,82 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
         J.n = (int)nin;
         J.m = (int)ca.m;
         const int ntiles = (int)((ca.m - p + TB - 1) / TB);
-        if (log_on) {  // keep what the correction reads from the cluster: replayed for the next batch (win_replay)
+        if (tm) {  // keep what the kernels read from the cluster: the buffer moves on, k_T_leave and the replay come later
           const int64_t need = (int64_t)(ca.m - p) * NP + NP;
-          if (w.blog_used + need <= h->blog_elems) {
-            J.logB = h->d_blog + w.blog_used;
+          if (w.blog_used + need <= w.blog_half) {
+            J.logB = h->d_blog + w.blog_base + w.blog_used;
             J.logAlpha = J.logB + (int64_t)(ca.m - p) * NP;
             w.blog_used += need;
           }
         }
-        if (npos > 0 || J.logB) {
-          TRY(ensure(h, &h->d_algw, &h->algw_elems, (int64_t)std::max<int64_t>(npos, 1) * ntiles * ALG_ENTRIES));
-          if (npos == 0) J.pos[0].ncols = 0;  // log only
-          k_alg_leave_part<<<dim3((unsigned)ntiles, (unsigned)std::max<int64_t>(npos, 1)), 256, 0, h->quick2>>>(J, h->d_algw);
+        J.maintain = (tm && J.logB) ? 1 : 0;
+        if (np0 > 0 || (J.logB && a1)) {
+          TRY(ensure(h, &h->d_algw, &h->algw_elems, (int64_t)std::max<int64_t>(np0, 1) * ntiles * ALG_ENTRIES));
+          if (np0 == 0) J.pos[0].ncols = 0;  // log only
+          if (np0 > 0) TRY(t_wait(h, h->quick2, w.cur_bi, a_slot));
+          k_alg_leave_part<<<dim3((unsigned)ntiles, (unsigned)std::max<int64_t>(np0, 1)), 256, 0, h->quick2>>>(J, h->d_algw);
           LAUNCHED(h);
-          if (npos > 0) {
-            k_alg_leave_fin<<<(unsigned)npos, 256, 0, h->quick2>>>(J, h->d_algw, ntiles);
+          if (np0 > 0) {
+            k_alg_leave_fin<<<(unsigned)np0, 256, 0, h->quick2>>>(J, h->d_algw, ntiles);
             LAUNCHED(h);
+            if (J.maintain) TRY(t_mark(h, h->quick2, w.cur_bi, a_slot));
           }
           CK(h, cudaEventRecord(h->ev_q2, h->quick2));
           // the cluster's old buffer must outlive these reads: the streams that may recycle it wait for them
           CK(h, cudaStreamWaitEvent(h->main_stream, h->ev_q2, 0));
           CK(h, cudaStreamWaitEvent(h->side, h->ev_q2, 0));
         }
-        a_alg = true;
+        a_alg = a0;
+        AlgJobs Jlog = J;  // the same job reading the logged copies: J.M[k * ld + p + a] with ld = NP reads logB[(k - p) * NP + a]
         if (J.logB) {
+          Jlog.M = J.logB - ((int64_t)p * NP + p);
+          Jlog.ld = NP;
+          Jlog.alpha = J.logAlpha - p;
+          Jlog.logB = Jlog.logAlpha = nullptr;
+        }
+        if (J.logB && a1) {
           ChangeLog cl;
           cl.slot = a_slot;
           cl.kind = 0;
-          cl.J = J;
-          cl.J.M = J.logB - ((int64_t)p * NP + p);  // J.M[k * ld + p + a] with ld = NP reads logB[(k - p) * NP + a]
-          cl.J.ld = NP;
-          cl.J.alpha = J.logAlpha - p;
-          cl.J.logB = cl.J.logAlpha = nullptr;
+          cl.J = Jlog;
           cl.ntiles = ntiles;
           cl.epoch_before = w.slot_epoch[a_slot];
-          TRY(replay_launch(h, cl, h->ev_q2));
+          TRY(replay_launch(h, cl, h->ev_q2, &lhook.J[1], &lhook.npos[1], &a_rp));
+          if (!a_rp) lhook.npos[1] = 0;
+        } else if (a1) {
+          w.rp_epoch[a_slot] = -1;
         }
+        if (J.maintain && (np0 > 0 || a_rp)) {  // the T of the positions ahead follows in remove_core (k_T_leave)
+          lhook.slot = a_slot;
+          if (np0 > 0) {
+            lhook.J[0] = Jlog;
+            lhook.npos[0] = (int)np0;
+            lhook.bi[0] = w.cur_bi;
+          }
+          lhook.bi[1] = w.cur_bi ^ 1;
+          h->leave_hook = &lhook;
+        }
+        a_maint = J.maintain != 0;
       }
     }
     if (chosen < n_ids && alg_ok(ch.slot_of_id[chosen]) && (npos > 0 || log_on)) {  // join side: launched by append_core once Ls, z_B exist
       b_slot = ch.slot_of_id[chosen];
       const Chain::WinEntry& en = w.e[w.cur][b_slot];
       fill_pos(hook.jobs, b_slot);
+      hook.jobs.th = make_theta(h->cl[b_slot]);
+      hook.jobs.thr_index = thr_cfg;
       hook.jobs.out = h->d_alg + 2 * OWN_BATCH;
       hook.jobs.n = (int)nin;
+      hook.jobs.m = (int)h->cl[b_slot].m;
       hook.jobs.Tn = en.T;
-      hook.jobs.stride_n = round_up(h->cl[b_slot].m, TB);
+      hook.jobs.stride_n = en.stride;
       hook.jobs.xn = h->d_px + c0n;
+      bool room = tm;  // the n rows the append adds to every cached column must fit under its stride
+      for (int64_t q = 0; q < npos; ++q) room = room && (h->cl[b_slot].m + nin <= hook.jobs.pos[q].stride);
+      hook.jobs.maintain = room ? 1 : 0;
       hook.npos = (int)npos;
+      hook.slot = b_slot;
+      hook.bi = w.cur_bi;
       h->alg_hook = &hook;
     }
   }
@@ -1341,18 +1537,24 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
     rc = chain_commit(h, chosen, a_draw, &is_new);
     w.in_step = false;
     h->alg_hook = nullptr;
+    h->leave_hook = nullptr;
     if (rc != MOGP_OK) return rc;
   }
   if (!stays) {
     const bool b_alg = hook.fired;
-    if (b_alg && log_on && hook.on_quick) {
-      ChangeLog cl;
-      cl.slot = b_slot;
-      cl.kind = 1;
-      cl.J = hook.jobs;  // Tn, Li, znew, xn stay valid until the next batch has been absorbed
-      cl.ntiles = hook.ntiles;
-      cl.epoch_before = w.slot_epoch[b_slot];
-      TRY(replay_launch(h, cl, h->ev_alg));
+    if (a_rp && !lhook.fired[1]) w.rp_epoch[a_slot] = -1;  // the correction was queued but T did not follow
+    if (b_slot >= 0 && replay_ready(b_slot)) {
+      bool queued = false;
+      if (b_alg && hook.on_quick) {
+        ChangeLog cl;
+        cl.slot = b_slot;
+        cl.kind = 1;
+        cl.J = hook.jobs;  // Tn, Li, znew, xn stay valid until the next batch has been absorbed
+        cl.ntiles = hook.ntiles;
+        cl.epoch_before = w.slot_epoch[b_slot];
+        TRY(replay_launch(h, cl, h->ev_alg, nullptr, nullptr, &queued));
+      }
+      if (!queued) w.rp_epoch[b_slot] = -1;
     }
     if ((a_alg || b_alg) && npos > 0) {
       PhaseTimer pt(&ch.t_alg);
@@ -1363,7 +1565,8 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
       h->bytes_d2h += (int64_t)sizeof(double) * 4 * OWN_BATCH;
       ch.win_algebra += 1;
     }
-    auto corrected = [&](int32_t slot, const double* out) {  // scores current, T stale, next batch's pass dirty
+    // scores current; T / ss / mu current too when the change was carried through to them (maintained), else stale
+    auto corrected = [&](int32_t slot, const double* out, bool maintained) {
       bool reopened = false;
       for (int64_t q = 0; q < npos; ++q) {
         Chain::WinEntry& e = w.e[w.cur + 1 + q][slot];
@@ -1378,51 +1581,30 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
         const double yt = h->h_ythr.empty() ? NAN : h->h_ythr[pn];
         if (!(yt - e.muthr > ch.cfg.threshold)) reopened = true;
       }
-      w.slot_T_ok[slot] = 0;
-      w.slot_alg[slot] = 1;
+      if (!maintained) {
+        w.slot_T_ok[slot] = 0;
+        w.slot_alg[slot] = 1;
+      }
       w.slot_epoch[slot] += 1;
-      if (reopened) w.slot_upto[slot] = 0;
+      if (reopened) {
+        w.slot_upto[slot] = 0;
+        w.slot_T_ok[slot] = 0;
+      }
       for (int64_t v = w.cur + 1; v < w.end_launched; ++v) {
         const int32_t id = ch.z[w.pat[v]];
         if (id >= 0 && ch.slot_of_id[id] == slot) w.own_ok[v] = 0;
       }
     };
     const int32_t slot_prev = ch.slot_of_id[prev];
-    if (a_alg && slot_prev == a_slot) corrected(a_slot, h->h_alg);
+    if (a_alg && slot_prev == a_slot) corrected(a_slot, h->h_alg, a_maint && (npos == 0 || lhook.fired[0]));
     else if (slot_prev >= 0) win_invalidate(ch, slot_prev);
-    if (b_alg && ch.slot_of_id[chosen] == b_slot) corrected(b_slot, h->h_alg + 2 * OWN_BATCH);
+    if (b_alg && ch.slot_of_id[chosen] == b_slot) corrected(b_slot, h->h_alg + 2 * OWN_BATCH, hook.jobs.maintain != 0);
     else win_invalidate(ch, ch.slot_of_id[chosen]);
     if (npos > 0 && env_int("MOGP_CHECK_CORRECTIONS", 0) != 0) {
-      // Test mode: re-score the corrected positions the long way (from the UPDATED factors, waiting for them) and
-      // record the worst disagreement with the rank-n formulas; the re-scored values take over.
       std::vector<int32_t> chk;
       if (a_alg && slot_prev == a_slot) chk.push_back(a_slot);
       if (b_alg && ch.slot_of_id[chosen] == b_slot) chk.push_back(b_slot);
-      if (!chk.empty()) {
-        const int64_t v0 = w.cur + 1, rem = w.batch_end - v0, Rrem = w.col0[w.batch_end] - w.col0[v0], Rtot = w.col0[w.n];
-        const int nb = (int)chk.size();
-        const int thr_index = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
-        TRY(ensure(h, &h->d_out, &h->out_elems, 2 * rem * nb + 8));
-        join_side(h);
-        ScorePlan pl;
-        TRY(score_device(h, rem, Rrem, h->d_woff + v0, h->d_wq + w.col0[v0], h->d_wq + Rtot + w.col0[v0], nb, chk.data(), thr_index,
-                         h->d_out, h->d_out + rem * nb, nullptr, nullptr, nullptr, true, &pl, arena));
-        std::vector<double> host(2 * rem * nb);
-        TRY(copy_back(h, host.data(), h->d_out, 2 * rem * nb));
-        for (int si = 0; si < nb; ++si)
-          for (int64_t q = 0; q < rem; ++q) {
-            const Chain::WinEntry& e = w.e[v0 + q][chk[si]];
-            const double s_ref = host[q * nb + si], m_ref = host[rem * nb + q * nb + si];
-            double err = e.pruned ? 0.0 : fabs(e.score - s_ref) / std::max(1.0, fabs(s_ref));
-            if (!(isnan(m_ref) && isnan(e.muthr))) err = std::max(err, fabs(e.muthr - m_ref) / std::max(1.0, fabs(m_ref)));
-            if (!(err <= ch.max_corr_err)) ch.max_corr_err = err;  // (NaN sticks)
-          }
-        const int64_t keep_cur = w.cur;
-        w.cur = v0;  // win_store fills [v0, batch_end)
-        win_store(h, v0, chk, pl, host.data(), host.data() + rem * nb);
-        w.cur = keep_cur;
-        ch.corr_checked += rem * nb;
-      }
+      TRY(win_check_slots(h, w.cur + 1, chk, arena, env_int("MOGP_CHECK_CORRECTIONS", 0) == 1));
     }
   }
   if (chosen_out) *chosen_out = chosen;
@@ -1465,16 +1647,28 @@ int sweep_pipelined(mogp_engine* h, int64_t n_steps, const int64_t* order, const
     w.batch_end = pos + B.cnt;
     w.cur_bi = (int)(jb & 1);
     TRY(win_replay(h, (int)(jb & 1)));
+    if (env_int("MOGP_CHECK_CORRECTIONS", 0) == 2) {  // the scores taken from the corrections chained behind the pass
+      std::vector<int32_t> chk;
+      for (size_t si = 0; si < B.slots.size(); ++si) {
+        const int32_t sl = B.slots[si];
+        if (h->cl[sl].used && w.slot_epoch[sl] != B.epoch[si] && w.slot_upto[sl] >= w.batch_end) chk.push_back(sl);
+      }
+      TRY(win_check_slots(h, pos, chk, &h->res_bump[jb & 1], false));
+    }
     w.blog_used = 0;
     {  // room for the logged block columns of this batch's leave-side changes
       int64_t maxm = 0;
       for (const Cluster& c : h->cl)
         if (c.used) maxm = std::max(maxm, c.m);
-      TRY(ensure(h, &h->d_blog, &h->blog_elems, (int64_t)(OWN_BATCH + 1) * ((maxm + (int64_t)OWN_BATCH * NP) * NP + NP)));
+      // (two halves, alternating per batch: the kernels queued behind the next batch's pass read this batch's log later)
+      TRY(ensure(h, &h->d_blog, &h->blog_elems, 2 * (int64_t)(OWN_BATCH + 1) * ((maxm + (int64_t)OWN_BATCH * NP) * NP + NP)));
+      w.blog_half = h->blog_elems / 2;
+      w.blog_base = (jb & 1) * w.blog_half;
     }
     std::fill(w.slot_alg.begin(), w.slot_alg.end(), 0);
     // re-scoring blocks written two batches ago are no longer referenced
     ScoreRes& arena = h->res_bump[jb & 1];
+    if (h->ev_ts_end[jb & 1]) CK(h, cudaStreamWaitEvent(h->main_stream, h->ev_ts_end[jb & 1], 0));  // (k_T_leave on them: long done)
     arena.scr_used = 0;
     for (double* p : arena.retired) cudaFree(p);
     arena.retired.clear();
@@ -1497,6 +1691,10 @@ int sweep_pipelined(mogp_engine* h, int64_t n_steps, const int64_t* order, const
       TRY(win_step(h, a_draw ? a_draw[pos + q] : 0.0, u[pos + q], &chosen, &arena));
       if (chosen_ids) chosen_ids[pos + q] = chosen;
       *mm = std::min(*mm, ch.last_margin);
+    }
+    if (tmaint_on()) {
+      if (!h->ev_ts_end[jb & 1]) CK(h, cudaEventCreateWithFlags(&h->ev_ts_end[jb & 1], cudaEventDisableTiming));
+      CK(h, cudaEventRecord(h->ev_ts_end[jb & 1], h->ts0));
     }
     pos += bcnt;
     ++jb;

@@ -29,13 +29,15 @@
 using namespace mogp;
 
 constexpr int ALG_OUT_SLOTS = 2 + 30;  // outputs of the two within-batch corrections + of a replay (one region per slot)
-constexpr int REPLAY_MAX = 12;         // corrections queued ahead for the next batch's positions, per batch
+constexpr int REPLAY_MAX = 24;         // corrections queued ahead for the next batch's positions, per batch
 
 // The join-side score correction a commit launches right after k_append_small (append_core), see update.cuh.
 struct AlgHook {
   AlgJobs jobs;
   int npos = 0, ntiles = 0;
   bool fired = false, on_quick = false;
+  int32_t slot = -1;  // the cluster joined and the batch buffer its cached columns live in (t_wait / t_mark)
+  int bi = 0;
 };
 // One rank-n change of the batch being processed, kept so that the same correction can be applied to the NEXT batch's
 // positions when their pass (launched before the change) is absorbed.
@@ -46,6 +48,18 @@ struct ChangeLog {
   int ntiles = 0;
   int64_t epoch_before = 0;
 };
+// The leave-side half of keeping the cached T current (k_T_leave): filled by the step that moves a patient, fired by
+// remove_core as soon as the deletion's operands exist (k_rm_prep).  Target 0 = the positions still ahead in the batch being
+// processed, target 1 = the positions of the next batch (their pass, launched before the move, is corrected behind it).
+struct LeaveHook {
+  AlgJobs J[2];
+  int npos[2] = {0, 0};
+  int bi[2] = {0, 0};      // batch buffer (parity) each target's columns live in
+  int32_t slot = -1;
+  bool fired[2] = {false, false};
+};
+constexpr int TS_RING = 40;   // private copies of a deletion's operands for k_T_leave (two batches of moves in flight)
+constexpr int TEV_RING = 256; // events ordering the readers / writers of the cached columns of one (batch, slot)
 namespace {
 
 thread_local std::string g_create_error;
@@ -122,6 +136,7 @@ struct Chain {
   struct WinEntry {
     double score = 0.0, muthr = 0.0;
     bool pruned = false;         // excluded by the monotonicity rule before the product: only its threshold column has T / ss / mu
+    int64_t stride = 0;          // rows between two columns of T (the slot's padded size when the columns were computed)
     const double* T = nullptr;   // the patient's columns of T = M Kx under that slot (stride = mpad when scored)
     const double* mu = nullptr;  // ... their predictive means
     const double* ss = nullptr;  // ... and their k*^T Ky^-1 k* (device, as mu)
@@ -166,7 +181,15 @@ struct Chain {
     std::vector<AsyncItem> async_items;
     int64_t rpw_used = 0;          // doubles used in the engine's d_rpw
     int cur_bi = 0;                // buffer index of the batch being processed
-    int64_t blog_used = 0;         // doubles used in the engine's d_blog
+    int64_t blog_used = 0;         // doubles used in the engine's d_blog (this batch's half: blog_base, blog_half)
+    int64_t blog_base = 0, blog_half = 0;
+    // cached columns kept current on the device (MOGP_TMAINT): [batch parity][slot] index of the event recorded after the last
+    // kernel that reads or writes them (-1: none pending); rp_epoch[slot]: change counter up to which the pass in flight for
+    // the NEXT batch has been brought by corrections queued behind it (-1: the chain of corrections is broken);
+    // rp_last[slot]: output block of the last of those corrections
+    std::vector<int> slot_tev[2];
+    std::vector<int64_t> rp_epoch;
+    std::vector<int> rp_last;
   } win;
   int64_t win_passes = 0, win_rescores = 0, win_patients = 0, win_algebra = 0, win_replayed = 0;  // accounting
   int64_t win_pairs = 0, win_pruned = 0;   // (patient, cluster) pairs of the window passes / those excluded before the product
@@ -267,6 +290,18 @@ struct mogp_engine {
   cudaEvent_t ev_replay = nullptr;
   cudaStream_t rq = nullptr;      // high priority: the corrections queued ahead run as soon as the pass they correct has finished
   AlgHook* alg_hook = nullptr;  // set while a commit should launch the append-side correction (append_core)
+  LeaveHook* leave_hook = nullptr;  // ... and the leave-side update of the cached columns (remove_core)
+  cudaStream_t ts0 = nullptr, ts1 = nullptr;  // high priority: k_T_leave for the current / the next batch's positions
+  cudaStream_t tq = nullptr;      // high priority: the corrections queued behind the next batch's pass
+  cudaEvent_t tev[TEV_RING] = {};
+  int tev_next = 0;
+  double* d_tsw = nullptr;        // ring of private copies of a deletion's operands (Bt | Gt | u | ... | S)
+  int64_t tsw_slot = 0;           // doubles per ring entry
+  int tsw_next = 0;
+  cudaEvent_t tsw_done[TS_RING][2] = {};  // the k_T_leave launches reading entry k have finished
+  cudaEvent_t tsw_cp = nullptr;
+  cudaEvent_t ev_ts[3] = {};      // batch_launch: the new pass reuses buffers the kernels on ts0 / ts1 / tq worked on
+  cudaEvent_t ev_ts_end[2] = {};  // [batch parity] ts0 at the end of a batch: its re-scoring arena is reused two batches later
   double* d_upd2 = nullptr;  // row-deletion workspace of the look-ahead streams (own-cluster scores)
   int64_t upd2_elems = 0;
   double *d_own1 = nullptr, *d_own2 = nullptr;  // Gram partials of the batched own-cluster scores (main-side / look-ahead)
@@ -1217,6 +1252,10 @@ static int engine_create_impl(int32_t device, bool light, mogp_engine** out) {
                   cudaMallocHost((void**)&h->h_replay, sizeof(double) * REPLAY_MAX * 2 * OWN_BATCH) != cudaSuccess ||
                   cudaEventCreateWithFlags(&h->ev_replay, cudaEventDisableTiming) != cudaSuccess ||
                   cudaStreamCreateWithPriority(&h->rq, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+                  cudaStreamCreateWithPriority(&h->tq, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+                  cudaStreamCreateWithPriority(&h->ts0, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+                  cudaStreamCreateWithPriority(&h->ts1, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+                  cudaEventCreateWithFlags(&h->tsw_cp, cudaEventDisableTiming) != cudaSuccess ||
                   cudaEventCreateWithFlags(&h->bb[0].scored, cudaEventDisableTiming) != cudaSuccess ||
                   cudaEventCreateWithFlags(&h->bb[1].scored, cudaEventDisableTiming) != cudaSuccess)) ||
       cudaEventCreateWithFlags(&h->ev_q2, cudaEventDisableTiming) != cudaSuccess ||
@@ -1316,6 +1355,20 @@ void mogp_engine_destroy(mogp_engine* h) {
   if (h->h_replay) cudaFreeHost(h->h_replay);
   if (h->ev_replay) cudaEventDestroy(h->ev_replay);
   if (h->rq) cudaStreamDestroy(h->rq);
+  if (h->tq) cudaStreamDestroy(h->tq);
+  if (h->ts0) cudaStreamDestroy(h->ts0);
+  if (h->ts1) cudaStreamDestroy(h->ts1);
+  if (h->tsw_cp) cudaEventDestroy(h->tsw_cp);
+  for (auto& e : h->tev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_ts)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_ts_end)
+    if (e) cudaEventDestroy(e);
+  for (auto& e2 : h->tsw_done)
+    for (auto& e : e2)
+      if (e) cudaEventDestroy(e);
+  cudaFree(h->d_tsw);
   cudaFree(h->d_algw);
   cudaFree(h->d_apring);
   if (h->h_alg) cudaFreeHost(h->h_alg);

@@ -241,6 +241,10 @@ struct AlgJobs {
   // it can be replayed for the NEXT batch's positions after the cluster's buffer has moved on (chain.inl)
   double* logB;         // [(k - p) * NP + a]
   double* logAlpha;     // [NP]
+  // maintain: besides the corrected scores, leave the patients' T / ss / mu ON THE DEVICE as a pass over the changed cluster
+  // would: the corrections write ss', mu' back (and a join the n rows it adds to every T column, at row m - needs
+  // m + n <= stride); a leave's T follows in k_T_leave.  The cached columns then serve further corrections and appends.
+  int maintain;
 };
 
 __device__ __forceinline__ void alg_finish(const AlgJobs& J, const AlgPos& P, const double* ssn, const double* mun,
@@ -339,6 +343,10 @@ __global__ void __launch_bounds__(256) k_alg_leave_fin(const __grid_constant__ A
     }
     ssn[tid] = ok ? P.ss[tid] - ds : nan("");
     mun[tid] = P.mu[tid] - dm;
+    if (J.maintain) {
+      const_cast<double*>(P.ss)[tid] = ssn[tid];
+      const_cast<double*>(P.mu)[tid] = mun[tid];
+    }
   }
   __syncthreads();
   alg_finish(J, P, ssn, mun, lpd);
@@ -388,9 +396,14 @@ __global__ void __launch_bounds__(256) k_alg_join_fin(const __grid_constant__ Al
       for (int c = 0; c <= i; ++c) t += J.Li[i * NP + c] * w[c];
       s2 += t * t;
       dm += t * J.znew[i];
+      if (J.maintain) const_cast<double*>(P.T)[(int64_t)tid * P.stride + J.m + i] = t;  // the rows the append adds to T_q
     }
     ssn[tid] = P.ss[tid] + s2;
     mun[tid] = P.mu[tid] + dm;
+    if (J.maintain) {
+      const_cast<double*>(P.ss)[tid] = ssn[tid];
+      const_cast<double*>(P.mu)[tid] = mun[tid];
+    }
   }
   __syncthreads();
   alg_finish(J, P, ssn, mun, lpd);
@@ -719,6 +732,104 @@ __global__ void __launch_bounds__(NTHREADS) k_rm_strip(const double* __restrict_
   if (strip == 0 && tid < 32) vec_new[4 * cap + tid] = vec_old[4 * cap + tid];  // the stat block travels with the buffer
 }
 
+// The same row operations applied to cached columns T_q = M k_q of the patients still ahead (look-ahead pipeline, chain.inl):
+// with M' E = G M (E drops the block's columns) T_q' = M' k_q' = G T_q - the contributions of the block's entries of k_q cancel
+// (g_i . G_{i-1} k_B = b_i . k_B) - so T_q' [i'] = u_i (T_q[i] - g_i . h_{i-1}), h_i = sum_{k <= i} b_k T_q[k] from the block's own
+// rows on: a column of T is transformed exactly like a column of M left of the block.  One CTA per patient (<= NP = RM_SW
+// columns: one strip), in place (a row tile is written where rows already consumed were read from), O(m n) per column
+// instead of the O(m^2) product against the updated factor.  w: the deletion's operands (a private copy: the deletion's own
+// workspace moves on); J.M / J.ld / J.p address the block's columns of the old factor (the logged copy).
+__global__ void __launch_bounds__(NTHREADS) k_T_leave(const __grid_constant__ AlgJobs J, RmGeom g, RmWork w) {
+  extern __shared__ __align__(16) unsigned char rm_smem_raw[];
+  RmStripStage* st = reinterpret_cast<RmStripStage*>(rm_smem_raw);
+  __shared__ double sH[NP][RM_SW];
+  const AlgPos P = alg_eff(J.pos[blockIdx.x]);
+  const int tid = threadIdx.x, nc = P.ncols;
+  if (nc <= 0) return;
+  double* T = const_cast<double*>(P.T);
+  const int64_t str = P.stride;
+  {  // carriers: rows p .. p+n-1 (b_k = M[k, p .. p+n), lower triangular inside the block)
+    const int q = tid / RM_SW, c = tid % RM_SW;
+    double run = 0.0;
+    if (q < g.n && c < nc)
+      for (int a = q; a < g.n; ++a) run += J.M[(int64_t)(g.p + a) * J.ld + J.p + q] * T[(int64_t)c * str + g.p + a];
+    sH[q][c] = run;
+  }
+  auto issue = [&](int I, RmStripStage& S) {
+    const int bx = I - g.I0;
+    for (int idx = tid; idx < TB * RM_SW; idx += NTHREADS) {
+      const int c = idx / TB, r = idx % TB, ip = I * TB + r;  // consecutive threads: consecutive rows of one column
+      double* dst = S.sB + r * LD_SW + c;
+      if (ip >= g.mnew || c >= nc) *dst = 0.0;
+      else cp_async8(dst, T + (int64_t)c * str + (ip < g.p ? ip : ip + g.n));
+    }
+    const double* Ss = w.S + (int64_t)bx * (TB * TB);
+    for (int idx = tid; idx < TB * TB / 2; idx += NTHREADS) {
+      const int r = idx >> 5, c = (idx & 31) << 1;
+      cp_async16(S.sA + r * LD_W + c, Ss + r * TB + c);
+    }
+    for (int idx = tid; idx < TB * NP / 2; idx += NTHREADS) {
+      const int r = idx / (NP / 2), a = (idx % (NP / 2)) * 2;
+      cp_async16(S.sA + r * LD_W + TB + a, w.Gt + ((int64_t)bx * TB + r) * NP + a);
+      cp_async16(S.sBt + r * LD_BT + a, w.Bt + ((int64_t)bx * TB + r) * NP + a);
+    }
+    if (tid < TB / 2) cp_async16(S.su + 2 * tid, w.u + (int64_t)bx * TB + 2 * tid);
+  };
+  const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  issue(g.I0, st[0]);
+  cp_async_commit();
+  int cur = 0;
+  for (int I = g.I0; I < g.nbn; ++I, cur ^= 1) {
+    RmStripStage& S = st[cur];
+    if (I + 1 < g.nbn) issue(I + 1, st[cur ^ 1]);
+    cp_async_commit();
+    cp_async_wait<1>();
+    S.sB[(TB + tid / RM_SW) * LD_SW + tid % RM_SW] = sH[tid / RM_SW][tid % RM_SW];
+    __syncthreads();
+    Acc<1, 2> acc;
+    acc.zero();
+    {
+      const double* arow = S.sA + (8 * warp + gq) * LD_W;
+      auto kstep = [&](int kb) {
+        const double a = arow[kb + tq];
+        const double b0 = S.sB[(kb + tq) * LD_SW + gq], b1 = S.sB[(kb + tq) * LD_SW + 8 + gq];
+        dmma884(acc.v[0][0][0], acc.v[0][0][1], a, b0);
+        dmma884(acc.v[0][1][0], acc.v[0][1][1], a, b1);
+      };
+      for (int kb = 0; kb < 8 * warp + 8; kb += 4) kstep(kb);
+#pragma unroll
+      for (int kb = TB; kb < TB + NP; kb += 4) kstep(kb);
+    }
+    {
+      const int r = 8 * warp + gq, ip = I * TB + r;
+      if (ip >= g.p) {  // (rows above the block stay as they are)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 8 * j + 2 * tq + e;
+            if (c < nc) T[(int64_t)c * str + ip] = ip < g.mnew ? S.su[r] * (S.sB[r * LD_SW + c] - acc.v[0][j][e]) : 0.0;
+          }
+      }
+    }
+    if (warp < 4) {
+      Acc<1, 1> hp;
+      hp.zero();
+      warp_mma<1, 1, false, false, TB, LD_BT, LD_SW>(hp, S.sBt, S.sB, 8 * (warp >> 1), 8 * (warp & 1));
+      const int q = 8 * (warp >> 1) + gq, c = 8 * (warp & 1) + 2 * tq;
+      sH[q][c] += hp.v[0][0][0];
+      sH[q][c + 1] += hp.v[0][0][1];
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  // the result is n rows shorter: rows [mnew, m) beyond the last tile written become padding (zero) again
+  for (int idx = tid; idx < nc * g.n; idx += NTHREADS) {
+    const int c = idx / g.n, ip = g.mnew + idx % g.n;
+    if (ip >= g.nbn * TB && ip < str) T[(int64_t)c * str + ip] = 0.0;
+  }
+}
+
 // x, y of the result (new order = old order with the block dropped).
 __global__ void k_rm_vec(const double* __restrict__ xo, const double* __restrict__ yo, double* __restrict__ xn,
                          double* __restrict__ yn, RmGeom g) {
@@ -768,13 +879,13 @@ struct ApWork {
   double *Li, *znew, *gpart, *part;
 };
 
-// Partial Gram matrices of T (n columns x mpad rows, T[c*mpad + r]): gpart[blk][(a,b)] over 256 rows.
-__global__ void __launch_bounds__(256) k_append_gram(const double* __restrict__ T, int mpad, int n, ApWork w) {
+// Partial Gram matrices of T (n columns x mpad rows, T[c*tstride + r]): gpart[blk][(a,b)] over 256 rows.
+__global__ void __launch_bounds__(256) k_append_gram(const double* __restrict__ T, int mpad, int64_t tstride, int n, ApWork w) {
   __shared__ double sT[NP][AP_GRAM_ROWS + 1];
   const int r0 = blockIdx.x * AP_GRAM_ROWS;
   for (int idx = threadIdx.x; idx < NP * AP_GRAM_ROWS; idx += 256) {
     int a = idx / AP_GRAM_ROWS, r = idx % AP_GRAM_ROWS;
-    sT[a][r] = (a < n && r0 + r < mpad) ? T[(int64_t)a * mpad + r0 + r] : 0.0;
+    sT[a][r] = (a < n && r0 + r < mpad) ? T[(int64_t)a * tstride + r0 + r] : 0.0;
   }
   __syncthreads();
   if (threadIdx.x < NG) {
@@ -851,7 +962,7 @@ __global__ void __launch_bounds__(256) k_append_small(const double* __restrict__
 constexpr int AP_STAGE = TB * LD_R + NP * LD_C;  // doubles per stage: M tile [k][c] | raw T slice [q][k]
 constexpr int AP_ROWS_SMEM = (2 * AP_STAGE + NP * LD_C) * (int)sizeof(double);
 __global__ void __launch_bounds__(NTHREADS) k_append_rows(const double* __restrict__ M, int64_t ld, int nb, int mpad,
-                                                          const double* __restrict__ T, int n, ApWork w) {
+                                                          const double* __restrict__ T, int64_t tstride, int n, ApWork w) {
   extern __shared__ __align__(16) double smem[];
   double* sC = smem + 2 * AP_STAGE;  // (Li T^T) tile [i][k], LD_C
   __shared__ double sLi[NP][NP + 1];
@@ -866,7 +977,7 @@ __global__ void __launch_bounds__(NTHREADS) k_append_rows(const double* __restri
     load_tile_async<LD_R>(sT, M + (int64_t)kb * TB * ld + (int64_t)J * TB, ld);
     for (int idx = threadIdx.x; idx < NP * TB / 2; idx += NTHREADS) {
       const int q = idx >> 5, k = (idx & 31) << 1;
-      if (q < n) cp_async16(sR + q * LD_C + k, T + (int64_t)q * mpad + kb * TB + k);
+      if (q < n) cp_async16(sR + q * LD_C + k, T + (int64_t)q * tstride + kb * TB + k);
     }
   };
   int stage = 0;
@@ -934,6 +1045,7 @@ inline void update_set_attributes() {
   cudaFuncSetAttribute(k_rm_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_PREP_SMEM);
   cudaFuncSetAttribute(k_rm_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_APPLY_SMEM);
   cudaFuncSetAttribute(k_rm_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_STRIP_SMEM);
+  cudaFuncSetAttribute(k_T_leave, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_STRIP_SMEM);
   cudaFuncSetAttribute(k_append_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_ROWS_SMEM);
 }
 

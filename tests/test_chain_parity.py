@@ -114,10 +114,12 @@ def test_fast_sweeps_match_oracle(eng, kernel, mean_func, threshold, single_blas
 
 @pytest.mark.parametrize("lookahead,pipeline,env", [(16, 2, {}), (32, 2, {}), (48, 2, {}), (64, 2, {}), (32, 1, {}),
                                                     (48, 2, {"MOGP_RANK_RESCORE": "0"}),   # every change re-scored
-                                                    (48, 2, {"MOGP_REPLAY": "1"}),         # corrections queued ahead for the next batch's positions
+                                                    (48, 2, {"MOGP_TMAINT": "0"}),         # cached columns not kept current: one correction per cluster and batch, the rest re-scored
+                                                    (32, 2, {"MOGP_TMAINT": "0"}),
                                                     (48, 2, {"MOGP_LAUNCH_AFTER": "1", "MOGP_ZIGZAG": "1"}),
                                                     (48, 2, {"MOGP_PRUNE": "0"}),          # threshold rule after the product only
-                                                    (64, 2, {"MOGP_CHECK_CORRECTIONS": "1"})])
+                                                    (64, 2, {"MOGP_CHECK_CORRECTIONS": "1"}),
+                                                    (64, 2, {"MOGP_CHECK_CORRECTIONS": "2"})])
 def test_lookahead_window_equals_patient_by_patient(eng, lookahead, pipeline, env, monkeypatch):
     """mogp_chain_sweep with the look-ahead pipeline (batches of patients scored per pass over the factors, the next
     batch's pass running while the current batch moves, cached scores corrected by rank-n formulas or re-scored against
@@ -158,13 +160,18 @@ def test_lookahead_window_equals_patient_by_patient(eng, lookahead, pipeline, en
         assert abs(l0[k] - l1[k]) <= 1e-9 * max(1.0, abs(l0[k]))
 
 
-def test_rank_n_score_corrections_equal_rescoring(eng, monkeypatch):
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_rank_n_score_corrections_equal_rescoring(eng, monkeypatch, mode):
     """After a move the cached scores of the patients ahead under the two clusters it changed are corrected by rank-n
-    formulas (k_alg_leave / k_alg_join) while the factors are still being updated.  In check mode every corrected pair is
-    re-scored from the UPDATED factor: log-likelihoods and threshold means agree within 1e-9 relative."""
+    formulas (k_alg_leave / k_alg_join) while the factors are still being updated, and the cached columns T = M Kx, ss, mu
+    are brought to the changed cluster on the device (k_T_leave, the write-backs of the corrections), for this batch and -
+    chained behind its pass - for the next.  In check mode every corrected pair is re-scored from the UPDATED factor:
+    log-likelihoods and threshold means agree within 1e-9 relative.  Mode 1: the re-scored columns take over (every
+    correction starts from fresh columns); mode 2: compare only - corrections keep building on maintained columns, and the
+    scores a batch takes from the corrections chained behind its pass are checked when it starts."""
     from mogp_b200 import MoGP_constrained
     from mogp_b200.synth import alsfrs_like, block_init
-    monkeypatch.setenv("MOGP_CHECK_CORRECTIONS", "1")
+    monkeypatch.setenv("MOGP_CHECK_CORRECTIONS", mode)
     N = 600
     X, Y = alsfrs_like(N, seed=11)
     z0 = block_init(N, 5, X)
@@ -177,8 +184,12 @@ def test_rank_n_score_corrections_equal_rescoring(eng, monkeypatch):
     c1 = eng.chain_counters()
     checked = c1["corrections_checked"] - c0["corrections_checked"]
     print("pairs checked:", checked, "worst relative disagreement:", c1["max_correction_err"])
+    print("batches served by chained corrections:", c1["replayed"] - c0["replayed"], "re-scoring passes:",
+          c1["rescoring_passes"] - c0["rescoring_passes"])
     assert c1["rank_corrections"] - c0["rank_corrections"] > 50 and checked > 200
     assert c1["max_correction_err"] <= 1e-9
+    if mode == "2":
+        assert c1["replayed"] - c0["replayed"] > 20
 
 
 @pytest.mark.slow
