@@ -22,6 +22,9 @@ alpha/seed-sweep sharding of SURVEY.md §8(e); a single chain is strictly sequen
 import argparse
 import json
 import os
+
+# before anything creates the CUDA context (mogp_b200/__init__.py explains): one hardware queue per stream of the pipeline
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import threading
@@ -446,7 +449,8 @@ def run_b200(args):
                           "start": "sweeps {}..{} of a chain started from the generator's classes".format(args.warmup + 1, args.warmup + args.steps),
                           "lookahead": {k: counters[k] for k in ("window_passes", "rescoring_passes", "window_patients",
                                                                  "open_s", "rescore_s", "commit_s", "rank_corrections", "correct_s", "replayed",
-                                                                 "window_pairs", "pruned_pairs")}}}
+                                                                 "window_pairs", "pruned_pairs", "chained_wait_s",
+                                                                 "chained_corrections")}}}
         if world == 1 and not args.no_cpu_baseline:
             line.update(cpu_and_parity(args, local))
     secondary = {}

@@ -108,7 +108,9 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
    out[14] = with MOGP_CHECK_CORRECTIONS=1 in the environment: worst relative disagreement between a rank-n corrected
    score / threshold mean and the same pair re-scored from the updated factor, out[15] = pairs checked,
    out[16] = (patient, cluster) pairs of the window passes, out[17] = those the monotonicity rule excluded on the device
-   before the O(m^2) product (their mean alone decides, mogp_constrained.py:254-266). */
+   before the O(m^2) product (their mean alone decides, mogp_constrained.py:254-266),
+   out[18] = host seconds waiting, when a batch starts, for the corrections chained behind its pass, out[19] = how many
+   corrections were chained behind passes in flight. */
 int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out);
 
 /* ---- one cluster's GP = one GPobs object ------------------------------------------------- */

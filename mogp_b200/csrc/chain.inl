@@ -40,12 +40,14 @@ int t_mark(mogp_engine* h, cudaStream_t s, int bi, int32_t slot) {
 int fire_leave_hook(mogp_engine* h, const RmGeom& g, const RmWork& w, int nT) {
   LeaveHook* hk = h->leave_hook;
   h->leave_hook = nullptr;
-  if (hk->npos[0] <= 0 && hk->npos[1] <= 0) return MOGP_OK;
+  bool any = false;
+  for (int t = 0; t < NTGT; ++t) any = any || hk->npos[t] > 0;
+  if (!any) return MOGP_OK;
   const int64_t used = (w.S + (int64_t)nT * TB * TB) - w.Bt;
   if (!h->d_tsw || used > h->tsw_slot) return MOGP_OK;  // not fired: the step falls back to re-scoring
   const int k = h->tsw_next;
   h->tsw_next = (k + 1) % TS_RING;
-  for (int t = 0; t < 2; ++t)
+  for (int t = 0; t < NTGT; ++t)
     if (h->tsw_done[k][t]) CK(h, cudaStreamWaitEvent(h->stream, h->tsw_done[k][t], 0));
   double* dst = h->d_tsw + (int64_t)k * h->tsw_slot;
   CK(h, cudaMemcpyAsync(dst, w.Bt, sizeof(double) * (size_t)used, cudaMemcpyDeviceToDevice, h->stream));
@@ -59,9 +61,9 @@ int fire_leave_hook(mogp_engine* h, const RmGeom& g, const RmWork& w, int nT) {
   wc.own = dst + (w.own - w.Bt);
   wc.gsol = dst + (w.gsol - w.Bt);
   wc.S = dst + (w.S - w.Bt);
-  for (int t = 0; t < 2; ++t) {
+  for (int t = 0; t < NTGT; ++t) {
     if (hk->npos[t] <= 0) continue;
-    cudaStream_t s = t == 0 ? h->ts0 : h->ts1;
+    cudaStream_t s = t == 0 ? h->ts0 : h->ts1[hk->bi[t]];
     CK(h, cudaStreamWaitEvent(s, h->tsw_cp, 0));
     TRY(t_wait(h, s, hk->bi[t], hk->slot));
     k_T_leave<<<(unsigned)hk->npos[t], NTHREADS, RM_STRIP_SMEM, s>>>(hk->J[t], g, wc);
@@ -721,9 +723,12 @@ int window_cols(const Chain& ch) {
   int v = env >= 0 ? env : (ch.cfg.lookahead == 0 ? 64 : ch.cfg.lookahead);
   return v <= 0 ? 0 : std::min(v, 64);
 }
-int pipeline_depth() {  // 2: the next batch's pass overlaps the current batch's moves; 1: one batch at a time
-  const int env = env_int("MOGP_PIPELINE", 2);
-  return env >= 2 ? 2 : 1;
+bool tmaint_on();
+int pipeline_depth() {  // 1: one batch at a time; 2: the next batch's pass overlaps the current batch's moves; 3: the next two
+  // (a pass launched two batches ahead is stale under every cluster that changes meanwhile: worth it only when those are
+  // brought up to date by the corrections chained behind it, MOGP_TMAINT)
+  const int env = env_int("MOGP_PIPELINE", tmaint_on() ? 3 : 2);
+  return std::max(1, std::min(env, NTGT));
 }
 
 void win_size_slots(Chain::Window& w, size_t n) {
@@ -732,10 +737,11 @@ void win_size_slots(Chain::Window& w, size_t n) {
   w.slot_T_ok.resize(n, 0);
   w.slot_alg.resize(n, 0);
   w.slot_epoch.resize(n, 0);
-  w.slot_tev[0].resize(n, -1);
-  w.slot_tev[1].resize(n, -1);
-  w.rp_epoch.resize(n, -1);
-  w.rp_last.resize(n, -1);
+  for (int i = 0; i < NBUF; ++i) {
+    w.slot_tev[i].resize(n, -1);
+    w.rp_epoch[i].resize(n, -1);
+    w.rp_last[i].resize(n, -1);
+  }
 }
 
 // The cluster in `slot` changed (rows appended / deleted, freed, created): cached scores under it are stale.
@@ -838,19 +844,27 @@ int win_prepare(mogp_engine* h, int64_t n_steps, const int64_t* order, const dou
   w.slot_T_ok.assign(h->cl.size(), 0);
   w.slot_alg.assign(h->cl.size(), 0);
   w.slot_epoch.assign(h->cl.size(), 0);
-  w.slot_tev[0].assign(h->cl.size(), -1);
-  w.slot_tev[1].assign(h->cl.size(), -1);
-  w.rp_epoch.assign(h->cl.size(), -1);
-  w.rp_last.assign(h->cl.size(), -1);
+  for (int i = 0; i < NBUF; ++i) {
+    w.slot_tev[i].assign(h->cl.size(), -1);
+    w.rp_epoch[i].assign(h->cl.size(), -1);
+    w.rp_last[i].assign(h->cl.size(), -1);
+    w.async_items[i].clear();
+    w.rpw_used[i] = 0;
+  }
+  w.flight.clear();
   w.batch_end = 0;
-  w.async_items.clear();
-  w.rpw_used = 0;
   w.cur_bi = 0;
   {  // partial sums of the corrections queued ahead: room for REPLAY_MAX of them against the largest cluster
     int64_t maxcap = TB;
     for (const Cluster& c : h->cl)
       if (c.used) maxcap = std::max(maxcap, c.cap);
-    TRY(ensure(h, &h->d_rpw, &h->rpw_elems, (int64_t)REPLAY_MAX * OWN_BATCH * (maxcap / TB + 8) * ALG_ENTRIES));
+    {  // (a share per batch buffer; a correction that does not fit breaks its chain and the cluster is re-scored)
+      const int64_t share = (int64_t)12 * OWN_BATCH * (maxcap / TB + 8) * ALG_ENTRIES;
+      if (share > h->rpw_share) {
+        TRY(ensure(h, &h->d_rpw, &h->rpw_elems, share * NBUF));
+        h->rpw_share = h->rpw_elems / NBUF;
+      }
+    }
     if (tmaint_on()) {  // private copies of the deletions' operands for k_T_leave (fire_leave_hook)
       const int64_t nT = maxcap / TB + 2, rows = nT * TB;
       const int64_t per = rows * NP * 2 + rows + nT * NG + NG + 8 + NP + nT * TB * TB;
@@ -950,6 +964,10 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   b.msz.clear();
   b.prof = h->prof_on;
   win_size_slots(w, h->cl.size());
+  std::fill(w.rp_epoch[bi].begin(), w.rp_epoch[bi].end(), -1);  // (what the buffer's previous pass left)
+  std::fill(w.rp_last[bi].begin(), w.rp_last[bi].end(), -1);
+  w.async_items[bi].clear();
+  w.rpw_used[bi] = 0;
   for (size_t k = 0; k < ch.Nk.size(); ++k)
     if (ch.Nk[k] > 0 && ch.slot_of_id[k] >= 0) {
       const int32_t slot = ch.slot_of_id[k];
@@ -959,8 +977,8 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
       }
       b.slots.push_back(slot);
       b.epoch.push_back(w.slot_epoch[slot]);
-      w.rp_epoch[slot] = w.slot_epoch[slot];  // the pass sees the cluster as it is now; corrections may be chained behind it
-      w.rp_last[slot] = -1;
+      w.rp_epoch[bi][slot] = w.slot_epoch[slot];  // the pass sees the cluster as it is now; corrections may be chained behind it
+      w.rp_last[bi][slot] = -1;
       w.slot_tev[bi][slot] = -1;
       b.mpad.push_back(round_up(h->cl[slot].m, TB));
       b.msz.push_back(h->cl[slot].m);
@@ -977,16 +995,29 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   for (int64_t v = s0; v < s0 + cnt; ++v) w.e[v].assign(h->cl.size(), Chain::WinEntry());
   const int64_t Rtot = w.col0[w.n], cb = w.col0[s0], R = w.col0[s0 + cnt] - cb;
   if (h->side_pending) join_side(h);
+  h->ahead = h->ahead_ring[bi];
+  // the product of this pass starts when that of the pass launched before it ends (its preamble does not wait)
+  bf.res.wide_after = h->last_wide;
+  h->last_wide = bf.res.wide_done;
   CK(h, cudaEventRecord(h->ev_fork, h->main_stream));
   CK(h, cudaStreamWaitEvent(h->ahead, h->ev_fork, 0));
   CK(h, cudaStreamWaitEvent(h->ahead2, h->ev_fork, 0));
-  if (tmaint_on()) {  // this pass overwrites columns the maintenance kernels of the batch before last may still be working on
-    cudaStream_t ms[3] = {h->ts0, h->ts1, h->tq};
-    for (int q = 0; q < 3; ++q) {
-      if (!h->ev_ts[q]) CK(h, cudaEventCreateWithFlags(&h->ev_ts[q], cudaEventDisableTiming));
-      CK(h, cudaEventRecord(h->ev_ts[q], ms[q]));
-      CK(h, cudaStreamWaitEvent(h->ahead, h->ev_ts[q], 0));
+  if (tmaint_on()) {
+    // This pass overwrites columns that maintenance kernels worked on when the buffer last held a batch, and that the
+    // corrections chained behind later passes read (the joiner's T): behind the correction streams of every buffer whose
+    // pass is not in flight (those of the passes in flight wait for passes this one is queued behind anyway) ...
+    for (int q = 0; q < NBUF; ++q) {
+      if (std::find(w.flight.begin(), w.flight.end(), q) != w.flight.end()) continue;
+      cudaStream_t ms[2] = {h->ts1[q], h->tq[q]};
+      for (int e = 0; e < 2; ++e) {
+        cudaEvent_t& ev = h->ev_ts[2 * q + e];
+        if (!ev) CK(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CK(h, cudaEventRecord(ev, ms[e]));
+        CK(h, cudaStreamWaitEvent(h->ahead, ev, 0));
+      }
     }
+    // ... and behind the in-batch maintenance of the batch the buffer last held
+    if (h->ev_ts_end[bi]) CK(h, cudaStreamWaitEvent(h->ahead, h->ev_ts_end[bi], 0));
   }
   b.own_slot.assign(cnt, -1);
   b.own_epoch.assign(cnt, 0);
@@ -1095,28 +1126,26 @@ int batch_absorb(mogp_engine* h, int bi) {
 // and the batch, once absorbed, finds current columns.  By the time the batch is absorbed the corrected scores are in
 // pinned memory: no launch, no wait.  A cluster whose chain breaks (new / emptied, no room, a change that could not be
 // expressed) is re-scored the long way as before.
-int replay_launch(mogp_engine* h, const ChangeLog& L, cudaEvent_t dep, AlgJobs* Jout, int* npos_out, bool* queued) {
+int replay_launch(mogp_engine* h, const ChangeLog& L, cudaEvent_t dep, int nbi, AlgJobs* Jout, int* npos_out, bool* queued) {
   Chain& ch = h->chain;
   Chain::Window& w = ch.win;
   *queued = false;
-  if (w.end_launched <= w.batch_end) return MOGP_OK;  // no pass in flight
   const int32_t slot = L.slot;
-  if (slot < 0 || slot >= (int32_t)w.rp_epoch.size()) return MOGP_OK;
+  if (slot < 0 || slot >= (int32_t)w.rp_epoch[nbi].size()) return MOGP_OK;
   auto broken = [&]() {
-    w.rp_epoch[slot] = -1;
+    w.rp_epoch[nbi][slot] = -1;
     return MOGP_OK;
   };
-  if (w.rp_epoch[slot] < 0 || w.rp_epoch[slot] != L.epoch_before) return broken();
-  const int nbi = w.cur_bi ^ 1;
+  if (w.rp_epoch[nbi][slot] < 0 || w.rp_epoch[nbi][slot] != L.epoch_before) return broken();
   const Chain::Batch& nb = w.b[nbi];
   const BatchBuf& nbf = h->bb[nbi];
-  if (nb.cnt <= 0 || nb.cnt > OWN_BATCH || (int)w.async_items.size() >= REPLAY_MAX || L.ntiles <= 0) return broken();
+  if (nb.cnt <= 0 || nb.cnt > OWN_BATCH || (int)w.async_items[nbi].size() >= REPLAY_MAX || L.ntiles <= 0) return broken();
   int si = -1;
   for (size_t q = 0; q < nb.slots.size(); ++q)
     if (nb.slots[q] == slot) si = (int)q;
   if (si < 0) return broken();  // not in that pass
   const int64_t wneed = nb.cnt * (int64_t)L.ntiles * (L.kind == 0 ? ALG_ENTRIES : NP * NP);
-  if (w.rpw_used + wneed > h->rpw_elems) return broken();
+  if (w.rpw_used[nbi] + wneed > h->rpw_share) return broken();
   if (L.kind == 1 && (int64_t)L.J.m + L.J.n > nb.mpad[si]) return broken();  // no room for the rows the join adds
   AlgJobs J = L.J;
   J.maintain = 1;
@@ -1137,39 +1166,40 @@ int replay_launch(mogp_engine* h, const ChangeLog& L, cudaEvent_t dep, AlgJobs* 
     P.thr = J.thr_index;
     P.flag = nbf.d_out + q * ns + si;  // the pair's score as the pass leaves it: -inf = excluded before the product
   }
-  const int k = (int)w.async_items.size();
-  J.out = h->d_replay + (int64_t)k * 2 * OWN_BATCH;
+  const int k = (int)w.async_items[nbi].size();
+  const int64_t out_off = ((int64_t)nbi * REPLAY_MAX + k) * 2 * OWN_BATCH;
+  J.out = h->d_replay + out_off;
   J.logB = J.logAlpha = nullptr;
-  double* part = h->d_rpw + w.rpw_used;
-  w.rpw_used += wneed;
+  double* part = h->d_rpw + (int64_t)nbi * h->rpw_share + w.rpw_used[nbi];
+  w.rpw_used[nbi] += wneed;
+  cudaStream_t tq = h->tq[nbi];
   // behind the pass they correct (its kernels, not its read-back), behind what the move contributes (logged copies /
   // Ls^-1, z_B) and behind whatever last touched these columns
-  CK(h, cudaStreamWaitEvent(h->tq, nbf.scored, 0));
-  CK(h, cudaStreamWaitEvent(h->tq, dep, 0));
-  TRY(t_wait(h, h->tq, nbi, slot));
+  CK(h, cudaStreamWaitEvent(tq, nbf.scored, 0));
+  CK(h, cudaStreamWaitEvent(tq, dep, 0));
+  TRY(t_wait(h, tq, nbi, slot));
   if (L.kind == 0) {
-    k_alg_leave_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, h->tq>>>(J, part);
+    k_alg_leave_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, tq>>>(J, part);
     LAUNCHED(h);
-    k_alg_leave_fin<<<(unsigned)nb.cnt, 256, 0, h->tq>>>(J, part, L.ntiles);
+    k_alg_leave_fin<<<(unsigned)nb.cnt, 256, 0, tq>>>(J, part, L.ntiles);
     LAUNCHED(h);
   } else {
-    k_alg_join_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, h->tq>>>(J, part);
+    k_alg_join_part<<<dim3((unsigned)L.ntiles, (unsigned)nb.cnt), 256, 0, tq>>>(J, part);
     LAUNCHED(h);
-    k_alg_join_fin<<<(unsigned)nb.cnt, 256, 0, h->tq>>>(J, part, L.ntiles);
+    k_alg_join_fin<<<(unsigned)nb.cnt, 256, 0, tq>>>(J, part, L.ntiles);
     LAUNCHED(h);
   }
-  TRY(t_mark(h, h->tq, nbi, slot));
-  CK(h, cudaMemcpyAsync(h->h_replay + (int64_t)k * 2 * OWN_BATCH, J.out, sizeof(double) * 2 * OWN_BATCH, cudaMemcpyDeviceToHost,
-                        h->tq));
-  CK(h, cudaEventRecord(h->ev_replay, h->tq));
+  TRY(t_mark(h, tq, nbi, slot));
+  CK(h, cudaMemcpyAsync(h->h_replay + out_off, J.out, sizeof(double) * 2 * OWN_BATCH, cudaMemcpyDeviceToHost, tq));
+  CK(h, cudaEventRecord(h->ev_replay[nbi], tq));
   h->bytes_d2h += (int64_t)sizeof(double) * 2 * OWN_BATCH;
   Chain::Window::AsyncItem it;
   it.slot = slot;
   it.epoch_before = L.epoch_before;
   it.out_idx = k;
-  w.async_items.push_back(it);
-  w.rp_epoch[slot] = L.epoch_before + 1;
-  w.rp_last[slot] = k;
+  w.async_items[nbi].push_back(it);
+  w.rp_epoch[nbi][slot] = L.epoch_before + 1;
+  w.rp_last[nbi][slot] = k;
   if (Jout) *Jout = J;
   if (npos_out) *npos_out = (int)nb.cnt;
   *queued = true;
@@ -1183,17 +1213,18 @@ int win_replay(mogp_engine* h, int bi) {
   Chain& ch = h->chain;
   Chain::Window& w = ch.win;
   Chain::Batch& b = w.b[bi];
-  if (w.async_items.empty()) return MOGP_OK;
+  if (w.async_items[bi].empty()) return MOGP_OK;
   {
-    PhaseTimer pt(&ch.t_alg);
-    CK(h, cudaEventSynchronize(h->ev_replay));
+    PhaseTimer pt(&ch.t_chain);
+    CK(h, cudaEventSynchronize(h->ev_replay[bi]));
   }
+  ch.win_chained += (int64_t)w.async_items[bi].size();
   for (size_t si = 0; si < b.slots.size(); ++si) {
     const int32_t slot = b.slots[si];
     if (slot < 0 || slot >= (int32_t)w.slot_epoch.size() || !h->cl[slot].used) continue;
     if (w.slot_epoch[slot] == b.epoch[si]) continue;  // unchanged: batch_absorb took the pass's own scores
-    if (w.rp_epoch[slot] != w.slot_epoch[slot] || w.rp_last[slot] < 0 || w.slot_upto[slot] > b.s0) continue;
-    const double* out = h->h_replay + (int64_t)w.rp_last[slot] * 2 * OWN_BATCH;
+    if (w.rp_epoch[bi][slot] != w.slot_epoch[slot] || w.rp_last[bi][slot] < 0 || w.slot_upto[slot] > b.s0) continue;
+    const double* out = h->h_replay + ((int64_t)bi * REPLAY_MAX + w.rp_last[bi][slot]) * 2 * OWN_BATCH;
     bool reopened = false;
     for (int64_t q = 0; q < b.cnt; ++q) {
       Chain::WinEntry& e = w.e[b.s0 + q][slot];
@@ -1211,8 +1242,8 @@ int win_replay(mogp_engine* h, int bi) {
     w.slot_T_ok[slot] = 1;
     ch.win_replayed += 1;
   }
-  w.async_items.clear();
-  w.rpw_used = 0;
+  w.async_items[bi].clear();
+  w.rpw_used[bi] = 0;
   return MOGP_OK;
 }
 
@@ -1397,15 +1428,21 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
   const int64_t npos = w.batch_end - (w.cur + 1);
   const bool alg_on = !stays && npos >= 0 && npos <= OWN_BATCH && ch.pending_lazy && env_int("MOGP_RANK_RESCORE", 1) != 0;
   const bool tm = tmaint_on();
-  const bool log_on = alg_on && tm && w.end_launched > w.batch_end;  // a next batch's pass is in flight
+  const bool log_on = alg_on && tm && !w.flight.empty();  // passes of later batches are in flight
   const int thr_cfg = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
   auto alg_ok = [&](int32_t slot) {
     return slot >= 0 && slot < (int32_t)w.slot_upto.size() && w.slot_upto[slot] >= w.batch_end && w.slot_T_ok[slot] &&
            (tm || !w.slot_alg[slot]);
   };
-  auto replay_ready = [&](int32_t slot) {  // every change since the next batch's pass was launched is chained behind it
-    return log_on && slot >= 0 && slot < (int32_t)w.rp_epoch.size() && w.rp_epoch[slot] >= 0 &&
-           w.rp_epoch[slot] == w.slot_epoch[slot];
+  auto chain_ok = [&](int f, int32_t slot) {  // every change since the pass in buffer f was launched is chained behind it
+    return slot >= 0 && slot < (int32_t)w.rp_epoch[f].size() && w.rp_epoch[f][slot] >= 0 &&
+           w.rp_epoch[f][slot] == w.slot_epoch[slot];
+  };
+  auto replay_ready = [&](int32_t slot) {
+    if (!log_on) return false;
+    for (int f : w.flight)
+      if (chain_ok(f, slot)) return true;
+    return false;
   };
   auto fill_pos = [&](AlgJobs& J, int32_t slot) {
     for (int64_t q = 0; q < npos; ++q) {
@@ -1491,10 +1528,20 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
           cl.J = Jlog;
           cl.ntiles = ntiles;
           cl.epoch_before = w.slot_epoch[a_slot];
-          TRY(replay_launch(h, cl, h->ev_q2, &lhook.J[1], &lhook.npos[1], &a_rp));
-          if (!a_rp) lhook.npos[1] = 0;
+          int t = 1;
+          for (int f : w.flight) {
+            if (!chain_ok(f, a_slot)) continue;
+            bool queued = false;
+            if (t < NTGT) TRY(replay_launch(h, cl, h->ev_q2, f, &lhook.J[t], &lhook.npos[t], &queued));
+            if (!queued) {
+              w.rp_epoch[f][a_slot] = -1;
+              continue;
+            }
+            lhook.bi[t++] = f;
+            a_rp = true;
+          }
         } else if (a1) {
-          w.rp_epoch[a_slot] = -1;
+          for (int f : w.flight) w.rp_epoch[f][a_slot] = -1;
         }
         if (J.maintain && (np0 > 0 || a_rp)) {  // the T of the positions ahead follows in remove_core (k_T_leave)
           lhook.slot = a_slot;
@@ -1503,7 +1550,6 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
             lhook.npos[0] = (int)np0;
             lhook.bi[0] = w.cur_bi;
           }
-          lhook.bi[1] = w.cur_bi ^ 1;
           h->leave_hook = &lhook;
         }
         a_maint = J.maintain != 0;
@@ -1542,20 +1588,23 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
   }
   if (!stays) {
     const bool b_alg = hook.fired;
-    if (a_rp && !lhook.fired[1]) w.rp_epoch[a_slot] = -1;  // the correction was queued but T did not follow
-    if (b_slot >= 0 && replay_ready(b_slot)) {
-      bool queued = false;
-      if (b_alg && hook.on_quick) {
-        ChangeLog cl;
-        cl.slot = b_slot;
-        cl.kind = 1;
-        cl.J = hook.jobs;  // Tn, Li, znew, xn stay valid until the next batch has been absorbed
-        cl.ntiles = hook.ntiles;
-        cl.epoch_before = w.slot_epoch[b_slot];
-        TRY(replay_launch(h, cl, h->ev_alg, nullptr, nullptr, &queued));
+    for (int t = 1; t < NTGT; ++t)  // a correction was queued but T did not follow
+      if (lhook.npos[t] > 0 && !lhook.fired[t]) w.rp_epoch[lhook.bi[t]][a_slot] = -1;
+    if (b_slot >= 0 && log_on)
+      for (int f : w.flight) {
+        if (!chain_ok(f, b_slot)) continue;
+        bool queued = false;
+        if (b_alg && hook.on_quick) {
+          ChangeLog cl;
+          cl.slot = b_slot;
+          cl.kind = 1;
+          cl.J = hook.jobs;  // Tn, Li, znew, xn stay valid until the passes in flight have been absorbed
+          cl.ntiles = hook.ntiles;
+          cl.epoch_before = w.slot_epoch[b_slot];
+          TRY(replay_launch(h, cl, h->ev_alg, f, nullptr, nullptr, &queued));
+        }
+        if (!queued) w.rp_epoch[f][b_slot] = -1;
       }
-      if (!queued) w.rp_epoch[b_slot] = -1;
-    }
     if ((a_alg || b_alg) && npos > 0) {
       PhaseTimer pt(&ch.t_alg);
       if (b_alg) CK(h, cudaStreamWaitEvent(h->quick, h->ev_alg, 0));
@@ -1620,85 +1669,94 @@ int sweep_pipelined(mogp_engine* h, int64_t n_steps, const int64_t* order, const
   Chain::Window& w = ch.win;
   TRY(win_prepare(h, n_steps, order, a_draw));
   const int depth = pipeline_depth();
-  int64_t pos = 0, jb = 0;
-  bool have_next = false;
+  int64_t pos = 0;          // position being processed
+  int64_t launch_pos = 0;   // first position without a pass
+  int64_t jl = 0;           // passes launched so far: pass j lives in buffer j % NBUF
+  std::deque<int> pending;  // buffers of the passes launched and not yet absorbed, oldest first
   while (pos < n_steps) {
-    if (!have_next) {
+    if (pending.empty()) {
       const int64_t cnt = batch_form(h, pos, max_cols);
       if (cnt == 0) {  // no visits / too many for a rank update: patient-by-patient step; the cache starts over
         int32_t chosen = -1;
         w.cur = w.end_launched = pos + 1;
+        w.flight.clear();
         TRY(mogp_chain_step(h, order[pos], a_draw ? a_draw[pos] : 0.0, u[pos], &chosen, nullptr, nullptr, nullptr, nullptr, 0));
         win_invalidate_all(ch);
         if (chosen_ids) chosen_ids[pos] = chosen;
         *mm = std::min(*mm, ch.last_margin);
         ++pos;
+        launch_pos = pos;
         continue;
       }
       w.cur = pos;
-      TRY(batch_launch(h, (int)(jb & 1), pos, cnt));
+      w.flight.clear();
+      TRY(batch_launch(h, (int)(jl % NBUF), pos, cnt));
+      pending.push_back((int)(jl % NBUF));
+      ++jl;
+      launch_pos = pos + cnt;
     }
-    Chain::Batch& B = w.b[jb & 1];
+    const int bi = pending.front();
+    pending.pop_front();
+    Chain::Batch& B = w.b[bi];
     {
       PhaseTimer pt(&ch.t_open);
-      TRY(batch_absorb(h, (int)(jb & 1)));
+      TRY(batch_absorb(h, bi));
     }
     w.cur = pos;
     w.batch_end = pos + B.cnt;
-    w.cur_bi = (int)(jb & 1);
-    TRY(win_replay(h, (int)(jb & 1)));
+    w.cur_bi = bi;
+    w.flight.assign(pending.begin(), pending.end());
+    // The passes of the next batches go out now, before this batch makes its moves: every cluster a move changes is stale
+    // in them and is brought up to date by corrections chained behind them (or re-scored when its batch starts).
+    while ((int)pending.size() < depth - 1 && launch_pos < n_steps) {
+      const int64_t cnt2 = batch_form(h, launch_pos, max_cols);
+      if (cnt2 <= 0) break;
+      TRY(batch_launch(h, (int)(jl % NBUF), launch_pos, cnt2));
+      pending.push_back((int)(jl % NBUF));
+      w.flight.push_back((int)(jl % NBUF));
+      ++jl;
+      launch_pos += cnt2;
+    }
+    TRY(win_replay(h, bi));
     if (env_int("MOGP_CHECK_CORRECTIONS", 0) == 2) {  // the scores taken from the corrections chained behind the pass
       std::vector<int32_t> chk;
       for (size_t si = 0; si < B.slots.size(); ++si) {
         const int32_t sl = B.slots[si];
         if (h->cl[sl].used && w.slot_epoch[sl] != B.epoch[si] && w.slot_upto[sl] >= w.batch_end) chk.push_back(sl);
       }
-      TRY(win_check_slots(h, pos, chk, &h->res_bump[jb & 1], false));
+      TRY(win_check_slots(h, pos, chk, &h->res_bump[bi], false));
     }
     w.blog_used = 0;
     {  // room for the logged block columns of this batch's leave-side changes
       int64_t maxm = 0;
       for (const Cluster& c : h->cl)
         if (c.used) maxm = std::max(maxm, c.m);
-      // (two halves, alternating per batch: the kernels queued behind the next batch's pass read this batch's log later)
-      TRY(ensure(h, &h->d_blog, &h->blog_elems, 2 * (int64_t)(OWN_BATCH + 1) * ((maxm + (int64_t)OWN_BATCH * NP) * NP + NP)));
-      w.blog_half = h->blog_elems / 2;
-      w.blog_base = (jb & 1) * w.blog_half;
+      // (one share per batch buffer: the kernels queued behind the passes in flight read this batch's log later)
+      TRY(ensure(h, &h->d_blog, &h->blog_elems, NBUF * (int64_t)(OWN_BATCH + 1) * ((maxm + (int64_t)OWN_BATCH * NP) * NP + NP)));
+      w.blog_half = h->blog_elems / NBUF;
+      w.blog_base = bi * w.blog_half;
     }
     std::fill(w.slot_alg.begin(), w.slot_alg.end(), 0);
-    // re-scoring blocks written two batches ago are no longer referenced
-    ScoreRes& arena = h->res_bump[jb & 1];
-    if (h->ev_ts_end[jb & 1]) CK(h, cudaStreamWaitEvent(h->main_stream, h->ev_ts_end[jb & 1], 0));  // (k_T_leave on them: long done)
+    // re-scoring blocks written NBUF batches ago are no longer referenced
+    ScoreRes& arena = h->res_bump[bi];
+    if (h->ev_ts_end[bi]) CK(h, cudaStreamWaitEvent(h->main_stream, h->ev_ts_end[bi], 0));  // (k_T_leave on them: long done)
     arena.scr_used = 0;
     for (double* p : arena.retired) cudaFree(p);
     arena.retired.clear();
-    have_next = false;
     const int64_t bcnt = B.cnt;
-    const int launch_after = env_int("MOGP_LAUNCH_AFTER", 0);  // steps of this batch before the next pass is launched
     for (int64_t q = 0; q < bcnt; ++q) {
-      // The next batch's pass goes out after the first step: that step starts by re-scoring this batch against the
-      // clusters the previous batch changed (waiting for their updates), which is quicker on a GPU that is not
-      // filling up with the next pass at the same moment.
-      if (depth >= 2 && !have_next && q == std::min<int64_t>(launch_after, bcnt - 1)) {
-        const int64_t np = pos + bcnt;
-        const int64_t cnt2 = np < n_steps ? batch_form(h, np, max_cols) : 0;
-        if (cnt2 > 0) {
-          TRY(batch_launch(h, (int)((jb + 1) & 1), np, cnt2));
-          have_next = true;
-        }
-      }
       int32_t chosen = -1;
       TRY(win_step(h, a_draw ? a_draw[pos + q] : 0.0, u[pos + q], &chosen, &arena));
       if (chosen_ids) chosen_ids[pos + q] = chosen;
       *mm = std::min(*mm, ch.last_margin);
     }
     if (tmaint_on()) {
-      if (!h->ev_ts_end[jb & 1]) CK(h, cudaEventCreateWithFlags(&h->ev_ts_end[jb & 1], cudaEventDisableTiming));
-      CK(h, cudaEventRecord(h->ev_ts_end[jb & 1], h->ts0));
+      if (!h->ev_ts_end[bi]) CK(h, cudaEventCreateWithFlags(&h->ev_ts_end[bi], cudaEventDisableTiming));
+      CK(h, cudaEventRecord(h->ev_ts_end[bi], h->ts0));
     }
     pos += bcnt;
-    ++jb;
   }
+  w.flight.clear();
   return MOGP_OK;
 }
 
@@ -1830,9 +1888,15 @@ int mogp_chain_sweep(mogp_engine* h, int64_t n_steps, const int64_t* order, cons
     int rc = sweep_pipelined(h, n_steps, order, a_draw, u, chosen_ids, &mm, max_cols);
     // whatever happened, nothing of the pipeline stays in flight or cached
     join_side(h);
-    cudaStreamSynchronize(h->ahead);
+    for (int i = 0; i < NBUF; ++i) {
+      cudaStreamSynchronize(h->ahead_ring[i]);
+      cudaStreamSynchronize(h->bb[i].res.pre);
+      cudaStreamSynchronize(h->tq[i]);
+      cudaStreamSynchronize(h->ts1[i]);
+    }
     cudaStreamSynchronize(h->ahead2);
-    cudaStreamSynchronize(h->rq);
+    cudaStreamSynchronize(h->ts0);
+    h->last_wide = nullptr;
     h->chain.win.open = h->chain.win.in_step = false;
     if (rc != MOGP_OK) return rc;
     if (min_margin) *min_margin = mm;

@@ -19,6 +19,7 @@
 #include <chrono>
 #include <string>
 #include <vector>
+#include <deque>
 
 #include "../../include/mogp_b200.h"
 #include "lbfgsb.hpp"
@@ -51,14 +52,17 @@ struct ChangeLog {
 // The leave-side half of keeping the cached T current (k_T_leave): filled by the step that moves a patient, fired by
 // remove_core as soon as the deletion's operands exist (k_rm_prep).  Target 0 = the positions still ahead in the batch being
 // processed, target 1 = the positions of the next batch (their pass, launched before the move, is corrected behind it).
+constexpr int NBUF = 4;       // batch buffers of the look-ahead pipeline: the batch being processed + up to two passes in flight
+                              // + one that stays untouched until the corrections reading it have run
+constexpr int NTGT = 3;       // targets of a move's corrections: the current batch + the passes in flight
 struct LeaveHook {
-  AlgJobs J[2];
-  int npos[2] = {0, 0};
-  int bi[2] = {0, 0};      // batch buffer (parity) each target's columns live in
+  AlgJobs J[NTGT];
+  int npos[NTGT] = {0, 0, 0};
+  int bi[NTGT] = {0, 0, 0};   // batch buffer each target's columns live in
   int32_t slot = -1;
-  bool fired[2] = {false, false};
+  bool fired[NTGT] = {false, false, false};
 };
-constexpr int TS_RING = 40;   // private copies of a deletion's operands for k_T_leave (two batches of moves in flight)
+constexpr int TS_RING = 64;   // private copies of a deletion's operands for k_T_leave (three batches of moves in flight)
 constexpr int TEV_RING = 256; // events ordering the readers / writers of the cached columns of one (batch, slot)
 namespace {
 
@@ -169,7 +173,8 @@ struct Chain {
     std::vector<double> new_ll;    // [position]
     std::vector<double> own_ll, own_mu, own_flag;  // [position] leave-block-out score under the patient's own cluster
     std::vector<char> own_ok;
-    Batch b[2];
+    Batch b[NBUF];
+    std::vector<int> flight;       // buffers of the passes launched and not yet absorbed (batches after the current one), oldest first
     // rank-n corrections of the NEXT batch's positions, queued on the look-ahead stream behind that batch's pass at the
     // moment a move of the current batch changes a cluster (replay_launch); harvested when that batch is absorbed
     struct AsyncItem {
@@ -178,22 +183,24 @@ struct Chain {
       int out_idx = 0;
       bool dead = false;           // the slot changed a second time: the correction does not describe it any more
     };
-    std::vector<AsyncItem> async_items;
-    int64_t rpw_used = 0;          // doubles used in the engine's d_rpw
+    std::vector<AsyncItem> async_items[NBUF];  // per pass in flight
+    int64_t rpw_used[NBUF] = {};   // doubles used in that pass's share of the engine's d_rpw
     int cur_bi = 0;                // buffer index of the batch being processed
     int64_t blog_used = 0;         // doubles used in the engine's d_blog (this batch's half: blog_base, blog_half)
     int64_t blog_base = 0, blog_half = 0;
-    // cached columns kept current on the device (MOGP_TMAINT): [batch parity][slot] index of the event recorded after the last
-    // kernel that reads or writes them (-1: none pending); rp_epoch[slot]: change counter up to which the pass in flight for
-    // the NEXT batch has been brought by corrections queued behind it (-1: the chain of corrections is broken);
-    // rp_last[slot]: output block of the last of those corrections
-    std::vector<int> slot_tev[2];
-    std::vector<int64_t> rp_epoch;
-    std::vector<int> rp_last;
+    // cached columns kept current on the device (MOGP_TMAINT): [batch buffer][slot] index of the event recorded after the last
+    // kernel that reads or writes them (-1: none pending); rp_epoch[buffer][slot]: change counter up to which the pass in
+    // flight in that buffer has been brought by corrections queued behind it (-1: the chain of corrections is broken);
+    // rp_last[buffer][slot]: output block of the last of those corrections
+    std::vector<int> slot_tev[NBUF];
+    std::vector<int64_t> rp_epoch[NBUF];
+    std::vector<int> rp_last[NBUF];
   } win;
   int64_t win_passes = 0, win_rescores = 0, win_patients = 0, win_algebra = 0, win_replayed = 0;  // accounting
   int64_t win_pairs = 0, win_pruned = 0;   // (patient, cluster) pairs of the window passes / those excluded before the product
   double t_open = 0.0, t_ensure = 0.0, t_commit = 0.0, t_alg = 0.0;
+  double t_chain = 0.0;          // host seconds waiting for the corrections chained behind a pass when its batch starts
+  int64_t win_chained = 0;       // corrections chained behind passes in flight
   double max_corr_err = 0.0;     // MOGP_CHECK_CORRECTIONS: worst |rank-n corrected - re-scored| (relative)
   int64_t corr_checked = 0;         // host seconds spent in the three phases of windowed steps
 };
@@ -214,6 +221,11 @@ struct ScoreRes {
   int64_t tmaps_cap = 0;
   TensorMap* h_tmaps = nullptr;    // own pinned staging of those (passes on the look-ahead stream)
   int64_t htmaps_cap = 0;
+  // a pass of the look-ahead pipeline: its short preamble / epilogue run on `pre` (high priority), handed over by ev_pre0 /
+  // ev_pre1; the long product waits for `wide_after` (the product of the pass before it: passes in flight do not share the
+  // SMs, the later one only fills the earlier one's tail) and records `wide_done`
+  cudaStream_t pre = nullptr;
+  cudaEvent_t ev_pre0 = nullptr, ev_pre1 = nullptr, wide_done = nullptr, wide_after = nullptr;
 };
 
 // One batch of the look-ahead pipeline (chain.inl): outputs of its scoring pass, device and pinned host.
@@ -233,7 +245,7 @@ struct BatchBuf {
 // Small append workspaces: up to AP_RING appends may be queued on the main stream while the next one's Gram / Ls are
 // already computed on the quick stream (a batch holds at most 16 patients, and every batch start waits for the main
 // stream).  A slot serves clusters of up to AP_RING_NBLK * 256 points; larger ones use the shared workspace.
-constexpr int AP_RING = 20, AP_RING_NBLK = 256;
+constexpr int AP_RING = 64, AP_RING_NBLK = 256;
 constexpr int64_t AP_RING_SLOT = NP * NP + NP + (int64_t)AP_RING_NBLK * NG;
 
 struct mogp_engine {
@@ -265,11 +277,12 @@ struct mogp_engine {
   int64_t apart_elems = 0;
   // scoring scratch
   ScoreRes res_main;        // patient-by-patient steps, predict, append
-  ScoreRes res_bump[2];     // re-scoring passes of the look-ahead pipeline (alternate per batch)
-  BatchBuf bb[2];           // the two batches in flight
-  cudaStream_t ahead = nullptr, ahead2 = nullptr;  // low priority: the next batch's pass / its own-cluster scores
+  ScoreRes res_bump[NBUF];  // re-scoring passes of the look-ahead pipeline (one arena per batch buffer)
+  BatchBuf bb[NBUF];        // the batches in flight
+  cudaStream_t ahead = nullptr, ahead2 = nullptr;  // low priority: the pass being launched (= ahead_ring[its buffer]) / own-cluster scores
+  cudaStream_t ahead_ring[NBUF] = {};              // one look-ahead stream per batch buffer
   cudaEvent_t ev_fork = nullptr, ev_ahead2 = nullptr;
-  cudaEvent_t ev_pre0 = nullptr, ev_pre1 = nullptr;  // hand-over between the look-ahead stream and the high-priority one (score_device)
+  cudaEvent_t last_wide = nullptr;                 // wide_done of the pass launched last (the next one's wide_after)
   cudaStream_t quick = nullptr, quick2 = nullptr;  // high priority: rank-n score corrections after a move (join / leave side)
   cudaEvent_t ev_q2 = nullptr;
   double* d_algw2 = nullptr;      // partial sums of the join-side correction
@@ -287,21 +300,22 @@ struct mogp_engine {
   double* h_replay = nullptr;     // ... pinned
   double* d_rpw = nullptr;        // ... their partial sums
   int64_t rpw_elems = 0;
-  cudaEvent_t ev_replay = nullptr;
-  cudaStream_t rq = nullptr;      // high priority: the corrections queued ahead run as soon as the pass they correct has finished
+  cudaEvent_t ev_replay[NBUF] = {};
+  int64_t rpw_share = 0;          // doubles of d_rpw per batch buffer
   AlgHook* alg_hook = nullptr;  // set while a commit should launch the append-side correction (append_core)
   LeaveHook* leave_hook = nullptr;  // ... and the leave-side update of the cached columns (remove_core)
-  cudaStream_t ts0 = nullptr, ts1 = nullptr;  // high priority: k_T_leave for the current / the next batch's positions
-  cudaStream_t tq = nullptr;      // high priority: the corrections queued behind the next batch's pass
+  cudaStream_t ts0 = nullptr;     // high priority: k_T_leave for the current batch's positions
+  cudaStream_t ts1[NBUF] = {};    // ... for the positions of a pass in flight (per batch buffer: each waits for its own pass)
+  cudaStream_t tq[NBUF] = {};     // high priority: the corrections queued behind a pass in flight
   cudaEvent_t tev[TEV_RING] = {};
   int tev_next = 0;
   double* d_tsw = nullptr;        // ring of private copies of a deletion's operands (Bt | Gt | u | ... | S)
   int64_t tsw_slot = 0;           // doubles per ring entry
   int tsw_next = 0;
-  cudaEvent_t tsw_done[TS_RING][2] = {};  // the k_T_leave launches reading entry k have finished
+  cudaEvent_t tsw_done[TS_RING][NTGT] = {};  // the k_T_leave launches reading entry k have finished
   cudaEvent_t tsw_cp = nullptr;
-  cudaEvent_t ev_ts[3] = {};      // batch_launch: the new pass reuses buffers the kernels on ts0 / ts1 / tq worked on
-  cudaEvent_t ev_ts_end[2] = {};  // [batch parity] ts0 at the end of a batch: its re-scoring arena is reused two batches later
+  cudaEvent_t ev_ts[2 * NBUF] = {};  // batch_launch: the new pass reuses a buffer the kernels on the ts1 / tq streams worked on
+  cudaEvent_t ev_ts_end[NBUF] = {};  // [batch buffer] ts0 at the end of the batch it held: buffer and arena are reused NBUF batches later
   double* d_upd2 = nullptr;  // row-deletion workspace of the look-ahead streams (own-cluster scores)
   int64_t upd2_elems = 0;
   double *d_own1 = nullptr, *d_own2 = nullptr;  // Gram partials of the batched own-cluster scores (main-side / look-ahead)
@@ -1031,11 +1045,11 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
   // runs on the high-priority stream instead, so that it does not queue behind everything else on a busy GPU; only the
   // long product itself yields to the chain's urgent kernels.  (MOGP_PRE_HI=0: everything on the look-ahead stream.)
   static const bool pre_hi_on = !(getenv("MOGP_PRE_HI") && getenv("MOGP_PRE_HI")[0] == '0');
-  const bool pre_hi = pre_hi_on && h->rq && res_in && res_in != &h->res_main && !res.bump;
-  cudaStream_t pre = pre_hi ? h->rq : h->stream;
+  const bool pre_hi = pre_hi_on && res.pre && res_in && res_in != &h->res_main && !res.bump;
+  cudaStream_t pre = pre_hi ? res.pre : h->stream;
   if (pre_hi) {
-    CK(h, cudaEventRecord(h->ev_pre0, h->stream));
-    CK(h, cudaStreamWaitEvent(h->rq, h->ev_pre0, 0));
+    CK(h, cudaEventRecord(res.ev_pre0, h->stream));
+    CK(h, cudaStreamWaitEvent(pre, res.ev_pre0, 0));
   }
   k_kx<<<dim3((unsigned)pl.max_rblk, (unsigned)((pl.Rpad + KX_COLS - 1) / KX_COLS), (unsigned)n_slots), KX_ROWS, 0, pre>>>(
       res.d_slots, pack, use_pack, xs_dev, (int)R, (int)pl.Rpad, pl.max_rblk, pl.kxT, pl.mupart);
@@ -1047,9 +1061,10 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
     LAUNCHED(h);
   }
   if (pre_hi) {
-    CK(h, cudaEventRecord(h->ev_pre1, h->rq));
-    CK(h, cudaStreamWaitEvent(h->stream, h->ev_pre1, 0));
+    CK(h, cudaEventRecord(res.ev_pre1, pre));
+    CK(h, cudaStreamWaitEvent(h->stream, res.ev_pre1, 0));
   }
+  if (res.wide_after) CK(h, cudaStreamWaitEvent(h->stream, res.wide_after, 0));
   switch (pl.BN) {  // <= 16 columns: bound by HBM (8-warp ring); wider: bound by the FP64 tensor pipe (16 warps)
     case 8: launch_score_gemm<8>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
     case 16: launch_score_gemm<16>(h, pl, pl.T, res.d_slots, pack, use_pack, cp); break;
@@ -1066,9 +1081,10 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
     LAUNCHED(h);
   }
   const int64_t pairs = n_pat * n_slots;
+  if (res.wide_done) CK(h, cudaEventRecord(res.wide_done, h->stream));
   if (pre_hi) {  // the short epilogue of a look-ahead pass: high priority again (the host is usually waiting for it)
-    CK(h, cudaEventRecord(h->ev_pre0, h->stream));
-    CK(h, cudaStreamWaitEvent(h->rq, h->ev_pre0, 0));
+    CK(h, cudaEventRecord(res.ev_pre0, h->stream));
+    CK(h, cudaStreamWaitEvent(pre, res.ev_pre0, 0));
   }
   k_score_epi<<<(unsigned)((pairs + 7) / 8), 256, 0, pre>>>(res.d_slots, pack, use_pack, n_slots, off_dev, n_pat, xs_dev, ys_dev,
                                                                      (int)pl.Rpad, pl.part, pl.mupart, pl.max_rblk, pl.mu,
@@ -1076,8 +1092,8 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
                                                                      mu_thr_dev, col_mean, col_var, col_lpd, pl.ss, d_flag);
   LAUNCHED(h);
   if (pre_hi) {
-    CK(h, cudaEventRecord(h->ev_pre1, h->rq));
-    CK(h, cudaStreamWaitEvent(h->stream, h->ev_pre1, 0));
+    CK(h, cudaEventRecord(res.ev_pre1, pre));
+    CK(h, cudaStreamWaitEvent(h->stream, res.ev_pre1, 0));
   }
   CK(h, cudaGetLastError());
   if (plan_out) *plan_out = pl;
@@ -1221,6 +1237,10 @@ int mogp_version(void) { return 100; }
 static int engine_create_impl(int32_t device, bool light, mogp_engine** out) {
   if (!out) return MOGP_EINVAL;
   *out = nullptr;
+  // One hardware work queue per stream of the look-ahead pipeline (default 8: streams share queues, and a stream waiting for
+  // a scoring pass blocks the urgent kernels queued behind it).  Effective when this library makes the process' first CUDA
+  // call; otherwise the host program sets it before it creates the context.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n <= 0) {
@@ -1241,34 +1261,21 @@ static int engine_create_impl(int32_t device, bool light, mogp_engine** out) {
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
       cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
-      (!light && (cudaStreamCreateWithPriority(&h->ahead, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
-                  cudaStreamCreateWithPriority(&h->ahead2, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+      (!light && (cudaStreamCreateWithPriority(&h->ahead2, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
                   cudaStreamCreateWithPriority(&h->quick, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
                   cudaStreamCreateWithPriority(&h->quick2, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
                   cudaMalloc((void**)&h->d_apring, sizeof(double) * AP_RING * AP_RING_SLOT) != cudaSuccess ||
                   cudaMalloc((void**)&h->d_alg, sizeof(double) * ALG_OUT_SLOTS * 2 * OWN_BATCH) != cudaSuccess ||
                   cudaMallocHost((void**)&h->h_alg, sizeof(double) * ALG_OUT_SLOTS * 2 * OWN_BATCH) != cudaSuccess ||
-                  cudaMalloc((void**)&h->d_replay, sizeof(double) * REPLAY_MAX * 2 * OWN_BATCH) != cudaSuccess ||
-                  cudaMallocHost((void**)&h->h_replay, sizeof(double) * REPLAY_MAX * 2 * OWN_BATCH) != cudaSuccess ||
-                  cudaEventCreateWithFlags(&h->ev_replay, cudaEventDisableTiming) != cudaSuccess ||
-                  cudaStreamCreateWithPriority(&h->rq, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
-                  cudaStreamCreateWithPriority(&h->tq, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+                  cudaMalloc((void**)&h->d_replay, sizeof(double) * NBUF * REPLAY_MAX * 2 * OWN_BATCH) != cudaSuccess ||
+                  cudaMallocHost((void**)&h->h_replay, sizeof(double) * NBUF * REPLAY_MAX * 2 * OWN_BATCH) != cudaSuccess ||
                   cudaStreamCreateWithPriority(&h->ts0, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
-                  cudaStreamCreateWithPriority(&h->ts1, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
-                  cudaEventCreateWithFlags(&h->tsw_cp, cudaEventDisableTiming) != cudaSuccess ||
-                  cudaEventCreateWithFlags(&h->bb[0].scored, cudaEventDisableTiming) != cudaSuccess ||
-                  cudaEventCreateWithFlags(&h->bb[1].scored, cudaEventDisableTiming) != cudaSuccess)) ||
+                  cudaEventCreateWithFlags(&h->tsw_cp, cudaEventDisableTiming) != cudaSuccess)) ||
       cudaEventCreateWithFlags(&h->ev_q2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_alg, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_apq, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_pre0, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_pre1, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_ahead2, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->bb[0].done, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->bb[1].done, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->bb[0].done_blk, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->bb[1].done_blk, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess ||
@@ -1278,7 +1285,26 @@ static int engine_create_impl(int32_t device, bool light, mogp_engine** out) {
     return MOGP_ECUDA;
   }
   h->main_stream = h->stream;
-  h->res_bump[0].bump = h->res_bump[1].bump = true;
+  for (int i = 0; i < NBUF; ++i) {
+    h->res_bump[i].bump = true;
+    bool ok = cudaEventCreateWithFlags(&h->bb[i].done, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->bb[i].done_blk, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
+    if (ok && !light)
+      ok = cudaEventCreateWithFlags(&h->bb[i].scored, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_replay[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&h->ahead_ring[i], cudaStreamNonBlocking, prio_least) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&h->bb[i].res.pre, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->bb[i].res.ev_pre0, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->bb[i].res.ev_pre1, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->bb[i].res.wide_done, cudaEventDisableTiming) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&h->tq[i], cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
+           cudaStreamCreateWithPriority(&h->ts1[i], cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
+    if (!ok) {
+      g_create_error = std::string("engine init failed: ") + cudaGetErrorString(cudaGetLastError());
+      delete h;
+      return MOGP_ECUDA;
+    }
+  }
   cudaMalloc((void**)&h->d_adraw, sizeof(double) * 8);
   cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM);
   cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
@@ -1328,7 +1354,7 @@ void mogp_engine_destroy(mogp_engine* h) {
     if (r.h_tmaps) cudaFreeHost(r.h_tmaps);
   };
   free_res(h->res_main);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < NBUF; ++i) {
     free_res(h->res_bump[i]);
     free_res(h->bb[i].res);
     cudaFree(h->bb[i].d_out);
@@ -1336,13 +1362,20 @@ void mogp_engine_destroy(mogp_engine* h) {
     if (h->bb[i].done) cudaEventDestroy(h->bb[i].done);
     if (h->bb[i].scored) cudaEventDestroy(h->bb[i].scored);
     if (h->bb[i].done_blk) cudaEventDestroy(h->bb[i].done_blk);
+    if (h->ev_replay[i]) cudaEventDestroy(h->ev_replay[i]);
+    if (h->ahead_ring[i]) cudaStreamDestroy(h->ahead_ring[i]);
+    if (h->bb[i].res.pre) cudaStreamDestroy(h->bb[i].res.pre);
+    for (cudaEvent_t e : {h->bb[i].res.ev_pre0, h->bb[i].res.ev_pre1, h->bb[i].res.wide_done})
+      if (e) cudaEventDestroy(e);
+    if (h->tq[i]) cudaStreamDestroy(h->tq[i]);
+    if (h->ts1[i]) cudaStreamDestroy(h->ts1[i]);
   }
   cudaFree(h->d_adraw);
   cudaFree(h->d_wt);
   cudaFree(h->d_upd2);
   cudaFree(h->d_own1);
   cudaFree(h->d_own2);
-  for (cudaEvent_t e : {h->ev_main, h->ev_side, h->ev_block, h->ev_fork, h->ev_ahead2, h->ev_alg, h->ev_apq, h->ev_q2, h->ev_pre0, h->ev_pre1})
+  for (cudaEvent_t e : {h->ev_main, h->ev_side, h->ev_block, h->ev_fork, h->ev_ahead2, h->ev_alg, h->ev_apq, h->ev_q2})
     if (e) cudaEventDestroy(e);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->quick) cudaStreamDestroy(h->quick);
@@ -1353,11 +1386,7 @@ void mogp_engine_destroy(mogp_engine* h) {
   cudaFree(h->d_replay);
   cudaFree(h->d_rpw);
   if (h->h_replay) cudaFreeHost(h->h_replay);
-  if (h->ev_replay) cudaEventDestroy(h->ev_replay);
-  if (h->rq) cudaStreamDestroy(h->rq);
-  if (h->tq) cudaStreamDestroy(h->tq);
   if (h->ts0) cudaStreamDestroy(h->ts0);
-  if (h->ts1) cudaStreamDestroy(h->ts1);
   if (h->tsw_cp) cudaEventDestroy(h->tsw_cp);
   for (auto& e : h->tev)
     if (e) cudaEventDestroy(e);
@@ -1372,7 +1401,6 @@ void mogp_engine_destroy(mogp_engine* h) {
   cudaFree(h->d_algw);
   cudaFree(h->d_apring);
   if (h->h_alg) cudaFreeHost(h->h_alg);
-  if (h->ahead) cudaStreamDestroy(h->ahead);
   if (h->ahead2) cudaStreamDestroy(h->ahead2);
   cudaFree(h->d_wq);
   cudaFree(h->d_woff);
@@ -1585,13 +1613,13 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
 int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out) {
   if (!h || !out) return MOGP_EINVAL;
   prof_drain(h);
-  const double v[18] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
+  const double v[20] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
                         h->chain.t_open, h->chain.t_ensure, h->chain.t_commit,
                         (double)h->prof_launches_c[1], h->prof_ms_c[1], h->prof_bytes_c[1], h->prof_flops_c[1],
                         (double)h->chain.win_algebra, h->chain.t_alg, (double)h->chain.win_replayed,
                         h->chain.max_corr_err, (double)h->chain.corr_checked, (double)h->chain.win_pairs,
-                        (double)h->chain.win_pruned};
-  for (int i = 0; i < n_out && i < 18; ++i) out[i] = v[i];
+                        (double)h->chain.win_pruned, h->chain.t_chain, (double)h->chain.win_chained};
+  for (int i = 0; i < n_out && i < 20; ++i) out[i] = v[i];
   return MOGP_OK;
 }
 

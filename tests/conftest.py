@@ -1,4 +1,7 @@
 import os
+
+# before anything creates the CUDA context (mogp_b200/__init__.py explains): one hardware queue per stream of the pipeline
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import sys
 
 import pytest

@@ -113,13 +113,16 @@ def test_fast_sweeps_match_oracle(eng, kernel, mean_func, threshold, single_blas
 
 
 @pytest.mark.parametrize("lookahead,pipeline,env", [(16, 2, {}), (32, 2, {}), (48, 2, {}), (64, 2, {}), (32, 1, {}),
+                                                    (16, 3, {}), (32, 3, {}), (64, 3, {}),   # two passes in flight
+                                                    (48, 3, {"MOGP_TMAINT": "0"}),
                                                     (48, 2, {"MOGP_RANK_RESCORE": "0"}),   # every change re-scored
                                                     (48, 2, {"MOGP_TMAINT": "0"}),         # cached columns not kept current: one correction per cluster and batch, the rest re-scored
                                                     (32, 2, {"MOGP_TMAINT": "0"}),
-                                                    (48, 2, {"MOGP_LAUNCH_AFTER": "1", "MOGP_ZIGZAG": "1"}),
+                                                    (48, 2, {"MOGP_ZIGZAG": "1"}),
                                                     (48, 2, {"MOGP_PRUNE": "0"}),          # threshold rule after the product only
                                                     (64, 2, {"MOGP_CHECK_CORRECTIONS": "1"}),
-                                                    (64, 2, {"MOGP_CHECK_CORRECTIONS": "2"})])
+                                                    (64, 2, {"MOGP_CHECK_CORRECTIONS": "2"}),
+                                                    (64, 3, {"MOGP_CHECK_CORRECTIONS": "2"})])
 def test_lookahead_window_equals_patient_by_patient(eng, lookahead, pipeline, env, monkeypatch):
     """mogp_chain_sweep with the look-ahead pipeline (batches of patients scored per pass over the factors, the next
     batch's pass running while the current batch moves, cached scores corrected by rank-n formulas or re-scored against
@@ -128,7 +131,7 @@ def test_lookahead_window_equals_patient_by_patient(eng, lookahead, pipeline, en
     window sees invalidations, new clusters and emptied clusters)."""
     from mogp_b200 import MoGP_constrained
     from mogp_b200.synth import alsfrs_like, block_init
-    monkeypatch.setenv("MOGP_PIPELINE", str(pipeline))   # 2: the next batch's pass overlaps the current batch's moves
+    monkeypatch.setenv("MOGP_PIPELINE", str(pipeline))   # passes in flight: 2 = the next batch's overlaps the current batch's moves, 3 = the next two
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     N = 400

@@ -225,7 +225,7 @@ def test_refit_with_repeated_inputs_collapsed(eng, case):
     c1 = eng.refit_counters()
     assert c1["launched"] > c0["launched"]
     th = eng.cluster_get_theta(slot)
-    assert np.allclose(th, o.param_array, rtol=2e-6)
+    assert np.allclose(th[(0 if case[1] else 1):], o.param_array, rtol=2e-6)   # (no slope parameter without the mean function)
     assert rel(eng.cluster_loglik(slot), o.log_likelihood()) < 1e-9
     assert int(evals[0]) == o.n_evals - n0          # the optimiser's evaluations + the closing f(x_opt)
     xs = rs.uniform(0, 8, 5)
