@@ -297,7 +297,9 @@ int remove_core(mogp_engine* h, Cluster& c, int64_t p, int n) {
   if (h->leave_hook) TRY(fire_leave_hook(h, g, w, nT));
   if (!legacy) {
     // one pass over the factor: strip walk with the prefix carried along (k_rm_strip), alpha / x / y / stat in its epilogue
-    k_rm_strip<<<g.nbn * (TB / RM_SW), NTHREADS, RM_STRIP_SMEM, h->stream>>>(c.M, nM, g, w, c.vec, nvec, c.cap);
+    static const int strip_w = env_int_once("MOGP_RM_SW", 16);
+    if (strip_w == 64) k_rm_strip64<<<g.nbn, NTHREADS, RM_STRIP64_SMEM, h->stream>>>(c.M, nM, g, w, c.vec, nvec, c.cap);
+    else k_rm_strip<<<g.nbn * (TB / RM_SW), NTHREADS, RM_STRIP_SMEM, h->stream>>>(c.M, nM, g, w, c.vec, nvec, c.cap);
     LAUNCHED(h);
     if (h->stream == h->side) h->pending_release.emplace_back(c.cap, c.M);  // reusable once the main stream has joined
     else pool_put(h, c.cap, c.M);
@@ -996,8 +998,10 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   const int64_t Rtot = w.col0[w.n], cb = w.col0[s0], R = w.col0[s0 + cnt] - cb;
   if (h->side_pending) join_side(h);
   h->ahead = h->ahead_ring[bi];
-  // the product of this pass starts when that of the pass launched before it ends (its preamble does not wait)
-  bf.res.wide_after = h->last_wide;
+  // Passes in flight are independent streams: the later pass's CTAs fill the SMs the earlier one's tail leaves idle (same
+  // priority: the block scheduler serves the older grid first).  MOGP_WIDE_CHAIN=1: the product of this pass waits for that of
+  // the pass launched before it instead (measured 2 % slower: 1.031 vs 1.050 sweeps/s).
+  bf.res.wide_after = env_int("MOGP_WIDE_CHAIN", 0) != 0 ? h->last_wide : nullptr;
   h->last_wide = bf.res.wide_done;
   CK(h, cudaEventRecord(h->ev_fork, h->main_stream));
   CK(h, cudaStreamWaitEvent(h->ahead, h->ev_fork, 0));

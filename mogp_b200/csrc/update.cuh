@@ -732,6 +732,120 @@ __global__ void __launch_bounds__(NTHREADS) k_rm_strip(const double* __restrict_
   if (strip == 0 && tid < 32) vec_new[4 * cap + tid] = vec_old[4 * cap + tid];  // the stat block travels with the buffer
 }
 
+// The same walk over 64-column strips (one CTA per block column): a quarter of the CTAs, four times the work per link.  The
+// chain of dependent row tiles takes longer than with 16-column strips, but the deletion holds far fewer SMs while it runs
+// (every CTA of it displaces a CTA of the scoring pass in flight): the better trade once nobody waits for the deletion
+// itself (cached columns kept current, chain.inl).  MOGP_RM_SW=64.
+struct RmStrip64Stage {      // one row tile's operands in shared memory
+  double sB[(TB + NP) * LD_R];   // old tile (rows 0..63) ; H (rows 64..64+NP)
+  double sA[TB * LD_W];          // S (cols 0..63) | G (cols 64..64+NP)
+  double sBt[TB * LD_BT];        // b rows of the tile: [k][a]
+  double su[TB];
+};
+constexpr int RM_STRIP64_SMEM = 2 * (int)sizeof(RmStrip64Stage);
+
+__global__ void __launch_bounds__(NTHREADS) k_rm_strip64(const double* __restrict__ Mo, double* __restrict__ Mn, RmGeom g, RmWork w,
+                                                       const double* __restrict__ vec_old, double* __restrict__ vec_new,
+                                                       int64_t cap) {
+  extern __shared__ __align__(16) unsigned char rm64_smem_raw[];
+  RmStrip64Stage* st = reinterpret_cast<RmStrip64Stage*>(rm64_smem_raw);
+  __shared__ double sH[NP][TB];  // the prefix carried down the strip
+  const int J = blockIdx.x, tid = threadIdx.x;
+  const int64_t ld = g.ld;
+  // rows above the deleted block: neither rows nor columns move (j <= i < p)
+  for (int I = J; I < g.I0; ++I)
+    for (int idx = tid; idx < TB * TB / 2; idx += NTHREADS) {
+      const int r = idx >> 5, c = (idx & 31) << 1;
+      const int64_t o = (int64_t)(I * TB + r) * ld + J * TB + c;
+      double2 v = *reinterpret_cast<const double2*>(Mo + o);
+      if (I == J) {  // (tiles above the diagonal hold nothing; inside the diagonal tile the upper part is kept at zero)
+        if (c > r) v.x = 0.0;
+        if (c + 1 > r) v.y = 0.0;
+      }
+      *reinterpret_cast<double2*>(Mn + o) = v;
+    }
+  const int Ifirst = max(J, g.I0);
+  // carriers: rows p..p+n-1 of the block's own columns contribute b_k[q] M[k, j] to every prefix
+  for (int idx = tid; idx < NP * TB; idx += NTHREADS) {
+    const int q = idx >> 6, c = idx & 63, jp = J * TB + c;
+    double run = 0.0;
+    if (q < g.n && jp < g.mnew) {
+      const int j = jp < g.p ? jp : jp + g.n;
+      for (int a = q; a < g.n; ++a)
+        if (j <= g.p + a) run += Mo[(int64_t)(g.p + a) * ld + g.p + q] * Mo[(int64_t)(g.p + a) * ld + j];
+    }
+    sH[q][c] = run;
+  }
+  auto issue = [&](int I, RmStrip64Stage& S) {  // operands of row tile I (cp.async; constants stored directly)
+    const int bx = I - g.I0;
+    for (int idx = tid; idx < TB * TB; idx += NTHREADS) {
+      const int r = idx >> 6, c = idx & 63, ip = I * TB + r, jp = J * TB + c;
+      double* dst = S.sB + r * LD_R + c;
+      if (ip >= g.mnew || jp >= g.mnew) {
+        *dst = (ip == jp) ? 1.0 : 0.0;
+      } else {
+        const int i = ip < g.p ? ip : ip + g.n, j = jp < g.p ? jp : jp + g.n;
+        if (j > i) *dst = 0.0;
+        else cp_async8(dst, Mo + (int64_t)i * ld + j);
+      }
+    }
+    const double* Ss = w.S + (int64_t)bx * (TB * TB);
+    for (int idx = tid; idx < TB * TB / 2; idx += NTHREADS) {
+      const int r = idx >> 5, c = (idx & 31) << 1;
+      cp_async16(S.sA + r * LD_W + c, Ss + r * TB + c);
+    }
+    for (int idx = tid; idx < TB * NP / 2; idx += NTHREADS) {
+      const int r = idx / (NP / 2), a = (idx % (NP / 2)) * 2;
+      cp_async16(S.sA + r * LD_W + TB + a, w.Gt + ((int64_t)bx * TB + r) * NP + a);
+      cp_async16(S.sBt + r * LD_BT + a, w.Bt + ((int64_t)bx * TB + r) * NP + a);
+    }
+    if (tid < TB / 2) cp_async16(S.su + 2 * tid, w.u + (int64_t)bx * TB + 2 * tid);
+  };
+  const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  if (Ifirst < g.nbn) issue(Ifirst, st[0]);
+  cp_async_commit();
+  int cur = 0;
+  for (int I = Ifirst; I < g.nbn; ++I, cur ^= 1) {
+    RmStrip64Stage& S = st[cur];
+    if (I + 1 < g.nbn) issue(I + 1, st[cur ^ 1]);
+    cp_async_commit();
+    cp_async_wait<1>();  // this thread's copies of tile I have landed ...
+    for (int idx = tid; idx < NP * TB; idx += NTHREADS) S.sB[(TB + (idx >> 6)) * LD_R + (idx & 63)] = sH[idx >> 6][idx & 63];
+    __syncthreads();     // ... everybody's have, and H is in place
+    Acc64 acc;
+    acc.zero();
+    warp_mma<2, 4, true, false, TB + NP, LD_W, LD_R>(acc, S.sA, S.sB, warp_rb64(), warp_cb64());
+    for_each_acc64(acc, [&](int r, int c, double& v) {
+      Mn[(int64_t)(I * TB + r) * ld + J * TB + c] = S.su[r] * (S.sB[r * LD_R + c] - v);
+    });
+    // H += B_I^T old: 16 x 64, warp w owns columns [8w, 8w + 8)
+    Acc<2, 1> hp;
+    hp.zero();
+    warp_mma<2, 1, false, false, TB, LD_BT, LD_R>(hp, S.sBt, S.sB, 0, warp * 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int q = 8 * i + gq, c = warp * 8 + 2 * tq;
+      sH[q][c] += hp.v[i][0][0];
+      sH[q][c + 1] += hp.v[i][0][1];
+    }
+    __syncthreads();  // the stage may be refilled, H is complete for the next tile
+  }
+  cp_async_wait<0>();
+  // closed-form alpha of the result and the strip's share of x, y  (vec = x | y | alpha | z, `cap` doubles each)
+  if (tid < TB) {
+    const int jp = J * TB + tid;
+    if (jp < g.mnew) {
+      const int j = jp < g.p ? jp : jp + g.n;
+      double sdot = 0.0;
+      for (int a = 0; a < g.n; ++a) sdot += sH[a][tid] * w.gsol[a];
+      vec_new[jp] = vec_old[j];
+      vec_new[cap + jp] = vec_old[cap + j];
+      vec_new[2 * cap + jp] = vec_old[2 * cap + j] - sdot;
+    }
+  }
+  if (J == 0 && tid < 32) vec_new[4 * cap + tid] = vec_old[4 * cap + tid];  // the stat block travels with the buffer
+}
+
 // The same row operations applied to cached columns T_q = M k_q of the patients still ahead (look-ahead pipeline, chain.inl):
 // with M' E = G M (E drops the block's columns) T_q' = M' k_q' = G T_q - the contributions of the block's entries of k_q cancel
 // (g_i . G_{i-1} k_B = b_i . k_B) - so T_q' [i'] = u_i (T_q[i] - g_i . h_{i-1}), h_i = sum_{k <= i} b_k T_q[k] from the block's own
@@ -1045,6 +1159,7 @@ inline void update_set_attributes() {
   cudaFuncSetAttribute(k_rm_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_PREP_SMEM);
   cudaFuncSetAttribute(k_rm_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_APPLY_SMEM);
   cudaFuncSetAttribute(k_rm_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_STRIP_SMEM);
+  cudaFuncSetAttribute(k_rm_strip64, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_STRIP64_SMEM);
   cudaFuncSetAttribute(k_T_leave, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_STRIP_SMEM);
   cudaFuncSetAttribute(k_append_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_ROWS_SMEM);
 }
