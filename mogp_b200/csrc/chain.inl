@@ -90,7 +90,21 @@ int pool_get(mogp_engine* h, int64_t cap, double** out) {
   return MOGP_OK;
 }
 void pool_put(mogp_engine* h, int64_t cap, double* buf) {
-  if (buf) h->pool.emplace_back(cap, buf);
+  if (!buf) return;
+  if (h->chain.win.open && h->pass_launched > h->pass_absorbed) {  // a pass in flight may be reading it (see HeldBuf)
+    h->held.push_back({cap, buf, h->pass_launched});
+    return;
+  }
+  h->pool.emplace_back(cap, buf);
+}
+// after a pass has been absorbed (or when nothing is in flight any more: all = true)
+void pool_unhold(mogp_engine* h, bool all) {
+  size_t keep = 0;
+  for (size_t i = 0; i < h->held.size(); ++i) {
+    if (all || h->held[i].tag <= h->pass_absorbed) h->pool.emplace_back(h->held[i].cap, h->held[i].buf);
+    else h->held[keep++] = h->held[i];
+  }
+  h->held.resize(keep);
 }
 
 // After a rank-n update alpha is kept current in closed form by the update itself (k_append_finalize / k_rm_alpha);
@@ -198,6 +212,10 @@ int append_core(mogp_engine* h, Cluster& c, int n, const double* xB_dev, const d
     CK(h, cudaEventRecord(h->ev_alg, s1));
     hk->fired = true;
   }
+  // alpha is updated in place below: behind the preambles of the passes in flight, which read it (their products read rows
+  // of M this append does not touch, and mask the padding it writes into, score.cuh)
+  if (h->chain.win.open)
+    for (int f : h->chain.win.flight) CK(h, cudaStreamWaitEvent(h->stream, h->bb[f].res.pre_done, 0));
   k_append_rows<<<dim3(nb, APPEND_KS), NTHREADS, AP_ROWS_SMEM, h->stream>>>(c.M, c.cap, nb, (int)mpad_old, T_dev, t_stride, n, w);
   LAUNCHED(h);
   if (mpad_new > mpad_old) {
@@ -1053,6 +1071,7 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   CK(h, cudaGetLastError());
   h->bytes_d2h += (int64_t)sizeof(double) * total;
   w.end_launched = s0 + cnt;
+  h->pass_launched += 1;
   ch.win_passes += 1;
   ch.win_patients += cnt;
   return MOGP_OK;
@@ -1066,6 +1085,8 @@ int batch_absorb(mogp_engine* h, int bi) {
   Chain::Batch& b = w.b[bi];
   BatchBuf& bf = h->bb[bi];
   CK(h, cudaEventSynchronize(h->blocking_sync ? bf.done_blk : bf.done));
+  h->pass_absorbed += 1;
+  pool_unhold(h, false);
   const int ns = (int)b.slots.size();
   const int64_t cnt = b.cnt, cb = w.col0[b.s0];
   const double* hs = bf.h_out;
@@ -1901,6 +1922,8 @@ int mogp_chain_sweep(mogp_engine* h, int64_t n_steps, const int64_t* order, cons
     cudaStreamSynchronize(h->ahead2);
     cudaStreamSynchronize(h->ts0);
     h->last_wide = nullptr;
+    h->pass_absorbed = h->pass_launched;
+    pool_unhold(h, true);
     h->chain.win.open = h->chain.win.in_step = false;
     if (rc != MOGP_OK) return rc;
     if (min_margin) *min_margin = mm;

@@ -226,6 +226,7 @@ struct ScoreRes {
   // SMs, the later one only fills the earlier one's tail) and records `wide_done`
   cudaStream_t pre = nullptr;
   cudaEvent_t ev_pre0 = nullptr, ev_pre1 = nullptr, wide_done = nullptr, wide_after = nullptr;
+  cudaEvent_t pre_done = nullptr;  // the preamble has read the clusters' x / alpha (an append updates alpha in place: it waits)
 };
 
 // One batch of the look-ahead pipeline (chain.inl): outputs of its scoring pass, device and pinned host.
@@ -255,6 +256,16 @@ struct mogp_engine {
   cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_block = nullptr;
   bool blocking_sync = false;
   std::vector<std::pair<int64_t, double*>> pending_release;  // buffers the side stream may still be reading
+  // Factor buffers retired while scoring passes are in flight (look-ahead pipeline): a pass launched before the retirement
+  // may still be reading the old factor - and what it computes from it is USED (corrected by the chained rank-n kernels) -
+  // so the buffer goes back to the pool only when every pass launched before has been absorbed.
+  struct HeldBuf {
+    int64_t cap;
+    double* buf;
+    int64_t tag;  // passes launched when it was retired
+  };
+  std::vector<HeldBuf> held;
+  int64_t pass_launched = 0, pass_absorbed = 0;
   bool side_pending = false;       // some cluster has side_busy set
   double* d_apart2 = nullptr;  // alpha partials of the side stream
   int64_t apart2_elems = 0;
@@ -1060,6 +1071,7 @@ int score_device(mogp_engine* h, int64_t n_pat, int64_t R, const int64_t* off_de
                                                d_ncols, d_flag);
     LAUNCHED(h);
   }
+  if (res.pre_done) CK(h, cudaEventRecord(res.pre_done, pre));
   if (pre_hi) {
     CK(h, cudaEventRecord(res.ev_pre1, pre));
     CK(h, cudaStreamWaitEvent(h->stream, res.ev_pre1, 0));
@@ -1297,6 +1309,7 @@ static int engine_create_impl(int32_t device, bool light, mogp_engine** out) {
            cudaEventCreateWithFlags(&h->bb[i].res.ev_pre0, cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&h->bb[i].res.ev_pre1, cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&h->bb[i].res.wide_done, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->bb[i].res.pre_done, cudaEventDisableTiming) == cudaSuccess &&
            cudaStreamCreateWithPriority(&h->tq[i], cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
            cudaStreamCreateWithPriority(&h->ts1[i], cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
     if (!ok) {
@@ -1365,7 +1378,7 @@ void mogp_engine_destroy(mogp_engine* h) {
     if (h->ev_replay[i]) cudaEventDestroy(h->ev_replay[i]);
     if (h->ahead_ring[i]) cudaStreamDestroy(h->ahead_ring[i]);
     if (h->bb[i].res.pre) cudaStreamDestroy(h->bb[i].res.pre);
-    for (cudaEvent_t e : {h->bb[i].res.ev_pre0, h->bb[i].res.ev_pre1, h->bb[i].res.wide_done})
+    for (cudaEvent_t e : {h->bb[i].res.ev_pre0, h->bb[i].res.ev_pre1, h->bb[i].res.wide_done, h->bb[i].res.pre_done})
       if (e) cudaEventDestroy(e);
     if (h->tq[i]) cudaStreamDestroy(h->tq[i]);
     if (h->ts1[i]) cudaStreamDestroy(h->ts1[i]);
@@ -1410,6 +1423,7 @@ void mogp_engine_destroy(mogp_engine* h) {
   cudaFree(h->d_upd);
   cudaFree(h->d_apw);
   for (auto& pb : h->pool) cudaFree(pb.second);
+  for (auto& hb : h->held) cudaFree(hb.buf);
   if (h->pin) cudaFreeHost(h->pin);
   if (h->pin_dn) cudaFreeHost(h->pin_dn);
   if (h->pin_up) cudaFreeHost(h->pin_up);

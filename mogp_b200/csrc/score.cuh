@@ -191,6 +191,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_score_gemm(SLOT_ARGS, const dou
     warp_mma<S::MS, S::NS, true, true>(acc, sA, sA + TB * LD_C, rbase, cbase);
   }
   cp_async_wait<0>();
+  // (rows beyond m are padding, exactly 0 - whatever an append running beside a look-ahead pass has written there meanwhile:
+  // see wide_item)
+#pragma unroll
+  for (int i = 0; i < S::MS; ++i)
+    if (rb * TB + rbase + 8 * i + g >= sv.m) {
+#pragma unroll
+      for (int j = 0; j < S::NS; ++j) acc.v[i][j][0] = acc.v[i][j][1] = 0.0;
+    }
   if (cp.kc > 0) {  // split contraction: this CTA's partial product goes to the scratch, k_score_reduce finishes
     double* o = cp.Tpart + sv.kx_off * cp.maxch + (int64_t)chunk * Rpad * sv.mpad;
 #pragma unroll
@@ -368,6 +376,16 @@ __device__ __forceinline__ void wide_item(const SlotView& sv, int rb, int chunk,
           acc.v[i][j][1] += v.y;
         }
     }
+    // Rows beyond the cluster's m are padding: identity rows of M times zero rows of Kx, exactly 0.  A pass of the look-ahead
+    // pipeline runs while patients join its clusters, and an append writes its new rows of M INTO that padding: whatever the
+    // tiles held when they were loaded, the pass reports the cluster it was launched for (the rows a join adds to the cached
+    // columns are written by the correction chained behind the pass, chain.inl).
+#pragma unroll
+    for (int i = 0; i < MS; ++i)
+      if (rb * TB + rbase + 8 * i + g >= sv.m) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) acc.v[i][j][0] = acc.v[i][j][1] = 0.0;
+      }
     if (cp.kc > 0) {  // split contraction: partial product to the scratch (k_score_reduce finishes)
       double* o = cp.Tpart + sv.kx_off * cp.maxch + (int64_t)chunk * Rpad * sv.mpad;
 #pragma unroll

@@ -131,6 +131,36 @@ def test_l2_teacher_forced_steps_at_10k_patients(eng):
     assert worst_s < RTOL and worst_p < RTOL
 
 
+def test_pipelined_sweep_at_10k_patients_is_reproducible_and_equals_the_two_batch_pipeline(eng, monkeypatch):
+    """The look-ahead pipeline at the headline size (two passes in flight while patients move, cached columns kept current
+    by kernels on a dozen streams): two sweeps from the same snapshot walk the same chain - every dependency between those
+    streams is expressed, nothing is left to timing (a pass reading a factor buffer that a later deletion recycled, or the
+    padding an append writes into, showed up here as a different chain from run to run) - and the same chain as the pipeline
+    with one pass in flight and no chained corrections."""
+    from mogp_b200 import MoGP_constrained
+    X, Y, kw = bench_workload()
+    mix = MoGP_constrained(X=X.copy(), Y=Y.copy(), engine=eng, **kw)
+    mix.initialize_sampler(mix.num_init_clusters, True)
+    mix.sweep()                                   # a warm state: ~30 clusters of ~2 600 points, ~10 % of the patients move per sweep
+    snap = mix.snapshot()
+    rs = np.random.get_state()
+    runs = []
+    for env in ({}, {}, {"MOGP_TMAINT": "0", "MOGP_PIPELINE": "2"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        mix.restore(snap)
+        np.random.set_state(rs)
+        c0 = eng.chain_counters()
+        mix.sweep()
+        mix.sweep()
+        c1 = eng.chain_counters()
+        runs.append((mix.z.copy(), list(mix.allocmodel.Nk), c1["chained_corrections"] - c0["chained_corrections"]))
+    print("chained corrections per run:", [r[2] for r in runs], "patients that moved:", int(np.sum(runs[0][0] != snap['z'])))
+    assert runs[0][2] > 1000 and runs[2][2] == 0
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]
+    assert np.array_equal(runs[0][0], runs[2][0]) and runs[0][1] == runs[2][1]
+
+
 def _golden(name):
     path = os.path.join(HERE, "golden", "chain_{}.npz".format(name))
     if not os.path.exists(path):
