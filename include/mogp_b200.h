@@ -110,7 +110,9 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
    out[16] = (patient, cluster) pairs of the window passes, out[17] = those the monotonicity rule excluded on the device
    before the O(m^2) product (their mean alone decides, mogp_constrained.py:254-266),
    out[18] = host seconds waiting, when a batch starts, for the corrections chained behind its pass, out[19] = how many
-   corrections were chained behind passes in flight. */
+   corrections were chained behind passes in flight, out[20] = device ms during which at least one profiled whole pass was
+   running (the union of their intervals: two passes can be in flight; mogp_profile_read's ms is the per-launch sum) since
+   the last profile reset - read it BEFORE mogp_profile_read(reset). */
 int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out);
 
 /* ---- one cluster's GP = one GPobs object ------------------------------------------------- */

@@ -221,13 +221,14 @@ class Engine:
         return dict(launches=n.value, ms=ms.value, alg_bytes=by.value, alg_flops=fl.value)
 
     def chain_counters(self):
-        out = np.zeros(20)
-        self.check(self.lib.mogp_chain_counters(self.h, dptr(out), 20))
+        out = np.zeros(21)
+        self.check(self.lib.mogp_chain_counters(self.h, dptr(out), 21))
         return dict(window_passes=int(out[0]), rescoring_passes=int(out[1]), window_patients=int(out[2]), pairs=out[3],
                     open_s=out[4], rescore_s=out[5], commit_s=out[6], rescoring_launches=int(out[7]), rescoring_ms=out[8],
                     rescoring_bytes=out[9], rescoring_flops=out[10], rank_corrections=int(out[11]), correct_s=out[12], replayed=int(out[13]),
                     max_correction_err=out[14], corrections_checked=int(out[15]), window_pairs=int(out[16]),
-                    pruned_pairs=int(out[17]), chained_wait_s=out[18], chained_corrections=int(out[19]))
+                    pruned_pairs=int(out[17]), chained_wait_s=out[18], chained_corrections=int(out[19]),
+                    passes_union_ms=out[20])
 
     def timer_start(self):
         self.check(self.lib.mogp_timer_start(self.h))

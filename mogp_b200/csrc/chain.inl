@@ -13,9 +13,13 @@ int env_int_once(const char* name, int dflt) {
 // rows a join adds) back, k_T_leave applies a deletion's row operations - instead of being recomputed by an O(m^2) product
 // against the updated factor.  Readers and writers of the columns of one (batch, slot) run on several streams; each waits
 // for the event of the one before it (t_wait) and leaves its own (t_mark).
-bool tmaint_on() {  // (read per call: tests toggle it)
+// Default: on for an engine that has the GPU to itself.  An engine in blocking-sync mode is one of many chains sharing a GPU
+// (bench.py's 64-chain leg, 8 host threads per process): the other chains already fill the SMs while this one waits, its
+// clusters are small (a re-scoring pass is cheap) and the extra streams and kernels cost more than they save - measured
+// 5.2 chain-sweeps/s with columns kept current and two passes in flight, 8.1 without.
+bool tmaint_on(const mogp_engine* h) {  // (read per call: tests toggle it)
   const char* e = getenv("MOGP_TMAINT");
-  return !(e && e[0] == '0');
+  return e ? e[0] != '0' : !h->blocking_sync;
 }
 int t_wait(mogp_engine* h, cudaStream_t s, int bi, int32_t slot) {
   const std::vector<int>& v = h->chain.win.slot_tev[bi];
@@ -91,7 +95,9 @@ int pool_get(mogp_engine* h, int64_t cap, double** out) {
 }
 void pool_put(mogp_engine* h, int64_t cap, double* buf) {
   if (!buf) return;
-  if (h->chain.win.open && h->pass_launched > h->pass_absorbed) {  // a pass in flight may be reading it (see HeldBuf)
+  // a pass in flight may be reading it (see HeldBuf); without chained corrections what a pass computes for a cluster that
+  // changed meanwhile is discarded, and the buffer can go round at once (stream order covers everything that is used)
+  if (h->chain.win.open && h->pass_launched > h->pass_absorbed && tmaint_on(h)) {
     h->held.push_back({cap, buf, h->pass_launched});
     return;
   }
@@ -743,11 +749,10 @@ int window_cols(const Chain& ch) {
   int v = env >= 0 ? env : (ch.cfg.lookahead == 0 ? 64 : ch.cfg.lookahead);
   return v <= 0 ? 0 : std::min(v, 64);
 }
-bool tmaint_on();
-int pipeline_depth() {  // 1: one batch at a time; 2: the next batch's pass overlaps the current batch's moves; 3: the next two
+int pipeline_depth(const mogp_engine* h) {  // 1: one batch at a time; 2: the next batch's pass overlaps the current batch's moves; 3: the next two
   // (a pass launched two batches ahead is stale under every cluster that changes meanwhile: worth it only when those are
   // brought up to date by the corrections chained behind it, MOGP_TMAINT)
-  const int env = env_int("MOGP_PIPELINE", tmaint_on() ? 3 : 2);
+  const int env = env_int("MOGP_PIPELINE", tmaint_on(h) ? 3 : 2);
   return std::max(1, std::min(env, NTGT));
 }
 
@@ -885,7 +890,7 @@ int win_prepare(mogp_engine* h, int64_t n_steps, const int64_t* order, const dou
         h->rpw_share = h->rpw_elems / NBUF;
       }
     }
-    if (tmaint_on()) {  // private copies of the deletions' operands for k_T_leave (fire_leave_hook)
+    if (tmaint_on(h)) {  // private copies of the deletions' operands for k_T_leave (fire_leave_hook)
       const int64_t nT = maxcap / TB + 2, rows = nT * TB;
       const int64_t per = rows * NP * 2 + rows + nT * NG + NG + 8 + NP + nT * TB * TB;
       if (per > h->tsw_slot) {
@@ -1024,7 +1029,7 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   CK(h, cudaEventRecord(h->ev_fork, h->main_stream));
   CK(h, cudaStreamWaitEvent(h->ahead, h->ev_fork, 0));
   CK(h, cudaStreamWaitEvent(h->ahead2, h->ev_fork, 0));
-  if (tmaint_on()) {
+  if (tmaint_on(h)) {
     // This pass overwrites columns that maintenance kernels worked on when the buffer last held a batch, and that the
     // corrections chained behind later passes read (the joiner's T): behind the correction streams of every buffer whose
     // pass is not in flight (those of the passes in flight wait for passes this one is queued behind anyway) ...
@@ -1057,7 +1062,7 @@ int batch_launch(mogp_engine* h, int bi, int64_t s0, int64_t cnt) {
   CK(h, cudaEventRecord(h->ev_ahead2, h->ahead2));
   h->stream = h->ahead;
   b.pl = ScorePlan();
-  bf.res.zigzag = pipeline_depth() >= 2 ? env_int("MOGP_ZIGZAG", 0) : 0;
+  bf.res.zigzag = pipeline_depth(h) >= 2 ? env_int("MOGP_ZIGZAG", 0) : 0;
   // the monotonicity rule applied on the device before the O(m^2) product (MOGP_PRUNE=0: after it, on the host only)
   PruneSpec prune{h->d_wq + 2 * Rtot + w.n + s0, ch.cfg.threshold};
   const bool do_prune = ch.cfg.use_threshold && env_int("MOGP_PRUNE", 1) != 0;
@@ -1452,7 +1457,7 @@ int win_step(mogp_engine* h, double a_draw, double u, int32_t* chosen_out, Score
   // (re-scoring against the updated factor).
   const int64_t npos = w.batch_end - (w.cur + 1);
   const bool alg_on = !stays && npos >= 0 && npos <= OWN_BATCH && ch.pending_lazy && env_int("MOGP_RANK_RESCORE", 1) != 0;
-  const bool tm = tmaint_on();
+  const bool tm = tmaint_on(h);
   const bool log_on = alg_on && tm && !w.flight.empty();  // passes of later batches are in flight
   const int thr_cfg = ch.cfg.use_threshold ? ch.cfg.thr_index : -1;
   auto alg_ok = [&](int32_t slot) {
@@ -1693,7 +1698,7 @@ int sweep_pipelined(mogp_engine* h, int64_t n_steps, const int64_t* order, const
   Chain& ch = h->chain;
   Chain::Window& w = ch.win;
   TRY(win_prepare(h, n_steps, order, a_draw));
-  const int depth = pipeline_depth();
+  const int depth = pipeline_depth(h);
   int64_t pos = 0;          // position being processed
   int64_t launch_pos = 0;   // first position without a pass
   int64_t jl = 0;           // passes launched so far: pass j lives in buffer j % NBUF
@@ -1775,7 +1780,7 @@ int sweep_pipelined(mogp_engine* h, int64_t n_steps, const int64_t* order, const
       if (chosen_ids) chosen_ids[pos + q] = chosen;
       *mm = std::min(*mm, ch.last_margin);
     }
-    if (tmaint_on()) {
+    if (tmaint_on(h)) {
       if (!h->ev_ts_end[bi]) CK(h, cudaEventCreateWithFlags(&h->ev_ts_end[bi], cudaEventDisableTiming));
       CK(h, cudaEventRecord(h->ev_ts_end[bi], h->ts0));
     }

@@ -63,7 +63,7 @@ struct LeaveHook {
   bool fired[NTGT] = {false, false, false};
 };
 constexpr int TS_RING = 64;   // private copies of a deletion's operands for k_T_leave (three batches of moves in flight)
-constexpr int TEV_RING = 256; // events ordering the readers / writers of the cached columns of one (batch, slot)
+constexpr int TEV_RING = 1024; // events ordering the readers / writers of the cached columns of one (batch, slot)
 namespace {
 
 thread_local std::string g_create_error;
@@ -381,6 +381,7 @@ struct mogp_engine {
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop), recycled
   size_t prof_used = 0;
+  double prof_union_ms = 0.0;  // union of the profiled whole passes' (start, stop) intervals
   // class 0: whole passes (a batch or a patient against every active cluster, batch prediction); class 1: the
   // re-scoring passes of the look-ahead pipeline (one or two clusters, latency bound) - kept apart in the accounts
   std::vector<char> prof_tag;
@@ -822,11 +823,31 @@ void priors_of(const mogp_model_spec& s, Gamma pr[4], bool fixed[4]) {
 // Profiling of the dominant kernel (k_score_gemm): CUDA events on the launching stream around every launch.
 void prof_drain(mogp_engine* h) {
   if (h->prof_used == 0) return;
-  cudaEventSynchronize(h->prof_ev[h->prof_used - 1]);
+  for (size_t i = 1; i < h->prof_used; i += 2) cudaEventSynchronize(h->prof_ev[i]);  // (several streams: every stop event)
+  // Two passes of the look-ahead pipeline can be in flight, the later one queued on the SMs behind the earlier one: the
+  // time between a launch's start and stop events then includes its wait.  Besides the per-launch sum, keep the UNION of the
+  // whole passes' intervals - the time during which the GPU was working on at least one of them.
+  std::vector<std::pair<float, float>> iv;
   for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) h->prof_ms_c[(int)h->prof_tag[i]] += ms;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) != cudaSuccess) continue;
+    h->prof_ms_c[(int)h->prof_tag[i]] += ms;
+    if (h->prof_tag[i] != 0) continue;
+    float t0 = 0.f;
+    if (cudaEventElapsedTime(&t0, h->prof_ev[0], h->prof_ev[i]) == cudaSuccess) iv.emplace_back(t0, t0 + ms);
   }
+  std::sort(iv.begin(), iv.end());
+  float lo = 0.f, hi = -1.f;
+  for (const auto& q : iv) {
+    if (hi < lo || q.first > hi) {
+      if (hi >= lo) h->prof_union_ms += hi - lo;
+      lo = q.first;
+      hi = q.second;
+    } else {
+      hi = std::max(hi, q.second);
+    }
+  }
+  if (hi >= lo) h->prof_union_ms += hi - lo;
   h->prof_used = 0;
 }
 void prof_mark(mogp_engine* h, bool stop) {
@@ -1620,6 +1641,7 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
       h->prof_ms_c[c] = h->prof_bytes_c[c] = h->prof_flops_c[c] = 0.0;
     }
     h->prof_pairs = 0.0;
+    h->prof_union_ms = 0.0;
   }
   return MOGP_OK;
 }
@@ -1627,13 +1649,13 @@ int mogp_profile_read(mogp_engine* h, int64_t* launches, double* ms, double* alg
 int mogp_chain_counters(mogp_engine* h, double* out, int32_t n_out) {
   if (!h || !out) return MOGP_EINVAL;
   prof_drain(h);
-  const double v[20] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
+  const double v[21] = {(double)h->chain.win_passes, (double)h->chain.win_rescores, (double)h->chain.win_patients, h->prof_pairs,
                         h->chain.t_open, h->chain.t_ensure, h->chain.t_commit,
                         (double)h->prof_launches_c[1], h->prof_ms_c[1], h->prof_bytes_c[1], h->prof_flops_c[1],
                         (double)h->chain.win_algebra, h->chain.t_alg, (double)h->chain.win_replayed,
                         h->chain.max_corr_err, (double)h->chain.corr_checked, (double)h->chain.win_pairs,
-                        (double)h->chain.win_pruned, h->chain.t_chain, (double)h->chain.win_chained};
-  for (int i = 0; i < n_out && i < 20; ++i) out[i] = v[i];
+                        (double)h->chain.win_pruned, h->chain.t_chain, (double)h->chain.win_chained, h->prof_union_ms};
+  for (int i = 0; i < n_out && i < 21; ++i) out[i] = v[i];
   return MOGP_OK;
 }
 
