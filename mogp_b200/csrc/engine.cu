@@ -175,13 +175,12 @@ struct Chain {
     std::vector<char> own_ok;
     Batch b[NBUF];
     std::vector<int> flight;       // buffers of the passes launched and not yet absorbed (batches after the current one), oldest first
-    // rank-n corrections of the NEXT batch's positions, queued on the look-ahead stream behind that batch's pass at the
-    // moment a move of the current batch changes a cluster (replay_launch); harvested when that batch is absorbed
+    // rank-n corrections of the positions of a pass in flight, queued behind that pass at the moment a move of the current
+    // batch changes a cluster (replay_launch); harvested when that batch is absorbed
     struct AsyncItem {
       int32_t slot = -1;
       int64_t epoch_before = 0;
       int out_idx = 0;
-      bool dead = false;           // the slot changed a second time: the correction does not describe it any more
     };
     std::vector<AsyncItem> async_items[NBUF];  // per pass in flight
     int64_t rpw_used[NBUF] = {};   // doubles used in that pass's share of the engine's d_rpw

@@ -22,6 +22,7 @@ struct RefitJob {
   int64_t seq = 0;        // launch order (the oldest launch is waited for when nothing has finished)
   int rc = MOGP_OK;
   bool collapsed = false; // the optimiser's evaluations run on the lane's shadow of the cluster (repeated inputs merged)
+  double t_start = 0.0, t_end = 0.0;  // host seconds since the refit began (MOGP_REFIT_TRACE)
 };
 
 // Repeated inputs.  Every patient contributes the same onset anchor (x = 0), so ~1/8 of a cluster's points share one input;
@@ -186,6 +187,9 @@ int mogp_refit_clusters(mogp_engine* h, int32_t n_slots, const int32_t* slots, i
   for (int i = 0; i < n_slots; ++i) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->cl[jobs[a].slot].m > h->cl[jobs[b].slot].m; });
   std::vector<int> lane_job(n_lanes, -1);
+  static const bool trace = getenv("MOGP_REFIT_TRACE") && getenv("MOGP_REFIT_TRACE")[0] == '1';
+  const auto t_zero = std::chrono::steady_clock::now();
+  auto now_s = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_zero).count(); };
   int next = 0, done = 0, rc_all = MOGP_OK;
   int64_t seq = 0;
   auto start_job = [&](int lane) -> int {
@@ -207,6 +211,7 @@ int mogp_refit_clusters(mogp_engine* h, int32_t n_slots, const int32_t* slots, i
       j.opt.init(j.nfree, t0);
       j.opt.step();  // -> T_FG at t0
       j.lane = lane;
+      j.t_start = now_s();
       {
         int rcs = refit_make_shadow(h->lanes[lane], c, &j.collapsed);
         if (rcs != MOGP_OK) {
@@ -245,6 +250,7 @@ int mogp_refit_clusters(mogp_engine* h, int32_t n_slots, const int32_t* slots, i
       rc_all = refit_advance(h, j, &seq);
       if (rc_all == MOGP_OK && j.phase == 2) {
         ++done;
+        j.t_end = now_s();
         rc_all = start_job(l);
       }
     }
@@ -260,6 +266,12 @@ int mogp_refit_clusters(mogp_engine* h, int32_t n_slots, const int32_t* slots, i
     h->bytes_h2d += h->lanes[l]->bytes_h2d;
     h->bytes_d2h += h->lanes[l]->bytes_d2h;
     h->lanes[l]->bytes_h2d = h->lanes[l]->bytes_d2h = 0;
+  }
+  if (trace) {  // one line per cluster: size, evaluations, when its chain of evaluations started and ended
+    fprintf(stderr, "refit trace: %d clusters, %d lanes, %.1f ms\n", (int)n_slots, n_lanes, now_s() * 1e3);
+    for (int i : order)
+      fprintf(stderr, "  m %5lld evals %3d  %7.1f .. %7.1f ms%s\n", (long long)h->cl[jobs[i].slot].m, jobs[i].evals,
+              jobs[i].t_start * 1e3, jobs[i].t_end * 1e3, jobs[i].collapsed ? "  (merged)" : "");
   }
   if (n_evals_out)
     for (int i = 0; i < n_slots; ++i) n_evals_out[i] = jobs[i].evals;

@@ -1,3 +1,4 @@
+# (historical: MOGP_LAUNCH_AFTER / MOGP_REPLAY were removed when the cached columns became maintained)
 run() { name=$1; shift; env "$@" python bench.py --steps 5 --warmup 5 --no-secondary --no-cpu-baseline > gpurun_out/r2_exp_$name.json 2> gpurun_out/r2_exp_$name.err; }
 run la40 MOGP_LOOKAHEAD=40
 run la56 MOGP_LOOKAHEAD=56
