@@ -26,6 +26,7 @@
 #include "score.cuh"
 #include "update.cuh"
 #include "kmeans.cuh"
+#include "wspace.cuh"
 
 using namespace mogp;
 
@@ -355,6 +356,10 @@ struct mogp_engine {
   bool light = false;
   double* d_wt = nullptr;  // a lane's copy of the multiplicities of the collapsed cluster it is evaluating
   int64_t wt_elems = 0;
+  double* d_ws = nullptr;   // a lane's weight-space workspace (wspace.cuh: WsWork) ...
+  int64_t ws_elems = 0;
+  double* d_wsC = nullptr;  // ... and the Lagrange basis values of the cluster's inputs [m][WS_R]
+  int64_t wsC_elems = 0;
   std::vector<mogp_engine*> lanes;
   std::vector<cudaEvent_t> lane_ev;
   int64_t refit_evals = 0, refit_launched = 0;   // objective evaluations requested / actually run on the device
@@ -1405,6 +1410,8 @@ void mogp_engine_destroy(mogp_engine* h) {
   }
   cudaFree(h->d_adraw);
   cudaFree(h->d_wt);
+  cudaFree(h->d_ws);
+  cudaFree(h->d_wsC);
   cudaFree(h->d_upd2);
   cudaFree(h->d_own1);
   cudaFree(h->d_own2);

@@ -23,7 +23,57 @@ struct RefitJob {
   int rc = MOGP_OK;
   bool collapsed = false; // the optimiser's evaluations run on the lane's shadow of the cluster (repeated inputs merged)
   double t_start = 0.0, t_end = 0.0;  // host seconds since the refit began (MOGP_REFIT_TRACE)
+  bool ws = false;        // the optimiser's evaluations run in weight space (wspace.cuh) on the lane ...
+  double span = 0.0;      // ... while (hi - lo) / lengthscale <= WS_MAX_SPAN (hi - lo = this); else on the cluster itself
+  int target = 0;         // what the evaluation in flight runs on: 0 the lane's shadow (merged inputs), 1 the cluster, 2 weight space
+  int ws_evals = 0;
 };
+
+// Weight-space evaluations (wspace.cuh): eligible clusters (RBF kernel, m >= 4 r) get the theta-independent part - the
+// Lagrange basis values of their inputs, S = C^T C, C^T y, C^T x and three scalar sums - once per refit on the lane's stream;
+// the lane's cluster 0 serves as the holder of theta / priors for objective_begin / objective_end.
+static bool ws_enabled() {  // on by default; MOGP_WS_REFIT=0: every evaluation the dense way (read per call: tests toggle it)
+  const char* e = getenv("MOGP_WS_REFIT");
+  return e ? e[0] != '0' : true;
+}
+static int ws_setup(mogp_engine* lane, const Cluster& c, bool* made, double* span) {
+  *made = false;
+  if (!ws_enabled() || c.spec.kernel != MOGP_KERNEL_RBF || c.m < 4 * WS_R || (int64_t)c.hx.size() != c.m || !c.M) return MOGP_OK;
+  mogp_engine* h = lane;
+  double lo = c.hx[0], hi = c.hx[0];
+  for (double v : c.hx) {
+    lo = std::min(lo, v);
+    hi = std::max(hi, v);
+  }
+  if (!(hi > lo)) return MOGP_OK;
+  if (lane->cl.empty()) {
+    int32_t slot = -1;
+    TRY(cluster_create_i(lane, &c.spec, c.theta, &slot));
+  }
+  Cluster& sh = lane->cl[0];
+  sh.spec = c.spec;
+  memcpy(sh.theta, c.theta, sizeof(double) * 4);
+  sh.theta_dirty = true;
+  sh.m = c.m;
+  sh.valid = sh.grad_valid = false;
+  sh.stat_on_device = false;
+  sh.wt = nullptr;
+  sh.corr_n1 = sh.corr_logn = sh.corr_ss = 0.0;
+  TRY(ensure(lane, &lane->d_ws, &lane->ws_elems, WS_WORK_ELEMS));
+  TRY(ensure(lane, &lane->d_wsC, &lane->wsC_elems, c.m * (int64_t)WS_R));
+  TRY(ensure_pin(lane, 256));
+  WsNodes nd;
+  ws_make_nodes(lo, hi, &nd);
+  WsWork w{lane->d_ws};
+  k_ws_basis<<<(unsigned)((c.m + 127) / 128), 128, 0, lane->stream>>>(nd, c.x(), (int)c.m, lane->d_wsC, w);
+  LAUNCHED(lane);
+  k_ws_gram<<<(WS_GRAM_ENTRIES + 127) / 128, 128, 0, lane->stream>>>(lane->d_wsC, c.x(), c.y(), (int)c.m, w);
+  LAUNCHED(lane);
+  CK(h, cudaGetLastError());
+  *made = true;
+  *span = hi - lo;
+  return MOGP_OK;
+}
 
 // Repeated inputs.  Every patient contributes the same onset anchor (x = 0), so ~1/8 of a cluster's points share one input;
 // n observations at the same input are ONE observation of their mean with noise s / n, times a factor that does not involve
@@ -105,15 +155,42 @@ static int refit_advance(mogp_engine* h, RefitJob& j, int64_t* seq) {
   mogp_engine* lane = h->lanes[j.lane];
   for (;;) {
     if (j.phase == 2) return MOGP_OK;
-    // the optimiser's evaluations on the lane's collapsed shadow, the closing f(x_opt) on the cluster itself
-    Cluster& c = (j.collapsed && j.phase == 0) ? lane->cl[0] : h->cl[j.slot];
+    // the optimiser's evaluations in weight space or on the lane's collapsed shadow, the closing f(x_opt) on the cluster itself
+    if (!j.launched) {
+      j.target = j.phase != 0 ? 1 : j.ws ? 2 : j.collapsed ? 0 : 1;
+      if (j.target == 2) {  // a length scale too short for the r nodes: this point the dense way, on the cluster
+        Gamma pr[4];
+        bool fixed[4];
+        priors_of(h->cl[j.slot].spec, pr, fixed);
+        int q = 0;
+        double ls = h->cl[j.slot].theta[2];
+        for (int i = 0; i < 4; ++i)
+          if (!fixed[i]) {
+            if (i == 2) ls = logexp_f(j.opt.x[q]);
+            ++q;
+          }
+        if (!(j.span <= WS_MAX_SPAN * ls)) j.target = 1;
+      }
+    }
+    Cluster& c = j.target == 1 ? h->cl[j.slot] : lane->cl[0];
     double f = 0.0, g[4] = {0, 0, 0, 0};
     int rc;
     if (!j.launched) {  // queue the evaluation at the optimiser's current point
       bool launched = false;
-      rc = objective_begin(lane, c, j.opt.x, j.nfree, true, &launched);
+      rc = objective_begin(lane, c, j.opt.x, j.nfree, j.target != 2, &launched);
       j.evals += 1;
       h->refit_evals += 1;
+      if (rc == MOGP_OK && j.target == 2 && !c.valid) {  // (valid: the point of the last evaluation again - cached)
+        WsTheta th{c.theta[0], c.theta[1], c.theta[2], c.theta[3], c.spec.mean_func ? 1 : 0};
+        WsWork w{lane->d_ws};
+        k_ws_eval<<<1, 256, 0, lane->stream>>>(w, th);
+        lane->launches += 1;
+        if (cudaMemcpyAsync(lane->pin, w.out(), sizeof(double) * 8, cudaMemcpyDeviceToHost, lane->stream) != cudaSuccess)
+          FAIL(h, MOGP_ECUDA, "refit: read-back of a weight-space evaluation");
+        lane->bytes_d2h += 64;
+        launched = true;
+        j.ws_evals += 1;
+      }
       if (rc == MOGP_OK && launched) {
         if (cudaEventRecord(h->lane_ev[j.lane], lane->stream) != cudaSuccess) FAIL(h, MOGP_ECUDA, "refit: event record");
         j.launched = true;
@@ -122,6 +199,21 @@ static int refit_advance(mogp_engine* h, RefitJob& j, int64_t* seq) {
         return MOGP_OK;
       }
       if (rc == MOGP_OK) rc = objective_end(lane, c, false, &f, g);  // cached (same theta) or eager
+    } else if (j.target == 2) {  // a weight-space evaluation has arrived
+      j.launched = false;
+      const double* o = reinterpret_cast<const double*>(lane->pin);
+      if (o[5] != 0.0 || !isfinite(o[0])) {
+        c.valid = c.grad_valid = false;
+        lane->err = "not positive definite (weight-space evaluation)";
+        rc = MOGP_ENOTPD;
+      } else {
+        c.lml = o[0];
+        memcpy(c.grad, o + 1, sizeof(double) * 4);
+        c.valid = c.grad_valid = true;
+        c.stat_on_device = false;
+        c.z_dirty = c.lml_dirty = false;
+        rc = objective_end(lane, c, false, &f, g);
+      }
     } else {  // the caller has seen the lane's event complete
       j.launched = false;
       lane->up_off = 0;  // the lane's stream is idle: its upload staging can be reused from the start
@@ -213,7 +305,8 @@ int mogp_refit_clusters(mogp_engine* h, int32_t n_slots, const int32_t* slots, i
       j.lane = lane;
       j.t_start = now_s();
       {
-        int rcs = refit_make_shadow(h->lanes[lane], c, &j.collapsed);
+        int rcs = ws_setup(h->lanes[lane], c, &j.ws, &j.span);
+        if (rcs == MOGP_OK && !j.ws) rcs = refit_make_shadow(h->lanes[lane], c, &j.collapsed);
         if (rcs != MOGP_OK) {
           h->err = h->lanes[lane]->err;
           return rcs;
@@ -271,7 +364,8 @@ int mogp_refit_clusters(mogp_engine* h, int32_t n_slots, const int32_t* slots, i
     fprintf(stderr, "refit trace: %d clusters, %d lanes, %.1f ms\n", (int)n_slots, n_lanes, now_s() * 1e3);
     for (int i : order)
       fprintf(stderr, "  m %5lld evals %3d  %7.1f .. %7.1f ms%s\n", (long long)h->cl[jobs[i].slot].m, jobs[i].evals,
-              jobs[i].t_start * 1e3, jobs[i].t_end * 1e3, jobs[i].collapsed ? "  (merged)" : "");
+              jobs[i].t_start * 1e3, jobs[i].t_end * 1e3,
+              jobs[i].ws ? "  (weight space)" : jobs[i].collapsed ? "  (merged)" : "");
   }
   if (n_evals_out)
     for (int i = 0; i < n_slots; ++i) n_evals_out[i] = jobs[i].evals;

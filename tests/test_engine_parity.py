@@ -212,11 +212,13 @@ def test_refit_reaches_the_oracle_optimum(eng):
                                   ('rbf', False, False, False, (0.0, 0.8, 2.0, 0.1), 520),
                                   ('linear', True, True, False, (0.4, 1.0, 1.0, 0.5), 260)],
                          ids=lambda c: "{}-mf{}-m{}".format(c[0], int(c[1]), c[5]))
-def test_refit_with_repeated_inputs_collapsed(eng, case):
+def test_refit_with_repeated_inputs_collapsed(eng, case, monkeypatch):
     """Clusters of >= 128 points with > 5 % repeated inputs (every patient's onset anchor): the native refit evaluates
     the optimiser's points on a collapsed shadow (refit.inl: one weighted observation per distinct input + a closed-form
     factor) and the closing f(x_opt) on the cluster itself.  Same optimum, same objective, same number of evaluations
-    as the oracle's SciPy L-BFGS-B on the full data; the cluster is left with a valid factor at the optimum."""
+    as the oracle's SciPy L-BFGS-B on the full data; the cluster is left with a valid factor at the optimum.
+    (MOGP_WS_REFIT=0: RBF clusters would otherwise be evaluated in weight space, test_refit_in_weight_space.)"""
+    monkeypatch.setenv("MOGP_WS_REFIT", "0")
     o, slot, spec, rs = build_pair(eng, case, seed=11)
     n0 = o.n_evals
     o.optimize()
@@ -228,6 +230,34 @@ def test_refit_with_repeated_inputs_collapsed(eng, case):
     assert np.allclose(th[(0 if case[1] else 1):], o.param_array, rtol=2e-6)   # (no slope parameter without the mean function)
     assert rel(eng.cluster_loglik(slot), o.log_likelihood()) < 1e-9
     assert int(evals[0]) == o.n_evals - n0          # the optimiser's evaluations + the closing f(x_opt)
+    xs = rs.uniform(0, 8, 5)
+    mu, var = eng.cluster_predict(slot, xs)
+    mo, vo = o.predict(xs.reshape(-1, 1))
+    assert rel(mu, mo.ravel()) < 1e-7 and rel(var, vo.ravel()) < 1e-7
+    eng.cluster_free(slot)
+
+
+@pytest.mark.parametrize("case", [('rbf', True, True, False, (0.3, 1.0, 3.0, 0.3), 300),
+                                  ('rbf', False, False, False, (0.0, 0.8, 2.0, 0.1), 520),
+                                  ('rbf', True, True, False, (0.28, 1.0, 1.58, 0.0133), 1100)],
+                         ids=lambda c: "{}-mf{}-m{}".format(c[0], int(c[1]), c[5]))
+def test_refit_in_weight_space(eng, case, monkeypatch):
+    """MOGP_WS_REFIT=1: the optimiser's evaluations of an RBF cluster run in weight space (wspace.cuh: the kernel
+    interpolated at 48 Chebyshev nodes, O(r^3) per evaluation whatever m; the closing f(x_opt) on the cluster itself).  Same
+    optimum, same objective, same number of evaluations as the oracle's SciPy L-BFGS-B on the dense GP, and the cluster is
+    left with a valid dense factor at the optimum."""
+    monkeypatch.setenv("MOGP_WS_REFIT", "1")
+    o, slot, spec, rs = build_pair(eng, case, seed=13)
+    n0 = o.n_evals
+    o.optimize()
+    c0 = eng.refit_counters()
+    evals = eng.refit_clusters([slot])
+    c1 = eng.refit_counters()
+    assert c1["launched"] > c0["launched"]
+    th = eng.cluster_get_theta(slot)
+    assert np.allclose(th[(0 if case[1] else 1):], o.param_array, rtol=2e-6)
+    assert rel(eng.cluster_loglik(slot), o.log_likelihood()) < 1e-9
+    assert abs(int(evals[0]) - (o.n_evals - n0)) <= 1
     xs = rs.uniform(0, 8, 5)
     mu, var = eng.cluster_predict(slot, xs)
     mo, vo = o.predict(xs.reshape(-1, 1))
