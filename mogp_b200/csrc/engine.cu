@@ -378,8 +378,9 @@ struct mogp_engine {
   // L-BFGS-B evaluation of the same cluster; keyed by the buffers it touches
   cudaGraph_t eval_graph = nullptr;
   cudaGraphExec_t eval_exec = nullptr;
-  const void* eval_key[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const void* eval_key[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int64_t eval_kernels = 0;
+  bool eval_with_grad = true;  // the graph launched last includes the gradient kernels
   // accounting (bench.py): bytes moved by the C ABI calls, and device time of the scoring GEMM
   int64_t bytes_h2d = 0, bytes_d2h = 0;
   bool prof_on = false;
@@ -1852,7 +1853,9 @@ bool graphs_enabled() {
 // evaluations of many clusters in flight (refit driver below): eval_launch queues the work on h->stream without
 // waiting, eval_collect reads the results once the stream has been waited for.  *ok = false when the factorisation
 // failed: the caller falls back to the eager path with GPy's jitter ladder.
-static int eval_launch(mogp_engine* h, Cluster& c, bool* launched) {
+// with_grad = false: factor, alpha, LML only - the closing f(x_opt) of a refit needs the factor and the objective, not the
+// gradient (a third of the evaluation's flops)
+static int eval_launch(mogp_engine* h, Cluster& c, bool* launched, bool with_grad = true) {
   *launched = false;
   const int64_t mpad = round_up(c.m, TB);
   const int nb = (int)(mpad / TB);
@@ -1866,7 +1869,8 @@ static int eval_launch(mogp_engine* h, Cluster& c, bool* launched) {
   TRY(ensure_pin(h, 256));
   TRY(sync_theta(h, c));
   double* st = c.stat();
-  const void* key[7] = {c.M, c.vec, h->d_L, h->d_apart, h->d_partial, reinterpret_cast<const void*>((intptr_t)c.m), c.wt};
+  const void* key[8] = {c.M, c.vec, h->d_L, h->d_apart, h->d_partial, reinterpret_cast<const void*>((intptr_t)c.m), c.wt,
+                        reinterpret_cast<const void*>((intptr_t)(with_grad ? 1 : 0))};
   if (!h->eval_exec || memcmp(key, h->eval_key, sizeof key) != 0) {
     if (h->eval_graph) cudaGraphDestroy(h->eval_graph);
     h->eval_graph = nullptr;
@@ -1881,10 +1885,12 @@ static int eval_launch(mogp_engine* h, Cluster& c, bool* launched) {
     k_z<<<(unsigned)((c.m + 7) / 8), NTHREADS, 0, h->stream>>>(c.M, ld, c.x(), c.y(), (int)c.m, th, c.z());
     LAUNCHED(h);
     int rc = launch_alpha_lml(h, c);
-    k_grad<<<dim3(nb, nb, nz), NTHREADS, GRAD_SMEM, h->stream>>>(c.M, c.cap, nb, c.x(), c.alpha(), (int)c.m, th, h->d_partial, grad_kc(), c.wt);
-    LAUNCHED(h);
-    k_grad_final<<<1, 256, 0, h->stream>>>(h->d_partial, (int)n_partial, th, st, st + 10);
-    LAUNCHED(h);
+    if (with_grad) {
+      k_grad<<<dim3(nb, nb, nz), NTHREADS, GRAD_SMEM, h->stream>>>(c.M, c.cap, nb, c.x(), c.alpha(), (int)c.m, th, h->d_partial, grad_kc(), c.wt);
+      LAUNCHED(h);
+      k_grad_final<<<1, 256, 0, h->stream>>>(h->d_partial, (int)n_partial, th, st, st + 10);
+      LAUNCHED(h);
+    }
     cudaMemcpyAsync(h->pin, st, sizeof(double) * 14, cudaMemcpyDeviceToHost, h->stream);
     cudaError_t ce = cudaStreamEndCapture(h->stream, &h->eval_graph);
     h->eval_kernels = h->launches - launches0;
@@ -1917,6 +1923,7 @@ static int eval_launch(mogp_engine* h, Cluster& c, bool* launched) {
     memcpy(h->eval_key, key, sizeof key);
   }
   CK(h, cudaGraphLaunch(h->eval_exec, h->stream));
+  h->eval_with_grad = with_grad;
   *launched = true;
   return MOGP_OK;
 }
@@ -1932,8 +1939,9 @@ static int eval_collect(mogp_engine* h, Cluster& c, bool* ok) {
   c.lml = hs[0];
   c.quad = hs[1];
   c.logdet = hs[2];
-  memcpy(c.grad, hs + 10, sizeof(double) * 4);
-  c.valid = c.grad_valid = true;
+  if (h->eval_with_grad) memcpy(c.grad, hs + 10, sizeof(double) * 4);
+  c.valid = true;
+  c.grad_valid = h->eval_with_grad;
   c.stat_on_device = false;
   c.z_dirty = false;
   c.lml_dirty = false;
@@ -1945,7 +1953,8 @@ static int eval_collect(mogp_engine* h, Cluster& c, bool* ok) {
 // objective_begin maps the optimiser coordinates to theta and, when a full evaluation is needed, queues it on
 // hw->stream without waiting (*launched); objective_end - after that stream has been waited for - finishes:
 // eager fallback with the jitter ladder if the queued factorisation failed, priors, Jacobian, chain rule.
-static int objective_begin(mogp_engine* hw, Cluster& c, const double* t, int32_t n_t, bool want_grad, bool* launched) {
+static int objective_begin(mogp_engine* hw, Cluster& c, const double* t, int32_t n_t, bool want_grad, bool* launched,
+                           bool grad_in_graph = true) {
   mogp_engine* h = hw;
   *launched = false;
   Gamma pr[4];
@@ -1971,7 +1980,7 @@ static int objective_begin(mogp_engine* hw, Cluster& c, const double* t, int32_t
       c.valid = c.grad_valid = false;
     }
   }
-  if (want_grad && !c.valid && c.m > 0 && graphs_enabled()) TRY(eval_launch(h, c, launched));
+  if (want_grad && !c.valid && c.m > 0 && graphs_enabled()) TRY(eval_launch(h, c, launched, grad_in_graph));
   return MOGP_OK;
 }
 

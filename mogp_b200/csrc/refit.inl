@@ -177,7 +177,8 @@ static int refit_advance(mogp_engine* h, RefitJob& j, int64_t* seq) {
     int rc;
     if (!j.launched) {  // queue the evaluation at the optimiser's current point
       bool launched = false;
-      rc = objective_begin(lane, c, j.opt.x, j.nfree, j.target != 2, &launched);
+      // (the closing f(x_opt) needs the factor and the objective only: its graph leaves the gradient kernels out)
+      rc = objective_begin(lane, c, j.opt.x, j.nfree, j.target != 2, &launched, j.phase == 0);
       j.evals += 1;
       h->refit_evals += 1;
       if (rc == MOGP_OK && j.target == 2 && !c.valid) {  // (valid: the point of the last evaluation again - cached)
@@ -198,7 +199,7 @@ static int refit_advance(mogp_engine* h, RefitJob& j, int64_t* seq) {
         h->refit_launched += 1;
         return MOGP_OK;
       }
-      if (rc == MOGP_OK) rc = objective_end(lane, c, false, &f, g);  // cached (same theta) or eager
+      if (rc == MOGP_OK) rc = objective_end(lane, c, false, &f, j.phase == 0 ? g : nullptr);  // cached (same theta) or eager
     } else if (j.target == 2) {  // a weight-space evaluation has arrived
       j.launched = false;
       const double* o = reinterpret_cast<const double*>(lane->pin);
@@ -217,7 +218,7 @@ static int refit_advance(mogp_engine* h, RefitJob& j, int64_t* seq) {
     } else {  // the caller has seen the lane's event complete
       j.launched = false;
       lane->up_off = 0;  // the lane's stream is idle: its upload staging can be reused from the start
-      rc = objective_end(lane, c, true, &f, g);
+      rc = objective_end(lane, c, true, &f, j.phase == 0 ? g : nullptr);
     }
     if (rc == MOGP_ENOTPD) {
       // paramz Model._objective_grads: a failed evaluation returns a huge objective and the clipped last gradient,
